@@ -1,0 +1,280 @@
+/*
+ * nmb200.h -- C ABI of libnmb200.so: the B200 (sm_100a) kernels behind the
+ * Neural Monkey encoder-decoder hot path.
+ *
+ * The reference (ufal/neuralmonkey @ 8b14652) has no FFI boundary: its hot
+ * path is a TensorFlow-1.12 graph evaluated by `sess.run`
+ * (neuralmonkey/tf_manager.py:179-180).  Every entry point below replaces the
+ * TF op group named in its comment (reference file:line), and is what a
+ * ctypes binding inside the reference's ModelPart classes would call
+ * (see INTEGRATION.md).
+ *
+ * Conventions
+ *   - plain pointers + int64_t sizes; no torch / C++ types cross the ABI;
+ *   - all pointers are DEVICE pointers unless the name ends in `_host`;
+ *   - all tensors are dense row-major fp32 unless stated; ids are int64
+ *     (the dtype `tf.contrib.lookup` tables emit, neuralmonkey/vocabulary.py:187-195),
+ *     lengths/steps are int32, flags are uint8;
+ *   - every function is asynchronous on `stream` (a cudaStream_t passed as
+ *     void*), allocates no persistent device memory and keeps no pointer after
+ *     it returns;
+ *   - return value: 0 = ok, <0 = invalid argument (NM_E_*), >0 = cudaError_t.
+ *     `nm_last_error()` returns a thread-local message.  No exceptions, no exit().
+ */
+#ifndef NMB200_H
+#define NMB200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NM_ABI_VERSION 1
+
+#define NM_OK 0
+#define NM_E_INVALID (-1)      /* bad argument (null pointer, negative size, ...) */
+#define NM_E_UNSUPPORTED (-2)  /* shape / mode outside what the kernel handles    */
+#define NM_E_NO_DEVICE (-3)    /* no sm_100 device visible                        */
+
+/* activation codes for nm_gemm epilogues and nm_act_bwd */
+#define NM_ACT_NONE 0
+#define NM_ACT_TANH 1
+#define NM_ACT_RELU 2
+#define NM_ACT_SIGMOID 3
+
+/* GEMM backends */
+#define NM_GEMM_AUTO 0  /* tcgen05 when the shape is TMA-addressable, else SIMT */
+#define NM_GEMM_SIMT 1  /* fp32 CUDA-core tiles (exact fp32 accumulate)         */
+#define NM_GEMM_TC 2    /* tcgen05 kind::tf32, TMA-staged, TMEM accumulators    */
+
+int nm_version(void);
+const char* nm_last_error(void);
+/* Fills SM count and compute capability of the current device. */
+int nm_device_info(int* sm_count, int* cc_major, int* cc_minor);
+
+/* ---- K1: embedding lookup -------------------------------------------------
+ * Replaces tf.nn.embedding_lookup * mask (neuralmonkey/model/sequence.py:181-191)
+ * and AutoregressiveDecoder.embed_input_symbols (decoders/autoregressive.py:269-272).
+ * out[i,:] = table[ids[i],:] * (mask ? mask[i] : 1).  n = number of ids. */
+int nm_embed_fwd(const int64_t* ids, const float* table, const float* mask,
+                 float* out, int64_t n, int64_t emb, int64_t vocab, void* stream);
+/* dtable[ids[i],:] += dout[i,:] * mask[i]  (dtable is accumulated into). */
+int nm_embed_bwd(const int64_t* ids, const float* dout, const float* mask,
+                 float* dtable, int64_t n, int64_t emb, int64_t vocab, void* stream);
+
+/* ---- dense projections (K2 input projection, K3, K5, K9, a5, a6) ----------
+ * Replaces tf.layers.dense / tf.matmul / the 1x1 tf.nn.conv2d of
+ * attention/feed_forward.py:111-118 and the logits matmul of
+ * decoders/autoregressive.py:450-452.
+ * C[M,N] = act(op(A) . op(B) + bias[N]) + beta * C      (beta in {0,1})
+ * op(A) is [M,K]: A is [M,K] (transA=0, lda>=K) or [K,M] (transA=1, lda>=M);
+ * op(B) is [K,N]: B is [K,N] (transB=0, ldb>=N) or [N,K] (transB=1, ldb>=K).
+ * bias may be NULL.  backend: NM_GEMM_*. */
+int nm_gemm(int transA, int transB, int64_t M, int64_t N, int64_t K,
+            const float* A, int64_t lda, const float* B, int64_t ldb,
+            float* C, int64_t ldc, const float* bias, int act, float beta,
+            int backend, void* stream);
+/* 1 if nm_gemm(AUTO) would take the tcgen05 path for this problem. */
+int nm_gemm_uses_tc(int transA, int transB, int64_t M, int64_t N, int64_t K,
+                    int64_t lda, int64_t ldb, int64_t ldc);
+
+/* dx = dy * act'(y) expressed through the activation OUTPUT y (tanh: 1-y^2,
+ * relu: y>0, sigmoid: y(1-y)); n elements; dx may alias dy. */
+int nm_act_bwd(const float* y, const float* dy, float* dx, int64_t n, int act,
+               void* stream);
+/* out[n] (+)= sum_m x[m,n]  -- bias gradients. accumulate in {0,1}. */
+int nm_colsum(const float* x, int64_t M, int64_t N, int64_t ldx, float* out,
+              int accumulate, void* stream);
+/* maxout of nn/projection.py:7-35: y[m,j] = max(z[m,j], z[m,O+j]); z is [M,2*O].
+ * fwd writes y and the uint8 winner (0: first half, 1: second half). */
+int nm_maxout_fwd(const float* z, float* y, uint8_t* which, int64_t M, int64_t O,
+                  void* stream);
+int nm_maxout_bwd(const float* dy, const uint8_t* which, float* dz, int64_t M,
+                  int64_t O, void* stream);
+
+/* ---- K7: layer normalisation ----------------------------------------------
+ * Replaces tf_utils.layer_norm (neuralmonkey/tf_utils.py:189-219): biased
+ * variance, eps inside the rsqrt, over the last dim.  rstd/mean are saved [M]. */
+int nm_layernorm_fwd(const float* x, const float* gamma, const float* beta,
+                     float* y, float* mean, float* rstd, int64_t M, int64_t D,
+                     float eps, void* stream);
+/* dgamma/dbeta are accumulated into (two call sites share LayerNorm/{gamma,beta}
+ * in RecurrentEncoder: encoders/recurrent.py:215-216). */
+int nm_layernorm_bwd(const float* x, const float* gamma, const float* mean,
+                     const float* rstd, const float* dy, float* dx, float* dgamma,
+                     float* dbeta, int64_t M, int64_t D, void* stream);
+
+/* ---- K2: GRU over a whole sequence ------------------------------------------
+ * Replaces tf.nn.dynamic_rnn / bidirectional_dynamic_rnn over
+ * tf.contrib.rnn.GRUCell (encoders/recurrent.py:71-110, nn/ortho_gru_cell.py:44-53)
+ * and, in teacher-forced training, the GRU part of Decoder.next_state
+ * (decoders/decoder.py:279-289).  TF-1.12 GRUCell semantics:
+ *     [r,u] = sigmoid(xg_t + h.Wgh)          (xg already holds x.Wgx + b_g)
+ *     c     = tanh(xc_t + (r*h).Wch)         (xc already holds x.Wcx + b_c)
+ *     h'    = u*h + (1-u)*c
+ * xproj is [B,T,3H] = [xg(2H) | xc(H)] per step.  lengths (int32 [B], may be
+ * NULL) gives dynamic_rnn masking: for t >= len the output is 0 and the state
+ * is carried.  reverse=1 walks t = len-1 .. 0 (tf.reverse_sequence semantics:
+ * outputs land at their original time index).
+ * Outputs: states [B,T,H]; final [B,H]; and, saved for the backward pass:
+ * gates [B,T,3H] = (r,u,c), hprev [B,T,H] = the state each step consumed,
+ * rh [B,T,H] = r*hprev (the A operand of the candidate matmul). */
+int nm_gru_seq_fwd(const float* xproj, const float* Wgh, const float* Wch,
+                   const float* h0, const int32_t* lengths, int reverse,
+                   float* states, float* final_state, float* gates, float* hprev,
+                   float* rh, int64_t B, int64_t T, int64_t H, void* stream);
+/* Inputs: dstates [B,T,H] (may be NULL), dfinal [B,H] (may be NULL).
+ * Outputs: dxproj [B,T,3H] (pre-activation grads = grads of xproj), dh0 [B,H]
+ * (may be NULL).  Weight grads are NOT produced here: they are the hoisted
+ * GEMMs hprev^T.dxproj[:, :2H] and rh^T.dxproj[:, 2H:], which the host issues
+ * through nm_gemm.  work is a scratch buffer of 2*B*H floats. */
+int nm_gru_seq_bwd(const float* Wgh, const float* Wch, const int32_t* lengths,
+                   int reverse, const float* gates, const float* hprev,
+                   const float* dstates, const float* dfinal, float* dxproj,
+                   float* dh0, float* work, int64_t B, int64_t T, int64_t H,
+                   void* stream);
+
+/* ---- K4: Bahdanau attention -------------------------------------------------
+ * Replaces Attention.attention (attention/feed_forward.py:125-166) for NQ query
+ * steps at once (NQ = Ty in teacher-forced training, 1 in step-wise decoding):
+ *     e[b,q,t] = sum_a v[a]*tanh(keys[b,t,a] + qproj[b,q,a]) + bias
+ *     w        = softmax_t(e) * mask ;  w /= (sum_t w + 1e-8)
+ *     ctx[b,q] = sum_t w[b,q,t] * values[b,t,:]
+ * keys [B,Tx,A] (hidden_features), values [B,Tx,C] (attention_states),
+ * mask [B,Tx] fp32 (may be NULL = no masking: plain softmax),
+ * qproj [B,NQ,A] (= query.W_q + b_p), v [A], bias [1] (device scalar).
+ * Outputs: energies [B,NQ,Tx] (pre-softmax e, saved for backward; may be NULL),
+ * weights [B,NQ,Tx], ctx [B,NQ,C]. */
+int nm_bahdanau_fwd(const float* keys, const float* values, const float* mask,
+                    const float* qproj, const float* v, const float* bias,
+                    float* energies, float* weights, float* ctx, int64_t B,
+                    int64_t Tx, int64_t NQ, int64_t A, int64_t C, void* stream);
+/* Backward.  dkeys [B,Tx,A], dvalues [B,Tx,C], dqproj [B,NQ,A] are overwritten;
+ * dv [A] and dbias [1] are accumulated into.  Gradient reaches the energies of
+ * masked positions too (the softmax runs before the mask), as in the reference.
+ * de_work is scratch of B*NQ*Tx floats. */
+int nm_bahdanau_bwd(const float* keys, const float* values, const float* mask,
+                    const float* qproj, const float* v, const float* energies,
+                    const float* weights, const float* dctx, float* dkeys,
+                    float* dvalues, float* dqproj, float* dv, float* dbias,
+                    float* de_work, int64_t B, int64_t Tx, int64_t NQ, int64_t A,
+                    int64_t C, void* stream);
+
+/* ---- K5/K6: vocabulary projection loss ---------------------------------------
+ * Replaces log_softmax + tf.contrib.seq2seq.sequence_loss
+ * (decoders/autoregressive.py:288-316) and the greedy argmax (:446-480).
+ * logits [M,V] (already includes bias and the -1e9 <unk> mask).
+ * Per row m: lse[m] = logsumexp_v logits; xent[m] = (lse - logits[m,target[m]])
+ * * weight[m]; argmax[m] = first index of the row maximum (tf.argmax order).
+ * targets may be NULL (then xent is not written). */
+int nm_xent_fwd(const float* logits, const int64_t* targets, const float* weights,
+                float* lse, float* xent, int64_t* argmax, int64_t M, int64_t V,
+                int64_t ldl, void* stream);
+/* dlogits[m,v] = (exp(logits[m,v]-lse[m]) - [v==target[m]]) * weights[m] * scale[0]
+ * (scale is a DEVICE scalar: upstream dloss / sum(mask)). May be in place. */
+int nm_xent_bwd(const float* logits, const int64_t* targets, const float* weights,
+                const float* lse, const float* scale, float* dlogits, int64_t M,
+                int64_t V, int64_t ldl, void* stream);
+/* logprobs[m,v] = logits[m,v] - lse[m]  (runtime_logprobs of the runner API). */
+int nm_log_softmax(const float* logits, const float* lse, float* logprobs,
+                   int64_t M, int64_t V, int64_t ldl, void* stream);
+
+/* Fused vocabulary projection + loss statistics (K5 without materialising the
+ * [M,V] logits): logits = X[M,K].W[K,V] + b (+ -1e9 at unk_index if >= 0) on
+ * tcgen05; writes lse, xent, argmax as nm_xent_fwd.  part is scratch of
+ * nm_logits_xent_scratch(M,V) floats (16-byte aligned).  logits_out (may be NULL)
+ * additionally receives the [M,V] logits (runtime_logits of the runner API).
+ * Returns NM_E_UNSUPPORTED when X/W are not TMA-addressable (rows not multiples
+ * of 16 bytes): callers then use nm_gemm + nm_xent_fwd. */
+int64_t nm_logits_xent_scratch(int64_t M, int64_t V);
+int nm_logits_xent_fwd(const float* X, int64_t ldx, const float* W, int64_t ldw,
+                       const float* b, int64_t unk_index, const int64_t* targets,
+                       const float* weights, float* lse, float* xent,
+                       int64_t* argmax, float* part, float* logits_out,
+                       int64_t ldl, int64_t M, int64_t V, int64_t K, void* stream);
+/* Recomputes the logits tile-by-tile and writes
+ * dlogits = (softmax - onehot) * weights[m] * scale[0]   [M,V]. */
+int nm_logits_xent_bwd(const float* X, int64_t ldx, const float* W, int64_t ldw,
+                       const float* b, int64_t unk_index, const int64_t* targets,
+                       const float* weights, const float* lse, const float* scale,
+                       float* dlogits, int64_t ldd, int64_t M, int64_t V,
+                       int64_t K, void* stream);
+
+/* ---- K11: beam-search step ----------------------------------------------------
+ * Replaces steps (1)-(8) of BeamSearchDecoder body
+ * (decoders/beam_search_decoder.py:440-496).  Per batch item b with beam k:
+ *   rows of finished hypotheses become {PAD:0, others:-1e9}; hyp = logprob_sum +
+ *   logprobs; len' = len + 1 - finished; score = hyp / ((5+len')/6)^alpha;
+ *   top-k over the k*V candidates (ties: lower flat index first, tf.nn.top_k);
+ *   word = idx % V (int64), beam = idx / V (int32); gathers lengths, the
+ *   UN-normalised logprob_sum and finished by (b, beam); finished |= word==2.
+ * In:  logprobs [B,k,V], logprob_sum [B,k], lengths [B,k] i32, finished [B,k] u8.
+ * Out: scores [B,k], word_ids [B,k] i64, beam_ids [B,k] i32, logprob_sum_out,
+ *      lengths_out, finished_out (may NOT alias the inputs).  The length penalty
+ *      is evaluated as fp32 (5+len)/6 followed by a correctly rounded powf, so the
+ *      scores and therefore the selected indices are bit-identical to an IEEE fp32
+ *      CPU evaluation of the same graph.  k <= 64. */
+int nm_beam_step(const float* logprobs, const float* logprob_sum,
+                 const int32_t* lengths, const uint8_t* finished, float alpha,
+                 float* scores, int64_t* word_ids, int32_t* beam_ids,
+                 float* logprob_sum_out, int32_t* lengths_out,
+                 uint8_t* finished_out, void* scratch, int64_t B, int64_t k,
+                 int64_t V, void* stream);
+/* Size of nm_beam_step's scratch in 4-byte words. */
+int64_t nm_beam_scratch(int64_t B, int64_t k, int64_t V);
+/* gather_flat (tf_utils.py:106-131): out[b*k+j, :] = x[b*k+beam_ids[b,j], :],
+ * row = `row_bytes` bytes (any dtype). */
+int nm_beam_gather(const void* x, const int32_t* beam_ids, void* out, int64_t B,
+                   int64_t k, int64_t row_bytes, void* stream);
+
+/* ---- K13: per-tensor clip + Adam over a flat parameter arena --------------------
+ * Replaces GenericTrainer.{regularization_losses,gradients,train_op}
+ * (trainers/generic_trainer.py:84-195) with tf.train.AdamOptimizer semantics:
+ *   g += 2*l2*p + l1*sign(p)            (only where seg_reg[s] != 0)
+ *   g *= min(1, clip/||g_s||)           per tensor s (tf.clip_by_norm), clip<=0: off
+ *   m = b1*m+(1-b1)*g ; v = b2*v+(1-b2)*g^2 ; p -= lr_t * m/(sqrt(v)+eps)
+ * with lr_t = lr*sqrt(1-b2^t)/(1-b1^t) computed by the caller.
+ * The arena holds `n` floats split into `nseg` tensors: seg_off [nseg+1] int64
+ * (device), seg_reg [nseg] uint8 (device).  norms [nseg] scratch (device).
+ * grad_scale multiplies g first (1/N for data-parallel means, 1/k for delayed
+ * updates).  l1l2_out [2] (device, may be NULL) receives sum|p|, sum p^2 over
+ * regularised tensors (the "L1"/"L2" losses the trainer reports). */
+int nm_clip_adam_step(float* params, float* grads, float* m, float* v,
+                      const int64_t* seg_off, const uint8_t* seg_reg, float* norms,
+                      int64_t n, int64_t nseg, float grad_scale, float lr_t,
+                      float beta1, float beta2, float eps, float clip_norm,
+                      float l1, float l2, float* l1l2_out, void* stream);
+
+/* ---- K8: multi-head scaled dot-product attention core ---------------------------
+ * Replaces attention() of attention/scaled_dot_product.py:98-226 between the
+ * q/k/v projections and the output projection:
+ *   E = (q/sqrt(dh)).k^T ; causal: where(tril, E, -1e9) ; key mask:
+ *   E*m + (1-m)*(-1e9) ; P = softmax(E) ; out = P.v
+ * q [B,Tq,h*dh], k/v [B,Tk,h*dh] (heads interleaved on the feature axis as
+ * split_for_heads does), key_mask [B,Tk] fp32 or NULL.  probs [B,h,Tq,Tk] saved. */
+int nm_mha_fwd(const float* q, const float* k, const float* v,
+               const float* key_mask, int causal, float* out, float* probs,
+               int64_t B, int64_t Tq, int64_t Tk, int64_t heads, int64_t dh,
+               void* stream);
+int nm_mha_bwd(const float* q, const float* k, const float* v,
+               const float* key_mask, int causal, const float* probs,
+               const float* dout, float* dq, float* dk, float* dv,
+               float* de_work /* scratch, B*heads*Tq*Tk floats */, int64_t B,
+               int64_t Tq, int64_t Tk, int64_t heads, int64_t dh, void* stream);
+
+/* ---- K12: VGG convolution stack primitives (forward only; the encoder is frozen,
+ * encoders/imagenet_encoder.py:212,234) -----------------------------------------
+ * NHWC fp32; 3x3, stride 1, SAME padding, + bias + ReLU (slim vgg_arg_scope);
+ * w is [3,3,Cin,Cout] (HWIO, the slim checkpoint layout). */
+int nm_conv3x3_bias_relu_fwd(const float* x, const float* w, const float* bias,
+                             float* y, int64_t N, int64_t H, int64_t W,
+                             int64_t Cin, int64_t Cout, void* stream);
+/* 2x2 / stride 2 max pool, NHWC (H, W even). */
+int nm_maxpool2x2_fwd(const float* x, float* y, int64_t N, int64_t H, int64_t W,
+                      int64_t C, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NMB200_H */

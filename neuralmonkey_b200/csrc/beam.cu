@@ -1,0 +1,236 @@
+// K11: one beam-search step (decoders/beam_search_decoder.py:440-496 of the reference):
+// finished-row masking, hypothesis log-prob sums, length-normalised scores, top-k over
+// the k*V candidates of every sentence, and the (batch, beam) index bookkeeping.
+//
+// HBM-bound: the step reads B*k*V fp32 log-probs once.  Phase 1 spreads the k*V
+// candidates of each sentence over many CTAs (coalesced, 16 candidates per thread in
+// registers) and keeps a per-CTA top-k; phase 2 merges the per-CTA lists in one CTA per
+// sentence and writes the integer outputs.  Ordering is exactly tf.nn.top_k's: larger
+// score first, equal scores by lower flat index.
+#include "common.cuh"
+
+namespace nm {
+
+constexpr int BEAM_THREADS = 256;
+constexpr int BEAM_ITEMS = 16;
+constexpr int BEAM_CHUNK = BEAM_THREADS * BEAM_ITEMS;  // candidates per phase-1 CTA
+constexpr int BEAM_MAX_K = 64;
+constexpr float BEAM_INF = 1e9f;  // INF of beam_search_decoder.py:43
+
+struct Cand {
+  float s;
+  int32_t i;
+};
+__device__ __forceinline__ bool cand_better(float s, int32_t i, float bs, int32_t bi) {
+  return s > bs || (s == bs && i < bi);
+}
+__device__ __forceinline__ Cand warp_best_cand(Cand c) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float os = __shfl_xor_sync(0xffffffffu, c.s, o);
+    const int32_t oi = __shfl_xor_sync(0xffffffffu, c.i, o);
+    if (cand_better(os, oi, c.s, c.i)) { c.s = os; c.i = oi; }
+  }
+  return c;
+}
+// Block-wide best candidate; all threads receive it.  sm: 2*32 words.
+__device__ __forceinline__ Cand block_best_cand(Cand c, float* sm_s, int32_t* sm_i) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  c = warp_best_cand(c);
+  __syncthreads();
+  if (lane == 0) { sm_s[w] = c.s; sm_i[w] = c.i; }
+  __syncthreads();
+  const int nw = blockDim.x >> 5;
+  Cand r{lane < nw ? sm_s[lane] : -INFINITY, lane < nw ? sm_i[lane] : 0x7fffffff};
+  r = warp_best_cand(r);
+  return r;  // identical in every warp
+}
+
+// length penalty ((5+len)/6)^alpha, the fp32 division first (as the reference graph does),
+// then a correctly rounded powf through double precision.
+__device__ __forceinline__ float length_penalty(int32_t len, float alpha) {
+  const float x = (5.f + (float)len) / 6.f;
+  return (float)pow((double)x, (double)alpha);
+}
+
+__device__ __forceinline__ float cand_hyp(const float* __restrict__ logprobs,
+                                          const float* __restrict__ logprob_sum,
+                                          const uint8_t* __restrict__ finished, int64_t b, int64_t k,
+                                          int64_t V, int32_t flat) {
+  const int64_t j = flat / V, w = flat - j * V;
+  const bool fin = finished[b * k + j] != 0;
+  const float lp = fin ? (w == 0 ? 0.f : -BEAM_INF) : logprobs[(b * k + j) * V + w];
+  return logprob_sum[b * k + j] + lp;
+}
+
+// phase 1: grid (chunks, B).  cand_s/cand_i: [B, chunks, k]
+__global__ void __launch_bounds__(BEAM_THREADS)
+beam_local_topk_kernel(const float* __restrict__ logprobs, const float* __restrict__ logprob_sum,
+                       const int32_t* __restrict__ lengths, const uint8_t* __restrict__ finished,
+                       float alpha, float* __restrict__ cand_s, int32_t* __restrict__ cand_i,
+                       int64_t k, int64_t V) {
+  __shared__ float sm_s[32];
+  __shared__ int32_t sm_i[32];
+  __shared__ float pen[BEAM_MAX_K];
+  const int64_t b = blockIdx.y;
+  const int64_t total = k * V;
+  if (threadIdx.x < k) {
+    const int32_t fin = finished[b * k + threadIdx.x] ? 1 : 0;
+    pen[threadIdx.x] = length_penalty(lengths[b * k + threadIdx.x] + 1 - fin, alpha);
+  }
+  __syncthreads();
+  float sc[BEAM_ITEMS];
+  const int64_t base = (int64_t)blockIdx.x * BEAM_CHUNK;
+#pragma unroll
+  for (int it = 0; it < BEAM_ITEMS; ++it) {
+    const int64_t flat = base + it * BEAM_THREADS + threadIdx.x;  // coalesced
+    if (flat < total) {
+      const int64_t j = flat / V;
+      sc[it] = cand_hyp(logprobs, logprob_sum, finished, b, k, V, (int32_t)flat) / pen[j];
+    } else {
+      sc[it] = -INFINITY;
+    }
+  }
+  uint32_t taken = 0;  // bit it: candidate `it` of this thread already emitted
+  for (int r = 0; r < k; ++r) {
+    Cand best{-INFINITY, 0x7fffffff};  // index 0x7fffffff = "no candidate left in this chunk"
+#pragma unroll
+    for (int it = 0; it < BEAM_ITEMS; ++it) {
+      const int64_t flat = base + it * BEAM_THREADS + threadIdx.x;
+      if (flat < total && !((taken >> it) & 1u) && cand_better(sc[it], (int32_t)flat, best.s, best.i)) {
+        best.s = sc[it];
+        best.i = (int32_t)flat;
+      }
+    }
+    const Cand win = block_best_cand(best, sm_s, sm_i);
+#pragma unroll
+    for (int it = 0; it < BEAM_ITEMS; ++it)
+      if (base + it * BEAM_THREADS + threadIdx.x == (int64_t)win.i) taken |= (1u << it);
+    if (threadIdx.x == 0) {
+      const int64_t o = (b * gridDim.x + blockIdx.x) * k + r;
+      cand_s[o] = win.s;
+      cand_i[o] = win.i;
+    }
+  }
+}
+
+// phase 2: grid (B).  Merges chunks*k candidates, writes all outputs.
+__global__ void __launch_bounds__(BEAM_THREADS)
+beam_merge_kernel(const float* __restrict__ cand_s, const int32_t* __restrict__ cand_i,
+                  int64_t chunks, const float* __restrict__ logprobs,
+                  const float* __restrict__ logprob_sum, const int32_t* __restrict__ lengths,
+                  const uint8_t* __restrict__ finished, float* __restrict__ scores,
+                  int64_t* __restrict__ word_ids, int32_t* __restrict__ beam_ids,
+                  float* __restrict__ logprob_sum_out, int32_t* __restrict__ lengths_out,
+                  uint8_t* __restrict__ finished_out, int64_t k, int64_t V) {
+  __shared__ float sm_s[32];
+  __shared__ int32_t sm_i[32];
+  const int64_t b = blockIdx.x;
+  const int64_t n = chunks * k;
+  const float* cs = cand_s + b * n;
+  const int32_t* ci = cand_i + b * n;
+  int32_t last_i = -1;
+  float last_s = INFINITY;
+  for (int r = 0; r < k; ++r) {
+    // best candidate strictly after (last_s, last_i) in the (score desc, index asc) order
+    Cand best{-INFINITY, 0x7fffffff};
+    for (int64_t c = threadIdx.x; c < n; c += BEAM_THREADS) {
+      const float s = cs[c];
+      const int32_t i = ci[c];
+      if (i == 0x7fffffff) continue;
+      const bool after = (r == 0) || s < last_s || (s == last_s && i > last_i);
+      if (after && cand_better(s, i, best.s, best.i)) { best.s = s; best.i = i; }
+    }
+    const Cand win = block_best_cand(best, sm_s, sm_i);
+    last_s = win.s;
+    last_i = win.i;
+    if (threadIdx.x == 0) {
+      const int64_t o = b * k + r;
+      const int32_t flat = win.i;
+      const int64_t j = flat / V, w = flat - j * V;
+      scores[o] = win.s;
+      word_ids[o] = w;
+      beam_ids[o] = (int32_t)j;
+      logprob_sum_out[o] = cand_hyp(logprobs, logprob_sum, finished, b, k, V, flat);
+      const int32_t fin = finished[b * k + j] ? 1 : 0;
+      lengths_out[o] = lengths[b * k + j] + 1 - fin;
+      finished_out[o] = (fin || w == 2) ? 1 : 0;  // END_TOKEN_INDEX = 2
+    }
+  }
+}
+
+// gather_flat: out[(b*k+j), :] = x[(b*k+beam_ids[b,j]), :], rows of row_bytes bytes.
+__global__ void beam_gather_kernel(const uint8_t* __restrict__ x, const int32_t* __restrict__ beam_ids,
+                                   uint8_t* __restrict__ out, int64_t k, int64_t row_bytes) {
+  const int64_t o = blockIdx.x;  // b*k + j
+  const int64_t b = o / k;
+  const int64_t src = b * k + beam_ids[o];
+  const uint8_t* s = x + src * row_bytes;
+  uint8_t* d = out + o * row_bytes;
+  if (((reinterpret_cast<uintptr_t>(s) | reinterpret_cast<uintptr_t>(d) | (uintptr_t)row_bytes) & 15) == 0) {
+    const int64_t n16 = row_bytes / 16;
+    for (int64_t i = blockIdx.y * (int64_t)blockDim.x + threadIdx.x; i < n16;
+         i += (int64_t)gridDim.y * blockDim.x)
+      reinterpret_cast<uint4*>(d)[i] = reinterpret_cast<const uint4*>(s)[i];
+  } else {
+    for (int64_t i = blockIdx.y * (int64_t)blockDim.x + threadIdx.x; i < row_bytes;
+         i += (int64_t)gridDim.y * blockDim.x)
+      d[i] = s[i];
+  }
+}
+
+}  // namespace nm
+
+using namespace nm;
+
+extern "C" {
+
+int64_t nm_beam_scratch(int64_t B, int64_t k, int64_t V) {
+  if (B <= 0 || k <= 0 || V <= 0) return 0;
+  return 2 * B * ceil_div(k * V, BEAM_CHUNK) * k;  // 4-byte words: scores then indices
+}
+
+int nm_beam_step(const float* logprobs, const float* logprob_sum, const int32_t* lengths,
+                 const uint8_t* finished, float alpha, float* scores, int64_t* word_ids,
+                 int32_t* beam_ids, float* logprob_sum_out, int32_t* lengths_out,
+                 uint8_t* finished_out, void* scratch, int64_t B, int64_t k, int64_t V,
+                 void* stream) {
+  NM_REQUIRE(logprobs && logprob_sum && lengths && finished && scores && word_ids && beam_ids &&
+                 logprob_sum_out && lengths_out && finished_out && scratch,
+             NM_E_INVALID, "nm_beam_step: null pointer");
+  NM_REQUIRE(B > 0 && k > 0 && V > 0, NM_E_INVALID, "nm_beam_step: bad sizes");
+  NM_REQUIRE(k <= BEAM_MAX_K, NM_E_UNSUPPORTED, "nm_beam_step: beam %lld > %d", (long long)k, BEAM_MAX_K);
+  NM_REQUIRE(k * V < 0x7fffffffLL && B <= 65535, NM_E_UNSUPPORTED, "nm_beam_step: k*V or B too large");
+  NM_REQUIRE(k <= V * k, NM_E_INVALID, "nm_beam_step: beam larger than candidate set");
+  cudaStream_t s = (cudaStream_t)stream;
+  const int64_t chunks = ceil_div(k * V, BEAM_CHUNK);
+  float* cand_s = reinterpret_cast<float*>(scratch);
+  int32_t* cand_i = reinterpret_cast<int32_t*>(scratch) + B * chunks * k;
+  dim3 grid1((unsigned)chunks, (unsigned)B);
+  beam_local_topk_kernel<<<grid1, BEAM_THREADS, 0, s>>>(logprobs, logprob_sum, lengths, finished, alpha,
+                                                        cand_s, cand_i, k, V);
+  NM_LAUNCH_CHECK("nm_beam_step(local)");
+  beam_merge_kernel<<<(unsigned)B, BEAM_THREADS, 0, s>>>(cand_s, cand_i, chunks, logprobs, logprob_sum,
+                                                         lengths, finished, scores, word_ids, beam_ids,
+                                                         logprob_sum_out, lengths_out, finished_out, k, V);
+  NM_LAUNCH_CHECK("nm_beam_step(merge)");
+  return NM_OK;
+}
+
+int nm_beam_gather(const void* x, const int32_t* beam_ids, void* out, int64_t B, int64_t k,
+                   int64_t row_bytes, void* stream) {
+  NM_REQUIRE(x && beam_ids && out, NM_E_INVALID, "nm_beam_gather: null pointer");
+  NM_REQUIRE(B > 0 && k > 0 && row_bytes >= 0, NM_E_INVALID, "nm_beam_gather: bad sizes");
+  NM_REQUIRE(x != out, NM_E_INVALID, "nm_beam_gather: in-place gather is not supported");
+  if (row_bytes == 0) return NM_OK;
+  int64_t gy = ceil_div(row_bytes / 16 + 1, 256);
+  if (gy > 64) gy = 64;
+  dim3 grid((unsigned)(B * k), (unsigned)gy);
+  beam_gather_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const uint8_t*>(x),
+                                                             beam_ids, reinterpret_cast<uint8_t*>(out),
+                                                             k, row_bytes);
+  NM_LAUNCH_CHECK("nm_beam_gather");
+  return NM_OK;
+}
+
+}  // extern "C"

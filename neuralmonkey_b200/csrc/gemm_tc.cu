@@ -1,0 +1,512 @@
+// tcgen05 GEMM for sm_100a: D[M,N] = op(A)[M,K] . op(B)[K,N], fp32 operands consumed as
+// TF32 (kind::tf32), fp32 accumulation in TMEM.
+//
+//   * persistent: one CTA per SM walks 128 x BN output tiles (static round-robin);
+//   * warp 0 = TMA producer, warp 1 = MMA issuer (one elected lane) + TMEM allocator,
+//     warps 2..5 = epilogue (TMEM lane quadrant = warp_idx % 4);
+//   * STAGES-deep smem ring of {A 128x32, B BNx32} fp32 tiles in the 128-byte swizzle,
+//     filled by cp.async.bulk.tensor (OOB rows/cols arrive as zeros: no tail code);
+//   * two TMEM accumulator buffers (2*BN columns) so the epilogue of tile i overlaps
+//     the main loop of tile i+1;
+//   * both operand majors: "K-major" (reduction dim contiguous) and "MN-major"
+//     (reduction dim strided), so forward (X.W), input-gradient (dY.W^T) and
+//     weight-gradient (X^T.dY) products need no transposes in HBM;
+//   * epilogues: dense (bias/activation/accumulate), and the fused vocabulary
+//     cross-entropy forward (online softmax partials + argmax + target logit) and
+//     backward (softmax - onehot), which never materialise fp32 logits twice.
+//
+// Descriptor bit layouts follow the PTX ISA "tcgen05 shared memory descriptor" and
+// "instruction descriptor" tables (as restated in CUTLASS cute/arch/mma_sm100_desc.hpp).
+#include <cuda.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "common.cuh"
+#include "gemm_tc.h"
+
+namespace nm {
+
+constexpr int TC_BM = 128;
+constexpr int TC_BK = 32;                      // fp32 elements = 128 bytes = one swizzle row
+constexpr int TC_UMMA_K = 8;                   // tf32: 32 bytes per instruction
+constexpr int TC_THREADS = 192;                // 6 warps
+constexpr int TC_A_BYTES = TC_BM * TC_BK * 4;  // 16 KB
+constexpr int TC_SMEM_BUDGET = 200 * 1024;
+
+template <int BN>
+struct TcCfg {
+  static constexpr int B_BYTES = BN * TC_BK * 4;
+  static constexpr int STAGE_BYTES = TC_A_BYTES + B_BYTES;
+  static constexpr int STAGES = (TC_SMEM_BUDGET / STAGE_BYTES) > 8 ? 8 : (TC_SMEM_BUDGET / STAGE_BYTES);
+  static constexpr int TMEM_COLS = 2 * BN;  // 128, 256, 512: powers of two >= 32
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+// ---------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra WAIT_DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "WAIT_DONE:\n\t"
+      "}" ::"r"(bar),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar,
+                                            int32_t c0, int32_t c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tcgen05_fence_before() {
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tcgen05_fence_after() {
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b,
+                                          uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&r)[32]) {
+  uint32_t* u = reinterpret_cast<uint32_t*>(r);
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32"
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15,"
+      " %16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]),
+        "=r"(u[7]), "=r"(u[8]), "=r"(u[9]), "=r"(u[10]), "=r"(u[11]), "=r"(u[12]), "=r"(u[13]),
+        "=r"(u[14]), "=r"(u[15]), "=r"(u[16]), "=r"(u[17]), "=r"(u[18]), "=r"(u[19]), "=r"(u[20]),
+        "=r"(u[21]), "=r"(u[22]), "=r"(u[23]), "=r"(u[24]), "=r"(u[25]), "=r"(u[26]), "=r"(u[27]),
+        "=r"(u[28]), "=r"(u[29]), "=r"(u[30]), "=r"(u[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// Shared-memory matrix descriptor, 128-byte swizzle, version 1 (Blackwell).
+// bits [0,14) start>>4 | [16,30) LBO>>4 | [32,46) SBO>>4 | [46,48) version | [61,64) layout
+__device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((addr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;  // SWIZZLE_128B
+  return d;
+}
+
+// ---------------------------------------------------------------------------
+// epilogue for one 32-column chunk owned by one thread (= one output row)
+// ---------------------------------------------------------------------------
+struct RowStats {
+  float mx, sum, tgt;
+  int32_t arg;
+};
+
+__device__ __forceinline__ void epilogue_chunk(const TcEpilogue& e, const float (&acc)[32],
+                                               int64_t row, int64_t col0, int64_t M, int64_t N,
+                                               RowStats& st, int64_t target, float row_lse,
+                                               float row_w) {
+  if (row >= M || col0 >= N) return;
+  const int ncols = (int)min((int64_t)32, N - col0);
+  if (e.mode == TC_EPI_DENSE) {
+    float* c = e.C + row * e.ldc + col0;
+    const bool vec = (ncols == 32) && ((e.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(e.C) & 15) == 0) &&
+                     ((col0 & 3) == 0);
+    if (vec) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) {
+        float4 o;
+        float x[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          float v = acc[j + i] + (e.bias ? __ldg(e.bias + col0 + j + i) : 0.f);
+          x[i] = apply_act(v, e.act);
+        }
+        if (e.beta != 0.f) {
+          const float4 old = *reinterpret_cast<const float4*>(c + j);
+          x[0] += old.x; x[1] += old.y; x[2] += old.z; x[3] += old.w;
+        }
+        o.x = x[0]; o.y = x[1]; o.z = x[2]; o.w = x[3];
+        *reinterpret_cast<float4*>(c + j) = o;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        if (j < ncols) {
+          float v = acc[j] + (e.bias ? __ldg(e.bias + col0 + j) : 0.f);
+          v = apply_act(v, e.act);
+          if (e.beta != 0.f) v += c[j];
+          c[j] = v;
+        }
+      }
+    }
+    return;
+  }
+  // xent modes: x = acc + bias + unk mask
+  float x[32];
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    float v = acc[j] + ((e.bias && j < ncols) ? __ldg(e.bias + col0 + j) : 0.f);
+    if (col0 + j == e.unk_index) v += -1e9f;
+    x[j] = v;
+  }
+  if (e.mode == TC_EPI_XENT_FWD) {
+    float cmx = -INFINITY;
+    int carg = 0;
+#pragma unroll
+    for (int j = 0; j < 32; ++j)
+      if (j < ncols && x[j] > cmx) { cmx = x[j]; carg = j; }
+    if (cmx > st.mx) {  // strict: earlier chunks (lower columns) win ties
+      st.sum *= __expf(st.mx - cmx);
+      st.mx = cmx;
+      st.arg = (int32_t)(col0 + carg);
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < 32; ++j)
+      if (j < ncols) s += __expf(x[j] - st.mx);
+    st.sum += s;
+    if (target >= col0 && target < col0 + ncols) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (col0 + j == target) st.tgt = x[j];
+    }
+    if (e.C) {
+      float* c = e.C + row * e.ldc + col0;
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (j < ncols) c[j] = x[j];
+    }
+  } else {  // TC_EPI_XENT_BWD
+    float* c = e.C + row * e.ldc + col0;
+    const bool vec = (ncols == 32) && ((e.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(e.C) & 15) == 0) &&
+                     ((col0 & 3) == 0);
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      const float p = __expf(x[j] - row_lse);
+      x[j] = (p - ((col0 + j == target) ? 1.f : 0.f)) * row_w;
+    }
+    if (vec) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 4)
+        *reinterpret_cast<float4*>(c + j) = make_float4(x[j], x[j + 1], x[j + 2], x[j + 3]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (j < ncols) c[j] = x[j];
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// the kernel
+// ---------------------------------------------------------------------------
+template <int BN, bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+               int64_t M, int64_t N, int64_t K, TcEpilogue epi) {
+  using Cfg = TcCfg<BN>;
+  constexpr int STAGES = Cfg::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;  // SW128 tiles: 1 KB aligned
+  const uint32_t bar_base = smem_base + STAGES * Cfg::STAGE_BYTES;
+  // barrier layout (8 B each): full[STAGES] | empty[STAGES] | tmem_full[2] | tmem_empty[2] | tmem ptr
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + 2 + a); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 4);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t tiles_m = (M + TC_BM - 1) / TC_BM;
+  const int64_t tiles_n = (N + BN - 1) / BN;
+  const int64_t num_tiles = tiles_m * tiles_n;
+  const int num_kb = (int)((K + TC_BK - 1) / TC_BK);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tfull_bar(a), 1);
+      mbar_init(tempty_bar(a), 4);  // one arrive per epilogue warp
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot),
+                 "r"((uint32_t)Cfg::TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int32_t m0 = (int32_t)((tile % tiles_m) * TC_BM);
+        const int32_t n0 = (int32_t)((tile / tiles_m) * BN);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(empty_bar(stage), phase ^ 1u);
+          const uint32_t a_dst = smem_base + stage * Cfg::STAGE_BYTES;
+          const uint32_t b_dst = a_dst + TC_A_BYTES;
+          mbar_expect_tx(full_bar(stage), (uint32_t)Cfg::STAGE_BYTES);
+          const int32_t k0 = kb * TC_BK;
+          if (!A_MN) {
+            tma_load_2d(a_dst, &map_a, full_bar(stage), k0, m0);  // box {32 k, 128 rows}
+          } else {
+#pragma unroll
+            for (int j = 0; j < TC_BM / 32; ++j)  // box {32 m, 32 k} per 4 KB block
+              tma_load_2d(a_dst + j * 4096, &map_a, full_bar(stage), m0 + 32 * j, k0);
+          }
+          if (!B_MN) {
+            tma_load_2d(b_dst, &map_b, full_bar(stage), k0, n0);  // box {32 k, BN rows}
+          } else {
+#pragma unroll
+            for (int j = 0; j < BN / 32; ++j)
+              tma_load_2d(b_dst + j * 4096, &map_b, full_bar(stage), n0 + 32 * j, k0);
+          }
+          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      // instruction descriptor: c=F32 [4,6)=1, a=TF32 [7,10)=2, b=TF32 [10,13)=2,
+      // a_major bit15, b_major bit16, N>>3 [17,23), M>>4 [24,29)
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((A_MN ? 1u : 0u) << 15) |
+                             ((B_MN ? 1u : 0u) << 16) | ((uint32_t)(BN >> 3) << 17) |
+                             ((uint32_t)(TC_BM >> 4) << 24);
+      int stage = 0;
+      uint32_t phase = 0;
+      int64_t it = 0;
+      for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+        const int acc = (int)(it & 1);
+        const uint32_t acc_phase = (uint32_t)((it >> 1) & 1);
+        mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+        tcgen05_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(full_bar(stage), phase);
+          tcgen05_fence_after();
+          const uint32_t a_addr = smem_base + stage * Cfg::STAGE_BYTES;
+          const uint32_t b_addr = a_addr + TC_A_BYTES;
+#pragma unroll
+          for (int k = 0; k < TC_BK / TC_UMMA_K; ++k) {
+            // K-major: 8 rows x 128 B atoms, next 8-row group at +1024 B, K step = +32 B.
+            // MN-major: 32-element MN atoms at +4096 B (LBO), 8-k-row groups at +1024 B (SBO),
+            //           K step = one 8-row group = +1024 B.
+            const uint64_t da = A_MN ? smem_desc(a_addr + k * 1024, 4096, 1024)
+                                     : smem_desc(a_addr + k * 32, 16, 1024);
+            const uint64_t db = B_MN ? smem_desc(b_addr + k * 1024, 4096, 1024)
+                                     : smem_desc(b_addr + k * 32, 16, 1024);
+            umma_tf32(d_tmem, da, db, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(empty_bar(stage));  // frees this smem stage when the MMAs retire
+          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        }
+        umma_commit(tfull_bar(acc));  // accumulator complete -> epilogue
+      }
+    }
+  } else {
+    // ===================== epilogue warps (2..5) =====================
+    const int quad = warp & 3;  // TMEM lanes [32*quad, 32*quad+32)
+    int64_t it = 0;
+    for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      const int acc = (int)(it & 1);
+      const uint32_t acc_phase = (uint32_t)((it >> 1) & 1);
+      const int64_t tm = tile % tiles_m, tn = tile / tiles_m;
+      const int64_t row = tm * TC_BM + quad * 32 + lane;
+      mbar_wait(tfull_bar(acc), acc_phase);
+      tcgen05_fence_after();
+      RowStats st{-INFINITY, 0.f, -INFINITY, 0};
+      int64_t target = -1;
+      float row_lse = 0.f, row_w = 0.f;
+      if (epi.mode != TC_EPI_DENSE && row < M) {
+        if (epi.targets) target = epi.targets[row];
+        if (epi.mode == TC_EPI_XENT_BWD) {
+          row_lse = epi.lse[row];
+          row_w = (epi.weights ? epi.weights[row] : 1.f) * epi.scale[0];
+        }
+      }
+      const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN);
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        float v[32];
+        tmem_ld32(t_row + (uint32_t)(c * 32), v);
+        epilogue_chunk(epi, v, row, tn * BN + c * 32, M, N, st, target, row_lse, row_w);
+      }
+      if (epi.mode == TC_EPI_XENT_FWD && row < M)
+        epi.part[row * tiles_n + tn] = make_float4(st.mx, st.sum, __int_as_float(st.arg), st.tgt);
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(acc));
+    }
+  }
+
+  // teardown: everyone done with TMEM before dealloc
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tcgen05_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
+                 "r"((uint32_t)Cfg::TMEM_COLS)
+                 : "memory");
+  }
+}
+
+// ---------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                  const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// 2-D fp32 tensor [rows, cols] with row pitch ld (elements); box = {box_cols, box_rows}.
+static int make_map(CUtensorMap* map, const float* base, int64_t rows, int64_t cols, int64_t ld,
+                    uint32_t box_cols, uint32_t box_rows) {
+  EncodeTiledFn fn = get_encode_fn();
+  NM_REQUIRE(fn != nullptr, NM_E_NO_DEVICE, "tc_gemm: cuTensorMapEncodeTiled not available");
+  static int dtype_mode = -1;  // NMB200_TMA_DTYPE=fp32 keeps raw fp32 bits (MMA truncates)
+  if (dtype_mode < 0) {
+    const char* e = getenv("NMB200_TMA_DTYPE");
+    dtype_mode = (e && strcmp(e, "fp32") == 0) ? 1 : 0;
+  }
+  const cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  const cuuint64_t gstride[1] = {(cuuint64_t)ld * 4};
+  const cuuint32_t box[2] = {box_cols, box_rows};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUresult r = fn(map, dtype_mode ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_TFLOAT32,
+                        2, const_cast<float*>(base), gdim, gstride, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  NM_REQUIRE(r == CUDA_SUCCESS, NM_E_INVALID,
+             "tc_gemm: cuTensorMapEncodeTiled failed (%d) rows=%lld cols=%lld ld=%lld", (int)r,
+             (long long)rows, (long long)cols, (long long)ld);
+  return NM_OK;
+}
+
+bool tc_gemm_supported(int transA, int transB, int64_t M, int64_t N, int64_t K, int64_t lda,
+                       int64_t ldb, int64_t ldc, const void* A, const void* B, const void* C) {
+  (void)transA; (void)transB; (void)ldc; (void)C;
+  if (M < 1 || N < 1 || K < 1) return false;
+  if ((lda & 3) || (ldb & 3)) return false;  // TMA global strides are multiples of 16 bytes
+  if (A && (reinterpret_cast<uintptr_t>(A) & 15)) return false;
+  if (B && (reinterpret_cast<uintptr_t>(B) & 15)) return false;
+  if (M > 0x7fffffffLL || N > 0x7fffffffLL || K > 0x7fffffffLL) return false;
+  return true;
+}
+
+template <int BN, bool A_MN, bool B_MN>
+static int launch_cfg(const CUtensorMap& ma, const CUtensorMap& mb, int64_t M, int64_t N, int64_t K,
+                      const TcEpilogue& epi, cudaStream_t s) {
+  using Cfg = TcCfg<BN>;
+  auto kern = tc_gemm_kernel<BN, A_MN, B_MN>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    NM_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    attr_done = true;
+  }
+  const int64_t tiles = ceil_div(M, TC_BM) * ceil_div(N, BN);
+  const int64_t grid = tiles < sm_count() ? tiles : sm_count();
+  kern<<<(unsigned)grid, TC_THREADS, Cfg::SMEM_BYTES, s>>>(ma, mb, M, N, K, epi);
+  NM_LAUNCH_CHECK("tc_gemm_kernel");
+  return NM_OK;
+}
+
+static int pick_bn(int64_t M, int64_t N) {
+  if (N <= 64) return 64;
+  if (N <= 128) return 128;
+  const int64_t pad128 = ceil_div(N, 128) * 128, pad256 = ceil_div(N, 256) * 256;
+  const int64_t tiles256 = ceil_div(M, TC_BM) * ceil_div(N, 256);
+  if (pad256 == pad128 && tiles256 >= sm_count()) return 256;
+  if (pad256 * 10 <= pad128 * 11 && tiles256 >= 2 * (int64_t)sm_count()) return 256;
+  return 128;
+}
+
+int tc_gemm_launch(int transA, int transB, int64_t M, int64_t N, int64_t K, const float* A,
+                   int64_t lda, const float* B, int64_t ldb, const TcEpilogue& epi, cudaStream_t s) {
+  // op(A) is [M,K]: transA=0 -> A stored [M,K], K contiguous (K-major);
+  //                 transA=1 -> A stored [K,M], M contiguous (MN-major).
+  // op(B) is [K,N]: transB=0 -> B stored [K,N], N contiguous (MN-major);
+  //                 transB=1 -> B stored [N,K], K contiguous (K-major).
+  const bool a_mn = transA != 0, b_mn = transB == 0;
+  const int bn = (epi.mode == TC_EPI_DENSE) ? pick_bn(M, N) : TC_XENT_BN;
+  CUtensorMap ma, mb;
+  int rc;
+  if (!a_mn) rc = make_map(&ma, A, M, K, lda, TC_BK, TC_BM);
+  else       rc = make_map(&ma, A, K, M, lda, 32, TC_BK);
+  if (rc) return rc;
+  if (!b_mn) rc = make_map(&mb, B, N, K, ldb, TC_BK, (uint32_t)bn);
+  else       rc = make_map(&mb, B, K, N, ldb, 32, TC_BK);
+  if (rc) return rc;
+#define NM_TC_DISPATCH(BN_)                                                            \
+  do {                                                                                 \
+    if (!a_mn && !b_mn) return launch_cfg<BN_, false, false>(ma, mb, M, N, K, epi, s); \
+    if (!a_mn && b_mn) return launch_cfg<BN_, false, true>(ma, mb, M, N, K, epi, s);   \
+    if (a_mn && !b_mn) return launch_cfg<BN_, true, false>(ma, mb, M, N, K, epi, s);   \
+    return launch_cfg<BN_, true, true>(ma, mb, M, N, K, epi, s);                       \
+  } while (0)
+  if (bn == 64) NM_TC_DISPATCH(64);
+  if (bn == 128) NM_TC_DISPATCH(128);
+  NM_TC_DISPATCH(256);
+#undef NM_TC_DISPATCH
+}
+
+}  // namespace nm

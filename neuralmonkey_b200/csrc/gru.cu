@@ -1,0 +1,187 @@
+// K2: TF-1.12 GRUCell over a whole sequence (forward and backward through time).
+//
+// The input half of both cell matmuls is hoisted out of the recurrence by the
+// host (one tensor-core GEMM over all B*T rows, see nm_gemm); what remains per
+// step is the recurrent half, which is kept in exact fp32 on the CUDA cores:
+//     [r,u] = sigmoid(xg_t + h.Wgh) ; c = tanh(xc_t + (r*h).Wch) ; h' = u*h + (1-u)*c
+// (reference: tf.contrib.rnn.GRUCell as used by nn/ortho_gru_cell.py:44-53,
+//  encoders/recurrent.py:82-95, decoders/decoder.py:283-289).
+// Each step is two fused GEMM+gate kernels forward and one gate kernel plus two
+// fused GEMM kernels backward; the state the step consumed is read from / written
+// to the `hprev` history directly, so no state copy kernels are launched.
+#include "gemm_simt.cuh"
+
+namespace nm {
+
+// --- forward epilogues -------------------------------------------------------
+struct GruGatesEpi {
+  const float* xproj;  // [B,T,3H]
+  const float* hprev;  // [B,T,H]
+  float* gates;        // [B,T,3H]
+  float* rh;           // [B,T,H]: r*h, A operand of the candidate matmul
+  int64_t T, H, t;
+  __device__ void operator()(int64_t b, int64_t n, float acc) const {
+    const int64_t base3 = (b * T + t) * 3 * H;
+    const float g = sigmoidf_(acc + xproj[base3 + n]);
+    gates[base3 + n] = g;
+    if (n < H) rh[(b * T + t) * H + n] = g * hprev[(b * T + t) * H + n];
+  }
+};
+
+struct GruCandEpi {
+  const float* xproj;
+  const float* hprev;
+  float* gates;
+  float* states;       // [B,T,H]
+  float* hnext;        // &hprev[0, t_next, 0] or final_state
+  int64_t hnext_stride;  // T*H or H
+  const int32_t* lengths;
+  int64_t T, H, t;
+  __device__ void operator()(int64_t b, int64_t n, float acc) const {
+    const int64_t base3 = (b * T + t) * 3 * H;
+    const float c = tanhf(acc + xproj[base3 + 2 * H + n]);
+    gates[base3 + 2 * H + n] = c;
+    const float u = gates[base3 + H + n];
+    const float h = hprev[(b * T + t) * H + n];
+    const bool live = (lengths == nullptr) || (t < (int64_t)lengths[b]);
+    const float hn = live ? (u * h + (1.f - u) * c) : h;
+    states[(b * T + t) * H + n] = live ? hn : 0.f;
+    hnext[b * hnext_stride + n] = hn;
+  }
+};
+
+// --- backward ----------------------------------------------------------------
+// E1: gate gradients that need no matmul.  dh_in = carry (+ dstates[t] on live rows).
+__global__ void gru_bwd_gate_kernel(const float* __restrict__ gates, const float* __restrict__ hprev,
+                                    const float* __restrict__ dstates, const float* __restrict__ dcarry,
+                                    const int32_t* __restrict__ lengths, float* __restrict__ dxproj,
+                                    float* __restrict__ dhp, int64_t B, int64_t T, int64_t H,
+                                    int64_t t) {
+  const int64_t total = B * H;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t b = i / H, n = i - b * H;
+    const int64_t base3 = (b * T + t) * 3 * H, base1 = (b * T + t) * H;
+    const bool live = (lengths == nullptr) || (t < (int64_t)lengths[b]);
+    const float u = gates[base3 + H + n], c = gates[base3 + 2 * H + n];
+    const float h = hprev[base1 + n];
+    float dh = dcarry ? dcarry[i] : 0.f;
+    if (!live) {
+      dxproj[base3 + n] = 0.f;  // dz_r is overwritten by the Wch kernel for live rows only
+      dxproj[base3 + H + n] = 0.f;
+      dxproj[base3 + 2 * H + n] = 0.f;
+      dhp[i] = dh;
+      continue;
+    }
+    if (dstates) dh += dstates[base1 + n];
+    const float du = dh * (h - c);
+    const float dc = dh * (1.f - u);
+    dxproj[base3 + 2 * H + n] = dc * (1.f - c * c);
+    dxproj[base3 + H + n] = du * u * (1.f - u);
+    dhp[i] = dh * u;
+  }
+}
+
+// G1: drh = dzc . Wch^T ; dz_r = drh*h*r*(1-r) ; dhp += drh*r      (live rows only)
+struct GruBwdCandEpi {
+  const float* gates;
+  const float* hprev;
+  const int32_t* lengths;
+  float* dxproj;
+  float* dhp;
+  int64_t T, H, t;
+  __device__ void operator()(int64_t b, int64_t n, float drh) const {
+    const bool live = (lengths == nullptr) || (t < (int64_t)lengths[b]);
+    if (!live) return;
+    const int64_t base3 = (b * T + t) * 3 * H;
+    const float r = gates[base3 + n];
+    const float h = hprev[(b * T + t) * H + n];
+    dxproj[base3 + n] = drh * h * r * (1.f - r);
+    dhp[b * H + n] += drh * r;
+  }
+};
+
+// G2: dcarry = dhp + [dz_r, dz_u] . Wgh^T
+struct GruBwdGatesEpi {
+  const float* dhp;
+  float* dcarry;
+  int64_t H;
+  __device__ void operator()(int64_t b, int64_t n, float acc) const {
+    dcarry[b * H + n] = dhp[b * H + n] + acc;
+  }
+};
+
+}  // namespace nm
+
+using namespace nm;
+
+extern "C" {
+
+int nm_gru_seq_fwd(const float* xproj, const float* Wgh, const float* Wch, const float* h0,
+                   const int32_t* lengths, int reverse, float* states, float* final_state,
+                   float* gates, float* hprev, float* rh, int64_t B, int64_t T, int64_t H,
+                   void* stream) {
+  NM_REQUIRE(xproj && Wgh && Wch && states && final_state && gates && hprev && rh, NM_E_INVALID,
+             "nm_gru_seq_fwd: null pointer");
+  NM_REQUIRE(B > 0 && T > 0 && H > 0, NM_E_INVALID, "nm_gru_seq_fwd: bad sizes B=%lld T=%lld H=%lld",
+             (long long)B, (long long)T, (long long)H);
+  cudaStream_t s = (cudaStream_t)stream;
+  const int64_t t_first = reverse ? T - 1 : 0;
+  // seed the state history with h0 (or zeros): hprev[:, t_first, :]
+  if (h0)
+    NM_CUDA_TRY(cudaMemcpy2DAsync(hprev + t_first * H, sizeof(float) * T * H, h0, sizeof(float) * H,
+                                  sizeof(float) * H, B, cudaMemcpyDeviceToDevice, s));
+  else
+    NM_CUDA_TRY(cudaMemset2DAsync(hprev + t_first * H, sizeof(float) * T * H, 0, sizeof(float) * H, B, s));
+  for (int64_t step = 0; step < T; ++step) {
+    const int64_t t = reverse ? T - 1 - step : step;
+    // [r,u] = sigmoid(xg_t + h.Wgh);  rh = r*h
+    GruGatesEpi e1{xproj, hprev, gates, rh, T, H, t};
+    simt_gemm_launch(hprev + t * H, T * H, 1, Wgh, 2 * H, 1, B, 2 * H, H, e1, s);
+    // c = tanh(xc_t + rh.Wch);  h' = u*h + (1-u)*c  -> next slot of the history / final state
+    const bool last = (step == T - 1);
+    const int64_t t_next = reverse ? t - 1 : t + 1;
+    GruCandEpi e2{xproj, hprev, gates, states, last ? final_state : hprev + t_next * H,
+                  last ? H : T * H, lengths, T, H, t};
+    simt_gemm_launch(rh + t * H, T * H, 1, Wch, H, 1, B, H, H, e2, s);
+  }
+  NM_LAUNCH_CHECK("nm_gru_seq_fwd");
+  return NM_OK;
+}
+
+int nm_gru_seq_bwd(const float* Wgh, const float* Wch, const int32_t* lengths, int reverse,
+                   const float* gates, const float* hprev, const float* dstates, const float* dfinal,
+                   float* dxproj, float* dh0, float* work, int64_t B, int64_t T, int64_t H,
+                   void* stream) {
+  NM_REQUIRE(Wgh && Wch && gates && hprev && dxproj && work, NM_E_INVALID,
+             "nm_gru_seq_bwd: null pointer");
+  NM_REQUIRE(B > 0 && T > 0 && H > 0, NM_E_INVALID, "nm_gru_seq_bwd: bad sizes");
+  cudaStream_t s = (cudaStream_t)stream;
+  float* dcarry = work;
+  float* dhp = work + B * H;
+  if (dfinal)
+    NM_CUDA_TRY(cudaMemcpyAsync(dcarry, dfinal, sizeof(float) * B * H, cudaMemcpyDeviceToDevice, s));
+  else
+    NM_CUDA_TRY(cudaMemsetAsync(dcarry, 0, sizeof(float) * B * H, s));
+  const int threads = 256;
+  int64_t blocks = ceil_div(B * H, threads);
+  const int64_t cap = (int64_t)sm_count() * 8;
+  if (blocks > cap) blocks = cap;
+  for (int64_t step = T - 1; step >= 0; --step) {
+    const int64_t t = reverse ? T - 1 - step : step;
+    gru_bwd_gate_kernel<<<(unsigned)blocks, threads, 0, s>>>(gates, hprev, dstates, dcarry, lengths,
+                                                            dxproj, dhp, B, T, H, t);
+    // drh = dz_c . Wch^T   (op(B)(k=j, n=i) = Wch[i*H + j])
+    GruBwdCandEpi g1{gates, hprev, lengths, dxproj, dhp, T, H, t};
+    simt_gemm_launch(dxproj + t * 3 * H + 2 * H, T * 3 * H, 1, Wch, 1, H, B, H, H, g1, s);
+    // dcarry = dhp + [dz_r, dz_u] . Wgh^T   (op(B)(k=j, n=i) = Wgh[i*2H + j])
+    GruBwdGatesEpi g2{dhp, dcarry, H};
+    simt_gemm_launch(dxproj + t * 3 * H, T * 3 * H, 1, Wgh, 1, 2 * H, B, H, 2 * H, g2, s);
+  }
+  if (dh0)
+    NM_CUDA_TRY(cudaMemcpyAsync(dh0, dcarry, sizeof(float) * B * H, cudaMemcpyDeviceToDevice, s));
+  NM_LAUNCH_CHECK("nm_gru_seq_bwd");
+  return NM_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,122 @@
+// K13: regularisation gradients, per-tensor clip_by_norm and TF-Adam over one flat
+// fp32 parameter arena (trainers/generic_trainer.py:84-195 of the reference).
+// Two HBM-bound passes over the arena: (1) g = scale*g + 2*l2*p + l1*sign(p) and
+// per-tensor sum of squares, (2) clip + Adam.  A CTA owns a fixed chunk of the
+// arena and walks the (1-2) tensors that overlap it, so the per-tensor reduction is
+// one atomicAdd per CTA per tensor.
+#include "common.cuh"
+
+namespace nm {
+
+constexpr int OPT_THREADS = 256;
+constexpr int64_t OPT_CHUNK = 8192;  // elements per CTA
+
+__device__ __forceinline__ int64_t find_segment(const int64_t* __restrict__ seg_off, int64_t nseg,
+                                                int64_t pos) {
+  // largest s with seg_off[s] <= pos
+  int64_t lo = 0, hi = nseg - 1;
+  while (lo < hi) {
+    const int64_t mid = (lo + hi + 1) >> 1;
+    if (seg_off[mid] <= pos) lo = mid; else hi = mid - 1;
+  }
+  return lo;
+}
+
+__global__ void __launch_bounds__(OPT_THREADS)
+reg_norm_kernel(const float* __restrict__ params, float* __restrict__ grads,
+                const int64_t* __restrict__ seg_off, const uint8_t* __restrict__ seg_reg,
+                float* __restrict__ norms, int64_t n, int64_t nseg, float grad_scale, float l1,
+                float l2, float* __restrict__ l1l2_out) {
+  __shared__ float red[32];
+  const int64_t c0 = (int64_t)blockIdx.x * OPT_CHUNK;
+  const int64_t c1 = min(n, c0 + OPT_CHUNK);
+  int64_t seg = find_segment(seg_off, nseg, c0);
+  float l1_acc = 0.f, l2_acc = 0.f;
+  while (seg < nseg && seg_off[seg] < c1) {
+    const int64_t a = max(c0, seg_off[seg]), b = min(c1, seg_off[seg + 1]);
+    const bool reg = seg_reg[seg] != 0;
+    float ss = 0.f;
+    for (int64_t i = a + threadIdx.x; i < b; i += OPT_THREADS) {
+      float g = grads[i] * grad_scale;
+      if (reg) {
+        const float p = params[i];
+        g += 2.f * l2 * p + l1 * (p > 0.f ? 1.f : (p < 0.f ? -1.f : 0.f));
+        l1_acc += fabsf(p);
+        l2_acc += p * p;
+      }
+      grads[i] = g;
+      ss += g * g;
+    }
+    ss = block_sum(ss, red);
+    if (threadIdx.x == 0 && b > a) atomicAdd(norms + seg, ss);
+    ++seg;
+  }
+  if (l1l2_out) {
+    l1_acc = block_sum(l1_acc, red);
+    l2_acc = block_sum(l2_acc, red);
+    if (threadIdx.x == 0) {
+      if (l1_acc != 0.f) atomicAdd(l1l2_out, l1_acc);
+      if (l2_acc != 0.f) atomicAdd(l1l2_out + 1, l2_acc);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(OPT_THREADS)
+clip_adam_kernel(float* __restrict__ params, const float* __restrict__ grads, float* __restrict__ m,
+                 float* __restrict__ v, const int64_t* __restrict__ seg_off,
+                 const float* __restrict__ norms, int64_t n, int64_t nseg, float lr_t, float beta1,
+                 float beta2, float eps, float clip_norm) {
+  const int64_t c0 = (int64_t)blockIdx.x * OPT_CHUNK;
+  const int64_t c1 = min(n, c0 + OPT_CHUNK);
+  int64_t seg = find_segment(seg_off, nseg, c0);
+  while (seg < nseg && seg_off[seg] < c1) {
+    const int64_t a = max(c0, seg_off[seg]), b = min(c1, seg_off[seg + 1]);
+    float scale = 1.f;
+    if (clip_norm > 0.f) {
+      // tf.clip_by_norm: t * clip / max(||t||, clip)
+      const float nrm = sqrtf(norms[seg]);
+      scale = clip_norm / fmaxf(nrm, clip_norm);
+    }
+    for (int64_t i = a + threadIdx.x; i < b; i += OPT_THREADS) {
+      const float g = grads[i] * scale;
+      const float mi = beta1 * m[i] + (1.f - beta1) * g;
+      const float vi = beta2 * v[i] + (1.f - beta2) * g * g;
+      m[i] = mi;
+      v[i] = vi;
+      params[i] -= lr_t * mi / (sqrtf(vi) + eps);
+    }
+    ++seg;
+  }
+}
+
+}  // namespace nm
+
+using namespace nm;
+
+extern "C" {
+
+int nm_clip_adam_step(float* params, float* grads, float* m, float* v, const int64_t* seg_off,
+                      const uint8_t* seg_reg, float* norms, int64_t n, int64_t nseg, float grad_scale,
+                      float lr_t, float beta1, float beta2, float eps, float clip_norm, float l1,
+                      float l2, float* l1l2_out, void* stream) {
+  NM_REQUIRE(params && grads && m && v && seg_off && seg_reg && norms, NM_E_INVALID,
+             "nm_clip_adam_step: null pointer");
+  NM_REQUIRE(n > 0 && nseg > 0, NM_E_INVALID, "nm_clip_adam_step: bad sizes");
+  cudaStream_t s = (cudaStream_t)stream;
+  const unsigned blocks = (unsigned)ceil_div(n, OPT_CHUNK);
+  const bool need_pass1 =
+      clip_norm > 0.f || l1 != 0.f || l2 != 0.f || grad_scale != 1.f || l1l2_out != nullptr;
+  if (need_pass1) {
+    NM_CUDA_TRY(cudaMemsetAsync(norms, 0, sizeof(float) * nseg, s));
+    if (l1l2_out) NM_CUDA_TRY(cudaMemsetAsync(l1l2_out, 0, sizeof(float) * 2, s));
+    reg_norm_kernel<<<blocks, OPT_THREADS, 0, s>>>(params, grads, seg_off, seg_reg, norms, n, nseg,
+                                                   grad_scale, l1, l2, l1l2_out);
+    NM_LAUNCH_CHECK("nm_clip_adam_step(reg_norm)");
+  }
+  clip_adam_kernel<<<blocks, OPT_THREADS, 0, s>>>(params, grads, m, v, seg_off, norms, n, nseg, lr_t,
+                                                  beta1, beta2, eps, clip_norm);
+  NM_LAUNCH_CHECK("nm_clip_adam_step(adam)");
+  return NM_OK;
+}
+
+}  // extern "C"
