@@ -50,6 +50,8 @@ extern "C" {
 
 int nm_version(void);
 const char* nm_last_error(void);
+/* Number of CUDA kernels this library has launched in this process so far. */
+int64_t nm_launch_count(void);
 /* Fills SM count and compute capability of the current device. */
 int nm_device_info(int* sm_count, int* cc_major, int* cc_minor);
 
@@ -116,24 +118,32 @@ int nm_layernorm_bwd(const float* x, const float* gamma, const float* mean,
  * xproj is [B,T,3H] = [xg(2H) | xc(H)] per step.  lengths (int32 [B], may be
  * NULL) gives dynamic_rnn masking: for t >= len the output is 0 and the state
  * is carried.  reverse=1 walks t = len-1 .. 0 (tf.reverse_sequence semantics:
- * outputs land at their original time index).
- * Outputs: states [B,T,H]; final [B,H]; and, saved for the backward pass:
+ * outputs land at their original time index).  drop_mask ([B,T,H], already scaled
+ * by 1/keep_prob, may be NULL) multiplies each new state BEFORE it is emitted and fed
+ * back: the reference decoder's recurrence runs on the dropped-out cell output
+ * (decoders/decoder.py:288-289,333-334,351).
+ * Outputs: states [B,T,H]; raw_states [B,T,H] (cell outputs before drop_mask, the
+ * attention query of decoder.py:291-297; may be NULL); final [B,H]; and, saved for
+ * the backward pass:
  * gates [B,T,3H] = (r,u,c), hprev [B,T,H] = the state each step consumed,
  * rh [B,T,H] = r*hprev (the A operand of the candidate matmul). */
 int nm_gru_seq_fwd(const float* xproj, const float* Wgh, const float* Wch,
-                   const float* h0, const int32_t* lengths, int reverse,
-                   float* states, float* final_state, float* gates, float* hprev,
-                   float* rh, int64_t B, int64_t T, int64_t H, void* stream);
+                   const float* h0, const int32_t* lengths,
+                   const float* drop_mask, int reverse, float* states,
+                   float* raw_states, float* final_state, float* gates,
+                   float* hprev, float* rh, int64_t B, int64_t T, int64_t H,
+                   void* stream);
 /* Inputs: dstates [B,T,H] (may be NULL), dfinal [B,H] (may be NULL).
  * Outputs: dxproj [B,T,3H] (pre-activation grads = grads of xproj), dh0 [B,H]
  * (may be NULL).  Weight grads are NOT produced here: they are the hoisted
  * GEMMs hprev^T.dxproj[:, :2H] and rh^T.dxproj[:, 2H:], which the host issues
  * through nm_gemm.  work is a scratch buffer of 2*B*H floats. */
 int nm_gru_seq_bwd(const float* Wgh, const float* Wch, const int32_t* lengths,
-                   int reverse, const float* gates, const float* hprev,
-                   const float* dstates, const float* dfinal, float* dxproj,
-                   float* dh0, float* work, int64_t B, int64_t T, int64_t H,
-                   void* stream);
+                   const float* drop_mask, int reverse, const float* gates,
+                   const float* hprev, const float* dstates,
+                   const float* draw /* grad of raw_states, may be NULL */,
+                   const float* dfinal, float* dxproj, float* dh0, float* work,
+                   int64_t B, int64_t T, int64_t H, void* stream);
 
 /* ---- K4: Bahdanau attention -------------------------------------------------
  * Replaces Attention.attention (attention/feed_forward.py:125-166) for NQ query
@@ -181,7 +191,8 @@ int nm_log_softmax(const float* logits, const float* lse, float* logprobs,
                    int64_t M, int64_t V, int64_t ldl, void* stream);
 
 /* Fused vocabulary projection + loss statistics (K5 without materialising the
- * [M,V] logits): logits = X[M,K].W[K,V] + b (+ -1e9 at unk_index if >= 0) on
+ * [M,V] logits): logits = X[M,K].W + b (+ -1e9 at unk_index if >= 0), W stored
+ * [K,V] (transW=0) or [V,K] (transW=1: tied embeddings, decoders/autoregressive.py:231-233), on
  * tcgen05; writes lse, xent, argmax as nm_xent_fwd.  part is scratch of
  * nm_logits_xent_scratch(M,V) floats (16-byte aligned).  logits_out (may be NULL)
  * additionally receives the [M,V] logits (runtime_logits of the runner API).
@@ -189,14 +200,14 @@ int nm_log_softmax(const float* logits, const float* lse, float* logprobs,
  * of 16 bytes): callers then use nm_gemm + nm_xent_fwd. */
 int64_t nm_logits_xent_scratch(int64_t M, int64_t V);
 int nm_logits_xent_fwd(const float* X, int64_t ldx, const float* W, int64_t ldw,
-                       const float* b, int64_t unk_index, const int64_t* targets,
+                       int transW, const float* b, int64_t unk_index, const int64_t* targets,
                        const float* weights, float* lse, float* xent,
                        int64_t* argmax, float* part, float* logits_out,
                        int64_t ldl, int64_t M, int64_t V, int64_t K, void* stream);
 /* Recomputes the logits tile-by-tile and writes
  * dlogits = (softmax - onehot) * weights[m] * scale[0]   [M,V]. */
 int nm_logits_xent_bwd(const float* X, int64_t ldx, const float* W, int64_t ldw,
-                       const float* b, int64_t unk_index, const int64_t* targets,
+                       int transW, const float* b, int64_t unk_index, const int64_t* targets,
                        const float* weights, const float* lse, const float* scale,
                        float* dlogits, int64_t ldd, int64_t M, int64_t V,
                        int64_t K, void* stream);
@@ -237,12 +248,14 @@ int nm_beam_gather(const void* x, const int32_t* beam_ids, void* out, int64_t B,
  * with lr_t = lr*sqrt(1-b2^t)/(1-b1^t) computed by the caller.
  * The arena holds `n` floats split into `nseg` tensors: seg_off [nseg+1] int64
  * (device), seg_reg [nseg] uint8 (device).  norms [nseg] scratch (device).
- * grad_scale multiplies g first (1/N for data-parallel means, 1/k for delayed
- * updates).  l1l2_out [2] (device, may be NULL) receives sum|p|, sum p^2 over
+ * grad_scale multiplies g first (1/k for delayed updates); grad_denominator (a
+ * DEVICE scalar, may be NULL) then divides it: the all-reduced global token count of
+ * a data-parallel step, so the host never has to read it back.  l1l2_out [2] (device, may be NULL) receives sum|p|, sum p^2 over
  * regularised tensors (the "L1"/"L2" losses the trainer reports). */
 int nm_clip_adam_step(float* params, float* grads, float* m, float* v,
                       const int64_t* seg_off, const uint8_t* seg_reg, float* norms,
-                      int64_t n, int64_t nseg, float grad_scale, float lr_t,
+                      int64_t n, int64_t nseg, float grad_scale,
+                      const float* grad_denominator, float lr_t,
                       float beta1, float beta2, float eps, float clip_norm,
                       float l1, float l2, float* l1l2_out, void* stream);
 

@@ -7,6 +7,9 @@
 namespace nm {
 
 static thread_local char g_err[512] = "";
+static unsigned long long g_launches = 0;
+
+void count_launches(int64_t n) { __atomic_fetch_add(&g_launches, (unsigned long long)n, __ATOMIC_RELAXED); }
 
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -35,6 +38,8 @@ extern "C" {
 int nm_version(void) { return NM_ABI_VERSION; }
 
 const char* nm_last_error(void) { return nm::g_err; }
+
+int64_t nm_launch_count(void) { return (int64_t)__atomic_load_n(&nm::g_launches, __ATOMIC_RELAXED); }
 
 int nm_device_info(int* sm_count, int* cc_major, int* cc_minor) {
   NM_REQUIRE(sm_count && cc_major && cc_minor, NM_E_INVALID, "nm_device_info: null output");

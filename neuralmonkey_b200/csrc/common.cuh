@@ -10,6 +10,8 @@
 namespace nm {
 
 void set_error(const char* fmt, ...);
+// process-wide count of kernel launches issued by this library (bench.py's gpu_launches)
+void count_launches(int64_t n);
 
 #define NM_REQUIRE(cond, code, ...)   \
   do {                                \
@@ -21,6 +23,7 @@ void set_error(const char* fmt, ...);
 
 #define NM_LAUNCH_CHECK(name)                                                  \
   do {                                                                         \
+    nm::count_launches(1);                                                     \
     cudaError_t e__ = cudaGetLastError();                                      \
     if (e__ != cudaSuccess) {                                                  \
       nm::set_error("%s: %s", name, cudaGetErrorString(e__));                  \

@@ -36,6 +36,8 @@ struct GruCandEpi {
   float* hnext;        // &hprev[0, t_next, 0] or final_state
   int64_t hnext_stride;  // T*H or H
   const int32_t* lengths;
+  const float* drop_mask;  // [B,T,H] (already scaled by 1/keep_prob) or null
+  float* raw_states;       // [B,T,H] cell outputs before dropout, or null
   int64_t T, H, t;
   __device__ void operator()(int64_t b, int64_t n, float acc) const {
     const int64_t base3 = (b * T + t) * 3 * H;
@@ -44,7 +46,11 @@ struct GruCandEpi {
     const float u = gates[base3 + H + n];
     const float h = hprev[(b * T + t) * H + n];
     const bool live = (lengths == nullptr) || (t < (int64_t)lengths[b]);
-    const float hn = live ? (u * h + (1.f - u) * c) : h;
+    float hn = live ? (u * h + (1.f - u) * c) : h;
+    // the decoder feeds the DROPPED-OUT cell output back as the next state
+    // (decoders/decoder.py:288-289,333-334,351 of the reference)
+    if (raw_states) raw_states[(b * T + t) * H + n] = live ? hn : 0.f;
+    if (drop_mask && live) hn *= drop_mask[(b * T + t) * H + n];
     states[(b * T + t) * H + n] = live ? hn : 0.f;
     hnext[b * hnext_stride + n] = hn;
   }
@@ -54,7 +60,9 @@ struct GruCandEpi {
 // E1: gate gradients that need no matmul.  dh_in = carry (+ dstates[t] on live rows).
 __global__ void gru_bwd_gate_kernel(const float* __restrict__ gates, const float* __restrict__ hprev,
                                     const float* __restrict__ dstates, const float* __restrict__ dcarry,
-                                    const int32_t* __restrict__ lengths, float* __restrict__ dxproj,
+                                    const int32_t* __restrict__ lengths,
+                                    const float* __restrict__ drop_mask,
+                                    const float* __restrict__ draw, float* __restrict__ dxproj,
                                     float* __restrict__ dhp, int64_t B, int64_t T, int64_t H,
                                     int64_t t) {
   const int64_t total = B * H;
@@ -74,6 +82,8 @@ __global__ void gru_bwd_gate_kernel(const float* __restrict__ gates, const float
       continue;
     }
     if (dstates) dh += dstates[base1 + n];
+    if (drop_mask) dh *= drop_mask[base1 + n];
+    if (draw) dh += draw[base1 + n];  // gradient of the pre-dropout cell output
     const float du = dh * (h - c);
     const float dc = dh * (1.f - u);
     dxproj[base3 + 2 * H + n] = dc * (1.f - c * c);
@@ -118,9 +128,9 @@ using namespace nm;
 extern "C" {
 
 int nm_gru_seq_fwd(const float* xproj, const float* Wgh, const float* Wch, const float* h0,
-                   const int32_t* lengths, int reverse, float* states, float* final_state,
-                   float* gates, float* hprev, float* rh, int64_t B, int64_t T, int64_t H,
-                   void* stream) {
+                   const int32_t* lengths, const float* drop_mask, int reverse, float* states,
+                   float* raw_states, float* final_state, float* gates, float* hprev, float* rh,
+                   int64_t B, int64_t T, int64_t H, void* stream) {
   NM_REQUIRE(xproj && Wgh && Wch && states && final_state && gates && hprev && rh, NM_E_INVALID,
              "nm_gru_seq_fwd: null pointer");
   NM_REQUIRE(B > 0 && T > 0 && H > 0, NM_E_INVALID, "nm_gru_seq_fwd: bad sizes B=%lld T=%lld H=%lld",
@@ -142,15 +152,17 @@ int nm_gru_seq_fwd(const float* xproj, const float* Wgh, const float* Wch, const
     const bool last = (step == T - 1);
     const int64_t t_next = reverse ? t - 1 : t + 1;
     GruCandEpi e2{xproj, hprev, gates, states, last ? final_state : hprev + t_next * H,
-                  last ? H : T * H, lengths, T, H, t};
+                  last ? H : T * H, lengths, drop_mask, raw_states, T, H, t};
     simt_gemm_launch(rh + t * H, T * H, 1, Wch, H, 1, B, H, H, e2, s);
   }
+  count_launches(2 * T - 1);  // 2 kernels per step; NM_LAUNCH_CHECK counts the last one
   NM_LAUNCH_CHECK("nm_gru_seq_fwd");
   return NM_OK;
 }
 
-int nm_gru_seq_bwd(const float* Wgh, const float* Wch, const int32_t* lengths, int reverse,
-                   const float* gates, const float* hprev, const float* dstates, const float* dfinal,
+int nm_gru_seq_bwd(const float* Wgh, const float* Wch, const int32_t* lengths,
+                   const float* drop_mask, int reverse, const float* gates, const float* hprev,
+                   const float* dstates, const float* draw, const float* dfinal,
                    float* dxproj, float* dh0, float* work, int64_t B, int64_t T, int64_t H,
                    void* stream) {
   NM_REQUIRE(Wgh && Wch && gates && hprev && dxproj && work, NM_E_INVALID,
@@ -170,7 +182,7 @@ int nm_gru_seq_bwd(const float* Wgh, const float* Wch, const int32_t* lengths, i
   for (int64_t step = T - 1; step >= 0; --step) {
     const int64_t t = reverse ? T - 1 - step : step;
     gru_bwd_gate_kernel<<<(unsigned)blocks, threads, 0, s>>>(gates, hprev, dstates, dcarry, lengths,
-                                                            dxproj, dhp, B, T, H, t);
+                                                            drop_mask, draw, dxproj, dhp, B, T, H, t);
     // drh = dz_c . Wch^T   (op(B)(k=j, n=i) = Wch[i*H + j])
     GruBwdCandEpi g1{gates, hprev, lengths, dxproj, dhp, T, H, t};
     simt_gemm_launch(dxproj + t * 3 * H + 2 * H, T * 3 * H, 1, Wch, 1, H, B, H, H, g1, s);
@@ -180,6 +192,7 @@ int nm_gru_seq_bwd(const float* Wgh, const float* Wch, const int32_t* lengths, i
   }
   if (dh0)
     NM_CUDA_TRY(cudaMemcpyAsync(dh0, dcarry, sizeof(float) * B * H, cudaMemcpyDeviceToDevice, s));
+  count_launches(3 * T - 1);
   NM_LAUNCH_CHECK("nm_gru_seq_bwd");
   return NM_OK;
 }

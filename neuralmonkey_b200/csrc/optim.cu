@@ -25,9 +25,11 @@ __device__ __forceinline__ int64_t find_segment(const int64_t* __restrict__ seg_
 __global__ void __launch_bounds__(OPT_THREADS)
 reg_norm_kernel(const float* __restrict__ params, float* __restrict__ grads,
                 const int64_t* __restrict__ seg_off, const uint8_t* __restrict__ seg_reg,
-                float* __restrict__ norms, int64_t n, int64_t nseg, float grad_scale, float l1,
-                float l2, float* __restrict__ l1l2_out) {
+                float* __restrict__ norms, int64_t n, int64_t nseg, float grad_scale,
+                const float* __restrict__ grad_denominator, float l1, float l2,
+                float* __restrict__ l1l2_out) {
   __shared__ float red[32];
+  if (grad_denominator) grad_scale /= grad_denominator[0];
   const int64_t c0 = (int64_t)blockIdx.x * OPT_CHUNK;
   const int64_t c1 = min(n, c0 + OPT_CHUNK);
   int64_t seg = find_segment(seg_off, nseg, c0);
@@ -97,7 +99,7 @@ extern "C" {
 
 int nm_clip_adam_step(float* params, float* grads, float* m, float* v, const int64_t* seg_off,
                       const uint8_t* seg_reg, float* norms, int64_t n, int64_t nseg, float grad_scale,
-                      float lr_t, float beta1, float beta2, float eps, float clip_norm, float l1,
+                      const float* grad_denominator, float lr_t, float beta1, float beta2, float eps, float clip_norm, float l1,
                       float l2, float* l1l2_out, void* stream) {
   NM_REQUIRE(params && grads && m && v && seg_off && seg_reg && norms, NM_E_INVALID,
              "nm_clip_adam_step: null pointer");
@@ -105,12 +107,13 @@ int nm_clip_adam_step(float* params, float* grads, float* m, float* v, const int
   cudaStream_t s = (cudaStream_t)stream;
   const unsigned blocks = (unsigned)ceil_div(n, OPT_CHUNK);
   const bool need_pass1 =
-      clip_norm > 0.f || l1 != 0.f || l2 != 0.f || grad_scale != 1.f || l1l2_out != nullptr;
+      clip_norm > 0.f || l1 != 0.f || l2 != 0.f || grad_scale != 1.f || grad_denominator != nullptr ||
+      l1l2_out != nullptr;
   if (need_pass1) {
     NM_CUDA_TRY(cudaMemsetAsync(norms, 0, sizeof(float) * nseg, s));
     if (l1l2_out) NM_CUDA_TRY(cudaMemsetAsync(l1l2_out, 0, sizeof(float) * 2, s));
     reg_norm_kernel<<<blocks, OPT_THREADS, 0, s>>>(params, grads, seg_off, seg_reg, norms, n, nseg,
-                                                   grad_scale, l1, l2, l1l2_out);
+                                                   grad_scale, grad_denominator, l1, l2, l1l2_out);
     NM_LAUNCH_CHECK("nm_clip_adam_step(reg_norm)");
   }
   clip_adam_kernel<<<blocks, OPT_THREADS, 0, s>>>(params, grads, m, v, seg_off, norms, n, nseg, lr_t,

@@ -54,17 +54,17 @@ int64_t nm_logits_xent_scratch(int64_t M, int64_t V) {
   return M * ceil_div(V, TC_XENT_BN) * 4;
 }
 
-int nm_logits_xent_fwd(const float* X, int64_t ldx, const float* W, int64_t ldw, const float* b,
-                       int64_t unk_index, const int64_t* targets, const float* weights, float* lse,
+int nm_logits_xent_fwd(const float* X, int64_t ldx, const float* W, int64_t ldw, int transW,
+                       const float* b, int64_t unk_index, const int64_t* targets, const float* weights, float* lse,
                        float* xent, int64_t* argmax, float* part, float* logits_out, int64_t ldl,
                        int64_t M, int64_t V, int64_t K, void* stream) {
   NM_REQUIRE(X && W && lse && part, NM_E_INVALID, "nm_logits_xent_fwd: null pointer");
-  NM_REQUIRE(M > 0 && V > 0 && K > 0 && ldx >= K && ldw >= V, NM_E_INVALID,
+  NM_REQUIRE(M > 0 && V > 0 && K > 0 && ldx >= K && ldw >= (transW ? K : V), NM_E_INVALID,
              "nm_logits_xent_fwd: bad sizes");
   NM_REQUIRE(!logits_out || ldl >= V, NM_E_INVALID, "nm_logits_xent_fwd: ldl < V");
   NM_REQUIRE((reinterpret_cast<uintptr_t>(part) & 15) == 0, NM_E_INVALID,
              "nm_logits_xent_fwd: part must be 16-byte aligned");
-  NM_REQUIRE(tc_gemm_supported(0, 0, M, V, K, ldx, ldw, V, X, W, nullptr), NM_E_UNSUPPORTED,
+  NM_REQUIRE(tc_gemm_supported(0, transW, M, V, K, ldx, ldw, V, X, W, nullptr), NM_E_UNSUPPORTED,
              "nm_logits_xent_fwd: operands not TMA-addressable (use nm_gemm + nm_xent_fwd)");
   cudaStream_t s = (cudaStream_t)stream;
   TcEpilogue epi{};
@@ -75,7 +75,7 @@ int nm_logits_xent_fwd(const float* X, int64_t ldx, const float* W, int64_t ldw,
   epi.unk_index = unk_index;
   epi.targets = targets;
   epi.part = reinterpret_cast<float4*>(part);
-  const int rc = tc_gemm_launch(0, 0, M, V, K, X, ldx, W, ldw, epi, s);
+  const int rc = tc_gemm_launch(0, transW, M, V, K, X, ldx, W, ldw, epi, s);
   if (rc) return rc;
   const int64_t tiles_n = ceil_div(V, TC_XENT_BN);
   xent_combine_kernel<<<(unsigned)ceil_div(M, 8), 256, 0, s>>>(reinterpret_cast<const float4*>(part), M,
@@ -85,15 +85,15 @@ int nm_logits_xent_fwd(const float* X, int64_t ldx, const float* W, int64_t ldw,
   return NM_OK;
 }
 
-int nm_logits_xent_bwd(const float* X, int64_t ldx, const float* W, int64_t ldw, const float* b,
-                       int64_t unk_index, const int64_t* targets, const float* weights,
+int nm_logits_xent_bwd(const float* X, int64_t ldx, const float* W, int64_t ldw, int transW,
+                       const float* b, int64_t unk_index, const int64_t* targets, const float* weights,
                        const float* lse, const float* scale, float* dlogits, int64_t ldd, int64_t M,
                        int64_t V, int64_t K, void* stream) {
   NM_REQUIRE(X && W && targets && lse && scale && dlogits, NM_E_INVALID,
              "nm_logits_xent_bwd: null pointer");
-  NM_REQUIRE(M > 0 && V > 0 && K > 0 && ldx >= K && ldw >= V && ldd >= V, NM_E_INVALID,
+  NM_REQUIRE(M > 0 && V > 0 && K > 0 && ldx >= K && ldw >= (transW ? K : V) && ldd >= V, NM_E_INVALID,
              "nm_logits_xent_bwd: bad sizes");
-  NM_REQUIRE(tc_gemm_supported(0, 0, M, V, K, ldx, ldw, ldd, X, W, dlogits), NM_E_UNSUPPORTED,
+  NM_REQUIRE(tc_gemm_supported(0, transW, M, V, K, ldx, ldw, ldd, X, W, dlogits), NM_E_UNSUPPORTED,
              "nm_logits_xent_bwd: operands not TMA-addressable (use nm_gemm + nm_xent_bwd)");
   TcEpilogue epi{};
   epi.mode = TC_EPI_XENT_BWD;
@@ -105,7 +105,7 @@ int nm_logits_xent_bwd(const float* X, int64_t ldx, const float* W, int64_t ldw,
   epi.weights = weights;
   epi.lse = lse;
   epi.scale = scale;
-  return tc_gemm_launch(0, 0, M, V, K, X, ldx, W, ldw, epi, (cudaStream_t)stream);
+  return tc_gemm_launch(0, transW, M, V, K, X, ldx, W, ldw, epi, (cudaStream_t)stream);
 }
 
 }  // extern "C"

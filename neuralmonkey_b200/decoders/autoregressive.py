@@ -1,0 +1,406 @@
+"""Autoregressive decoder base (reference: neuralmonkey/decoders/autoregressive.py:28-584).
+
+What the reference expresses as two `tf.while_loop`s is split by what the data allows:
+
+* training (teacher forcing): every step's input is known up front, so subclasses compute
+  all output states in one batched pass (`train_output_states`) and the vocabulary
+  projection + cross-entropy is ONE fused tensor-core GEMM over all T*B rows
+  (`ops.logits_xent`) - the `[T,B,V]` logits are never materialised unless asked for;
+* runtime (greedy feedback): a host loop over steps, each step = subclass `next_state` +
+  fused logits/argmax kernel; histories are kept as lists and stacked once (the reference
+  re-concatenates every history at every step, tf_utils.py:222-235).
+"""
+from typing import Any, Callable, Dict, List, NamedTuple, Optional, Tuple
+
+import numpy as np
+import torch
+
+from neuralmonkey_b200 import ops, runtime
+from neuralmonkey_b200.decorators import tensor
+from neuralmonkey_b200.logging import warn
+from neuralmonkey_b200.model.model_part import ModelPart
+from neuralmonkey_b200.model.parameterized import InitializerSpecs
+from neuralmonkey_b200.model.sequence import EmbeddedSequence
+from neuralmonkey_b200.nn.utils import dropout
+from neuralmonkey_b200.params import uniform_initializer, zeros_initializer
+from neuralmonkey_b200.vocabulary import (END_TOKEN_INDEX, PAD_TOKEN_INDEX, START_TOKEN_INDEX,
+                                          UNK_TOKEN_INDEX, Vocabulary, pad_batch)
+
+# Loop-state tuples of the reference (autoregressive.py:28-113).  `other` carries the
+# subclass-specific part (RNNFeedables / TransformerFeedables ...).
+DecoderConstants = NamedTuple("DecoderConstants", [("train_inputs", Optional[torch.Tensor])])
+DecoderHistories = NamedTuple("DecoderHistories", [
+    ("logits", Any), ("output_states", Any), ("output_symbols", Any), ("output_mask", Any),
+    ("other", Any)])
+DecoderFeedables = NamedTuple("DecoderFeedables", [
+    ("step", int), ("finished", torch.Tensor), ("embedded_input", torch.Tensor), ("other", Any)])
+LoopState = NamedTuple("LoopState", [
+    ("histories", Any), ("constants", Any), ("feedables", Any)])
+
+
+class AutoregressiveDecoder(ModelPart):
+    # pylint: disable=too-many-arguments,too-many-instance-attributes
+    def __init__(self, name: str, vocabulary: Vocabulary, data_id: str, max_output_len: int,
+                 dropout_keep_prob: float = 1.0, embedding_size: int = None,
+                 embeddings_source: EmbeddedSequence = None, tie_embeddings: bool = False,
+                 label_smoothing: float = None, supress_unk: bool = False, reuse: ModelPart = None,
+                 save_checkpoint: str = None, load_checkpoint: str = None,
+                 initializers: InitializerSpecs = None) -> None:
+        ModelPart.__init__(self, name, reuse, save_checkpoint, load_checkpoint, initializers)
+        self.vocabulary = vocabulary
+        self.data_id = data_id
+        self.max_output_len = max_output_len
+        self.dropout_keep_prob = dropout_keep_prob
+        self._embedding_size = embedding_size
+        self.embeddings_source = embeddings_source
+        self.label_smoothing = label_smoothing
+        self.tie_embeddings = tie_embeddings
+        self.supress_unk = supress_unk
+        # callables so a BeamSearchDecoder can substitute beam-tiled tensors
+        self.encoder_states = lambda: []  # type: Callable[[], List[torch.Tensor]]
+        self.encoder_masks = lambda: []  # type: Callable[[], List[torch.Tensor]]
+        if self.max_output_len <= 0:
+            raise ValueError("Maximum sequence length must be a positive integer.")
+        if self._embedding_size is not None and self._embedding_size <= 0:
+            raise ValueError("Embedding size must be a positive integer.")
+        if self.dropout_keep_prob < 0.0 or self.dropout_keep_prob > 1.0:
+            raise ValueError("Dropout keep probability must be a real number in the interval [0,1].")
+        if self.label_smoothing:
+            raise NotImplementedError(
+                "label_smoothing is outside the B200 hot path built so far (SURVEY.md trap 14)")
+        self._train_ids_host = None  # type: Optional[torch.Tensor]
+
+    # -- static configuration ----------------------------------------------------------
+    @property
+    def embedding_size(self) -> int:
+        if self.embeddings_source is None:
+            if self._embedding_size is None:
+                raise ValueError(
+                    "You must specify either embedding size or the embedded sequence from which "
+                    "to reuse the embeddings (e.g. set 'embedding_size' or 'embeddings_source' "
+                    "parameter)")
+            return self._embedding_size
+        if self._embedding_size is not None:
+            warn("Overriding the embedding_size parameter with the size of the reused "
+                 "embeddings from the encoder.")
+        return self.embeddings_source.embedding_sizes[0]
+
+    @property
+    def output_dimension(self) -> int:
+        raise NotImplementedError("Abstract property")
+
+    def declare_variables(self) -> None:
+        if self.embeddings_source is not None:
+            self.embeddings_source.ensure_declared()
+        else:
+            self.declare("word_embeddings", [len(self.vocabulary), self.embedding_size])
+        if self.tie_embeddings:
+            if self.embedding_size != self.output_dimension:
+                raise ValueError("`embedding_size must be equal to the output_projection size when "
+                                 "using the `tie_embeddings` option")
+        else:
+            self.declare("state_to_word_W", [self.output_dimension, len(self.vocabulary)],
+                         uniform_initializer(-0.5, 0.5))
+            self.declare("state_to_word_b", [len(self.vocabulary)], zeros_initializer())
+
+    @property
+    def embedding_matrix(self) -> torch.Tensor:
+        if self.embeddings_source is not None:
+            return self.embeddings_source.embedding_matrix
+        return self.var("word_embeddings")
+
+    @property
+    def decoding_w(self) -> torch.Tensor:
+        """[output_dimension, V]; with tied embeddings the [V, E] matrix is used transposed
+        inside the GEMM (`_w_transposed`), never copied."""
+        if self.tie_embeddings:
+            return self.embedding_matrix
+        return self.var("state_to_word_W")
+
+    @property
+    def _w_transposed(self) -> bool:
+        return bool(self.tie_embeddings)
+
+    @property
+    def decoding_b(self) -> Optional[torch.Tensor]:
+        if self.tie_embeddings:
+            return None  # tf.zeros constant (autoregressive.py:241-242)
+        return self.var("state_to_word_b")
+
+    @property
+    def _unk_index(self) -> int:
+        return UNK_TOKEN_INDEX if self.supress_unk else -1
+
+    # -- feeding -------------------------------------------------------------------------
+    @property
+    def input_types(self) -> Dict[str, Any]:
+        return {self.data_id: str}
+
+    @property
+    def input_shapes(self) -> Dict[str, Any]:
+        return {self.data_id: [None, None]}
+
+    def feed_dict(self, dataset, train: bool = False) -> Dict[str, Any]:
+        fd = ModelPart.feed_dict(self, dataset, train)
+        sentences = dataset.maybe_get_series(self.data_id)
+        if sentences is None and train:
+            raise ValueError("When training, you must feed reference sentences")
+        self._train_ids_host = None
+        if sentences is not None:
+            padded = pad_batch(list(sentences), self.max_output_len, add_start_symbol=False,
+                               add_end_symbol=True)
+            self._train_ids_host = self.vocabulary.strings_to_indices(padded)
+            fd[self.data_id] = self._train_ids_host
+        return fd
+
+    def feed_ids(self, ids: Optional[torch.Tensor], batch_size: int, train: bool = False) -> None:
+        """Feed indexed references ([batch, time] int64 incl. </s>, or None)."""
+        self.reset_batch()
+        self.train_mode = bool(train)
+        self.batch_size = batch_size
+        self._train_ids_host = ids.cpu() if ids is not None else None
+
+    @tensor
+    def _train_targets_bm(self) -> torch.Tensor:
+        """[batch, time] int64 gold symbols incl. </s> (batch-major: the layout every training
+        kernel works in; the reference's time-major `train_inputs` is a view of it)."""
+        if self._train_ids_host is None:
+            raise ValueError("Decoder '{}' has no reference series fed".format(self.name))
+        return self._train_ids_host.contiguous().to(runtime.device(), non_blocking=True)
+
+    @tensor
+    def _train_mask_bm(self) -> torch.Tensor:
+        return (self._train_targets_bm != PAD_TOKEN_INDEX).to(torch.float32)
+
+    @tensor
+    def train_inputs(self) -> torch.Tensor:
+        """[time, batch] int64 (autoregressive.py:199-202)."""
+        return self._train_targets_bm.t()
+
+    @tensor
+    def train_mask(self) -> torch.Tensor:
+        return self._train_mask_bm.t()
+
+    @tensor
+    def _train_step_inputs_bm(self) -> torch.Tensor:
+        """[batch, time] symbols fed at each training step: <s>, then the gold symbol of the
+        previous step times `unfinished` (logits_to_symbols, autoregressive.py:461-475)."""
+        gold = self._train_ids_host.numpy()  # [B,T]
+        bsz, steps = gold.shape
+        finished = np.zeros(bsz, dtype=bool)
+        fed = np.empty((bsz, steps), dtype=np.int64)
+        fed[:, 0] = START_TOKEN_INDEX
+        for s in range(steps - 1):
+            nxt = gold[:, s] * (~finished)
+            finished |= (nxt == END_TOKEN_INDEX)
+            fed[:, s + 1] = nxt
+        return torch.from_numpy(fed).to(runtime.device(), non_blocking=True)
+
+    def embed_input_symbols(self, input_symbols: torch.Tensor) -> torch.Tensor:
+        embedded = ops.embed(input_symbols, self.embedding_matrix)
+        return dropout(embedded, self.dropout_keep_prob, self.train_mode)
+
+    # -- training tensors ------------------------------------------------------------------
+    @property
+    def _train_states_bm(self) -> torch.Tensor:
+        """[batch, time, output_dimension]: subclasses compute all steps in one pass."""
+        raise NotImplementedError("Abstract property")
+
+    @property
+    def train_output_states(self) -> torch.Tensor:
+        """[time, batch, output_dimension] (a transposed view)."""
+        return self._train_states_bm.transpose(0, 1)
+
+    @tensor
+    def _train_xent_result(self):
+        states = self._train_states_bm
+        bsz, steps, dim = states.shape
+        targets = self._train_targets_bm[:, :steps]
+        weights = self._train_mask_bm[:, :steps]
+        xent, lse, argmax, _ = ops.logits_xent(
+            states.reshape(bsz * steps, dim), self.decoding_w, self.decoding_b,
+            targets.reshape(-1), weights.reshape(-1), self._unk_index, self._w_transposed)
+        return xent.view(bsz, steps), lse.view(bsz, steps), argmax.view(bsz, steps)
+
+    @tensor
+    def train_xents(self) -> torch.Tensor:
+        """[batch, time] masked cross-entropies (autoregressive.py:292-310)."""
+        return self._train_xent_result[0]
+
+    @tensor
+    def train_loss(self) -> torch.Tensor:
+        """sum(xent) / sum(mask) (autoregressive.py:312-316)."""
+        return self._train_xent_result[0].sum() / self._train_mask_bm.sum()
+
+    @tensor
+    def train_xent_sum(self) -> torch.Tensor:
+        """Un-normalised sum of cross-entropies: what data-parallel ranks exchange."""
+        return self._train_xent_result[0].sum()
+
+    @property
+    def cost(self) -> torch.Tensor:
+        return self.train_loss
+
+    @tensor
+    def train_logits(self) -> torch.Tensor:
+        """[time, batch, V]; materialised only when a runner asks for it."""
+        states = self._train_states_bm.detach()
+        bsz, steps, dim = states.shape
+        _, _, _, logits = ops.logits_xent(
+            states.reshape(bsz * steps, dim), self.decoding_w.detach(),
+            self.decoding_b.detach() if self.decoding_b is not None else None,
+            self._train_targets_bm[:, :steps].reshape(-1),
+            self._train_mask_bm[:, :steps].reshape(-1), self._unk_index, self._w_transposed,
+            keep_logits=True)
+        return logits.view(bsz, steps, -1).transpose(0, 1)
+
+    @tensor
+    def train_logprobs(self) -> torch.Tensor:
+        logits = self.train_logits.transpose(0, 1).contiguous()  # [B,T,V]
+        lse = self._train_xent_result[1].detach()
+        return ops.log_softmax_from_lse(logits.reshape(-1, logits.shape[-1]),
+                                        lse.reshape(-1)).view(logits.shape).transpose(0, 1)
+
+    # -- runtime (greedy) loop ------------------------------------------------------------
+    def get_initial_feedables(self) -> DecoderFeedables:
+        dev = runtime.device()
+        go = torch.full((self.batch_size,), START_TOKEN_INDEX, dtype=torch.int64, device=dev)
+        return DecoderFeedables(
+            step=0, finished=torch.zeros(self.batch_size, dtype=torch.bool, device=dev),
+            embedded_input=self.embed_input_symbols(go), other=None)
+
+    def get_initial_histories(self) -> DecoderHistories:
+        return DecoderHistories(logits=[], output_states=[], output_symbols=[], output_mask=[],
+                                other=None)
+
+    def get_initial_loop_state(self) -> LoopState:
+        return LoopState(histories=self.get_initial_histories(),
+                         constants=DecoderConstants(train_inputs=None),
+                         feedables=self.get_initial_feedables())
+
+    def next_state(self, loop_state: LoopState) -> Tuple[torch.Tensor, Any, Any]:
+        """One decoder step: (output state [batch, output_dimension], feedables.other,
+        histories.other)."""
+        raise NotImplementedError("Abstract method.")
+
+    def state_to_logits(self, state: torch.Tensor, keep_logits: bool = True):
+        """logits (+ -1e9 on <unk>), their logsumexp and first-index argmax, in one fused
+        kernel (autoregressive.py:450-459,470)."""
+        bsz = state.shape[0]
+        dev = state.device
+        dummy_t = torch.zeros(bsz, dtype=torch.int64, device=dev)
+        dummy_w = torch.zeros(bsz, dtype=torch.float32, device=dev)
+        _, lse, argmax, logits = ops.logits_xent(state, self.decoding_w, self.decoding_b, dummy_t,
+                                                 dummy_w, self._unk_index, self._w_transposed,
+                                                 keep_logits=keep_logits)
+        return logits, lse, argmax
+
+    def body(self, loop_state: LoopState) -> LoopState:
+        """get_body(train_mode=False) (autoregressive.py:482-517)."""
+        feedables = loop_state.feedables
+        histories = loop_state.histories
+        output_state, dec_other, hist_other = self.next_state(loop_state)
+        logits, _lse, argmax = self.state_to_logits(output_state)
+        next_symbols = argmax * (~feedables.finished).to(torch.int64)
+        finished = feedables.finished | (next_symbols == END_TOKEN_INDEX)
+        next_feedables = DecoderFeedables(
+            step=feedables.step + 1, finished=finished,
+            embedded_input=self.embed_input_symbols(next_symbols), other=dec_other)
+        histories.logits.append(logits)
+        histories.output_states.append(output_state)
+        histories.output_symbols.append(next_symbols)
+        histories.output_mask.append(~finished)
+        next_histories = histories._replace(other=hist_other)
+        return LoopState(histories=next_histories, constants=loop_state.constants,
+                         feedables=next_feedables)
+
+    def finalize_loop(self, final_loop_state: LoopState, train_mode: bool) -> None:
+        """Post-loop hook (attention histories etc.)."""
+
+    @tensor
+    def runtime_loop_result(self) -> LoopState:
+        """decoding_loop(train_mode=False) (autoregressive.py:532-562)."""
+        with torch.no_grad():
+            loop_state = self.get_initial_loop_state()
+            step = 0
+            # loop_continue_criterion: not all finished and step < max_output_len (:425-437);
+            # the all-finished test is one device->host flag per step
+            while step < self.max_output_len:
+                loop_state = self.body(loop_state)
+                step += 1
+                if bool(loop_state.feedables.finished.all()):
+                    break
+            self.finalize_loop(loop_state, False)
+        return loop_state
+
+    @tensor
+    def runtime_logits(self) -> torch.Tensor:
+        return torch.stack(self.runtime_loop_result.histories.logits, 0)
+
+    @tensor
+    def runtime_output_states(self) -> torch.Tensor:
+        return torch.stack(self.runtime_loop_result.histories.output_states, 0)
+
+    @tensor
+    def runtime_mask(self) -> torch.Tensor:
+        return torch.stack(self.runtime_loop_result.histories.output_mask, 0)
+
+    @tensor
+    def runtime_symbols(self) -> torch.Tensor:
+        """[time, batch] greedy symbols (argmax over the full vocabulary, PAD once finished)."""
+        return torch.stack(self.runtime_loop_result.histories.output_symbols, 0)
+
+    @tensor
+    def decoded(self) -> torch.Tensor:
+        """argmax over logits[:, :, 1:] + 1 (autoregressive.py:341-349)."""
+        logits = self.runtime_logits
+        steps, bsz, vocab = logits.shape
+        dev = logits.device
+        lse = torch.empty(steps * bsz, device=dev, dtype=torch.float32)
+        arg = torch.empty(steps * bsz, device=dev, dtype=torch.int64)
+        from neuralmonkey_b200 import lib
+        # columns 1..V-1 of every row: same buffer, pointer advanced by one float, ld = V
+        lib.call("nm_xent_fwd", lib.ptr(logits) + 4, None, None, lib.ptr(lse), None, lib.ptr(arg),
+                 steps * bsz, vocab - 1, vocab, lib.stream())
+        return (arg + 1).view(steps, bsz)
+
+    @tensor
+    def _runtime_lse(self) -> torch.Tensor:
+        logits = self.runtime_logits
+        steps, bsz, vocab = logits.shape
+        dev = logits.device
+        lse = torch.empty(steps * bsz, device=dev, dtype=torch.float32)
+        from neuralmonkey_b200 import lib
+        lib.call("nm_xent_fwd", lib.ptr(logits), None, None, lib.ptr(lse), None, None, steps * bsz,
+                 vocab, vocab, lib.stream())
+        return lse
+
+    @tensor
+    def runtime_logprobs(self) -> torch.Tensor:
+        logits = self.runtime_logits
+        return ops.log_softmax_from_lse(logits.reshape(-1, logits.shape[-1]),
+                                        self._runtime_lse).view(logits.shape)
+
+    @tensor
+    def runtime_xents(self) -> torch.Tensor:
+        """[batch, min_time] (autoregressive.py:351-366)."""
+        logits = self.runtime_logits
+        targets = self.train_inputs
+        min_time = min(targets.shape[0], logits.shape[0])
+        bsz, vocab = logits.shape[1], logits.shape[2]
+        dev = logits.device
+        lg = logits[:min_time].reshape(min_time * bsz, vocab)
+        lse = torch.empty(min_time * bsz, device=dev, dtype=torch.float32)
+        xent = torch.empty(min_time * bsz, device=dev, dtype=torch.float32)
+        tg = targets[:min_time].reshape(-1).contiguous()
+        wt = self.train_mask[:min_time].reshape(-1).contiguous()
+        from neuralmonkey_b200 import lib
+        lib.call("nm_xent_fwd", lib.ptr(lg), lib.ptr(tg), lib.ptr(wt), lib.ptr(lse), lib.ptr(xent),
+                 None, min_time * bsz, vocab, vocab, lib.stream())
+        return xent.view(min_time, bsz).t()
+
+    @tensor
+    def runtime_loss(self) -> torch.Tensor:
+        """sum(runtime_xents) / sum(runtime_mask) - the mask excludes the </s> step
+        (autoregressive.py:368-371,510-511)."""
+        return self.runtime_xents.sum() / self.runtime_mask.to(torch.float32).sum()

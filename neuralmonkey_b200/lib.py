@@ -100,9 +100,40 @@ def ptr(t: Optional[torch.Tensor]) -> Optional[int]:
     return t.data_ptr()
 
 
+_profile = None  # type: Optional[Dict[str, list]]
+
+
+def profile_start() -> None:
+    """Record a CUDA-event pair around every C-ABI call (bench.py's per-kernel breakdown)."""
+    global _profile
+    _profile = {}
+
+
+def profile_stop() -> Dict[str, Dict[str, float]]:
+    """Stop recording; returns {entry point: {"calls": n, "ms": total device time}}."""
+    global _profile
+    rec, _profile = _profile, None
+    torch.cuda.synchronize()
+    out = {}
+    for name, pairs in (rec or {}).items():
+        out[name] = {"calls": len(pairs), "ms": sum(a.elapsed_time(b) for a, b in pairs)}
+    return out
+
+
+def launch_count() -> int:
+    return int(load().nm_launch_count())
+
+
 def call(name: str, *args) -> None:
     lib = load()
-    rc = getattr(lib, name)(*args)
+    if _profile is not None:
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        rc = getattr(lib, name)(*args)
+        ev1.record()
+        _profile.setdefault(name, []).append((ev0, ev1))
+    else:
+        rc = getattr(lib, name)(*args)
     if rc != 0:
         msg = lib.nm_last_error().decode("utf-8", "replace")
         if rc < 0:

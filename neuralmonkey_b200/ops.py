@@ -1,0 +1,557 @@
+"""Differentiable host-side wrappers over the libnmb200 C ABI.
+
+torch.autograd only *sequences* the calls: every forward and every backward is a
+libnmb200 kernel launched on the current CUDA stream through ctypes.  Parameters
+may carry an ``nm_grad`` attribute (a view into the flat gradient arena of
+``neuralmonkey_b200.params.ParameterArena``); the backward passes then accumulate
+weight gradients straight into that arena (GEMM epilogue ``beta = 1``) and return
+``None`` to autograd, so no torch kernels run on the weight-gradient path.
+"""
+from typing import Optional, Tuple
+
+import torch
+
+from neuralmonkey_b200 import lib
+from neuralmonkey_b200.lib import call, ptr
+
+_GEMM_BACKEND = lib.GEMM_AUTO
+
+
+def set_gemm_backend(name: str) -> None:
+    """'auto' (tcgen05 when TMA-addressable), 'simt' (exact fp32) or 'tc'."""
+    global _GEMM_BACKEND
+    _GEMM_BACKEND = {"auto": lib.GEMM_AUTO, "simt": lib.GEMM_SIMT, "tc": lib.GEMM_TC}[name]
+
+
+def gemm_backend() -> int:
+    return _GEMM_BACKEND
+
+
+def _f32(t: torch.Tensor) -> torch.Tensor:
+    if t.dtype != torch.float32:
+        raise TypeError("expected float32, got {}".format(t.dtype))
+    return t
+
+
+def _rows(t: torch.Tensor) -> Tuple[torch.Tensor, int]:
+    """2-D view with unit inner stride; returns (tensor, leading dimension)."""
+    if t.dim() != 2:
+        raise ValueError("expected a 2-D tensor")
+    if t.stride(1) != 1 and t.size(1) != 1:
+        t = t.contiguous()
+    ld = t.stride(0) if t.size(0) > 1 else max(t.size(1), t.stride(0))
+    if ld < t.size(1):
+        t = t.contiguous()
+        ld = t.size(1)
+    return t, ld
+
+
+def gemm(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor, trans_a: bool = False,
+         trans_b: bool = False, bias: Optional[torch.Tensor] = None, act: Optional[str] = None,
+         beta: float = 0.0, backend: Optional[int] = None) -> torch.Tensor:
+    """out = act(op(a) @ op(b) + bias) + beta*out, all through nm_gemm (no torch math)."""
+    a, lda = _rows(_f32(a))
+    b, ldb = _rows(_f32(b))
+    if out.dim() != 2 or (out.stride(1) != 1 and out.size(1) != 1):
+        raise ValueError("gemm output must be a 2-D tensor with unit inner stride")
+    ldc = out.stride(0) if out.size(0) > 1 else max(out.size(1), out.stride(0))
+    m, k = (a.size(1), a.size(0)) if trans_a else (a.size(0), a.size(1))
+    kb, n = (b.size(1), b.size(0)) if trans_b else (b.size(0), b.size(1))
+    if k != kb or out.size(0) != m or out.size(1) != n:
+        raise ValueError("gemm shape mismatch: op(a) [{},{}] op(b) [{},{}] out {}".format(
+            m, k, kb, n, tuple(out.shape)))
+    call("nm_gemm", int(trans_a), int(trans_b), m, n, k, ptr(a), lda, ptr(b), ldb, ptr(out), ldc,
+         ptr(bias), lib.NM_ACT[act], float(beta),
+         _GEMM_BACKEND if backend is None else backend, lib.stream())
+    return out
+
+
+def _sink(t: torch.Tensor) -> Optional[torch.Tensor]:
+    return getattr(t, "nm_grad", None)
+
+
+def _weight_grad(a: torch.Tensor, b: torch.Tensor, trans_a: bool, trans_b: bool,
+                 sink: Optional[torch.Tensor], shape) -> Optional[torch.Tensor]:
+    """op(a) @ op(b) accumulated into `sink` (returns None) or returned as a new tensor."""
+    if sink is not None:
+        gemm(a, b, sink, trans_a, trans_b, beta=1.0)
+        return None
+    out = torch.empty(shape, device=a.device, dtype=torch.float32)
+    return gemm(a, b, out, trans_a, trans_b)
+
+
+def _bias_grad(dy: torch.Tensor, sink: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
+    dy2, ld = _rows(dy)
+    if sink is not None:
+        call("nm_colsum", ptr(dy2), dy2.size(0), dy2.size(1), ld, ptr(sink), 1, lib.stream())
+        return None
+    out = torch.empty(dy2.size(1), device=dy.device, dtype=torch.float32)
+    call("nm_colsum", ptr(dy2), dy2.size(0), dy2.size(1), ld, ptr(out), 0, lib.stream())
+    return out
+
+
+# ---------------------------------------------------------------------------
+# K1 embedding
+# ---------------------------------------------------------------------------
+class _Embed(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, ids, table, mask):
+        ids = ids.contiguous()
+        n = ids.numel()
+        v, e = table.shape
+        out = torch.empty(tuple(ids.shape) + (e,), device=table.device, dtype=torch.float32)
+        mask_c = mask.contiguous() if mask is not None else None
+        call("nm_embed_fwd", ptr(ids), ptr(table), ptr(mask_c), ptr(out), n, e, v, lib.stream())
+        ctx.save_for_backward(ids, mask_c)
+        ctx.shape = (v, e)
+        ctx.sink = _sink(table)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        ids, mask = ctx.saved_tensors
+        v, e = ctx.shape
+        dout = dout.contiguous()
+        if ctx.sink is not None:
+            dtable, ret = ctx.sink, None
+        else:
+            dtable = torch.zeros(v, e, device=dout.device, dtype=torch.float32)
+            ret = dtable
+        call("nm_embed_bwd", ptr(ids), ptr(dout), ptr(mask), ptr(dtable), ids.numel(), e, v,
+             lib.stream())
+        return None, ret, None
+
+
+def embed(ids: torch.Tensor, table: torch.Tensor, mask: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """table[ids] * mask[..., None]  (model/sequence.py:181-191; autoregressive.py:269-272)."""
+    return _Embed.apply(ids, table, mask)
+
+
+# ---------------------------------------------------------------------------
+# dense projection
+# ---------------------------------------------------------------------------
+class _Linear(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, w, b, act):
+        shape = x.shape
+        x2 = x.reshape(-1, shape[-1])
+        y = torch.empty(x2.size(0), w.size(1), device=x.device, dtype=torch.float32)
+        gemm(x2, w, y, bias=b, act=act)
+        ctx.save_for_backward(x2, w, y if act is not None else None)
+        ctx.act = act
+        ctx.has_bias = b is not None
+        ctx.sinks = (_sink(w), _sink(b) if b is not None else None)
+        ctx.in_shape = shape
+        return y.view(tuple(shape[:-1]) + (w.size(1),))
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2, w, y = ctx.saved_tensors
+        dy2 = dy.reshape(-1, dy.shape[-1])
+        dy2, _ = _rows(dy2)
+        if ctx.act is not None:
+            dpre = torch.empty_like(y)
+            dyc = dy2.contiguous()
+            call("nm_act_bwd", ptr(y), ptr(dyc), ptr(dpre), y.numel(), lib.NM_ACT[ctx.act],
+                 lib.stream())
+        else:
+            dpre = dy2
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            dx = torch.empty(x2.shape, device=dy.device, dtype=torch.float32)
+            gemm(dpre, w, dx, trans_b=True)
+            dx = dx.view(ctx.in_shape)
+        if ctx.needs_input_grad[1]:
+            dw = _weight_grad(x2, dpre, True, False, ctx.sinks[0], w.shape)
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            db = _bias_grad(dpre, ctx.sinks[1])
+        return dx, dw, db, None
+
+
+def linear(x: torch.Tensor, w: torch.Tensor, b: Optional[torch.Tensor] = None,
+           act: Optional[str] = None) -> torch.Tensor:
+    """act(x @ w + b) over the last dim; w is [in, out] (tf.layers.dense layout)."""
+    return _Linear.apply(x, w, b, act)
+
+
+class _Maxout(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, z):
+        z2 = z.reshape(-1, z.shape[-1]).contiguous()
+        m, two_o = z2.shape
+        o = two_o // 2
+        y = torch.empty(m, o, device=z.device, dtype=torch.float32)
+        which = torch.empty(m, o, device=z.device, dtype=torch.uint8)
+        call("nm_maxout_fwd", ptr(z2), ptr(y), ptr(which), m, o, lib.stream())
+        ctx.save_for_backward(which)
+        ctx.in_shape = z.shape
+        return y.view(tuple(z.shape[:-1]) + (o,))
+
+    @staticmethod
+    def backward(ctx, dy):
+        (which,) = ctx.saved_tensors
+        m, o = which.shape
+        dy2 = dy.reshape(m, o).contiguous()
+        dz = torch.empty(m, 2 * o, device=dy.device, dtype=torch.float32)
+        call("nm_maxout_bwd", ptr(dy2), ptr(which), ptr(dz), m, o, lib.stream())
+        return dz.view(ctx.in_shape)
+
+
+def maxout(z: torch.Tensor) -> torch.Tensor:
+    """y[..., j] = max(z[..., j], z[..., O + j])  (nn/projection.py:7-35 as executed)."""
+    return _Maxout.apply(z)
+
+
+# ---------------------------------------------------------------------------
+# K7 layer norm
+# ---------------------------------------------------------------------------
+class _LayerNorm(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, gamma, beta, eps):
+        x2 = x.reshape(-1, x.shape[-1]).contiguous()
+        m, d = x2.shape
+        y = torch.empty_like(x2)
+        mean = torch.empty(m, device=x.device, dtype=torch.float32)
+        rstd = torch.empty(m, device=x.device, dtype=torch.float32)
+        call("nm_layernorm_fwd", ptr(x2), ptr(gamma), ptr(beta), ptr(y), ptr(mean), ptr(rstd), m, d,
+             float(eps), lib.stream())
+        ctx.save_for_backward(x2, gamma, mean, rstd)
+        ctx.sinks = (_sink(gamma), _sink(beta))
+        ctx.in_shape = x.shape
+        return y.view(x.shape)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2, gamma, mean, rstd = ctx.saved_tensors
+        m, d = x2.shape
+        dy2 = dy.reshape(m, d).contiguous()
+        dx = torch.empty_like(x2)
+        sg, sb = ctx.sinks
+        dg = sg if sg is not None else torch.zeros(d, device=dy.device, dtype=torch.float32)
+        db = sb if sb is not None else torch.zeros(d, device=dy.device, dtype=torch.float32)
+        call("nm_layernorm_bwd", ptr(x2), ptr(gamma), ptr(mean), ptr(rstd), ptr(dy2), ptr(dx), ptr(dg),
+             ptr(db), m, d, lib.stream())
+        return (dx.view(ctx.in_shape), None if sg is not None else dg,
+                None if sb is not None else db, None)
+
+
+def layer_norm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor,
+               eps: float = 1e-6) -> torch.Tensor:
+    """tf_utils.layer_norm (tf_utils.py:189-219)."""
+    return _LayerNorm.apply(x, gamma, beta, eps)
+
+
+# ---------------------------------------------------------------------------
+# K2 GRU layer (input projection hoisted onto the tensor cores + recurrent kernels)
+# ---------------------------------------------------------------------------
+class _GRULayer(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, wg, bg, wc, bc, h0, lengths, reverse, drop_mask):
+        # x [B,T,E]; wg [E+H,2H], bg [2H]; wc [E+H,H], bc [H]   (TF GRUCell kernels)
+        bsz, t, e = x.shape
+        h = wc.size(1)
+        x2 = x.reshape(bsz * t, e)
+        xproj = torch.empty(bsz * t, 3 * h, device=x.device, dtype=torch.float32)
+        gemm(x2, wg[:e], xproj[:, :2 * h], bias=bg)
+        gemm(x2, wc[:e], xproj[:, 2 * h:], bias=bc)
+        states = torch.empty(bsz, t, h, device=x.device, dtype=torch.float32)
+        raw = torch.empty_like(states) if drop_mask is not None else None
+        final = torch.empty(bsz, h, device=x.device, dtype=torch.float32)
+        gates = torch.empty(bsz, t, 3 * h, device=x.device, dtype=torch.float32)
+        hprev = torch.empty(bsz, t, h, device=x.device, dtype=torch.float32)
+        rh = torch.empty(bsz, t, h, device=x.device, dtype=torch.float32)
+        h0c = h0.contiguous() if h0 is not None else None
+        dm = drop_mask.contiguous() if drop_mask is not None else None
+        call("nm_gru_seq_fwd", ptr(xproj), ptr(wg[e:]), ptr(wc[e:]), ptr(h0c), ptr(lengths), ptr(dm),
+             int(reverse), ptr(states), ptr(raw), ptr(final), ptr(gates), ptr(hprev), ptr(rh), bsz, t,
+             h, lib.stream())
+        ctx.save_for_backward(x2, wg, wc, lengths, gates, hprev, rh, dm)
+        ctx.dims = (bsz, t, e, h)
+        ctx.reverse = reverse
+        ctx.has_h0 = h0 is not None
+        ctx.sinks = (_sink(wg), _sink(bg), _sink(wc), _sink(bc))
+        return states, final, (raw if raw is not None else states)
+
+    @staticmethod
+    def backward(ctx, dstates, dfinal, draw):
+        x2, wg, wc, lengths, gates, hprev, rh, dm = ctx.saved_tensors
+        bsz, t, e, h = ctx.dims
+        dev = x2.device
+        dstates = dstates.contiguous() if dstates is not None else None
+        dfinal = dfinal.contiguous() if dfinal is not None else None
+        if draw is not None:
+            if dm is None:  # raw aliases states: autograd delivers the two gradients separately
+                dstates = draw.contiguous() if dstates is None else dstates + draw
+                draw = None
+            else:
+                draw = draw.contiguous()
+        dxproj = torch.empty(bsz * t, 3 * h, device=dev, dtype=torch.float32)
+        dh0 = torch.empty(bsz, h, device=dev, dtype=torch.float32) if ctx.has_h0 else None
+        work = torch.empty(2 * bsz * h, device=dev, dtype=torch.float32)
+        call("nm_gru_seq_bwd", ptr(wg[e:]), ptr(wc[e:]), ptr(lengths), ptr(dm), int(ctx.reverse),
+             ptr(gates), ptr(hprev), ptr(dstates), ptr(draw), ptr(dfinal), ptr(dxproj), ptr(dh0),
+             ptr(work), bsz, t, h, lib.stream())
+        dzg, dzc = dxproj[:, :2 * h], dxproj[:, 2 * h:]
+        sg, sbg, sc, sbc = ctx.sinks
+        # weight gradients: rows [:E] from x, rows [E:] from the recurrent operand
+        dwg = sg if sg is not None else torch.empty_like(wg)
+        dwc = sc if sc is not None else torch.empty_like(wc)
+        beta = 1.0 if sg is not None else 0.0
+        hp2, rh2 = hprev.view(bsz * t, h), rh.view(bsz * t, h)
+        gemm(x2, dzg, dwg[:e], trans_a=True, beta=beta)
+        gemm(hp2, dzg, dwg[e:], trans_a=True, beta=beta)
+        beta = 1.0 if sc is not None else 0.0
+        gemm(x2, dzc, dwc[:e], trans_a=True, beta=beta)
+        gemm(rh2, dzc, dwc[e:], trans_a=True, beta=beta)
+        dbg = _bias_grad(dzg, sbg)
+        dbc = _bias_grad(dzc, sbc)
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dx = torch.empty(bsz * t, e, device=dev, dtype=torch.float32)
+            gemm(dzg, wg[:e], dx, trans_b=True)
+            gemm(dzc, wc[:e], dx, trans_b=True, beta=1.0)
+            dx = dx.view(bsz, t, e)
+        return (dx, None if sg is not None else dwg, dbg, None if sc is not None else dwc, dbc,
+                dh0, None, None, None)
+
+
+def gru_layer(x: torch.Tensor, gates_kernel: torch.Tensor, gates_bias: torch.Tensor,
+              cand_kernel: torch.Tensor, cand_bias: torch.Tensor,
+              h0: Optional[torch.Tensor] = None, lengths: Optional[torch.Tensor] = None,
+              reverse: bool = False,
+              drop_mask: Optional[torch.Tensor] = None):
+    """dynamic_rnn over a TF-1.12 GRUCell (encoders/recurrent.py:71-110).
+
+    Returns (outputs [B,T,H], final state [B,H], raw outputs [B,T,H] = outputs before
+    `drop_mask`); with `lengths` (int32) the outputs past
+    each length are zero and the state is carried, with `reverse` the sequence is walked
+    backwards inside its length (tf.reverse_sequence semantics)."""
+    return _GRULayer.apply(x, gates_kernel, gates_bias, cand_kernel, cand_bias, h0, lengths, reverse,
+                           drop_mask)
+
+
+# ---------------------------------------------------------------------------
+# K4 Bahdanau attention
+# ---------------------------------------------------------------------------
+class _Bahdanau(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, keys, values, mask, qproj, v, bias):
+        bsz, tx, a = keys.shape
+        c = values.size(2)
+        nq = qproj.size(1)
+        keys, values, qproj = keys.contiguous(), values.contiguous(), qproj.contiguous()
+        mask_c = mask.contiguous() if mask is not None else None
+        dev = keys.device
+        energies = torch.empty(bsz, nq, tx, device=dev, dtype=torch.float32)
+        weights = torch.empty(bsz, nq, tx, device=dev, dtype=torch.float32)
+        ctxv = torch.empty(bsz, nq, c, device=dev, dtype=torch.float32)
+        call("nm_bahdanau_fwd", ptr(keys), ptr(values), ptr(mask_c), ptr(qproj), ptr(v), ptr(bias),
+             ptr(energies), ptr(weights), ptr(ctxv), bsz, tx, nq, a, c, lib.stream())
+        ctx.save_for_backward(keys, values, mask_c, qproj, v, energies, weights)
+        ctx.sinks = (_sink(v), _sink(bias))
+        ctx.mark_non_differentiable(weights)
+        return ctxv, weights
+
+    @staticmethod
+    def backward(ctx, dctx, _dweights):
+        keys, values, mask, qproj, v, energies, weights = ctx.saved_tensors
+        bsz, tx, a = keys.shape
+        c = values.size(2)
+        nq = qproj.size(1)
+        dev = keys.device
+        dctx = dctx.contiguous()
+        dkeys = torch.empty_like(keys)
+        dvalues = torch.empty_like(values)
+        dq = torch.empty_like(qproj)
+        sv, sb = ctx.sinks
+        dv = sv if sv is not None else torch.zeros(a, device=dev, dtype=torch.float32)
+        db = sb if sb is not None else torch.zeros(1, device=dev, dtype=torch.float32)
+        work = torch.empty(bsz * nq * tx, device=dev, dtype=torch.float32)
+        call("nm_bahdanau_bwd", ptr(keys), ptr(values), ptr(mask), ptr(qproj), ptr(v), ptr(energies),
+             ptr(weights), ptr(dctx), ptr(dkeys), ptr(dvalues), ptr(dq), ptr(dv), ptr(db), ptr(work),
+             bsz, tx, nq, a, c, lib.stream())
+        return (dkeys, dvalues, None, dq, None if sv is not None else dv,
+                None if sb is not None else db)
+
+
+def bahdanau_attention(keys: torch.Tensor, values: torch.Tensor, mask: Optional[torch.Tensor],
+                       qproj: torch.Tensor, v: torch.Tensor,
+                       bias: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Attention.attention (attention/feed_forward.py:125-166) for all query steps at once.
+
+    keys [B,Tx,A], values [B,Tx,C], mask [B,Tx] or None, qproj [B,NQ,A], v [A], bias [1].
+    Returns (contexts [B,NQ,C], weights [B,NQ,Tx])."""
+    return _Bahdanau.apply(keys, values, mask, qproj, v, bias)
+
+
+# ---------------------------------------------------------------------------
+# K5/K6 vocabulary projection + cross-entropy
+# ---------------------------------------------------------------------------
+class _LogitsXent(torch.autograd.Function):
+    """xent[m] = (logsumexp(x@W+b) - (x@W+b)[target]) * weights[m]; also lse and argmax."""
+
+    @staticmethod
+    def forward(ctx, x, w, b, targets, weights, unk_index, trans_w, keep_logits):
+        x2 = x.reshape(-1, x.shape[-1])
+        x2, ldx = _rows(x2)
+        m, k = x2.shape
+        v = w.size(0) if trans_w else w.size(1)
+        dev = x.device
+        targets = targets.reshape(-1).contiguous()
+        weights = weights.reshape(-1).contiguous()
+        lse = torch.empty(m, device=dev, dtype=torch.float32)
+        xent = torch.empty(m, device=dev, dtype=torch.float32)
+        argmax = torch.empty(m, device=dev, dtype=torch.int64)
+        w2, ldw = _rows(w)
+        logits = torch.empty(m, v, device=dev, dtype=torch.float32) if keep_logits else None
+        fused = (_GEMM_BACKEND != lib.GEMM_SIMT and
+                 lib.load().nm_gemm_uses_tc(0, int(trans_w), m, v, k, ldx, ldw, v) == 1 and
+                 x2.data_ptr() % 16 == 0 and w2.data_ptr() % 16 == 0)
+        if fused:
+            part = torch.empty(lib.load().nm_logits_xent_scratch(m, v), device=dev,
+                               dtype=torch.float32)
+            call("nm_logits_xent_fwd", ptr(x2), ldx, ptr(w2), ldw, int(trans_w), ptr(b), unk_index,
+                 ptr(targets), ptr(weights), ptr(lse), ptr(xent), ptr(argmax), ptr(part),
+                 ptr(logits), v, m, v, k, lib.stream())
+        else:
+            if logits is None:
+                logits = torch.empty(m, v, device=dev, dtype=torch.float32)
+            bias_eff = b
+            if unk_index >= 0:  # fold the -1e9 <unk> mask into the bias vector ([V], host plumbing)
+                bias_eff = b.detach().clone() if b is not None else torch.zeros(
+                    v, device=dev, dtype=torch.float32)
+                bias_eff[unk_index] += -1e9
+            gemm(x2, w2, logits, trans_b=trans_w, bias=bias_eff)
+            call("nm_xent_fwd", ptr(logits), ptr(targets), ptr(weights), ptr(lse), ptr(xent),
+                 ptr(argmax), m, v, v, lib.stream())
+        ctx.save_for_backward(x2, w2, b, targets, weights, lse, None if fused else logits)
+        ctx.cfg = (fused, unk_index, trans_w, x.shape)
+        ctx.sinks = (_sink(w), _sink(b) if b is not None else None)
+        ctx.mark_non_differentiable(lse, argmax)
+        if keep_logits:
+            ctx.mark_non_differentiable(logits)
+            return xent, lse, argmax, logits
+        return xent, lse, argmax, None
+
+    @staticmethod
+    def backward(ctx, dxent, _dlse, _dargmax, _dlogits):
+        x2, w2, b, targets, weights, lse, logits = ctx.saved_tensors
+        fused, unk_index, trans_w, in_shape = ctx.cfg
+        m, k = x2.shape
+        v = w2.size(0) if trans_w else w2.size(1)
+        dev = x2.device
+        # fold the upstream per-row gradient into the row weights (tiny [M] product)
+        roww = torch.empty(m, device=dev, dtype=torch.float32)
+        ones = torch.ones(1, device=dev, dtype=torch.float32)
+        torch.mul(weights, dxent.reshape(-1), out=roww)
+        if fused:
+            dlogits = torch.empty(m, v, device=dev, dtype=torch.float32)
+            _, ldx = _rows(x2)
+            _, ldw = _rows(w2)
+            call("nm_logits_xent_bwd", ptr(x2), ldx, ptr(w2), ldw, int(trans_w), ptr(b), unk_index,
+                 ptr(targets), ptr(roww), ptr(lse), ptr(ones), ptr(dlogits), v, m, v, k, lib.stream())
+        else:
+            dlogits = logits  # in place
+            call("nm_xent_bwd", ptr(logits), ptr(targets), ptr(roww), ptr(lse), ptr(ones),
+                 ptr(dlogits), m, v, v, lib.stream())
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            dx = torch.empty(m, k, device=dev, dtype=torch.float32)
+            gemm(dlogits, w2, dx, trans_b=not trans_w)
+            dx = dx.view(in_shape)
+        if ctx.needs_input_grad[1]:
+            if trans_w:   # w is [V,K]: dW = dlogits^T @ x
+                dw = _weight_grad(dlogits, x2, True, False, ctx.sinks[0], w2.shape)
+            else:         # w is [K,V]: dW = x^T @ dlogits
+                dw = _weight_grad(x2, dlogits, True, False, ctx.sinks[0], w2.shape)
+        if b is not None and ctx.needs_input_grad[2]:
+            db = _bias_grad(dlogits, ctx.sinks[1])
+        return dx, dw, db, None, None, None, None, None
+
+
+def logits_xent(x: torch.Tensor, w: torch.Tensor, b: Optional[torch.Tensor], targets: torch.Tensor,
+                weights: torch.Tensor, unk_index: int = -1, trans_w: bool = False,
+                keep_logits: bool = False):
+    """Vocabulary projection + masked cross-entropy (decoders/autoregressive.py:288-316,450-459).
+
+    Returns (xent [M], lse [M], argmax [M] int64, logits [M,V] or None)."""
+    return _LogitsXent.apply(x, w, b, targets, weights, unk_index, trans_w, keep_logits)
+
+
+# ---------------------------------------------------------------------------
+# K8 multi-head attention core
+# ---------------------------------------------------------------------------
+class _MHA(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, q, k, v, key_mask, causal, heads):
+        bsz, tq, d = q.shape
+        tk = k.size(1)
+        dh = d // heads
+        q, k, v = q.contiguous(), k.contiguous(), v.contiguous()
+        mask_c = key_mask.contiguous() if key_mask is not None else None
+        out = torch.empty_like(q)
+        probs = torch.empty(bsz, heads, tq, tk, device=q.device, dtype=torch.float32)
+        call("nm_mha_fwd", ptr(q), ptr(k), ptr(v), ptr(mask_c), int(causal), ptr(out), ptr(probs), bsz,
+             tq, tk, heads, dh, lib.stream())
+        ctx.save_for_backward(q, k, v, mask_c, probs)
+        ctx.cfg = (causal, heads)
+        ctx.mark_non_differentiable(probs)
+        return out, probs
+
+    @staticmethod
+    def backward(ctx, dout, _dprobs):
+        q, k, v, mask, probs = ctx.saved_tensors
+        causal, heads = ctx.cfg
+        bsz, tq, d = q.shape
+        tk = k.size(1)
+        dout = dout.contiguous()
+        dq, dk, dv = torch.empty_like(q), torch.empty_like(k), torch.empty_like(v)
+        work = torch.empty_like(probs)
+        call("nm_mha_bwd", ptr(q), ptr(k), ptr(v), ptr(mask), int(causal), ptr(probs), ptr(dout),
+             ptr(dq), ptr(dk), ptr(dv), ptr(work), bsz, tq, tk, heads, d // heads, lib.stream())
+        return dq, dk, dv, None, None, None
+
+
+def mha_core(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, key_mask: Optional[torch.Tensor],
+             causal: bool, heads: int) -> Tuple[torch.Tensor, torch.Tensor]:
+    """softmax(mask(q/sqrt(dh) k^T)) v per head (attention/scaled_dot_product.py:184-214)."""
+    return _MHA.apply(q, k, v, key_mask, causal, heads)
+
+
+# ---------------------------------------------------------------------------
+# non-differentiable helpers
+# ---------------------------------------------------------------------------
+def log_softmax_from_lse(logits: torch.Tensor, lse: torch.Tensor) -> torch.Tensor:
+    m, v = logits.shape
+    out = torch.empty_like(logits)
+    call("nm_log_softmax", ptr(logits), ptr(lse), ptr(out), m, v, logits.stride(0), lib.stream())
+    return out
+
+
+def beam_step(logprobs: torch.Tensor, logprob_sum: torch.Tensor, lengths: torch.Tensor,
+              finished: torch.Tensor, alpha: float):
+    """One BeamSearchDecoder step (beam_search_decoder.py:440-496).  Returns
+    (scores, word_ids i64, beam_ids i32, logprob_sum', lengths' i32, finished' u8)."""
+    bsz, k, v = logprobs.shape
+    dev = logprobs.device
+    scores = torch.empty(bsz, k, device=dev, dtype=torch.float32)
+    words = torch.empty(bsz, k, device=dev, dtype=torch.int64)
+    beams = torch.empty(bsz, k, device=dev, dtype=torch.int32)
+    lsum = torch.empty(bsz, k, device=dev, dtype=torch.float32)
+    lens = torch.empty(bsz, k, device=dev, dtype=torch.int32)
+    fin = torch.empty(bsz, k, device=dev, dtype=torch.uint8)
+    scratch = torch.empty(lib.load().nm_beam_scratch(bsz, k, v), device=dev, dtype=torch.int32)
+    call("nm_beam_step", ptr(logprobs.contiguous()), ptr(logprob_sum.contiguous()),
+         ptr(lengths.contiguous()), ptr(finished.contiguous()), float(alpha), ptr(scores), ptr(words),
+         ptr(beams), ptr(lsum), ptr(lens), ptr(fin), ptr(scratch), bsz, k, v, lib.stream())
+    return scores, words, beams, lsum, lens, fin
+
+
+def beam_gather(x: torch.Tensor, beam_ids: torch.Tensor, bsz: int, k: int) -> torch.Tensor:
+    """gather_flat (tf_utils.py:106-131) on a [B*k, ...] tensor."""
+    x = x.contiguous()
+    out = torch.empty_like(x)
+    row_bytes = (x.numel() // (bsz * k)) * x.element_size()
+    call("nm_beam_gather", ptr(x), ptr(beam_ids.contiguous()), ptr(out), bsz, k, row_bytes,
+         lib.stream())
+    return out

@@ -1,0 +1,55 @@
+"""Greedy runner (reference: neuralmonkey/runners/runner.py:18-90).
+
+The reference fetches `runtime_logprobs [T,B,V]` to the host and argmaxes there
+(runner.py:49); with one session that is exactly the decoder's own greedy symbols, which
+the fused logits kernel already produced on the device, so only `[T,B]` int64 crosses
+PCIe.  With `num_sessions > 1` the ensemble path of the reference (log-sum-exp of the
+sessions' log-probs) is not built: trainers and this runner are single-session.
+"""
+from typing import Any, Callable, Dict, List, Optional
+
+import numpy as np
+
+from neuralmonkey_b200.decoders.autoregressive import AutoregressiveDecoder
+from neuralmonkey_b200.runners.base_runner import BaseRunner
+
+Postprocessor = Optional[Callable[[List[List[str]]], List[List[str]]]]
+
+
+class GreedyRunner(BaseRunner):
+    class Executable(BaseRunner.Executable):
+        def execute(self) -> None:
+            runner = self.executor
+            decoder = runner.decoder
+            if self.num_sessions != 1:
+                raise NotImplementedError("GreedyRunner ensembles (num_sessions > 1) are not built")
+            # argmax over the full vocabulary of the (single-session) log-probs == the greedy
+            # feedback symbols without the `* unfinished` masking (runner.py:45-49)
+            logits = decoder.runtime_logits
+            steps, bsz, vocab = logits.shape
+            import torch
+            from neuralmonkey_b200 import lib
+            arg = torch.empty(steps * bsz, device=logits.device, dtype=torch.int64)
+            lse = torch.empty(steps * bsz, device=logits.device, dtype=torch.float32)
+            lib.call("nm_xent_fwd", lib.ptr(logits), None, None, lib.ptr(lse), None, lib.ptr(arg),
+                     steps * bsz, vocab, vocab, lib.stream())
+            symbols = arg.view(steps, bsz).cpu().numpy()
+            train_loss = runtime_loss = 0.0
+            if self.compute_losses:
+                train_loss = float(decoder.train_loss)
+                runtime_loss = float(decoder.runtime_loss)
+            decoded_tokens = runner.vocabulary.vectors_to_sentences(symbols)
+            if runner.postprocess is not None:
+                decoded_tokens = runner.postprocess(decoded_tokens)
+            self.set_runner_result(outputs=decoded_tokens, losses=[train_loss, runtime_loss],
+                                   size=bsz)
+
+    def __init__(self, output_series: str, decoder: AutoregressiveDecoder,
+                 postprocess: Postprocessor = None) -> None:
+        BaseRunner.__init__(self, output_series, decoder)
+        self.postprocess = postprocess
+        self.vocabulary = self.decoder.vocabulary
+
+    @property
+    def loss_names(self) -> List[str]:
+        return ["train_xent", "runtime_xent"]

@@ -1,0 +1,37 @@
+"""Process-wide runtime context: the CUDA device this rank drives and the arena."""
+import os
+from typing import Optional
+
+import torch
+
+from neuralmonkey_b200.params import ParameterArena
+
+_device = None  # type: Optional[torch.device]
+_arena = None  # type: Optional[ParameterArena]
+
+
+def device() -> torch.device:
+    """cuda:LOCAL_RANK.  There is no CPU execution path: model tensors live on the GPU."""
+    global _device
+    if _device is None:
+        if not torch.cuda.is_available():
+            raise RuntimeError(
+                "neuralmonkey_b200 needs a CUDA device (sm_100a); no CPU fallback exists")
+        local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        torch.cuda.set_device(local_rank)
+        _device = torch.device("cuda", local_rank)
+    return _device
+
+
+def arena() -> ParameterArena:
+    """The arena model parts declare their variables in (one per experiment)."""
+    global _arena
+    if _arena is None:
+        _arena = ParameterArena()
+    return _arena
+
+
+def reset() -> None:
+    """Start a fresh experiment (new arena)."""
+    global _arena
+    _arena = None

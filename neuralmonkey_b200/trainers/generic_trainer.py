@@ -1,0 +1,149 @@
+"""Generic trainer (reference: neuralmonkey/trainers/generic_trainer.py:20-250).
+
+One `train_step()` =
+    zero the flat gradient buffer
+    -> backward of the objectives (weight gradients accumulate straight into the arena)
+    -> [data parallel: one all-reduce of gradients + loss sum + token count]
+    -> nm_clip_adam_step: L1/L2 terms, per-tensor clip_by_norm, TF-Adam (K13)
+with no device->host synchronisation inside; the losses are returned as device tensors.
+"""
+import math
+import re
+from typing import Any, Dict, List, Optional, Sequence, Set
+
+import torch
+
+from neuralmonkey_b200 import distributed, lib, runtime, tf
+from neuralmonkey_b200.lib import call, ptr
+from neuralmonkey_b200.logging import warn
+from neuralmonkey_b200.model.feedable import Feedable
+from neuralmonkey_b200.runners.base_runner import ExecutionResult, GraphExecutor
+from neuralmonkey_b200.trainers.objective import Objective
+
+BIAS_REGEX = re.compile(r"[Bb]ias")
+
+
+class GenericTrainer(GraphExecutor, Feedable):
+    @staticmethod
+    def default_optimizer():
+        return tf.AdamOptimizer(learning_rate=1e-4)
+
+    # pylint: disable=too-many-arguments
+    def __init__(self, objectives: Sequence[Objective], l1_weight: float = 0.0,
+                 l2_weight: float = 0.0, clip_norm: float = None, optimizer=None,
+                 var_scopes: List[str] = None, var_collection: str = None) -> None:
+        GraphExecutor.__init__(self, {obj.decoder for obj in objectives})
+        Feedable.__init__(self)
+        self.objectives = objectives
+        self.l1_weight = l1_weight
+        self.l2_weight = l2_weight
+        self.clip_norm = clip_norm
+        self.var_scopes = var_scopes
+        self.var_collection = var_collection
+        self.optimizer = optimizer if optimizer is not None else self.default_optimizer()
+        self.global_step = 0
+        self.batches_per_update = 1
+        if var_scopes is not None:
+            raise NotImplementedError(
+                "var_scopes: per-scope training is outside the B200 hot path built so far")
+        if clip_norm is not None and clip_norm <= 0.0:
+            raise ValueError("clip_norm must be positive")
+
+    @property
+    def var_list(self) -> List[str]:
+        return list(runtime.arena().train_names)
+
+    # -- one optimisation step ---------------------------------------------------------------
+    def _backward(self) -> Dict[str, torch.Tensor]:
+        """Backward of the weighted objectives into the arena; fills the stat slots.
+        Returns the device tensors reported as losses."""
+        arena = runtime.arena()
+        exact = None
+        if len(self.objectives) == 1 and self.objectives[0].gradients is None:
+            exact = self.objectives[0].loss_sum_and_count
+        if exact is not None:
+            # token-mean loss: differentiate the SUM, divide by the (global) count in the
+            # optimizer kernel -> N ranks reproduce the single-GPU token mean exactly
+            loss_sum, count = exact
+            w = self.objectives[0].weight
+            (loss_sum if w is None else loss_sum * w).backward()
+            arena.stats[0].copy_(loss_sum.detach())
+            arena.stats[1].copy_(count.detach())
+            return {"exact": True}
+        total = None
+        for obj in self.objectives:
+            if obj.gradients is not None:
+                raise NotImplementedError("objectives with explicit gradients (RL) are out of scope")
+            w = 1.0 if obj.weight is None else obj.weight
+            term = obj.loss * w
+            total = term if total is None else total + term
+        total.backward()
+        return {"exact": False}
+
+    def train_step(self, apply_update: bool = True, grad_scale: float = 1.0,
+                   zero_grad: bool = True) -> Dict[str, Any]:
+        """Run one step on the batch currently fed to the model parts (train mode)."""
+        arena = runtime.arena()
+        if zero_grad:
+            arena.zero_grad()
+        info = self._backward()
+        losses = [obj.loss.detach() for obj in self.objectives]
+        denominator = None
+        world = distributed.world_size()
+        if apply_update:
+            if info["exact"]:
+                distributed.all_reduce_sum(arena.allreduce_view)
+                denominator = arena.stats[1:2]
+                losses = [arena.stats[0] / arena.stats[1]]
+            elif world > 1:
+                distributed.all_reduce_sum(arena.allreduce_view)
+                grad_scale = grad_scale / world
+            self.apply_gradients(grad_scale, denominator)
+        return {"losses": losses, "l1l2": self._l1l2}
+
+    def apply_gradients(self, grad_scale: float = 1.0,
+                        denominator: Optional[torch.Tensor] = None) -> None:
+        arena = runtime.arena()
+        opt = self.optimizer
+        if getattr(opt, "lazy", False):
+            warn("LazyAdamOptimizer: using dense Adam updates (rows without gradient also decay)")
+        self.global_step += 1
+        t = self.global_step
+        lr = opt.lr_at(t)
+        lr_t = lr * math.sqrt(1.0 - opt.beta2 ** t) / (1.0 - opt.beta1 ** t)
+        if not hasattr(self, "_l1l2_buf"):
+            self._l1l2_buf = torch.zeros(2, device=arena.params.device, dtype=torch.float32)
+        n = arena.trainable_size
+        call("nm_clip_adam_step", ptr(arena.params), ptr(arena.grads), ptr(arena.adam_m),
+             ptr(arena.adam_v), ptr(arena.seg_off), ptr(arena.seg_reg), ptr(arena.seg_norms), n,
+             len(arena.train_names), float(grad_scale), ptr(denominator), float(lr_t),
+             float(opt.beta1), float(opt.beta2), float(opt.epsilon),
+             float(self.clip_norm) if self.clip_norm else 0.0, float(self.l1_weight),
+             float(self.l2_weight), ptr(self._l1l2_buf), lib.stream())
+
+    @property
+    def _l1l2(self) -> torch.Tensor:
+        return getattr(self, "_l1l2_buf", None)
+
+    # -- executor protocol (runners/base_runner.py) --------------------------------------------
+    def get_executable(self, compute_losses: bool = True, summaries: bool = True,
+                       num_sessions: int = 1):
+        if num_sessions != 1:
+            raise ValueError("Trainer only supports execution in a single session")
+        return _TrainExecutable(self)
+
+
+class _TrainExecutable:
+    def __init__(self, trainer: GenericTrainer) -> None:
+        self.trainer = trainer
+        self.result = None  # type: Optional[ExecutionResult]
+
+    def execute(self) -> None:
+        out = self.trainer.train_step()
+        names = [obj.name for obj in self.trainer.objectives] + ["L1", "L2"]
+        vals = [float(l) for l in out["losses"]]
+        l1l2 = out["l1l2"]
+        vals += [float(l1l2[0]), float(l1l2[1])] if l1l2 is not None else [0.0, 0.0]
+        self.result = ExecutionResult(outputs={}, losses=dict(zip(names, vals)),
+                                      size=self.trainer.objectives[0].decoder.batch_size,
+                                      summaries=[])

@@ -1,0 +1,483 @@
+"""CPU oracle: an op-for-op restatement of the Neural Monkey hot path (torch-CPU).
+
+TEST INFRASTRUCTURE ONLY.  Nothing under neuralmonkey_b200/ may import this
+module; only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+--impl reference legs do, and only as the checker or the timed CPU baseline.
+
+PARITY UNPINNED.  The reference (ufal/neuralmonkey @ 8b14652) evaluates this path
+with TensorFlow 1.12, which cannot be installed here (Python 3.12, no network),
+and its own tests hold no numeric golden vectors for the path.
+This file therefore restates the reference graph from its source, following the
+files cited at each function, plus the published TF-1.12 semantics of the ops
+they call:
+
+  * tf.contrib.rnn.GRUCell (TF 1.12 rnn_cell_impl.py):
+        gate_inputs = matmul(concat([x, h], 1), gates/kernel) + gates/bias
+        r, u = split(sigmoid(gate_inputs), 2)
+        candidate = matmul(concat([x, r * h], 1), candidate/kernel) + candidate/bias
+        c = tanh(candidate);  new_h = u * h + (1 - u) * c
+  * tf.nn.dynamic_rnn with sequence_length: for t >= length the output is zero and
+    the state is copied through; bidirectional_dynamic_rnn runs the backward cell on
+    tf.reverse_sequence(x, lengths) and reverses its outputs back.
+  * tf.nn.softmax / log_softmax over the last axis; tf.argmax and tf.nn.top_k
+    return the lowest index among equal values.
+  * tf.contrib.seq2seq.sequence_loss(average_across_* = False):
+        sparse_softmax_cross_entropy_with_logits(targets, logits) * weights
+  * tf.train.AdamOptimizer:  lr_t = lr * sqrt(1 - b2^t) / (1 - b1^t)
+        m = b1 m + (1-b1) g ; v = b2 v + (1-b2) g^2 ; var -= lr_t * m / (sqrt(v) + eps)
+  * tf.clip_by_norm(t, c) = t * c / max(||t||_2, c)
+
+Everything runs in the dtype of the parameters passed in (float32 to mirror the
+reference, float64 to measure kernel error); gradients come from torch.autograd
+over the same restated graph.
+"""
+import math
+from typing import Callable, Dict, List, Optional, Tuple
+
+import torch
+
+PAD, START, END, UNK = 0, 1, 2, 3   # neuralmonkey/vocabulary.py:19-29
+INF = 1e9                           # decoders/beam_search_decoder.py:43
+
+Params = Dict[str, torch.Tensor]
+
+
+# ---------------------------------------------------------------------------
+# primitives
+# ---------------------------------------------------------------------------
+def layer_norm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor,
+               eps: float = 1e-6) -> torch.Tensor:
+    """neuralmonkey/tf_utils.py:189-219."""
+    mean = x.mean(dim=-1, keepdim=True)
+    variance = ((x - mean) ** 2).mean(dim=-1, keepdim=True)
+    norm_x = (x - mean) * torch.rsqrt(variance + eps)
+    return norm_x * gamma + beta
+
+
+def gru_cell(x: torch.Tensor, h: torch.Tensor, wg: torch.Tensor, bg: torch.Tensor,
+             wc: torch.Tensor, bc: torch.Tensor) -> torch.Tensor:
+    """tf.contrib.rnn.GRUCell as used by OrthoGRUCell (nn/ortho_gru_cell.py:44-53)."""
+    gates = torch.sigmoid(torch.cat([x, h], 1) @ wg + bg)
+    size = h.shape[1]
+    r, u = gates[:, :size], gates[:, size:]
+    c = torch.tanh(torch.cat([x, r * h], 1) @ wc + bc)
+    return u * h + (1 - u) * c
+
+
+def dynamic_gru(x: torch.Tensor, lengths: Optional[torch.Tensor], wg, bg, wc, bc,
+                h0: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+    """tf.nn.dynamic_rnn(GRUCell, x, sequence_length=lengths)."""
+    bsz, steps, _ = x.shape
+    size = wc.shape[1]
+    h = h0 if h0 is not None else x.new_zeros(bsz, size)
+    outs = []
+    for t in range(steps):
+        new_h = gru_cell(x[:, t], h, wg, bg, wc, bc)
+        if lengths is not None:
+            live = (t < lengths).to(x.dtype).unsqueeze(1)
+            outs.append(new_h * live)
+            h = new_h * live + h * (1 - live)
+        else:
+            outs.append(new_h)
+            h = new_h
+    return torch.stack(outs, 1), h
+
+
+def reverse_sequence(x: torch.Tensor, lengths: torch.Tensor) -> torch.Tensor:
+    """tf.reverse_sequence(x, lengths, seq_axis=1)."""
+    out = x.clone()
+    for b in range(x.shape[0]):
+        n = int(lengths[b])
+        if n > 0:
+            out[b, :n] = x[b, :n].flip(0)
+    return out
+
+
+def bidirectional_gru(x, lengths, fw: Tuple, bw: Tuple) -> Tuple[torch.Tensor, torch.Tensor]:
+    """rnn_layer(..., direction='bidirectional') (encoders/recurrent.py:82-95)."""
+    out_fw, fin_fw = dynamic_gru(x, lengths, *fw)
+    out_bw_rev, fin_bw = dynamic_gru(reverse_sequence(x, lengths), lengths, *bw)
+    out_bw = reverse_sequence(out_bw_rev, lengths)
+    return torch.cat([out_fw, out_bw], 2), torch.cat([fin_fw, fin_bw], 1)
+
+
+def sentence_mask(ids: torch.Tensor, dtype) -> torch.Tensor:
+    """vocabulary.sentence_mask (vocabulary.py:357-358): id != PAD as float."""
+    return (ids != PAD).to(dtype)
+
+
+# ---------------------------------------------------------------------------
+# SentenceEncoder (encoders/recurrent.py:113-314, model/sequence.py:170-199)
+# ---------------------------------------------------------------------------
+def sentence_encoder(p: Params, prefix: str, ids: torch.Tensor) -> Dict[str, torch.Tensor]:
+    emb = p[prefix + "_input/embedding_matrix_0"]
+    dtype = emb.dtype
+    mask = sentence_mask(ids, dtype)
+    lengths = mask.sum(1).to(torch.int64)
+    embedded = emb[ids] * mask.unsqueeze(-1)          # sequence.py:181-191
+    cell = prefix + "/rnn_0_bidirectional/bidirectional_rnn/{}/OrthoGRUCell/"
+    names = ("gates/kernel", "gates/bias", "candidate/kernel", "candidate/bias")
+    fw = tuple(p[cell.format("fw") + n] for n in names)
+    bw = tuple(p[cell.format("bw") + n] for n in names)
+    states, final = bidirectional_gru(embedded, lengths, fw, bw)
+    gamma, beta = p[prefix + "/LayerNorm/gamma"], p[prefix + "/LayerNorm/beta"]
+    # include_final_layer_norm=True: both through the SAME LayerNorm variables (recurrent.py:215-216)
+    return {"temporal_states": layer_norm(states, gamma, beta),
+            "output": layer_norm(final, gamma, beta),
+            "temporal_mask": mask}
+
+
+# ---------------------------------------------------------------------------
+# Attention (attention/feed_forward.py:47-166)
+# ---------------------------------------------------------------------------
+def bahdanau_precompute(p: Params, prefix: str, states: torch.Tensor) -> torch.Tensor:
+    """hidden_features: 1x1 conv == states @ key_projection (feed_forward.py:111-118)."""
+    return states @ p[prefix + "/attn_key_projection"]
+
+
+def bahdanau_step(p: Params, prefix: str, query: torch.Tensor, hidden: torch.Tensor,
+                  states: torch.Tensor, mask: Optional[torch.Tensor]):
+    """Attention.attention (feed_forward.py:125-166)."""
+    y = query @ p[prefix + "/Attention/attn_query_projection"] + p[prefix + "/attn_projection_bias"]
+    v = p[prefix + "/attn_similarity_v"]
+    energies = (v * torch.tanh(hidden + y.unsqueeze(1))).sum(-1) + p[prefix + "/attn_bias"]
+    if mask is None:
+        weights = torch.softmax(energies, dim=-1)
+    else:
+        weights_all = torch.softmax(energies, dim=-1) * mask
+        norm = weights_all.sum(1, keepdim=True) + 1e-8
+        weights = weights_all / norm
+    context = (weights.unsqueeze(-1) * states).sum(1)
+    return context, weights
+
+
+# ---------------------------------------------------------------------------
+# Decoder (decoders/decoder.py:226-358, autoregressive.py:381-519)
+# ---------------------------------------------------------------------------
+class RNNDecoderSpec:
+    """Static configuration of decoders.decoder.Decoder for the oracle."""
+
+    def __init__(self, prefix: str, att_prefix: str, max_output_len: int,
+                 output_projection: str = "tanh", supress_unk: bool = False) -> None:
+        self.prefix = prefix
+        self.att_prefix = att_prefix
+        self.max_output_len = max_output_len
+        self.output_projection = output_projection  # "tanh" | "maxout"
+        self.supress_unk = supress_unk
+
+
+def decoder_initial_state(p: Params, spec: RNNDecoderSpec, enc_output: torch.Tensor) -> torch.Tensor:
+    """linear_encoder_projection (encoder_projection.py:47-73); dropout off."""
+    pre = spec.prefix + "/initial_state/encoders_projection/"
+    return enc_output @ p[pre + "kernel"] + p[pre + "bias"]
+
+
+def output_projection(p: Params, spec: RNNDecoderSpec, cell_output, embedded_input, context):
+    """nonlinear_output / maxout_output (output_projection.py:115-160, nn/projection.py:7-35)."""
+    cat = torch.cat([cell_output, embedded_input, context], 1)
+    if spec.output_projection == "tanh":
+        pre = spec.prefix + "/attention_decoder/dense/"
+        return torch.tanh(cat @ p[pre + "kernel"] + p[pre + "bias"])
+    pre = spec.prefix + "/attention_decoder/MaxoutProjection/MaxoutProjection/"
+    z = cat @ p[pre + "kernel"] + p[pre + "bias"]
+    size = z.shape[1] // 2
+    # reshape [-1,1,2,size] + max_pool over the length-2 axis: first half vs second half
+    return torch.maximum(z[:, :size], z[:, size:])
+
+
+def state_to_logits(p: Params, spec: RNNDecoderSpec, state: torch.Tensor) -> torch.Tensor:
+    """autoregressive.py:450-459."""
+    logits = state @ p[spec.prefix + "/state_to_word_W"] + p[spec.prefix + "/state_to_word_b"]
+    if spec.supress_unk:
+        unk_mask = torch.zeros(logits.shape[1], dtype=logits.dtype)
+        unk_mask[UNK] = -1e9
+        logits = logits + unk_mask
+    return logits
+
+
+def decoder_step(p: Params, spec: RNNDecoderSpec, embedded_input, prev_output, hidden, states, mask):
+    """Decoder.next_state, GRU branch, attention_on_input=False, no conditional GRU
+    (decoder.py:279-358); dropout off so prev_rnn_output == cell_output."""
+    pre = spec.prefix + "/attention_decoder/OrthoGRUCell/"
+    cell_output = gru_cell(embedded_input, prev_output, p[pre + "gates/kernel"], p[pre + "gates/bias"],
+                           p[pre + "candidate/kernel"], p[pre + "candidate/bias"])
+    context, weights = bahdanau_step(p, spec.att_prefix, cell_output, hidden, states, mask)
+    output = output_projection(p, spec, cell_output, embedded_input, context)
+    return output, cell_output, context, weights
+
+
+def decoder_train(p: Params, spec: RNNDecoderSpec, enc: Dict[str, torch.Tensor],
+                  train_inputs: torch.Tensor) -> Dict[str, torch.Tensor]:
+    """decoding_loop(train_mode=True) + train_xents/train_loss (autoregressive.py:292-316,532-562).
+
+    train_inputs: [T, B] int64 = padded references with </s> appended (feed_dict :579-582),
+    already transposed to time-major as `train_inputs` is (:199-202)."""
+    emb = p[spec.prefix + "/word_embeddings"]
+    steps, bsz = train_inputs.shape
+    states, mask = enc["temporal_states"], enc["temporal_mask"]
+    hidden = bahdanau_precompute(p, spec.att_prefix, states)
+    prev = decoder_initial_state(p, spec, enc["output"])
+    finished = torch.zeros(bsz, dtype=torch.bool)
+    embedded = emb[torch.full((bsz,), START, dtype=torch.int64)]
+    logits_hist, out_states, att_weights, rnn_outputs = [], [], [], []
+    step = 0
+    while (not bool(finished.all())) and step < spec.max_output_len:
+        output, prev, _ctx, w = decoder_step(p, spec, embedded, prev, hidden, states, mask)
+        logits = state_to_logits(p, spec, output)
+        next_symbols = train_inputs[step] * (~finished).to(torch.int64)
+        finished = finished | (next_symbols == END)
+        embedded = emb[next_symbols]
+        logits_hist.append(logits)
+        out_states.append(output)
+        att_weights.append(w)
+        rnn_outputs.append(prev)
+        step += 1
+    logits_t = torch.stack(logits_hist, 0)                       # [T,B,V]
+    train_mask = sentence_mask(train_inputs, logits_t.dtype)     # [T,B]
+    logprobs = torch.log_softmax(logits_t, dim=-1)
+    xents = -logprobs.gather(2, train_inputs[:logits_t.shape[0]].unsqueeze(-1)).squeeze(-1)
+    xents = xents * train_mask[:logits_t.shape[0]]
+    loss = xents.sum() / train_mask.sum()
+    return {"train_logits": logits_t, "train_xents": xents.t(), "train_loss": loss,
+            "train_mask": train_mask, "train_output_states": torch.stack(out_states, 0),
+            "attention_weights": torch.stack(att_weights, 0),
+            "rnn_outputs": torch.stack(rnn_outputs, 0)}
+
+
+def decoder_greedy(p: Params, spec: RNNDecoderSpec, enc: Dict[str, torch.Tensor],
+                   train_inputs: Optional[torch.Tensor] = None) -> Dict[str, torch.Tensor]:
+    """decoding_loop(train_mode=False): argmax feedback (autoregressive.py:446-519) and, when
+    references are given, runtime_xents / runtime_loss (:351-371)."""
+    emb = p[spec.prefix + "/word_embeddings"]
+    states, mask = enc["temporal_states"], enc["temporal_mask"]
+    bsz = states.shape[0]
+    hidden = bahdanau_precompute(p, spec.att_prefix, states)
+    prev = decoder_initial_state(p, spec, enc["output"])
+    finished = torch.zeros(bsz, dtype=torch.bool)
+    embedded = emb[torch.full((bsz,), START, dtype=torch.int64)]
+    logits_hist, symbols, out_mask = [], [], []
+    step = 0
+    while (not bool(finished.all())) and step < spec.max_output_len:
+        output, prev, _ctx, _w = decoder_step(p, spec, embedded, prev, hidden, states, mask)
+        logits = state_to_logits(p, spec, output)
+        next_symbols = torch.argmax(logits, dim=1) * (~finished).to(torch.int64)
+        finished = finished | (next_symbols == END)
+        embedded = emb[next_symbols]
+        logits_hist.append(logits)
+        symbols.append(next_symbols)
+        out_mask.append(~finished)
+        step += 1
+    logits_t = torch.stack(logits_hist, 0)
+    res = {"runtime_logits": logits_t, "runtime_logprobs": torch.log_softmax(logits_t, -1),
+           "output_symbols": torch.stack(symbols, 0), "runtime_mask": torch.stack(out_mask, 0),
+           "decoded": torch.argmax(logits_t[:, :, 1:], -1) + 1}
+    if train_inputs is not None:
+        min_time = min(train_inputs.shape[0], logits_t.shape[0])
+        lp = torch.log_softmax(logits_t[:min_time], -1)
+        tmask = sentence_mask(train_inputs, logits_t.dtype)[:min_time]
+        xents = -lp.gather(2, train_inputs[:min_time].unsqueeze(-1)).squeeze(-1) * tmask
+        res["runtime_xents"] = xents.t()
+        res["runtime_loss"] = xents.sum() / res["runtime_mask"].to(logits_t.dtype).sum()
+    return res
+
+
+# ---------------------------------------------------------------------------
+# Beam search (decoders/beam_search_decoder.py:218-596)
+# ---------------------------------------------------------------------------
+def length_penalty(lengths: torch.Tensor, alpha: float) -> torch.Tensor:
+    """_length_penalty (:560-573): fp32 arithmetic as the TF graph evaluates it."""
+    return ((5.0 + lengths.to(torch.float32)) / 6.0) ** alpha
+
+
+def beam_step(logprobs: torch.Tensor, logprob_sum: torch.Tensor, lengths: torch.Tensor,
+              finished: torch.Tensor, alpha: float):
+    """Steps (1)-(8) of the beam body (:440-496) on fp32 tensors.
+
+    logprobs [B,k,V] fp32, logprob_sum [B,k] fp32, lengths [B,k] int32, finished [B,k] bool."""
+    bsz, k, vocab = logprobs.shape
+    fmask = finished.to(torch.float32).unsqueeze(2)
+    finished_row = torch.full((vocab,), -INF, dtype=torch.float32)
+    finished_row[PAD] = 0.0
+    lp = (1.0 - fmask) * logprobs + fmask * finished_row
+    hyp_probs = logprob_sum.unsqueeze(2) + lp
+    hyp_lengths = lengths + 1 - finished.to(torch.int32)
+    scores = hyp_probs / length_penalty(hyp_lengths, alpha).unsqueeze(2)
+    flat = scores.reshape(bsz, k * vocab)
+    # tf.nn.top_k: descending, lower index first among equals -> stable sort on -score
+    order = torch.sort(-flat, dim=1, stable=True).indices[:, :k]
+    topk_scores = flat.gather(1, order)
+    word_ids = (order % vocab).to(torch.int64)
+    beam_ids = (order // vocab).to(torch.int32)
+    next_lengths = hyp_lengths.gather(1, beam_ids.to(torch.int64))
+    next_logprob_sum = hyp_probs.reshape(bsz, k * vocab).gather(1, order)
+    next_finished = finished.gather(1, beam_ids.to(torch.int64)) | (word_ids == END)
+    return topk_scores, word_ids, beam_ids, next_logprob_sum, next_lengths, next_finished
+
+
+def beam_search(step_fn: Callable, init_state, first_logprobs: torch.Tensor, beam: int,
+                max_steps: int, alpha: float, gather_state: Callable):
+    """BeamSearchDecoder.outputs loop (:167-191,330-376) around a decoder body.
+
+    first_logprobs [B*k, V]: log-softmax of the decoder body run once on the start symbol
+    (get_initial_loop_state :218-328).  step_fn(state, word_ids[B*k]) -> (state, logprobs[B*k,V]).
+    Returns token_ids [T,B,k] int64, scores [B,k], lengths, finished."""
+    vocab = first_logprobs.shape[1]
+    bsz = first_logprobs.shape[0] // beam
+    logprob_sum = torch.full((bsz, beam), -INF, dtype=torch.float32)
+    logprob_sum[:, 0] = 0.0
+    lengths = torch.zeros(bsz, beam, dtype=torch.int32)
+    finished = torch.zeros(bsz, beam, dtype=torch.bool)
+    prev_logprobs = first_logprobs.reshape(bsz, beam, vocab).to(torch.float32)
+    token_ids = torch.zeros(0, bsz, beam, dtype=torch.int64)
+    scores = torch.zeros(bsz, beam, dtype=torch.float32)
+    state = init_state
+    step = 0
+    # loop_continue_criterion (:330-355): step counts from 1 after the initial body run
+    while step < max_steps and not bool(finished.all()):
+        scores, words, beams, logprob_sum, lengths, finished = beam_step(
+            prev_logprobs, logprob_sum, lengths, finished, alpha)
+        flat_src = (torch.arange(bsz).unsqueeze(1) * beam + beams.to(torch.int64)).reshape(-1)
+        state = gather_state(state, flat_src)
+        token_ids = token_ids[:, torch.arange(bsz).unsqueeze(1), beams.to(torch.int64)]
+        token_ids = torch.cat([token_ids, words.unsqueeze(0)], 0)
+        state, lp = step_fn(state, words.reshape(-1), finished.reshape(-1))
+        prev_logprobs = lp.reshape(bsz, beam, vocab).to(torch.float32)
+        step += 1
+    return {"token_ids": token_ids, "scores": scores, "lengths": lengths, "finished": finished}
+
+
+# ---------------------------------------------------------------------------
+# Trainer (trainers/generic_trainer.py:84-195) and tf.train.AdamOptimizer
+# ---------------------------------------------------------------------------
+def is_regularizable(name: str) -> bool:
+    """BIAS_REGEX = r'[Bb]ias' (generic_trainer.py:17,87-91)."""
+    import re
+    return (not re.findall(r"[Bb]ias", name) and not name.startswith("vgg")
+            and not name.startswith("Inception") and not name.startswith("resnet"))
+
+
+def regularization(p: Params) -> Tuple[torch.Tensor, torch.Tensor]:
+    reg = [v for n, v in p.items() if is_regularizable(n)]
+    return sum(v.abs().sum() for v in reg), sum((v ** 2).sum() for v in reg)
+
+
+def clip_by_norm(g: torch.Tensor, clip: float) -> torch.Tensor:
+    norm = g.pow(2).sum().sqrt()
+    return g * clip / torch.maximum(norm, torch.tensor(clip, dtype=g.dtype))
+
+
+class AdamState:
+    def __init__(self, p: Params) -> None:
+        self.m = {n: torch.zeros_like(v) for n, v in p.items()}
+        self.v = {n: torch.zeros_like(v) for n, v in p.items()}
+        self.t = 0
+
+
+def adam_step(p: Params, grads: Params, st: AdamState, lr: float = 1e-4, beta1: float = 0.9,
+              beta2: float = 0.999, eps: float = 1e-8, clip_norm: Optional[float] = None) -> None:
+    """apply_gradients with tf.train.AdamOptimizer defaults (generic_trainer.py:56-57,183-195)."""
+    st.t += 1
+    lr_t = lr * math.sqrt(1 - beta2 ** st.t) / (1 - beta1 ** st.t)
+    with torch.no_grad():
+        for n, v in p.items():
+            g = grads[n]
+            if clip_norm:
+                g = clip_by_norm(g, clip_norm)
+            st.m[n].mul_(beta1).add_(g, alpha=1 - beta1)
+            st.v[n].mul_(beta2).addcmul_(g, g, value=1 - beta2)
+            v.sub_(lr_t * st.m[n] / (st.v[n].sqrt() + eps))
+
+
+def train_step(p: Params, spec: RNNDecoderSpec, enc_prefix: str, src_ids: torch.Tensor,
+               train_inputs: torch.Tensor, st: AdamState, l1: float = 0.0, l2: float = 0.0,
+               clip_norm: Optional[float] = None, lr: float = 1e-4) -> Dict[str, torch.Tensor]:
+    """One CrossEntropyTrainer step on the Bahdanau model; returns the fetched losses."""
+    for v in p.values():
+        v.requires_grad_(True)
+        v.grad = None
+    enc = sentence_encoder(p, enc_prefix, src_ids)
+    dec = decoder_train(p, spec, enc, train_inputs)
+    l1_norm, l2_norm = regularization(p)
+    total = dec["train_loss"] + l1 * l1_norm + l2 * l2_norm
+    total.backward()
+    grads = {n: (v.grad if v.grad is not None else torch.zeros_like(v)) for n, v in p.items()}
+    for v in p.values():
+        v.requires_grad_(False)
+    adam_step(p, grads, st, lr=lr, clip_norm=clip_norm)
+    return {"loss": dec["train_loss"].detach(), "l1": l1_norm.detach(), "l2": l2_norm.detach(),
+            "grads": grads}
+
+
+# ---------------------------------------------------------------------------
+# parameter initialisation with the reference's initialisers
+# ---------------------------------------------------------------------------
+def orthogonal(rows: int, cols: int, gen: torch.Generator, dtype) -> torch.Tensor:
+    """tf.orthogonal_initializer on a [rows, cols] kernel."""
+    a = torch.randn(max(rows, cols), min(rows, cols), generator=gen, dtype=torch.float64)
+    q, r = torch.linalg.qr(a)
+    q = q * torch.sign(torch.diagonal(r))
+    if rows < cols:
+        q = q.t()
+    return q[:rows, :cols].to(dtype).contiguous()
+
+
+def init_bahdanau_params(vs: int, vt: int, es: int, he: int, et: int, hd: int, att: Optional[int],
+                         out: int, maxout: bool, seed: int = 2574600, dtype=torch.float32,
+                         enc_prefix: str = "sentence_encoder", att_prefix: str = "attention",
+                         dec_prefix: str = "decoder") -> Params:
+    gen = torch.Generator().manual_seed(seed)
+    ctx = 2 * he
+    att = att if att is not None else ctx
+
+    def normal(*shape):
+        return (torch.randn(*shape, generator=gen, dtype=torch.float64) * 0.001).to(dtype)
+
+    p = {}
+    p[enc_prefix + "_input/embedding_matrix_0"] = normal(vs, es)
+    for d in ("fw", "bw"):
+        cell = "{}/rnn_0_bidirectional/bidirectional_rnn/{}/OrthoGRUCell/".format(enc_prefix, d)
+        p[cell + "gates/kernel"] = orthogonal(es + he, 2 * he, gen, dtype)
+        p[cell + "gates/bias"] = torch.ones(2 * he, dtype=dtype)
+        p[cell + "candidate/kernel"] = orthogonal(es + he, he, gen, dtype)
+        p[cell + "candidate/bias"] = torch.zeros(he, dtype=dtype)
+    p[enc_prefix + "/LayerNorm/gamma"] = torch.ones(ctx, dtype=dtype)
+    p[enc_prefix + "/LayerNorm/beta"] = torch.zeros(ctx, dtype=dtype)
+    p[att_prefix + "/Attention/attn_query_projection"] = normal(hd, att)
+    p[att_prefix + "/attn_key_projection"] = normal(ctx, att)
+    p[att_prefix + "/attn_similarity_v"] = normal(att)
+    p[att_prefix + "/attn_projection_bias"] = torch.zeros(att, dtype=dtype)
+    p[att_prefix + "/attn_bias"] = torch.zeros(1, dtype=dtype)
+    p[dec_prefix + "/word_embeddings"] = normal(vt, et)
+    p[dec_prefix + "/state_to_word_W"] = (
+        (torch.rand(out, vt, generator=gen, dtype=torch.float64) - 0.5).to(dtype))
+    p[dec_prefix + "/state_to_word_b"] = torch.zeros(vt, dtype=dtype)
+    p[dec_prefix + "/initial_state/encoders_projection/kernel"] = normal(ctx, hd)
+    p[dec_prefix + "/initial_state/encoders_projection/bias"] = torch.zeros(hd, dtype=dtype)
+    cell = dec_prefix + "/attention_decoder/OrthoGRUCell/"
+    p[cell + "gates/kernel"] = orthogonal(et + hd, 2 * hd, gen, dtype)
+    p[cell + "gates/bias"] = torch.ones(2 * hd, dtype=dtype)
+    p[cell + "candidate/kernel"] = orthogonal(et + hd, hd, gen, dtype)
+    p[cell + "candidate/bias"] = torch.zeros(hd, dtype=dtype)
+    cat = hd + et + ctx
+    if maxout:
+        pre = dec_prefix + "/attention_decoder/MaxoutProjection/MaxoutProjection/"
+        p[pre + "kernel"] = normal(cat, 2 * out)
+        p[pre + "bias"] = torch.zeros(2 * out, dtype=dtype)
+    else:
+        pre = dec_prefix + "/attention_decoder/dense/"
+        p[pre + "kernel"] = normal(cat, out)
+        p[pre + "bias"] = torch.zeros(out, dtype=dtype)
+    return p
+
+
+def randomize(p: Params, scale: float = 0.3, seed: int = 7) -> Params:
+    """Replace the near-zero reference initialisation with O(scale) values so that parity tests
+    exercise every non-linearity (N(0, 0.001^2) weights make tanh/softmax nearly linear)."""
+    gen = torch.Generator().manual_seed(seed)
+    out = {}
+    for n, v in p.items():
+        r = torch.randn(v.shape, generator=gen, dtype=torch.float64) * scale
+        if n.endswith("gamma"):
+            r = 1.0 + r
+        out[n] = r.to(v.dtype)
+    return out

@@ -1,0 +1,126 @@
+"""The Bahdanau encoder-decoder through the ModelPart API against the CPU oracle:
+forward tensors, loss, every gradient, the optimizer step, and greedy decoding."""
+import pytest
+import torch
+
+from oracle import nm_oracle as O
+from tests.helpers import (build_bahdanau, feed, max_abs, oracle_params_for, oracle_spec,
+                           random_batch, rel_err)
+
+pytestmark = pytest.mark.gpu
+
+TOY = dict(vs=60, vt=70, es=11, he=7, et=9, hd=8, out=9, maxout=True, max_len=10, supress_unk=True)
+MID = dict(vs=120, vt=200, es=32, he=16, et=24, hd=32, out=24, maxout=False, max_len=12,
+           supress_unk=False)
+
+
+def _setup(cfg, backend, bsz=6, tx=8, ty=7, seed=0, **trainer_kw):
+    from neuralmonkey_b200 import ops
+    ops.set_gemm_backend(backend)
+    model = build_bahdanau(**cfg, **trainer_kw)
+    params = oracle_params_for(model)
+    model["arena"].load_dict(params)
+    src, tgt = random_batch(bsz, tx, ty, cfg["vs"], cfg["vt"], seed=seed)
+    return model, params, src, tgt
+
+
+@pytest.mark.parametrize("cfg,backend,tol", [(TOY, "simt", 2e-5), (MID, "simt", 2e-5),
+                                             (MID, "auto", 5e-3)])
+def test_train_forward_and_gradients(cfg, backend, tol):
+    from neuralmonkey_b200 import ops
+    try:
+        model, params, src, tgt = _setup(cfg, backend)
+        feed(model, src, tgt, train=True)
+        enc, dec = model["enc"], model["dec"]
+        spec = oracle_spec(cfg["maxout"], cfg["max_len"], cfg["supress_unk"])
+        p64 = {n: v.double().requires_grad_(True) for n, v in params.items()}
+        oenc = O.sentence_encoder(p64, "sentence_encoder", src)
+        odec = O.decoder_train(p64, spec, oenc, tgt.t())
+        assert max_abs(enc.temporal_states, oenc["temporal_states"]) < tol
+        assert max_abs(enc.output, oenc["output"]) < tol
+        assert max_abs(dec.train_output_states, odec["train_output_states"]) < tol
+        assert max_abs(dec.train_xents, odec["train_xents"]) < 10 * tol
+        assert abs(float(dec.train_loss) - float(odec["train_loss"])) < max(tol, 1e-5)
+        assert max_abs(dec.train_logits, odec["train_logits"]) < 10 * tol
+        # gradients of the token-mean loss w.r.t. every variable
+        arena = model["arena"]
+        arena.zero_grad()
+        dec.train_loss.backward()
+        odec["train_loss"].backward()
+        gtol = 2e-4 if backend == "simt" else 1e-2
+        for name, grad in arena.named_grads().items():
+            want = p64[name].grad
+            want = torch.zeros_like(p64[name]) if want is None else want
+            err = float((grad.double() - want.reshape(grad.shape)).norm())
+            assert err <= gtol * float(want.norm()) + 1e-7, (name, err, float(want.norm()))
+    finally:
+        ops.set_gemm_backend("auto")
+
+
+@pytest.mark.parametrize("trainer_kw", [dict(), dict(l2=1e-3, clip=1.0), dict(l1=1e-4, clip=10.0)])
+def test_optimizer_steps_match_oracle(trainer_kw):
+    """Three CrossEntropyTrainer steps: losses and all parameters track TF-Adam semantics."""
+    from neuralmonkey_b200 import ops
+    try:
+        model, params, src, tgt = _setup(TOY, "simt", lr=1e-2, **trainer_kw)
+        spec = oracle_spec()
+        p32 = {n: v.clone() for n, v in params.items()}
+        st = O.AdamState(p32)
+        for step in range(3):
+            src, tgt = random_batch(6, 8, 7, TOY["vs"], TOY["vt"], seed=10 + step)
+            feed(model, src, tgt, train=True)
+            out = model["trainer"].train_step()
+            ref = O.train_step(p32, spec, "sentence_encoder", src, tgt.t(), st,
+                               l1=trainer_kw.get("l1", 0.0), l2=trainer_kw.get("l2", 0.0),
+                               clip_norm=trainer_kw.get("clip"), lr=1e-2)
+            assert abs(float(out["losses"][0]) - float(ref["loss"])) < 2e-4
+            if trainer_kw:
+                assert abs(float(out["l1l2"][1]) - float(ref["l2"])) < 1e-3 * float(ref["l2"]) + 1e-5
+        got = model["arena"].state_dict()
+        for name, want in p32.items():
+            assert max_abs(got[name], want) < 5e-4, name
+    finally:
+        ops.set_gemm_backend("auto")
+
+
+@pytest.mark.parametrize("cfg,backend,tol", [(TOY, "simt", 5e-5), (MID, "auto", 2e-2)])
+def test_greedy_decoding(cfg, backend, tol):
+    from neuralmonkey_b200 import ops
+    try:
+        model, params, src, tgt = _setup(cfg, backend, seed=3)
+        feed(model, src, tgt, train=False)
+        dec = model["dec"]
+        spec = oracle_spec(cfg["maxout"], cfg["max_len"], cfg["supress_unk"])
+        oenc = O.sentence_encoder(params, "sentence_encoder", src)
+        og = O.decoder_greedy(params, spec, oenc, tgt.t())
+        steps = og["runtime_logits"].shape[0]
+        assert dec.runtime_logits.shape[0] == steps
+        assert max_abs(dec.runtime_logits, og["runtime_logits"]) < tol
+        if backend == "simt":   # integer bookkeeping is exact when the logits are fp32-exact
+            assert bool((dec.runtime_symbols.cpu() == og["output_symbols"]).all())
+            assert bool((dec.runtime_mask.cpu() == og["runtime_mask"]).all())
+            assert bool((dec.decoded.cpu() == og["decoded"]).all())
+        assert abs(float(dec.runtime_loss) - float(og["runtime_loss"])) < 20 * tol
+        assert max_abs(dec.runtime_logprobs, og["runtime_logprobs"]) < 2 * tol
+    finally:
+        ops.set_gemm_backend("auto")
+
+
+def test_greedy_runner_tokens():
+    from neuralmonkey_b200 import ops
+    from neuralmonkey_b200.runners import GreedyRunner
+    try:
+        model, params, src, tgt = _setup(TOY, "simt", seed=4)
+        feed(model, src, tgt, train=False)
+        runner = GreedyRunner(output_series="target", decoder=model["dec"])
+        exe = runner.get_executable(compute_losses=True, summaries=False, num_sessions=1)
+        exe.execute()
+        res = exe.result
+        oenc = O.sentence_encoder(params, "sentence_encoder", src)
+        og = O.decoder_greedy(params, oracle_spec(), oenc, tgt.t())
+        want = model["dec"].vocabulary.vectors_to_sentences(
+            og["runtime_logprobs"].argmax(-1).numpy())
+        assert res.outputs["target"] == want
+        assert abs(res.losses["target/runtime_xent"] - float(og["runtime_loss"])) < 1e-3
+    finally:
+        ops.set_gemm_backend("auto")

@@ -1,0 +1,103 @@
+"""Host-side logic that needs no GPU: vocabulary, padding, arena layout, sharding."""
+import os
+import subprocess
+import sys
+
+import pytest
+import torch
+
+from neuralmonkey_b200 import distributed
+from neuralmonkey_b200.params import ParameterArena, normal_initializer, zeros_initializer
+from neuralmonkey_b200.vocabulary import (END_TOKEN, PAD_TOKEN, Vocabulary, from_wordlist, pad_batch,
+                                          sentence_mask)
+
+
+def test_pad_batch_matches_reference_rules():
+    # longest + </s>, truncated to max_length; </s> is cut off when the sentence is too long
+    out = pad_batch([["a", "b", "c"], ["d"]], max_length=3, add_end_symbol=True)
+    assert out == [["a", "b", "c"], ["d", END_TOKEN, PAD_TOKEN]]
+    out = pad_batch([["a", "b"], []], add_end_symbol=True)
+    assert out == [["a", "b", END_TOKEN], [END_TOKEN, PAD_TOKEN, PAD_TOKEN]]
+    out = pad_batch([["a"]], add_start_symbol=True)
+    assert out == [["<s>", "a"]]
+
+
+def test_vocabulary_roundtrip_and_unknowns(tmp_path):
+    path = tmp_path / "vocab.tsv"
+    path.write_text("word\tcount\n<pad>\t0\n<s>\t0\n</s>\t0\n<unk>\t0\nhello\t5\nworld\t3\n")
+    vocab = from_wordlist(str(path))
+    assert len(vocab) == 6 and vocab.index_to_word[4] == "hello"
+    ids = vocab.strings_to_indices([["hello", "zzz", "</s>", "<pad>"]])
+    assert ids.tolist() == [[4, 3, 2, 0]] and ids.dtype == torch.int64
+    assert sentence_mask(ids).tolist() == [[1.0, 1.0, 1.0, 0.0]]
+    import numpy as np
+    sents = vocab.vectors_to_sentences(np.array([[4], [5], [2], [4]]))
+    assert sents == [["hello", "world"]]
+
+
+def test_arena_layout_is_aligned_and_trainables_first():
+    arena = ParameterArena()
+    arena.declare("frozen/w", [3, 5], normal_initializer(), trainable=False)
+    arena.declare("a/kernel", [7, 9], normal_initializer())
+    arena.declare("a/bias", [9], zeros_initializer())
+    arena.declare("a/kernel", [7, 9], normal_initializer())  # AUTO_REUSE: same shape is fine
+    with pytest.raises(ValueError):
+        arena.declare("a/kernel", [7, 8], normal_initializer())
+    arena.finalize(torch.device("cpu"))
+    offs = arena.seg_off.tolist()
+    assert offs[0] == 0 and all(o % ParameterArena.ALIGN == 0 for o in offs)
+    assert arena.train_names == ["a/kernel", "a/bias"]
+    assert arena.seg_reg.tolist() == [1, 0]       # biases are not regularised
+    assert arena.variables["frozen/w"].offset >= arena.trainable_size
+    assert arena.get("a/kernel").requires_grad and not arena.get("frozen/w").requires_grad
+    assert arena.get("a/kernel").nm_grad.shape == (7, 9)
+    assert arena.allreduce_view.numel() == arena.trainable_size + ParameterArena.STAT_SLOTS
+
+
+def test_shard_bounds_cover_everything_once():
+    for n in (0, 1, 7, 256, 257):
+        for ranks in (1, 2, 3, 8):
+            b = distributed.shard_bounds(n, ranks)
+            assert b[0] == 0 and b[-1] == n and len(b) == ranks + 1
+            sizes = [b[i + 1] - b[i] for i in range(ranks)]
+            assert max(sizes) - min(sizes) <= 1
+
+
+_GLOO_WORKER = r"""
+import os, sys, torch
+sys.path.insert(0, {root!r})
+from neuralmonkey_b200 import distributed
+from neuralmonkey_b200.params import ParameterArena, normal_initializer
+distributed.init_from_env(backend="gloo")
+r, n = distributed.rank(), distributed.world_size()
+arena = ParameterArena()
+arena.declare("w", [4, 3], normal_initializer())
+arena.finalize(torch.device("cpu"))
+# each rank contributes grad = rank+1 everywhere, loss_sum = 10*(rank+1), count = rank+2
+arena.grads.fill_(float(r + 1))
+arena.stats[0] = 10.0 * (r + 1)
+arena.stats[1] = float(r + 2)
+distributed.all_reduce_sum(arena.allreduce_view)
+exp = sum(range(1, n + 1))
+assert torch.all(arena.grads == exp), arena.grads
+assert float(arena.stats[0]) == 10.0 * exp and float(arena.stats[1]) == exp + n
+items = list(range(11))
+mine = distributed.shard(items)
+gathered = [None] * n
+torch.distributed.all_gather_object(gathered, list(mine))
+assert sum(gathered, []) == items
+print("rank", r, "ok")
+"""
+
+
+def test_two_rank_gloo_allreduce_of_the_exchange_buffer(tmp_path):
+    """world_size-2 CPU run of the data-parallel exchange (gradients + loss sum + count)."""
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    script = tmp_path / "worker.py"
+    script.write_text(_GLOO_WORKER.format(root=root))
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+           "--master-addr", "127.0.0.1", "--master-port", "29611", str(script)]
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=240, env=env)
+    assert res.returncode == 0, res.stdout + res.stderr
+    assert res.stdout.count("ok") == 2
