@@ -4,7 +4,8 @@
 //   * persistent: one CTA per SM walks 128 x BN output tiles (static round-robin);
 //   * warp 0 = TMA producer, warp 1 = MMA issuer (one elected lane) + TMEM allocator,
 //     warps 2..5 = epilogue (TMEM lane quadrant = warp_idx % 4);
-//   * STAGES-deep smem ring of {A 128x32, B BNx32} fp32 tiles in the 128-byte swizzle,
+//   * STAGES-deep smem ring of {A 128x32, B BNx32} fp32 tiles in the 128-byte swizzle
+//     (16-byte atoms for K-major operands, 32-byte atoms for MN-major ones),
 //     filled by cp.async.bulk.tensor (OOB rows/cols arrive as zeros: no tail code);
 //   * two TMEM accumulator buffers (2*BN columns) so the epilogue of tile i overlaps
 //     the main loop of tile i+1;
@@ -117,13 +118,16 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&r)[32]) {
 
 // Shared-memory matrix descriptor, 128-byte swizzle, version 1 (Blackwell).
 // bits [0,14) start>>4 | [16,30) LBO>>4 | [32,46) SBO>>4 | [46,48) version | [61,64) layout
-__device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+constexpr uint32_t SMEM_LAYOUT_SW128 = 2;       // 128-byte swizzle, 16-byte atoms
+constexpr uint32_t SMEM_LAYOUT_SW128_32B = 1;   // 128-byte swizzle, 32-byte atoms
+__device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes,
+                                              uint32_t layout) {
   uint64_t d = 0;
   d |= (uint64_t)((addr & 0x3FFFFu) >> 4);
   d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
   d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
   d |= (uint64_t)1 << 46;
-  d |= (uint64_t)2 << 61;  // SWIZZLE_128B
+  d |= (uint64_t)layout << 61;
   return d;
 }
 
@@ -234,10 +238,16 @@ __device__ __forceinline__ void epilogue_chunk(const TcEpilogue& e, const float 
 // ---------------------------------------------------------------------------
 // the kernel
 // ---------------------------------------------------------------------------
+// smem descriptor fields of an MN-major operand tile (bytes); a kernel argument so a
+// diagnostic run can probe them (NMB200_MN_* environment variables), fixed otherwise.
+struct MnDesc {
+  uint32_t layout, sbo, lbo, kadv;
+};
+
 template <int BN, bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
-               int64_t M, int64_t N, int64_t K, TcEpilogue epi) {
+               int64_t M, int64_t N, int64_t K, TcEpilogue epi, MnDesc mn) {
   using Cfg = TcCfg<BN>;
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
@@ -336,13 +346,17 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           const uint32_t b_addr = a_addr + TC_A_BYTES;
 #pragma unroll
           for (int k = 0; k < TC_BK / TC_UMMA_K; ++k) {
-            // K-major: 8 rows x 128 B atoms, next 8-row group at +1024 B, K step = +32 B.
-            // MN-major: 32-element MN atoms at +4096 B (LBO), 8-k-row groups at +1024 B (SBO),
-            //           K step = one 8-row group = +1024 B.
-            const uint64_t da = A_MN ? smem_desc(a_addr + k * 1024, 4096, 1024)
-                                     : smem_desc(a_addr + k * 32, 16, 1024);
-            const uint64_t db = B_MN ? smem_desc(b_addr + k * 1024, 4096, 1024)
-                                     : smem_desc(b_addr + k * 32, 16, 1024);
+            // K-major (SWIZZLE_128B): atoms of 8 rows x 128 B, next 8-row group at +1024 B
+            //   (SBO), K step of one instruction (8 tf32) = +32 B inside the swizzled row.
+            // MN-major: tf32 operands whose reduction dim is strided must use the
+            //   128B-swizzle-with-32B-atoms layout (the only MN-major tf32 layout tcgen05
+            //   accepts): atoms of 4 k-rows x 128 B (32 MN elements); next 4-k-row group at
+            //   +512 B (SBO), next 32-element MN atom = next TMA box at +4096 B (LBO);
+            //   K step (8 k-rows) = +1024 B.
+            const uint64_t da = A_MN ? smem_desc(a_addr + k * mn.kadv, mn.lbo, mn.sbo, mn.layout)
+                                     : smem_desc(a_addr + k * 32, 16, 1024, SMEM_LAYOUT_SW128);
+            const uint64_t db = B_MN ? smem_desc(b_addr + k * mn.kadv, mn.lbo, mn.sbo, mn.layout)
+                                     : smem_desc(b_addr + k * 32, 16, 1024, SMEM_LAYOUT_SW128);
             umma_tf32(d_tmem, da, db, idesc, (kb > 0 || k > 0) ? 1u : 0u);
           }
           umma_commit(empty_bar(stage));  // frees this smem stage when the MMAs retire
@@ -419,8 +433,28 @@ static EncodeTiledFn get_encode_fn() {
 }
 
 // 2-D fp32 tensor [rows, cols] with row pitch ld (elements); box = {box_cols, box_rows}.
+static uint32_t env_u32(const char* name, uint32_t dflt) {
+  const char* e = getenv(name);
+  return (e && *e) ? (uint32_t)strtoul(e, nullptr, 0) : dflt;
+}
+
+static MnDesc mn_desc_config() {
+  static MnDesc d = {0, 0, 0, 0};
+  static bool init = false;
+  if (!init) {
+    d.layout = env_u32("NMB200_MN_LAYOUT", SMEM_LAYOUT_SW128_32B);
+    d.sbo = env_u32("NMB200_MN_SBO", 512);
+    d.lbo = env_u32("NMB200_MN_LBO", 4096);
+    d.kadv = env_u32("NMB200_MN_KADV", 1024);
+    init = true;
+  }
+  return d;
+}
+
 static int make_map(CUtensorMap* map, const float* base, int64_t rows, int64_t cols, int64_t ld,
-                    uint32_t box_cols, uint32_t box_rows) {
+                    uint32_t box_cols, uint32_t box_rows, bool mn_major) {
+  static int mn_swizzle = -1;  // CUtensorMapSwizzle for MN-major operand tiles
+  if (mn_swizzle < 0) mn_swizzle = (int)env_u32("NMB200_MN_SWIZZLE", (uint32_t)CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
   EncodeTiledFn fn = get_encode_fn();
   NM_REQUIRE(fn != nullptr, NM_E_NO_DEVICE, "tc_gemm: cuTensorMapEncodeTiled not available");
   static int dtype_mode = -1;  // NMB200_TMA_DTYPE=fp32 keeps raw fp32 bits (MMA truncates)
@@ -434,7 +468,8 @@ static int make_map(CUtensorMap* map, const float* base, int64_t rows, int64_t c
   const cuuint32_t estr[2] = {1, 1};
   const CUresult r = fn(map, dtype_mode ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_TFLOAT32,
                         2, const_cast<float*>(base), gdim, gstride, box, estr,
-                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        mn_major ? (CUtensorMapSwizzle)mn_swizzle : CU_TENSOR_MAP_SWIZZLE_128B,
                         CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   NM_REQUIRE(r == CUDA_SUCCESS, NM_E_INVALID,
              "tc_gemm: cuTensorMapEncodeTiled failed (%d) rows=%lld cols=%lld ld=%lld", (int)r,
@@ -465,7 +500,7 @@ static int launch_cfg(const CUtensorMap& ma, const CUtensorMap& mb, int64_t M, i
   }
   const int64_t tiles = ceil_div(M, TC_BM) * ceil_div(N, BN);
   const int64_t grid = tiles < sm_count() ? tiles : sm_count();
-  kern<<<(unsigned)grid, TC_THREADS, Cfg::SMEM_BYTES, s>>>(ma, mb, M, N, K, epi);
+  kern<<<(unsigned)grid, TC_THREADS, Cfg::SMEM_BYTES, s>>>(ma, mb, M, N, K, epi, mn_desc_config());
   NM_LAUNCH_CHECK("tc_gemm_kernel");
   return NM_OK;
 }
@@ -490,11 +525,11 @@ int tc_gemm_launch(int transA, int transB, int64_t M, int64_t N, int64_t K, cons
   const int bn = (epi.mode == TC_EPI_DENSE) ? pick_bn(M, N) : TC_XENT_BN;
   CUtensorMap ma, mb;
   int rc;
-  if (!a_mn) rc = make_map(&ma, A, M, K, lda, TC_BK, TC_BM);
-  else       rc = make_map(&ma, A, K, M, lda, 32, TC_BK);
+  if (!a_mn) rc = make_map(&ma, A, M, K, lda, TC_BK, TC_BM, false);
+  else       rc = make_map(&ma, A, K, M, lda, 32, TC_BK, true);
   if (rc) return rc;
-  if (!b_mn) rc = make_map(&mb, B, N, K, ldb, TC_BK, (uint32_t)bn);
-  else       rc = make_map(&mb, B, K, N, ldb, 32, TC_BK);
+  if (!b_mn) rc = make_map(&mb, B, N, K, ldb, TC_BK, (uint32_t)bn, false);
+  else       rc = make_map(&mb, B, K, N, ldb, 32, TC_BK, true);
   if (rc) return rc;
 #define NM_TC_DISPATCH(BN_)                                                            \
   do {                                                                                 \

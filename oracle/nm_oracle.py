@@ -285,8 +285,15 @@ def decoder_greedy(p: Params, spec: RNNDecoderSpec, enc: Dict[str, torch.Tensor]
 # Beam search (decoders/beam_search_decoder.py:218-596)
 # ---------------------------------------------------------------------------
 def length_penalty(lengths: torch.Tensor, alpha: float) -> torch.Tensor:
-    """_length_penalty (:560-573): fp32 arithmetic as the TF graph evaluates it."""
-    return ((5.0 + lengths.to(torch.float32)) / 6.0) ** alpha
+    """_length_penalty (:560-573): ((5 + len) / 6) ** alpha on fp32 tensors.
+
+    The fp32 division is IEEE-exact everywhere; the power is taken as the CORRECTLY ROUNDED
+    fp32 power (evaluate in fp64, round once), which is what glibc's powf - behind Eigen's
+    scalar pow in the TF-1.12 CPU kernel - delivers.  torch's vectorised fp32 pow differs
+    from it in the last ulp for some arguments, so it is not used here."""
+    base = (5.0 + lengths.to(torch.float32)) / 6.0
+    return torch.pow(base.to(torch.float64), float(torch.tensor(alpha, dtype=torch.float32))
+                     ).to(torch.float32)
 
 
 def beam_step(logprobs: torch.Tensor, logprob_sum: torch.Tensor, lengths: torch.Tensor,

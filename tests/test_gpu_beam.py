@@ -16,13 +16,12 @@ def _case(bsz, k, vocab, seed, finished_frac=0.3, ties=False):
     logprob_sum = -torch.rand(bsz, k, generator=g) * 10
     if ties:
         logprob_sum = torch.round(logprob_sum)
+    lengths = torch.randint(0, 20, (bsz, k), generator=g, dtype=torch.int32)
+    finished = torch.rand(bsz, k, generator=g) < finished_frac
+    if ties and k > 1:  # beams 0 and 1 are exact copies: every candidate ties across beams
         logprob_sum[:, 1] = logprob_sum[:, 0]
         logprobs[:, 1] = logprobs[:, 0]
-    lengths = torch.randint(0, 20, (bsz, k), generator=g, dtype=torch.int32)
-    if ties:
         lengths[:, 1] = lengths[:, 0]
-    finished = torch.rand(bsz, k, generator=g) < finished_frac
-    if ties:
         finished[:, :2] = False
     return logprobs, logprob_sum, lengths, finished
 

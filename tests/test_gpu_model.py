@@ -10,7 +10,7 @@ from tests.helpers import (build_bahdanau, feed, max_abs, oracle_params_for, ora
 pytestmark = pytest.mark.gpu
 
 TOY = dict(vs=60, vt=70, es=11, he=7, et=9, hd=8, out=9, maxout=True, max_len=10, supress_unk=True)
-MID = dict(vs=120, vt=200, es=32, he=16, et=24, hd=32, out=24, maxout=False, max_len=12,
+MID = dict(vs=120, vt=200, es=32, he=16, et=32, hd=32, out=32, maxout=False, max_len=12,
            supress_unk=False)
 
 
@@ -41,7 +41,9 @@ def test_train_forward_and_gradients(cfg, backend, tol):
         assert max_abs(dec.train_output_states, odec["train_output_states"]) < tol
         assert max_abs(dec.train_xents, odec["train_xents"]) < 10 * tol
         assert abs(float(dec.train_loss) - float(odec["train_loss"])) < max(tol, 1e-5)
-        assert max_abs(dec.train_logits, odec["train_logits"]) < 10 * tol
+        keep = torch.ones(cfg["vt"], dtype=torch.bool)
+        keep[3] = not cfg["supress_unk"]  # the suppressed <unk> column holds -1e9
+        assert max_abs(dec.train_logits.cpu()[..., keep], odec["train_logits"][..., keep]) < 10 * tol
         # gradients of the token-mean loss w.r.t. every variable
         arena = model["arena"]
         arena.zero_grad()
@@ -95,13 +97,15 @@ def test_greedy_decoding(cfg, backend, tol):
         og = O.decoder_greedy(params, spec, oenc, tgt.t())
         steps = og["runtime_logits"].shape[0]
         assert dec.runtime_logits.shape[0] == steps
-        assert max_abs(dec.runtime_logits, og["runtime_logits"]) < tol
+        keep = torch.ones(cfg["vt"], dtype=torch.bool)
+        keep[3] = not cfg["supress_unk"]
+        assert max_abs(dec.runtime_logits.cpu()[..., keep], og["runtime_logits"][..., keep]) < tol
         if backend == "simt":   # integer bookkeeping is exact when the logits are fp32-exact
             assert bool((dec.runtime_symbols.cpu() == og["output_symbols"]).all())
             assert bool((dec.runtime_mask.cpu() == og["runtime_mask"]).all())
             assert bool((dec.decoded.cpu() == og["decoded"]).all())
         assert abs(float(dec.runtime_loss) - float(og["runtime_loss"])) < 20 * tol
-        assert max_abs(dec.runtime_logprobs, og["runtime_logprobs"]) < 2 * tol
+        assert max_abs(dec.runtime_logprobs.cpu()[..., keep], og["runtime_logprobs"][..., keep]) < 2 * tol
     finally:
         ops.set_gemm_backend("auto")
 

@@ -150,8 +150,10 @@ def test_bahdanau_fwd_bwd(use_mask, dims):
     dctx = torch.randn(bsz, nq, c, generator=g)
     (ctx * dctx.cuda()).sum().backward()
     (cref * dctx.double()).sum().backward()
-    for got, want, name in zip(leaves, (k64, v64, q64, vv64, b64), ("keys", "values", "q", "v", "bias")):
+    for got, want, name in zip(leaves[:4], (k64, v64, q64, vv64), ("keys", "values", "q", "v")):
         assert rel_err(got.grad, want.grad) < 1e-4, name
+    # softmax is shift invariant: the scalar bias has (mathematically) zero gradient
+    assert abs(float(leaves[4].grad) - float(b64.grad)) < 1e-4
 
 
 @pytest.mark.parametrize("cfg", [(37, 70, 9, "simt", False), (300, 1000, 64, "auto", False),
@@ -177,8 +179,12 @@ def test_logits_xent_fwd_bwd(cfg):
         lg = lg + unk
         ref_lse = torch.logsumexp(lg, -1)
         ref_xent = (ref_lse - lg.gather(1, targets.unsqueeze(1)).squeeze(1)) * weights.double()
-        tol = 1e-5 if backend == "simt" else 5e-3
-        assert max_abs(logits, lg) < tol * 10
+        # tf32 products: error grows with sum_k |x_k w_k| ~ 0.2 * K * 2^-11 for these operands
+        tol = 1e-5 if backend == "simt" else max(5e-3, 4e-5 * k)
+        keep = torch.ones(vocab, dtype=torch.bool)
+        keep[3] = False  # the <unk> column holds -1e9 (+ O(1)): 64-ulp fp32 granularity
+        assert max_abs(logits.cpu()[:, keep], lg[:, keep]) < tol * 10
+        assert float(logits[:, 3].max()) < -9e8
         assert max_abs(lse, ref_lse) < tol
         assert max_abs(xent, ref_xent) < tol * 2
         # argmax: exact wherever the oracle's top-2 margin exceeds the kernel's error
