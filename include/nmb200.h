@@ -124,7 +124,8 @@ int nm_layernorm_bwd(const float* x, const float* gamma, const float* mean,
  * (decoders/decoder.py:288-289,333-334,351).
  * Outputs: states [B,T,H]; raw_states [B,T,H] (cell outputs before drop_mask, the
  * attention query of decoder.py:291-297; may be NULL); final [B,H]; and, saved for
- * the backward pass:
+ * the backward pass (sm_budget > 0 limits the launch to that many SMs so that two
+ * directions can run side by side on two streams; 0 = whole chip):
  * gates [B,T,3H] = (r,u,c), hprev [B,T,H] = the state each step consumed,
  * rh [B,T,H] = r*hprev (the A operand of the candidate matmul). */
 int nm_gru_seq_fwd(const float* xproj, const float* Wgh, const float* Wch,
@@ -132,7 +133,7 @@ int nm_gru_seq_fwd(const float* xproj, const float* Wgh, const float* Wch,
                    const float* drop_mask, int reverse, float* states,
                    float* raw_states, float* final_state, float* gates,
                    float* hprev, float* rh, int64_t B, int64_t T, int64_t H,
-                   void* stream);
+                   int sm_budget, void* stream);
 /* Inputs: dstates [B,T,H] (may be NULL), dfinal [B,H] (may be NULL).
  * Outputs: dxproj [B,T,3H] (pre-activation grads = grads of xproj), dh0 [B,H]
  * (may be NULL).  Weight grads are NOT produced here: they are the hoisted
@@ -143,7 +144,7 @@ int nm_gru_seq_bwd(const float* Wgh, const float* Wch, const int32_t* lengths,
                    const float* hprev, const float* dstates,
                    const float* draw /* grad of raw_states, may be NULL */,
                    const float* dfinal, float* dxproj, float* dh0, float* work,
-                   int64_t B, int64_t T, int64_t H, void* stream);
+                   int64_t B, int64_t T, int64_t H, int sm_budget, void* stream);
 
 /* ---- K4: Bahdanau attention -------------------------------------------------
  * Replaces Attention.attention (attention/feed_forward.py:125-166) for NQ query

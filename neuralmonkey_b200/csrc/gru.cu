@@ -9,7 +9,11 @@
 // Each step is two fused GEMM+gate kernels forward and one gate kernel plus two
 // fused GEMM kernels backward; the state the step consumed is read from / written
 // to the `hprev` history directly, so no state copy kernels are launched.
+#include <stdlib.h>
+#include <string.h>
+
 #include "gemm_simt.cuh"
+#include "gru_cluster.cuh"
 
 namespace nm {
 
@@ -125,17 +129,94 @@ struct GruBwdGatesEpi {
 
 using namespace nm;
 
+namespace {
+
+// Persistent cluster kernels need the three weight vectors of a unit slice in registers:
+// H <= 320.  NMB200_GRU=steps forces the per-step kernels (debugging / A-B timing).
+bool cluster_path_ok(int64_t H) {
+  static int forced = -1;
+  if (forced < 0) {
+    const char* e = getenv("NMB200_GRU");
+    forced = (e && strcmp(e, "steps") == 0) ? 1 : 0;
+  }
+  return forced == 0 && H >= 8 && H <= 320;
+}
+
+struct ClusterPlan {
+  int Bc, nclusters, ch;
+  size_t smem;
+};
+
+ClusterPlan plan_clusters(int64_t B, int64_t H, int sm_budget, bool backward) {
+  const int SL = (int)((H + GC_KS - 1) / GC_KS);
+  const int ROW = GC_KS * gc_slice_pad(SL);
+  const int budget = sm_budget > 0 ? sm_budget : sm_count();
+  int max_clusters = budget / GC_CLUSTER;
+  if (max_clusters < 1) max_clusters = 1;
+  int Bc = (int)((B + max_clusters - 1) / max_clusters);
+  Bc = (Bc + 3) / 4 * 4;
+  const size_t per_row = backward ? (size_t)(2 * ROW + 2 * GC_MAX_UNITS) * 4 : (size_t)ROW * 4;
+  const int cap = (int)((200 * 1024) / per_row) / 4 * 4;
+  if (Bc > cap) Bc = cap;
+  if (Bc < 4) Bc = 4;
+  ClusterPlan p;
+  p.Bc = Bc;
+  p.nclusters = (int)((B + Bc - 1) / Bc);
+  const int need = (SL + 3) / 4;
+  p.ch = need <= 2 ? 2 : need <= 4 ? 4 : need <= 6 ? 6 : need <= 8 ? 8 : 10;
+  p.smem = per_row * Bc;
+  return p;
+}
+
+template <class Args, class Kern>
+int launch_cluster(Kern kern, const Args& args, const ClusterPlan& p, cudaStream_t s, const char* name) {
+  NM_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(p.nclusters * GC_CLUSTER));
+  cfg.blockDim = dim3(GC_THREADS);
+  cfg.dynamicSmemBytes = p.smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = GC_CLUSTER;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  NM_CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, args));
+  NM_LAUNCH_CHECK(name);
+  return NM_OK;
+}
+
+#define NM_GC_DISPATCH(KERN, args, plan, s, name)                                     \
+  switch ((plan).ch) {                                                                \
+    case 2: return launch_cluster(KERN<2>, args, plan, s, name);                      \
+    case 4: return launch_cluster(KERN<4>, args, plan, s, name);                      \
+    case 6: return launch_cluster(KERN<6>, args, plan, s, name);                      \
+    case 8: return launch_cluster(KERN<8>, args, plan, s, name);                      \
+    default: return launch_cluster(KERN<10>, args, plan, s, name);                    \
+  }
+
+}  // namespace
+
 extern "C" {
 
 int nm_gru_seq_fwd(const float* xproj, const float* Wgh, const float* Wch, const float* h0,
                    const int32_t* lengths, const float* drop_mask, int reverse, float* states,
                    float* raw_states, float* final_state, float* gates, float* hprev, float* rh,
-                   int64_t B, int64_t T, int64_t H, void* stream) {
+                   int64_t B, int64_t T, int64_t H, int sm_budget, void* stream) {
   NM_REQUIRE(xproj && Wgh && Wch && states && final_state && gates && hprev && rh, NM_E_INVALID,
              "nm_gru_seq_fwd: null pointer");
   NM_REQUIRE(B > 0 && T > 0 && H > 0, NM_E_INVALID, "nm_gru_seq_fwd: bad sizes B=%lld T=%lld H=%lld",
              (long long)B, (long long)T, (long long)H);
   cudaStream_t s = (cudaStream_t)stream;
+  if (cluster_path_ok(H)) {
+    GcFwdArgs a{xproj, Wgh, Wch, h0, lengths, drop_mask, states, raw_states, final_state, gates,
+                hprev, rh, (int)B, (int)T, (int)H, 0, reverse};
+    const ClusterPlan p = plan_clusters(B, H, sm_budget, false);
+    a.Bc = p.Bc;
+    NM_GC_DISPATCH(gru_seq_fwd_cluster_kernel, a, p, s, "nm_gru_seq_fwd(cluster)");
+  }
   const int64_t t_first = reverse ? T - 1 : 0;
   // seed the state history with h0 (or zeros): hprev[:, t_first, :]
   if (h0)
@@ -164,11 +245,18 @@ int nm_gru_seq_bwd(const float* Wgh, const float* Wch, const int32_t* lengths,
                    const float* drop_mask, int reverse, const float* gates, const float* hprev,
                    const float* dstates, const float* draw, const float* dfinal,
                    float* dxproj, float* dh0, float* work, int64_t B, int64_t T, int64_t H,
-                   void* stream) {
+                   int sm_budget, void* stream) {
   NM_REQUIRE(Wgh && Wch && gates && hprev && dxproj && work, NM_E_INVALID,
              "nm_gru_seq_bwd: null pointer");
   NM_REQUIRE(B > 0 && T > 0 && H > 0, NM_E_INVALID, "nm_gru_seq_bwd: bad sizes");
   cudaStream_t s = (cudaStream_t)stream;
+  if (cluster_path_ok(H)) {
+    GcBwdArgs a{Wgh, Wch, lengths, drop_mask, gates, hprev, dstates, draw, dfinal, dxproj, dh0,
+                (int)B, (int)T, (int)H, 0, reverse};
+    const ClusterPlan p = plan_clusters(B, H, sm_budget, true);
+    a.Bc = p.Bc;
+    NM_GC_DISPATCH(gru_seq_bwd_cluster_kernel, a, p, s, "nm_gru_seq_bwd(cluster)");
+  }
   float* dcarry = work;
   float* dhp = work + B * H;
   if (dfinal)

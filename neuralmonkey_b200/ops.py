@@ -246,7 +246,7 @@ def layer_norm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor,
 # ---------------------------------------------------------------------------
 class _GRULayer(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, wg, bg, wc, bc, h0, lengths, reverse, drop_mask):
+    def forward(ctx, x, wg, bg, wc, bc, h0, lengths, reverse, drop_mask, sm_budget):
         # x [B,T,E]; wg [E+H,2H], bg [2H]; wc [E+H,H], bc [H]   (TF GRUCell kernels)
         bsz, t, e = x.shape
         h = wc.size(1)
@@ -264,10 +264,11 @@ class _GRULayer(torch.autograd.Function):
         dm = drop_mask.contiguous() if drop_mask is not None else None
         call("nm_gru_seq_fwd", ptr(xproj), ptr(wg[e:]), ptr(wc[e:]), ptr(h0c), ptr(lengths), ptr(dm),
              int(reverse), ptr(states), ptr(raw), ptr(final), ptr(gates), ptr(hprev), ptr(rh), bsz, t,
-             h, lib.stream())
+             h, int(sm_budget), lib.stream())
         ctx.save_for_backward(x2, wg, wc, lengths, gates, hprev, rh, dm)
         ctx.dims = (bsz, t, e, h)
         ctx.reverse = reverse
+        ctx.sm_budget = sm_budget
         ctx.has_h0 = h0 is not None
         ctx.sinks = (_sink(wg), _sink(bg), _sink(wc), _sink(bc))
         return states, final, (raw if raw is not None else states)
@@ -290,7 +291,7 @@ class _GRULayer(torch.autograd.Function):
         work = torch.empty(2 * bsz * h, device=dev, dtype=torch.float32)
         call("nm_gru_seq_bwd", ptr(wg[e:]), ptr(wc[e:]), ptr(lengths), ptr(dm), int(ctx.reverse),
              ptr(gates), ptr(hprev), ptr(dstates), ptr(draw), ptr(dfinal), ptr(dxproj), ptr(dh0),
-             ptr(work), bsz, t, h, lib.stream())
+             ptr(work), bsz, t, h, int(ctx.sm_budget), lib.stream())
         dzg, dzc = dxproj[:, :2 * h], dxproj[:, 2 * h:]
         sg, sbg, sc, sbc = ctx.sinks
         # weight gradients: rows [:E] from x, rows [E:] from the recurrent operand
@@ -312,14 +313,14 @@ class _GRULayer(torch.autograd.Function):
             gemm(dzc, wc[:e], dx, trans_b=True, beta=1.0)
             dx = dx.view(bsz, t, e)
         return (dx, None if sg is not None else dwg, dbg, None if sc is not None else dwc, dbc,
-                dh0, None, None, None)
+                dh0, None, None, None, None)
 
 
 def gru_layer(x: torch.Tensor, gates_kernel: torch.Tensor, gates_bias: torch.Tensor,
               cand_kernel: torch.Tensor, cand_bias: torch.Tensor,
               h0: Optional[torch.Tensor] = None, lengths: Optional[torch.Tensor] = None,
               reverse: bool = False,
-              drop_mask: Optional[torch.Tensor] = None):
+              drop_mask: Optional[torch.Tensor] = None, sm_budget: int = 0):
     """dynamic_rnn over a TF-1.12 GRUCell (encoders/recurrent.py:71-110).
 
     Returns (outputs [B,T,H], final state [B,H], raw outputs [B,T,H] = outputs before
@@ -327,7 +328,7 @@ def gru_layer(x: torch.Tensor, gates_kernel: torch.Tensor, gates_bias: torch.Ten
     each length are zero and the state is carried, with `reverse` the sequence is walked
     backwards inside its length (tf.reverse_sequence semantics)."""
     return _GRULayer.apply(x, gates_kernel, gates_bias, cand_kernel, cand_bias, h0, lengths, reverse,
-                           drop_mask)
+                           drop_mask, sm_budget)
 
 
 # ---------------------------------------------------------------------------
