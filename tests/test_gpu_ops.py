@@ -50,7 +50,8 @@ def test_layer_norm_fwd_bwd(dims):
 
 @pytest.mark.parametrize("reverse", [False, True])
 @pytest.mark.parametrize("use_lengths", [False, True])
-@pytest.mark.parametrize("dims", [(5, 6, 11, 7), (9, 4, 32, 32)])
+@pytest.mark.parametrize("dims", [(5, 6, 11, 7), (9, 4, 32, 32), (7, 6, 12, 300), (70, 3, 16, 64),
+                                  (3, 5, 8, 100)])
 def test_gru_layer_fwd_bwd(reverse, use_lengths, dims):
     from neuralmonkey_b200 import ops
     ops.set_gemm_backend("simt")
