@@ -134,6 +134,12 @@ int nm_gru_seq_fwd(const float* xproj, const float* Wgh, const float* Wch,
                    float* raw_states, float* final_state, float* gates,
                    float* hprev, float* rh, int64_t B, int64_t T, int64_t H,
                    int sm_budget, void* stream);
+/* Number of 8-CTA clusters of the persistent GRU kernel that are co-resident on the
+ * current device (forward: backward=0).  Diagnostic. */
+int nm_gru_resident_clusters(int backward);
+/* Diagnostic: 8 int64 device counters receiving the cycles CTA 0 of the forward cluster
+ * kernel spends per section (phase 1: load, dot, gates, barrier; phase 2: same). NULL = off. */
+int nm_gru_debug_profile(void* counters);
 /* Inputs: dstates [B,T,H] (may be NULL), dfinal [B,H] (may be NULL).
  * Outputs: dxproj [B,T,3H] (pre-activation grads = grads of xproj), dh0 [B,H]
  * (may be NULL).  Weight grads are NOT produced here: they are the hoisted

@@ -147,23 +147,56 @@ struct ClusterPlan {
   size_t smem;
 };
 
+// Clusters of 8 must fit inside one GPC: fewer than sm_count()/8 of them are co-resident.
+// Measured once per kernel with cudaOccupancyMaxActiveClusters; a second wave would double
+// the time of the whole sequence, so the batch slice per cluster is sized for ONE wave.
+template <class Kern>
+int max_active_clusters(Kern kern, size_t smem) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(GC_CLUSTER * 64);
+  cfg.blockDim = dim3(GC_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = GC_CLUSTER;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  int n = 0;
+  if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess ||
+      cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess || n < 1) {
+    cudaGetLastError();
+    n = sm_count() / GC_CLUSTER / 2;
+  }
+  return n;
+}
+
+int resident_clusters(bool backward) {
+  static int cached[2] = {0, 0};
+  if (cached[backward] == 0)
+    cached[backward] = backward ? max_active_clusters(gru_seq_bwd_cluster_kernel<3>, 64 * 1024)
+                                : max_active_clusters(gru_seq_fwd_cluster_kernel<3>, 64 * 1024);
+  return cached[backward];
+}
+
 ClusterPlan plan_clusters(int64_t B, int64_t H, int sm_budget, bool backward) {
-  const int SL = (int)((H + GC_KS - 1) / GC_KS);
-  const int ROW = GC_KS * gc_slice_pad(SL);
-  const int budget = sm_budget > 0 ? sm_budget : sm_count();
-  int max_clusters = budget / GC_CLUSTER;
+  const int SL32 = (int)((H + GC_SLICES - 1) / GC_SLICES);
+  ClusterPlan p;
+  p.ch = (SL32 + 3) / 4;  // 1, 2 or 3 for H <= 320
+  const int ROW = GC_SLICES * 4 * (p.ch | 1);
+  int max_clusters = resident_clusters(backward);
+  if (sm_budget > 0 && sm_budget / GC_CLUSTER < max_clusters) max_clusters = sm_budget / GC_CLUSTER;
   if (max_clusters < 1) max_clusters = 1;
   int Bc = (int)((B + max_clusters - 1) / max_clusters);
   Bc = (Bc + 3) / 4 * 4;
-  const size_t per_row = backward ? (size_t)(2 * ROW + 2 * GC_MAX_UNITS) * 4 : (size_t)ROW * 4;
+  const size_t per_row = backward ? (size_t)(2 * ROW + 3 * GC_MAX_UNITS) * 4
+                                  : (size_t)(ROW + 7 * GC_MAX_UNITS) * 4;
   const int cap = (int)((200 * 1024) / per_row) / 4 * 4;
   if (Bc > cap) Bc = cap;
   if (Bc < 4) Bc = 4;
-  ClusterPlan p;
   p.Bc = Bc;
   p.nclusters = (int)((B + Bc - 1) / Bc);
-  const int need = (SL + 3) / 4;
-  p.ch = need <= 2 ? 2 : need <= 4 ? 4 : need <= 6 ? 6 : need <= 8 ? 8 : 10;
   p.smem = per_row * Bc;
   return p;
 }
@@ -188,18 +221,26 @@ int launch_cluster(Kern kern, const Args& args, const ClusterPlan& p, cudaStream
   return NM_OK;
 }
 
-#define NM_GC_DISPATCH(KERN, args, plan, s, name)                                     \
-  switch ((plan).ch) {                                                                \
-    case 2: return launch_cluster(KERN<2>, args, plan, s, name);                      \
-    case 4: return launch_cluster(KERN<4>, args, plan, s, name);                      \
-    case 6: return launch_cluster(KERN<6>, args, plan, s, name);                      \
-    case 8: return launch_cluster(KERN<8>, args, plan, s, name);                      \
-    default: return launch_cluster(KERN<10>, args, plan, s, name);                    \
+#define NM_GC_DISPATCH(KERN, args, plan, s, name)                   \
+  switch ((plan).ch) {                                              \
+    case 1: return launch_cluster(KERN<1>, args, plan, s, name);    \
+    case 2: return launch_cluster(KERN<2>, args, plan, s, name);    \
+    default: return launch_cluster(KERN<3>, args, plan, s, name);   \
   }
 
 }  // namespace
 
 extern "C" {
+
+int nm_gru_resident_clusters(int backward) { return resident_clusters(backward != 0); }
+
+static long long* g_gru_prof = nullptr;
+/* Diagnostic: device buffer of 8 int64 cycle counters filled by CTA 0 of the next forward
+ * cluster launches (load, dot, gate, barrier for each of the two phases); NULL disables. */
+int nm_gru_debug_profile(void* counters) {
+  g_gru_prof = reinterpret_cast<long long*>(counters);
+  return NM_OK;
+}
 
 int nm_gru_seq_fwd(const float* xproj, const float* Wgh, const float* Wch, const float* h0,
                    const int32_t* lengths, const float* drop_mask, int reverse, float* states,
@@ -212,7 +253,7 @@ int nm_gru_seq_fwd(const float* xproj, const float* Wgh, const float* Wch, const
   cudaStream_t s = (cudaStream_t)stream;
   if (cluster_path_ok(H)) {
     GcFwdArgs a{xproj, Wgh, Wch, h0, lengths, drop_mask, states, raw_states, final_state, gates,
-                hprev, rh, (int)B, (int)T, (int)H, 0, reverse};
+                hprev, rh, (int)B, (int)T, (int)H, 0, reverse, g_gru_prof};
     const ClusterPlan p = plan_clusters(B, H, sm_budget, false);
     a.Bc = p.Bc;
     NM_GC_DISPATCH(gru_seq_fwd_cluster_kernel, a, p, s, "nm_gru_seq_fwd(cluster)");
