@@ -30,7 +30,8 @@ namespace nm {
 constexpr int TC_BM = 128;
 constexpr int TC_BK = 32;                      // fp32 elements = 128 bytes = one swizzle row
 constexpr int TC_UMMA_K = 8;                   // tf32: 32 bytes per instruction
-constexpr int TC_THREADS = 192;                // 6 warps
+constexpr int TC_THREADS = 320;                // TMA warp, MMA warp, 8 epilogue warps
+constexpr int TC_EPI_WARPS = 8;
 constexpr int TC_A_BYTES = TC_BM * TC_BK * 4;  // 16 KB
 constexpr int TC_SMEM_BUDGET = 200 * 1024;
 
@@ -132,106 +133,121 @@ __device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo_bytes,
 }
 
 // ---------------------------------------------------------------------------
-// epilogue for one 32-column chunk owned by one thread (= one output row)
+// epilogue for one 32-column chunk owned by one thread (= one output row).
+// The epilogue runs once per output element, so it is written for instruction count:
+// 32-bit column arithmetic, bias fetched as 8 x 16-byte uniform loads, exp as one FFMA +
+// one MUFU.EX2, and the rare cases (the <unk> column, the row's target column, ragged
+// right edge) handled in branches only the affected chunk takes.
 // ---------------------------------------------------------------------------
 struct RowStats {
   float mx, sum, tgt;
   int32_t arg;
 };
 
-__device__ __forceinline__ void epilogue_chunk(const TcEpilogue& e, const float (&acc)[32],
-                                               int64_t row, int64_t col0, int64_t M, int64_t N,
-                                               RowStats& st, int64_t target, float row_lse,
-                                               float row_w) {
-  if (row >= M || col0 >= N) return;
-  const int ncols = (int)min((int64_t)32, N - col0);
-  if (e.mode == TC_EPI_DENSE) {
-    float* c = e.C + row * e.ldc + col0;
-    const bool vec = (ncols == 32) && ((e.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(e.C) & 15) == 0) &&
-                     ((col0 & 3) == 0);
-    if (vec) {
+constexpr float TC_LOG2E = 1.4426950408889634f;
+
+__device__ __forceinline__ void load_bias32(const float* __restrict__ bias, int col0, int ncols,
+                                            float (&b)[32]) {
+  if (bias == nullptr) {
 #pragma unroll
-      for (int j = 0; j < 32; j += 4) {
-        float4 o;
-        float x[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          float v = acc[j + i] + (e.bias ? __ldg(e.bias + col0 + j + i) : 0.f);
-          x[i] = apply_act(v, e.act);
-        }
-        if (e.beta != 0.f) {
-          const float4 old = *reinterpret_cast<const float4*>(c + j);
-          x[0] += old.x; x[1] += old.y; x[2] += old.z; x[3] += old.w;
-        }
-        o.x = x[0]; o.y = x[1]; o.z = x[2]; o.w = x[3];
-        *reinterpret_cast<float4*>(c + j) = o;
-      }
-    } else {
-#pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        if (j < ncols) {
-          float v = acc[j] + (e.bias ? __ldg(e.bias + col0 + j) : 0.f);
-          v = apply_act(v, e.act);
-          if (e.beta != 0.f) v += c[j];
-          c[j] = v;
-        }
-      }
-    }
+    for (int j = 0; j < 32; ++j) b[j] = 0.f;
     return;
   }
-  // xent modes: x = acc + bias + unk mask
-  float x[32];
+  if (ncols == 32 && ((reinterpret_cast<uintptr_t>(bias + col0) & 15) == 0)) {
 #pragma unroll
-  for (int j = 0; j < 32; ++j) {
-    float v = acc[j] + ((e.bias && j < ncols) ? __ldg(e.bias + col0 + j) : 0.f);
-    if (col0 + j == e.unk_index) v += -1e9f;
-    x[j] = v;
+    for (int j = 0; j < 32; j += 4) {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(bias + col0 + j));
+      b[j] = v.x; b[j + 1] = v.y; b[j + 2] = v.z; b[j + 3] = v.w;
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) b[j] = (j < ncols) ? __ldg(bias + col0 + j) : 0.f;
   }
-  if (e.mode == TC_EPI_XENT_FWD) {
-    float cmx = -INFINITY;
-    int carg = 0;
+}
+
+__device__ __forceinline__ void store32(float* __restrict__ c, const float (&x)[32], int ncols,
+                                        bool vec_ok) {
+  if (vec_ok && ncols == 32) {
+#pragma unroll
+    for (int j = 0; j < 32; j += 4)
+      *reinterpret_cast<float4*>(c + j) = make_float4(x[j], x[j + 1], x[j + 2], x[j + 3]);
+  } else {
 #pragma unroll
     for (int j = 0; j < 32; ++j)
-      if (j < ncols && x[j] > cmx) { cmx = x[j]; carg = j; }
-    if (cmx > st.mx) {  // strict: earlier chunks (lower columns) win ties
-      st.sum *= __expf(st.mx - cmx);
-      st.mx = cmx;
-      st.arg = (int32_t)(col0 + carg);
+      if (j < ncols) c[j] = x[j];
+  }
+}
+
+// mode is a compile-time constant so each kernel instance carries one epilogue only.
+template <int MODE>
+__device__ __forceinline__ void epilogue_chunk(const TcEpilogue& e, float (&x)[32], int64_t row,
+                                               int col0, int64_t M, int N, RowStats& st,
+                                               int target, float row_lse2, float row_w,
+                                               bool vec_ok) {
+  if (row >= M || col0 >= N) return;
+  const int ncols = min(32, N - col0);
+  float b[32];
+  load_bias32(e.bias, col0, ncols, b);
+  if (MODE == TC_EPI_DENSE) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) x[j] = apply_act(x[j] + b[j], e.act);
+    float* c = e.C + row * e.ldc + col0;
+    if (e.beta != 0.f) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (j < ncols) x[j] += c[j];
     }
+    store32(c, x, ncols, vec_ok);
+    return;
+  }
+#pragma unroll
+  for (int j = 0; j < 32; ++j) x[j] += b[j];
+  const int unk_rel = (int)e.unk_index - col0;  // rare: only the chunk holding <unk>
+  if (unk_rel >= 0 && unk_rel < 32) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j)
+      if (j == unk_rel) x[j] += -1e9f;
+  }
+  if (MODE == TC_EPI_XENT_FWD) {
+    if (ncols < 32) {  // ragged right edge: padding columns must not win the max
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (j >= ncols) x[j] = -INFINITY;
+    }
+    float cmx = x[0];
+#pragma unroll
+    for (int j = 1; j < 32; ++j) cmx = fmaxf(cmx, x[j]);
+    if (cmx > st.mx) {  // strict: earlier chunks (lower columns) keep ties
+      int carg = 0;
+#pragma unroll
+      for (int j = 31; j >= 0; --j)
+        if (x[j] == cmx) carg = j;  // lowest index among equals
+      st.sum *= exp2f((st.mx - cmx) * TC_LOG2E);
+      st.mx = cmx;
+      st.arg = col0 + carg;
+    }
+    const float m2 = st.mx * TC_LOG2E;
     float s = 0.f;
 #pragma unroll
-    for (int j = 0; j < 32; ++j)
-      if (j < ncols) s += __expf(x[j] - st.mx);
+    for (int j = 0; j < 32; ++j) s += exp2f(fmaf(x[j], TC_LOG2E, -m2));
     st.sum += s;
-    if (target >= col0 && target < col0 + ncols) {
+    const int t_rel = target - col0;  // rare: the chunk holding this row's target
+    if (t_rel >= 0 && t_rel < ncols) {
 #pragma unroll
       for (int j = 0; j < 32; ++j)
-        if (col0 + j == target) st.tgt = x[j];
+        if (j == t_rel) st.tgt = x[j];
     }
-    if (e.C) {
-      float* c = e.C + row * e.ldc + col0;
+    if (e.C) store32(e.C + row * e.ldc + col0, x, ncols, vec_ok);
+  } else {  // TC_EPI_XENT_BWD: (softmax - onehot) * row weight
+#pragma unroll
+    for (int j = 0; j < 32; ++j) x[j] = exp2f(fmaf(x[j], TC_LOG2E, -row_lse2)) * row_w;
+    const int t_rel = target - col0;
+    if (t_rel >= 0 && t_rel < ncols) {
 #pragma unroll
       for (int j = 0; j < 32; ++j)
-        if (j < ncols) c[j] = x[j];
+        if (j == t_rel) x[j] -= row_w;
     }
-  } else {  // TC_EPI_XENT_BWD
-    float* c = e.C + row * e.ldc + col0;
-    const bool vec = (ncols == 32) && ((e.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(e.C) & 15) == 0) &&
-                     ((col0 & 3) == 0);
-#pragma unroll
-    for (int j = 0; j < 32; ++j) {
-      const float p = __expf(x[j] - row_lse);
-      x[j] = (p - ((col0 + j == target) ? 1.f : 0.f)) * row_w;
-    }
-    if (vec) {
-#pragma unroll
-      for (int j = 0; j < 32; j += 4)
-        *reinterpret_cast<float4*>(c + j) = make_float4(x[j], x[j + 1], x[j + 2], x[j + 3]);
-    } else {
-#pragma unroll
-      for (int j = 0; j < 32; ++j)
-        if (j < ncols) c[j] = x[j];
-    }
+    store32(e.C + row * e.ldc + col0, x, ncols, vec_ok);
   }
 }
 
@@ -244,7 +260,7 @@ struct MnDesc {
   uint32_t layout, sbo, lbo, kadv;
 };
 
-template <int BN, bool A_MN, bool B_MN>
+template <int BN, bool A_MN, bool B_MN, int MODE>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                int64_t M, int64_t N, int64_t K, TcEpilogue epi, MnDesc mn) {
@@ -273,7 +289,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
-      mbar_init(tempty_bar(a), 4);  // one arrive per epilogue warp
+      mbar_init(tempty_bar(a), TC_EPI_WARPS);  // one arrive per epilogue warp
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -366,8 +382,14 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       }
     }
   } else {
-    // ===================== epilogue warps (2..5) =====================
-    const int quad = warp & 3;  // TMEM lanes [32*quad, 32*quad+32)
+    // ===================== epilogue warps (2..9) =====================
+    // Two warps per TMEM lane quadrant (quadrant = warp_idx % 4 is a hardware rule); the
+    // pair splits the tile's 32-column chunks (even / odd), which also gives every SM
+    // sub-partition two epilogue warps to overlap their latencies.
+    const int quad = warp & 3;                // TMEM lanes [32*quad, 32*quad+32)
+    const int half = (warp - 2) >> 2;         // 0: even chunks, 1: odd chunks
+    const bool vec_ok = ((epi.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(epi.C) & 15) == 0);
+    const int n32 = (int)N;
     int64_t it = 0;
     for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       const int acc = (int)(it & 1);
@@ -376,25 +398,27 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       const int64_t row = tm * TC_BM + quad * 32 + lane;
       mbar_wait(tfull_bar(acc), acc_phase);
       tcgen05_fence_after();
-      RowStats st{-INFINITY, 0.f, -INFINITY, 0};
-      int64_t target = -1;
-      float row_lse = 0.f, row_w = 0.f;
-      if (epi.mode != TC_EPI_DENSE && row < M) {
-        if (epi.targets) target = epi.targets[row];
-        if (epi.mode == TC_EPI_XENT_BWD) {
-          row_lse = epi.lse[row];
+      RowStats st{-INFINITY, 0.f, -INFINITY, 0x7fffffff};
+      int target = -1;
+      float row_lse2 = 0.f, row_w = 0.f;
+      if (MODE != TC_EPI_DENSE && row < M) {
+        if (epi.targets) target = (int)epi.targets[row];
+        if (MODE == TC_EPI_XENT_BWD) {
+          row_lse2 = epi.lse[row] * TC_LOG2E;
           row_w = (epi.weights ? epi.weights[row] : 1.f) * epi.scale[0];
         }
       }
       const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN);
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
+      for (int c = half; c < BN / 32; c += 2) {
         float v[32];
         tmem_ld32(t_row + (uint32_t)(c * 32), v);
-        epilogue_chunk(epi, v, row, tn * BN + c * 32, M, N, st, target, row_lse, row_w);
+        epilogue_chunk<MODE>(epi, v, row, (int)(tn * BN) + c * 32, M, n32, st, target, row_lse2,
+                             row_w, vec_ok);
       }
-      if (epi.mode == TC_EPI_XENT_FWD && row < M)
-        epi.part[row * tiles_n + tn] = make_float4(st.mx, st.sum, __int_as_float(st.arg), st.tgt);
+      if (MODE == TC_EPI_XENT_FWD && row < M)
+        epi.part[(row * tiles_n + tn) * 2 + half] =
+            make_float4(st.mx, st.sum, __int_as_float(st.arg), st.tgt);
       tcgen05_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty_bar(acc));
@@ -488,11 +512,11 @@ bool tc_gemm_supported(int transA, int transB, int64_t M, int64_t N, int64_t K, 
   return true;
 }
 
-template <int BN, bool A_MN, bool B_MN>
+template <int BN, bool A_MN, bool B_MN, int MODE>
 static int launch_cfg(const CUtensorMap& ma, const CUtensorMap& mb, int64_t M, int64_t N, int64_t K,
                       const TcEpilogue& epi, cudaStream_t s) {
   using Cfg = TcCfg<BN>;
-  auto kern = tc_gemm_kernel<BN, A_MN, B_MN>;
+  auto kern = tc_gemm_kernel<BN, A_MN, B_MN, MODE>;
   static bool attr_done = false;
   if (!attr_done) {
     NM_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
@@ -531,16 +555,24 @@ int tc_gemm_launch(int transA, int transB, int64_t M, int64_t N, int64_t K, cons
   if (!b_mn) rc = make_map(&mb, B, N, K, ldb, TC_BK, (uint32_t)bn, false);
   else       rc = make_map(&mb, B, K, N, ldb, 32, TC_BK, true);
   if (rc) return rc;
-#define NM_TC_DISPATCH(BN_)                                                            \
-  do {                                                                                 \
-    if (!a_mn && !b_mn) return launch_cfg<BN_, false, false>(ma, mb, M, N, K, epi, s); \
-    if (!a_mn && b_mn) return launch_cfg<BN_, false, true>(ma, mb, M, N, K, epi, s);   \
-    if (a_mn && !b_mn) return launch_cfg<BN_, true, false>(ma, mb, M, N, K, epi, s);   \
-    return launch_cfg<BN_, true, true>(ma, mb, M, N, K, epi, s);                       \
+#define NM_TC_DISPATCH(BN_, MODE_)                                                             \
+  do {                                                                                         \
+    if (!a_mn && !b_mn) return launch_cfg<BN_, false, false, MODE_>(ma, mb, M, N, K, epi, s);  \
+    if (!a_mn && b_mn) return launch_cfg<BN_, false, true, MODE_>(ma, mb, M, N, K, epi, s);    \
+    if (a_mn && !b_mn) return launch_cfg<BN_, true, false, MODE_>(ma, mb, M, N, K, epi, s);    \
+    return launch_cfg<BN_, true, true, MODE_>(ma, mb, M, N, K, epi, s);                        \
   } while (0)
-  if (bn == 64) NM_TC_DISPATCH(64);
-  if (bn == 128) NM_TC_DISPATCH(128);
-  NM_TC_DISPATCH(256);
+  if (epi.mode == TC_EPI_XENT_FWD) {  // A is always K-major for the vocabulary projection
+    if (b_mn) return launch_cfg<256, false, true, TC_EPI_XENT_FWD>(ma, mb, M, N, K, epi, s);
+    return launch_cfg<256, false, false, TC_EPI_XENT_FWD>(ma, mb, M, N, K, epi, s);
+  }
+  if (epi.mode == TC_EPI_XENT_BWD) {
+    if (b_mn) return launch_cfg<256, false, true, TC_EPI_XENT_BWD>(ma, mb, M, N, K, epi, s);
+    return launch_cfg<256, false, false, TC_EPI_XENT_BWD>(ma, mb, M, N, K, epi, s);
+  }
+  if (bn == 64) NM_TC_DISPATCH(64, TC_EPI_DENSE);
+  if (bn == 128) NM_TC_DISPATCH(128, TC_EPI_DENSE);
+  NM_TC_DISPATCH(256, TC_EPI_DENSE);
 #undef NM_TC_DISPATCH
 }
 

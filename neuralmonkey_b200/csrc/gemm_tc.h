@@ -26,7 +26,8 @@ struct TcEpilogue {
   const float* weights;    // [M] or null (xent_bwd)
   const float* lse;        // [M] (xent_bwd)
   const float* scale;      // device scalar (xent_bwd)
-  float4* part;            // [M][ceil(N/TC_XENT_BN)] (xent_fwd): (max, sumexp, argmax bits, target logit or -inf)
+  float4* part;            // [M][2*ceil(N/TC_XENT_BN)] (xent_fwd): (max, sumexp, argmax bits,
+                           //   target logit or -inf) per (row, n-tile, epilogue half)
 };
 
 // True when the operands can be addressed by TMA (16-byte aligned rows and bases).

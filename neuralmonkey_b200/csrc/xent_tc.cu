@@ -51,7 +51,7 @@ extern "C" {
 
 int64_t nm_logits_xent_scratch(int64_t M, int64_t V) {
   if (M <= 0 || V <= 0) return 0;
-  return M * ceil_div(V, TC_XENT_BN) * 4;
+  return M * ceil_div(V, TC_XENT_BN) * 2 * 4;  // two epilogue halves per (row, n-tile)
 }
 
 int nm_logits_xent_fwd(const float* X, int64_t ldx, const float* W, int64_t ldw, int transW,
@@ -77,7 +77,7 @@ int nm_logits_xent_fwd(const float* X, int64_t ldx, const float* W, int64_t ldw,
   epi.part = reinterpret_cast<float4*>(part);
   const int rc = tc_gemm_launch(0, transW, M, V, K, X, ldx, W, ldw, epi, s);
   if (rc) return rc;
-  const int64_t tiles_n = ceil_div(V, TC_XENT_BN);
+  const int64_t tiles_n = 2 * ceil_div(V, TC_XENT_BN);  // partials per row
   xent_combine_kernel<<<(unsigned)ceil_div(M, 8), 256, 0, s>>>(reinterpret_cast<const float4*>(part), M,
                                                               tiles_n, targets, weights, lse, xent,
                                                               argmax);

@@ -1,0 +1,148 @@
+"""Execution manager (API of neuralmonkey/tf_manager.py:29-306).
+
+The class keeps its historical name because every Neural Monkey INI instantiates
+`tf_manager.TensorFlowManager`; there is no TensorFlow behind it.  `execute()` feeds one batch
+to the feedables and runs the executables of the given trainers / runners on the CUDA
+kernels; the n-best checkpoint bookkeeping (`variables.data[.i]`, `variables.data.best`) is
+kept; checkpoints are `torch.save`d {TF-style variable name: tensor} dictionaries.
+"""
+import os
+from typing import Any, List, Set, Union
+
+import numpy as np
+import torch
+
+from neuralmonkey_b200 import runtime
+from neuralmonkey_b200.logging import log
+from neuralmonkey_b200.model.feedable import Feedable
+from neuralmonkey_b200.runners.base_runner import ExecutionResult, GraphExecutor
+
+
+class TensorFlowManager:
+    # pylint: disable=too-many-arguments
+    def __init__(self, num_sessions: int, num_threads: int, save_n_best: int = 1,
+                 minimize_metric: bool = False, gpu_allow_growth: bool = True,
+                 per_process_gpu_memory_fraction: float = 1.0,
+                 enable_tf_debug: bool = False) -> None:
+        if num_sessions < 1:
+            raise ValueError("num_sessions must be positive")
+        if num_sessions != 1:
+            raise NotImplementedError("model ensembles (num_sessions > 1) are not built yet")
+        self.num_sessions = num_sessions
+        self.num_threads = num_threads  # host threads only matter for the CPU reference
+        self.saver_max_to_keep = save_n_best
+        self.minimize_metric = minimize_metric
+        self.best_score_index = 0
+        self.best_score_epoch = 0
+        self.best_score_batch = 0
+        init_score = np.inf if self.minimize_metric else -np.inf
+        self.saved_scores = [init_score for _ in range(self.saver_max_to_keep)]
+        self.best_vars_file = None
+        self.variables_files = []  # type: List[str]
+        self.sessions = [self]  # kept for code that iterates over sessions
+
+    @property
+    def best_score(self) -> float:
+        return self.saved_scores[self.best_score_index]
+
+    def _is_better(self, score1: float, score2: float) -> bool:
+        return score1 < score2 if self.minimize_metric else score1 > score2
+
+    def _argworst(self, scores: List[float]) -> int:
+        return int(np.argmax(scores)) if self.minimize_metric else int(np.argmin(scores))
+
+    def _update_best_vars(self, var_index: int) -> None:
+        best_vars_prefix = os.path.basename(self.variables_files[var_index])
+        with open(self.best_vars_file, "w", encoding="utf-8") as var_file:
+            var_file.write(best_vars_prefix)
+
+    def init_saving(self, vars_prefix: str) -> None:
+        if self.saver_max_to_keep == 1:
+            self.variables_files = [vars_prefix]
+        else:
+            self.variables_files = ["{}.{}".format(vars_prefix, i)
+                                    for i in range(self.saver_max_to_keep)]
+        self.best_vars_file = "{}.best".format(vars_prefix)
+        self._update_best_vars(var_index=0)
+
+    def validation_hook(self, score: float, epoch: int, batch: int) -> None:
+        """Keep the n best checkpoints (tf_manager.py:133-155)."""
+        if self._is_better(score, self.best_score):
+            self.best_score_epoch = epoch
+            self.best_score_batch = batch
+        worst_index = self._argworst(self.saved_scores)
+        worst_score = self.saved_scores[worst_index]
+        if self._is_better(score, worst_score):
+            worst_var_file = self.variables_files[worst_index]
+            self.save(worst_var_file)
+            self.saved_scores[worst_index] = score
+            log("Variable file saved in {}".format(worst_var_file))
+            if self._is_better(score, self.best_score):
+                self.best_score_index = worst_index
+                self._update_best_vars(self.best_score_index)
+                log("Best scores saved so far: {}".format(self.saved_scores))
+        log("Best scores saved so far: {}".format(self.saved_scores))
+
+    # -- execution ---------------------------------------------------------------------------
+    # pylint: disable=too-many-arguments
+    def execute(self, batch, feedables: Set[Feedable], runners: List[GraphExecutor],
+                train: bool = False, compute_losses: bool = True,
+                summaries: bool = True) -> List[ExecutionResult]:
+        """Feed `batch` and run every executor on it (tf_manager.py:188-225)."""
+        for feedable in feedables:
+            feedable.feed_dict(batch, train)
+        executables = [runner.get_executable(compute_losses=compute_losses, summaries=summaries,
+                                             num_sessions=self.num_sessions) for runner in runners]
+        for executable in executables:
+            executable.execute()
+        return [executable.result for executable in executables]
+
+    # -- checkpoints ---------------------------------------------------------------------------
+    def save(self, variable_files: Union[str, List[str]]) -> None:
+        if isinstance(variable_files, str):
+            variable_files = [variable_files]
+        if len(variable_files) != self.num_sessions:
+            raise Exception("Provided {} files for restoring {} sessions.".format(
+                len(variable_files), self.num_sessions))
+        arena = runtime.arena()
+        for path in variable_files:
+            torch.save({"variables": arena.state_dict(),
+                        "adam_m": arena.adam_m.detach().cpu(), "adam_v": arena.adam_v.detach().cpu(),
+                        "order": list(arena.order)}, path)
+
+    def restore(self, variable_files: Union[str, List[str]]) -> None:
+        if isinstance(variable_files, str):
+            variable_files = [variable_files]
+        if len(variable_files) != self.num_sessions:
+            raise Exception("Provided {} files for restoring {} sessions.".format(
+                len(variable_files), self.num_sessions))
+        arena = runtime.arena()
+        for path in variable_files:
+            log("Loading variables from {}".format(path))
+            ckpt = torch.load(path, map_location="cpu")
+            arena.load_dict(ckpt["variables"])
+            if ckpt.get("order") == list(arena.order):
+                arena.adam_m.copy_(ckpt["adam_m"])
+                arena.adam_v.copy_(ckpt["adam_v"])
+
+    def restore_best_vars(self) -> None:
+        self.restore(self.variables_files[self.best_score_index])
+
+    def initialize_sessions(self) -> None:
+        """Variables were initialised when the arena was finalised; nothing to run."""
+
+    def initialize_model_parts(self, runners, save: bool = False) -> None:
+        """Per-ModelPart `load_checkpoint` / `save_checkpoint` files (tf_manager.py:279-289)."""
+        parameterizeds = set.union(*[rnr.parameterizeds for rnr in runners]) if runners else set()
+        for coder in parameterizeds:
+            path = getattr(coder, "_load_checkpoint", None)
+            if path:
+                log("Loading {} from {}".format(coder.name, path))
+                ckpt = torch.load(path, map_location="cpu")
+                prefix = coder.scope_name + "/"
+                runtime.arena().load_dict({k: v for k, v in ckpt["variables"].items()
+                                           if k.startswith(prefix)})
+
+
+def get_default_tf_manager() -> TensorFlowManager:
+    return TensorFlowManager(num_sessions=1, num_threads=4)

@@ -109,7 +109,7 @@ class GenericTrainer(GraphExecutor, Feedable):
             warn("LazyAdamOptimizer: using dense Adam updates (rows without gradient also decay)")
         self.global_step += 1
         t = self.global_step
-        lr = opt.lr_at(t)
+        lr = opt.lr_at(t - 1)  # schedules read the global step before its increment
         lr_t = lr * math.sqrt(1.0 - opt.beta2 ** t) / (1.0 - opt.beta1 ** t)
         if not hasattr(self, "_l1l2_buf"):
             self._l1l2_buf = torch.zeros(2, device=arena.params.device, dtype=torch.float32)
