@@ -251,6 +251,22 @@ __device__ __forceinline__ void epilogue_chunk(const TcEpilogue& e, float (&x)[3
   }
 }
 
+// split-K partial tile: C += x (+ bias once, from split 0); no activation.
+__device__ __forceinline__ void epilogue_chunk_atomic(const TcEpilogue& e, const float (&x)[32],
+                                                      int64_t row, int col0, int64_t M, int N,
+                                                      bool add_bias) {
+  if (row >= M || col0 >= N) return;
+  const int ncols = min(32, N - col0);
+  float* c = e.C + row * e.ldc + col0;
+#pragma unroll
+  for (int j = 0; j < 32; ++j)
+    if (j < ncols) {
+      float v = x[j];
+      if (add_bias && e.bias) v += __ldg(e.bias + col0 + j);
+      atomicAdd(c + j, v);
+    }
+}
+
 // ---------------------------------------------------------------------------
 // the kernel
 // ---------------------------------------------------------------------------
@@ -263,7 +279,7 @@ struct MnDesc {
 template <int BN, bool A_MN, bool B_MN, int MODE>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
-               int64_t M, int64_t N, int64_t K, TcEpilogue epi, MnDesc mn) {
+               int64_t M, int64_t N, int64_t K, TcEpilogue epi, MnDesc mn, int splits, int kb_per_split) {
   using Cfg = TcCfg<BN>;
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
@@ -279,8 +295,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t tiles_m = (M + TC_BM - 1) / TC_BM;
   const int64_t tiles_n = (N + BN - 1) / BN;
-  const int64_t num_tiles = tiles_m * tiles_n;
-  const int num_kb = (int)((K + TC_BK - 1) / TC_BK);
+  // split-K: the reduction is cut into `splits` slices, each an independent work item whose
+  // epilogue adds its partial tile into C with red.global.add (weight-gradient products
+  // have tiny outputs and very long K: without this only a handful of SMs would work)
+  const int64_t num_tiles = tiles_m * tiles_n * splits;
+  const int num_kb_total = (int)((K + TC_BK - 1) / TC_BK);  // host guarantees no empty split
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) {
@@ -313,8 +332,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       uint32_t phase = 0;
       for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int32_t m0 = (int32_t)((tile % tiles_m) * TC_BM);
-        const int32_t n0 = (int32_t)((tile / tiles_m) * BN);
-        for (int kb = 0; kb < num_kb; ++kb) {
+        const int32_t n0 = (int32_t)(((tile / tiles_m) % tiles_n) * BN);
+        const int kb_begin = (int)(tile / (tiles_m * tiles_n)) * kb_per_split;
+        const int kb_end = min(num_kb_total, kb_begin + kb_per_split);
+        for (int kb = kb_begin; kb < kb_end; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1u);
           const uint32_t a_dst = smem_base + stage * Cfg::STAGE_BYTES;
           const uint32_t b_dst = a_dst + TC_A_BYTES;
@@ -355,6 +376,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
         tcgen05_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+        const int kb_begin = (int)(tile / (tiles_m * tiles_n)) * kb_per_split;
+        const int num_kb = min(num_kb_total, kb_begin + kb_per_split) - kb_begin;
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(full_bar(stage), phase);
           tcgen05_fence_after();
@@ -394,7 +417,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       const int acc = (int)(it & 1);
       const uint32_t acc_phase = (uint32_t)((it >> 1) & 1);
-      const int64_t tm = tile % tiles_m, tn = tile / tiles_m;
+      const int64_t tm = tile % tiles_m, tn = (tile / tiles_m) % tiles_n;
+      const int split = (int)(tile / (tiles_m * tiles_n));
       const int64_t row = tm * TC_BM + quad * 32 + lane;
       mbar_wait(tfull_bar(acc), acc_phase);
       tcgen05_fence_after();
@@ -413,8 +437,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       for (int c = half; c < BN / 32; c += 2) {
         float v[32];
         tmem_ld32(t_row + (uint32_t)(c * 32), v);
-        epilogue_chunk<MODE>(epi, v, row, (int)(tn * BN) + c * 32, M, n32, st, target, row_lse2,
-                             row_w, vec_ok);
+        if (MODE == TC_EPI_DENSE && splits > 1)
+          epilogue_chunk_atomic(epi, v, row, (int)(tn * BN) + c * 32, M, n32, split == 0);
+        else
+          epilogue_chunk<MODE>(epi, v, row, (int)(tn * BN) + c * 32, M, n32, st, target, row_lse2,
+                               row_w, vec_ok);
       }
       if (MODE == TC_EPI_XENT_FWD && row < M)
         epi.part[(row * tiles_n + tn) * 2 + half] =
@@ -514,7 +541,7 @@ bool tc_gemm_supported(int transA, int transB, int64_t M, int64_t N, int64_t K, 
 
 template <int BN, bool A_MN, bool B_MN, int MODE>
 static int launch_cfg(const CUtensorMap& ma, const CUtensorMap& mb, int64_t M, int64_t N, int64_t K,
-                      const TcEpilogue& epi, cudaStream_t s) {
+                      const TcEpilogue& epi, cudaStream_t s, int splits = 1, int kb_per_split = 0) {
   using Cfg = TcCfg<BN>;
   auto kern = tc_gemm_kernel<BN, A_MN, B_MN, MODE>;
   static bool attr_done = false;
@@ -522,9 +549,11 @@ static int launch_cfg(const CUtensorMap& ma, const CUtensorMap& mb, int64_t M, i
     NM_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     attr_done = true;
   }
-  const int64_t tiles = ceil_div(M, TC_BM) * ceil_div(N, BN);
+  const int64_t tiles = ceil_div(M, TC_BM) * ceil_div(N, BN) * splits;
   const int64_t grid = tiles < sm_count() ? tiles : sm_count();
-  kern<<<(unsigned)grid, TC_THREADS, Cfg::SMEM_BYTES, s>>>(ma, mb, M, N, K, epi, mn_desc_config());
+  if (kb_per_split <= 0) kb_per_split = (int)ceil_div(K, TC_BK);
+  kern<<<(unsigned)grid, TC_THREADS, Cfg::SMEM_BYTES, s>>>(ma, mb, M, N, K, epi, mn_desc_config(),
+                                                           splits, kb_per_split);
   NM_LAUNCH_CHECK("tc_gemm_kernel");
   return NM_OK;
 }
@@ -555,12 +584,12 @@ int tc_gemm_launch(int transA, int transB, int64_t M, int64_t N, int64_t K, cons
   if (!b_mn) rc = make_map(&mb, B, N, K, ldb, TC_BK, (uint32_t)bn, false);
   else       rc = make_map(&mb, B, K, N, ldb, 32, TC_BK, true);
   if (rc) return rc;
-#define NM_TC_DISPATCH(BN_, MODE_)                                                             \
-  do {                                                                                         \
-    if (!a_mn && !b_mn) return launch_cfg<BN_, false, false, MODE_>(ma, mb, M, N, K, epi, s);  \
-    if (!a_mn && b_mn) return launch_cfg<BN_, false, true, MODE_>(ma, mb, M, N, K, epi, s);    \
-    if (a_mn && !b_mn) return launch_cfg<BN_, true, false, MODE_>(ma, mb, M, N, K, epi, s);    \
-    return launch_cfg<BN_, true, true, MODE_>(ma, mb, M, N, K, epi, s);                        \
+#define NM_TC_DISPATCH(BN_, MODE_)                                                                     \
+  do {                                                                                                 \
+    if (!a_mn && !b_mn) return launch_cfg<BN_, false, false, MODE_>(ma, mb, M, N, K, epi, s, splits, kb_per);  \
+    if (!a_mn && b_mn) return launch_cfg<BN_, false, true, MODE_>(ma, mb, M, N, K, epi, s, splits, kb_per);    \
+    if (a_mn && !b_mn) return launch_cfg<BN_, true, false, MODE_>(ma, mb, M, N, K, epi, s, splits, kb_per);    \
+    return launch_cfg<BN_, true, true, MODE_>(ma, mb, M, N, K, epi, s, splits, kb_per);                        \
   } while (0)
   if (epi.mode == TC_EPI_XENT_FWD) {  // A is always K-major for the vocabulary projection
     if (b_mn) return launch_cfg<256, false, true, TC_EPI_XENT_FWD>(ma, mb, M, N, K, epi, s);
@@ -569,6 +598,23 @@ int tc_gemm_launch(int transA, int transB, int64_t M, int64_t N, int64_t K, cons
   if (epi.mode == TC_EPI_XENT_BWD) {
     if (b_mn) return launch_cfg<256, false, true, TC_EPI_XENT_BWD>(ma, mb, M, N, K, epi, s);
     return launch_cfg<256, false, false, TC_EPI_XENT_BWD>(ma, mb, M, N, K, epi, s);
+  }
+  // split-K when the output alone cannot occupy the chip (and nothing forbids partial sums)
+  int splits = 1;
+  int kb_per = (int)ceil_div(K, TC_BK);
+  {
+    const int64_t tiles = ceil_div(M, TC_BM) * ceil_div(N, bn);
+    const int64_t num_kb = ceil_div(K, TC_BK);
+    if (epi.act == NM_ACT_NONE && tiles * 2 <= sm_count() && num_kb >= 16) {
+      int64_t want = ceil_div(sm_count(), tiles);
+      if (want > num_kb / 8) want = num_kb / 8;
+      if (want > 1) {
+        kb_per = (int)ceil_div(num_kb, want);
+        splits = (int)ceil_div(num_kb, kb_per);  // every split owns >= 1 k-block
+      }
+    }
+    if (splits > 1 && epi.beta == 0.f)  // partial sums are added: start from zero
+      NM_CUDA_TRY(cudaMemset2DAsync(epi.C, sizeof(float) * epi.ldc, 0, sizeof(float) * N, M, s));
   }
   if (bn == 64) NM_TC_DISPATCH(64, TC_EPI_DENSE);
   if (bn == 128) NM_TC_DISPATCH(128, TC_EPI_DENSE);

@@ -131,7 +131,11 @@ def call(name: str, *args) -> None:
         ev0.record()
         rc = getattr(lib, name)(*args)
         ev1.record()
-        _profile.setdefault(name, []).append((ev0, ev1))
+        key = name
+        if name == "nm_gemm":  # split the projection calls by shape in the breakdown
+            key = "nm_gemm[{}{} {}x{}x{}]".format("T" if args[0] else "N", "T" if args[1] else "N",
+                                                 args[2], args[3], args[4])
+        _profile.setdefault(key, []).append((ev0, ev1))
     else:
         rc = getattr(lib, name)(*args)
     if rc != 0:

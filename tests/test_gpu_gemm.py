@@ -106,3 +106,17 @@ def test_tc_rounding_mode_report(capsys):
         print("\n[tf32 path] mean signed relative error = {:.3e} (|.| << 2.4e-4 means rounding)"
               .format(signed))
     assert abs(signed) < 1e-3
+
+
+@pytest.mark.parametrize("beta", [0.0, 1.0])
+def test_tc_gemm_split_k_weight_gradient_shape(beta):
+    """Tiny output, long reduction: the kernel splits K over the SMs and adds partial tiles."""
+    from neuralmonkey_b200 import lib, ops
+    m, n, k = 300, 600, 12800
+    a, b = _operands(m, n, k, True, False, seed=5)
+    bias = torch.randn(n)
+    c0 = torch.randn(m, n)
+    out = c0.clone().cuda()
+    ops.gemm(a.cuda(), b.cuda(), out, trans_a=True, bias=bias.cuda(), beta=beta, backend=lib.GEMM_TC)
+    ref = a.double().t() @ b.double() + bias.double() + beta * c0.double()
+    assert rel_err(out, ref) < TC_REL
