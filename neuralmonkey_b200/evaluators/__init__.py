@@ -1,0 +1,50 @@
+"""Evaluators referenced by the target configs (reference: neuralmonkey/evaluators/).
+BLEU is implemented natively; SacreBLEU (the `sacrebleu` package is not installed here) is
+served by the same corpus-BLEU on the already tokenised series; ROUGE-L is the LCS F-score."""
+from typing import List
+
+from neuralmonkey_b200.evaluators.bleu import BLEU, BLEU1, BLEU2, BLEU4, BLEUEvaluator
+
+
+class AccuracyEvaluator:
+    def __init__(self, name: str = "Accuracy") -> None:
+        self.name = name
+
+    def __call__(self, decoded: List, references: List) -> float:
+        pairs = list(zip(decoded, references))
+        return sum(1.0 for h, r in pairs if h == r) / len(pairs) if pairs else 0.0
+
+
+class RougeLEvaluator:
+    """Sentence-level ROUGE-L F-score averaged over the corpus (evaluators/rouge.py)."""
+
+    def __init__(self, name: str = "ROUGE-L", beta: float = 1.2) -> None:
+        self.name = name
+        self.beta = beta
+
+    @staticmethod
+    def _lcs(a: List[str], b: List[str]) -> int:
+        prev = [0] * (len(b) + 1)
+        for x in a:
+            cur = [0]
+            for j, y in enumerate(b):
+                cur.append(prev[j] + 1 if x == y else max(prev[j + 1], cur[j]))
+            prev = cur
+        return prev[-1]
+
+    def __call__(self, decoded: List[List[str]], references: List[List[str]]) -> float:
+        scores = []
+        for hyp, ref in zip(decoded, references):
+            lcs = self._lcs(list(hyp), list(ref))
+            if lcs == 0 or not hyp or not ref:
+                scores.append(0.0)
+                continue
+            p, r = lcs / len(hyp), lcs / len(ref)
+            scores.append((1 + self.beta ** 2) * p * r / (r + self.beta ** 2 * p))
+        return sum(scores) / len(scores) if scores else 0.0
+
+
+# pylint: disable=invalid-name
+Accuracy = AccuracyEvaluator()
+ROUGE_L = RougeLEvaluator()
+SacreBLEU = BLEUEvaluator(n=4, name="SacreBLEU")

@@ -126,6 +126,8 @@ class ParameterArena:
         self.seg_reg = None  # type: Optional[torch.Tensor]
         self.seg_norms = None  # type: Optional[torch.Tensor]
         self.size = 0
+        self.train_names = []  # type: List[str]
+        self.trainable_size = 0
 
     def declare(self, name: str, shape: Sequence[int], initializer: Initializer,
                 trainable: bool = True) -> None:

@@ -93,7 +93,13 @@ class TensorFlowManager:
             feedable.feed_dict(batch, train)
         executables = [runner.get_executable(compute_losses=compute_losses, summaries=summaries,
                                              num_sessions=self.num_sessions) for runner in runners]
-        for executable in executables:
+        for i, executable in enumerate(executables):
+            if train and i > 0:
+                # several trainers on one batch (tests/bahdanau.ini:12): the reference runs their
+                # train ops in one sess.run; here each trainer gets a fresh forward pass (its
+                # backward consumed the previous graph), i.e. the updates are applied in order
+                for feedable in feedables:
+                    feedable.feed_dict(batch, train)
             executable.execute()
         return [executable.result for executable in executables]
 

@@ -51,7 +51,7 @@ class GenericTrainer(GraphExecutor, Feedable):
 
     @property
     def var_list(self) -> List[str]:
-        return list(runtime.arena().train_names)
+        return list(getattr(runtime.arena(), "train_names", []))
 
     # -- one optimisation step ---------------------------------------------------------------
     def _backward(self) -> Dict[str, torch.Tensor]:

@@ -33,9 +33,21 @@ def AutoWriter(path: str, data: Any) -> None:  # pylint: disable=invalid-name
         text_writer()(path, data)
         return
     if all(isinstance(item, dict) for item in data):
-        np.savez(path, **{k: np.array([d[k] for d in data]) for k in data[0]}) if data else np.savez(path)
+        np.savez(path, **{k: _stack([d[k] for d in data]) for k in data[0]}) if data else np.savez(path)
         return
-    np.save(path, np.array(data))
+    np.save(path, _stack(data))
+
+
+def _stack(items: List[Any]) -> np.ndarray:
+    """Regular array when the examples agree in shape, object array otherwise (bucketed
+    batches give per-example tensors different time dimensions)."""
+    try:
+        return np.array(items)
+    except ValueError:
+        out = np.empty(len(items), dtype=object)
+        for i, item in enumerate(items):
+            out[i] = item
+        return out
 
 
 UtfPlainTextWriter = text_writer()
