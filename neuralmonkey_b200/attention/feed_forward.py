@@ -77,9 +77,30 @@ class Attention(BaseAttention):
         (contexts [batch, NQ, ctx], weights [batch, NQ, time])."""
         y = ops.linear(queries, self.var("Attention/attn_query_projection"),
                        self.var("attn_projection_bias"))
-        return ops.bahdanau_attention(self.hidden_features, self.attention_states,
-                                      self.attention_mask, y, self.var("attn_similarity_v"),
+        keys, values, mask = self.hidden_features, self.attention_states, self.attention_mask
+        if queries.shape[0] != keys.shape[0]:
+            keys, values, mask = self._beam_tiled(queries.shape[0])
+        return ops.bahdanau_attention(keys, values, mask, y, self.var("attn_similarity_v"),
                                       self.var("attn_bias"))
+
+    def _beam_tiled(self, rows: int):
+        """Keys / values / mask repeated beam-minor for a BeamSearchDecoder parent.  The
+        reference relies on broadcasting, which only works for batch size 1
+        (beam_search_decoder.py docstring); tiling gives the same numbers there and extends
+        to any batch."""
+        cache = self.__dict__.setdefault("_batch_cache", {})
+        key = ("beam_tiled", rows)
+        if key not in cache:
+            bsz = self.hidden_features.shape[0]
+            if rows % bsz != 0:
+                raise ValueError("Attention '{}': {} query rows over a batch of {}".format(
+                    self.name, rows, bsz))
+            rep = rows // bsz
+            mask = self.attention_mask
+            cache[key] = (self.hidden_features.repeat_interleave(rep, 0),
+                          self.attention_states.repeat_interleave(rep, 0),
+                          mask.repeat_interleave(rep, 0) if mask is not None else None)
+        return cache[key]
 
     def attention(self, query: torch.Tensor, decoder_prev_state: torch.Tensor,
                   decoder_input: torch.Tensor,

@@ -556,3 +556,24 @@ def beam_gather(x: torch.Tensor, beam_ids: torch.Tensor, bsz: int, k: int) -> to
     call("nm_beam_gather", ptr(x), ptr(beam_ids.contiguous()), ptr(out), bsz, k, row_bytes,
          lib.stream())
     return out
+
+
+# ---------------------------------------------------------------------------
+# K12 frozen VGG stack primitives (forward only)
+# ---------------------------------------------------------------------------
+def conv3x3_bias_relu(x: torch.Tensor, w: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+    """NHWC 3x3 SAME conv + bias + ReLU; w is HWIO (slim vgg_arg_scope)."""
+    n, h, wd, cin = x.shape
+    cout = w.shape[-1]
+    x, w, b = _f32(x.detach()).contiguous(), _f32(w.detach()).contiguous(), _f32(b.detach())
+    y = torch.empty(n, h, wd, cout, device=x.device, dtype=torch.float32)
+    call("nm_conv3x3_bias_relu_fwd", ptr(x), ptr(w), ptr(b), ptr(y), n, h, wd, cin, cout, lib.stream())
+    return y
+
+
+def maxpool2x2(x: torch.Tensor) -> torch.Tensor:
+    n, h, wd, c = x.shape
+    x = _f32(x.detach()).contiguous()
+    y = torch.empty(n, h // 2, wd // 2, c, device=x.device, dtype=torch.float32)
+    call("nm_maxpool2x2_fwd", ptr(x), ptr(y), n, h, wd, c, lib.stream())
+    return y

@@ -282,6 +282,210 @@ def decoder_greedy(p: Params, spec: RNNDecoderSpec, enc: Dict[str, torch.Tensor]
 
 
 # ---------------------------------------------------------------------------
+# Transformer (encoders/transformer.py, decoders/transformer.py,
+# attention/scaled_dot_product.py, attention/transformer_cross_layer.py)
+# ---------------------------------------------------------------------------
+def position_signal(dimension: int, length: int, dtype=torch.float32) -> torch.Tensor:
+    """encoders/transformer.py:23-45 - [1, length, dimension]; sin half then cos half."""
+    positions = torch.arange(length, dtype=torch.float32)
+    num_timescales = dimension // 2
+    log_timescale_increment = math.log(1.0e4) / (num_timescales - 1)
+    inv_timescales = torch.exp(torch.arange(num_timescales, dtype=torch.float32)
+                               * -log_timescale_increment)
+    scaled_time = positions.unsqueeze(1) * inv_timescales.unsqueeze(0)
+    signal = torch.cat([torch.sin(scaled_time), torch.cos(scaled_time)], dim=1)
+    if dimension % 2:
+        signal = torch.nn.functional.pad(signal, (0, 1))
+    return signal.reshape(1, length, dimension).to(dtype)
+
+
+def _split_for_heads(x: torch.Tensor, heads: int, head_dim: int) -> torch.Tensor:
+    """scaled_dot_product.py:24-41: [B,T,D] -> [B,heads,T,head_dim]."""
+    return x.reshape(x.shape[0], x.shape[1], heads, head_dim).permute(0, 2, 1, 3)
+
+
+def multihead_attention(p: Params, scope: str, queries, keys, values, keys_mask, heads: int,
+                        masked: bool = False, use_bias: bool = False):
+    """attention() (scaled_dot_product.py:98-226); dropout callback = identity."""
+    dim = queries.shape[-1]
+    head_dim = dim // heads
+
+    def dense(x, name):
+        y = x @ p["{}/{}/kernel".format(scope, name)]
+        return y + p["{}/{}/bias".format(scope, name)] if use_bias else y
+
+    if heads > 1:
+        queries, keys, values = dense(queries, "query_proj"), dense(keys, "keys_proj"), dense(values, "vals_proj")
+    q = _split_for_heads(queries / math.sqrt(head_dim), heads, head_dim)
+    k = _split_for_heads(keys, heads, head_dim)
+    v = _split_for_heads(values, heads, head_dim)
+    energies = q @ k.transpose(-1, -2)
+    if masked:  # mask_future (:44-66): lower triangle kept, the rest REPLACED by -1e9
+        tq, tk = energies.shape[-2:]
+        keep = torch.tril(torch.ones(tq, tk, dtype=torch.bool))
+        energies = torch.where(keep, energies, torch.full_like(energies, -INF))
+    if keys_mask is not None:  # mask_energies (:69-83): e * m + (1 - m) * -1e9
+        m = keys_mask.to(energies.dtype).unsqueeze(1).unsqueeze(1)
+        energies = energies * m + (1.0 - m) * -INF
+    weights = torch.softmax(energies, dim=-1)
+    context = (weights @ v).permute(0, 2, 1, 3).reshape(queries.shape[0], queries.shape[1], dim)
+    if heads > 1:
+        context = dense(context, "output_proj")
+    return context, weights
+
+
+def _scoped_ln(p: Params, scope: str, x):
+    prefix = scope + "/LayerNorm/" if scope else "LayerNorm/"
+    return layer_norm(x, p[prefix + "gamma"], p[prefix + "beta"])
+
+
+def transformer_feedforward(p: Params, scope: str, x):
+    """feedforward_sublayer (encoders/transformer.py:266-288)."""
+    normalized = _scoped_ln(p, scope, x)
+    hidden = torch.relu(normalized @ p[scope + "/hidden_state/kernel"] + p[scope + "/hidden_state/bias"])
+    return hidden @ p[scope + "/output/kernel"] + p[scope + "/output/bias"] + x
+
+
+def transformer_encoder(p: Params, prefix: str, inputs: torch.Tensor, mask: torch.Tensor, depth: int,
+                        heads: int, use_positional_encoding: bool = True) -> Dict[str, torch.Tensor]:
+    """TransformerEncoder.temporal_states / output (encoders/transformer.py:174-330), no dropout.
+    `inputs` [B,T,D]: the embedded input sequence; `mask` [B,T]."""
+    x = inputs
+    if use_positional_encoding:
+        x = x + position_signal(x.shape[-1], x.shape[1], x.dtype)
+    for i in range(depth):
+        scope = "{}/layer_{}".format(prefix, i)
+        normalized = _scoped_ln(p, scope + "/self_attention", x)
+        ctx, _ = multihead_attention(p, scope + "/self_attention", normalized, normalized, normalized,
+                                     mask, heads)
+        x = ctx + x
+        x = transformer_feedforward(p, scope + "/feedforward", x)
+    states = _scoped_ln(p, prefix, x)
+    return {"states": states, "mask": mask, "output": states.sum(dim=1)}
+
+
+class TransformerDecoderSpec:
+    def __init__(self, prefix: str, depth: int, heads_self: int, heads_enc: int, max_len: int,
+                 tie_embeddings: bool = True, supress_unk: bool = False) -> None:
+        self.prefix, self.depth, self.heads_self, self.heads_enc = prefix, depth, heads_self, heads_enc
+        self.max_len, self.tie_embeddings, self.supress_unk = max_len, tie_embeddings, supress_unk
+
+
+def transformer_decoder_stack(p: Params, spec: TransformerDecoderSpec, inputs, mask, enc_states, enc_mask):
+    """TransformerDecoder.layer (decoders/transformer.py:270-387), serial strategy, one encoder."""
+    x = inputs
+    for i in range(spec.depth):
+        scope = "{}/layer_{}".format(spec.prefix, i)
+        normalized = _scoped_ln(p, scope + "/self_attention", x)
+        ctx, _ = multihead_attention(p, scope + "/self_attention", normalized, normalized, normalized,
+                                     mask, spec.heads_self, masked=True)
+        x = ctx + x
+        cross = scope + "/encdec_attention/enc_0"
+        normalized = _scoped_ln(p, cross, x)
+        ctx, _ = multihead_attention(p, cross, normalized, enc_states, enc_states, enc_mask, spec.heads_enc)
+        x = ctx + x
+        x = transformer_feedforward(p, scope + "/feedforward", x)
+    return _scoped_ln(p, spec.prefix, x)
+
+
+def transformer_logits(p: Params, spec: TransformerDecoderSpec, states: torch.Tensor) -> torch.Tensor:
+    """decoding_w / decoding_b (autoregressive.py:228-243) + supress_unk (:450-459)."""
+    if spec.tie_embeddings:
+        logits = states @ p[spec.prefix + "/word_embeddings"].t()
+    else:
+        logits = states @ p[spec.prefix + "/state_to_word_W"] + p[spec.prefix + "/state_to_word_b"]
+    if spec.supress_unk:
+        pen = torch.zeros(logits.shape[-1], dtype=logits.dtype)
+        pen[UNK] = -INF
+        logits = logits + pen
+    return logits
+
+
+def transformer_decoder_train(p: Params, spec: TransformerDecoderSpec, enc: Dict[str, torch.Tensor],
+                              tgt_ids: torch.Tensor) -> Dict[str, torch.Tensor]:
+    """train_loop_result (decoders/transformer.py:389-447) + train_xents / train_loss
+    (autoregressive.py:292-316).  tgt_ids [B,T] incl. </s>.  Inputs are embedded WITHOUT a
+    position signal: the base-class `embed_input_symbols` is what the reference calls."""
+    bsz, steps = tgt_ids.shape
+    emb = p[spec.prefix + "/word_embeddings"]
+    go = torch.full((bsz, 1), START, dtype=torch.int64)
+    inputs = emb[torch.cat([go, tgt_ids[:, :-1]], dim=1)]
+    mask = (tgt_ids != PAD).to(emb.dtype)
+    states = transformer_decoder_stack(p, spec, inputs, mask, enc["states"], enc["mask"])
+    logits = transformer_logits(p, spec, states)
+    logprobs = torch.log_softmax(logits, dim=-1)
+    xent = -logprobs.gather(2, tgt_ids.unsqueeze(2)).squeeze(2) * mask
+    return {"states": states, "logits": logits, "xents": xent, "loss": xent.sum() / mask.sum(),
+            "loss_sum": xent.sum(), "count": mask.sum()}
+
+
+def transformer_decoder_greedy(p: Params, spec: TransformerDecoderSpec, enc: Dict[str, torch.Tensor]):
+    """decoding_loop(train_mode=False) with TransformerDecoder.next_state (:485-518): the whole
+    prefix is re-run every step; the mask column appended at a step is `not finished`."""
+    bsz = enc["states"].shape[0]
+    emb = p[spec.prefix + "/word_embeddings"]
+    dim = emb.shape[1]
+    seq = torch.zeros(bsz, 0, dim, dtype=emb.dtype)
+    mask = torch.zeros(bsz, 0, dtype=emb.dtype)
+    finished = torch.zeros(bsz, dtype=torch.bool)
+    embedded = emb[torch.full((bsz,), START, dtype=torch.int64)]
+    symbols, logits_hist, masks = [], [], []
+    step = 0
+    while step < spec.max_len and not bool(finished.all()):
+        seq = torch.cat([seq, embedded.unsqueeze(1)], 1)
+        mask = torch.cat([mask, (~finished).to(emb.dtype).unsqueeze(1)], 1)
+        states = transformer_decoder_stack(p, spec, seq, mask, enc["states"], enc["mask"])
+        logits = transformer_logits(p, spec, states[:, -1])
+        nxt = torch.argmax(logits, dim=-1) * (~finished).to(torch.int64)
+        finished = finished | (nxt == END)
+        embedded = emb[nxt]
+        symbols.append(nxt)
+        logits_hist.append(logits)
+        masks.append(~finished)
+        step += 1
+    return {"symbols": torch.stack(symbols), "logits": torch.stack(logits_hist),
+            "mask": torch.stack(masks)}
+
+
+# ---------------------------------------------------------------------------
+# ImageNet encoder (encoders/imagenet_encoder.py:131-240) over the slim VGG stack
+# ---------------------------------------------------------------------------
+VGG_BLOCKS = {"vgg_16": (2, 2, 3, 3, 3), "vgg_19": (2, 2, 4, 4, 4)}
+VGG_CHANNELS = (64, 128, 256, 512, 512)
+
+
+def vgg_features(p: Params, network_type: str, images: torch.Tensor,
+                 spatial_layer: str) -> Dict[str, torch.Tensor]:
+    """tensorflow/models research/slim nets/vgg.py (third-party, not vendored by the reference;
+    restated from the published definition): repeat(conv 3x3 SAME + bias + relu), max_pool 2x2.
+    images [B,H,W,3]; weights HWIO.  Returns the ImageNet part's tensors with
+    `temporal_*` aliases so the RNN decoder oracle can attend over the flattened map
+    (attention/base_attention.py:79-118)."""
+    x = images.permute(0, 3, 1, 2)
+    found = None
+    for block, convs in enumerate(VGG_BLOCKS[network_type], 1):
+        for i in range(1, convs + 1):
+            name = "{}/conv{}/conv{}_{}".format(network_type, block, block, i)
+            w = p[name + "/weights"].permute(3, 2, 0, 1)
+            x = torch.relu(torch.nn.functional.conv2d(x, w, p[name + "/biases"], padding=1))
+            if name == spatial_layer:
+                found = x
+                break
+        if found is not None:
+            break
+        x = torch.nn.functional.max_pool2d(x, 2, 2)
+        if "{}/pool{}".format(network_type, block) == spatial_layer:
+            found = x
+            break
+    states = found.permute(0, 2, 3, 1).contiguous()
+    bsz, h, w, c = states.shape
+    return {"spatial_states": states, "spatial_mask": torch.ones(bsz, h, w, dtype=states.dtype),
+            "output": states.mean(dim=(1, 2)),
+            "temporal_states": states.reshape(bsz, h * w, c),
+            "temporal_mask": torch.ones(bsz, h * w, dtype=states.dtype)}
+
+
+# ---------------------------------------------------------------------------
 # Beam search (decoders/beam_search_decoder.py:218-596)
 # ---------------------------------------------------------------------------
 def length_penalty(lengths: torch.Tensor, alpha: float) -> torch.Tensor:
