@@ -137,6 +137,10 @@ int nm_gru_seq_fwd(const float* xproj, const float* Wgh, const float* Wch,
 /* Number of 8-CTA clusters of the persistent GRU kernel that are co-resident on the
  * current device (forward: backward=0).  Diagnostic. */
 int nm_gru_resident_clusters(int backward);
+/* Recurrence engine of nm_gru_seq_fwd/bwd: 0 (default) = tcgen05 tensor cores, recurrent
+ * weights resident in tensor memory, TF32 operands with fp32 accumulation; 1 = exact fp32
+ * on the CUDA cores (the engine the fp32 parity tests pin against the oracle). */
+int nm_gru_set_mode(int mode);
 /* Diagnostic: 8 int64 device counters receiving the cycles CTA 0 of the forward cluster
  * kernel spends per section (phase 1: load, dot, gates, barrier; phase 2: same). NULL = off. */
 int nm_gru_debug_profile(void* counters);

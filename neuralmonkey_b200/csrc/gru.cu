@@ -14,6 +14,7 @@
 
 #include "gemm_simt.cuh"
 #include "gru_cluster.cuh"
+#include "gru_tc.cuh"
 
 namespace nm {
 
@@ -142,6 +143,20 @@ bool cluster_path_ok(int64_t H) {
   return forced == 0 && H >= 8 && H <= 320;
 }
 
+// Recurrence engine: 0 = tensor cores (TF32 operands, fp32 accumulate; gru_tc.cuh),
+// 1 = exact fp32 on the CUDA cores (gru_cluster.cuh).  NMB200_GRU=cluster|tc overrides.
+int g_gru_mode = 0;
+bool tc_path_ok(int64_t H) {
+  static int forced = -1;
+  if (forced < 0) {
+    const char* e = getenv("NMB200_GRU");
+    forced = !e ? 0 : (strcmp(e, "tc") == 0 ? 1 : (strcmp(e, "cluster") == 0 || strcmp(e, "steps") == 0 ? 2 : 0));
+  }
+  if (forced == 2) return false;
+  if (forced == 0 && g_gru_mode != 0) return false;
+  return H >= 1 && H <= GT_MAX_UPC * GT_CLUSTER;
+}
+
 struct ClusterPlan {
   int Bc, nclusters, ch;
   size_t smem;
@@ -221,6 +236,71 @@ int launch_cluster(Kern kern, const Args& args, const ClusterPlan& p, cudaStream
   return NM_OK;
 }
 
+struct TcPlan {
+  int Bc, nclusters;
+  size_t smem;
+};
+
+template <class Kern>
+int tc_resident_clusters(Kern kern, size_t smem) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(GT_CLUSTER * 64);
+  cfg.blockDim = dim3(GT_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = GT_CLUSTER;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  int n = 0;
+  if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess ||
+      cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess || n < 1) {
+    cudaGetLastError();
+    n = sm_count() / GT_CLUSTER / 2;
+  }
+  return n;
+}
+
+template <int ESZ, class Kern>
+TcPlan plan_tc(Kern kern, int64_t B, int64_t H, int sm_budget, int ntiles, int* cache) {
+  const GtGeom<ESZ> geo((int)H);
+  const GtSmem lay(geo.tile_bytes, ntiles);
+  TcPlan p;
+  p.smem = (size_t)lay.total;
+  if (*cache == 0)
+    *cache = tc_resident_clusters(kern, (size_t)GtSmem(GtGeom<ESZ>(GT_MAX_UPC * GT_CLUSTER).tile_bytes, ntiles).total);
+  int max_clusters = *cache;
+  if (sm_budget > 0 && sm_budget / GT_CLUSTER < max_clusters) max_clusters = sm_budget / GT_CLUSTER;
+  if (max_clusters < 1) max_clusters = 1;
+  int Bc = (int)((B + max_clusters - 1) / max_clusters);
+  if (Bc > GT_NB) Bc = GT_NB;  // more sentences than one wave holds: clusters queue up
+  p.Bc = Bc;
+  p.nclusters = (int)((B + Bc - 1) / Bc);
+  return p;
+}
+
+template <class Args, class Kern>
+int launch_tc(Kern kern, const Args& args, const TcPlan& p, cudaStream_t s, const char* name) {
+  NM_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(p.nclusters * GT_CLUSTER));
+  cfg.blockDim = dim3(GT_THREADS);
+  cfg.dynamicSmemBytes = p.smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = GT_CLUSTER;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  NM_CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, args));
+  NM_LAUNCH_CHECK(name);
+  return NM_OK;
+}
+
 #define NM_GC_DISPATCH(KERN, args, plan, s, name)                   \
   switch ((plan).ch) {                                              \
     case 1: return launch_cluster(KERN<1>, args, plan, s, name);    \
@@ -233,6 +313,12 @@ int launch_cluster(Kern kern, const Args& args, const ClusterPlan& p, cudaStream
 extern "C" {
 
 int nm_gru_resident_clusters(int backward) { return resident_clusters(backward != 0); }
+
+int nm_gru_set_mode(int mode) {
+  NM_REQUIRE(mode == 0 || mode == 1, NM_E_INVALID, "nm_gru_set_mode: mode must be 0 (tensor cores) or 1 (exact fp32)");
+  g_gru_mode = mode;
+  return NM_OK;
+}
 
 static long long* g_gru_prof = nullptr;
 /* Diagnostic: device buffer of 8 int64 cycle counters filled by CTA 0 of the next forward
@@ -251,6 +337,14 @@ int nm_gru_seq_fwd(const float* xproj, const float* Wgh, const float* Wch, const
   NM_REQUIRE(B > 0 && T > 0 && H > 0, NM_E_INVALID, "nm_gru_seq_fwd: bad sizes B=%lld T=%lld H=%lld",
              (long long)B, (long long)T, (long long)H);
   cudaStream_t s = (cudaStream_t)stream;
+  if (tc_path_ok(H) && T * H < (1 << 24)) {
+    static int resident = 0;
+    GtFwdArgs a{xproj, Wgh, Wch, h0, lengths, drop_mask, states, raw_states, final_state, gates,
+                hprev, rh, (int)B, (int)T, (int)H, 0, reverse, g_gru_prof};
+    const TcPlan p = plan_tc<2>(gru_seq_fwd_tc_kernel, B, H, sm_budget, 2, &resident);
+    a.Bc = p.Bc;
+    return launch_tc(gru_seq_fwd_tc_kernel, a, p, s, "nm_gru_seq_fwd(tc)");
+  }
   if (cluster_path_ok(H)) {
     GcFwdArgs a{xproj, Wgh, Wch, h0, lengths, drop_mask, states, raw_states, final_state, gates,
                 hprev, rh, (int)B, (int)T, (int)H, 0, reverse, g_gru_prof};
@@ -291,6 +385,14 @@ int nm_gru_seq_bwd(const float* Wgh, const float* Wch, const int32_t* lengths,
              "nm_gru_seq_bwd: null pointer");
   NM_REQUIRE(B > 0 && T > 0 && H > 0, NM_E_INVALID, "nm_gru_seq_bwd: bad sizes");
   cudaStream_t s = (cudaStream_t)stream;
+  if (tc_path_ok(H) && T * H < (1 << 24)) {
+    static int resident = 0;
+    GtBwdArgs a{Wgh, Wch, lengths, drop_mask, gates, hprev, dstates, draw, dfinal, dxproj, dh0,
+                (int)B, (int)T, (int)H, 0, reverse};
+    const TcPlan p = plan_tc<4>(gru_seq_bwd_tc_kernel, B, H, sm_budget, 3, &resident);
+    a.Bc = p.Bc;
+    return launch_tc(gru_seq_bwd_tc_kernel, a, p, s, "nm_gru_seq_bwd(tc)");
+  }
   if (cluster_path_ok(H)) {
     GcBwdArgs a{Wgh, Wch, lengths, drop_mask, gates, hprev, dstates, draw, dfinal, dxproj, dh0,
                 (int)B, (int)T, (int)H, 0, reverse};

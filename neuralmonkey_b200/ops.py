@@ -21,6 +21,8 @@ def set_gemm_backend(name: str) -> None:
     """'auto' (tcgen05 when TMA-addressable), 'simt' (exact fp32) or 'tc'."""
     global _GEMM_BACKEND
     _GEMM_BACKEND = {"auto": lib.GEMM_AUTO, "simt": lib.GEMM_SIMT, "tc": lib.GEMM_TC}[name]
+    # the GRU recurrence follows: exact fp32 engine with 'simt', tensor cores otherwise
+    call("nm_gru_set_mode", 1 if name == "simt" else 0)
 
 
 def gemm_backend() -> int:

@@ -52,15 +52,24 @@ def test_layer_norm_fwd_bwd(dims):
 @pytest.mark.parametrize("use_lengths", [False, True])
 @pytest.mark.parametrize("dims", [(5, 6, 11, 7), (9, 4, 32, 32), (7, 6, 12, 300), (70, 3, 16, 64),
                                   (3, 5, 8, 100)])
-def test_gru_layer_fwd_bwd(reverse, use_lengths, dims):
-    from neuralmonkey_b200 import ops
+@pytest.mark.parametrize("engine", ["exact", "tc"])
+def test_gru_layer_fwd_bwd(reverse, use_lengths, dims, engine):
+    """engine 'exact': fp32 CUDA-core recurrence; 'tc': tcgen05 recurrence (TF32 operands)."""
+    from neuralmonkey_b200 import lib, ops
     ops.set_gemm_backend("simt")
+    tol, gtol = (2e-5, 5e-5) if engine == "exact" else (3e-3, 1e-2)
+    if engine == "tc":
+        lib.call("nm_gru_set_mode", 0)
     try:
         bsz, steps, e, h = dims
         g = torch.Generator().manual_seed(2)
         x = torch.randn(bsz, steps, e, generator=g)
-        wg, bg = torch.randn(e + h, 2 * h, generator=g) * 0.3, torch.randn(2 * h, generator=g) * 0.3
-        wc, bc = torch.randn(e + h, h, generator=g) * 0.3, torch.randn(h, generator=g) * 0.3
+        # the reduced-precision engine is checked in the regime real models live in (recurrent
+        # gain ~1, as with the orthogonal initialiser); randn*0.3 at H=300 has gain ~5, where the
+        # recurrence amplifies ANY rounding difference by orders of magnitude within a few steps
+        ws = 0.3 if engine == "exact" else min(0.3, 1.0 / h ** 0.5)
+        wg, bg = torch.randn(e + h, 2 * h, generator=g) * ws, torch.randn(2 * h, generator=g) * 0.3
+        wc, bc = torch.randn(e + h, h, generator=g) * ws, torch.randn(h, generator=g) * 0.3
         h0 = torch.randn(bsz, h, generator=g) * 0.5
         lengths = torch.randint(1, steps + 1, (bsz,), generator=g) if use_lengths else None
         if lengths is not None:
@@ -77,14 +86,14 @@ def test_gru_layer_fwd_bwd(reverse, use_lengths, dims):
             ref_states = O.reverse_sequence(out_rev, lens)
         else:
             ref_states, fin = O.dynamic_gru(x64, lengths, *l64[1:5], h0=l64[5])
-        assert max_abs(states, ref_states) < 2e-5
-        assert max_abs(final, fin) < 2e-5
+        assert max_abs(states, ref_states) < tol
+        assert max_abs(final, fin) < tol
         ds, df = torch.randn(bsz, steps, h, generator=g), torch.randn(bsz, h, generator=g)
         (states * ds.cuda()).sum().backward(retain_graph=True)
         (final * df.cuda()).sum().backward()
         ((ref_states * ds.double()).sum() + (fin * df.double()).sum()).backward()
         for got, want, name in zip(leaves, l64, ("x", "wg", "bg", "wc", "bc", "h0")):
-            assert rel_err(got.grad, want.grad) < 5e-5, name
+            assert rel_err(got.grad, want.grad) < gtol, name
     finally:
         ops.set_gemm_backend("auto")
 
