@@ -124,8 +124,8 @@ class BeamSearchDecoder(ModelPart):
                 state.finished.to(torch.uint8), self.length_normalization)
             finished = fin.to(torch.bool)
             gathered = map_structure(
-                lambda x: ops.beam_gather(x, beams, bsz, k) if x.dim() >= 1 and x.shape[0] == bsz * k
-                else x, dec_ls.feedables)
+                lambda x: ops.beam_gather(x, beams, bsz, k)
+                if x.dim() >= 1 and x.shape[0] == bsz * k and x.numel() > 0 else x, dec_ls.feedables)
             gathered = gathered._replace(
                 embedded_input=parent.embed_input_symbols(words.view(-1)),
                 finished=finished.view(-1))

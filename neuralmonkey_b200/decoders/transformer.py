@@ -13,7 +13,7 @@ from typing import Any, List, NamedTuple, Tuple, Union
 
 import torch
 
-from neuralmonkey_b200 import runtime
+from neuralmonkey_b200 import ops, runtime
 from neuralmonkey_b200.attention.base_attention import (Attendable, get_attention_mask,
                                                         get_attention_states)
 from neuralmonkey_b200.attention.scaled_dot_product import attention, declare_attention
@@ -34,8 +34,11 @@ from neuralmonkey_b200.vocabulary import START_TOKEN_INDEX, Vocabulary
 
 STRATEGIES = ["serial", "parallel", "flat", "hierarchical"]
 
+# `kv_cache`: per layer the projected self-attention keys and values of the prefix
+# ([batch, time, dim] each).  Being a feedable, it is re-ordered with the beam by
+# BeamSearchDecoder like every other per-hypothesis tensor.
 TransformerFeedables = NamedTuple("TransformerFeedables", [
-    ("input_sequence", torch.Tensor), ("input_mask", torch.Tensor)])
+    ("input_sequence", torch.Tensor), ("input_mask", torch.Tensor), ("kv_cache", Any)])
 
 
 class TransformerDecoder(AutoregressiveDecoder):
@@ -166,20 +169,103 @@ class TransformerDecoder(AutoregressiveDecoder):
         return self._stack(input_sequence, self._train_mask_bm)
 
     # -- runtime --------------------------------------------------------------------------------
+    # The reference re-runs all layers over the whole prefix at every step and keeps the last
+    # position (:485-518).  Position j of a causal stack depends only on positions <= j and on the
+    # key-mask entries appended up to j, none of which change later, so the states of the prefix
+    # computed at earlier steps are exactly what the recomputation would produce: the projected
+    # self-attention keys / values of the prefix are cached per layer and a step runs the stack on
+    # the NEW position only - O(t) instead of O(t^2) work per step.  `use_kv_cache=False` restores
+    # the reference's schedule (used by the parity tests as the cross-check).
+    use_kv_cache = True
+
     def get_initial_feedables(self) -> DecoderFeedables:
         feedables = AutoregressiveDecoder.get_initial_feedables(self)
         dev = runtime.device()
+        cache = None
+        if self.use_kv_cache:
+            cache = [torch.zeros(self.batch_size, 0, self.dimension, device=dev)
+                     for _ in range(2 * self.depth)]
         return feedables._replace(other=TransformerFeedables(
             input_sequence=torch.zeros(self.batch_size, 0, self.dimension, device=dev),
-            input_mask=torch.zeros(self.batch_size, 0, 1, device=dev)))
+            input_mask=torch.zeros(self.batch_size, 0, 1, device=dev), kv_cache=cache))
+
+    def _cross_kv(self, layer: int, enc_index: int, states: torch.Tensor):
+        """Projected encoder keys / values of one (layer, encoder): fixed for a whole decode."""
+        cache = self.__dict__.setdefault("_batch_cache", {})
+        key = ("cross_kv", layer, enc_index, states.data_ptr(), tuple(states.shape))
+        if key not in cache:
+            scope = "layer_{}/encdec_attention/enc_{}".format(layer, enc_index)
+            if self.n_heads_enc[enc_index] > 1:
+                cache[key] = (ops.linear(states, self.var(scope + "/keys_proj/kernel")),
+                              ops.linear(states, self.var(scope + "/vals_proj/kernel")))
+            else:
+                cache[key] = (states, states)
+        return cache[key]
+
+    def _project(self, scope: str, name: str, x: torch.Tensor, heads: int, bias: bool) -> torch.Tensor:
+        if heads <= 1:
+            return x
+        b = self.var("{}/{}/bias".format(scope, name)) if bias else None
+        return ops.linear(x, self.var("{}/{}/kernel".format(scope, name)), b)
+
+    def _step_cached(self, new_input: torch.Tensor, mask: torch.Tensor, kv_cache):
+        """One position through the stack.  new_input [batch, 1, dim]; mask [batch, t] incl. the
+        new position; kv_cache as in TransformerFeedables.  Returns (state [batch, dim], cache')."""
+        states = new_input
+        enc_states, enc_masks = self.encoder_states(), self.encoder_masks()
+        new_cache = []
+        for i in range(self.depth):
+            scope = "layer_{}".format(i)
+            sa = scope + "/self_attention"
+            normalized = scoped_layer_norm(self, sa, states)
+            bias = self.use_att_transform_bias
+            q = self._project(sa, "query_proj", normalized, self.n_heads_self, bias)
+            keys = torch.cat([kv_cache[2 * i],
+                              self._project(sa, "keys_proj", normalized, self.n_heads_self, bias)], 1)
+            vals = torch.cat([kv_cache[2 * i + 1],
+                              self._project(sa, "vals_proj", normalized, self.n_heads_self, bias)], 1)
+            new_cache += [keys, vals]
+            # the new position is the last one: the causal mask lets it see every cached key
+            ctx, _ = ops.mha_core(q, keys, vals, mask, False, self.n_heads_self)
+            ctx = self._project(sa, "output_proj", ctx, self.n_heads_self, bias)
+            states = ctx + states
+            cross = scope + "/encdec_attention"
+            if self.attention_combination_strategy == "serial":
+                for j, (es, em) in enumerate(zip(enc_states, enc_masks)):
+                    cs = "{}/enc_{}".format(cross, j)
+                    heads = self.n_heads_enc[j]
+                    normalized = scoped_layer_norm(self, cs, states)
+                    ek, ev = self._cross_kv(i, j, es)
+                    q = self._project(cs, "query_proj", normalized, heads, False)
+                    ctx, _ = ops.mha_core(q, ek, ev, em, False, heads)
+                    states = self._project(cs, "output_proj", ctx, heads, False) + states
+            else:
+                normalized = scoped_layer_norm(self, cross, states)
+                total = states
+                for j, (es, em) in enumerate(zip(enc_states, enc_masks)):
+                    cs = "{}/enc_{}".format(cross, j)
+                    heads = self.n_heads_enc[j]
+                    ek, ev = self._cross_kv(i, j, es)
+                    q = self._project(cs, "query_proj", normalized, heads, False)
+                    ctx, _ = ops.mha_core(q, ek, ev, em, False, heads)
+                    total = total + self._project(cs, "output_proj", ctx, heads, False)
+                states = total
+            states = feedforward_sublayer(self, scope + "/feedforward", states, 1.0, False)
+        return scoped_layer_norm(self, "", states)[:, 0, :].contiguous(), new_cache
 
     def next_state(self, loop_state: LoopState) -> Tuple[torch.Tensor, Any, Any]:
         feedables = loop_state.feedables
         tr = feedables.other
-        input_sequence = torch.cat([tr.input_sequence, feedables.embedded_input.unsqueeze(1)], dim=1)
+        new_input = feedables.embedded_input.unsqueeze(1)
+        input_sequence = torch.cat([tr.input_sequence, new_input], dim=1)
         unfinished = (~feedables.finished).to(torch.float32)
         input_mask = torch.cat([tr.input_mask, unfinished.view(-1, 1, 1)], dim=1)
-        states = self._stack(input_sequence, input_mask.squeeze(-1))
-        output_state = states[:, -1, :].contiguous()
-        return (output_state, TransformerFeedables(input_sequence=input_sequence, input_mask=input_mask),
+        if tr.kv_cache is not None and not self.train_mode:
+            output_state, cache = self._step_cached(new_input, input_mask.squeeze(-1), tr.kv_cache)
+        else:
+            cache = tr.kv_cache
+            states = self._stack(input_sequence, input_mask.squeeze(-1))
+            output_state = states[:, -1, :].contiguous()
+        return (output_state,
+                TransformerFeedables(input_sequence=input_sequence, input_mask=input_mask, kv_cache=cache),
                 loop_state.histories.other)

@@ -462,13 +462,28 @@ class _LogitsXent(torch.autograd.Function):
             dx = torch.empty(m, k, device=dev, dtype=torch.float32)
             gemm(dlogits, w2, dx, trans_b=not trans_w)
             dx = dx.view(in_shape)
-        if ctx.needs_input_grad[1]:
+        w_sink, b_sink = ctx.sinks
+        want_w, want_b = ctx.needs_input_grad[1], b is not None and ctx.needs_input_grad[2]
+        if (want_w and want_b and not trans_w and w_sink is not None and b_sink is not None
+                and b_sink.data_ptr() == w_sink.data_ptr() + 4 * k * v and w_sink.is_contiguous()):
+            # The bias gradient is the column sum of dlogits = one more row of X^T . dlogits with a
+            # column of ones appended to X, and the bias segment sits right behind the weight
+            # segment in the flat gradient buffer: ONE GEMM writes both (the 301st row costs no
+            # extra tile) instead of re-reading the [M,V] matrix for a column sum.
+            kpad = (k + 1 + 3) // 4 * 4
+            x_aug = torch.zeros(m, kpad, device=dev, dtype=torch.float32)
+            x_aug[:, :k] = x2
+            x_aug[:, k] = 1.0
+            sink_aug = torch.as_strided(w_sink, (k + 1, v), (v, 1))
+            gemm(x_aug[:, :k + 1], dlogits, sink_aug, trans_a=True, beta=1.0)
+            return dx, None, None, None, None, None, None, None
+        if want_w:
             if trans_w:   # w is [V,K]: dW = dlogits^T @ x
-                dw = _weight_grad(dlogits, x2, True, False, ctx.sinks[0], w2.shape)
+                dw = _weight_grad(dlogits, x2, True, False, w_sink, w2.shape)
             else:         # w is [K,V]: dW = x^T @ dlogits
-                dw = _weight_grad(x2, dlogits, True, False, ctx.sinks[0], w2.shape)
-        if b is not None and ctx.needs_input_grad[2]:
-            db = _bias_grad(dlogits, ctx.sinks[1])
+                dw = _weight_grad(x2, dlogits, True, False, w_sink, w2.shape)
+        if want_b:
+            db = _bias_grad(dlogits, b_sink)
         return dx, dw, db, None, None, None, None, None
 
 

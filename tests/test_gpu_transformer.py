@@ -242,3 +242,22 @@ def test_beam_search_rnn_parent(beam, bsz):
         assert max_abs(got.scores, want["scores"]) < 1e-4
     finally:
         ops.set_gemm_backend("auto")
+
+
+def test_kv_cache_equals_prefix_recompute():
+    """The cached runtime step and the reference's recompute-the-prefix schedule give the same
+    greedy symbols and (to fp32 rounding) the same logits."""
+    from neuralmonkey_b200 import ops
+    try:
+        model, _params, src, tgt = _setup("simt", seed=7)
+        dec = model["dec"]
+        feed_transformer(model, src, tgt, train=False)
+        cached_logits = dec.runtime_logits.clone()
+        cached_symbols = dec.runtime_symbols.clone()
+        dec.use_kv_cache = False
+        feed_transformer(model, src, tgt, train=False)
+        assert dec.runtime_loop_result.feedables.other.kv_cache is None
+        assert bool((dec.runtime_symbols == cached_symbols).all())
+        assert max_abs(dec.runtime_logits, cached_logits) < 1e-4
+    finally:
+        ops.set_gemm_backend("auto")
