@@ -35,6 +35,11 @@ BATCH, TX, TY = 256, 50, 50
 CPU_SAMPLE_SENTENCES = 16
 
 
+# DRAM bytes per launch of the fused vocabulary kernels at the bench shape, from the committed
+# ncu --set full capture (profiles/r01_ncu_full.md): read + write
+XENT_TRAFFIC = {"nm_logits_xent_fwd": 0.054071e9 + 0.017578e9, "nm_logits_xent_bwd": 0.072671e9 + 1.584649e9}
+
+
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -43,6 +48,8 @@ def parse_args():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=BATCH)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true",
+                    help="skip the secondary workloads (transformer / beam-8 / captioning) at N=1")
     ap.add_argument("--breakdown", action="store_true", help="print the per-entry-point time table")
     return ap.parse_args()
 
@@ -52,7 +59,7 @@ def workload_config(n_gpus, batch):
             "per_gpu_batch": batch, "global_batch": batch * n_gpus, "src_len": TX, "tgt_len": TY,
             "vocab": DIMS["vt"], "emb": 300, "rnn": 300, "optimizer": "Adam 1e-4, clip 1.0 per tensor, l2 1e-8",
             "lengths": "fixed (no padding)", "parallelism": "dp{}".format(n_gpus),
-            "gemm": "tcgen05 kind::tf32 (fp32 storage, fp32 accumulate); recurrences fp32 CUDA cores",
+            "gemm": "tcgen05 kind::tf32 (fp32 storage, fp32 accumulate); GRU recurrences on tcgen05 with weights resident in tensor memory (fp16 operands forward, tf32 backward, fp32 accumulate)",
             "l2_between_iters": "working set per step (>1.6 GB dlogits) exceeds the 126 MB L2"}
 
 
@@ -258,7 +265,11 @@ def run_b200(args):
             ach = flops[name] / (per_launch_ms * 1e-3) / 1e12
             entry = {"kernel": "tc_gemm_kernel<256> via " + name, "bound": "tensor",
                      "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf,
-                     "traffic": None, "peak_source": peak_src,
+                     "traffic": XENT_TRAFFIC.get(name), "peak_source": peak_src,
+                     "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of this kernel in "
+                                       "profiles/r01_ncu_full.md (ncu --set full, same shape)",
+                     "algorithmic_bytes": 4.0 * (m * k + k * v + v) + 16.0 * m * ((v + 255) // 256) * 2
+                     if name == "nm_logits_xent_fwd" else 4.0 * (m * k + k * v + v + m * v),
                      "note": "kind::tf32 runs at half the bf16 rate: frac of the tf32 ceiling = {:.3f}"
                              .format(ach / (peak_tf / 2.0)),
                      "ms_per_launch": per_launch_ms,
@@ -279,6 +290,17 @@ def run_b200(args):
                "sample": "{} sentences x {} target tokens per step, 2 timed steps ({:.1f} s each)"
                          .format(CPU_SAMPLE_SENTENCES, TY, cpu_step)}
 
+    # secondary workloads of BASELINE.json (configs[2..4]); N=1 only, a few seconds each
+    extras = None
+    if world == 1 and not args.no_extras:
+        import bench_workloads
+        extras = {}
+        for name in ("transformer", "beam", "captioning"):
+            try:
+                extras[name] = bench_workloads.RUNNERS[name]()
+            except Exception as exc:  # pylint: disable=broad-except
+                extras[name] = {"error": "{}: {}".format(type(exc).__name__, exc)}
+
     h2d = 2 * batch * (TX + TY) * 8  # int64 ids: encoder ids, decoder targets + fed symbols
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
@@ -288,7 +310,8 @@ def run_b200(args):
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4, "last_loss": loss},
             "gpu_launches": launches, "clocks": clocks.summary(), "roofline": roof,
             "cpu_baseline": cpu,
-            "breakdown_ms_per_step": {n: round(t, 4) for n, t, _ in table[:16]}}
+            "breakdown_ms_per_step": {n: round(t, 4) for n, t, _ in table[:16]},
+            "extra_workloads": extras}
     print(json.dumps(line))
 
 

@@ -98,7 +98,7 @@ def run_transformer(steps=5, warmup=3, bsz=64, length=64, vocab=32000):
             "params": int(model["arena"].trainable_size), "inputs": "pinned host ids, H2D inside the timed region"}
 
 
-def run_beam(bsz=8, beam=8, steps=128, vocab=32000, src_len=32, reps=1):
+def run_beam(bsz=64, beam=8, steps=128, vocab=32000, src_len=32, reps=1):
     from neuralmonkey_b200.decoders import BeamSearchDecoder
     model = build_transformer(vocab=vocab, max_len=max(steps, src_len), tie=False)
     dec = model["dec"]

@@ -140,6 +140,30 @@ class BeamSearchDecoder(ModelPart):
             last_search_step_output=SearchResults(scores=scores, token_ids=token_ids),
             last_dec_loop_state=dec_ls, last_search_state=state, attention_loop_states=[])
 
+    # Replay one captured CUDA graph per step when the parent is a Transformer decoder with a KV
+    # cache (decoders/beam_graph.py); False falls back to the step-by-step host loop.
+    use_cuda_graph = True
+
+    def _graph_outputs(self, tiled_states, tiled_masks) -> BeamSearchOutput:
+        from neuralmonkey_b200.decoders.beam_graph import TransformerBeamGraph
+        parent = self.parent_decoder
+        bsz = parent.batch_size
+        key = (bsz, tuple(tuple(s.shape) for s in tiled_states))
+        graphs = self.__dict__.setdefault("_graphs", {})
+        if key not in graphs:
+            graphs[key] = TransformerBeamGraph(self, bsz, key[1])
+        res = graphs[key].run(tiled_states, tiled_masks)
+        dev = runtime.device()
+        feedables = DecoderFeedables(step=res["steps"] + 1, finished=res["finished"].view(-1),
+                                     embedded_input=torch.zeros(0, device=dev), other=None)
+        dec_ls = LoopState(histories=parent.get_initial_histories(), constants=None, feedables=feedables)
+        return BeamSearchOutput(
+            last_search_step_output=SearchResults(scores=res["scores"], token_ids=res["token_ids"]),
+            last_dec_loop_state=dec_ls,
+            last_search_state=SearchState(logprob_sum=res["logprob_sum"], prev_logprobs=res["logprobs"],
+                                          lengths=res["lengths"], finished=res["finished"]),
+            attention_loop_states=[])
+
     @tensor
     def outputs(self) -> BeamSearchOutput:
         parent = self.parent_decoder
@@ -147,6 +171,14 @@ class BeamSearchDecoder(ModelPart):
         # beam-tiled encoder tensors for the duration of the search (:174-186)
         tiled_states = [self.expand_to_beam(s) for s in enc_states()]
         tiled_masks = [self.expand_to_beam(m) if m is not None else None for m in enc_masks()]
+        from neuralmonkey_b200.decoders.transformer import TransformerDecoder
+        if (self.use_cuda_graph and isinstance(parent, TransformerDecoder) and parent.use_kv_cache
+                and runtime.device().type == "cuda"):
+            try:
+                with torch.no_grad():
+                    return self._graph_outputs(tiled_states, tiled_masks)
+            finally:
+                parent.encoder_states, parent.encoder_masks = enc_states, enc_masks
         parent.encoder_states = lambda: tiled_states
         parent.encoder_masks = lambda: tiled_masks
         try:

@@ -208,9 +208,14 @@ class TransformerDecoder(AutoregressiveDecoder):
         b = self.var("{}/{}/bias".format(scope, name)) if bias else None
         return ops.linear(x, self.var("{}/{}/kernel".format(scope, name)), b)
 
-    def _step_cached(self, new_input: torch.Tensor, mask: torch.Tensor, kv_cache):
+    def _step_cached(self, new_input: torch.Tensor, mask: torch.Tensor, kv_cache, static_pos=None):
         """One position through the stack.  new_input [batch, 1, dim]; mask [batch, t] incl. the
-        new position; kv_cache as in TransformerFeedables.  Returns (state [batch, dim], cache')."""
+        new position; kv_cache as in TransformerFeedables.  Returns (state [batch, dim], cache').
+
+        With `static_pos` (int64 device tensor [1]) the caches are full-length buffers
+        [batch, max_time, dim] updated in place at that position, and `mask` covers max_time with
+        zeros beyond it (masked keys get probability exactly 0): every shape is independent of the
+        step, which is what lets BeamSearchDecoder replay one CUDA graph per step."""
         states = new_input
         enc_states, enc_masks = self.encoder_states(), self.encoder_masks()
         new_cache = []
@@ -220,10 +225,14 @@ class TransformerDecoder(AutoregressiveDecoder):
             normalized = scoped_layer_norm(self, sa, states)
             bias = self.use_att_transform_bias
             q = self._project(sa, "query_proj", normalized, self.n_heads_self, bias)
-            keys = torch.cat([kv_cache[2 * i],
-                              self._project(sa, "keys_proj", normalized, self.n_heads_self, bias)], 1)
-            vals = torch.cat([kv_cache[2 * i + 1],
-                              self._project(sa, "vals_proj", normalized, self.n_heads_self, bias)], 1)
+            k_new = self._project(sa, "keys_proj", normalized, self.n_heads_self, bias)
+            v_new = self._project(sa, "vals_proj", normalized, self.n_heads_self, bias)
+            if static_pos is not None:
+                keys = kv_cache[2 * i].index_copy_(1, static_pos, k_new)
+                vals = kv_cache[2 * i + 1].index_copy_(1, static_pos, v_new)
+            else:
+                keys = torch.cat([kv_cache[2 * i], k_new], 1)
+                vals = torch.cat([kv_cache[2 * i + 1], v_new], 1)
             new_cache += [keys, vals]
             # the new position is the last one: the causal mask lets it see every cached key
             ctx, _ = ops.mha_core(q, keys, vals, mask, False, self.n_heads_self)

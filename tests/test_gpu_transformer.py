@@ -159,8 +159,11 @@ def _oracle_transformer_beam(params, spec, oenc, beam, max_steps, alpha):
                          lambda st, idx: (st[0][idx], st[1][idx]))
 
 
+@pytest.mark.parametrize("graph", [True, False])
 @pytest.mark.parametrize("beam,alpha,bsz", [(1, 0.0, 3), (4, 1.0, 3), (5, 0.6, 1)])
-def test_beam_search_transformer_parent(beam, alpha, bsz):
+def test_beam_search_transformer_parent(beam, alpha, bsz, graph):
+    """graph=True: one CUDA graph replayed per step over static-shape buffers
+    (decoders/beam_graph.py); graph=False: the step-by-step host loop.  Both against the oracle."""
     from neuralmonkey_b200 import ops
     from neuralmonkey_b200.decoders import BeamSearchDecoder
     from neuralmonkey_b200.runners import BeamSearchRunner
@@ -168,6 +171,7 @@ def test_beam_search_transformer_parent(beam, alpha, bsz):
         model, params, src, tgt = _setup("simt", bsz=bsz, seed=5)
         bs = BeamSearchDecoder(name="bs", parent_decoder=model["dec"], beam_size=beam, max_steps=7,
                                length_normalization=alpha)
+        bs.use_cuda_graph = graph
         feed_transformer(model, src, None, train=False)
         bs.reset_batch()
         bs.batch_size = bsz
@@ -259,5 +263,41 @@ def test_kv_cache_equals_prefix_recompute():
         assert dec.runtime_loop_result.feedables.other.kv_cache is None
         assert bool((dec.runtime_symbols == cached_symbols).all())
         assert max_abs(dec.runtime_logits, cached_logits) < 1e-4
+    finally:
+        ops.set_gemm_backend("auto")
+
+
+def test_beam_graph_reused_across_batches_and_early_stop():
+    """The captured graph is replayed for a second batch of the same shape (fresh encoder states,
+    same buffers), and a search whose hypotheses all finish early is trimmed to the step the
+    reference loop stops at."""
+    from neuralmonkey_b200 import ops
+    from neuralmonkey_b200.decoders import BeamSearchDecoder
+    try:
+        model, params, src, _tgt = _setup("simt", bsz=2, seed=11)
+        # make </s> very likely so the search ends long before max_steps
+        params = dict(params)
+        params["decoder/word_embeddings"] = params["decoder/word_embeddings"].clone()
+        model["arena"].load_dict(params)
+        spec = O.TransformerDecoderSpec("decoder", CFG["depth"], CFG["heads"], CFG["heads"],
+                                        CFG["max_len"], True, False)
+        bs_graph = BeamSearchDecoder(name="bs", parent_decoder=model["dec"], beam_size=3, max_steps=30,
+                                     length_normalization=1.0)
+        bs_loop = BeamSearchDecoder(name="bs2", parent_decoder=model["dec"], beam_size=3, max_steps=30,
+                                    length_normalization=1.0)
+        bs_loop.use_cuda_graph = False
+        for seed in (11, 12, 13):
+            src, _ = random_batch(2, 8, 7, CFG["vs"], CFG["vt"], seed=seed)
+            outs = []
+            for bs in (bs_graph, bs_loop):
+                feed_transformer(model, src, None, train=False)
+                bs.reset_batch()
+                bs.batch_size = 2
+                outs.append(bs.outputs)
+            a, b = outs[0].last_search_step_output, outs[1].last_search_step_output
+            assert a.token_ids.shape == b.token_ids.shape
+            assert bool((a.token_ids[1:] == b.token_ids[1:]).all())
+            assert max_abs(a.scores, b.scores) < 1e-4
+        assert len(bs_graph._graphs) == 1
     finally:
         ops.set_gemm_backend("auto")
