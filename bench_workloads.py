@@ -79,7 +79,7 @@ def synthetic_ids(bsz, length, vocab, seed, eos=True):
     return ids
 
 
-def run_transformer(steps=5, warmup=3, bsz=64, length=64, vocab=32000):
+def run_transformer(steps=5, warmup=3, bsz=64, length=64, vocab=32000, breakdown=False):
     model = build_transformer(vocab=vocab, max_len=length)
     batches = [(synthetic_ids(bsz, length, vocab, SEED + i, eos=False).pin_memory(),
                 synthetic_ids(bsz, length, vocab, SEED + 100 + i).pin_memory()) for i in range(4)]
@@ -91,6 +91,15 @@ def run_transformer(steps=5, warmup=3, bsz=64, length=64, vocab=32000):
 
     ms = _time(step, steps, warmup)
     loss = float(step(0)["losses"][0])
+    if breakdown:
+        from neuralmonkey_b200 import lib
+        lib.profile_start()
+        step(1)
+        prof = lib.profile_stop()
+        table = sorted(((n, d["ms"], d["calls"]) for n, d in prof.items()), key=lambda x: -x[1])
+        for n, t, c in table[:30]:
+            print("# {:34s} {:8.3f} ms  {:4d} calls".format(n, t, c), file=sys.stderr)
+        print("# sum {:.3f} ms vs {:.3f} ms per step".format(sum(t for _, t, _ in table), ms), file=sys.stderr)
     return {"workload": "tests/transformer.ini perf shape: L=6 d=512 h=8 F=2048 V={} batch {}x{}".format(
                 vocab, bsz, length),
             "metric": "train_target_tokens_per_sec", "value": bsz * length / (ms * 1e-3),
@@ -183,8 +192,8 @@ def run_captioning(steps=3, warmup=2, bsz=32, vt=10000, ty=16):
 RUNNERS = {"transformer": run_transformer, "beam": run_beam, "captioning": run_captioning}
 
 if __name__ == "__main__":
-    for name in (sys.argv[1:] or list(RUNNERS)):
+    for name in ([a for a in sys.argv[1:] if not a.startswith('--')] or list(RUNNERS)):
         t0 = time.perf_counter()
-        result = RUNNERS[name]()
+        result = RUNNERS[name](breakdown=True) if name == "transformer" and "--breakdown" in sys.argv else RUNNERS[name]()
         result["wall_s"] = time.perf_counter() - t0
         print(json.dumps(result), flush=True)

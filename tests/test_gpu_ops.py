@@ -243,16 +243,25 @@ def test_linear_and_maxout_grad():
         ops.set_gemm_backend("auto")
 
 
+# (bsz, tq, tk, heads, dh): row kernels (tq < 8 or dh % 8 != 0) and tiled kernels (one, two, three
+# strips of 64 keys; ragged query blocks; cross-attention shapes)
+MHA_SHAPES = [(3, 5, 7, 2, 8), (2, 9, 9, 3, 6), (3, 40, 40, 4, 16), (2, 70, 70, 2, 64),
+              (2, 33, 130, 2, 32), (2, 1, 50, 4, 16), (1, 130, 64, 8, 64)]
+
+
 @pytest.mark.parametrize("causal", [False, True])
 @pytest.mark.parametrize("use_mask", [False, True])
-def test_mha_core_fwd_bwd(causal, use_mask):
+@pytest.mark.parametrize("shape", MHA_SHAPES)
+def test_mha_core_fwd_bwd(causal, use_mask, shape):
     from neuralmonkey_b200 import ops
-    bsz, tq, tk, heads, dh = 3, 5, (5 if causal else 7), 2, 8
+    bsz, tq, tk, heads, dh = shape
+    if causal:
+        tk = tq
     g = torch.Generator().manual_seed(8)
     q, k, v = (torch.randn(bsz, t, heads * dh, generator=g) for t in (tq, tk, tk))
     mask = None
     if use_mask:
-        lens = torch.tensor([tk, 3, 1])
+        lens = torch.tensor([tk, 3, 1][:bsz])
         mask = (torch.arange(tk).unsqueeze(0) < lens.unsqueeze(1)).float()
     qd, kd, vd = _leaf(q), _leaf(k), _leaf(v)
     out, probs = ops.mha_core(qd, kd, vd, mask.cuda() if use_mask else None, causal, heads)
