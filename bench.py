@@ -200,15 +200,19 @@ def run_b200(args):
             torch.distributed.barrier()
         torch.cuda.synchronize()
 
+    host_ms = [0.0]
+
     def timed(step_fn, steps, read_loss):
         barrier()
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ev0.record()
         last = None
+        t_host = time.perf_counter()
         for i in range(steps):
             out = step_fn(i)
             if read_loss:
                 last = float(out["losses"][0])  # device -> host read of the step's loss
+        host_ms[0] = (time.perf_counter() - t_host) * 1e3 / steps   # time the host needs to ENQUEUE a step
         ev1.record()
         barrier()
         ms = torch.tensor([ev0.elapsed_time(ev1)], device=dev)
@@ -221,6 +225,7 @@ def run_b200(args):
     launches0 = lib.launch_count()
     with ClockSampler(dev.index or 0) as clocks:
         ms_step, _ = timed(step_device_inputs, args.steps, read_loss=False)
+    host_enqueue_ms = host_ms[0]
     launches = lib.launch_count() - launches0
 
     # per-entry-point device time inside timed steps (CUDA events around every C-ABI call)
@@ -253,29 +258,50 @@ def run_b200(args):
     peak_tf = float(peaks.get("bf16_tflops_sustained", 1400.0))
     peak_src = "measured bf16_tflops_sustained" if peaks else "fallback (B200_PROFILING.md sustained)"
     m, k, v = batch * TY, DIMS["out"], DIMS["vt"]
-    flops = {"nm_logits_xent_fwd": 2.0 * m * k * v, "nm_logits_xent_bwd": 2.0 * m * k * v}
     table = sorted(((n, d["ms"] / prof_steps, d["calls"] // prof_steps) for n, d in prof.items()),
                    key=lambda x: -x[1])
     total_ms = sum(t for _, t, _ in table)
-    dominant = table[0][0] if table else None
+    # The dominant kernel is tc_gemm_kernel (gemm_tc.cu): every dense projection, weight-gradient
+    # product and the fused vocabulary forward/backward are instances of it.  Algorithmic flops per
+    # launch = 2*M*N*K of the product; time = CUDA events around the launches
+    # inside the profiled steps.
+    import re
+    fam_flops, fam_ms, instances = 0.0, 0.0, []
+    for name, d in prof.items():
+        fl = None
+        mm = re.match(r"nm_gemm\[(\w\w) (\d+)x(\d+)x(\d+)\]", name)
+        if mm:
+            fl = 2.0 * int(mm.group(2)) * int(mm.group(3)) * int(mm.group(4))
+        elif name in ("nm_logits_xent_fwd", "nm_logits_xent_bwd"):
+            fl = 2.0 * m * k * v
+        if fl is None:
+            continue
+        calls = d["calls"]
+        fam_flops += fl * calls
+        fam_ms += d["ms"]
+        instances.append({"call": name, "launches_per_step": calls // prof_steps,
+                          "ms_per_launch": d["ms"] / calls, "tflops": fl / (d["ms"] / calls * 1e-3) / 1e12,
+                          "traffic": XENT_TRAFFIC.get(name)})
+    instances.sort(key=lambda e: -e["ms_per_launch"] * e["launches_per_step"])
     roof = None
-    for name in ("nm_logits_xent_fwd", "nm_logits_xent_bwd"):
-        if name in prof:
-            per_launch_ms = prof[name]["ms"] / prof[name]["calls"]
-            ach = flops[name] / (per_launch_ms * 1e-3) / 1e12
-            entry = {"kernel": "tc_gemm_kernel<256> via " + name, "bound": "tensor",
-                     "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf,
-                     "traffic": XENT_TRAFFIC.get(name), "peak_source": peak_src,
-                     "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of this kernel in "
-                                       "profiles/r01_ncu_full.md (ncu --set full, same shape)",
-                     "algorithmic_bytes": 4.0 * (m * k + k * v + v) + 16.0 * m * ((v + 255) // 256) * 2
-                     if name == "nm_logits_xent_fwd" else 4.0 * (m * k + k * v + v + m * v),
-                     "note": "kind::tf32 runs at half the bf16 rate: frac of the tf32 ceiling = {:.3f}"
-                             .format(ach / (peak_tf / 2.0)),
-                     "ms_per_launch": per_launch_ms,
-                     "share_of_step": prof[name]["ms"] / prof_steps / max(total_ms, 1e-9)}
-            if roof is None or name == dominant:
-                roof = entry
+    if fam_ms > 0:
+        ach = fam_flops / (fam_ms * 1e-3) / 1e12
+        best = max(instances, key=lambda e: e["tflops"])
+        roof = {"kernel": "tc_gemm_kernel (tcgen05 kind::tf32, all instances of the step)", "bound": "tensor",
+                "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf,
+                "traffic": XENT_TRAFFIC["nm_logits_xent_fwd"] + XENT_TRAFFIC["nm_logits_xent_bwd"],
+                "traffic_note": "DRAM read+write bytes per launch of the two fused vocabulary instances "
+                                "(profiles/r01_ncu_full.md, ncu --set full); their algorithmic bytes are "
+                                "{:.0f} MB (fwd) and {:.0f} MB (bwd, incl. the fp32 dlogits it must write)"
+                                .format((4.0 * (m * k + k * v + v) + 32.0 * m * ((v + 255) // 256)) / 1e6,
+                                        4.0 * (m * k + k * v + v + m * v) / 1e6),
+                "peak_source": peak_src,
+                "note": "kind::tf32 issues at half the bf16 rate, so 0.5 is the ceiling of frac for this "
+                        "kernel; frac of the tf32 ceiling = {:.3f} (best instance {}: {:.0f} TFLOP/s = {:.3f})"
+                        .format(ach / (peak_tf / 2.0), best["call"], best["tflops"],
+                                best["tflops"] / (peak_tf / 2.0)),
+                "share_of_step": fam_ms / prof_steps / max(total_ms, 1e-9),
+                "instances": instances[:6]}
     if args.breakdown:
         for n, t, c in table:
             print("# {:34s} {:8.3f} ms/step  {:4d} calls/step".format(n, t, c), file=sys.stderr)
@@ -311,6 +337,7 @@ def run_b200(args):
             "gpu_launches": launches, "clocks": clocks.summary(), "roofline": roof,
             "cpu_baseline": cpu,
             "breakdown_ms_per_step": {n: round(t, 4) for n, t, _ in table[:16]},
+            "host_enqueue_ms_per_step": host_enqueue_ms,
             "extra_workloads": extras}
     print(json.dumps(line))
 

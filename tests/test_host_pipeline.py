@@ -1,0 +1,104 @@
+"""Host-side logic next to the hot path: dataset batching, learning-rate
+schedule, BLEU, image reader, beam runner ranges - all on the CPU."""
+import math
+import os
+
+import numpy as np
+import pytest
+
+
+def _write(path, lines):
+    with open(path, "w") as f:
+        f.write("\n".join(lines) + "\n")
+
+
+def test_dataset_fixed_batches_and_series(tmp_path):
+    from neuralmonkey_b200.dataset import BatchingScheme, load
+    src, tgt = tmp_path / "s.txt", tmp_path / "t.txt"
+    _write(src, ["a b c", "d e", "f", "g h i j", "k"])
+    _write(tgt, ["A B", "C", "D E F", "G", "H I"])
+    ds = load("toy", ["source", "target"], [str(src), str(tgt)], BatchingScheme(batch_size=2))
+    batches = list(ds.batches())
+    assert [len(b) for b in batches] == [2, 2, 1]
+    assert list(batches[0].get_series("source")) == [["a", "b", "c"], ["d", "e"]]
+    assert list(batches[2].get_series("target")) == [["H", "I"]]
+    dropped = load("toy", ["source", "target"], [str(src), str(tgt)],
+                   BatchingScheme(batch_size=2, drop_remainder=True))
+    assert [len(b) for b in dropped.batches()] == [2, 2]
+
+
+def test_dataset_bucketing_groups_by_length(tmp_path):
+    from neuralmonkey_b200.dataset import BatchingScheme, load
+    src = tmp_path / "s.txt"
+    _write(src, ["x"] * 5 + ["x y z w"] * 3 + ["x y z w u v t"] * 2)
+    scheme = BatchingScheme(bucket_boundaries=[2, 5], bucket_batch_sizes=[4, 2, 1])
+    ds = load("toy", ["source"], [str(src)], scheme)
+    seen = 0
+    for batch in ds.batches():
+        lens = [len(s) for s in batch.get_series("source")]
+        seen += len(lens)
+        buckets = {0 if n <= 2 else (1 if n <= 5 else 2) for n in lens}
+        assert len(buckets) == 1                          # never mixes buckets
+        assert len(lens) <= [4, 2, 1][buckets.pop()]      # bucket batch size respected
+    assert seen == 10
+
+
+def test_batching_scheme_validation():
+    from neuralmonkey_b200.dataset import BatchingScheme
+    with pytest.raises(ValueError):
+        BatchingScheme()
+    with pytest.raises(ValueError):
+        BatchingScheme(batch_size=4, bucket_boundaries=[3], bucket_batch_sizes=[1, 1])
+
+
+def test_noam_decay_uses_step_before_increment():
+    from neuralmonkey_b200.functions import noam_decay
+    sched = noam_decay(learning_rate=0.2, model_dimension=6, warmup_steps=111)
+    assert sched(0) == 0.0                                # first update runs at rate 0
+    peak = 0.2 / math.sqrt(6) / math.sqrt(111)
+    assert abs(sched(111) - peak) < 1e-12
+    assert sched(50) < sched(111) > sched(500)
+    assert abs(sched(444) - peak / 2) < 1e-12             # step^-0.5 decay after warm-up
+
+
+def test_bleu_matches_hand_computation():
+    from neuralmonkey_b200.evaluators.bleu import BLEUEvaluator
+    bleu = BLEUEvaluator()
+    ref = [["the", "cat", "sat", "on", "the", "mat"]]
+    assert abs(bleu(ref, ref) - 100.0) < 1e-9
+    assert bleu([["dog"]], ref) == 0.0
+    hyp = [["the", "cat", "sat", "on", "a", "mat"]]
+    # precisions 5/6, 3/5, 1/4, 0/3 smoothed by the evaluator: just bounded here
+    assert 0.0 <= bleu(hyp, ref) < 100.0
+    assert BLEUEvaluator.compare_scores(2.0, 1.0) == 1
+
+
+def test_imagenet_reader_crops_and_pads(tmp_path):
+    """Reference quirk kept on purpose: no rescaling, centre crop + zero padding
+    (readers/image_reader.py:147-178)."""
+    from neuralmonkey_b200.readers.image_reader import imagenet_reader
+    big = np.arange(10 * 12 * 3, dtype=np.float64).reshape(10, 12, 3)
+    small = np.ones((4, 5, 3))
+    np.save(tmp_path / "big.npy", big)
+    np.save(tmp_path / "small.npy", small)
+    _write(tmp_path / "list.txt", ["big.npy", "small.npy"])
+    load = imagenet_reader(str(tmp_path), target_width=8, target_height=6, vgg_normalization=True)
+    a, b = list(load([str(tmp_path / "list.txt")]))
+    assert a.shape == b.shape == (6, 8, 3)
+    means = np.array([123.68, 116.779, 103.939])
+    assert np.allclose(a + means, big[2:8, 2:10])         # centre crop of the larger image
+    assert np.allclose(b[:4, :5] + means, 1.0) and np.allclose(b[4:, :] + means, 0.0)
+
+
+def test_beam_search_runner_range_names_and_validation():
+    from neuralmonkey_b200.runners import beam_search_runner_range
+
+    from neuralmonkey_b200.model.model_part import GenericModelPart
+
+    class Dec(GenericModelPart):
+        beam_size = 3
+        vocabulary = None
+    runners = beam_search_runner_range("target", Dec(), max_rank=2)
+    assert [r.output_series for r in runners] == ["target.rank001", "target.rank002"]
+    with pytest.raises(ValueError):
+        beam_search_runner_range("target", Dec(), max_rank=4)
