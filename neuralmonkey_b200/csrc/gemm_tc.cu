@@ -42,7 +42,8 @@ struct TcCfg {
   static constexpr int STAGE_BYTES = TC_A_BYTES + B_BYTES;
   static constexpr int STAGES = (TC_SMEM_BUDGET / STAGE_BYTES) > 8 ? 8 : (TC_SMEM_BUDGET / STAGE_BYTES);
   static constexpr int TMEM_COLS = 2 * BN;  // 128, 256, 512: powers of two >= 32
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ +
+                                    TC_EPI_WARPS * 4096 /*per-warp store staging*/;
 };
 
 // ---------------------------------------------------------------------------
@@ -91,19 +92,52 @@ __device__ __forceinline__ void store32(float* __restrict__ c, const float (&x)[
   }
 }
 
+// Coalesced store of a warp's 32x32 chunk.  tcgen05.ld hands every thread one ROW (32 columns),
+// so direct stores scatter 16-byte pieces over 32 different cache lines per instruction - the L2
+// request rate, not DRAM, then bounds a kernel that writes a large C (the 1.6 GB dlogits).  Going
+// through a 4 KB per-warp staging tile (XOR-swizzled float4 slots: conflict-free both ways) turns
+// each store instruction into four full 128-byte row segments.
+__device__ __forceinline__ void store32_coalesced(float* __restrict__ stage, float* __restrict__ C,
+                                                  int64_t ldc, int64_t row_base, int col0, int64_t M,
+                                                  const float (&x)[32], int lane) {
+  float4* st4 = reinterpret_cast<float4*>(stage);
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+    st4[lane * 8 + (j ^ (lane & 7))] = make_float4(x[4 * j], x[4 * j + 1], x[4 * j + 2], x[4 * j + 3]);
+  __syncwarp();
+  const int sub = lane >> 3, slot = lane & 7;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int r = 4 * i + sub;
+    const float4 v = st4[r * 8 + (slot ^ (r & 7))];
+    const int64_t grow = row_base + r;
+    if (grow < M) *reinterpret_cast<float4*>(C + grow * ldc + col0 + 4 * slot) = v;
+  }
+  __syncwarp();
+}
+
 // mode is a compile-time constant so each kernel instance carries one epilogue only.
 template <int MODE>
 __device__ __forceinline__ void epilogue_chunk(const TcEpilogue& e, float (&x)[32], int64_t row,
                                                int col0, int64_t M, int N, RowStats& st,
                                                int target, float row_lse2, float row_w,
-                                               bool vec_ok) {
-  if (row >= M || col0 >= N) return;
+                                               bool vec_ok, float* __restrict__ stage, int lane) {
+  if (col0 >= N) return;                                     // warp-uniform
   const int ncols = min(32, N - col0);
+  // full, aligned chunks leave through the staging tile (all 32 lanes take part, rows >= M are
+  // masked at the store); everything else keeps the per-row path
+  const bool coalesced = vec_ok && ncols == 32 &&
+                         (MODE == TC_EPI_XENT_BWD || (MODE == TC_EPI_DENSE && e.beta == 0.f));
+  if (row >= M && !coalesced) return;
   float b[32];
   load_bias32(e.bias, col0, ncols, b);
   if (MODE == TC_EPI_DENSE) {
 #pragma unroll
     for (int j = 0; j < 32; ++j) x[j] = apply_act(x[j] + b[j], e.act);
+    if (coalesced) {
+      store32_coalesced(stage, e.C, e.ldc, row - lane, col0, M, x, lane);
+      return;
+    }
     float* c = e.C + row * e.ldc + col0;
     if (e.beta != 0.f) {
 #pragma unroll
@@ -160,7 +194,10 @@ __device__ __forceinline__ void epilogue_chunk(const TcEpilogue& e, float (&x)[3
       for (int j = 0; j < 32; ++j)
         if (j == t_rel) x[j] -= row_w;
     }
-    store32(e.C + row * e.ldc + col0, x, ncols, vec_ok);
+    if (coalesced)
+      store32_coalesced(stage, e.C, e.ldc, row - lane, col0, M, x, lane);
+    else
+      store32(e.C + row * e.ldc + col0, x, ncols, vec_ok);
   }
 }
 
@@ -325,6 +362,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     const int quad = warp & 3;                // TMEM lanes [32*quad, 32*quad+32)
     const int half = (warp - 2) >> 2;         // 0: even chunks, 1: odd chunks
     const bool vec_ok = ((epi.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(epi.C) & 15) == 0);
+    // per-warp staging tile behind the barriers (generic pointer of the 1 KB-aligned window)
+    float* stage = reinterpret_cast<float*>(smem_raw + (smem_base - smem_u32(smem_raw)) +
+                                            STAGES * Cfg::STAGE_BYTES + 256 + (warp - 2) * 4096);
     const int n32 = (int)N;
     int64_t it = 0;
     for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
@@ -354,7 +394,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           epilogue_chunk_atomic(epi, v, row, (int)(tn * BN) + c * 32, M, n32, split == 0);
         else
           epilogue_chunk<MODE>(epi, v, row, (int)(tn * BN) + c * 32, M, n32, st, target, row_lse2,
-                               row_w, vec_ok);
+                               row_w, vec_ok, stage, lane);
       }
       if (MODE == TC_EPI_XENT_FWD && row < M)
         epi.part[(row * tiles_n + tn) * 2 + half] =

@@ -27,7 +27,7 @@ def test_bahdanau_against_golden():
         model["arena"].load_dict(_params(g, "bp::"))
         src, tgt = torch.from_numpy(g["b_src"]), torch.from_numpy(g["b_tgt"])
         feed(model, src, tgt, train=True)
-        assert np.abs(model["enc"].output.cpu().numpy() - g["b_enc_output"]).max() < 5e-5
+        assert np.abs(model["enc"].output.detach().cpu().numpy() - g["b_enc_output"]).max() < 5e-5
         assert abs(float(model["dec"].train_loss) - float(g["b_train_loss"])) < 1e-4
         assert np.abs(model["dec"].train_xents.detach().cpu().numpy() - g["b_train_xents"]).max() < 2e-4
         feed(model, src, tgt, train=False)
