@@ -41,7 +41,7 @@ struct TcCfg {
   static constexpr int B_BYTES = BN * TC_BK * 4;
   static constexpr int STAGE_BYTES = TC_A_BYTES + B_BYTES;
   static constexpr int STAGES = (TC_SMEM_BUDGET / STAGE_BYTES) > 8 ? 8 : (TC_SMEM_BUDGET / STAGE_BYTES);
-  static constexpr int TMEM_COLS = 2 * BN;  // 128, 256, 512: powers of two >= 32
+  static constexpr int TMEM_COLS = BN <= 64 ? 128 : (BN <= 128 ? 256 : 512);  // 2*BN rounded to a power of two
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ +
                                     TC_EPI_WARPS * 4096 /*per-warp store staging*/;
 };
@@ -511,9 +511,12 @@ static int launch_cfg(const CUtensorMap& ma, const CUtensorMap& mb, int64_t M, i
   return NM_OK;
 }
 
-static int pick_bn(int64_t M, int64_t N) {
+static int pick_bn(int64_t M, int64_t N, int64_t K) {
   if (N <= 64) return 64;
   if (N <= 128) return 128;
+  // skinny output, very long reduction (dX of the vocabulary projection: 12800 x 300 x 32000):
+  // the A stream dominates and is re-read once per N tile, so cover N with the fewest equal tiles
+  if (K >= 8192 && N > 256 && N <= 320) return 160;
   const int64_t pad128 = ceil_div(N, 128) * 128, pad256 = ceil_div(N, 256) * 256;
   const int64_t tiles256 = ceil_div(M, TC_BM) * ceil_div(N, 256);
   if (pad256 == pad128 && tiles256 >= sm_count()) return 256;
@@ -528,7 +531,7 @@ int tc_gemm_launch(int transA, int transB, int64_t M, int64_t N, int64_t K, cons
   // op(B) is [K,N]: transB=0 -> B stored [K,N], N contiguous (MN-major);
   //                 transB=1 -> B stored [N,K], K contiguous (K-major).
   const bool a_mn = transA != 0, b_mn = transB == 0;
-  const int bn = (epi.mode == TC_EPI_DENSE) ? pick_bn(M, N) : TC_XENT_BN;
+  const int bn = (epi.mode == TC_EPI_DENSE) ? pick_bn(M, N, K) : TC_XENT_BN;
   CUtensorMap ma, mb;
   int rc;
   if (!a_mn) rc = make_map(&ma, A, M, K, lda, TC_BK, TC_BM, false);
@@ -565,12 +568,27 @@ int tc_gemm_launch(int transA, int transB, int64_t M, int64_t N, int64_t K, cons
         kb_per = (int)ceil_div(num_kb, want);
         splits = (int)ceil_div(num_kb, kb_per);  // every split owns >= 1 k-block
       }
+    } else if (epi.act == NM_ACT_NONE && num_kb >= 256 && tiles < 4 * (int64_t)sm_count()) {
+      // a few waves of very long tiles: the last, partly filled wave costs a whole tile time.
+      // Cut K so that the work items fill the waves (static round-robin: ceil(items/SMs) rounds).
+      int best = 1;
+      double best_cost = (double)ceil_div(tiles, sm_count());
+      for (int sp = 2; sp <= 8; ++sp) {
+        if (num_kb / sp < 64) break;
+        const double cost = (double)ceil_div(tiles * sp, sm_count()) / sp;
+        if (cost < best_cost * 0.93) { best_cost = cost; best = sp; }
+      }
+      if (best > 1) {
+        kb_per = (int)ceil_div(num_kb, best);
+        splits = (int)ceil_div(num_kb, kb_per);
+      }
     }
     if (splits > 1 && epi.beta == 0.f)  // partial sums are added: start from zero
       NM_CUDA_TRY(cudaMemset2DAsync(epi.C, sizeof(float) * epi.ldc, 0, sizeof(float) * N, M, s));
   }
   if (bn == 64) NM_TC_DISPATCH(64, TC_EPI_DENSE);
   if (bn == 128) NM_TC_DISPATCH(128, TC_EPI_DENSE);
+  if (bn == 160) NM_TC_DISPATCH(160, TC_EPI_DENSE);
   NM_TC_DISPATCH(256, TC_EPI_DENSE);
 #undef NM_TC_DISPATCH
 }

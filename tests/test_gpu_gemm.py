@@ -26,7 +26,8 @@ def _ref(a, b, ta, tb):
 @pytest.mark.parametrize("ta", [False, True])
 @pytest.mark.parametrize("tb", [False, True])
 @pytest.mark.parametrize("shape", [(128, 128, 32), (256, 384, 96), (200, 300, 300), (1000, 600, 300),
-                                   (12, 900, 1200), (300, 1000, 1024), (129, 257, 36)])
+                                   (12, 900, 1200), (300, 1000, 1024), (129, 257, 36),
+                                   (1100, 300, 8192)])   # skinny N, long K: 160-wide tiles (+ split-K)
 def test_tc_gemm_matches_fp64(ta, tb, shape):
     from neuralmonkey_b200 import lib, ops
     m, n, k = shape
