@@ -48,6 +48,8 @@ def parse_args():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=BATCH)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-cuda-graph", action="store_true",
+                    help="issue every kernel of a step from Python instead of replaying the captured step")
     ap.add_argument("--no-extras", action="store_true",
                     help="skip the secondary workloads (transformer / beam-8 / captioning) at N=1")
     ap.add_argument("--breakdown", action="store_true", help="print the per-entry-point time table")
@@ -59,6 +61,7 @@ def workload_config(n_gpus, batch):
             "per_gpu_batch": batch, "global_batch": batch * n_gpus, "src_len": TX, "tgt_len": TY,
             "vocab": DIMS["vt"], "emb": 300, "rnn": 300, "optimizer": "Adam 1e-4, clip 1.0 per tensor, l2 1e-8",
             "lengths": "fixed (no padding)", "parallelism": "dp{}".format(n_gpus),
+            "step_submission": "CrossEntropyTrainer(use_cuda_graph=True): one captured CUDA graph per batch shape, replayed (single GPU); eager launches under torchrun",
             "gemm": "tcgen05 kind::tf32 (fp32 storage, fp32 accumulate); GRU recurrences on tcgen05 with weights resident in tensor memory (fp16 operands forward, tf32 backward, fp32 accumulate)",
             "l2_between_iters": "working set per step (>1.6 GB dlogits) exceeds the 126 MB L2"}
 
@@ -167,7 +170,7 @@ def run_b200(args):
     from tests.helpers import build_bahdanau, feed
     distributed.init_from_env()
     rank, world = distributed.rank(), distributed.world_size()
-    model = build_bahdanau(**DIMS, clip=1.0, l2=1e-8, lr=1e-4)
+    model = build_bahdanau(**DIMS, clip=1.0, l2=1e-8, lr=1e-4, cuda_graph=not args.no_cuda_graph)
     trainer = model["trainer"]
     dev = model["arena"].params.device
     batch = args.batch

@@ -268,7 +268,11 @@ int nm_clip_adam_step(float* params, float* grads, float* m, float* v,
                       int64_t n, int64_t nseg, float grad_scale,
                       const float* grad_denominator, float lr_t,
                       float beta1, float beta2, float eps, float clip_norm,
-                      float l1, float l2, float* l1l2_out, void* stream);
+                      float l1, float l2, float* l1l2_out,
+                      const float* lr_t_dev /* optional device scalar that replaces lr_t, so a
+                                               captured CUDA graph of the step can be replayed
+                                               with the schedule's next value */,
+                      void* stream);
 
 /* ---- K8: multi-head scaled dot-product attention core ---------------------------
  * Replaces attention() of attention/scaled_dot_product.py:98-226 between the

@@ -67,7 +67,8 @@ __global__ void __launch_bounds__(OPT_THREADS)
 clip_adam_kernel(float* __restrict__ params, const float* __restrict__ grads, float* __restrict__ m,
                  float* __restrict__ v, const int64_t* __restrict__ seg_off,
                  const float* __restrict__ norms, int64_t n, int64_t nseg, float lr_t, float beta1,
-                 float beta2, float eps, float clip_norm) {
+                 float beta2, float eps, float clip_norm, const float* __restrict__ lr_t_dev) {
+  if (lr_t_dev) lr_t = lr_t_dev[0];
   const int64_t c0 = (int64_t)blockIdx.x * OPT_CHUNK;
   const int64_t c1 = min(n, c0 + OPT_CHUNK);
   int64_t seg = find_segment(seg_off, nseg, c0);
@@ -100,7 +101,7 @@ extern "C" {
 int nm_clip_adam_step(float* params, float* grads, float* m, float* v, const int64_t* seg_off,
                       const uint8_t* seg_reg, float* norms, int64_t n, int64_t nseg, float grad_scale,
                       const float* grad_denominator, float lr_t, float beta1, float beta2, float eps, float clip_norm, float l1,
-                      float l2, float* l1l2_out, void* stream) {
+                      float l2, float* l1l2_out, const float* lr_t_dev, void* stream) {
   NM_REQUIRE(params && grads && m && v && seg_off && seg_reg && norms, NM_E_INVALID,
              "nm_clip_adam_step: null pointer");
   NM_REQUIRE(n > 0 && nseg > 0, NM_E_INVALID, "nm_clip_adam_step: bad sizes");
@@ -117,7 +118,7 @@ int nm_clip_adam_step(float* params, float* grads, float* m, float* v, const int
     NM_LAUNCH_CHECK("nm_clip_adam_step(reg_norm)");
   }
   clip_adam_kernel<<<blocks, OPT_THREADS, 0, s>>>(params, grads, m, v, seg_off, norms, n, nseg, lr_t,
-                                                  beta1, beta2, eps, clip_norm);
+                                                  beta1, beta2, eps, clip_norm, lr_t_dev);
   NM_LAUNCH_CHECK("nm_clip_adam_step(adam)");
   return NM_OK;
 }

@@ -160,6 +160,17 @@ class AutoregressiveDecoder(ModelPart):
         self.batch_size = batch_size
         self._train_ids_host = ids.cpu() if ids is not None else None
 
+    def static_inputs(self) -> Dict[str, Any]:
+        if self._train_ids_host is None:
+            return {}
+        return {"targets": self._train_targets_bm, "fed_symbols": self._train_step_inputs_bm}
+
+    def bind_static(self, tensors: Dict[str, Any]) -> None:
+        self.reset_batch()
+        if tensors:
+            self.__dict__["_batch_cache"].update({"_train_targets_bm": tensors["targets"],
+                                                  "_train_step_inputs_bm": tensors["fed_symbols"]})
+
     @tensor
     def _train_targets_bm(self) -> torch.Tensor:
         """[batch, time] int64 gold symbols incl. </s> (batch-major: the layout every training

@@ -107,6 +107,14 @@ class ImageNet(ModelPart, SpatialStatefulWithOutput):
         self.batch_size = int(images.shape[0])
         self._images = images.to(runtime.device(), non_blocking=True)
 
+    def static_inputs(self) -> Dict[str, Any]:
+        return {"images": self._images} if self._images is not None else {}
+
+    def bind_static(self, tensors: Dict[str, Any]) -> None:
+        self.reset_batch()
+        if tensors:
+            self._images = tensors["images"]
+
     @tensor
     def input_image(self) -> torch.Tensor:
         return self._images

@@ -35,5 +35,15 @@ class Feedable:
     def dataset(self) -> Dict[str, Any]:
         return self._inputs
 
+    # -- CUDA-graph support (trainers/generic_trainer.py) ------------------------------------------
+    def static_inputs(self) -> Dict[str, Any]:
+        """Device tensors this part received from the feed stage (its graph leaves): everything
+        else it exposes is computed from them.  Default: none."""
+        return {}
+
+    def bind_static(self, tensors: Dict[str, Any]) -> None:
+        """Drop every per-batch cache and read the leaves from `tensors` (same keys) instead."""
+        self.reset_batch()
+
     def register_input(self, dataset: Dict[str, Any]) -> None:
         """Kept for API compatibility (experiment.py:152-174): inputs are fed per batch."""

@@ -101,6 +101,13 @@ class EmbeddedFactorSequence(Sequence):
         dev = runtime.device()
         self._ids = [i.to(dev, non_blocking=True) if not i.is_cuda else i for i in ids]
 
+    def static_inputs(self) -> Dict[str, Any]:
+        return {"ids{}".format(i): t for i, t in enumerate(self._ids)}
+
+    def bind_static(self, tensors: Dict[str, Any]) -> None:
+        self.reset_batch()
+        self._ids = [tensors["ids{}".format(i)] for i in range(len(self._ids))]
+
     @tensor
     def input_factor_indices(self) -> List[torch.Tensor]:
         return self._ids

@@ -15,7 +15,8 @@ class CrossEntropyTrainer(GenericTrainer):
     # pylint: disable=too-many-arguments
     def __init__(self, decoders: List[Any], decoder_weights: List[ObjectiveWeight] = None,
                  l1_weight: float = 0., l2_weight: float = 0., clip_norm: float = None,
-                 optimizer=None, var_scopes: List[str] = None, var_collection: str = None) -> None:
+                 optimizer=None, var_scopes: List[str] = None, var_collection: str = None,
+                 use_cuda_graph: bool = False) -> None:
         if decoder_weights is None:
             decoder_weights = [None for _ in decoders]
         if len(decoder_weights) != len(decoders):
@@ -24,4 +25,5 @@ class CrossEntropyTrainer(GenericTrainer):
         objectives = [CostObjective(dec, w) for dec, w in zip(decoders, decoder_weights)]
         GenericTrainer.__init__(self, objectives=objectives, l1_weight=l1_weight,
                                 l2_weight=l2_weight, clip_norm=clip_norm, optimizer=optimizer,
-                                var_scopes=var_scopes, var_collection=var_collection)
+                                var_scopes=var_scopes, var_collection=var_collection,
+                                use_cuda_graph=use_cuda_graph)

@@ -31,8 +31,14 @@ class GenericTrainer(GraphExecutor, Feedable):
     # pylint: disable=too-many-arguments
     def __init__(self, objectives: Sequence[Objective], l1_weight: float = 0.0,
                  l2_weight: float = 0.0, clip_norm: float = None, optimizer=None,
-                 var_scopes: List[str] = None, var_collection: str = None) -> None:
+                 var_scopes: List[str] = None, var_collection: str = None,
+                 use_cuda_graph: bool = False) -> None:
         GraphExecutor.__init__(self, {obj.decoder for obj in objectives})
+        # Capture zero-grad + forward + backward + clip/Adam of a batch shape once and replay it:
+        # a step is ~700 kernel launches, i.e. ~7 ms of Python/driver time per step (`bench.py`
+        # reports it as host_enqueue_ms_per_step) next to ~8 ms of GPU time.  Single GPU only.
+        self.use_cuda_graph = use_cuda_graph
+        self._graphs = {}   # shape key -> "seen" | captured step
         Feedable.__init__(self)
         self.objectives = objectives
         self.l1_weight = l1_weight
@@ -80,10 +86,67 @@ class GenericTrainer(GraphExecutor, Feedable):
         total.backward()
         return {"exact": False}
 
+    # -- CUDA-graph replay of a whole step -------------------------------------------------------
+    def _leaf_parts(self):
+        return sorted((p for p in self.feedables if p is not self and hasattr(p, "static_inputs")),
+                      key=lambda p: getattr(p, "name", type(p).__name__))
+
+    def _graphed_step(self) -> Optional[Dict[str, Any]]:
+        arena = runtime.arena()
+        parts = self._leaf_parts()
+        leaves = [(p, p.static_inputs()) for p in parts]
+        key = tuple((getattr(p, "name", ""), k, tuple(t.shape), str(t.dtype), bool(p.train_mode), p.batch_size)
+                    for p, d in leaves for k, t in sorted(d.items()))
+        entry = self._graphs.get(key)
+        if entry is None:
+            self._graphs[key] = "seen"       # first batch of this shape: eager (it is the warm-up)
+            return None
+        if entry == "failed":
+            return None
+        opt = self.optimizer
+        if entry == "seen":
+            if not hasattr(self, "_lr_dev"):
+                self._lr_dev = torch.zeros(1, device=arena.params.device, dtype=torch.float32)
+            static = [{k: t.clone() for k, t in d.items()} for _, d in leaves]
+            try:
+                torch.cuda.synchronize()
+                graph = torch.cuda.CUDAGraph()
+                for p, st in zip(parts, static):
+                    p.bind_static(st)
+                with torch.cuda.graph(graph):
+                    arena.zero_grad()
+                    self._backward()
+                    self._adam_kernel(1.0, arena.stats[1:2], 0.0, self._lr_dev)
+            except Exception as exc:  # pylint: disable=broad-except
+                warn("CUDA-graph capture of the training step failed ({}: {}); staying eager".format(
+                    type(exc).__name__, exc))
+                self._graphs[key] = "failed"
+                for p in parts:
+                    p.reset_batch()
+                return None
+            entry = self._graphs[key] = (graph, static)
+        graph, static = entry
+        for (_, d), st in zip(leaves, static):
+            for k, t in d.items():
+                if st[k] is not t:
+                    st[k].copy_(t)
+        self.global_step += 1
+        t = self.global_step
+        lr = opt.lr_at(t - 1)
+        self._lr_dev.fill_(lr * math.sqrt(1.0 - opt.beta2 ** t) / (1.0 - opt.beta1 ** t))
+        graph.replay()
+        return {"losses": [arena.stats[0] / arena.stats[1]], "l1l2": self._l1l2}
+
     def train_step(self, apply_update: bool = True, grad_scale: float = 1.0,
                    zero_grad: bool = True) -> Dict[str, Any]:
         """Run one step on the batch currently fed to the model parts (train mode)."""
         arena = runtime.arena()
+        if (self.use_cuda_graph and apply_update and zero_grad and grad_scale == 1.0
+                and distributed.world_size() == 1 and arena.params.is_cuda
+                and len(self.objectives) == 1 and hasattr(type(self.objectives[0].decoder), "train_xent_sum")):
+            out = self._graphed_step()
+            if out is not None:
+                return out
         if zero_grad:
             arena.zero_grad()
         info = self._backward()
@@ -111,6 +174,12 @@ class GenericTrainer(GraphExecutor, Feedable):
         t = self.global_step
         lr = opt.lr_at(t - 1)  # schedules read the global step before its increment
         lr_t = lr * math.sqrt(1.0 - opt.beta2 ** t) / (1.0 - opt.beta1 ** t)
+        self._adam_kernel(grad_scale, denominator, lr_t, None)
+
+    def _adam_kernel(self, grad_scale: float, denominator: Optional[torch.Tensor], lr_t: float,
+                     lr_t_dev: Optional[torch.Tensor]) -> None:
+        arena = runtime.arena()
+        opt = self.optimizer
         if not hasattr(self, "_l1l2_buf"):
             self._l1l2_buf = torch.zeros(2, device=arena.params.device, dtype=torch.float32)
         n = arena.trainable_size
@@ -119,7 +188,7 @@ class GenericTrainer(GraphExecutor, Feedable):
              len(arena.train_names), float(grad_scale), ptr(denominator), float(lr_t),
              float(opt.beta1), float(opt.beta2), float(opt.epsilon),
              float(self.clip_norm) if self.clip_norm else 0.0, float(self.l1_weight),
-             float(self.l2_weight), ptr(self._l1l2_buf), lib.stream())
+             float(self.l2_weight), ptr(self._l1l2_buf), ptr(lr_t_dev), lib.stream())
 
     @property
     def _l1l2(self) -> torch.Tensor:

@@ -59,6 +59,6 @@ class CostObjective(Objective):
     @property
     def loss_sum_and_count(self):
         dec = self.decoder
-        if hasattr(dec, "train_xent_sum") and hasattr(dec, "_train_mask_bm"):
+        if hasattr(type(dec), "train_xent_sum") and hasattr(type(dec), "_train_mask_bm"):
             return dec.train_xent_sum, dec._train_mask_bm.sum()
         return None

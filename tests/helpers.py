@@ -8,7 +8,7 @@ from oracle import nm_oracle as O
 
 
 def build_bahdanau(vs=60, vt=70, es=11, he=7, et=9, hd=8, out=9, maxout=True, max_len=10,
-                   supress_unk=True, l1=0.0, l2=0.0, clip=None, lr=1e-4):
+                   supress_unk=True, l1=0.0, l2=0.0, clip=None, lr=1e-4, cuda_graph=False):
     """Encoder + attention + decoder + trainer of tests/bahdanau.ini's shape family."""
     from neuralmonkey_b200 import runtime
     from neuralmonkey_b200.attention import Attention
@@ -30,7 +30,7 @@ def build_bahdanau(vs=60, vt=70, es=11, he=7, et=9, hd=8, out=9, maxout=True, ma
                   output_projection=maxout_output(out) if maxout else None,
                   supress_unk=supress_unk)
     trainer = CrossEntropyTrainer(decoders=[dec], l1_weight=l1, l2_weight=l2, clip_norm=clip,
-                                  optimizer=tf.AdamOptimizer(learning_rate=lr))
+                                  optimizer=tf.AdamOptimizer(learning_rate=lr), use_cuda_graph=cuda_graph)
     for part in trainer.parameterizeds:
         part.ensure_declared()
     runtime.arena().finalize(runtime.device())
@@ -76,7 +76,8 @@ def random_batch(bsz, tx, ty, vs, vt, seed=0, ragged=True):
 def oracle_params_for(model, scale=0.3, seed=7, dtype=torch.float32) -> Dict[str, torch.Tensor]:
     """Random O(scale) parameters with the framework's variable names and shapes."""
     arena = model["arena"]
-    shapes = {n: torch.zeros(arena.variables[n].shape, dtype=dtype) for n in arena.order}
+    # sorted: the declaration order follows the iteration order of a set of model parts
+    shapes = {n: torch.zeros(arena.variables[n].shape, dtype=dtype) for n in sorted(arena.order)}
     return O.randomize(shapes, scale=scale, seed=seed)
 
 

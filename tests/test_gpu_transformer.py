@@ -75,7 +75,7 @@ def test_position_signal_matches_oracle():
 
 
 @pytest.mark.parametrize("backend,tie,tol", [("simt", True, 5e-5), ("simt", False, 5e-5),
-                                             ("auto", True, 2e-2)])
+                                             ("auto", True, 3e-2)])
 def test_train_forward_and_gradients(backend, tie, tol):
     from neuralmonkey_b200 import ops
     try:
