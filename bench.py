@@ -225,18 +225,23 @@ def run_b200(args):
 
     for i in range(args.warmup):
         step_device_inputs(i)
-    launches0 = lib.launch_count()
     with ClockSampler(dev.index or 0) as clocks:
         ms_step, _ = timed(step_device_inputs, args.steps, read_loss=False)
     host_enqueue_ms = host_ms[0]
-    launches = lib.launch_count() - launches0
 
-    # per-entry-point device time inside timed steps (CUDA events around every C-ABI call)
+    # per-entry-point device time (CUDA events around every C-ABI call) and the kernel count of a
+    # step: these steps issue every launch from Python - a replayed graph contains the same kernel
+    # nodes but does not pass through the library's launch counter
+    graphed = trainer.use_cuda_graph
+    trainer.use_cuda_graph = False
+    launches0 = lib.launch_count()
     lib.profile_start()
     prof_steps = min(args.steps, 5)
     for i in range(prof_steps):
         step_device_inputs(i)
     prof = lib.profile_stop()
+    launches = (lib.launch_count() - launches0) // prof_steps * args.steps
+    trainer.use_cuda_graph = graphed
 
     def step_e2e(i):
         src, tgt = pinned[i % len(pinned)]
@@ -337,7 +342,11 @@ def run_b200(args):
             "data": "synthetic", "config": workload_config(world, batch),
             "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e,
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4, "last_loss": loss},
-            "gpu_launches": launches, "clocks": clocks.summary(), "roofline": roof,
+            "gpu_launches": launches,
+            "gpu_launches_note": "kernels of libnmb200 per step x timed steps, counted by nm_launch_count() over "
+                                 "eagerly issued steps" + (" (the timed steps replay the same kernels as one "
+                                                           "captured CUDA graph per step)" if graphed else ""),
+            "clocks": clocks.summary(), "roofline": roof,
             "cpu_baseline": cpu,
             "breakdown_ms_per_step": {n: round(t, 4) for n, t, _ in table[:16]},
             "host_enqueue_ms_per_step": host_enqueue_ms,

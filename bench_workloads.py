@@ -54,7 +54,7 @@ def build_transformer(vocab=32000, dim=512, ff=2048, depth=6, heads=8, max_len=6
     dec = TransformerDecoder(name="decoder", encoders=[enc], vocabulary=tgt_vocab, data_id="target",
                              ff_hidden_size=ff, n_heads_self=heads, n_heads_enc=heads, depth=depth,
                              max_output_len=max_len, embedding_size=dim, tie_embeddings=tie)
-    trainer = CrossEntropyTrainer(decoders=[dec], optimizer=tf.AdamOptimizer(learning_rate=lr))
+    trainer = CrossEntropyTrainer(decoders=[dec], optimizer=tf.AdamOptimizer(learning_rate=lr), use_cuda_graph=True)
     for part in trainer.parameterizeds:
         part.ensure_declared()
     runtime.arena().finalize(runtime.device())
@@ -164,7 +164,7 @@ def run_captioning(steps=3, warmup=2, bsz=32, vt=10000, ty=16):
     att = Attention(name="attention", encoder=enc, state_size=512)
     dec = Decoder(encoders=[enc], vocabulary=vocab, data_id="target", name="decoder", max_output_len=ty,
                   rnn_size=512, embedding_size=512, attentions=[att])
-    trainer = CrossEntropyTrainer(decoders=[dec], optimizer=tf.AdamOptimizer(learning_rate=1e-4))
+    trainer = CrossEntropyTrainer(decoders=[dec], optimizer=tf.AdamOptimizer(learning_rate=1e-4), use_cuda_graph=True)
     for part in trainer.parameterizeds:
         part.ensure_declared()
     runtime.arena().finalize(runtime.device())

@@ -232,6 +232,65 @@ bahdanau_bwd_keys_kernel(const float* __restrict__ keys, const float* __restrict
   }
 }
 
+// Register variant of the keys kernel for NQ <= NQMAX: the NQ query projections and the NQ
+// dqproj accumulators of this thread's column live in registers, so the inner loop is one
+// broadcast shared-memory load (de), one MUFU.TANH and four FMAs per (t, q) - no read-modify-write
+// of shared memory.  dynamic smem: des[NQ][Tx] only.
+template <int NQMAX>
+__global__ void __launch_bounds__(ATT_ACH)
+bahdanau_bwd_keys_reg_kernel(const float* __restrict__ keys, const float* __restrict__ qproj,
+                             const float* __restrict__ v, const float* __restrict__ de,
+                             float* __restrict__ dkeys, float* __restrict__ dqproj,
+                             float* __restrict__ dv, int Tx, int NQ, int A) {
+  extern __shared__ float smem[];
+  float* des = smem;                 // [Tx][NQMAX]: q contiguous for vector broadcast loads
+  const int b = blockIdx.y;
+  const int a = blockIdx.x * ATT_ACH + threadIdx.x;
+  const bool ok = a < A;
+  for (int i = threadIdx.x; i < Tx * NQMAX; i += ATT_ACH) {
+    const int t = i / NQMAX, q = i - t * NQMAX;
+    des[i] = q < NQ ? de[((int64_t)b * NQ + q) * Tx + t] : 0.f;
+  }
+  float qp[NQMAX], dq[NQMAX];
+#pragma unroll
+  for (int q = 0; q < NQMAX; ++q) {
+    qp[q] = (ok && q < NQ) ? qproj[((int64_t)b * NQ + q) * A + a] : 0.f;
+    dq[q] = 0.f;
+  }
+  __syncthreads();
+  if (!ok) return;
+  const float va = v[a];
+  float dv_acc = 0.f;
+  const float* kp = keys + (int64_t)b * Tx * A + a;
+  float* dkp = dkeys + (int64_t)b * Tx * A + a;
+  float k_next = kp[0];
+  for (int t = 0; t < Tx; ++t) {
+    const float k = k_next;
+    if (t + 1 < Tx) k_next = kp[(int64_t)(t + 1) * A];
+    const float4* d4 = reinterpret_cast<const float4*>(des + t * NQMAX);
+    float dk = 0.f;
+#pragma unroll
+    for (int q4 = 0; q4 < NQMAX / 4; ++q4) {
+      const float4 d = d4[q4];
+      const float dd[4] = {d.x, d.y, d.z, d.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int q = 4 * q4 + j;
+        const float th = fast_tanh(k + qp[q]);
+        const float g = dd[j] * (va - va * th * th);   // zero for the padded q (de = 0)
+        dk += g;
+        dq[q] += g;
+        dv_acc = fmaf(dd[j], th, dv_acc);
+      }
+    }
+    dkp[(int64_t)t * A] = dk;
+  }
+#pragma unroll
+  for (int q = 0; q < NQMAX; ++q)
+    if (q < NQ) dqproj[((int64_t)b * NQ + q) * A + a] = dq[q];
+  atomicAdd(dv + a, dv_acc);
+}
+
 // Backward C: dvalues[b,t,c] = sum_q w[b,q,t] * dctx[b,q,c].  grid (ceil(C/128), B).
 // dynamic smem: ws[NQ][Tx] | dcs[NQ][128]
 __global__ void __launch_bounds__(ATT_ACH)
@@ -311,6 +370,10 @@ int nm_bahdanau_bwd(const float* keys, const float* values, const float* mask, c
                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ATT_SMEM_LIMIT));
     NM_CUDA_TRY(cudaFuncSetAttribute(bahdanau_bwd_values_kernel,
                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ATT_SMEM_LIMIT));
+    NM_CUDA_TRY(cudaFuncSetAttribute(bahdanau_bwd_keys_reg_kernel<32>,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+    NM_CUDA_TRY(cudaFuncSetAttribute(bahdanau_bwd_keys_reg_kernel<64>,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
     attr_set = true;
   }
   dim3 grid_a((unsigned)ceil_div(NQ, ATT_QCH), (unsigned)B);
@@ -318,8 +381,17 @@ int nm_bahdanau_bwd(const float* keys, const float* values, const float* mask, c
                                                                 de_work, dbias, (int)Tx, (int)NQ, (int)C);
   NM_LAUNCH_CHECK("nm_bahdanau_bwd(energy)");
   dim3 grid_b((unsigned)ceil_div(A, ATT_ACH), (unsigned)B);
-  bahdanau_bwd_keys_kernel<<<grid_b, ATT_ACH, smem_b, s>>>(keys, qproj, v, de_work, dkeys, dqproj, dv,
-                                                          (int)Tx, (int)NQ, (int)A);
+  if (NQ <= 64 && sizeof(float) * Tx * 64 <= 96 * 1024) {
+    if (NQ <= 32)
+      bahdanau_bwd_keys_reg_kernel<32><<<grid_b, ATT_ACH, sizeof(float) * Tx * 32, s>>>(
+          keys, qproj, v, de_work, dkeys, dqproj, dv, (int)Tx, (int)NQ, (int)A);
+    else
+      bahdanau_bwd_keys_reg_kernel<64><<<grid_b, ATT_ACH, sizeof(float) * Tx * 64, s>>>(
+          keys, qproj, v, de_work, dkeys, dqproj, dv, (int)Tx, (int)NQ, (int)A);
+  } else {
+    bahdanau_bwd_keys_kernel<<<grid_b, ATT_ACH, smem_b, s>>>(keys, qproj, v, de_work, dkeys, dqproj, dv,
+                                                            (int)Tx, (int)NQ, (int)A);
+  }
   NM_LAUNCH_CHECK("nm_bahdanau_bwd(keys)");
   dim3 grid_c((unsigned)ceil_div(C, ATT_ACH), (unsigned)B);
   bahdanau_bwd_values_kernel<<<grid_c, ATT_ACH, smem_c, s>>>(weights, dctx, dvalues, (int)Tx, (int)NQ,

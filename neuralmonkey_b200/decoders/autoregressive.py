@@ -177,7 +177,7 @@ class AutoregressiveDecoder(ModelPart):
         kernel works in; the reference's time-major `train_inputs` is a view of it)."""
         if self._train_ids_host is None:
             raise ValueError("Decoder '{}' has no reference series fed".format(self.name))
-        return self._train_ids_host.contiguous().to(runtime.device(), non_blocking=True)
+        return runtime.to_device(self._train_ids_host.contiguous())
 
     @tensor
     def _train_mask_bm(self) -> torch.Tensor:
@@ -205,7 +205,7 @@ class AutoregressiveDecoder(ModelPart):
             nxt = gold[:, s] * (~finished)
             finished |= (nxt == END_TOKEN_INDEX)
             fed[:, s + 1] = nxt
-        return torch.from_numpy(fed).to(runtime.device(), non_blocking=True)
+        return runtime.to_device(torch.from_numpy(fed))
 
     def embed_input_symbols(self, input_symbols: torch.Tensor) -> torch.Tensor:
         embedded = ops.embed(input_symbols, self.embedding_matrix)

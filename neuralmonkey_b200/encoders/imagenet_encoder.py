@@ -105,7 +105,7 @@ class ImageNet(ModelPart, SpatialStatefulWithOutput):
         self.reset_batch()
         self.train_mode = bool(train)
         self.batch_size = int(images.shape[0])
-        self._images = images.to(runtime.device(), non_blocking=True)
+        self._images = runtime.to_device(images)
 
     def static_inputs(self) -> Dict[str, Any]:
         return {"images": self._images} if self._images is not None else {}

@@ -99,7 +99,7 @@ class EmbeddedFactorSequence(Sequence):
 
     def _set_ids(self, ids: List[torch.Tensor]) -> None:
         dev = runtime.device()
-        self._ids = [i.to(dev, non_blocking=True) if not i.is_cuda else i for i in ids]
+        self._ids = [runtime.to_device(i) for i in ids]
 
     def static_inputs(self) -> Dict[str, Any]:
         return {"ids{}".format(i): t for i, t in enumerate(self._ids)}

@@ -35,3 +35,15 @@ def reset() -> None:
     """Start a fresh experiment (new arena)."""
     global _arena
     _arena = None
+
+
+def to_device(host: torch.Tensor) -> torch.Tensor:
+    """Host tensor -> device without stalling the host.  A copy from pageable memory waits for
+    everything queued on the stream before it (the next step's feed would serialise with the
+    previous step's kernels); staging through the pinned-memory allocator keeps it asynchronous."""
+    dev = device()
+    if host.is_cuda or dev.type != "cuda":
+        return host.to(dev)
+    if not host.is_pinned():
+        host = host.contiguous().pin_memory()
+    return host.to(dev, non_blocking=True)
