@@ -61,7 +61,7 @@ def workload_config(n_gpus, batch):
             "per_gpu_batch": batch, "global_batch": batch * n_gpus, "src_len": TX, "tgt_len": TY,
             "vocab": DIMS["vt"], "emb": 300, "rnn": 300, "optimizer": "Adam 1e-4, clip 1.0 per tensor, l2 1e-8",
             "lengths": "fixed (no padding)", "parallelism": "dp{}".format(n_gpus),
-            "step_submission": "CrossEntropyTrainer(use_cuda_graph=True): one captured CUDA graph per batch shape, replayed (single GPU); eager launches under torchrun",
+            "step_submission": "CrossEntropyTrainer(use_cuda_graph=True): the step is captured once per batch shape and replayed (N>1: backward graph, NCCL all-reduce, clip+Adam graph)",
             "gemm": "tcgen05 kind::tf32 (fp32 storage, fp32 accumulate); GRU recurrences on tcgen05 with weights resident in tensor memory (fp16 operands forward, tf32 backward, fp32 accumulate)",
             "l2_between_iters": "working set per step (>1.6 GB dlogits) exceeds the 126 MB L2"}
 
@@ -111,7 +111,7 @@ def run_reference(args):
                              "sample": sample,
                              "note": "restated-reference CPU baseline (TF 1.12 unavailable on this box)"},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+    emit(line)
 
 
 # ---------------------------------------------------------------------------
@@ -351,10 +351,29 @@ def run_b200(args):
             "breakdown_ms_per_step": {n: round(t, 4) for n, t, _ in table[:16]},
             "host_enqueue_ms_per_step": host_enqueue_ms,
             "extra_workloads": extras}
-    print(json.dumps(line))
+    emit(line)
+
+
+_REAL_STDOUT = None
+
+
+def emit(line):
+    """The ONE JSON line, written to the process's original stdout."""
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
 
 
 def main():
+    # Libraries (NCCL prints its version banner) write to file descriptor 1: keep the real stdout
+    # for the JSON line only and send everything else to stderr.
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     args = parse_args()
     if args.impl == "reference":
         run_reference(args)

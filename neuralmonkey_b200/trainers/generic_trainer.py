@@ -36,7 +36,8 @@ class GenericTrainer(GraphExecutor, Feedable):
         GraphExecutor.__init__(self, {obj.decoder for obj in objectives})
         # Capture zero-grad + forward + backward + clip/Adam of a batch shape once and replay it:
         # a step is ~700 kernel launches, i.e. ~7 ms of Python/driver time per step (`bench.py`
-        # reports it as host_enqueue_ms_per_step) next to ~8 ms of GPU time.  Single GPU only.
+        # reports it as host_enqueue_ms_per_step) next to ~8 ms of GPU time.  Data parallel: two graphs
+        # with the NCCL all-reduce between them.
         self.use_cuda_graph = use_cuda_graph
         self._graphs = {}   # shape key -> "seen" | captured step
         Feedable.__init__(self)
@@ -113,10 +114,21 @@ class GenericTrainer(GraphExecutor, Feedable):
                 graph = torch.cuda.CUDAGraph()
                 for p, st in zip(parts, static):
                     p.bind_static(st)
-                with torch.cuda.graph(graph):
-                    arena.zero_grad()
-                    self._backward()
-                    self._adam_kernel(1.0, arena.stats[1:2], 0.0, self._lr_dev)
+                graph2 = None
+                if distributed.world_size() > 1:
+                    # data parallel: the gradient exchange stays an eager NCCL call between two
+                    # captured halves (backward | clip + Adam)
+                    with torch.cuda.graph(graph):
+                        arena.zero_grad()
+                        self._backward()
+                    graph2 = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(graph2, pool=graph.pool()):
+                        self._adam_kernel(1.0, arena.stats[1:2], 0.0, self._lr_dev)
+                else:
+                    with torch.cuda.graph(graph):
+                        arena.zero_grad()
+                        self._backward()
+                        self._adam_kernel(1.0, arena.stats[1:2], 0.0, self._lr_dev)
             except Exception as exc:  # pylint: disable=broad-except
                 warn("CUDA-graph capture of the training step failed ({}: {}); staying eager".format(
                     type(exc).__name__, exc))
@@ -124,8 +136,8 @@ class GenericTrainer(GraphExecutor, Feedable):
                 for p in parts:
                     p.reset_batch()
                 return None
-            entry = self._graphs[key] = (graph, static)
-        graph, static = entry
+            entry = self._graphs[key] = (graph, static, graph2)
+        graph, static, graph2 = entry
         for (_, d), st in zip(leaves, static):
             for k, t in d.items():
                 if st[k] is not t:
@@ -135,6 +147,9 @@ class GenericTrainer(GraphExecutor, Feedable):
         lr = opt.lr_at(t - 1)
         self._lr_dev.fill_(lr * math.sqrt(1.0 - opt.beta2 ** t) / (1.0 - opt.beta1 ** t))
         graph.replay()
+        if graph2 is not None:
+            distributed.all_reduce_sum(arena.allreduce_view)
+            graph2.replay()
         return {"losses": [arena.stats[0] / arena.stats[1]], "l1l2": self._l1l2}
 
     def train_step(self, apply_update: bool = True, grad_scale: float = 1.0,
@@ -142,7 +157,7 @@ class GenericTrainer(GraphExecutor, Feedable):
         """Run one step on the batch currently fed to the model parts (train mode)."""
         arena = runtime.arena()
         if (self.use_cuda_graph and apply_update and zero_grad and grad_scale == 1.0
-                and distributed.world_size() == 1 and arena.params.is_cuda
+                and arena.params.is_cuda
                 and len(self.objectives) == 1 and hasattr(type(self.objectives[0].decoder), "train_xent_sum")):
             out = self._graphed_step()
             if out is not None:
