@@ -202,11 +202,46 @@ __device__ __forceinline__ void epilogue_chunk(const TcEpilogue& e, float (&x)[3
 }
 
 // split-K partial tile: C += x (+ bias once, from split 0); no activation.
+__device__ __forceinline__ void red_add_v4(float* addr, const float4& v) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(v.x), "f"(v.y), "f"(v.z),
+               "f"(v.w)
+               : "memory");
+}
+
 __device__ __forceinline__ void epilogue_chunk_atomic(const TcEpilogue& e, const float (&x)[32],
                                                       int64_t row, int col0, int64_t M, int N,
-                                                      bool add_bias) {
-  if (row >= M || col0 >= N) return;
+                                                      bool add_bias, bool vec_ok,
+                                                      float* __restrict__ stage, int lane) {
+  if (col0 >= N) return;                                   // warp-uniform
   const int ncols = min(32, N - col0);
+  if (vec_ok && ncols == 32) {
+    // same transposition as store32_coalesced: one vector reduction covers 16 bytes of a row
+    // and a warp instruction four full 128-byte row segments, instead of 32 scalar atomics
+    // scattered over 32 rows
+    float4* st4 = reinterpret_cast<float4*>(stage);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float4 v = make_float4(x[4 * j], x[4 * j + 1], x[4 * j + 2], x[4 * j + 3]);
+      if (add_bias && e.bias) {
+        const float4 b = __ldg(reinterpret_cast<const float4*>(e.bias + col0 + 4 * j));
+        v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
+      }
+      st4[lane * 8 + (j ^ (lane & 7))] = v;
+    }
+    __syncwarp();
+    const int sub = lane >> 3, slot = lane & 7;
+    const int64_t row_base = row - lane;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int r = 4 * i + sub;
+      const float4 v = st4[r * 8 + (slot ^ (r & 7))];
+      const int64_t grow = row_base + r;
+      if (grow < M) red_add_v4(e.C + grow * e.ldc + col0 + 4 * slot, v);
+    }
+    __syncwarp();
+    return;
+  }
+  if (row >= M) return;
   float* c = e.C + row * e.ldc + col0;
 #pragma unroll
   for (int j = 0; j < 32; ++j)
@@ -217,9 +252,6 @@ __device__ __forceinline__ void epilogue_chunk_atomic(const TcEpilogue& e, const
     }
 }
 
-// ---------------------------------------------------------------------------
-// the kernel
-// ---------------------------------------------------------------------------
 // smem descriptor fields of an MN-major operand tile (bytes); a kernel argument so a
 // diagnostic run can probe them (NMB200_MN_* environment variables), fixed otherwise.
 struct MnDesc {
@@ -391,7 +423,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         float v[32];
         tmem_ld32(t_row + (uint32_t)(c * 32), v);
         if (MODE == TC_EPI_DENSE && splits > 1)
-          epilogue_chunk_atomic(epi, v, row, (int)(tn * BN) + c * 32, M, n32, split == 0);
+          epilogue_chunk_atomic(epi, v, row, (int)(tn * BN) + c * 32, M, n32, split == 0,
+                                vec_ok && ((reinterpret_cast<uintptr_t>(epi.bias) & 15) == 0), stage, lane);
         else
           epilogue_chunk<MODE>(epi, v, row, (int)(tn * BN) + c * 32, M, n32, st, target, row_lse2,
                                row_w, vec_ok, stage, lane);
