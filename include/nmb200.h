@@ -298,6 +298,12 @@ int nm_mha_bwd(const float* q, const float* k, const float* v,
 int nm_conv3x3_bias_relu_fwd(const float* x, const float* w, const float* bias,
                              float* y, int64_t N, int64_t H, int64_t W,
                              int64_t Cin, int64_t Cout, void* stream);
+/* Patch matrix of the same convolution for the tensor-core path (the conv is then nm_gemm with
+ * the bias+ReLU epilogue; output rows are NHWC pixels): cols[(n,y,x)][tap*Cin + c], row pitch ldc
+ * floats (>= 9*Cin; a multiple of 4 keeps the rows TMA-addressable), zeros outside the image.
+ * Same layer as above: slim vgg_arg_scope conv2d (encoders/imagenet_encoder.py:52-68). */
+int nm_im2col3x3(const float* x, float* cols, int64_t N, int64_t H, int64_t W,
+                 int64_t Cin, int64_t ldc, void* stream);
 /* 2x2 / stride 2 max pool, NHWC (H, W even). */
 int nm_maxpool2x2_fwd(const float* x, float* y, int64_t N, int64_t H, int64_t W,
                       int64_t C, void* stream);

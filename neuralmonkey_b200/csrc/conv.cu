@@ -82,6 +82,34 @@ conv3x3_kernel(const float* __restrict__ x, const float* __restrict__ w, const f
   }
 }
 
+// im2col for the tensor-core path: cols[m][tap*Cin + c] = x[n, y+dy, x+dx, c] (zero outside the
+// image), row pitch `ldc` floats.  One thread per (pixel, tap, 4-channel group).
+__global__ void im2col3x3_kernel(const float* __restrict__ x, float* __restrict__ cols, int64_t NB, int H,
+                                 int W, int Cin, int64_t ldc) {
+  const int groups = (Cin + 3) / 4;
+  const int64_t total = NB * H * W * 9 * groups;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int g = (int)(i % groups);
+    int64_t r = i / groups;
+    const int tap = (int)(r % 9);
+    const int64_t m = r / 9;
+    const int xx0 = (int)(m % W);
+    const int yy0 = (int)((m / W) % H);
+    const int64_t n = m / ((int64_t)W * H);
+    const int yy = yy0 + tap / 3 - 1, xx = xx0 + tap % 3 - 1;
+    const bool inside = yy >= 0 && yy < H && xx >= 0 && xx < W;
+    const float* src = x + ((n * H + yy) * W + xx) * Cin + 4 * g;
+    float* dst = cols + m * ldc + tap * Cin + 4 * g;
+    if ((Cin & 3) == 0) {
+      const float4 v = inside ? *reinterpret_cast<const float4*>(src) : make_float4(0.f, 0.f, 0.f, 0.f);
+      *reinterpret_cast<float4*>(dst) = v;
+    } else {
+      for (int c = 0; c < 4 && 4 * g + c < Cin; ++c) dst[c] = inside ? src[c] : 0.f;
+    }
+  }
+}
+
 __global__ void maxpool2x2_kernel(const float* __restrict__ x, float* __restrict__ y, int64_t NB, int H,
                                   int W, int C) {
   const int Ho = H / 2, Wo = W / 2;
@@ -131,6 +159,20 @@ int nm_conv3x3_bias_relu_fwd(const float* x, const float* w, const float* bias, 
   conv3x3_kernel<<<grid, SIMT_THREADS, 0, (cudaStream_t)stream>>>(x, w, bias, y, N, (int)H, (int)W,
                                                                   (int)Cin, (int)Cout);
   NM_LAUNCH_CHECK("nm_conv3x3_bias_relu_fwd");
+  return NM_OK;
+}
+
+int nm_im2col3x3(const float* x, float* cols, int64_t N, int64_t H, int64_t W, int64_t Cin,
+                 int64_t ldc, void* stream) {
+  NM_REQUIRE(x && cols, NM_E_INVALID, "nm_im2col3x3: null pointer");
+  NM_REQUIRE(N > 0 && H > 0 && W > 0 && Cin > 0 && ldc >= 9 * Cin, NM_E_INVALID, "nm_im2col3x3: bad sizes");
+  const int64_t total = N * H * W * 9 * ((Cin + 3) / 4);
+  int64_t blocks = ceil_div(total, 256);
+  const int64_t cap = (int64_t)sm_count() * 16;
+  if (blocks > cap) blocks = cap;
+  im2col3x3_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(x, cols, N, (int)H, (int)W, (int)Cin,
+                                                                      ldc);
+  NM_LAUNCH_CHECK("nm_im2col3x3");
   return NM_OK;
 }
 

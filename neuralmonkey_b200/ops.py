@@ -584,6 +584,22 @@ def conv3x3_bias_relu(x: torch.Tensor, w: torch.Tensor, b: torch.Tensor) -> torc
     cout = w.shape[-1]
     x, w, b = _f32(x.detach()).contiguous(), _f32(w.detach()).contiguous(), _f32(b.detach())
     y = torch.empty(n, h, wd, cout, device=x.device, dtype=torch.float32)
+    if _GEMM_BACKEND != lib.GEMM_SIMT and cout % 4 == 0:
+        # tensor-core path: patch matrix (im2col) x filter matrix [9*Cin, Cout] through the tcgen05
+        # GEMM with the bias + ReLU epilogue; the output rows ARE the NHWC pixels.  The patch matrix
+        # is built for a few images at a time so it stays below ~768 MB.
+        k = 9 * cin
+        ld = (k + 3) // 4 * 4
+        per_image = h * wd * ld * 4
+        chunk = max(1, min(n, (768 << 20) // per_image))
+        cols = torch.zeros(chunk * h * wd, ld, device=x.device, dtype=torch.float32)
+        w2 = w.view(k, cout)
+        y2 = y.view(n * h * wd, cout)
+        for n0 in range(0, n, chunk):
+            nb = min(chunk, n - n0)
+            call("nm_im2col3x3", ptr(x[n0:n0 + nb]), ptr(cols), nb, h, wd, cin, ld, lib.stream())
+            gemm(cols[:nb * h * wd, :k], w2, y2[n0 * h * wd:(n0 + nb) * h * wd], bias=b, act="relu")
+        return y
     call("nm_conv3x3_bias_relu_fwd", ptr(x), ptr(w), ptr(b), ptr(y), n, h, wd, cin, cout, lib.stream())
     return y
 

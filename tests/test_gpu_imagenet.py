@@ -43,7 +43,19 @@ def _params(model):
 
 @pytest.mark.parametrize("layer,size", [("vgg_16/conv1/conv1_2", 8), ("vgg_16/pool2", 12),
                                         ("vgg_16/conv5/conv5_3", 32)])
-def test_vgg_stack_matches_oracle(layer, size):
+@pytest.mark.parametrize("backend,rtol", [("simt", 2e-5), ("auto", 5e-3)])
+def test_vgg_stack_matches_oracle(layer, size, backend, rtol):
+    """simt: implicit-GEMM convolution on the CUDA cores (exact fp32); auto: im2col + tcgen05 GEMM
+    with the bias+ReLU epilogue (TF32 operands)."""
+    from neuralmonkey_b200 import ops
+    ops.set_gemm_backend(backend)
+    try:
+        _vgg_check(layer, size, rtol)
+    finally:
+        ops.set_gemm_backend("auto")
+
+
+def _vgg_check(layer, size, rtol):
     model = build_captioning(layer)
     params = _params(model)
     images = torch.randn(2, size, size, 3, generator=torch.Generator().manual_seed(1)) * 50.0
@@ -52,8 +64,8 @@ def test_vgg_stack_matches_oracle(layer, size):
     got = model["enc"].spatial_states
     assert got.shape == want["spatial_states"].shape
     scale = float(want["spatial_states"].abs().max())
-    assert max_abs(got, want["spatial_states"]) < 2e-5 * scale + 1e-6
-    assert max_abs(model["enc"].output, want["output"]) < 2e-5 * scale + 1e-6
+    assert max_abs(got, want["spatial_states"]) < rtol * scale + 1e-6
+    assert max_abs(model["enc"].output, want["output"]) < rtol * scale + 1e-6
     assert float(model["enc"].spatial_mask.min()) == 1.0
 
 
