@@ -102,3 +102,41 @@ def test_beam_search_runner_range_names_and_validation():
     assert [r.output_series for r in runners] == ["target.rank001", "target.rank002"]
     with pytest.raises(ValueError):
         beam_search_runner_range("target", Dec(), max_rank=4)
+
+
+def test_bpe_matches_reference_subword_nmt(tmp_path):
+    """Golden segmentations generated with the reference's vendored subword-nmt
+    (tests/golden/make_bpe_golden.py)."""
+    import json
+    from neuralmonkey_b200.processors.bpe import BPEPostprocessor, BPEPreprocessor
+    golden = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden",
+                                         "bpe_golden.json")))
+    merges = tmp_path / "merges.txt"
+    _write(merges, golden["merges"])
+    pre = BPEPreprocessor(str(merges))
+    for sent, want in zip(golden["sentences"], golden["segmented"]):
+        assert pre(sent) == want
+    post = BPEPostprocessor()
+    assert post([golden["segmented"][0]]) == [golden["sentences"][0]]
+
+
+def test_plugin_names_of_the_reference_configs_are_importable():
+    """Every `class=` path the five named INIs use resolves in this package."""
+    import importlib
+    names = """encoders.recurrent.SentenceEncoder encoders.SentenceEncoder encoders.transformer.TransformerEncoder
+    encoders.imagenet_encoder.ImageNet model.sequence.EmbeddedSequence attention.Attention decoders.decoder.Decoder
+    decoders.Decoder decoders.transformer.TransformerDecoder decoders.output_projection.maxout_output
+    decoders.beam_search_decoder.BeamSearchDecoder trainers.cross_entropy_trainer.CrossEntropyTrainer
+    trainers.cross_entropy_trainer.CostObjective trainers.delayed_update_trainer.DelayedUpdateTrainer
+    trainers.multitask_trainer.MultitaskTrainer runners.GreedyRunner runners.beam_search_runner_range
+    runners.BeamSearchRunner runners.runner.GreedyRunner runners.tensor_runner.TensorRunner
+    runners.tensor_runner.RepresentationRunner tf_manager.TensorFlowManager dataset.load dataset.BatchingScheme
+    vocabulary.from_wordlist functions.noam_decay evaluators.BLEU evaluators.ROUGE_L evaluators.SacreBLEU
+    evaluators.bleu.BLEU1 evaluators.bleu.BLEU4 readers.image_reader.imagenet_reader
+    processors.helpers.preprocess_char_based processors.bpe.BPEPreprocessor processors.bpe.BPEPostprocessor
+    dataset.load_dataset_from_files vocabulary.from_bpe""".split()
+    for name in names:
+        module, attr = name.rsplit(".", 1)
+        assert hasattr(importlib.import_module("neuralmonkey_b200." + module), attr), name
+    from neuralmonkey_b200 import tf
+    assert tf.contrib.opt.LazyAdamOptimizer and tf.train.AdamOptimizer
