@@ -262,7 +262,9 @@ int nm_beam_gather(const void* x, const int32_t* beam_ids, void* out, int64_t B,
  * grad_scale multiplies g first (1/k for delayed updates); grad_denominator (a
  * DEVICE scalar, may be NULL) then divides it: the all-reduced global token count of
  * a data-parallel step, so the host never has to read it back.  l1l2_out [2] (device, may be NULL) receives sum|p|, sum p^2 over
- * regularised tensors (the "L1"/"L2" losses the trainer reports). */
+ * regularised tensors (the "L1"/"L2" losses the trainer reports).  * seg_reg flags per segment: bit 0 = receives the L1/L2 terms (generic_trainer.py:87-91),
+ * bit 1 = lazy (tf.contrib.opt.LazyAdamOptimizer): entries whose gradient is exactly zero keep
+ * their moments and value. */
 int nm_clip_adam_step(float* params, float* grads, float* m, float* v,
                       const int64_t* seg_off, const uint8_t* seg_reg, float* norms,
                       int64_t n, int64_t nseg, float grad_scale,

@@ -36,7 +36,7 @@ reg_norm_kernel(const float* __restrict__ params, float* __restrict__ grads,
   float l1_acc = 0.f, l2_acc = 0.f;
   while (seg < nseg && seg_off[seg] < c1) {
     const int64_t a = max(c0, seg_off[seg]), b = min(c1, seg_off[seg + 1]);
-    const bool reg = seg_reg[seg] != 0;
+    const bool reg = (seg_reg[seg] & 1) != 0;
     float ss = 0.f;
     for (int64_t i = a + threadIdx.x; i < b; i += OPT_THREADS) {
       float g = grads[i] * grad_scale;
@@ -66,6 +66,7 @@ reg_norm_kernel(const float* __restrict__ params, float* __restrict__ grads,
 __global__ void __launch_bounds__(OPT_THREADS)
 clip_adam_kernel(float* __restrict__ params, const float* __restrict__ grads, float* __restrict__ m,
                  float* __restrict__ v, const int64_t* __restrict__ seg_off,
+                 const uint8_t* __restrict__ seg_reg,
                  const float* __restrict__ norms, int64_t n, int64_t nseg, float lr_t, float beta1,
                  float beta2, float eps, float clip_norm, const float* __restrict__ lr_t_dev) {
   if (lr_t_dev) lr_t = lr_t_dev[0];
@@ -80,8 +81,13 @@ clip_adam_kernel(float* __restrict__ params, const float* __restrict__ grads, fl
       const float nrm = sqrtf(norms[seg]);
       scale = clip_norm / fmaxf(nrm, clip_norm);
     }
+    // flag bit 1: tf.contrib.opt.LazyAdamOptimizer semantics for a sparsely updated table -
+    // entries that received no gradient (embedding rows absent from the batch) keep their
+    // moments and value instead of decaying
+    const bool lazy = (seg_reg[seg] & 2) != 0;
     for (int64_t i = a + threadIdx.x; i < b; i += OPT_THREADS) {
       const float g = grads[i] * scale;
+      if (lazy && g == 0.f) continue;
       const float mi = beta1 * m[i] + (1.f - beta1) * g;
       const float vi = beta2 * v[i] + (1.f - beta2) * g * g;
       m[i] = mi;
@@ -117,7 +123,7 @@ int nm_clip_adam_step(float* params, float* grads, float* m, float* v, const int
                                                    grad_scale, grad_denominator, l1, l2, l1l2_out);
     NM_LAUNCH_CHECK("nm_clip_adam_step(reg_norm)");
   }
-  clip_adam_kernel<<<blocks, OPT_THREADS, 0, s>>>(params, grads, m, v, seg_off, norms, n, nseg, lr_t,
+  clip_adam_kernel<<<blocks, OPT_THREADS, 0, s>>>(params, grads, m, v, seg_off, seg_reg, norms, n, nseg, lr_t,
                                                   beta1, beta2, eps, clip_norm, lr_t_dev);
   NM_LAUNCH_CHECK("nm_clip_adam_step(adam)");
   return NM_OK;

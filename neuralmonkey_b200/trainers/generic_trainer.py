@@ -183,8 +183,6 @@ class GenericTrainer(GraphExecutor, Feedable):
                         denominator: Optional[torch.Tensor] = None) -> None:
         arena = runtime.arena()
         opt = self.optimizer
-        if getattr(opt, "lazy", False):
-            warn("LazyAdamOptimizer: using dense Adam updates (rows without gradient also decay)")
         self.global_step += 1
         t = self.global_step
         lr = opt.lr_at(t - 1)  # schedules read the global step before its increment
@@ -198,8 +196,16 @@ class GenericTrainer(GraphExecutor, Feedable):
         if not hasattr(self, "_l1l2_buf"):
             self._l1l2_buf = torch.zeros(2, device=arena.params.device, dtype=torch.float32)
         n = arena.trainable_size
+        seg_flags = arena.seg_reg
+        if getattr(opt, "lazy", False):
+            # LazyAdam: embedding tables are updated only where a gradient arrived (flag bit 1)
+            if not hasattr(self, "_lazy_flags"):
+                lazy = torch.tensor([2 if ("embedding" in name) else 0 for name in arena.train_names] or [0],
+                                    dtype=torch.uint8, device=arena.seg_reg.device)
+                self._lazy_flags = arena.seg_reg | lazy
+            seg_flags = self._lazy_flags
         call("nm_clip_adam_step", ptr(arena.params), ptr(arena.grads), ptr(arena.adam_m),
-             ptr(arena.adam_v), ptr(arena.seg_off), ptr(arena.seg_reg), ptr(arena.seg_norms), n,
+             ptr(arena.adam_v), ptr(arena.seg_off), ptr(seg_flags), ptr(arena.seg_norms), n,
              len(arena.train_names), float(grad_scale), ptr(denominator), float(lr_t),
              float(opt.beta1), float(opt.beta2), float(opt.epsilon),
              float(self.clip_norm) if self.clip_norm else 0.0, float(self.l1_weight),

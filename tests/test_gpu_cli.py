@@ -218,3 +218,136 @@ batching=<batching>
     results = json.load(open(tmp_path / "res.json"))
     assert "target/SacreBLEU" in results[0] and "target/runtime_xent" in results[0]
     assert len(open(os.path.join(out, "run.out")).read().splitlines()) == 30
+
+
+# Modelled on the reference's tests/transformer.ini + tests/beamsearch.ini: EmbeddedSequence +
+# TransformerEncoder/Decoder with dropout, DelayedUpdateTrainer, LazyAdam with the Noam schedule, a
+# char-level preprocessed series, BeamSearchDecoder + beam_search_runner_range, BLEU on rank 1.
+TRANSFORMER_INI = """
+[main]
+name="toy reversal transformer with beam search"
+tf_manager=<tf_manager>
+output="{out}"
+overwrite_output_dir=True
+batch_size=16
+epochs={epochs}
+train_dataset=<train_data>
+val_dataset=<val_data>
+trainer=<trainer>
+runners=<bs_runners>
+postprocess=None
+evaluation=[("target_beam.rank001", "target", evaluators.BLEU)]
+logging_period=10
+validation_period=20
+random_seed=1234
+
+[tf_manager]
+class=tf_manager.TensorFlowManager
+num_threads=4
+num_sessions=1
+save_n_best=2
+
+[train_data]
+class=dataset.load
+series=["source", "target", "source_chars"]
+data=["{data}/train.src", "{data}/train.tgt", (processors.helpers.preprocess_char_based, "source")]
+buffer_size=32
+
+[val_data]
+class=dataset.load
+series=["source", "target", "source_chars"]
+data=["{data}/val.src", "{data}/val.tgt", (processors.helpers.preprocess_char_based, "source")]
+
+[encoder_vocabulary]
+class=vocabulary.from_wordlist
+path="{data}/src_vocab.tsv"
+
+[inpseq]
+class=model.sequence.EmbeddedSequence
+name="input"
+embedding_size=12
+max_length=9
+data_id="source"
+vocabulary=<encoder_vocabulary>
+
+[encoder]
+class=encoders.transformer.TransformerEncoder
+name="transformer_encoder"
+input_sequence=<inpseq>
+ff_hidden_size=20
+depth=2
+n_heads=3
+dropout_keep_prob=0.9
+
+[decoder_vocabulary]
+class=vocabulary.from_wordlist
+path="{data}/tgt_vocab.tsv"
+
+[decoder]
+class=decoders.transformer.TransformerDecoder
+name="decoder"
+encoders=[<encoder>]
+dropout_keep_prob=0.9
+data_id="target"
+max_output_len=9
+vocabulary=<decoder_vocabulary>
+embedding_size=12
+ff_hidden_size=20
+depth=2
+n_heads_self=3
+n_heads_enc=2
+
+[trainer]
+class=trainers.delayed_update_trainer.DelayedUpdateTrainer
+batches_per_update=2
+l2_weight=1.0e-8
+clip_norm=1.0
+objectives=[<obj>]
+optimizer=<lazyadam_g>
+
+[obj]
+class=trainers.cross_entropy_trainer.CostObjective
+decoder=<decoder>
+
+[decayed_lr]
+class=functions.noam_decay
+learning_rate=0.5
+model_dimension=12
+warmup_steps=20
+
+[lazyadam_g]
+class=tf.contrib.opt.LazyAdamOptimizer
+beta1=0.9
+beta2=0.98
+epsilon=1.0e-9
+learning_rate=<decayed_lr>
+
+[bs_decoder]
+class=decoders.beam_search_decoder.BeamSearchDecoder
+name="beam_search_decoder"
+parent_decoder=<decoder>
+length_normalization=0.6
+max_steps=10
+beam_size=3
+
+[bs_runners]
+class=runners.beam_search_runner_range
+output_series="target_beam"
+decoder=<bs_decoder>
+max_rank=2
+"""
+
+
+def test_transformer_beam_search_experiment(tmp_path):
+    data, out = str(tmp_path / "data"), str(tmp_path / "out")
+    _write_data(data)
+    ini = tmp_path / "transformer.ini"
+    ini.write_text(TRANSFORMER_INI.format(out=out, data=data, epochs=4))
+    res = _run(["bin/neuralmonkey-train", str(ini)])
+    assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
+    log_text = open(os.path.join(out, "experiment.log")).read()
+    assert "Validation (epoch" in log_text and "target_beam.rank001/BLEU" in log_text
+    train_lines = [line for line in log_text.splitlines() if " train " in line]
+    assert len(train_lines) >= 3, log_text[-2000:]
+    assert "beam_search_score" in log_text
+    assert os.path.exists(os.path.join(out, "variables.data.best"))

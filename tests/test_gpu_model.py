@@ -161,3 +161,36 @@ def test_cuda_graph_training_step_matches_eager():
             assert max_abs(results[True][1][name], want) < 2e-5, name
     finally:
         ops.set_gemm_backend("auto")
+
+
+def test_lazy_adam_leaves_absent_embedding_rows_untouched():
+    """tf.contrib.opt.LazyAdamOptimizer: after a first step that touched every row, a second step
+    on a batch using few words must not move the rows of the words it does not contain (dense Adam
+    would keep moving them along their first moment)."""
+    from neuralmonkey_b200 import ops, tf
+    try:
+        ops.set_gemm_backend("simt")
+        results = {}
+        for lazy in (True, False):
+            model = build_bahdanau(**TOY, lr=1e-2)
+            opt = tf.contrib.opt.LazyAdamOptimizer(learning_rate=1e-2) if lazy else tf.AdamOptimizer(learning_rate=1e-2)
+            model["trainer"].optimizer = opt
+            model["arena"].load_dict(oracle_params_for(model))
+            bsz = (TOY["vs"] - 4) // 2
+            src = torch.arange(4, TOY["vs"]).view(bsz, 2)                           # every source word
+            tgt = torch.full((bsz, 3), 5)
+            tgt[:, 2] = 2
+            feed(model, src, tgt, train=True)
+            model["trainer"].train_step()
+            before = model["arena"].state_dict()["sentence_encoder_input/embedding_matrix_0"].clone()
+            src2 = torch.full((4, 2), 7)
+            feed(model, src2, tgt[:4], train=True)
+            model["trainer"].train_step()
+            after = model["arena"].state_dict()["sentence_encoder_input/embedding_matrix_0"]
+            results[lazy] = (after - before).abs().sum(dim=1)
+        moved_lazy, moved_dense = results[True], results[False]
+        assert float(moved_lazy[7]) > 0                      # the word in the batch is updated
+        assert float(moved_lazy[20:40].max()) == 0.0         # absent rows: untouched
+        assert float(moved_dense[20:40].min()) > 0.0         # dense Adam keeps moving them
+    finally:
+        ops.set_gemm_backend("auto")
