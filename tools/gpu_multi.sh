@@ -1,5 +1,5 @@
 #!/bin/bash
-# usage: tools_gpu_multi.sh N   (run under gpurun --gpus N)
+# usage: tools/gpu_multi.sh N   (run under gpurun --gpus N)
 N=${1:-2}
 mkdir -p gpurun_out
 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 \

@@ -1,5 +1,5 @@
 #!/bin/bash
-# usage: tools_gpu_run.sh [tests] [bench] [smoke]
+# usage: tools/gpu_run.sh [tests] [bench] [smoke]
 mkdir -p gpurun_out
 for what in "$@"; do
 case $what in

@@ -5,7 +5,7 @@ timeout 300 python -m pytest tests/test_gpu_gemm.py -m gpu -q --no-header -p no:
 echo "exit $?"; tail -n 8 gpurun_out/test_gpu_gemm.log
 if ! grep -q " passed" gpurun_out/test_gpu_gemm.log || grep -q "failed" gpurun_out/test_gpu_gemm.log; then
   echo "=== probing MN-major descriptor space"
-  timeout 900 python tools_mn_probe.py 2>&1 | tee gpurun_out/mn_probe.log
+  timeout 900 python tools/mn_probe.py 2>&1 | tee gpurun_out/mn_probe.log
 fi
 for f in test_gpu_beam test_gpu_ops test_gpu_model; do
   echo "=== $f"

@@ -1,7 +1,7 @@
 """GPU probe: tensor-core GRU vs exact engine (values + timing at the bench shape)."""
 import sys, time
 import torch
-sys.path.insert(0, "/root/repo")
+sys.path.insert(0, __import__("os").path.dirname(__import__("os").path.dirname(__import__("os").path.abspath(__file__))))
 from neuralmonkey_b200 import lib, ops
 
 def run(mode, B, T, E, H, reverse=False, lengths=None, seed=0, bwd=True):

@@ -1,4 +1,4 @@
-"""Summarise gpurun_out/ ncu artefacts into profiles/ (tracked).  Usage: python tools_profile_summary.py r01"""
+"""Summarise gpurun_out/ ncu artefacts into profiles/ (tracked).  Usage: python tools/profile_summary.py r01"""
 import csv, io, subprocess, sys, collections, json, os
 
 tag = sys.argv[1] if len(sys.argv) > 1 else "r01"
