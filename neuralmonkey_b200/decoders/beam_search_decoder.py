@@ -143,6 +143,8 @@ class BeamSearchDecoder(ModelPart):
     # Replay one captured CUDA graph per step when the parent is a Transformer decoder with a KV
     # cache (decoders/beam_graph.py); False falls back to the step-by-step host loop.
     use_cuda_graph = True
+    MAX_GRAPHS = 4        # captured (batch, source length) shapes kept alive
+    GRAPH_AFTER = 2       # a shape is captured the second time it shows up; one-offs use the loop
 
     def _graph_outputs(self, tiled_states, tiled_masks) -> BeamSearchOutput:
         from neuralmonkey_b200.decoders.beam_graph import TransformerBeamGraph
@@ -151,7 +153,11 @@ class BeamSearchDecoder(ModelPart):
         key = (bsz, tuple(tuple(s.shape) for s in tiled_states))
         graphs = self.__dict__.setdefault("_graphs", {})
         if key not in graphs:
+            while len(graphs) >= self.MAX_GRAPHS:          # bounded: each holds its KV buffers
+                graphs.pop(next(iter(graphs)))
             graphs[key] = TransformerBeamGraph(self, bsz, key[1])
+        else:
+            graphs[key] = graphs.pop(key)                  # most recently used last
         res = graphs[key].run(tiled_states, tiled_masks)
         dev = runtime.device()
         feedables = DecoderFeedables(step=res["steps"] + 1, finished=res["finished"].view(-1),
@@ -172,8 +178,13 @@ class BeamSearchDecoder(ModelPart):
         tiled_states = [self.expand_to_beam(s) for s in enc_states()]
         tiled_masks = [self.expand_to_beam(m) if m is not None else None for m in enc_masks()]
         from neuralmonkey_b200.decoders.transformer import TransformerDecoder
+        seen = self.__dict__.setdefault("_shape_seen", {})
+        shape_key = (parent.batch_size, tuple(tuple(s.shape) for s in tiled_states))
+        seen[shape_key] = seen.get(shape_key, 0) + 1
+        if len(seen) > 4096:
+            seen.clear()
         if (self.use_cuda_graph and isinstance(parent, TransformerDecoder) and parent.use_kv_cache
-                and runtime.device().type == "cuda"):
+                and runtime.device().type == "cuda" and seen[shape_key] >= self.GRAPH_AFTER):
             try:
                 with torch.no_grad():
                     return self._graph_outputs(tiled_states, tiled_masks)

@@ -39,7 +39,8 @@ class GenericTrainer(GraphExecutor, Feedable):
         # reports it as host_enqueue_ms_per_step) next to ~8 ms of GPU time.  Data parallel: two graphs
         # with the NCCL all-reduce between them.
         self.use_cuda_graph = use_cuda_graph
-        self._graphs = {}   # shape key -> "seen" | captured step
+        self._graphs = {}   # shape key -> "seen" | "failed" | captured step
+        self.MAX_GRAPHS = 4
         Feedable.__init__(self)
         self.objectives = objectives
         self.l1_weight = l1_weight
@@ -106,6 +107,9 @@ class GenericTrainer(GraphExecutor, Feedable):
             return None
         opt = self.optimizer
         if entry == "seen":
+            captured = [k for k, v in self._graphs.items() if isinstance(v, tuple)]
+            if len(captured) >= self.MAX_GRAPHS:          # bounded: a captured step owns its activations
+                del self._graphs[captured[0]]
             if not hasattr(self, "_lr_dev"):
                 self._lr_dev = torch.zeros(1, device=arena.params.device, dtype=torch.float32)
             static = [{k: t.clone() for k, t in d.items()} for _, d in leaves]

@@ -55,6 +55,7 @@ def test_transformer_against_golden(graph):
         bs = BeamSearchDecoder(name="bs", parent_decoder=model["dec"], beam_size=3, max_steps=6,
                                length_normalization=0.6)
         bs.use_cuda_graph = graph
+        bs.GRAPH_AFTER = 1        # capture on first use (default: second occurrence of a shape)
         feed_transformer(model, src, None, train=False)
         bs.reset_batch()
         bs.batch_size = src.shape[0]

@@ -172,6 +172,7 @@ def test_beam_search_transformer_parent(beam, alpha, bsz, graph):
         bs = BeamSearchDecoder(name="bs", parent_decoder=model["dec"], beam_size=beam, max_steps=7,
                                length_normalization=alpha)
         bs.use_cuda_graph = graph
+        bs.GRAPH_AFTER = 1        # capture on first use (default: second occurrence of a shape)
         feed_transformer(model, src, None, train=False)
         bs.reset_batch()
         bs.batch_size = bsz
