@@ -126,7 +126,7 @@ class TransformerBeamGraph:
             torch.cuda.synchronize()
             self._init_state()
             self.graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(self.graph):
+            with torch.cuda.graph(self.graph, capture_error_mode="thread_local"):
                 self._step()
             # a capture records, it does not execute: the state is still the one after position 0
         steps = 0

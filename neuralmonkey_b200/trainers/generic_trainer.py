@@ -122,14 +122,14 @@ class GenericTrainer(GraphExecutor, Feedable):
                 if distributed.world_size() > 1:
                     # data parallel: the gradient exchange stays an eager NCCL call between two
                     # captured halves (backward | clip + Adam)
-                    with torch.cuda.graph(graph):
+                    with torch.cuda.graph(graph, capture_error_mode="thread_local"):
                         arena.zero_grad()
                         self._backward()
                     graph2 = torch.cuda.CUDAGraph()
-                    with torch.cuda.graph(graph2, pool=graph.pool()):
+                    with torch.cuda.graph(graph2, pool=graph.pool(), capture_error_mode="thread_local"):
                         self._adam_kernel(1.0, arena.stats[1:2], 0.0, self._lr_dev)
                 else:
-                    with torch.cuda.graph(graph):
+                    with torch.cuda.graph(graph, capture_error_mode="thread_local"):
                         arena.zero_grad()
                         self._backward()
                         self._adam_kernel(1.0, arena.stats[1:2], 0.0, self._lr_dev)
