@@ -1,20 +1,29 @@
-"""argparse-like loader for the [main] section
-(behaviour of neuralmonkey/config/configuration.py:10-120)."""
+"""Declaration and loading of the `[main]` section of an experiment
+(behaviour of neuralmonkey/config/configuration.py: declared fields with defaults and
+conditions, unknown or missing fields are errors, failures are logged and end the process)."""
+import sys
 import traceback
 from argparse import Namespace
 from collections import OrderedDict
-from typing import Any, Callable, List, Optional
+from typing import Any, Callable, Dict, List, NamedTuple, Optional
 
 from neuralmonkey_b200.config.builder import build_config
 from neuralmonkey_b200.config.parsing import parse_file, write_file
 from neuralmonkey_b200.logging import log
 
+_Field = NamedTuple("_Field", [("required", bool), ("default", Any),
+                               ("condition", Optional[Callable[[Any], bool]])])
+
+
+def _fail(stage: str, exc: Exception) -> None:
+    log("Failed to {}: {}".format(stage, exc), color="red")
+    traceback.print_exc()
+    sys.exit(1)
+
 
 class Configuration:
     def __init__(self) -> None:
-        self.names = []  # type: List[str]
-        self.defaults = {}
-        self.conditions = {}
+        self._fields = OrderedDict()  # type: Dict[str, _Field]
         self.ignored = set()
         self.raw_config = OrderedDict()
         self.config_dict = OrderedDict()
@@ -22,44 +31,50 @@ class Configuration:
         self.args = None
         self.model = None
 
+    # -- declaration ---------------------------------------------------------------------------
+    @property
+    def names(self) -> List[str]:
+        return list(self._fields)
+
+    @property
+    def defaults(self) -> Dict[str, Any]:
+        return {n: f.default for n, f in self._fields.items() if not f.required}
+
+    @property
+    def conditions(self) -> Dict[str, Callable[[Any], bool]]:
+        return {n: f.condition for n, f in self._fields.items() if f.condition is not None}
+
     def add_argument(self, name: str, required: bool = False, default: Any = None,
                      cond: Callable[[Any], bool] = None) -> None:
-        if name in self.names:
+        if name in self._fields:
             raise Exception("Data filed defined multiple times.")
-        self.names.append(name)
-        if not required:
-            self.defaults[name] = default
-        if cond is not None:
-            self.conditions[name] = cond
+        self._fields[name] = _Field(required, default, cond)
 
     def ignore_argument(self, name: str) -> None:
         self.ignored.add(name)
 
-    def make_namespace(self, d_obj) -> Namespace:
-        n_space = Namespace()
+    # -- values -----------------------------------------------------------------------------------
+    def make_namespace(self, d_obj: Dict[str, Any]) -> Namespace:
+        values = dict(self.defaults)
         for name, value in d_obj.items():
-            if name in self.conditions and not self.conditions[name](value):
-                code = self.conditions[name].__code__
+            field = self._fields.get(name)
+            if field is not None and field.condition is not None and not field.condition(value):
+                code = field.condition.__code__
                 raise Exception("Value of field '{}' does not satisfy condition defined at {}:{}."
                                 .format(name, code.co_filename, code.co_firstlineno))
-            setattr(n_space, name, value)
-        for name, value in self.defaults.items():
-            if name not in n_space.__dict__:
-                n_space.__dict__[name] = value
-        return n_space
+            values[name] = value
+        return Namespace(**values)
 
     def load_file(self, path: str, changes: Optional[List[str]] = None) -> None:
         log("Loading INI file: '{}'".format(path), color="blue")
         try:
-            with open(path, "r", encoding="utf-8") as file:
-                raw_config, config_dict = parse_file(file, changes)
-            log("INI file is parsed.")
-            self.raw_config.update(raw_config)
-            self.config_dict.update(config_dict)
+            with open(path, "r", encoding="utf-8") as handle:
+                raw, parsed = parse_file(handle, changes)
         except Exception as exc:  # pylint: disable=broad-except
-            log("Failed to load INI file: {}".format(exc), color="red")
-            traceback.print_exc()
-            exit(1)
+            _fail("load INI file", exc)
+        log("INI file is parsed.")
+        self.raw_config.update(raw)
+        self.config_dict.update(parsed)
         if "main" in self.config_dict:
             self.args = self.make_namespace(self.config_dict["main"])
 
@@ -67,23 +82,22 @@ class Configuration:
         log("Building model based on the config.")
         self._check_loaded_conf()
         try:
-            model, self.objects = build_config(self.config_dict, self.ignored, warn_unused)
+            built, self.objects = build_config(self.config_dict, self.ignored, warn_unused)
         except Exception as exc:  # pylint: disable=broad-except
-            log("Failed to build model: {}".format(exc), color="red")
-            traceback.print_exc()
-            exit(1)
+            _fail("build model", exc)
         log("Model built.")
-        self.model = self.make_namespace(model)
+        self.model = self.make_namespace(built)
 
     def _check_loaded_conf(self) -> None:
-        missing = [n for n in self.names if n not in self.args.__dict__]
+        given = set(vars(self.args))
+        missing = [name for name in self._fields if name not in given]
         if missing:
             raise Exception("Missing mandatory fields: {}".format(", ".join(missing)))
-        unexpected = [n for n in self.config_dict["main"]
-                      if n not in self.names and n not in self.ignored]
+        unexpected = [name for name in self.config_dict["main"]
+                      if name not in self._fields and name not in self.ignored]
         if unexpected:
             raise Exception("Unexpected fields: {}".format(", ".join(unexpected)))
 
     def save_file(self, path: str) -> None:
-        with open(path, "w", encoding="utf-8") as file:
-            write_file(self.raw_config, file)
+        with open(path, "w", encoding="utf-8") as handle:
+            write_file(self.raw_config, handle)

@@ -1,33 +1,38 @@
-"""Pre/post-processing helpers (reference: neuralmonkey/processors/helpers.py)."""
-from typing import Any, Callable, Dict, Generator, List
+"""Series pre/post-processors named by the reference's INIs
+(behaviour of neuralmonkey/processors/helpers.py).
+
+    preprocess_char_based   words -> characters, with a space token between words
+    postprocess_char_based  inverse, for batches of decoded sentences
+    untruecase              capitalise the first token of every sentence (lazy)
+    pipeline                left-to-right composition of processors
+"""
+from functools import reduce
+from typing import Any, Callable, Iterator, List, Sequence
+
+Sentence = List[str]
 
 
-def preprocess_char_based(sentence: List[str]) -> List[str]:
-    return list(" ".join(sentence))
+def preprocess_char_based(sentence: Sentence) -> Sentence:
+    chars = []  # type: Sentence
+    for position, word in enumerate(sentence):
+        if position:
+            chars.append(" ")
+        chars.extend(word)
+    return chars
 
 
-def preprocess_add_noise(sentence: List[str]) -> List[str]:
+def preprocess_add_noise(sentence: Sentence) -> Sentence:
+    """Placeholder kept for configuration compatibility: the identity."""
     return sentence
 
 
-def postprocess_char_based(sentences: List[List[str]]) -> List[List[str]]:
-    result = []
-    for sentence in sentences:
-        result.append("".join(sentence).split(" "))
-    return result
+def postprocess_char_based(sentences: Sequence[Sentence]) -> List[Sentence]:
+    return ["".join(characters).split(" ") for characters in sentences]
 
 
-def untruecase(sentences: List[List[str]]) -> Generator[List[str], None, None]:
-    for sentence in sentences:
-        if sentence:
-            yield [sentence[0].capitalize()] + sentence[1:]
-        else:
-            yield []
+def untruecase(sentences: Sequence[Sentence]) -> Iterator[Sentence]:
+    return ([tokens[0].capitalize(), *tokens[1:]] if tokens else [] for tokens in sentences)
 
 
-def pipeline(processors: List[Callable]) -> Callable:
-    def process(data: Any) -> Any:
-        for processor in processors:
-            data = processor(data)
-        return data
-    return process
+def pipeline(processors: Sequence[Callable[[Any], Any]]) -> Callable[[Any], Any]:
+    return lambda data: reduce(lambda value, stage: stage(value), processors, data)
