@@ -13,6 +13,7 @@ scopes so checkpoints can be keyed the same way.
 """
 import math
 import re
+import zlib
 from typing import Callable, Dict, List, Optional, Sequence, Tuple
 
 import torch
@@ -147,8 +148,13 @@ class ParameterArena:
         prefix is what the optimizer and the all-reduce walk), frozen ones after."""
         if self.finalized:
             return
-        names = ([n for n in self.order if self.variables[n].trainable]
-                 + [n for n in self.order if not self.variables[n].trainable])
+        # Layout and initial values must not depend on the order in which model parts happened to
+        # declare their variables (it follows the iteration order of Python sets, which differs
+        # between processes): data-parallel ranks all-reduce this buffer element by element, so
+        # every rank needs the same layout and the same initial parameters.  Hence: sorted names,
+        # and one generator per variable seeded from (seed, crc32(name)).
+        names = (sorted(n for n in self.order if self.variables[n].trainable)
+                 + sorted(n for n in self.order if not self.variables[n].trainable))
         off = 0
         for n in names:
             self.variables[n].offset = off
@@ -159,10 +165,10 @@ class ParameterArena:
             self.trainable_size = 0
         self.size = off
         self.order = names
-        gen = torch.Generator().manual_seed(seed)
         host = torch.zeros(max(off, 1), dtype=torch.float32)
         for n in names:
             var = self.variables[n]
+            gen = torch.Generator().manual_seed((int(seed) * 1000003 + zlib.crc32(n.encode("utf-8"))) % (2 ** 63))
             val = var.initializer(var.shape, gen).to(torch.float32).reshape(-1)
             host[var.offset:var.offset + var.numel] = val
         self.params = host.to(device)
@@ -223,6 +229,22 @@ class ParameterArena:
 
     def state_dict(self) -> Dict[str, torch.Tensor]:
         return {n: self._views[n].detach().cpu().clone() for n in self.order}
+
+    def moment_dict(self, flat: torch.Tensor) -> Dict[str, torch.Tensor]:
+        """A flat per-parameter buffer (Adam m / v) split by trainable variable name."""
+        out = {}
+        for n in self.train_names:
+            var = self.variables[n]
+            out[n] = flat[var.offset:var.offset + var.numel].detach().cpu().clone().view(var.shape)
+        return out
+
+    def load_moments(self, flat: torch.Tensor, values: Dict[str, torch.Tensor]) -> None:
+        with torch.no_grad():
+            for n, v in values.items():
+                var = self.variables.get(n)
+                if var is None or not var.trainable or tuple(v.shape) != var.shape:
+                    continue
+                flat[var.offset:var.offset + var.numel].copy_(v.reshape(-1).to(flat.device))
 
     def named_grads(self) -> Dict[str, torch.Tensor]:
         return {n: self._views[n].nm_grad.detach().cpu().clone() for n in self.train_names}

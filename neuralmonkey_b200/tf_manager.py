@@ -112,9 +112,8 @@ class TensorFlowManager:
                 len(variable_files), self.num_sessions))
         arena = runtime.arena()
         for path in variable_files:
-            torch.save({"variables": arena.state_dict(),
-                        "adam_m": arena.adam_m.detach().cpu(), "adam_v": arena.adam_v.detach().cpu(),
-                        "order": list(arena.order)}, path)
+            torch.save({"variables": arena.state_dict(), "adam_m": arena.moment_dict(arena.adam_m),
+                        "adam_v": arena.moment_dict(arena.adam_v)}, path)
 
     def restore(self, variable_files: Union[str, List[str]]) -> None:
         if isinstance(variable_files, str):
@@ -127,9 +126,9 @@ class TensorFlowManager:
             log("Loading variables from {}".format(path))
             ckpt = torch.load(path, map_location="cpu")
             arena.load_dict(ckpt["variables"])
-            if ckpt.get("order") == list(arena.order):
-                arena.adam_m.copy_(ckpt["adam_m"])
-                arena.adam_v.copy_(ckpt["adam_v"])
+            if isinstance(ckpt.get("adam_m"), dict):   # optimizer moments, keyed by variable name
+                arena.load_moments(arena.adam_m, ckpt["adam_m"])
+                arena.load_moments(arena.adam_v, ckpt["adam_v"])
 
     def restore_best_vars(self) -> None:
         self.restore(self.variables_files[self.best_score_index])

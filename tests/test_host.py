@@ -46,12 +46,39 @@ def test_arena_layout_is_aligned_and_trainables_first():
     arena.finalize(torch.device("cpu"))
     offs = arena.seg_off.tolist()
     assert offs[0] == 0 and all(o % ParameterArena.ALIGN == 0 for o in offs)
-    assert arena.train_names == ["a/kernel", "a/bias"]
-    assert arena.seg_reg.tolist() == [1, 0]       # biases are not regularised
+    assert arena.train_names == ["a/bias", "a/kernel"]   # sorted by name, whatever the declaration order
+    assert arena.seg_reg.tolist() == [0, 1]       # biases are not regularised
     assert arena.variables["frozen/w"].offset >= arena.trainable_size
     assert arena.get("a/kernel").requires_grad and not arena.get("frozen/w").requires_grad
     assert arena.get("a/kernel").nm_grad.shape == (7, 9)
     assert arena.allreduce_view.numel() == arena.trainable_size + ParameterArena.STAT_SLOTS
+
+
+def test_arena_is_independent_of_declaration_order(tmp_path):
+    """Data-parallel ranks declare variables in whatever order their sets iterate: layout, initial
+    values and checkpoints must come out the same."""
+    from neuralmonkey_b200.params import orthogonal_initializer
+    decls = [("dec/state_to_word_W", [6, 32], normal_initializer()), ("dec/state_to_word_b", [32], zeros_initializer()),
+             ("enc/gates/kernel", [8, 8], orthogonal_initializer()), ("enc/emb", [30, 4], normal_initializer(0.1))]
+    arenas = []
+    for order in (decls, decls[::-1], [decls[2], decls[0], decls[3], decls[1]]):
+        arena = ParameterArena()
+        for name, shape, init in order:
+            arena.declare(name, shape, init)
+        arena.finalize(torch.device("cpu"), seed=11)
+        arenas.append(arena)
+    for other in arenas[1:]:
+        assert other.train_names == arenas[0].train_names
+        assert torch.equal(other.params, arenas[0].params)
+    first = arenas[0]
+    w, b = first.variables["dec/state_to_word_W"], first.variables["dec/state_to_word_b"]
+    assert b.offset == w.offset + w.numel          # the bias segment directly follows its weight matrix
+    # Adam moments survive a save / restore keyed by variable name
+    first.adam_m.uniform_(-1, 1)
+    moments = first.moment_dict(first.adam_m)
+    arenas[1].load_moments(arenas[1].adam_m, moments)
+    restored = arenas[1].moment_dict(arenas[1].adam_m)
+    assert all(torch.equal(restored[n], moments[n]) for n in moments)
 
 
 def test_shard_bounds_cover_everything_once():
