@@ -7,12 +7,34 @@ from neuralmonkey_b200.evaluators.bleu import BLEU, BLEU1, BLEU2, BLEU4, BLEUEva
 
 
 class AccuracyEvaluator:
-    def __init__(self, name: str = "Accuracy") -> None:
+    """Token-level accuracy: aligned hypothesis / reference tokens of the whole batch are scored
+    with `==` and averaged together (evaluators/evaluator.py:122-187, evaluators/accuracy.py);
+    reference tokens equal to `mask_symbol` are left out."""
+
+    def __init__(self, name: str = "Accuracy", mask_symbol=None) -> None:
+        self.name = name
+        self.mask_symbol = mask_symbol
+
+    def __call__(self, decoded: List, references: List) -> float:
+        hits, total = 0.0, 0
+        for hyp, ref in zip(decoded, references):
+            for h_tok, r_tok in zip(hyp, ref):
+                if self.mask_symbol and r_tok == self.mask_symbol:
+                    continue
+                hits += float(h_tok == r_tok)
+                total += 1
+        return hits / total if total else 0.0
+
+
+class AccuracySeqLevelEvaluator:
+    """1.0 for an exactly matching sequence, 0.0 otherwise, averaged over the batch."""
+
+    def __init__(self, name: str = "AccuracySeqLevel") -> None:
         self.name = name
 
     def __call__(self, decoded: List, references: List) -> float:
         pairs = list(zip(decoded, references))
-        return sum(1.0 for h, r in pairs if h == r) / len(pairs) if pairs else 0.0
+        return sum(1.0 for hyp, ref in pairs if hyp == ref) / len(pairs) if pairs else 0.0
 
 
 class RougeLEvaluator:

@@ -140,3 +140,50 @@ def test_plugin_names_of_the_reference_configs_are_importable():
         assert hasattr(importlib.import_module("neuralmonkey_b200." + module), attr), name
     from neuralmonkey_b200 import tf
     assert tf.contrib.opt.LazyAdamOptimizer and tf.train.AdamOptimizer
+
+
+def test_tf_manager_keeps_n_best_checkpoints_and_restores(tmp_path):
+    """n-best bookkeeping of TensorFlowManager (tf_manager.py:133-155 of the reference): the worst
+    kept file is overwritten, `<prefix>.best` names the best one, restore brings the values back."""
+    import torch
+    from neuralmonkey_b200 import runtime
+    from neuralmonkey_b200.params import normal_initializer
+    from neuralmonkey_b200.tf_manager import TensorFlowManager
+    runtime.reset()
+    arena = runtime.arena()
+    arena.declare("part/kernel", [4, 3], normal_initializer(0.5))
+    arena.declare("part/bias", [3], normal_initializer(0.5))
+    arena.finalize(torch.device("cpu"), seed=3)
+    mgr = TensorFlowManager(num_sessions=1, num_threads=1, save_n_best=2)
+    prefix = str(tmp_path / "variables.data")
+    mgr.init_saving(prefix)
+    assert mgr.variables_files == [prefix + ".0", prefix + ".1"]
+    snapshots = {}
+    for step, score in enumerate([0.1, 0.5, 0.3, 0.2, 0.9]):
+        with torch.no_grad():
+            arena.params.add_(1.0)
+        snapshots[score] = arena.state_dict()
+        mgr.validation_hook(score, epoch=1, batch=step)
+    assert sorted(mgr.saved_scores) == [0.5, 0.9]
+    assert mgr.best_score == 0.9
+    best_name = open(prefix + ".best").read()
+    assert best_name == os.path.basename(mgr.variables_files[mgr.best_score_index])
+    with torch.no_grad():
+        arena.params.zero_()
+    mgr.restore_best_vars()
+    for name, want in snapshots[0.9].items():
+        assert torch.equal(arena.state_dict()[name], want)
+    runtime.reset()
+
+
+def test_rouge_l_and_accuracy_evaluators():
+    from neuralmonkey_b200.evaluators import ROUGE_L, AccuracyEvaluator, AccuracySeqLevelEvaluator
+    ref = [["a", "b", "c", "d"]]
+    assert abs(ROUGE_L(ref, ref) - 1.0) < 1e-9
+    assert ROUGE_L([["x"]], ref) == 0.0
+    partial = ROUGE_L([["a", "c", "x"]], ref)
+    assert 0.0 < partial < 1.0
+    acc = AccuracyEvaluator()
+    assert acc([["a", "b"], ["c"]], [["a", "x"], ["c"]]) == pytest.approx(2.0 / 3.0)     # token level
+    assert AccuracySeqLevelEvaluator()([["a", "b"], ["c"]], [["a", "x"], ["c"]]) == pytest.approx(0.5)
+    assert AccuracyEvaluator(mask_symbol="x")([["a", "b"]], [["a", "x"]]) == pytest.approx(1.0)
