@@ -1,0 +1,124 @@
+"""Golden vectors for the HOST side of the path, produced by the reference's own code run in this
+container: vocabulary / padding / index conversion (`neuralmonkey/vocabulary.py`), dataset batching and
+bucketing (`neuralmonkey/dataset.py`), BLEU (`neuralmonkey/evaluators/bleu.py`), char-level helpers
+(`neuralmonkey/processors/helpers.py`).  Only third-party imports that are absent here are stubbed
+(termcolor, typeguard, and an empty `tensorflow` module - none of the functions called below use it);
+`collections.Sized/Iterable` get their Python >= 3.10 aliases.
+    python tests/golden/make_host_golden.py
+"""
+import json
+import os
+import sys
+import tempfile
+import types
+
+REF = "/root/reference"
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+SENTENCES = [["the", "cat", "sat"], ["a", "dog"], [], ["the", "zebra", "sat", "on", "the", "mat", "again"]]
+WORDS = ["the", "cat", "sat", "a", "dog", "on", "mat"]
+HYPS = [["the", "cat", "sat", "on", "the", "mat"], ["a", "dog", "dog", "barks"], ["hello"], []]
+REFS = [["the", "cat", "sat", "on", "a", "mat"], ["a", "dog", "barks"], ["hello", "world"], ["x"]]
+CORPUS = ["a", "b c", "d e f", "g h i j", "k l m n o", "p", "q r", "s t u v w x y", "z z", "a b c d e f g h i"]
+
+
+def install_stubs():
+    term = types.ModuleType("termcolor")
+    term.colored = lambda text, *a, **k: text
+    sys.modules["termcolor"] = term
+    guard = types.ModuleType("typeguard")
+    guard.check_argument_types = lambda *a, **k: True
+
+    def matches(value, expected):
+        import collections.abc
+        import typing
+        origin, args = typing.get_origin(expected), typing.get_args(expected)
+        if expected is typing.Any:
+            return True
+        if origin is typing.Union:
+            return any(matches(value, a) for a in args)
+        if origin in (list, typing.List):
+            return isinstance(value, list) and all(matches(v, args[0]) for v in value) if args else isinstance(value, list)
+        if origin in (tuple, typing.Tuple):
+            return isinstance(value, tuple) and len(value) == len(args) and all(matches(v, a) for v, a in zip(value, args))
+        if origin is collections.abc.Callable or expected is typing.Callable:
+            return callable(value)
+        return isinstance(value, expected)
+
+    def check_type(_name, value, expected, _memo=None):
+        if not matches(value, expected):
+            raise TypeError("type mismatch")
+    guard.check_type = check_type
+    sys.modules["typeguard"] = guard
+    tf = types.ModuleType("tensorflow")
+    tf.Tensor = object
+    # Vocabulary.__init__ builds two TF lookup tables we never query here
+    lookup = types.SimpleNamespace(index_table_from_tensor=lambda *a, **k: None,
+                                   index_to_string_table_from_tensor=lambda *a, **k: None)
+    tf.contrib = types.SimpleNamespace(lookup=lookup)
+    sys.modules["tensorflow"] = tf
+    # packages the evaluators package imports at module level but BLEU does not use
+    for name, attrs in (("sacrebleu", {"corpus_bleu": None, "TOKENIZERS": {"none": None, "13a": None, "intl": None, "zh": None}}), ("rouge", {"Rouge": object}),
+                        ("pyter", {"ter": None})):
+        mod = types.ModuleType(name)
+        mod.__dict__.update(attrs)
+        sys.modules[name] = mod
+    # the reference predates Python 3.10: collections.Sized / Iterable moved to collections.abc
+    import collections
+    import collections.abc
+    for name in ("Sized", "Iterable", "Callable"):
+        if not hasattr(collections, name):
+            setattr(collections, name, getattr(collections.abc, name))
+    sys.path.insert(0, REF)
+
+
+def main():
+    install_stubs()
+    import numpy as np
+    out = {}
+    # ---- vocabulary ------------------------------------------------------------------------
+    from neuralmonkey import vocabulary as V
+    with tempfile.TemporaryDirectory() as tmp:
+        path = os.path.join(tmp, "vocab.tsv")
+        with open(path, "w") as f:
+            for w in ["<pad>", "<s>", "</s>", "<unk>"] + WORDS:
+                f.write(w + "\n")
+        vocab = V.from_wordlist(path, contains_header=False, contains_frequencies=False)
+    out["vocab_index_to_word"] = list(vocab.index_to_word)
+    for max_len, start, end in ((None, False, False), (4, False, True), (3, True, True), (None, True, False)):
+        padded = V.pad_batch([list(s) for s in SENTENCES], max_len, start, end)
+        key = "pad_{}_{}_{}".format(max_len, int(start), int(end))
+        out[key] = [list(s) for s in padded]
+    out["sentence_mask_rule"] = "id != 0"
+    vectors = np.array([[4, 5, 6, 2, 0], [7, 8, 2, 0, 0], [3, 3, 3, 3, 3]]).T      # time-major
+    out["vectors_to_sentences"] = vocab.vectors_to_sentences(vectors)
+    # ---- dataset batching --------------------------------------------------------------------
+    from neuralmonkey.dataset import BatchingScheme, load
+    with tempfile.TemporaryDirectory() as tmp:
+        path = os.path.join(tmp, "src.txt")
+        with open(path, "w") as f:
+            f.write("\n".join(CORPUS) + "\n")
+        for name, scheme in (("fixed3", BatchingScheme(batch_size=3)),
+                             ("fixed4_drop", BatchingScheme(batch_size=4, drop_remainder=True)),
+                             ("buckets", BatchingScheme(bucket_boundaries=[2, 5],
+                                                        bucket_batch_sizes=[3, 2, 1]))):
+            ds = load("toy", ["source"], [path], scheme)
+            out["dataset_" + name] = [[list(s) for s in b.get_series("source")] for b in ds.batches()]
+    # ---- BLEU ------------------------------------------------------------------------------------
+    from neuralmonkey.evaluators.bleu import BLEUEvaluator
+    for n in (1, 2, 4):
+        for dedup in (False, True):
+            ev = BLEUEvaluator(n=n, deduplicate=dedup)
+            out["bleu_{}_{}".format(n, int(dedup))] = float(ev(HYPS, REFS))
+    out["bleu_identity"] = float(BLEUEvaluator()(REFS, REFS))
+    # ---- helpers -----------------------------------------------------------------------------------
+    from neuralmonkey.processors import helpers as H
+    out["char_based"] = [H.preprocess_char_based(s) for s in SENTENCES]
+    out["char_based_back"] = H.postprocess_char_based(out["char_based"])
+    out["inputs"] = {"sentences": SENTENCES, "words": WORDS, "hyps": HYPS, "refs": REFS, "corpus": CORPUS}
+    json.dump(out, open(os.path.join(HERE, "host_golden.json"), "w"), indent=1, sort_keys=True)
+    print({k: (v if not isinstance(v, list) else "...") for k, v in out.items()})
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,76 @@
+"""Host side of the path against golden vectors produced by the REFERENCE's own code
+(tests/golden/make_host_golden.py ran neuralmonkey/{vocabulary,dataset,evaluators/bleu,
+processors/helpers}.py in the build container): vocabulary + padding + index conversion (rows a1 and
+a15 of SURVEY.md section 8), dataset batching / bucketing, BLEU, char-level helpers."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+@pytest.fixture(scope="module")
+def golden():
+    return json.load(open(os.path.join(HERE, "golden", "host_golden.json")))
+
+
+def _vocab(tmp_path, words):
+    from neuralmonkey_b200.vocabulary import from_wordlist
+    path = tmp_path / "vocab.tsv"
+    path.write_text("\n".join(["<pad>", "<s>", "</s>", "<unk>"] + words) + "\n")
+    return from_wordlist(str(path), contains_header=False, contains_frequencies=False)
+
+
+def test_vocabulary_and_padding_match_reference(golden, tmp_path):
+    from neuralmonkey_b200.vocabulary import pad_batch
+    vocab = _vocab(tmp_path, golden["inputs"]["words"])
+    assert list(vocab.index_to_word) == golden["vocab_index_to_word"]
+    sentences = golden["inputs"]["sentences"]
+    for max_len, start, end in ((None, False, False), (4, False, True), (3, True, True), (None, True, False)):
+        got = pad_batch([list(s) for s in sentences], max_len, start, end)
+        assert [list(s) for s in got] == golden["pad_{}_{}_{}".format(max_len, int(start), int(end))]
+    vectors = np.array([[4, 5, 6, 2, 0], [7, 8, 2, 0, 0], [3, 3, 3, 3, 3]]).T
+    assert vocab.vectors_to_sentences(vectors) == golden["vectors_to_sentences"]
+
+
+def test_strings_to_indices_follow_the_reference_vocabulary_order(golden, tmp_path):
+    from neuralmonkey_b200.vocabulary import pad_batch
+    vocab = _vocab(tmp_path, golden["inputs"]["words"])
+    padded = pad_batch([["the", "zebra", "mat"], ["dog"]], None, False, True)
+    ids = vocab.strings_to_indices(padded).tolist()
+    word_to_index = {w: i for i, w in enumerate(golden["vocab_index_to_word"])}
+    want = [[word_to_index.get(w, 3) for w in row] for row in [list(r) for r in padded]]
+    assert ids == want
+
+
+def test_dataset_batching_matches_reference(golden, tmp_path):
+    from neuralmonkey_b200.dataset import BatchingScheme, load
+    path = tmp_path / "src.txt"
+    path.write_text("\n".join(golden["inputs"]["corpus"]) + "\n")
+    schemes = {"fixed3": BatchingScheme(batch_size=3),
+               "fixed4_drop": BatchingScheme(batch_size=4, drop_remainder=True),
+               "buckets": BatchingScheme(bucket_boundaries=[2, 5], bucket_batch_sizes=[3, 2, 1])}
+    for name, scheme in schemes.items():
+        ds = load("toy", ["source"], [str(path)], scheme)
+        got = [[list(s) for s in b.get_series("source")] for b in ds.batches()]
+        assert got == golden["dataset_" + name], name
+
+
+def test_bleu_matches_reference(golden):
+    from neuralmonkey_b200.evaluators.bleu import BLEUEvaluator
+    hyps, refs = golden["inputs"]["hyps"], golden["inputs"]["refs"]
+    for n in (1, 2, 4):
+        for dedup in (False, True):
+            got = BLEUEvaluator(n=n, deduplicate=dedup)(hyps, refs)
+            assert got == pytest.approx(golden["bleu_{}_{}".format(n, int(dedup))], rel=1e-9), (n, dedup)
+    assert BLEUEvaluator()(refs, refs) == pytest.approx(golden["bleu_identity"])
+
+
+def test_char_helpers_match_reference(golden):
+    from neuralmonkey_b200.processors.helpers import postprocess_char_based, preprocess_char_based
+    sentences = golden["inputs"]["sentences"]
+    chars = [preprocess_char_based(s) for s in sentences]
+    assert chars == golden["char_based"]
+    assert postprocess_char_based(chars) == golden["char_based_back"]
