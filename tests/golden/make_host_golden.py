@@ -22,6 +22,12 @@ REFS = [["the", "cat", "sat", "on", "a", "mat"], ["a", "dog", "barks"], ["hello"
 CORPUS = ["a", "b c", "d e f", "g h i j", "k l m n o", "p", "q r", "s t u v w x y", "z z", "a b c d e f g h i"]
 
 
+TEXT_LINES = ["Hello, world!  It's 42.", "  leading and trailing  ", "naive café: 3.14 -- ok", "x", "a+b=c (d)",
+              "Ünïcödé ... \u4e2d\u6587 test"]
+TSV_LINES = ["id1\tthe first text\tlabel a", "id2\t second  text \tlabel b", "id3\tthird"]
+CSV_LINES = ['one two, "quoted, with comma", x y', 'three, plain field, z', 'four five,,']
+
+
 def install_stubs():
     term = types.ModuleType("termcolor")
     term.colored = lambda text, *a, **k: text
@@ -115,7 +121,25 @@ def main():
     from neuralmonkey.processors import helpers as H
     out["char_based"] = [H.preprocess_char_based(s) for s in SENTENCES]
     out["char_based_back"] = H.postprocess_char_based(out["char_based"])
-    out["inputs"] = {"sentences": SENTENCES, "words": WORDS, "hyps": HYPS, "refs": REFS, "corpus": CORPUS}
+    # ---- text readers ------------------------------------------------------------------------------
+    from neuralmonkey.readers import plain_text_reader as R
+    with tempfile.TemporaryDirectory() as tmp:
+        txt = os.path.join(tmp, "text.txt")
+        with open(txt, "w", encoding="utf-8") as f:
+            f.write("\n".join(TEXT_LINES) + "\n")
+        tsv = os.path.join(tmp, "table.tsv")
+        with open(tsv, "w", encoding="utf-8") as f:
+            f.write("\n".join(TSV_LINES) + "\n")
+        csvf = os.path.join(tmp, "table.csv")
+        with open(csvf, "w", encoding="utf-8") as f:
+            f.write("\n".join(CSV_LINES) + "\n")
+        out["reader_tokenized"] = [list(x) for x in R.tokenized_text_reader()([txt])]
+        out["reader_t2t"] = [list(x) for x in R.t2t_tokenized_text_reader()([txt])]
+        out["reader_tsv2"] = [list(x) for x in R.tsv_reader(2)([tsv])]
+        out["reader_csv1"] = [list(x) for x in R.csv_reader(1)([csvf])]
+        out["reader_csv3"] = [list(x) for x in R.csv_reader(3)([csvf])]
+    out["inputs"] = {"text_lines": TEXT_LINES, "tsv_lines": TSV_LINES, "csv_lines": CSV_LINES,
+                     "sentences": SENTENCES, "words": WORDS, "hyps": HYPS, "refs": REFS, "corpus": CORPUS}
     json.dump(out, open(os.path.join(HERE, "host_golden.json"), "w"), indent=1, sort_keys=True)
     print({k: (v if not isinstance(v, list) else "...") for k, v in out.items()})
 

@@ -74,3 +74,18 @@ def test_char_helpers_match_reference(golden):
     chars = [preprocess_char_based(s) for s in sentences]
     assert chars == golden["char_based"]
     assert postprocess_char_based(chars) == golden["char_based_back"]
+
+
+def test_text_readers_match_reference(golden, tmp_path):
+    from neuralmonkey_b200.readers import plain_text_reader as R
+    inputs = golden["inputs"]
+    txt, tsv, csvf = tmp_path / "text.txt", tmp_path / "table.tsv", tmp_path / "table.csv"
+    txt.write_text("\n".join(inputs["text_lines"]) + "\n", encoding="utf-8")
+    tsv.write_text("\n".join(inputs["tsv_lines"]) + "\n", encoding="utf-8")
+    csvf.write_text("\n".join(inputs["csv_lines"]) + "\n", encoding="utf-8")
+    assert [list(x) for x in R.tokenized_text_reader()([str(txt)])] == golden["reader_tokenized"]
+    assert [list(x) for x in R.UtfPlainTextReader([str(txt)])] == golden["reader_tokenized"]
+    assert [list(x) for x in R.t2t_tokenized_text_reader()([str(txt)])] == golden["reader_t2t"]
+    assert [list(x) for x in R.tsv_reader(2)([str(tsv)])] == golden["reader_tsv2"]
+    assert [list(x) for x in R.csv_reader(1)([str(csvf)])] == golden["reader_csv1"]
+    assert [list(x) for x in R.csv_reader(3)([str(csvf)])] == golden["reader_csv3"]
