@@ -110,6 +110,17 @@ def main():
                                                         bucket_batch_sizes=[3, 2, 1]))):
             ds = load("toy", ["source"], [path], scheme)
             out["dataset_" + name] = [[list(s) for s in b.get_series("source")] for b in ds.batches()]
+        # series-level preprocessor, lazy buffer and shuffling (Python's `random`, seeded here)
+        import random
+        from neuralmonkey.processors.helpers import preprocess_char_based
+        ds = load("toy", ["source", "chars"], [path, (preprocess_char_based, "source")], BatchingScheme(batch_size=4))
+        out["dataset_preprocessed"] = [{k: [list(s) for s in b.get_series(k)] for k in ("source", "chars")}
+                                       for b in ds.batches()]
+        for name, kwargs in (("lazy", dict(buffer_size=4)), ("shuffled", dict(shuffled=True)),
+                             ("lazy_shuffled", dict(buffer_size=6, shuffled=True))):
+            random.seed(5)
+            ds = load("toy", ["source"], [path], BatchingScheme(batch_size=3), **kwargs)
+            out["dataset_" + name] = [[list(s) for s in b.get_series("source")] for b in ds.batches()]
     # ---- BLEU ------------------------------------------------------------------------------------
     from neuralmonkey.evaluators.bleu import BLEUEvaluator
     for n in (1, 2, 4):

@@ -89,3 +89,21 @@ def test_text_readers_match_reference(golden, tmp_path):
     assert [list(x) for x in R.tsv_reader(2)([str(tsv)])] == golden["reader_tsv2"]
     assert [list(x) for x in R.csv_reader(1)([str(csvf)])] == golden["reader_csv1"]
     assert [list(x) for x in R.csv_reader(3)([str(csvf)])] == golden["reader_csv3"]
+
+
+def test_dataset_preprocessors_lazy_buffer_and_shuffle_match_reference(golden, tmp_path):
+    import random
+    from neuralmonkey_b200.dataset import BatchingScheme, load
+    from neuralmonkey_b200.processors.helpers import preprocess_char_based
+    path = tmp_path / "src.txt"
+    path.write_text("\n".join(golden["inputs"]["corpus"]) + "\n")
+    ds = load("toy", ["source", "chars"], [str(path), (preprocess_char_based, "source")],
+              BatchingScheme(batch_size=4))
+    got = [{k: [list(s) for s in b.get_series(k)] for k in ("source", "chars")} for b in ds.batches()]
+    assert got == golden["dataset_preprocessed"]
+    for name, kwargs in (("lazy", dict(buffer_size=4)), ("shuffled", dict(shuffled=True)),
+                         ("lazy_shuffled", dict(buffer_size=6, shuffled=True))):
+        random.seed(5)
+        ds = load("toy", ["source"], [str(path)], BatchingScheme(batch_size=3), **kwargs)
+        got = [[list(s) for s in b.get_series("source")] for b in ds.batches()]
+        assert got == golden["dataset_" + name], name
