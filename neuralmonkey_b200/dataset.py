@@ -13,7 +13,8 @@ from typing import Any, Callable, Dict, Iterator, List, Optional, Tuple, Union
 
 from neuralmonkey_b200.logging import debug, log, warn
 from neuralmonkey_b200.readers.plain_text_reader import UtfPlainTextReader
-from neuralmonkey_b200.writers.plain_text_writer import AutoWriter, Writer
+from neuralmonkey_b200.writers.auto import AutoWriter
+from neuralmonkey_b200.writers.plain_text_writer import Writer
 
 Reader = Callable[[List[str]], Any]
 

@@ -1,53 +1,56 @@
-"""Writers of output series (reference: neuralmonkey/writers/plain_text_writer.py, writers/auto.py).
-A writer is called as writer(path, data)."""
-from typing import Any, Callable, Iterable, List
+"""Text writers of output series (names and behaviour of neuralmonkey/writers/plain_text_writer.py).
+A writer is called as `writer(path, data)`; `tokenized_text_writer` inverts `tokenized_text_reader`,
+`t2t_tokenized_text_writer` inverts `t2t_tokenized_text_reader`."""
+from typing import Any, Callable, Iterable, Iterator, List
 
-import numpy as np
+from neuralmonkey_b200.logging import log
+from neuralmonkey_b200.readers.plain_text_reader import _is_alnum
 
 Writer = Callable[[str, Any], None]
 
 
+def t2t_detokenize(data: Iterable[List[str]]) -> Iterator[str]:
+    """Glue tensor2tensor-style tokens back together: a space goes only between two neighbouring
+    tokens that both start with an alphanumeric character."""
+    for sentence in data:
+        pieces, previous_alnum = [], False
+        for position, token in enumerate(sentence):
+            starts_alnum = _is_alnum(token[0])
+            if position and previous_alnum and starts_alnum:
+                pieces.append(" ")
+            pieces.append(token)
+            previous_alnum = starts_alnum
+        yield "".join(pieces)
+
+
 def text_writer(encoding: str = "utf-8") -> Writer:
-    def writer(path: str, data: Iterable[List[str]]) -> None:
-        with open(path, "w", encoding=encoding) as f_out:
-            for sentence in data:
-                f_out.write(" ".join(str(tok) for tok in sentence) + "\n")
+    """One `str(item)` per line."""
+    def writer(path: str, data: Iterable[Any]) -> None:
+        with open(path, "w", encoding=encoding) as handle:
+            handle.writelines(str(item) + "\n" for item in data)
+        log("Result saved as plain text in '{}'".format(path))
     return writer
 
 
-def numpy_writer(path: str, data: Any) -> None:
-    np.save(path, np.asarray(list(data), dtype=object) if not isinstance(data, np.ndarray) else data)
+def tokenized_text_writer(encoding: str = "utf-8") -> Writer:
+    """Token lists joined by single spaces."""
+    plain = text_writer(encoding)
+    return lambda path, data: plain(path, (" ".join(str(tok) for tok in sentence) for sentence in data))
 
 
-def AutoWriter(path: str, data: Any) -> None:  # pylint: disable=invalid-name
-    """Text for lists of token lists / strings, numpy otherwise (writers/auto.py:20-60)."""
-    data = list(data) if not isinstance(data, (list, np.ndarray)) else data
-    if isinstance(data, np.ndarray):
-        np.save(path, data)
-        return
-    if all(isinstance(item, str) for item in data):
-        with open(path, "w", encoding="utf-8") as f_out:
-            f_out.write("\n".join(data) + "\n")
-        return
-    if all(isinstance(item, (list, tuple)) and all(isinstance(t, str) for t in item) for item in data):
-        text_writer()(path, data)
-        return
-    if all(isinstance(item, dict) for item in data):
-        np.savez(path, **{k: _stack([d[k] for d in data]) for k in data[0]}) if data else np.savez(path)
-        return
-    np.save(path, _stack(data))
+def t2t_tokenized_text_writer(encoding: str = "utf-8") -> Writer:
+    plain = text_writer(encoding)
+    return lambda path, data: plain(path, t2t_detokenize(data))
 
 
-def _stack(items: List[Any]) -> np.ndarray:
-    """Regular array when the examples agree in shape, object array otherwise (bucketed
-    batches give per-example tensors different time dimensions)."""
-    try:
-        return np.array(items)
-    except ValueError:
-        out = np.empty(len(items), dtype=object)
-        for i, item in enumerate(items):
-            out[i] = item
-        return out
+# pylint: disable=invalid-name
+UtfPlainTextWriter = tokenized_text_writer()
+T2TWriter = t2t_tokenized_text_writer()
 
 
-UtfPlainTextWriter = text_writer()
+def __getattr__(name: str):
+    # AutoWriter lived here before the writers were split like the reference's package
+    if name in ("AutoWriter", "auto_writer"):
+        from neuralmonkey_b200.writers import auto
+        return getattr(auto, name)
+    raise AttributeError(name)

@@ -47,6 +47,8 @@ def install_stubs():
             return isinstance(value, list) and all(matches(v, args[0]) for v in value) if args else isinstance(value, list)
         if origin in (tuple, typing.Tuple):
             return isinstance(value, tuple) and len(value) == len(args) and all(matches(v, a) for v, a in zip(value, args))
+        if origin in (dict, typing.Dict):
+            return isinstance(value, dict) and all(matches(k, args[0]) and matches(v, args[1]) for k, v in value.items())
         if origin is collections.abc.Callable or expected is typing.Callable:
             return callable(value)
         return isinstance(value, expected)
@@ -149,6 +151,24 @@ def main():
         out["reader_tsv2"] = [list(x) for x in R.tsv_reader(2)([tsv])]
         out["reader_csv1"] = [list(x) for x in R.csv_reader(1)([csvf])]
         out["reader_csv3"] = [list(x) for x in R.csv_reader(3)([csvf])]
+    # ---- writers ---------------------------------------------------------------------------------------
+    from neuralmonkey.writers import plain_text_writer as W
+    from neuralmonkey.writers.auto import AutoWriter
+    with tempfile.TemporaryDirectory() as tmp:
+        def text_of(writer, data, name):
+            target = os.path.join(tmp, name)
+            writer(target, data)
+            return open(target, encoding="utf-8").read()
+        out["writer_tokenized"] = text_of(W.tokenized_text_writer(), out["reader_tokenized"], "a.txt")
+        out["writer_t2t"] = text_of(W.t2t_tokenized_text_writer(), out["reader_t2t"], "b.txt")
+        out["writer_plain"] = text_of(W.text_writer(), ["x y", 3, 4.5], "c.txt")
+        out["writer_auto_tokens"] = text_of(AutoWriter, [["a", "b"], ["c"]], "d.txt")
+        out["writer_auto_plain"] = text_of(AutoWriter, [1.5, 2.5], "e.txt")
+        AutoWriter(os.path.join(tmp, "f"), [{"x": np.ones((2, 3)), "y": np.zeros(4)}, {"x": np.ones((2, 3)), "y": np.ones(4)}])
+        loaded = np.load(os.path.join(tmp, "f.npz"))
+        out["writer_auto_npz"] = {k: list(loaded[k].shape) for k in loaded.files}
+        AutoWriter(os.path.join(tmp, "g"), np.arange(6).reshape(2, 3))
+        out["writer_auto_npy"] = np.load(os.path.join(tmp, "g.npy")).tolist()
     out["inputs"] = {"text_lines": TEXT_LINES, "tsv_lines": TSV_LINES, "csv_lines": CSV_LINES,
                      "sentences": SENTENCES, "words": WORDS, "hyps": HYPS, "refs": REFS, "corpus": CORPUS}
     json.dump(out, open(os.path.join(HERE, "host_golden.json"), "w"), indent=1, sort_keys=True)

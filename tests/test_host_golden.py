@@ -107,3 +107,29 @@ def test_dataset_preprocessors_lazy_buffer_and_shuffle_match_reference(golden, t
         ds = load("toy", ["source"], [str(path)], BatchingScheme(batch_size=3), **kwargs)
         got = [[list(s) for s in b.get_series("source")] for b in ds.batches()]
         assert got == golden["dataset_" + name], name
+
+
+def test_writers_match_reference(golden, tmp_path):
+    from neuralmonkey_b200.writers import plain_text_writer as W
+    from neuralmonkey_b200.writers.auto import AutoWriter
+
+    def text_of(writer, data, name):
+        target = str(tmp_path / name)
+        writer(target, data)
+        return open(target, encoding="utf-8").read()
+
+    assert text_of(W.tokenized_text_writer(), golden["reader_tokenized"], "a.txt") == golden["writer_tokenized"]
+    assert text_of(W.UtfPlainTextWriter, golden["reader_tokenized"], "a2.txt") == golden["writer_tokenized"]
+    # reader -> writer round trip of the t2t tokenisation reproduces the (stripped) lines
+    assert text_of(W.t2t_tokenized_text_writer(), golden["reader_t2t"], "b.txt") == golden["writer_t2t"]
+    assert text_of(W.text_writer(), ["x y", 3, 4.5], "c.txt") == golden["writer_plain"]
+    assert text_of(AutoWriter, [["a", "b"], ["c"]], "d.txt") == golden["writer_auto_tokens"]
+    assert text_of(AutoWriter, [1.5, 2.5], "e.txt") == golden["writer_auto_plain"]
+    AutoWriter(str(tmp_path / "f"), [{"x": np.ones((2, 3)), "y": np.zeros(4)}, {"x": np.ones((2, 3)), "y": np.ones(4)}])
+    loaded = np.load(str(tmp_path / "f.npz"))
+    assert {k: list(loaded[k].shape) for k in loaded.files} == golden["writer_auto_npz"]
+    AutoWriter(str(tmp_path / "g"), np.arange(6).reshape(2, 3))
+    assert np.load(str(tmp_path / "g.npy")).tolist() == golden["writer_auto_npy"]
+    # per-example arrays of different length (bucketed batches) still save
+    AutoWriter(str(tmp_path / "h"), [np.ones(3), np.ones(5)])
+    assert len(np.load(str(tmp_path / "h.npy"), allow_pickle=True)) == 2
