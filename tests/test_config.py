@@ -123,3 +123,25 @@ def test_tf_names_used_by_reference_configs_resolve():
     for name in ("tf.contrib.opt.LazyAdamOptimizer", "tf.train.AdamOptimizer",
                  "tf.random_uniform_initializer", "tf.tanh"):
         assert ClassSymbol(name).create() is not None
+
+
+def test_builder_matches_reference_on_toy_plugin():
+    """Object graphs built by the reference's own config/builder.py (golden/make_builder_golden.py)
+    from INIs over tests/golden/toy_plugin/nmtoy.py: default names, shared references, attribute
+    chains, tuples, callables, unused sections."""
+    import json
+    import sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    sys.path.insert(0, os.path.join(here, "golden", "toy_plugin"))
+    try:
+        import nmtoy
+        golden = json.load(open(os.path.join(here, "golden", "builder_golden.json")))
+        for name, text in golden["inis"].items():
+            _raw, parsed = parsing.parse_file(text.strip().splitlines(keepends=True))
+            model, objects = build_config(parsed, set())
+            seen = {}
+            got = {k: nmtoy.describe(v, seen) for k, v in sorted(model.items())}
+            assert got == golden[name]["model"], name
+            assert sorted(objects) == golden[name]["objects"], name
+    finally:
+        sys.path.pop(0)
