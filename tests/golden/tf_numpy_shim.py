@@ -1,0 +1,196 @@
+"""A numpy stand-in for the handful of TensorFlow-1 ops that the *pure* functions of the reference's
+hot path use, so that those functions - the reference's own code, imported from /root/reference - can
+be executed in this container and their outputs committed as golden vectors.
+
+What this pins and what it does not: the executed code is the reference's (op order, constants,
+masking rules, reshapes); the semantics of each TF op are restated here in numpy from the TF-1.12
+documentation.  Every op below is a one-liner over numpy, fp32 in / fp32 out.
+
+Used only by tests/golden/make_tf_shim_golden.py.
+"""
+import contextlib
+import sys
+import types
+
+import numpy as np
+
+
+class Shape(tuple):
+    """What `tensor.shape` / `get_shape()` return: a tuple with `.as_list()` and `.ndims`."""
+
+    def as_list(self):
+        return list(self)
+
+    @property
+    def ndims(self):
+        return len(self)
+
+    @property
+    def dims(self):
+        return list(self)
+
+
+class T(np.ndarray):
+    """ndarray whose `.shape` behaves like a TensorShape."""
+
+    @property
+    def shape(self):  # pylint: disable=invalid-overridden-method
+        return Shape(np.ndarray.shape.__get__(self))
+
+    def get_shape(self):
+        return self.shape
+
+    def set_shape(self, _shape):
+        return None
+
+
+def t(x, dtype=None):
+    return np.asarray(x, dtype=dtype).view(T)
+
+
+class _Missing:
+    """Anything of TF that is touched at import time only (annotations, default arguments)."""
+
+    def __init__(self, name):
+        self._name = name
+
+    def __getattr__(self, item):
+        return _Missing(self._name + "." + item)
+
+    def __call__(self, *args, **kwargs):
+        return _Missing(self._name + "()")
+
+    def __getitem__(self, item):
+        return self
+
+    def __mro_entries__(self, bases):
+        return (object,)
+
+
+class _Namespace(types.ModuleType):
+    def __getattr__(self, item):
+        return _Missing(self.__name__ + "." + item)
+
+
+VARIABLES = {}      # full variable name -> numpy array (layer_norm gamma / beta ...)
+DENSE = {}          # dense layer name -> (kernel, bias or None)
+_scope = []
+GLOBAL_STEP = [0]
+
+
+@contextlib.contextmanager
+def _scope_cm(name, *args, **kwargs):
+    _scope.append(name if isinstance(name, str) else "")
+    try:
+        yield
+    finally:
+        _scope.pop()
+
+
+def _get_variable(name, shape=None, dtype=None, initializer=None, **kwargs):
+    full = "/".join([s for s in _scope if s] + [name])
+    if full not in VARIABLES:
+        raise KeyError("variable '{}' was not provided to the shim".format(full))
+    return t(VARIABLES[full], np.float32)
+
+
+def _dense(inputs, units, activation=None, use_bias=True, name=None, **kwargs):
+    kernel, bias = DENSE[name]
+    assert kernel.shape[1] == units
+    out = np.asarray(inputs) @ kernel
+    if use_bias and bias is not None:
+        out = out + bias
+    out = t(out, np.float32)
+    return activation(out) if activation is not None else out
+
+
+def _matrix_band_part(x, lower, upper):
+    rows, cols = x.shape[-2:]
+    i, j = np.arange(rows)[:, None], np.arange(cols)[None, :]
+    keep = ((lower < 0) | (i - j <= lower)) & ((upper < 0) | (j - i <= upper))
+    return t(np.asarray(x) * keep)
+
+
+def _softmax(x, axis=-1):
+    x = np.asarray(x, np.float32)
+    e = np.exp(x - x.max(axis=axis, keepdims=True))
+    return t(e / e.sum(axis=axis, keepdims=True), np.float32)
+
+
+def _max_pool(value, ksize, strides, padding):
+    """NHWC max pooling, only the window == stride, exact-division case the maxout layer uses."""
+    assert list(ksize) == list(strides) and padding == "SAME"
+    n, h, w, c = value.shape
+    kh, kw = ksize[1], ksize[2]
+    assert h % kh == 0 and w % kw == 0
+    x = np.asarray(value).reshape(n, h // kh, kh, w // kw, kw, c)
+    return t(x.max(axis=(2, 4)))
+
+
+def _gather_nd(params, indices):
+    indices = np.asarray(indices)
+    return t(np.asarray(params)[tuple(indices[..., k] for k in range(indices.shape[-1]))])
+
+
+def _pad(x, paddings):
+    return t(np.pad(np.asarray(x), [(int(a), int(b)) for a, b in paddings]))
+
+
+def install():
+    """Put the shim into sys.modules as `tensorflow` and return it."""
+    tf = _Namespace("tensorflow")
+    tf.float32, tf.int32, tf.int64, tf.bool = np.float32, np.int32, np.int64, np.bool_
+    tf.Tensor = T
+    tf.TensorShape = Shape
+    tf.to_float = lambda x: t(x, np.float32)
+    tf.to_int32 = lambda x: t(x, np.int32)
+    tf.to_int64 = lambda x: t(x, np.int64)
+    tf.range = lambda *a, dtype=None: t(np.arange(*[int(v) for v in a]), dtype or np.int32)
+    tf.exp = lambda x: t(np.exp(np.asarray(x, np.float32)), np.float32)
+    tf.sin = lambda x: t(np.sin(np.asarray(x, np.float32)), np.float32)
+    tf.cos = lambda x: t(np.cos(np.asarray(x, np.float32)), np.float32)
+    tf.sqrt = lambda x: t(np.sqrt(np.asarray(x, np.float32)), np.float32)
+    tf.rsqrt = lambda x: t(1.0 / np.sqrt(np.asarray(x, np.float32)), np.float32)
+    tf.square = lambda x: t(np.square(np.asarray(x)))
+    tf.minimum = lambda a, b: t(np.minimum(a, b))
+    tf.mod = lambda a, b: np.mod(a, b)
+    tf.expand_dims = lambda x, axis: t(np.expand_dims(np.asarray(x), axis))
+    tf.concat = lambda values, axis: t(np.concatenate([np.asarray(v) for v in values], axis=axis))
+    tf.pad = _pad
+    tf.reshape = lambda x, shape: t(np.reshape(np.asarray(x), [int(s) for s in shape]))
+    tf.shape = lambda x: Shape(np.asarray(x).shape)
+    tf.transpose = lambda x, perm=None: t(np.transpose(np.asarray(x), perm))
+    tf.ones_like = lambda x: t(np.ones_like(np.asarray(x)))
+    tf.matrix_band_part = _matrix_band_part
+    tf.equal = lambda a, b: t(np.equal(a, b))
+    tf.fill = lambda dims, value: t(np.full([int(d) for d in dims], value, np.float32))
+    tf.where = lambda cond, a, b: t(np.where(np.asarray(cond), np.asarray(a), np.asarray(b)))
+    tf.matmul = lambda a, b, transpose_b=False: t(
+        np.matmul(np.asarray(a), np.swapaxes(np.asarray(b), -1, -2) if transpose_b else np.asarray(b)))
+    tf.identity = lambda x, name=None: x
+    tf.convert_to_tensor = lambda x, *a, **k: x if isinstance(x, T) else t(x)
+    tf.gather_nd = _gather_nd
+    tf.reduce_mean = lambda x, axis=None, keepdims=False: t(
+        np.mean(np.asarray(x), axis=tuple(axis) if isinstance(axis, list) else axis, keepdims=keepdims))
+    tf.variable_scope = _scope_cm
+    tf.name_scope = _scope_cm
+    tf.get_variable = _get_variable
+    tf.get_variable_scope = lambda: types.SimpleNamespace(name="/".join(s for s in _scope if s))
+    tf.ones_initializer = lambda: None
+    tf.zeros_initializer = lambda: None
+    tf.AUTO_REUSE = object()
+    tf.nn = _Namespace("tensorflow.nn")
+    tf.nn.softmax = _softmax
+    tf.nn.max_pool = _max_pool
+    tf.nn.relu = lambda x: t(np.maximum(np.asarray(x), 0))
+    tf.layers = _Namespace("tensorflow.layers")
+    tf.layers.dense = _dense
+    tf.train = _Namespace("tensorflow.train")
+    tf.train.get_or_create_global_step = lambda: t(GLOBAL_STEP[0], np.int64)
+    tf.contrib = _Namespace("tensorflow.contrib")
+    sys.modules["tensorflow"] = tf
+    for sub in ("tensorflow.contrib", "tensorflow.contrib.slim", "tensorflow.contrib.slim.nets",
+                "tensorflow.python", "tensorflow.python.framework", "tensorflow.contrib.tensorboard",
+                "tensorflow.contrib.tensorboard.plugins"):
+        sys.modules[sub] = _Namespace(sub)
+    return tf

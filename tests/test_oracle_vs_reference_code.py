@@ -1,0 +1,89 @@
+"""The oracle against outputs of the reference's OWN functions (tests/golden/tf_shim_golden.npz:
+neuralmonkey/{encoders/transformer,attention/scaled_dot_product,tf_utils,nn/projection,functions,
+decoders/beam_search_decoder}.py executed over a numpy stand-in for the TensorFlow ops they call -
+tests/golden/tf_numpy_shim.py, make_tf_shim_golden.py).  This pins the oracle's restatement of the
+op order, constants, masking rules and reshapes to the reference's code itself."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import nm_oracle as O
+
+G = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "tf_shim_golden.npz"))
+
+
+def _t(name):
+    return torch.from_numpy(G[name])
+
+
+def test_position_signal():
+    for dim, length in ((6, 7), (512, 50), (9, 4)):
+        want = G["pos_{}_{}".format(dim, length)]
+        got = O.position_signal(dim, length).numpy()
+        # fp32 exp / sin of arguments up to ~50: libm differences of an ulp in the argument show up as ~1e-5
+        assert got.shape == want.shape and np.abs(got - want).max() < 2e-5
+
+
+def test_attention_masks_and_single_head():
+    q, k, v, mask = _t("att_q"), _t("att_k"), _t("att_v"), _t("att_mask")
+    ctx, weights = O.multihead_attention({}, "", q, k, v, mask, heads=1)
+    assert np.abs(ctx.numpy() - G["att1_ctx"]).max() < 2e-6
+    assert np.abs(weights.numpy() - G["att1_w"]).max() < 2e-6
+    # padded keys get probability exactly zero, as in the reference's e*m + (1-m)*(-1e9)
+    assert float(weights[1, 0, :, 3:].abs().max()) == 0.0 and float(G["att1_w"][1, 0, :, 3:].max()) == 0.0
+    # the two masking helpers, applied to given energies
+    e = _t("energies")
+    m4 = mask.unsqueeze(1).unsqueeze(1)
+    assert np.array_equal((e * m4 + (1.0 - m4) * -1e9).numpy(), G["mask_energies"])
+    sq = _t("energies_sq")
+    keep = torch.tril(torch.ones(5, 5, dtype=torch.bool))
+    assert np.array_equal(torch.where(keep, sq, torch.full_like(sq, -1e9)).numpy(), G["mask_future"])
+    assert np.array_equal(O._split_for_heads(q, 3, 4).numpy(), G["split_heads"])
+
+
+def test_multi_head_cross_and_masked_self_attention():
+    p = {"s/{}/kernel".format(n): _t("dense_" + n) for n in ("query_proj", "keys_proj", "vals_proj", "output_proj")}
+    ctx, weights = O.multihead_attention(p, "s", _t("att_q"), _t("att_k"), _t("att_v"), _t("att_mask"), heads=3)
+    assert np.abs(ctx.numpy() - G["att3_ctx"]).max() < 5e-6
+    assert np.abs(weights.numpy() - G["att3_w"]).max() < 2e-6
+    qs = _t("self_q")
+    ctx, weights = O.multihead_attention(p, "s", qs, qs, qs, _t("self_mask"), heads=3, masked=True)
+    assert np.abs(ctx.numpy() - G["self_ctx"]).max() < 5e-6
+    assert np.abs(weights.numpy() - G["self_w"]).max() < 2e-6
+
+
+def test_layer_norm_and_maxout():
+    got = O.layer_norm(_t("ln_x"), _t("ln_gamma"), _t("ln_beta")).numpy()
+    assert np.abs(got - G["ln_y"]).max() < 5e-6
+    spec = O.RNNDecoderSpec("d", "a", 5, "maxout", False)
+    pre = "d/attention_decoder/MaxoutProjection/MaxoutProjection/"
+    p = {pre + "kernel": _t("maxout_kernel"), pre + "bias": _t("maxout_bias")}
+    x = _t("maxout_in")
+    got = O.output_projection(p, spec, x[:, :3], x[:, 3:5], x[:, 5:]).numpy()   # concat of the three = x
+    assert np.abs(got - G["maxout_out"]).max() < 2e-6
+
+
+def test_beam_reordering_helpers():
+    """gather_flat (the per-hypothesis re-ordering of every decoder feedable), partial_transpose and
+    append_tensor as the oracle's beam search uses them."""
+    state, beams = _t("gf_state"), torch.from_numpy(G["gf_beam_ids"]).long()
+    batch, beam = beams.shape
+    flat = (torch.arange(batch).unsqueeze(1) * beam + beams).reshape(-1)       # oracle: beam_search()
+    assert np.array_equal(state[flat].numpy(), G["gf_out"])
+    assert np.array_equal(_t("pt_in").transpose(0, 1).numpy(), G["pt_out"])
+    hist = _t("pt_in")
+    assert np.array_equal(torch.cat([hist, (hist[0] * 2).unsqueeze(0)], 0).numpy(), G["append_out"])
+
+
+def test_length_penalty_and_noam_schedule():
+    from neuralmonkey_b200.functions import noam_decay
+    lengths = torch.from_numpy(G["lp_lengths"])
+    for alpha in (0.0, 0.6, 1.0):
+        got = O.length_penalty(lengths, alpha).numpy()
+        want = G["lp_{}".format(alpha)]
+        assert np.abs(got - want).max() <= 2.4e-7 * np.abs(want).max()        # within 1 ulp of fp32 pow
+    sched = noam_decay(0.2, 6, 111)
+    for step, want in zip(G["noam_steps"].tolist(), G["noam_values"].tolist()):
+        assert sched(step) == pytest.approx(want, rel=1e-6, abs=1e-12)
