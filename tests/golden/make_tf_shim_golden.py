@@ -29,7 +29,7 @@ def main():
     out = {}
 
     def f32(*shape, scale=1.0):
-        return (rng.randn(*shape) * scale).astype(np.float32)
+        return np.asarray(rng.randn(*shape) * scale, dtype=np.float32)
 
     # ---- position signal ---------------------------------------------------------------------
     from neuralmonkey.encoders.transformer import position_signal
@@ -101,6 +101,50 @@ def main():
         dummy = types.SimpleNamespace(length_normalization=alpha)
         out["lp_{}".format(alpha)] = np.asarray(BeamSearchDecoder._length_penalty(dummy, shim.t(lengths)))
     out["lp_lengths"] = lengths
+    # ---- Bahdanau attention: Attention.attention (attention/feed_forward.py:125-166) -----------------
+    from neuralmonkey.attention.feed_forward import Attention
+    from neuralmonkey.attention.namedtuples import AttentionLoopState
+    states = f32(3, 6, 10)
+    amask = np.array([[1, 1, 1, 1, 1, 1], [1, 1, 1, 0, 0, 0], [1, 0, 0, 0, 0, 0]], np.float32)
+    query = f32(3, 8)
+    for name, shape in (("Attention/attn_query_projection", (8, 7)), ("attn_key_projection", (10, 7)),
+                        ("attn_similarity_v", (7,)), ("attn_projection_bias", (7,)), ("attn_bias", ())):
+        shim.VARIABLES["att/" + name] = f32(*shape, scale=0.5)
+        out["bah_" + name.split("/")[-1]] = shim.VARIABLES["att/" + name]
+    out.update({"bah_states": states, "bah_mask": amask, "bah_query": query})
+    for label, use_mask in (("masked", True), ("nomask", False)):
+        att = object.__new__(Attention)
+        att._variable_scope = shim.VarScope("att")
+        att._reuse = None
+        att._name = "att"
+        att._state_size = 7
+        att._attention_states_cached_placeholder = shim.t(states)
+        att._attention_mask_cached_placeholder = shim.t(amask) if use_mask else None
+        empty = AttentionLoopState(contexts=shim.t(np.zeros((0, 3, 10), np.float32)),
+                                   weights=shim.t(np.zeros((0, 3, 6), np.float32)))
+        ctx, loop_state = att.attention(shim.t(query), None, None, empty)
+        out["bah_ctx_" + label] = np.asarray(ctx)
+        out["bah_w_" + label] = np.asarray(loop_state.weights)[0]
+
+    # ---- decoder projections (decoders/encoder_projection.py, decoders/output_projection.py) -------------
+    from neuralmonkey.decoders.encoder_projection import linear_encoder_projection
+    from neuralmonkey.decoders.output_projection import maxout_output, nonlinear_output
+    enc_a, enc_b = f32(4, 6), f32(4, 3)
+    shim.DENSE["encoders_projection"] = (f32(9, 5, scale=0.4), f32(5, scale=0.4))
+    init = linear_encoder_projection(1.0)(None, 5, [types.SimpleNamespace(output=shim.t(enc_a)),
+                                                    types.SimpleNamespace(output=shim.t(enc_b))])
+    out.update({"proj_enc_a": enc_a, "proj_enc_b": enc_b, "proj_kernel": shim.DENSE["encoders_projection"][0],
+                "proj_bias": shim.DENSE["encoders_projection"][1], "proj_init": np.asarray(init)})
+    cell, emb, ctx1 = f32(4, 5), f32(4, 3), f32(4, 6)
+    shim.DENSE[None] = (f32(14, 4, scale=0.4), f32(4, scale=0.4))          # tf.layers.dense without a name
+    fn, size = nonlinear_output(4)
+    out.update({"op_cell": cell, "op_emb": emb, "op_ctx": ctx1, "op_tanh_kernel": shim.DENSE[None][0],
+                "op_tanh_bias": shim.DENSE[None][1],
+                "op_tanh_out": np.asarray(fn(shim.t(cell), shim.t(emb), [shim.t(ctx1)], None))})
+    shim.DENSE["MaxoutProjection"] = (f32(14, 8, scale=0.4), f32(8, scale=0.4))
+    fn, size = maxout_output(4)
+    out.update({"op_max_kernel": shim.DENSE["MaxoutProjection"][0], "op_max_bias": shim.DENSE["MaxoutProjection"][1],
+                "op_max_out": np.asarray(fn(shim.t(cell), shim.t(emb), [shim.t(ctx1)], None))})
     np.savez_compressed(os.path.join(HERE, "tf_shim_golden.npz"), **out)
     print(sorted(out))
 

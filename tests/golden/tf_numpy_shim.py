@@ -15,8 +15,26 @@ import types
 import numpy as np
 
 
+class Dim(int):
+    """A static dimension: an int with the `.value` TF-1 dimensions carry."""
+
+    @property
+    def value(self):
+        return int(self)
+
+
+class VarScope:
+    """What a model part keeps in `_variable_scope`: re-entering it makes its name the full scope."""
+
+    def __init__(self, name):
+        self.name, self.reuse, self.original_name_scope = name, False, name + "/"
+
+
 class Shape(tuple):
     """What `tensor.shape` / `get_shape()` return: a tuple with `.as_list()` and `.ndims`."""
+
+    def __new__(cls, dims=()):
+        return super().__new__(cls, [Dim(d) for d in dims])
 
     def as_list(self):
         return list(self)
@@ -80,11 +98,26 @@ GLOBAL_STEP = [0]
 
 @contextlib.contextmanager
 def _scope_cm(name, *args, **kwargs):
-    _scope.append(name if isinstance(name, str) else "")
+    saved = list(_scope)
+    if isinstance(name, VarScope):
+        _scope[:] = [name.name]            # a scope OBJECT replaces the current scope
+    else:
+        _scope.append(name if isinstance(name, str) else "")
     try:
         yield
     finally:
-        _scope.pop()
+        _scope[:] = saved
+
+
+@contextlib.contextmanager
+def _name_scope_cm(*args, **kwargs):
+    yield                                  # op names do not matter here
+
+
+def _conv2d_1x1(value, filters, strides, padding):
+    """tf.nn.conv2d for the 1x1 / stride-1 case the attention key projection uses (NHWC x HWIO)."""
+    assert filters.shape[0] == 1 and filters.shape[1] == 1 and list(strides) == [1, 1, 1, 1]
+    return t(np.asarray(value) @ np.asarray(filters)[0, 0], np.float32)
 
 
 def _get_variable(name, shape=None, dtype=None, initializer=None, **kwargs):
@@ -152,6 +185,11 @@ def install():
     tf.sqrt = lambda x: t(np.sqrt(np.asarray(x, np.float32)), np.float32)
     tf.rsqrt = lambda x: t(1.0 / np.sqrt(np.asarray(x, np.float32)), np.float32)
     tf.square = lambda x: t(np.square(np.asarray(x)))
+    tf.tanh = lambda x: t(np.tanh(np.asarray(x, np.float32)), np.float32)
+    tf.zeros = lambda shape, dtype=None: t(np.zeros([int(d) for d in shape], np.float32))
+    tf.reduce_sum = lambda x, axis=None, keepdims=False: t(
+        np.sum(np.asarray(x), axis=tuple(axis) if isinstance(axis, list) else axis, keepdims=keepdims))
+    tf.Variable = T
     tf.minimum = lambda a, b: t(np.minimum(a, b))
     tf.mod = lambda a, b: np.mod(a, b)
     tf.expand_dims = lambda x, axis: t(np.expand_dims(np.asarray(x), axis))
@@ -173,7 +211,7 @@ def install():
     tf.reduce_mean = lambda x, axis=None, keepdims=False: t(
         np.mean(np.asarray(x), axis=tuple(axis) if isinstance(axis, list) else axis, keepdims=keepdims))
     tf.variable_scope = _scope_cm
-    tf.name_scope = _scope_cm
+    tf.name_scope = _name_scope_cm
     tf.get_variable = _get_variable
     tf.get_variable_scope = lambda: types.SimpleNamespace(name="/".join(s for s in _scope if s))
     tf.ones_initializer = lambda: None
@@ -182,6 +220,7 @@ def install():
     tf.nn = _Namespace("tensorflow.nn")
     tf.nn.softmax = _softmax
     tf.nn.max_pool = _max_pool
+    tf.nn.conv2d = _conv2d_1x1
     tf.nn.relu = lambda x: t(np.maximum(np.asarray(x), 0))
     tf.layers = _Namespace("tensorflow.layers")
     tf.layers.dense = _dense

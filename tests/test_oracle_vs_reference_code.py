@@ -87,3 +87,36 @@ def test_length_penalty_and_noam_schedule():
     sched = noam_decay(0.2, 6, 111)
     for step, want in zip(G["noam_steps"].tolist(), G["noam_values"].tolist()):
         assert sched(step) == pytest.approx(want, rel=1e-6, abs=1e-12)
+
+
+def test_bahdanau_attention_step():
+    """Attention.attention (attention/feed_forward.py:125-166): query projection + bias, tanh energies,
+    softmax over ALL positions, then mask and renormalise with +1e-8; context over the states."""
+    p = {"a/Attention/attn_query_projection": _t("bah_attn_query_projection"),
+         "a/attn_key_projection": _t("bah_attn_key_projection"), "a/attn_similarity_v": _t("bah_attn_similarity_v"),
+         "a/attn_projection_bias": _t("bah_attn_projection_bias"), "a/attn_bias": _t("bah_attn_bias")}
+    states, query = _t("bah_states"), _t("bah_query")
+    hidden = O.bahdanau_precompute(p, "a", states)
+    for label, mask in (("masked", _t("bah_mask")), ("nomask", None)):
+        ctx, weights = O.bahdanau_step(p, "a", query, hidden, states, mask)
+        assert np.abs(weights.numpy() - G["bah_w_" + label]).max() < 2e-6, label
+        assert np.abs(ctx.numpy() - G["bah_ctx_" + label]).max() < 5e-6, label
+    # a sentence of length 1 puts (almost) all weight on its only position: 1 / (1 + 1e-8 / w)
+    assert abs(float(G["bah_w_masked"][2, 0]) - 1.0) < 1e-6 and float(np.abs(G["bah_w_masked"][2, 1:]).max()) == 0.0
+
+
+def test_decoder_projections():
+    """linear_encoder_projection (encoder outputs concatenated in list order -> dense) and the two
+    output projections (concat of [cell output, embedded input, contexts] -> dense+tanh / maxout)."""
+    spec_t = O.RNNDecoderSpec("d", "a", 5, "tanh", False)
+    spec_m = O.RNNDecoderSpec("d", "a", 5, "maxout", False)
+    p = {"d/initial_state/encoders_projection/kernel": _t("proj_kernel"),
+         "d/initial_state/encoders_projection/bias": _t("proj_bias"),
+         "d/attention_decoder/dense/kernel": _t("op_tanh_kernel"), "d/attention_decoder/dense/bias": _t("op_tanh_bias"),
+         "d/attention_decoder/MaxoutProjection/MaxoutProjection/kernel": _t("op_max_kernel"),
+         "d/attention_decoder/MaxoutProjection/MaxoutProjection/bias": _t("op_max_bias")}
+    init = O.decoder_initial_state(p, spec_t, torch.cat([_t("proj_enc_a"), _t("proj_enc_b")], 1))
+    assert np.abs(init.numpy() - G["proj_init"]).max() < 2e-6
+    cell, emb, ctx = _t("op_cell"), _t("op_emb"), _t("op_ctx")
+    assert np.abs(O.output_projection(p, spec_t, cell, emb, ctx).numpy() - G["op_tanh_out"]).max() < 2e-6
+    assert np.abs(O.output_projection(p, spec_m, cell, emb, ctx).numpy() - G["op_max_out"]).max() < 2e-6
