@@ -145,6 +145,63 @@ def main():
     fn, size = maxout_output(4)
     out.update({"op_max_kernel": shim.DENSE["MaxoutProjection"][0], "op_max_bias": shim.DENSE["MaxoutProjection"][1],
                 "op_max_out": np.asarray(fn(shim.t(cell), shim.t(emb), [shim.t(ctx1)], None))})
+    # ---- whole Transformer stacks: TransformerEncoder.temporal_states / output and
+    #      TransformerDecoder.layer(depth, ...) with every variable looked up by its full TF name ----------
+    from neuralmonkey.encoders.transformer import TransformerEncoder
+    from neuralmonkey.decoders.transformer import TransformerDecoder
+    dim, ff, depth, heads = 12, 20, 2, 3
+
+    def ln_vars(scope):
+        shim.VARIABLES[scope + "/LayerNorm/gamma"] = 1.0 + f32(dim, scale=0.2)
+        shim.VARIABLES[scope + "/LayerNorm/beta"] = f32(dim, scale=0.2)
+
+    def att_vars(scope):
+        for name in ("query_proj", "keys_proj", "vals_proj", "output_proj"):
+            shim.VARIABLES["{}/{}/kernel".format(scope, name)] = f32(dim, dim, scale=0.3)
+
+    def ff_vars(scope):
+        ln_vars(scope)
+        shim.VARIABLES[scope + "/hidden_state/kernel"], shim.VARIABLES[scope + "/hidden_state/bias"] = f32(dim, ff, scale=0.3), f32(ff, scale=0.2)
+        shim.VARIABLES[scope + "/output/kernel"], shim.VARIABLES[scope + "/output/bias"] = f32(ff, dim, scale=0.3), f32(dim, scale=0.2)
+
+    first_new = len(shim.VARIABLES)
+    for i in range(depth):
+        ln_vars("tenc/layer_{}/self_attention".format(i)); att_vars("tenc/layer_{}/self_attention".format(i))
+        ff_vars("tenc/layer_{}/feedforward".format(i))
+        ln_vars("tdec/layer_{}/self_attention".format(i)); att_vars("tdec/layer_{}/self_attention".format(i))
+        ln_vars("tdec/layer_{}/encdec_attention/enc_0".format(i)); att_vars("tdec/layer_{}/encdec_attention/enc_0".format(i))
+        ff_vars("tdec/layer_{}/feedforward".format(i))
+    ln_vars("tenc")
+    ln_vars("tdec")
+    for name in list(shim.VARIABLES)[first_new:]:
+        out["tv::" + name] = shim.VARIABLES[name]
+    enc_in = f32(3, 6, dim)
+    enc_mask = np.array([[1, 1, 1, 1, 1, 1], [1, 1, 1, 1, 0, 0], [1, 0, 0, 0, 0, 0]], np.float32)
+    enc = object.__new__(TransformerEncoder)
+    enc.__dict__.update(dict(
+        input_sequence=types.SimpleNamespace(temporal_states=shim.t(enc_in), temporal_mask=shim.t(enc_mask), dimension=dim),
+        ff_hidden_size=ff, depth=depth, n_heads=heads, dropout_keep_prob=1.0, attention_dropout_keep_prob=1.0,
+        target_space_id=None, use_att_transform_bias=False, use_positional_encoding=True,
+        input_for_cross_attention=None, n_cross_att_heads=None, train_mode=None,
+        _variable_scope=shim.VarScope("tenc"), _reuse=None, _name="tenc"))
+    shim.USED[:] = []
+    enc_states = np.asarray(enc.temporal_states)
+    out.update({"tenc_in": enc_in, "tenc_mask": enc_mask, "tenc_states": enc_states,
+                "tenc_output": np.asarray(enc.output)})
+    dec = object.__new__(TransformerDecoder)
+    dec.__dict__.update(dict(
+        encoders=[enc], ff_hidden_size=ff, n_heads_self=heads, n_heads_enc=[2 if dim % 2 == 0 else heads], depth=depth,
+        attention_dropout_keep_prob=[1.0], self_att_dropout_keep_prob=1.0, dropout_keep_prob=1.0,
+        use_att_transform_bias=False, attention_combination_strategy="serial", n_heads_hier=None,
+        encoder_states=lambda: [shim.t(enc_states)], encoder_masks=lambda: [shim.t(enc_mask)],
+        _embedding_size=dim, embeddings_source=None, train_mode=None,
+        _variable_scope=shim.VarScope("tdec"), _reuse=None, _name="tdec"))
+    dec_in = f32(3, 5, dim)
+    dec_mask = np.array([[1, 1, 1, 1, 1], [1, 1, 1, 0, 0], [1, 1, 0, 0, 0]], np.float32)
+    with dec.use_scope():
+        last = dec.layer(depth, shim.t(dec_in), shim.t(dec_mask))
+    out.update({"tdec_in": dec_in, "tdec_mask": dec_mask, "tdec_states": np.asarray(last.temporal_states)})
+    out["transformer_dense_names"] = np.array(sorted(set(shim.USED)))
     np.savez_compressed(os.path.join(HERE, "tf_shim_golden.npz"), **out)
     print(sorted(out))
 

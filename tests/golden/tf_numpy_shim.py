@@ -61,6 +61,16 @@ class T(np.ndarray):
     def set_shape(self, _shape):
         return None
 
+    # TF tensors are immutable: `x += y` rebinds the name, it must not write into x's buffer
+    def __iadd__(self, other):
+        return self + other
+
+    def __imul__(self, other):
+        return self * other
+
+    def __isub__(self, other):
+        return self - other
+
 
 def t(x, dtype=None):
     return np.asarray(x, dtype=dtype).view(T)
@@ -92,6 +102,7 @@ class _Namespace(types.ModuleType):
 
 VARIABLES = {}      # full variable name -> numpy array (layer_norm gamma / beta ...)
 DENSE = {}          # dense layer name -> (kernel, bias or None)
+USED = []           # full names of the dense kernels that were looked up (checks the naming scheme)
 _scope = []
 GLOBAL_STEP = [0]
 
@@ -120,15 +131,26 @@ def _conv2d_1x1(value, filters, strides, padding):
     return t(np.asarray(value) @ np.asarray(filters)[0, 0], np.float32)
 
 
+def _full_name(name):
+    return "/".join([s for s in _scope if s] + [name])
+
+
 def _get_variable(name, shape=None, dtype=None, initializer=None, **kwargs):
-    full = "/".join([s for s in _scope if s] + [name])
+    full = _full_name(name)
     if full not in VARIABLES:
         raise KeyError("variable '{}' was not provided to the shim".format(full))
     return t(VARIABLES[full], np.float32)
 
 
 def _dense(inputs, units, activation=None, use_bias=True, name=None, **kwargs):
-    kernel, bias = DENSE[name]
+    # a layer is looked up by its full TF variable name first (VARIABLES["<scope>/<name>/kernel"]),
+    # then by its bare name in DENSE (the early, scope-less fixtures)
+    full = _full_name(name or "dense")
+    if full + "/kernel" in VARIABLES:
+        kernel, bias = VARIABLES[full + "/kernel"], VARIABLES.get(full + "/bias")
+        USED.append(full + "/kernel")
+    else:
+        kernel, bias = DENSE[name]
     assert kernel.shape[1] == units
     out = np.asarray(inputs) @ kernel
     if use_bias and bias is not None:
