@@ -202,6 +202,67 @@ def main():
         last = dec.layer(depth, shim.t(dec_in), shim.t(dec_mask))
     out.update({"tdec_in": dec_in, "tdec_mask": dec_mask, "tdec_states": np.asarray(last.temporal_states)})
     out["transformer_dense_names"] = np.array(sorted(set(shim.USED)))
+    # ---- one beam search step: BeamSearchDecoder.get_body()() (decoders/beam_search_decoder.py:385-558)
+    #      around a stand-in parent decoder whose body returns given logits -----------------------------------
+    from neuralmonkey.decoders import beam_search_decoder as bsd
+    from neuralmonkey.decoders.autoregressive import (DecoderConstants, DecoderFeedables, DecoderHistories,
+                                                      LoopState)
+    bsz, beam, vocab_size, edim = 3, 4, 9, 5
+    rows = bsz * beam
+    emb_table = f32(vocab_size, edim)
+    next_logits = f32(rows, vocab_size, scale=2.0)
+
+    def decoder_body(*args):
+        ls = LoopState(*args)
+        hist = ls.histories._replace(logits=shim.t(np.concatenate(
+            [np.asarray(ls.histories.logits), next_logits[None]], 0)))
+        return LoopState(histories=hist, constants=ls.constants,
+                         feedables=ls.feedables._replace(step=ls.feedables.step + 1))
+
+    parent = types.SimpleNamespace(get_body=lambda train_mode: decoder_body, vocabulary=list(range(vocab_size)),
+                                   embed_input_symbols=lambda ids: shim.t(emb_table[np.asarray(ids)]))
+    for case, alpha in (("a", 0.6), ("b", 1.0)):
+        dec = object.__new__(bsd.BeamSearchDecoder)
+        dec.__dict__.update(dict(parent_decoder=parent, beam_size=beam, batch_size=bsz, length_normalization=alpha,
+                                 max_steps_int=10, _variable_scope=shim.VarScope("bs"), _reuse=None, _name="bs"))
+        prev_logprobs = np.log(np.asarray(shim._softmax(f32(bsz, beam, vocab_size, scale=2.0))))
+        if case == "b":                              # exact ties inside a sentence: top_k keeps the lower index
+            prev_logprobs[0, 1] = prev_logprobs[0, 0]
+        logprob_sum = -np.abs(f32(bsz, beam))
+        if case == "b":
+            logprob_sum[0, 1] = logprob_sum[0, 0]
+        lengths = rng.randint(0, 6, size=(bsz, beam)).astype(np.int32)
+        if case == "b":
+            lengths[0, 1] = lengths[0, 0]
+        finished = np.array([[0, 1, 0, 0], [0, 0, 0, 1], [1, 1, 0, 0]], bool)
+        token_ids = rng.randint(4, vocab_size, size=(3, bsz, beam)).astype(np.int64)
+        state_feed = f32(rows, 6)
+        feedables = DecoderFeedables(step=shim.t(np.int32(3)), finished=shim.t(finished.reshape(-1)),
+                                     embedded_input=shim.t(f32(rows, edim)), other=[shim.t(state_feed)])
+        histories = DecoderHistories(logits=shim.t(f32(3, rows, vocab_size)), output_states=shim.t(f32(3, rows, 2)),
+                                     output_symbols=shim.t(np.zeros((3, rows), np.int64)),
+                                     output_mask=shim.t(np.ones((3, rows), bool)), other=[])
+        loop_state = bsd.BeamSearchLoopState(
+            search_state=bsd.SearchState(logprob_sum=shim.t(logprob_sum), prev_logprobs=shim.t(prev_logprobs),
+                                         lengths=shim.t(lengths), finished=shim.t(finished)),
+            search_results=bsd.SearchResults(scores=shim.t(np.zeros((bsz, beam), np.float32)),
+                                             token_ids=shim.t(token_ids)),
+            decoder_loop_state=LoopState(histories=histories, constants=DecoderConstants(train_inputs=shim.t(np.zeros(1))),
+                                         feedables=feedables))
+        nxt = dec.get_body()(*loop_state)
+        pre = "beam_{}_".format(case)
+        out.update({pre + "alpha": np.float32(alpha), pre + "prev_logprobs": prev_logprobs, pre + "logprob_sum": logprob_sum,
+                    pre + "lengths": lengths, pre + "finished": finished, pre + "token_ids": token_ids,
+                    pre + "state_feed": state_feed, pre + "next_logits": next_logits, pre + "emb_table": emb_table,
+                    pre + "out_scores": np.asarray(nxt.search_results.scores),
+                    pre + "out_token_ids": np.asarray(nxt.search_results.token_ids),
+                    pre + "out_logprob_sum": np.asarray(nxt.search_state.logprob_sum),
+                    pre + "out_lengths": np.asarray(nxt.search_state.lengths),
+                    pre + "out_finished": np.asarray(nxt.search_state.finished),
+                    pre + "out_prev_logprobs": np.asarray(nxt.search_state.prev_logprobs),
+                    pre + "out_state_feed": np.asarray(nxt.decoder_loop_state.feedables.other[0]),
+                    pre + "out_embedded": np.asarray(nxt.decoder_loop_state.feedables.embedded_input),
+                    pre + "out_dec_finished": np.asarray(nxt.decoder_loop_state.feedables.finished)})
     np.savez_compressed(os.path.join(HERE, "tf_shim_golden.npz"), **out)
     print(sorted(out))
 

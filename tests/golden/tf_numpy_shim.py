@@ -191,6 +191,35 @@ def _pad(x, paddings):
     return t(np.pad(np.asarray(x), [(int(a), int(b)) for a, b in paddings]))
 
 
+def _map_structure(fn, *structures):
+    """tf.contrib.framework.nest.map_structure over (named) tuples and lists of tensors."""
+    first = structures[0]
+    if isinstance(first, tuple) and hasattr(first, "_fields"):
+        return type(first)(*[_map_structure(fn, *parts) for parts in zip(*structures)])
+    if isinstance(first, (list, tuple)):
+        return type(first)(_map_structure(fn, *parts) for parts in zip(*structures))
+    return fn(*structures)
+
+
+def _top_k(values, k):
+    """tf.nn.top_k over the last axis: descending, the lower index first among equal values."""
+    values = np.asarray(values)
+    order = np.argsort(-values, axis=-1, kind="stable")[..., :k]
+    return t(np.take_along_axis(values, order, axis=-1)), t(order.astype(np.int32))
+
+
+def _one_hot(index, depth, dtype=np.float32, on_value=1.0, off_value=0.0):
+    out = np.full((depth,), off_value, dtype=dtype)
+    out[int(index)] = on_value
+    return t(out)
+
+
+def _log_softmax(x, axis=-1):
+    x = np.asarray(x, np.float32)
+    shifted = x - x.max(axis=axis, keepdims=True)
+    return t(shifted - np.log(np.exp(shifted).sum(axis=axis, keepdims=True)), np.float32)
+
+
 def install():
     """Put the shim into sys.modules as `tensorflow` and return it."""
     tf = _Namespace("tensorflow")
@@ -213,7 +242,7 @@ def install():
         np.sum(np.asarray(x), axis=tuple(axis) if isinstance(axis, list) else axis, keepdims=keepdims))
     tf.Variable = T
     tf.minimum = lambda a, b: t(np.minimum(a, b))
-    tf.mod = lambda a, b: np.mod(a, b)
+    tf.mod = lambda a, b: t(np.mod(np.asarray(a), b)) if isinstance(a, np.ndarray) else np.mod(a, b)
     tf.expand_dims = lambda x, axis: t(np.expand_dims(np.asarray(x), axis))
     tf.concat = lambda values, axis: t(np.concatenate([np.asarray(v) for v in values], axis=axis))
     tf.pad = _pad
@@ -249,6 +278,21 @@ def install():
     tf.train = _Namespace("tensorflow.train")
     tf.train.get_or_create_global_step = lambda: t(GLOBAL_STEP[0], np.int64)
     tf.contrib = _Namespace("tensorflow.contrib")
+    tf.contrib.framework = _Namespace("tensorflow.contrib.framework")
+    tf.contrib.framework.nest = _Namespace("tensorflow.contrib.framework.nest")
+    tf.contrib.framework.nest.map_structure = _map_structure
+    tf.nn.top_k = _top_k
+    tf.nn.log_softmax = _log_softmax
+    tf.one_hot = _one_hot
+    tf.tile = lambda x, multiples: t(np.tile(np.asarray(x), [int(m) for m in multiples]))
+    tf.stack = lambda values, axis=0: t(np.stack([np.asarray(v) for v in values], axis=axis))
+    tf.div = lambda a, b: t(np.floor_divide(np.asarray(a), b))
+    tf.logical_or = lambda a, b: t(np.logical_or(a, b))
+    tf.logical_not = lambda a: t(np.logical_not(a))
+    tf.logical_and = lambda a, b: t(np.logical_and(a, b))
+    tf.less = lambda a, b: t(np.less(a, b))
+    tf.reduce_all = lambda x: t(np.all(np.asarray(x)))
+    tf.constant = lambda x, dtype=None, **k: t(x, dtype)
     sys.modules["tensorflow"] = tf
     for sub in ("tensorflow.contrib", "tensorflow.contrib.slim", "tensorflow.contrib.slim.nets",
                 "tensorflow.python", "tensorflow.python.framework", "tensorflow.contrib.tensorboard",

@@ -173,3 +173,33 @@ def test_product_variable_names_follow_the_reference_scopes():
         part.names |= {"LayerNorm/gamma", "LayerNorm/beta"}
     assert enc_part.names == enc_names
     assert dec_part.names == dec_names
+
+
+@pytest.mark.parametrize("case", ["a", "b"])
+def test_one_beam_search_step(case):
+    """BeamSearchDecoder.get_body()() - the reference's beam step (finished-row masking, hypothesis
+    scores with the length penalty, top-k over beam*vocabulary, gathers of lengths / UN-normalised
+    logprob sums / finished flags / every decoder feedable, token history re-ordering, embedding of
+    the chosen words, log-softmax of the parent's next logits) against the oracle.  Case b holds
+    exact score ties inside a sentence."""
+    pre = "beam_{}_".format(case)
+    alpha = float(G[pre + "alpha"])
+    scores, words, beams, lsum, lens, fin = O.beam_step(_t(pre + "prev_logprobs"), _t(pre + "logprob_sum"),
+                                                        _t(pre + "lengths"), _t(pre + "finished"), alpha)
+    assert np.array_equal(lens.numpy(), G[pre + "out_lengths"])
+    assert np.array_equal(fin.numpy(), G[pre + "out_finished"])
+    assert np.abs(scores.numpy() - G[pre + "out_scores"]).max() < 2e-6
+    assert np.abs(lsum.numpy() - G[pre + "out_logprob_sum"]).max() < 2e-6
+    bsz, beam = beams.shape
+    # token history: re-ordered by the surviving beams, the new words appended (oracle: beam_search)
+    tokens = _t(pre + "token_ids")
+    tokens = tokens[:, torch.arange(bsz).unsqueeze(1), beams.long()]
+    tokens = torch.cat([tokens, words.unsqueeze(0)], 0)
+    assert np.array_equal(tokens.numpy(), G[pre + "out_token_ids"])
+    flat = (torch.arange(bsz).unsqueeze(1) * beam + beams.long()).reshape(-1)
+    assert np.array_equal(_t(pre + "state_feed")[flat].numpy(), G[pre + "out_state_feed"])
+    assert np.array_equal(_t(pre + "emb_table")[words.reshape(-1)].numpy(), G[pre + "out_embedded"])
+    assert np.array_equal(fin.reshape(-1).numpy(), G[pre + "out_dec_finished"])
+    want_lp = G[pre + "out_prev_logprobs"]
+    got_lp = torch.log_softmax(_t(pre + "next_logits"), -1).reshape(want_lp.shape).numpy()
+    assert np.abs(got_lp - want_lp).max() < 2e-6
