@@ -192,11 +192,12 @@ class AutoregressiveDecoder(ModelPart):
     def train_mask(self) -> torch.Tensor:
         return self._train_mask_bm.t()
 
-    @tensor
-    def _train_step_inputs_bm(self) -> torch.Tensor:
-        """[batch, time] symbols fed at each training step: <s>, then the gold symbol of the
-        previous step times `unfinished` (logits_to_symbols, autoregressive.py:461-475)."""
-        gold = self._train_ids_host.numpy()  # [B,T]
+    @staticmethod
+    def teacher_forcing_inputs(gold: np.ndarray) -> np.ndarray:
+        """[batch, time] symbols fed at each training step, from the gold ids [batch, time]: <s>, then
+        the gold symbol of the previous step times `unfinished` - i.e. <pad> after the first </s>
+        (get_body: logits_to_symbols / is_finished, autoregressive.py:446-475).  Host arithmetic on
+        the ids of one batch; the device sees only the result."""
         bsz, steps = gold.shape
         finished = np.zeros(bsz, dtype=bool)
         fed = np.empty((bsz, steps), dtype=np.int64)
@@ -205,7 +206,11 @@ class AutoregressiveDecoder(ModelPart):
             nxt = gold[:, s] * (~finished)
             finished |= (nxt == END_TOKEN_INDEX)
             fed[:, s + 1] = nxt
-        return runtime.to_device(torch.from_numpy(fed))
+        return fed
+
+    @tensor
+    def _train_step_inputs_bm(self) -> torch.Tensor:
+        return runtime.to_device(torch.from_numpy(self.teacher_forcing_inputs(self._train_ids_host.numpy())))
 
     def embed_input_symbols(self, input_symbols: torch.Tensor) -> torch.Tensor:
         embedded = ops.embed(input_symbols, self.embedding_matrix)

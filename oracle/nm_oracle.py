@@ -206,6 +206,36 @@ def decoder_step(p: Params, spec: RNNDecoderSpec, embedded_input, prev_output, h
     return output, cell_output, context, weights
 
 
+def autoregressive_loop(next_output: Callable, to_logits: Callable, embed: Callable, bsz: int,
+                        max_len: int, train_inputs: Optional[torch.Tensor] = None) -> Dict[str, list]:
+    """AutoregressiveDecoder.decoding_loop + get_body (autoregressive.py:425-562), the part every
+    decoder shares.  `next_output(embedded_input, finished)` is the subclass's next_state (it keeps its
+    own recurrent state), `to_logits` the vocabulary projection, `embed` the embedding lookup.
+
+    Per step: logits = to_logits(output); next symbol = gold `train_inputs[step]` (training) or
+    argmax over the FULL vocabulary (runtime); `symbol *= not finished` (pad once finished);
+    `finished |= symbol == </s>`; the mask appended is `not finished` AFTER the update.  The loop
+    runs while `not all(finished) and step < max_len` (:425-437)."""
+    finished = torch.zeros(bsz, dtype=torch.bool)
+    embedded = embed(torch.full((bsz,), START, dtype=torch.int64))
+    hist = {"logits": [], "outputs": [], "symbols": [], "mask": [], "extra": []}
+    step = 0
+    while (not bool(finished.all())) and step < max_len:
+        output, extra = next_output(embedded, finished)
+        logits = to_logits(output)
+        chosen = train_inputs[step] if train_inputs is not None else torch.argmax(logits, dim=1)
+        symbols = chosen * (~finished).to(torch.int64)
+        finished = finished | (symbols == END)
+        embedded = embed(symbols)
+        hist["logits"].append(logits)
+        hist["outputs"].append(output)
+        hist["symbols"].append(symbols)
+        hist["mask"].append(~finished)
+        hist["extra"].append(extra)
+        step += 1
+    return hist
+
+
 def decoder_train(p: Params, spec: RNNDecoderSpec, enc: Dict[str, torch.Tensor],
                   train_inputs: torch.Tensor) -> Dict[str, torch.Tensor]:
     """decoding_loop(train_mode=True) + train_xents/train_loss (autoregressive.py:292-316,532-562).
@@ -213,25 +243,19 @@ def decoder_train(p: Params, spec: RNNDecoderSpec, enc: Dict[str, torch.Tensor],
     train_inputs: [T, B] int64 = padded references with </s> appended (feed_dict :579-582),
     already transposed to time-major as `train_inputs` is (:199-202)."""
     emb = p[spec.prefix + "/word_embeddings"]
-    steps, bsz = train_inputs.shape
+    _steps, bsz = train_inputs.shape
     states, mask = enc["temporal_states"], enc["temporal_mask"]
     hidden = bahdanau_precompute(p, spec.att_prefix, states)
-    prev = decoder_initial_state(p, spec, enc["output"])
-    finished = torch.zeros(bsz, dtype=torch.bool)
-    embedded = emb[torch.full((bsz,), START, dtype=torch.int64)]
-    logits_hist, out_states, att_weights, rnn_outputs = [], [], [], []
-    step = 0
-    while (not bool(finished.all())) and step < spec.max_output_len:
-        output, prev, _ctx, w = decoder_step(p, spec, embedded, prev, hidden, states, mask)
-        logits = state_to_logits(p, spec, output)
-        next_symbols = train_inputs[step] * (~finished).to(torch.int64)
-        finished = finished | (next_symbols == END)
-        embedded = emb[next_symbols]
-        logits_hist.append(logits)
-        out_states.append(output)
-        att_weights.append(w)
-        rnn_outputs.append(prev)
-        step += 1
+    rnn = {"prev": decoder_initial_state(p, spec, enc["output"])}
+
+    def next_output(embedded, _finished):
+        output, rnn["prev"], _ctx, w = decoder_step(p, spec, embedded, rnn["prev"], hidden, states, mask)
+        return output, (w, rnn["prev"])
+
+    hist = autoregressive_loop(next_output, lambda o: state_to_logits(p, spec, o), lambda ids: emb[ids], bsz,
+                               spec.max_output_len, train_inputs)
+    logits_hist, out_states = hist["logits"], hist["outputs"]
+    att_weights, rnn_outputs = [e[0] for e in hist["extra"]], [e[1] for e in hist["extra"]]
     logits_t = torch.stack(logits_hist, 0)                       # [T,B,V]
     train_mask = sentence_mask(train_inputs, logits_t.dtype)     # [T,B]
     logprobs = torch.log_softmax(logits_t, dim=-1)
@@ -252,21 +276,15 @@ def decoder_greedy(p: Params, spec: RNNDecoderSpec, enc: Dict[str, torch.Tensor]
     states, mask = enc["temporal_states"], enc["temporal_mask"]
     bsz = states.shape[0]
     hidden = bahdanau_precompute(p, spec.att_prefix, states)
-    prev = decoder_initial_state(p, spec, enc["output"])
-    finished = torch.zeros(bsz, dtype=torch.bool)
-    embedded = emb[torch.full((bsz,), START, dtype=torch.int64)]
-    logits_hist, symbols, out_mask = [], [], []
-    step = 0
-    while (not bool(finished.all())) and step < spec.max_output_len:
-        output, prev, _ctx, _w = decoder_step(p, spec, embedded, prev, hidden, states, mask)
-        logits = state_to_logits(p, spec, output)
-        next_symbols = torch.argmax(logits, dim=1) * (~finished).to(torch.int64)
-        finished = finished | (next_symbols == END)
-        embedded = emb[next_symbols]
-        logits_hist.append(logits)
-        symbols.append(next_symbols)
-        out_mask.append(~finished)
-        step += 1
+    rnn = {"prev": decoder_initial_state(p, spec, enc["output"])}
+
+    def next_output(embedded, _finished):
+        output, rnn["prev"], _ctx, _w = decoder_step(p, spec, embedded, rnn["prev"], hidden, states, mask)
+        return output, None
+
+    hist = autoregressive_loop(next_output, lambda o: state_to_logits(p, spec, o), lambda ids: emb[ids], bsz,
+                               spec.max_output_len)
+    logits_hist, symbols, out_mask = hist["logits"], hist["symbols"], hist["mask"]
     logits_t = torch.stack(logits_hist, 0)
     res = {"runtime_logits": logits_t, "runtime_logprobs": torch.log_softmax(logits_t, -1),
            "output_symbols": torch.stack(symbols, 0), "runtime_mask": torch.stack(out_mask, 0),
@@ -425,26 +443,18 @@ def transformer_decoder_greedy(p: Params, spec: TransformerDecoderSpec, enc: Dic
     bsz = enc["states"].shape[0]
     emb = p[spec.prefix + "/word_embeddings"]
     dim = emb.shape[1]
-    seq = torch.zeros(bsz, 0, dim, dtype=emb.dtype)
-    mask = torch.zeros(bsz, 0, dtype=emb.dtype)
-    finished = torch.zeros(bsz, dtype=torch.bool)
-    embedded = emb[torch.full((bsz,), START, dtype=torch.int64)]
-    symbols, logits_hist, masks = [], [], []
-    step = 0
-    while step < spec.max_len and not bool(finished.all()):
-        seq = torch.cat([seq, embedded.unsqueeze(1)], 1)
-        mask = torch.cat([mask, (~finished).to(emb.dtype).unsqueeze(1)], 1)
-        states = transformer_decoder_stack(p, spec, seq, mask, enc["states"], enc["mask"])
-        logits = transformer_logits(p, spec, states[:, -1])
-        nxt = torch.argmax(logits, dim=-1) * (~finished).to(torch.int64)
-        finished = finished | (nxt == END)
-        embedded = emb[nxt]
-        symbols.append(nxt)
-        logits_hist.append(logits)
-        masks.append(~finished)
-        step += 1
-    return {"symbols": torch.stack(symbols), "logits": torch.stack(logits_hist),
-            "mask": torch.stack(masks)}
+    prefix = {"seq": torch.zeros(bsz, 0, dim, dtype=emb.dtype), "mask": torch.zeros(bsz, 0, dtype=emb.dtype)}
+
+    def next_output(embedded, finished):
+        prefix["seq"] = torch.cat([prefix["seq"], embedded.unsqueeze(1)], 1)
+        prefix["mask"] = torch.cat([prefix["mask"], (~finished).to(emb.dtype).unsqueeze(1)], 1)
+        states = transformer_decoder_stack(p, spec, prefix["seq"], prefix["mask"], enc["states"], enc["mask"])
+        return states[:, -1], None
+
+    hist = autoregressive_loop(next_output, lambda o: transformer_logits(p, spec, o), lambda ids: emb[ids], bsz,
+                               spec.max_len)
+    return {"symbols": torch.stack(hist["symbols"]), "logits": torch.stack(hist["logits"]),
+            "mask": torch.stack(hist["mask"])}
 
 
 # ---------------------------------------------------------------------------

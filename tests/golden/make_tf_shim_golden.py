@@ -263,6 +263,42 @@ def main():
                     pre + "out_state_feed": np.asarray(nxt.decoder_loop_state.feedables.other[0]),
                     pre + "out_embedded": np.asarray(nxt.decoder_loop_state.feedables.embedded_input),
                     pre + "out_dec_finished": np.asarray(nxt.decoder_loop_state.feedables.finished)})
+    # ---- the decoding loop every decoder shares: AutoregressiveDecoder.get_initial_loop_state /
+    #      loop_continue_criterion / get_body (decoders/autoregressive.py:381-519), driven by a python
+    #      `while` in place of tf.while_loop, around a stand-in next_state ------------------------------------
+    from neuralmonkey.decoders.autoregressive import AutoregressiveDecoder
+    vsz, odim, edim2, max_len, nb = 11, 6, 6, 7, 5   # output size == embedding size, as the reference requires
+    dec_w, dec_b, table = f32(odim, vsz), f32(vsz, scale=0.3), f32(vsz, edim2)
+    step_states = f32(max_len, nb, odim)
+    gold = np.array([[5, 6, 2, 0, 0, 0], [7, 8, 9, 4, 2, 0], [4, 2, 0, 0, 0, 0], [3, 3, 3, 3, 3, 2], [6, 2, 0, 0, 0, 0]],
+                    np.int64).T                     # time-major [T, B], incl. </s>, padded
+    # make the runtime argmax hit </s> at different steps for different sentences
+    dec_b_run = dec_b.copy()
+    out.update({"loop_w": dec_w, "loop_b": dec_b, "loop_table": table, "loop_states": step_states, "loop_gold": gold})
+    for mode, supress, eos_bonus in (("train", True, 0.0), ("run", False, 0.0), ("run_unk", True, 0.0),
+                                     ("run_eos", True, 2.5)):
+        bias = dec_b.copy()
+        bias[2] += eos_bonus
+        out["loop_{}_bias".format(mode)] = bias
+        ad = object.__new__(AutoregressiveDecoder)
+        ad.__dict__.update(dict(
+            vocabulary=list(range(vsz)), supress_unk=supress, max_output_len=max_len, batch_size=nb,
+            dropout_keep_prob=1.0, train_mode=None, _embedding_size=edim2, embeddings_source=None,
+            _variable_scope=shim.VarScope("dec"), _reuse=None, _name="dec",
+            _decoding_w_cached_placeholder=shim.t(dec_w), _decoding_b_cached_placeholder=shim.t(bias),
+            _embedding_matrix_cached_placeholder=shim.t(table),
+            _go_symbols_cached_placeholder=shim.t(np.full((nb,), 1, np.int64)),
+            _train_inputs_cached_placeholder=shim.t(gold)))
+        ad.next_state = lambda ls: (shim.t(step_states[int(ls.feedables.step)]), None, None)
+        body = ad.get_body(train_mode=(mode == "train"))
+        state = ad.get_initial_loop_state()
+        while bool(np.asarray(ad.loop_continue_criterion(*state))):
+            state = body(*state)
+        out["loop_{}_logits".format(mode)] = np.asarray(state.histories.logits)
+        out["loop_{}_symbols".format(mode)] = np.asarray(state.histories.output_symbols)
+        out["loop_{}_mask".format(mode)] = np.asarray(state.histories.output_mask)
+        out["loop_{}_steps".format(mode)] = np.int64(np.asarray(state.feedables.step))
+        out["loop_{}_last_input".format(mode)] = np.asarray(state.feedables.embedded_input)
     np.savez_compressed(os.path.join(HERE, "tf_shim_golden.npz"), **out)
     print(sorted(out))
 

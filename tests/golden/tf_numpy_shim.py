@@ -237,7 +237,7 @@ def install():
     tf.rsqrt = lambda x: t(1.0 / np.sqrt(np.asarray(x, np.float32)), np.float32)
     tf.square = lambda x: t(np.square(np.asarray(x)))
     tf.tanh = lambda x: t(np.tanh(np.asarray(x, np.float32)), np.float32)
-    tf.zeros = lambda shape, dtype=None: t(np.zeros([int(d) for d in shape], np.float32))
+    tf.zeros = lambda shape, dtype=None, name=None: t(np.zeros([int(d) for d in shape], dtype or np.float32))
     tf.reduce_sum = lambda x, axis=None, keepdims=False: t(
         np.sum(np.asarray(x), axis=tuple(axis) if isinstance(axis, list) else axis, keepdims=keepdims))
     tf.Variable = T
@@ -293,6 +293,8 @@ def install():
     tf.less = lambda a, b: t(np.less(a, b))
     tf.reduce_all = lambda x: t(np.all(np.asarray(x)))
     tf.constant = lambda x, dtype=None, **k: t(x, dtype)
+    tf.nn.embedding_lookup = lambda table, ids: t(np.asarray(table)[np.asarray(ids)])
+    tf.argmax = lambda x, axis=None: t(np.argmax(np.asarray(x), axis=axis).astype(np.int64))
     sys.modules["tensorflow"] = tf
     for sub in ("tensorflow.contrib", "tensorflow.contrib.slim", "tensorflow.contrib.slim.nets",
                 "tensorflow.python", "tensorflow.python.framework", "tensorflow.contrib.tensorboard",

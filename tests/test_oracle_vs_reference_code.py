@@ -203,3 +203,51 @@ def test_one_beam_search_step(case):
     want_lp = G[pre + "out_prev_logprobs"]
     got_lp = torch.log_softmax(_t(pre + "next_logits"), -1).reshape(want_lp.shape).numpy()
     assert np.abs(got_lp - want_lp).max() < 2e-6
+
+
+@pytest.mark.parametrize("mode", ["train", "run", "run_unk", "run_eos"])
+def test_shared_decoding_loop(mode):
+    """AutoregressiveDecoder.get_initial_loop_state / loop_continue_criterion / get_body
+    (autoregressive.py:381-519) driven step by step around a stand-in next_state: logits with the
+    -1e9 <unk> column, gold vs argmax feedback over the full vocabulary, `symbol *= unfinished`,
+    `finished |= symbol == </s>`, mask = not finished AFTER the step, stop when all finished or at
+    max_output_len - against the loop the oracle's three decoders share."""
+    states = _t("loop_states")
+    w, b, table = _t("loop_w"), _t("loop_" + mode + "_bias"), _t("loop_table")
+    supress = mode != "run"
+    gold = torch.from_numpy(G["loop_gold"]) if mode == "train" else None
+    counter = {"step": 0}
+
+    def next_output(_embedded, _finished):
+        out = states[counter["step"]]
+        counter["step"] += 1
+        return out, None
+
+    def to_logits(out):
+        logits = out @ w + b
+        if supress:
+            pen = torch.zeros(logits.shape[-1])
+            pen[O.UNK] = -1e9
+            logits = logits + pen
+        return logits
+
+    seen_inputs = []
+
+    def embed(ids):
+        seen_inputs.append(ids.clone())
+        return table[ids]
+
+    hist = O.autoregressive_loop(next_output, to_logits, embed, states.shape[1], states.shape[0], gold)
+    steps = int(G["loop_{}_steps".format(mode)])
+    assert len(hist["symbols"]) == steps
+    assert np.array_equal(torch.stack(hist["symbols"]).numpy(), G["loop_{}_symbols".format(mode)])
+    assert np.array_equal(torch.stack(hist["mask"]).numpy(), G["loop_{}_mask".format(mode)])
+    assert np.abs(torch.stack(hist["logits"]).numpy() - G["loop_{}_logits".format(mode)]).max() < 2e-6
+    assert np.array_equal(table[seen_inputs[-1]].numpy(), G["loop_{}_last_input".format(mode)])
+    if mode == "train":
+        # the product computes the symbols fed at every training step on the host, for all steps at
+        # once: they are the inputs the reference's loop embedded, step by step
+        from neuralmonkey_b200.decoders.autoregressive import AutoregressiveDecoder
+        fed = AutoregressiveDecoder.teacher_forcing_inputs(G["loop_gold"].T.copy())       # [B, T]
+        want = torch.stack(seen_inputs[:steps]).t().numpy()                                 # <s>, then fed-back gold
+        assert np.array_equal(fed[:, :steps], want)
