@@ -32,7 +32,7 @@ reference, float64 to measure kernel error); gradients come from torch.autograd
 over the same restated graph.
 """
 import math
-from typing import Callable, Dict, List, Optional, Tuple
+from typing import Callable, Dict, List, Optional, Sequence, Tuple
 
 import torch
 
@@ -109,22 +109,71 @@ def sentence_mask(ids: torch.Tensor, dtype) -> torch.Tensor:
 # ---------------------------------------------------------------------------
 # SentenceEncoder (encoders/recurrent.py:113-314, model/sequence.py:170-199)
 # ---------------------------------------------------------------------------
+def embedded_sequence(p: Params, name: str, factor_ids: Sequence[torch.Tensor],
+                      scale_embeddings_by_depth: bool = False) -> Dict[str, torch.Tensor]:
+    """EmbeddedFactorSequence.temporal_states / temporal_mask (model/sequence.py:170-199): every factor
+    is looked up in its own `embedding_matrix_<i>`, optionally scaled by sqrt(size), multiplied by the
+    mask of the FIRST factor, and the factors are concatenated on the feature axis."""
+    dtype = p[name + "/embedding_matrix_0"].dtype
+    mask = sentence_mask(factor_ids[0], dtype)
+    factors = []
+    for i, ids in enumerate(factor_ids):
+        matrix = p["{}/embedding_matrix_{}".format(name, i)]
+        emb = matrix[ids]
+        if scale_embeddings_by_depth:
+            emb = emb * matrix.shape[-1] ** 0.5
+        factors.append(emb * mask.unsqueeze(-1))
+    return {"temporal_states": torch.cat(factors, 2), "temporal_mask": mask}
+
+
+def _cell_params(p: Params, scope: str) -> Tuple:
+    return tuple(p[scope + n] for n in ("gates/kernel", "gates/bias", "candidate/kernel", "candidate/bias"))
+
+
+def rnn_layer(p: Params, scope: str, x: torch.Tensor, lengths: torch.Tensor, direction: str):
+    """rnn_layer (encoders/recurrent.py:71-110), GRU cells; variable scopes as TensorFlow names them:
+    <scope>/bidirectional_rnn/{fw,bw}/OrthoGRUCell or <scope>/rnn/OrthoGRUCell."""
+    if direction == "bidirectional":
+        base = scope + "/bidirectional_rnn/{}/OrthoGRUCell/"
+        return bidirectional_gru(x, lengths, _cell_params(p, base.format("fw")), _cell_params(p, base.format("bw")))
+    cell = _cell_params(p, scope + "/rnn/OrthoGRUCell/")
+    if direction == "backward":
+        out_rev, final = dynamic_gru(reverse_sequence(x, lengths), lengths, *cell)
+        return reverse_sequence(out_rev, lengths), final
+    return dynamic_gru(x, lengths, *cell)
+
+
+def recurrent_encoder(p: Params, prefix: str, inputs: torch.Tensor, mask: torch.Tensor,
+                      rnn_layers: Sequence[Tuple[int, str]] = ((0, "bidirectional"),),
+                      add_residual: bool = False, add_layer_norm: bool = False,
+                      include_final_layer_norm: bool = True) -> Dict[str, torch.Tensor]:
+    """RecurrentEncoder.rnn (encoders/recurrent.py:180-218), dropout off.  Layer i lives in scope
+    rnn_<i>_<direction>; with add_layer_norm its INPUT is normalised first (own LayerNorm variables)
+    and - note - the residual then adds the normalised input, not the raw one; the residual applies
+    only when input and output widths agree; the final LayerNorm normalises the states and the final
+    state with the SAME variables (:215-216)."""
+    lengths = mask.sum(1).to(torch.int64)             # model/stateful.py:56-62
+    layer_input, layer_final = inputs, inputs[:, -1]
+    for i, (_size, direction) in enumerate(rnn_layers):
+        scope = "{}/rnn_{}_{}".format(prefix, i, direction)
+        if add_layer_norm:
+            layer_input = layer_norm(layer_input, p[scope + "/LayerNorm/gamma"], p[scope + "/LayerNorm/beta"])
+        layer_output, layer_final_output = rnn_layer(p, scope, layer_input, lengths, direction)
+        if add_residual and layer_input.shape[-1] == layer_output.shape[-1]:
+            layer_input = layer_input + layer_output
+            layer_final = layer_final + layer_final_output
+        else:
+            layer_input, layer_final = layer_output, layer_final_output
+    if include_final_layer_norm:
+        gamma, beta = p[prefix + "/LayerNorm/gamma"], p[prefix + "/LayerNorm/beta"]
+        layer_input, layer_final = layer_norm(layer_input, gamma, beta), layer_norm(layer_final, gamma, beta)
+    return {"temporal_states": layer_input, "output": layer_final, "temporal_mask": mask}
+
+
 def sentence_encoder(p: Params, prefix: str, ids: torch.Tensor) -> Dict[str, torch.Tensor]:
-    emb = p[prefix + "_input/embedding_matrix_0"]
-    dtype = emb.dtype
-    mask = sentence_mask(ids, dtype)
-    lengths = mask.sum(1).to(torch.int64)
-    embedded = emb[ids] * mask.unsqueeze(-1)          # sequence.py:181-191
-    cell = prefix + "/rnn_0_bidirectional/bidirectional_rnn/{}/OrthoGRUCell/"
-    names = ("gates/kernel", "gates/bias", "candidate/kernel", "candidate/bias")
-    fw = tuple(p[cell.format("fw") + n] for n in names)
-    bw = tuple(p[cell.format("bw") + n] for n in names)
-    states, final = bidirectional_gru(embedded, lengths, fw, bw)
-    gamma, beta = p[prefix + "/LayerNorm/gamma"], p[prefix + "/LayerNorm/beta"]
-    # include_final_layer_norm=True: both through the SAME LayerNorm variables (recurrent.py:215-216)
-    return {"temporal_states": layer_norm(states, gamma, beta),
-            "output": layer_norm(final, gamma, beta),
-            "temporal_mask": mask}
+    """SentenceEncoder (recurrent.py:221-314): one embedded factor, one bidirectional GRU layer."""
+    seq = embedded_sequence(p, prefix + "_input", [ids])
+    return recurrent_encoder(p, prefix, seq["temporal_states"], seq["temporal_mask"])
 
 
 # ---------------------------------------------------------------------------

@@ -299,6 +299,139 @@ def main():
         out["loop_{}_mask".format(mode)] = np.asarray(state.histories.output_mask)
         out["loop_{}_steps".format(mode)] = np.int64(np.asarray(state.feedables.step))
         out["loop_{}_last_input".format(mode)] = np.asarray(state.feedables.embedded_input)
+
+    # ---- the whole attention decoder: decoders/decoder.py Decoder (initial_state, get_initial_feedables /
+    #      histories, next_state) under AutoregressiveDecoder's loop, with the reference's own Attention,
+    #      encoder projection and output projections; only the GRU cell arithmetic is the shim's
+    #      restatement of TensorFlow's published GRUCell.  Variables are looked up by their full TF names.
+    from neuralmonkey.decoders.decoder import Decoder
+    from neuralmonkey.decoders.autoregressive import LoopState
+
+    def rnn_decoder_case(tag, hsz, esz, maxout, use_mask):
+        nb, tx, csz, asz, vsz, max_len = 4, 6, 10, 8, 13, 6
+        dname, aname = "rd_" + tag, "ra_" + tag
+        first = len(shim.VARIABLES)
+        var = shim.VARIABLES
+        var[aname + "/Attention/attn_query_projection"] = f32(hsz, asz, scale=0.5)
+        var[aname + "/attn_key_projection"] = f32(csz, asz, scale=0.5)
+        var[aname + "/attn_similarity_v"] = f32(asz, scale=0.7)
+        var[aname + "/attn_projection_bias"] = f32(asz, scale=0.3)
+        var[aname + "/attn_bias"] = f32(scale=0.3)
+        var[dname + "/initial_state/encoders_projection/kernel"] = f32(csz, hsz, scale=0.4)
+        var[dname + "/initial_state/encoders_projection/bias"] = f32(hsz, scale=0.3)
+        cell = dname + "/attention_decoder/OrthoGRUCell/"
+        var[cell + "gates/kernel"], var[cell + "gates/bias"] = f32(esz + hsz, 2 * hsz, scale=0.5), 1.0 + f32(2 * hsz, scale=0.2)
+        var[cell + "candidate/kernel"], var[cell + "candidate/bias"] = f32(esz + hsz, hsz, scale=0.5), f32(hsz, scale=0.2)
+        if maxout:
+            proj = dname + "/attention_decoder/MaxoutProjection/MaxoutProjection/"
+            var[proj + "kernel"], var[proj + "bias"] = f32(hsz + esz + csz, 2 * esz, scale=0.4), f32(2 * esz, scale=0.3)
+        else:
+            proj = dname + "/attention_decoder/dense/"
+            var[proj + "kernel"], var[proj + "bias"] = f32(hsz + esz + csz, hsz, scale=0.4), f32(hsz, scale=0.3)
+        for name in list(var)[first:]:
+            out["rv::" + name] = var[name]
+        states, enc_out = f32(nb, tx, csz), f32(nb, csz)
+        amask = np.array([[1, 1, 1, 1, 1, 1], [1, 1, 1, 1, 0, 0], [1, 1, 0, 0, 0, 0], [1, 0, 0, 0, 0, 0]], np.float32)
+        dec_w, dec_b, table = f32(esz, vsz, scale=0.8), f32(vsz, scale=0.3), f32(vsz, esz)
+        gold = np.array([[5, 6, 7, 2, 0, 0], [7, 8, 9, 4, 3, 2], [4, 2, 0, 0, 0, 0], [3, 11, 12, 10, 2, 0]], np.int64).T
+        out.update({"rd_{}_states".format(tag): states, "rd_{}_enc_out".format(tag): enc_out,
+                    "rd_{}_mask".format(tag): amask, "rd_{}_w".format(tag): dec_w, "rd_{}_b".format(tag): dec_b,
+                    "rd_{}_table".format(tag): table, "rd_{}_gold".format(tag): gold})
+        for mode in ("train", "run"):
+            att = object.__new__(Attention)
+            att.__dict__.update(dict(
+                _variable_scope=shim.VarScope(aname), _reuse=None, _name=aname, _state_size=asz, batch_size=nb,
+                _histories={}, _attention_states_cached_placeholder=shim.t(states),
+                _attention_mask_cached_placeholder=shim.t(amask) if use_mask else None))
+            rd = object.__new__(Decoder)
+            rd.__dict__.update(dict(
+                vocabulary=list(range(vsz)), supress_unk=False, max_output_len=max_len, batch_size=nb,
+                dropout_keep_prob=1.0, train_mode=None, _embedding_size=esz, embeddings_source=None,
+                _variable_scope=shim.VarScope(dname), _reuse=None, _name=dname,
+                _decoding_w_cached_placeholder=shim.t(dec_w), _decoding_b_cached_placeholder=shim.t(dec_b),
+                _embedding_matrix_cached_placeholder=shim.t(table),
+                _go_symbols_cached_placeholder=shim.t(np.full((nb,), 1, np.int64)),
+                _train_inputs_cached_placeholder=shim.t(gold),
+                encoders=[types.SimpleNamespace(output=shim.t(enc_out))],
+                _output_projection_spec=maxout_output(esz) if maxout else None, _conditional_gru=False,
+                _attention_on_input=False, _rnn_cell_str="GRU", _rnn_size=hsz, _encoder_projection=None,
+                attentions=[att], step_scope=shim.VarScope(dname + "/attention_decoder"),
+                input_projection=lambda *args: LoopState(*args).feedables.embedded_input))
+            shim.USED[:] = []
+            shim.GRUCell.CALLS[:] = []
+            body = rd.get_body(train_mode=(mode == "train"))
+            state = rd.get_initial_loop_state()
+            while bool(np.asarray(rd.loop_continue_criterion(*state))):
+                state = body(*state)
+            rd.finalize_loop(state, mode == "train")
+            key = "rd_{}_{}_".format(tag, mode)
+            out[key + "logits"] = np.asarray(state.histories.logits)
+            out[key + "output_states"] = np.asarray(state.histories.output_states)
+            out[key + "symbols"] = np.asarray(state.histories.output_symbols)
+            out[key + "out_mask"] = np.asarray(state.histories.output_mask)
+            out[key + "rnn_outputs"] = np.asarray(state.histories.other.rnn_outputs)
+            out[key + "att_weights"] = np.asarray(att.histories["{}_{}".format(dname, mode)])
+            out[key + "att_contexts"] = np.asarray(state.histories.other.attention_histories[0].contexts)
+            out[key + "initial_state"] = np.asarray(rd.initial_state)
+        out["rd_{}_dense_names".format(tag)] = np.array(sorted(set(shim.USED)))
+        out["rd_{}_cell_scopes".format(tag)] = np.array(sorted({c[0] for c in shim.GRUCell.CALLS}))
+
+    rnn_decoder_case("maxout", hsz=7, esz=5, maxout=True, use_mask=True)
+    rnn_decoder_case("tanh", hsz=6, esz=6, maxout=False, use_mask=False)
+
+    # ---- the recurrent encoder: model/sequence.py EmbeddedFactorSequence.temporal_states / temporal_mask and
+    #      encoders/recurrent.py RecurrentEncoder.rnn + rnn_layer, over the shim's restatement of
+    #      tf.nn.(bidirectional_)dynamic_rnn and GRUCell (TensorFlow library code) ----------------------------
+    from neuralmonkey.model.sequence import EmbeddedFactorSequence
+    from neuralmonkey.encoders.recurrent import RecurrentEncoder, _make_rnn_spec
+
+    def recurrent_case(tag, emb_sizes, layers, residual, layer_norm_, final_norm, scale):
+        name = "re_" + tag
+        first = len(shim.VARIABLES)
+        var = shim.VARIABLES
+        vocab_sizes = [9, 5][:len(emb_sizes)]
+        for i, (vs_, es_) in enumerate(zip(vocab_sizes, emb_sizes)):
+            var["{}_input/embedding_matrix_{}".format(name, i)] = f32(vs_, es_)
+        in_dim = sum(emb_sizes)
+        for i, (size, direction) in enumerate(layers):
+            scope = "{}/rnn_{}_{}".format(name, i, direction)
+            cells = ([scope + "/bidirectional_rnn/fw/OrthoGRUCell/", scope + "/bidirectional_rnn/bw/OrthoGRUCell/"]
+                     if direction == "bidirectional" else [scope + "/rnn/OrthoGRUCell/"])
+            for cell in cells:
+                var[cell + "gates/kernel"], var[cell + "gates/bias"] = f32(in_dim + size, 2 * size, scale=0.5), 1.0 + f32(2 * size, scale=0.2)
+                var[cell + "candidate/kernel"], var[cell + "candidate/bias"] = f32(in_dim + size, size, scale=0.5), f32(size, scale=0.2)
+            if layer_norm_:
+                var[scope + "/LayerNorm/gamma"], var[scope + "/LayerNorm/beta"] = 1.0 + f32(in_dim, scale=0.2), f32(in_dim, scale=0.2)
+            in_dim = 2 * size if direction == "bidirectional" else size
+        if final_norm:
+            var[name + "/LayerNorm/gamma"], var[name + "/LayerNorm/beta"] = 1.0 + f32(in_dim, scale=0.2), f32(in_dim, scale=0.2)
+        for vname in list(var)[first:]:
+            out["ev::" + vname] = var[vname]
+        ids = np.array([[4, 5, 6, 7, 8, 3], [3, 4, 5, 0, 0, 0], [8, 0, 0, 0, 0, 0], [5, 5, 4, 4, 3, 0]], np.int64)
+        factors = [ids, (ids % 4 + 1) * (ids != 0)][:len(emb_sizes)]
+        seq = object.__new__(EmbeddedFactorSequence)
+        seq.__dict__.update(dict(
+            _variable_scope=shim.VarScope(name + "_input"), _reuse=None, _name=name + "_input",
+            vocabularies=[list(range(v)) for v in vocab_sizes], vocabulary_sizes=vocab_sizes,
+            data_ids=["f{}".format(i) for i in range(len(emb_sizes))], embedding_sizes=list(emb_sizes),
+            scale_embeddings_by_depth=scale, embeddings_source=None, trainable=True,
+            _input_factor_indices_cached_placeholder=[shim.t(f) for f in factors]))
+        enc = object.__new__(RecurrentEncoder)
+        enc.__dict__.update(dict(
+            _variable_scope=shim.VarScope(name), _reuse=None, _name=name, input_sequence=seq,
+            dropout_keep_prob=1.0, train_mode=None, rnn_specs=[_make_rnn_spec(*l) for l in layers],
+            add_residual=residual, add_layer_norm=layer_norm_, include_final_layer_norm=final_norm))
+        shim.GRUCell.CALLS[:] = []
+        out.update({name + "_ids": np.stack(factors), name + "_embedded": np.asarray(seq.temporal_states),
+                    name + "_mask": np.asarray(seq.temporal_mask), name + "_lengths": np.asarray(seq.lengths),
+                    name + "_states": np.asarray(enc.temporal_states), name + "_output": np.asarray(enc.output),
+                    name + "_enc_mask": np.asarray(enc.temporal_mask)})
+        out[name + "_cell_scopes"] = np.array(sorted({c[0] for c in shim.GRUCell.CALLS}))
+
+    recurrent_case("sentence", [5], [(4, "bidirectional")], False, False, True, False)
+    recurrent_case("deep", [3, 1], [(4, "forward"), (4, "backward"), (2, "bidirectional"), (3, "bidirectional")],
+                   True, True, True, True)
+    recurrent_case("plain", [4], [(3, "backward"), (3, "forward")], True, False, False, False)
     np.savez_compressed(os.path.join(HERE, "tf_shim_golden.npz"), **out)
     print(sorted(out))
 

@@ -220,6 +220,90 @@ def _log_softmax(x, axis=-1):
     return t(shifted - np.log(np.exp(shifted).sum(axis=axis, keepdims=True)), np.float32)
 
 
+class GRUCell:
+    """tf.contrib.rnn.GRUCell as PUBLISHED by TensorFlow 1.x (rnn_cell_impl.GRUCell.call) -- the cell
+    arithmetic is library code the reference does not carry, so this is a restatement, not reference
+    code being run:
+
+        [r, u] = sigmoid([x, h] . gates/kernel + gates/bias)
+        c      = tanh([x, r * h] . candidate/kernel + candidate/bias)
+        h'     = u * h + (1 - u) * c                  (returned as both output and state)
+
+    What running the reference AROUND it pins is everything else: which tensors are fed as x and h,
+    the variable scope the cell is called in (ortho_gru_cell.py:51 passes scope="OrthoGRUCell"), and
+    what is done with the result.  CALLS records (scope, input shape, state shape) per call."""
+    CALLS = []
+
+    def __init__(self, num_units, activation=None, reuse=None, kernel_initializer=None,
+                 bias_initializer=None, **kwargs):
+        self._num_units = num_units
+        self._activation = activation or (lambda x: t(np.tanh(np.asarray(x, np.float32)), np.float32))
+
+    @property
+    def state_size(self):
+        return self._num_units
+
+    @property
+    def output_size(self):
+        return self._num_units
+
+    def __call__(self, inputs, state, scope=None):
+        with _scope_cm(scope or "gru_cell"):
+            wg, bg = _get_variable("gates/kernel"), _get_variable("gates/bias")
+            wc, bc = _get_variable("candidate/kernel"), _get_variable("candidate/bias")
+            GRUCell.CALLS.append((_full_name(""), tuple(np.shape(inputs)), tuple(np.shape(state))))
+        x, h = np.asarray(inputs, np.float32), np.asarray(state, np.float32)
+        assert h.shape[1] == self._num_units and wg.shape == (x.shape[1] + h.shape[1], 2 * h.shape[1])
+        gates = 1.0 / (1.0 + np.exp(-(np.concatenate([x, h], 1) @ wg + bg)))
+        r, u = gates[:, :h.shape[1]], gates[:, h.shape[1]:]
+        c = np.asarray(self._activation(t(np.concatenate([x, r * h], 1) @ wc + bc, np.float32)))
+        new_h = t(u * h + (1.0 - u) * c, np.float32)
+        return new_h, new_h
+
+
+def _rnn_loop(cell, inputs, lengths):
+    """The recurrence of tf.nn.dynamic_rnn as TensorFlow documents it (library code, restated): zero
+    initial state; past a sentence's length the output is zero and the state is carried unchanged."""
+    x = np.asarray(inputs, np.float32)
+    lengths = np.full((x.shape[0],), x.shape[1]) if lengths is None else np.asarray(lengths)
+    state = np.zeros((x.shape[0], cell.state_size), np.float32)
+    outputs = []
+    for step in range(x.shape[1]):
+        out, new = cell(t(x[:, step]), t(state))
+        alive = (step < lengths)[:, None]
+        state = np.where(alive, np.asarray(new), state)
+        outputs.append(np.where(alive, np.asarray(out), 0.0))
+    return t(np.stack(outputs, 1), np.float32), t(state, np.float32)
+
+
+def _reverse_sequence(x, lengths, seq_axis=1, batch_axis=0):
+    assert seq_axis == 1 and batch_axis == 0
+    out = np.array(np.asarray(x))
+    for b, n in enumerate(np.asarray(lengths)):
+        out[b, :n] = out[b, :n][::-1]
+    return t(out)
+
+
+def _dynamic_rnn(cell, inputs, sequence_length=None, dtype=None, scope=None, **kwargs):
+    with _scope_cm(scope or "rnn"):
+        return _rnn_loop(cell, inputs, sequence_length)
+
+
+def _bidirectional_dynamic_rnn(cell_fw, cell_bw, inputs, sequence_length=None, dtype=None, scope=None,
+                               **kwargs):
+    """tf.nn.bidirectional_dynamic_rnn (library code, restated): scopes bidirectional_rnn/{fw,bw}; the
+    backward direction runs over the length-reversed input and its outputs are reversed back."""
+    with _scope_cm(scope or "bidirectional_rnn"):
+        with _scope_cm("fw"):
+            out_fw, st_fw = _rnn_loop(cell_fw, inputs, sequence_length)
+        with _scope_cm("bw"):
+            lengths = (np.full((np.shape(inputs)[0],), np.shape(inputs)[1]) if sequence_length is None
+                       else sequence_length)
+            out_bw, st_bw = _rnn_loop(cell_bw, _reverse_sequence(inputs, lengths), lengths)
+            out_bw = _reverse_sequence(out_bw, lengths)
+    return (out_fw, out_bw), (st_fw, st_bw)
+
+
 def install():
     """Put the shim into sys.modules as `tensorflow` and return it."""
     tf = _Namespace("tensorflow")
@@ -295,6 +379,19 @@ def install():
     tf.constant = lambda x, dtype=None, **k: t(x, dtype)
     tf.nn.embedding_lookup = lambda table, ids: t(np.asarray(table)[np.asarray(ids)])
     tf.argmax = lambda x, axis=None: t(np.argmax(np.asarray(x), axis=axis).astype(np.int64))
+    tf.contrib.rnn = _Namespace("tensorflow.contrib.rnn")
+    tf.contrib.rnn.GRUCell = GRUCell
+    tf.contrib.rnn.RNNCell = GRUCell
+    tf.contrib.rnn.LSTMCell = type("LSTMCell", (), {})
+    tf.nn.rnn_cell = _Namespace("tensorflow.nn.rnn_cell")
+    tf.nn.rnn_cell.RNNCell = GRUCell
+    tf.nn.rnn_cell.LSTMCell = tf.contrib.rnn.LSTMCell
+    tf.nn.dynamic_rnn = _dynamic_rnn
+    tf.nn.bidirectional_dynamic_rnn = _bidirectional_dynamic_rnn
+    tf.reverse_sequence = _reverse_sequence
+    tf.not_equal = lambda a, b: t(np.not_equal(a, b))
+    tf.orthogonal_initializer = lambda *a, **k: None
+    tf.random_normal_initializer = lambda *a, **k: None
     sys.modules["tensorflow"] = tf
     for sub in ("tensorflow.contrib", "tensorflow.contrib.slim", "tensorflow.contrib.slim.nets",
                 "tensorflow.python", "tensorflow.python.framework", "tensorflow.contrib.tensorboard",

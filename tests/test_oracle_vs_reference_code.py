@@ -251,3 +251,85 @@ def test_shared_decoding_loop(mode):
         fed = AutoregressiveDecoder.teacher_forcing_inputs(G["loop_gold"].T.copy())       # [B, T]
         want = torch.stack(seen_inputs[:steps]).t().numpy()                                 # <s>, then fed-back gold
         assert np.array_equal(fed[:, :steps], want)
+
+
+@pytest.mark.parametrize("tag,maxout,use_mask", [("maxout", True, True), ("tanh", False, False)])
+def test_whole_attention_decoder(tag, maxout, use_mask):
+    """decoders/decoder.py Decoder run whole (initial_state :226-251, get_initial_feedables/histories
+    :360-382, next_state :279-358) under AutoregressiveDecoder's loop with the reference's own Attention,
+    linear_encoder_projection and maxout / tanh output projection, in training and in greedy mode; only
+    the GRU cell arithmetic inside is TensorFlow's published GRUCell restated by the shim.  Pins, against
+    the oracle's decoder_train / decoder_greedy: the cell is fed (embedded_input, prev_rnn_output); the
+    attention query is the cell output; the projection input order [cell, embedding, context]; the
+    variable names; initial state = dense(encoder output)."""
+    dname, aname = "rd_" + tag, "ra_" + tag
+    p = {k[4:]: _t(k) for k in G.files if k.startswith("rv::" + dname) or k.startswith("rv::" + aname)}
+    p[dname + "/word_embeddings"] = _t(dname + "_table")
+    p[dname + "/state_to_word_W"], p[dname + "/state_to_word_b"] = _t(dname + "_w"), _t(dname + "_b")
+    spec = O.RNNDecoderSpec(dname, aname, max_output_len=6, output_projection="maxout" if maxout else "tanh")
+    enc = {"temporal_states": _t(dname + "_states"), "output": _t(dname + "_enc_out"),
+           "temporal_mask": _t(dname + "_mask") if use_mask else None}
+    gold = torch.from_numpy(G[dname + "_gold"])
+    assert np.abs(O.decoder_initial_state(p, spec, enc["output"]).numpy()
+                  - G[dname + "_train_initial_state"]).max() < 2e-6
+    # the names the reference asked the variable store for
+    dense = {n[:-len("/kernel")] for n in G[dname + "_dense_names"].tolist()}
+    proj = "MaxoutProjection/MaxoutProjection" if maxout else "dense"
+    assert dense == {dname + "/initial_state/encoders_projection", dname + "/attention_decoder/" + proj}
+    assert G[dname + "_cell_scopes"].tolist() == [dname + "/attention_decoder/OrthoGRUCell/"]
+
+    train = O.decoder_train(p, spec, enc, gold)
+    key = dname + "_train_"
+    assert np.abs(train["train_logits"].numpy() - G[key + "logits"]).max() < 5e-6
+    assert np.abs(train["train_output_states"].numpy() - G[key + "output_states"]).max() < 5e-6
+    assert np.abs(train["rnn_outputs"].numpy() - G[key + "rnn_outputs"]).max() < 5e-6
+    assert np.abs(train["attention_weights"].numpy() - G[key + "att_weights"]).max() < 5e-6
+    if use_mask:
+        assert float(np.abs(G[key + "att_weights"][:, 3, 1:]).max()) == 0.0     # padded source positions
+
+    run = O.decoder_greedy(p, spec, enc)
+    key = dname + "_run_"
+    assert np.array_equal(run["output_symbols"].numpy(), G[key + "symbols"])
+    assert np.array_equal(run["runtime_mask"].numpy(), G[key + "out_mask"])
+    assert np.abs(run["runtime_logits"].numpy() - G[key + "logits"]).max() < 5e-6
+
+
+@pytest.mark.parametrize("tag,layers,residual,layer_norm,final_norm,scale", [
+    ("sentence", [(4, "bidirectional")], False, False, True, False),
+    ("deep", [(4, "forward"), (4, "backward"), (2, "bidirectional"), (3, "bidirectional")], True, True, True, True),
+    ("plain", [(3, "backward"), (3, "forward")], True, False, False, False)])
+def test_recurrent_encoder(tag, layers, residual, layer_norm, final_norm, scale):
+    """model/sequence.py EmbeddedFactorSequence.temporal_states / temporal_mask (:170-199) and
+    encoders/recurrent.py RecurrentEncoder.rnn + rnn_layer (:71-110,180-218) run whole: factor lookup,
+    sqrt(size) scaling, masking by the first factor, per-layer scopes and LayerNorm variables, which
+    input the residual adds, the shared final LayerNorm, fw|bw concatenation order.  The recurrence
+    underneath (dynamic_rnn, GRUCell) is TensorFlow library code restated by the shim."""
+    name = "re_" + tag
+    p = {k[4:]: _t(k) for k in G.files if k.startswith("ev::" + name + "/") or k.startswith("ev::" + name + "_input/")}
+    factors = [torch.from_numpy(f) for f in G[name + "_ids"]]
+    seq = O.embedded_sequence(p, name + "_input", factors, scale_embeddings_by_depth=scale)
+    assert np.array_equal(seq["temporal_mask"].numpy(), G[name + "_mask"])
+    assert np.abs(seq["temporal_states"].numpy() - G[name + "_embedded"]).max() < 1e-6
+    assert np.array_equal(seq["temporal_mask"].sum(1).to(torch.int32).numpy(), G[name + "_lengths"])
+    enc = O.recurrent_encoder(p, name, seq["temporal_states"], seq["temporal_mask"], layers, residual,
+                              layer_norm, final_norm)
+    assert np.abs(enc["temporal_states"].numpy() - G[name + "_states"]).max() < 5e-6
+    assert np.abs(enc["output"].numpy() - G[name + "_output"]).max() < 5e-6
+    assert np.array_equal(enc["temporal_mask"].numpy(), G[name + "_enc_mask"])
+    # the scopes the reference called its cells in are the ones the oracle reads its parameters from
+    cell_scopes = {k[: k.index("gates/kernel")] for k in p if k.endswith("gates/kernel")}
+    assert set(G[name + "_cell_scopes"].tolist()) == cell_scopes
+
+
+def test_product_declares_the_variables_the_reference_asks_for():
+    """The names under which the product's RecurrentEncoder / Decoder / Attention declare their
+    parameters are the names the reference's code looked up in the variable store (recorded by the
+    shim) - what makes reference checkpoints and the oracle's parameter dictionaries interchangeable."""
+    from neuralmonkey_b200.encoders.recurrent import RecurrentEncoder, _make_rnn_spec
+    enc = object.__new__(RecurrentEncoder)
+    want = set(G["re_deep_cell_scopes"].tolist())
+    layers = [(4, "forward"), (4, "backward"), (2, "bidirectional"), (3, "bidirectional")]
+    got = set()
+    for i, layer in enumerate(layers):
+        got.update("re_deep/" + scope + "/" for scope in RecurrentEncoder._cell_scopes(enc, i, _make_rnn_spec(*layer)))
+    assert got == want
