@@ -1,12 +1,35 @@
 """Beam search runner (reference: neuralmonkey/runners/beamsearch_runner.py:14-190):
 picks the `rank`-th hypothesis of the final beam, drops the start slot, cuts at </s>."""
-from typing import Callable, List
+from typing import Callable, List, Tuple
 
 import numpy as np
 
 from neuralmonkey_b200.decoders.beam_search_decoder import BeamSearchDecoder
 from neuralmonkey_b200.runners.base_runner import BaseRunner
 from neuralmonkey_b200.vocabulary import END_TOKEN_INDEX
+
+
+def select_hypotheses(scores: np.ndarray, token_ids: np.ndarray, rank: int,
+                      index_to_word: List[str]) -> Tuple[List[List[str]], float]:
+    """Host post-processing of a finished search (beamsearch_runner.py:81-103, `prepare_results`).
+
+    `scores` is [batch, beam] (best first), `token_ids` is [time, batch, beam] with the start symbol
+    in slot 0.  Returns the words of every sentence's `rank`-th hypothesis up to (excluding) the
+    first </s>, and the runner's loss: the sum of the selected hypotheses' scores.
+
+    One deliberate difference: a hypothesis that is empty (its first symbol is </s>) comes out as
+    `[]`.  The reference assigns the word list inside the token loop (:94), so for an empty
+    hypothesis it leaves the raw array of token ids in the output batch; the test documents this."""
+    bs_scores = [s[rank - 1] for s in scores]
+    decoded_tokens = []
+    for toks in np.transpose(token_ids, [1, 2, 0]):
+        decoded = []
+        for tok_id in toks[rank - 1][1:]:
+            if tok_id == END_TOKEN_INDEX:
+                break
+            decoded.append(index_to_word[tok_id])
+        decoded_tokens.append(decoded)
+    return decoded_tokens, float(np.mean(bs_scores) * len(bs_scores))
 
 
 class BeamSearchRunner(BaseRunner):
@@ -16,22 +39,12 @@ class BeamSearchRunner(BaseRunner):
             if self.num_sessions != 1:
                 raise NotImplementedError("beam search ensembles (num_sessions > 1) are not built")
             output = runner.decoder.outputs.last_search_step_output
-            scores = output.scores.cpu().numpy()
-            bs_scores = [s[runner.rank - 1] for s in scores]
-            tok_ids = np.transpose(output.token_ids.cpu().numpy(), [1, 2, 0])
-            index_to_word = runner.decoder.vocabulary.index_to_word
-            decoded_tokens = []
-            for toks in tok_ids:
-                decoded = []
-                for tok_id in toks[runner.rank - 1][1:]:
-                    if tok_id == END_TOKEN_INDEX:
-                        break
-                    decoded.append(index_to_word[tok_id])
-                decoded_tokens.append(decoded)
+            decoded_tokens, loss = select_hypotheses(
+                output.scores.cpu().numpy(), output.token_ids.cpu().numpy(), runner.rank,
+                runner.decoder.vocabulary.index_to_word)
             if runner.postprocess is not None:
                 decoded_tokens = runner.postprocess(decoded_tokens)
-            self.set_runner_result(outputs=decoded_tokens,
-                                   losses=[float(np.mean(bs_scores) * len(bs_scores))])
+            self.set_runner_result(outputs=decoded_tokens, losses=[loss])
 
     def __init__(self, output_series: str, decoder: BeamSearchDecoder, rank: int = 1,
                  postprocess: Callable[[List[str]], List[str]] = None) -> None:

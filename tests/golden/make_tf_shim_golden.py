@@ -202,6 +202,30 @@ def main():
         last = dec.layer(depth, shim.t(dec_in), shim.t(dec_mask))
     out.update({"tdec_in": dec_in, "tdec_mask": dec_mask, "tdec_states": np.asarray(last.temporal_states)})
     out["transformer_dense_names"] = np.array(sorted(set(shim.USED)))
+
+    # ---- the Transformer decoder's own loops: train_loop_result (decoders/transformer.py:393-453), the
+    #      run-time decoding_loop with next_state (:487-516) re-running the prefix, and - further below -
+    #      a whole beam search around it (three sentences, encoder states tiled to the beam by
+    #      BeamSearchDecoder.outputs) ------------------------------------------------------------------------------
+    tvsz, tmax = 11, 6
+    ttable = f32(tvsz, dim, scale=0.6)
+    tgold = np.array([[5, 6, 2, 0, 0], [7, 8, 9, 4, 2], [4, 2, 0, 0, 0]], np.int64).T
+    dec.__dict__.update(dict(
+        vocabulary=list(range(tvsz)), supress_unk=False, max_output_len=tmax, batch_size=3, tie_embeddings=True,
+        _embedding_matrix_cached_placeholder=shim.t(ttable),
+        _go_symbols_cached_placeholder=shim.t(np.full((3,), 1, np.int64)),
+        _train_inputs_cached_placeholder=shim.t(tgold)))
+    out.update({"tloop_table": ttable.copy(), "tloop_gold": tgold})
+    train_ls = dec.train_loop_result
+    out["tloop_train_logits"] = np.asarray(train_ls.histories.logits)
+    out["tloop_train_states"] = np.asarray(train_ls.histories.output_states)
+    out["tloop_train_input_symbols"] = np.asarray(dec.train_input_symbols)
+    run_ls = dec.decoding_loop(train_mode=False)
+    out["tloop_run_logits"] = np.asarray(run_ls.histories.logits)
+    out["tloop_run_symbols"] = np.asarray(run_ls.histories.output_symbols)
+    out["tloop_run_mask"] = np.asarray(run_ls.histories.output_mask)
+    out["tloop_run_input_mask"] = np.asarray(run_ls.feedables.other.input_mask)
+    transformer_parent = dec
     # ---- one beam search step: BeamSearchDecoder.get_body()() (decoders/beam_search_decoder.py:385-558)
     #      around a stand-in parent decoder whose body returns given logits -----------------------------------
     from neuralmonkey.decoders import beam_search_decoder as bsd
@@ -307,8 +331,10 @@ def main():
     from neuralmonkey.decoders.decoder import Decoder
     from neuralmonkey.decoders.autoregressive import LoopState
 
-    def rnn_decoder_case(tag, hsz, esz, maxout, use_mask):
-        nb, tx, csz, asz, vsz, max_len = 4, 6, 10, 8, 13, 6
+    built = {}
+
+    def rnn_decoder_case(tag, hsz, esz, maxout, use_mask, nb=4, modes=("train", "run"), eos_bonus=0.0):
+        tx, csz, asz, vsz, max_len = 6, 10, 8, 13, 6
         dname, aname = "rd_" + tag, "ra_" + tag
         first = len(shim.VARIABLES)
         var = shim.VARIABLES
@@ -331,13 +357,14 @@ def main():
         for name in list(var)[first:]:
             out["rv::" + name] = var[name]
         states, enc_out = f32(nb, tx, csz), f32(nb, csz)
-        amask = np.array([[1, 1, 1, 1, 1, 1], [1, 1, 1, 1, 0, 0], [1, 1, 0, 0, 0, 0], [1, 0, 0, 0, 0, 0]], np.float32)
+        amask = np.array([[1, 1, 1, 1, 0, 0], [1, 1, 1, 1, 1, 1], [1, 1, 0, 0, 0, 0], [1, 0, 0, 0, 0, 0]], np.float32)[:nb]
         dec_w, dec_b, table = f32(esz, vsz, scale=0.8), f32(vsz, scale=0.3), f32(vsz, esz)
-        gold = np.array([[5, 6, 7, 2, 0, 0], [7, 8, 9, 4, 3, 2], [4, 2, 0, 0, 0, 0], [3, 11, 12, 10, 2, 0]], np.int64).T
+        dec_b[2] += eos_bonus
+        gold = np.array([[5, 6, 7, 2, 0, 0], [7, 8, 9, 4, 3, 2], [4, 2, 0, 0, 0, 0], [3, 11, 12, 10, 2, 0]], np.int64)[:nb].T
         out.update({"rd_{}_states".format(tag): states, "rd_{}_enc_out".format(tag): enc_out,
                     "rd_{}_mask".format(tag): amask, "rd_{}_w".format(tag): dec_w, "rd_{}_b".format(tag): dec_b,
                     "rd_{}_table".format(tag): table, "rd_{}_gold".format(tag): gold})
-        for mode in ("train", "run"):
+        for mode in modes:
             att = object.__new__(Attention)
             att.__dict__.update(dict(
                 _variable_scope=shim.VarScope(aname), _reuse=None, _name=aname, _state_size=asz, batch_size=nb,
@@ -356,7 +383,11 @@ def main():
                 _output_projection_spec=maxout_output(esz) if maxout else None, _conditional_gru=False,
                 _attention_on_input=False, _rnn_cell_str="GRU", _rnn_size=hsz, _encoder_projection=None,
                 attentions=[att], step_scope=shim.VarScope(dname + "/attention_decoder"),
+                encoder_states=lambda: [], encoder_masks=lambda: [],
                 input_projection=lambda *args: LoopState(*args).feedables.embedded_input))
+            built[tag] = rd
+            if mode == "build":
+                return
             shim.USED[:] = []
             shim.GRUCell.CALLS[:] = []
             body = rd.get_body(train_mode=(mode == "train"))
@@ -378,6 +409,49 @@ def main():
 
     rnn_decoder_case("maxout", hsz=7, esz=5, maxout=True, use_mask=True)
     rnn_decoder_case("tanh", hsz=6, esz=6, maxout=False, use_mask=False)
+
+    # ---- a whole beam search: BeamSearchDecoder.get_initial_loop_state / loop_continue_criterion / get_body
+    #      (decoders/beam_search_decoder.py:218-558) around the reference's own attention Decoder, one
+    #      sentence (the reference's RNN decoder does not tile the encoder states to the beam) --------------
+    def beam_search_case(tag, parent, bsz, beam, alpha, max_steps):
+        bs = object.__new__(bsd.BeamSearchDecoder)
+        bs.__dict__.update(dict(parent_decoder=parent, beam_size=beam, batch_size=bsz, length_normalization=alpha,
+                                max_steps_int=max_steps, max_steps=max_steps, _initial_loop_state=None,
+                                _variable_scope=shim.VarScope("bs_" + tag), _reuse=None, _name="bs_" + tag))
+        result = bs.outputs               # the reference's own driver: initial state + tf.while_loop
+        state = bs.initial_loop_state
+        pre = "bsearch_{}_".format(tag)
+        out[pre + "init_token_ids"] = np.asarray(state.search_results.token_ids)
+        out[pre + "init_prev_logprobs"] = np.asarray(state.search_state.prev_logprobs)
+        out[pre + "init_logprob_sum"] = np.asarray(state.search_state.logprob_sum)
+        state = types.SimpleNamespace(search_results=result.last_search_step_output,
+                                      search_state=result.last_search_state)
+        steps = np.asarray(state.search_results.token_ids).shape[0] - 1
+        out.update({pre + "steps": np.int64(steps), pre + "alpha": np.float32(alpha), pre + "beam": np.int64(beam),
+                    pre + "max_steps": np.int64(max_steps),
+                    pre + "scores": np.asarray(state.search_results.scores),
+                    pre + "token_ids": np.asarray(state.search_results.token_ids),
+                    pre + "logprob_sum": np.asarray(state.search_state.logprob_sum),
+                    pre + "lengths": np.asarray(state.search_state.lengths),
+                    pre + "finished": np.asarray(state.search_state.finished)})
+
+    beam_search_case("tr", transformer_parent, bsz=3, beam=3, alpha=0.6, max_steps=5)
+    ttable[2] = ttable[2] * 2.5              # tied embeddings: a long </s> row makes hypotheses finish early
+    transformer_parent._embedding_matrix_cached_placeholder = shim.t(ttable)
+    del transformer_parent.__dict__["_decoding_w_cached_placeholder"]
+    out["tloop_table_eos"] = ttable.copy()
+    beam_search_case("tr_eos", transformer_parent, bsz=3, beam=4, alpha=1.0, max_steps=6)
+    run_ls = transformer_parent.decoding_loop(train_mode=False)
+    out["tloop_run_eos_logits"] = np.asarray(run_ls.histories.logits)
+    out["tloop_run_eos_symbols"] = np.asarray(run_ls.histories.output_symbols)
+    out["tloop_run_eos_mask"] = np.asarray(run_ls.histories.output_mask)
+    out["tloop_run_eos_input_mask"] = np.asarray(run_ls.feedables.other.input_mask)
+    rnn_decoder_case("beam", hsz=7, esz=5, maxout=True, use_mask=True, nb=1, modes=("build",))
+    beam_search_case("rnn", built["beam"], bsz=1, beam=3, alpha=0.6, max_steps=6)
+    rnn_decoder_case("beam1", hsz=6, esz=6, maxout=False, use_mask=True, nb=1, modes=("build",), eos_bonus=2.0)
+    beam_search_case("rnn1", built["beam1"], bsz=1, beam=4, alpha=1.0, max_steps=5)
+    rnn_decoder_case("beam2", hsz=6, esz=6, maxout=False, use_mask=False, nb=1, modes=("build",), eos_bonus=3.5)
+    beam_search_case("rnn2", built["beam2"], bsz=1, beam=2, alpha=0.0, max_steps=12)
 
     # ---- the recurrent encoder: model/sequence.py EmbeddedFactorSequence.temporal_states / temporal_mask and
     #      encoders/recurrent.py RecurrentEncoder.rnn + rnn_layer, over the shim's restatement of

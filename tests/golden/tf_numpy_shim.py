@@ -34,7 +34,7 @@ class Shape(tuple):
     """What `tensor.shape` / `get_shape()` return: a tuple with `.as_list()` and `.ndims`."""
 
     def __new__(cls, dims=()):
-        return super().__new__(cls, [Dim(d) for d in dims])
+        return super().__new__(cls, [None if d is None else Dim(d) for d in dims])
 
     def as_list(self):
         return list(self)
@@ -304,6 +304,14 @@ def _bidirectional_dynamic_rnn(cell_fw, cell_bw, inputs, sequence_length=None, d
     return (out_fw, out_bw), (st_fw, st_bw)
 
 
+def _while_loop(cond, body, loop_vars, shape_invariants=None, **kwargs):
+    """tf.while_loop run eagerly: the loop variables are one (named) tuple passed unpacked."""
+    state = loop_vars
+    while bool(np.asarray(cond(*state))):
+        state = body(*state)
+    return state
+
+
 def install():
     """Put the shim into sys.modules as `tensorflow` and return it."""
     tf = _Namespace("tensorflow")
@@ -321,16 +329,18 @@ def install():
     tf.rsqrt = lambda x: t(1.0 / np.sqrt(np.asarray(x, np.float32)), np.float32)
     tf.square = lambda x: t(np.square(np.asarray(x)))
     tf.tanh = lambda x: t(np.tanh(np.asarray(x, np.float32)), np.float32)
-    tf.zeros = lambda shape, dtype=None, name=None: t(np.zeros([int(d) for d in shape], dtype or np.float32))
+    tf.zeros = lambda shape, dtype=None, name=None: t(np.zeros(
+        [int(d) for d in (shape if isinstance(shape, (list, tuple)) else [shape])], dtype or np.float32))
     tf.reduce_sum = lambda x, axis=None, keepdims=False: t(
         np.sum(np.asarray(x), axis=tuple(axis) if isinstance(axis, list) else axis, keepdims=keepdims))
     tf.Variable = T
     tf.minimum = lambda a, b: t(np.minimum(a, b))
     tf.mod = lambda a, b: t(np.mod(np.asarray(a), b)) if isinstance(a, np.ndarray) else np.mod(a, b)
-    tf.expand_dims = lambda x, axis: t(np.expand_dims(np.asarray(x), axis))
+    tf.expand_dims = lambda x, axis: t(np.expand_dims(
+        np.asarray(x, np.float32) if isinstance(x, list) else np.asarray(x), axis))
     tf.concat = lambda values, axis: t(np.concatenate([np.asarray(v) for v in values], axis=axis))
     tf.pad = _pad
-    tf.reshape = lambda x, shape: t(np.reshape(np.asarray(x), [int(s) for s in shape]))
+    tf.reshape = lambda x, shape, name=None: t(np.reshape(np.asarray(x), [int(s) for s in shape]))
     tf.shape = lambda x: Shape(np.asarray(x).shape)
     tf.transpose = lambda x, perm=None: t(np.transpose(np.asarray(x), perm))
     tf.ones_like = lambda x: t(np.ones_like(np.asarray(x)))
@@ -368,7 +378,8 @@ def install():
     tf.nn.top_k = _top_k
     tf.nn.log_softmax = _log_softmax
     tf.one_hot = _one_hot
-    tf.tile = lambda x, multiples: t(np.tile(np.asarray(x), [int(m) for m in multiples]))
+    tf.tile = lambda x, multiples, name=None: t(np.tile(np.asarray(x), [int(m) for m in multiples]))
+    tf.placeholder_with_default = lambda x, shape=None, name=None: x
     tf.stack = lambda values, axis=0: t(np.stack([np.asarray(v) for v in values], axis=axis))
     tf.div = lambda a, b: t(np.floor_divide(np.asarray(a), b))
     tf.logical_or = lambda a, b: t(np.logical_or(a, b))
@@ -390,6 +401,9 @@ def install():
     tf.nn.bidirectional_dynamic_rnn = _bidirectional_dynamic_rnn
     tf.reverse_sequence = _reverse_sequence
     tf.not_equal = lambda a, b: t(np.not_equal(a, b))
+    tf.while_loop = _while_loop
+    tf.control_dependencies = _name_scope_cm
+    tf.squeeze = lambda x, axis=None: t(np.squeeze(np.asarray(x), axis=axis))
     tf.orthogonal_initializer = lambda *a, **k: None
     tf.random_normal_initializer = lambda *a, **k: None
     sys.modules["tensorflow"] = tf

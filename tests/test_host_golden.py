@@ -133,3 +133,52 @@ def test_writers_match_reference(golden, tmp_path):
     # per-example arrays of different length (bucketed batches) still save
     AutoWriter(str(tmp_path / "h"), [np.ones(3), np.ones(5)])
     assert len(np.load(str(tmp_path / "h.npy"), allow_pickle=True)) == 2
+
+
+@pytest.fixture(scope="module")
+def runner_golden():
+    return json.load(open(os.path.join(HERE, "golden", "runner_golden.json")))
+
+
+def test_beam_search_runner_postprocessing_matches_reference(runner_golden, tmp_path):
+    """runners/beamsearch_runner.py prepare_results (:81-103), run on the same final beam: the rank-th
+    hypothesis without the start slot up to </s>, loss = sum of the selected scores, and the name of
+    the loss.  An EMPTY hypothesis is where the product deliberately differs: the reference leaves the
+    raw id array in the batch (the assignment sits inside its token loop), the product returns []."""
+    from neuralmonkey_b200.runners.beamsearch_runner import BeamSearchRunner, select_hypotheses
+    vocab = _vocab(tmp_path, runner_golden["words"])
+    beam = runner_golden["beam"]
+    scores, token_ids = np.array(beam["scores"], np.float32), np.array(beam["token_ids"], np.int64)
+    saw_empty = False
+    for rank, want in beam["ranks"].items():
+        outputs, loss = select_hypotheses(scores, token_ids, int(rank), vocab.index_to_word)
+        assert len(outputs) == want["size"]
+        for got_sentence, want_sentence in zip(outputs, want["outputs"]):
+            if isinstance(want_sentence, dict):
+                assert got_sentence == [] and want_sentence["raw_ids"][0] == 2
+                saw_empty = True
+            else:
+                assert got_sentence == want_sentence
+        (name, value), = want["losses"].items()
+        assert name == "target.rank{:03d}/beam_search_score".format(int(rank))
+        assert abs(loss - value) < 1e-6
+    assert saw_empty
+    runner = object.__new__(BeamSearchRunner)
+    assert runner.loss_names == ["beam_search_score"]
+
+
+def test_greedy_runner_postprocessing_matches_reference(runner_golden, tmp_path):
+    """runners/runner.py collect_results (:33-62) with one session: argmax of the fetched log-probs
+    over the FULL vocabulary per step, `vectors_to_sentences`, the postprocessor, and the loss names.
+    (The product takes the argmax on the device and copies [T, B] ids instead of [T, B, V] floats.)"""
+    from neuralmonkey_b200.runners.runner import GreedyRunner
+    vocab = _vocab(tmp_path, runner_golden["words"])
+    for case, post in (("greedy_single", None), ("greedy_post", lambda ss: [[w.upper() for w in s] for s in ss])):
+        want = runner_golden[case]
+        symbols = np.argmax(np.array(want["logprobs"][0], np.float32), axis=-1)       # [T, B]
+        outputs = vocab.vectors_to_sentences(symbols)
+        if post is not None:
+            outputs = post(outputs)
+        assert outputs == want["outputs"] and want["size"] == symbols.shape[1]
+        assert sorted(want["losses"]) == sorted("target/" + n for n in object.__new__(GreedyRunner).loss_names)
+        assert abs(want["losses"]["target/train_xent"] - want["train_xent"][0]) < 1e-12

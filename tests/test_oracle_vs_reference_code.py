@@ -333,3 +333,117 @@ def test_product_declares_the_variables_the_reference_asks_for():
     for i, layer in enumerate(layers):
         got.update("re_deep/" + scope + "/" for scope in RecurrentEncoder._cell_scopes(enc, i, _make_rnn_spec(*layer)))
     assert got == want
+
+
+@pytest.mark.parametrize("tag,dtag,maxout,use_mask", [("rnn", "beam", True, True), ("rnn1", "beam1", False, True),
+                                                      ("rnn2", "beam2", False, False)])
+def test_whole_beam_search_over_the_attention_decoder(tag, dtag, maxout, use_mask):
+    """BeamSearchDecoder.get_initial_loop_state / loop_continue_criterion / get_body
+    (decoders/beam_search_decoder.py:218-558) run to the end around the reference's own attention
+    Decoder (one sentence: the reference's RNN decoder does not tile encoder states to the beam),
+    against the oracle's beam_search over its decoder_step: hypotheses, scores, lengths, finished
+    flags, number of steps (max_steps reached / all finished), and the first-step log-probs."""
+    dname, aname, pre = "rd_" + dtag, "ra_" + dtag, "bsearch_{}_".format(tag)
+    p = {k[4:]: _t(k) for k in G.files if k.startswith("rv::" + dname + "/") or k.startswith("rv::" + aname + "/")}
+    p[dname + "/word_embeddings"] = _t(dname + "_table")
+    p[dname + "/state_to_word_W"], p[dname + "/state_to_word_b"] = _t(dname + "_w"), _t(dname + "_b")
+    spec = O.RNNDecoderSpec(dname, aname, max_output_len=6, output_projection="maxout" if maxout else "tanh")
+    states, mask = _t(dname + "_states"), (_t(dname + "_mask") if use_mask else None)
+    beam, alpha, max_steps = int(G[pre + "beam"]), float(G[pre + "alpha"]), int(G[pre + "max_steps"])
+    hidden = O.bahdanau_precompute(p, aname, states)
+    emb = p[dname + "/word_embeddings"]
+
+    def run_step(prev_output, words):
+        output, cell, _ctx, _w = O.decoder_step(p, spec, emb[words], prev_output, hidden, states, mask)
+        return cell, torch.log_softmax(O.state_to_logits(p, spec, output), -1)
+
+    init = O.decoder_initial_state(p, spec, _t(dname + "_enc_out")).repeat_interleave(beam, 0)
+    state, first = run_step(init, torch.full((beam,), O.START, dtype=torch.int64))
+    assert np.abs(first.reshape(1, beam, -1).numpy() - G[pre + "init_prev_logprobs"]).max() < 5e-6
+    assert np.array_equal(G[pre + "init_logprob_sum"][0, 1:], np.full(beam - 1, -1e9, np.float32))
+    calls = {"n": 0}
+
+    def step_fn(st, words, _finished):
+        calls["n"] += 1
+        return run_step(st, words)
+
+    got = O.beam_search(step_fn, state, first, beam, max_steps, alpha, lambda st, idx: st[idx])
+    assert calls["n"] == int(G[pre + "steps"])
+    # slot 0 of the reference's token history holds the first step's greedy symbol (:301-313), which
+    # the runner drops (beamsearch_runner.py:84); the hypotheses start at slot 1
+    assert np.array_equal(got["token_ids"].numpy(), G[pre + "token_ids"][1:])
+    assert np.array_equal(got["lengths"].numpy(), G[pre + "lengths"])
+    assert np.array_equal(got["finished"].numpy(), G[pre + "finished"])
+    assert np.abs(got["scores"].numpy() - G[pre + "scores"]).max() < 5e-6
+    assert np.array_equal(G[pre + "init_token_ids"].reshape(-1), np.full(beam, int(first[0].argmax())))
+
+
+def _transformer_setup(table_key="tloop_table"):
+    p = {k[4:]: torch.from_numpy(G[k]) for k in G.files if k.startswith("tv::")}
+    p["tdec/word_embeddings"] = _t(table_key)
+    spec = O.TransformerDecoderSpec("tdec", 2, 3, 2, 6, tie_embeddings=True)
+    enc = {"states": _t("tenc_states"), "mask": _t("tenc_mask")}
+    return p, spec, enc
+
+
+def test_transformer_decoder_training_pass():
+    """TransformerDecoder.train_loop_result (decoders/transformer.py:393-453) run whole: inputs are
+    <s> + gold[:-1] embedded WITHOUT the position signal, the self-attention mask is the gold mask,
+    logits come from the transposed embedding matrix (tie_embeddings, zero bias)."""
+    p, spec, enc = _transformer_setup()
+    gold = torch.from_numpy(G["tloop_gold"]).t().contiguous()                     # [B, T]
+    assert np.array_equal(G["tloop_train_input_symbols"][:, 1:], gold[:, :-1].numpy())
+    assert np.array_equal(G["tloop_train_input_symbols"][:, 0], np.full(gold.shape[0], O.START))
+    train = O.transformer_decoder_train(p, spec, enc, gold)
+    assert np.abs(train["logits"].transpose(0, 1).numpy() - G["tloop_train_logits"]).max() < 5e-5
+    assert np.abs(train["states"].transpose(0, 1).numpy() - G["tloop_train_states"]).max() < 2e-5
+
+
+@pytest.mark.parametrize("case,table", [("run", "tloop_table"), ("run_eos", "tloop_table_eos")])
+def test_transformer_decoder_greedy_loop(case, table):
+    """AutoregressiveDecoder.decoding_loop(train_mode=False) around TransformerDecoder.next_state
+    (:487-516): the prefix is re-run at every step, and the self-attention mask column appended at a
+    step is `not finished` as it stood BEFORE that step's symbol was chosen."""
+    p, spec, enc = _transformer_setup(table)
+    got = O.transformer_decoder_greedy(p, spec, enc)
+    assert np.array_equal(got["symbols"].numpy(), G["tloop_{}_symbols".format(case)])
+    assert np.array_equal(got["mask"].numpy(), G["tloop_{}_mask".format(case)])
+    assert np.abs(got["logits"].numpy() - G["tloop_{}_logits".format(case)]).max() < 5e-5
+    input_mask = G["tloop_{}_input_mask".format(case)][..., 0]
+    finished_before = np.concatenate([np.zeros((1, input_mask.shape[0]), bool),
+                                      ~G["tloop_{}_mask".format(case)][:-1]], 0)
+    assert np.array_equal(input_mask, (~finished_before).T.astype(np.float32))
+
+
+@pytest.mark.parametrize("tag,table", [("tr", "tloop_table"), ("tr_eos", "tloop_table_eos")])
+def test_whole_beam_search_over_the_transformer_decoder(tag, table):
+    """BeamSearchDecoder.outputs (:167-191: encoder states and masks tiled to the beam, initial loop
+    state, tf.while_loop) around the reference's TransformerDecoder, three sentences."""
+    p, spec, enc = _transformer_setup(table)
+    pre = "bsearch_{}_".format(tag)
+    beam, alpha, max_steps = int(G[pre + "beam"]), float(G[pre + "alpha"]), int(G[pre + "max_steps"])
+    emb = p["tdec/word_embeddings"]
+    states, emask = enc["states"].repeat_interleave(beam, 0), enc["mask"].repeat_interleave(beam, 0)
+    rows = states.shape[0]
+
+    def run(seq, mask):
+        out = O.transformer_decoder_stack(p, spec, seq, mask, states, emask)
+        return torch.log_softmax(O.transformer_logits(p, spec, out[:, -1]), -1)
+
+    seq0 = emb[torch.full((rows,), O.START, dtype=torch.int64)].unsqueeze(1)
+    mask0 = torch.ones(rows, 1)
+    first = run(seq0, mask0)
+    assert np.abs(first.reshape(-1, beam, first.shape[-1]).numpy() - G[pre + "init_prev_logprobs"]).max() < 5e-5
+
+    def step_fn(state, words, finished):
+        seq = torch.cat([state[0], emb[words].unsqueeze(1)], 1)
+        mask = torch.cat([state[1], (~finished).to(emb.dtype).unsqueeze(1)], 1)
+        return (seq, mask), run(seq, mask)
+
+    got = O.beam_search(step_fn, (seq0, mask0), first, beam, max_steps, alpha,
+                        lambda st, idx: (st[0][idx], st[1][idx]))
+    assert got["token_ids"].shape[0] == int(G[pre + "steps"])
+    assert np.array_equal(got["token_ids"].numpy(), G[pre + "token_ids"][1:])
+    assert np.array_equal(got["lengths"].numpy(), G[pre + "lengths"])
+    assert np.array_equal(got["finished"].numpy(), G[pre + "finished"])
+    assert np.abs(got["scores"].numpy() - G[pre + "scores"]).max() < 2e-5
