@@ -333,7 +333,8 @@ def main():
 
     built = {}
 
-    def rnn_decoder_case(tag, hsz, esz, maxout, use_mask, nb=4, modes=("train", "run"), eos_bonus=0.0):
+    def rnn_decoder_case(tag, hsz, esz, maxout, use_mask, nb=4, modes=("train", "run", "loss"), eos_bonus=0.0,
+                         short_gold=False):
         tx, csz, asz, vsz, max_len = 6, 10, 8, 13, 6
         dname, aname = "rd_" + tag, "ra_" + tag
         first = len(shim.VARIABLES)
@@ -361,6 +362,8 @@ def main():
         dec_w, dec_b, table = f32(esz, vsz, scale=0.8), f32(vsz, scale=0.3), f32(vsz, esz)
         dec_b[2] += eos_bonus
         gold = np.array([[5, 6, 7, 2, 0, 0], [7, 8, 9, 4, 3, 2], [4, 2, 0, 0, 0, 0], [3, 11, 12, 10, 2, 0]], np.int64)[:nb].T
+        if short_gold:                       # training ends after 4 steps, the run-time loop goes on: min_time
+            gold = np.array([[5, 6, 7, 2], [7, 8, 2, 0], [4, 2, 0, 0], [3, 11, 12, 2]], np.int64)[:nb].T
         out.update({"rd_{}_states".format(tag): states, "rd_{}_enc_out".format(tag): enc_out,
                     "rd_{}_mask".format(tag): amask, "rd_{}_w".format(tag): dec_w, "rd_{}_b".format(tag): dec_b,
                     "rd_{}_table".format(tag): table, "rd_{}_gold".format(tag): gold})
@@ -373,6 +376,7 @@ def main():
             rd = object.__new__(Decoder)
             rd.__dict__.update(dict(
                 vocabulary=list(range(vsz)), supress_unk=False, max_output_len=max_len, batch_size=nb,
+                label_smoothing=None,
                 dropout_keep_prob=1.0, train_mode=None, _embedding_size=esz, embeddings_source=None,
                 _variable_scope=shim.VarScope(dname), _reuse=None, _name=dname,
                 _decoding_w_cached_placeholder=shim.t(dec_w), _decoding_b_cached_placeholder=shim.t(dec_b),
@@ -388,6 +392,12 @@ def main():
             built[tag] = rd
             if mode == "build":
                 return
+            if mode == "loss":                   # the lazily built loss tensors (autoregressive.py:292-371)
+                key = "rd_{}_".format(tag)
+                for attr in ("train_xents", "train_loss", "train_mask", "runtime_xents", "runtime_loss", "decoded",
+                             "runtime_logprobs", "runtime_mask"):
+                    out[key + attr] = np.asarray(getattr(rd, attr))
+                continue
             shim.USED[:] = []
             shim.GRUCell.CALLS[:] = []
             body = rd.get_body(train_mode=(mode == "train"))
@@ -408,7 +418,7 @@ def main():
         out["rd_{}_cell_scopes".format(tag)] = np.array(sorted({c[0] for c in shim.GRUCell.CALLS}))
 
     rnn_decoder_case("maxout", hsz=7, esz=5, maxout=True, use_mask=True)
-    rnn_decoder_case("tanh", hsz=6, esz=6, maxout=False, use_mask=False)
+    rnn_decoder_case("tanh", hsz=6, esz=6, maxout=False, use_mask=False, short_gold=True)
 
     # ---- a whole beam search: BeamSearchDecoder.get_initial_loop_state / loop_continue_criterion / get_body
     #      (decoders/beam_search_decoder.py:218-558) around the reference's own attention Decoder, one
@@ -506,6 +516,50 @@ def main():
     recurrent_case("deep", [3, 1], [(4, "forward"), (4, "backward"), (2, "bidirectional"), (3, "bidirectional")],
                    True, True, True, True)
     recurrent_case("plain", [4], [(3, "backward"), (3, "forward")], True, False, False, False)
+
+    # ---- the trainer's host logic: GenericTrainer.regularization_losses / differentiable_loss_sum /
+    #      gradients (per-tensor clip_by_norm) / collect_results (trainers/generic_trainer.py:84-195,27-50),
+    #      around an optimizer stand-in that hands back given gradients -------------------------------------------
+    from neuralmonkey.trainers.generic_trainer import GenericTrainer
+    names = ["enc/rnn/gates/kernel:0", "enc/rnn/gates/bias:0", "dec/attn_projection_bias:0", "dec/attn_bias:0",
+             "dec/state_to_word_W:0", "dec/state_to_word_b:0", "vgg_16/conv1/conv1_1/weights:0",
+             "enc/LayerNorm/gamma:0", "dec/Bias_like/kernel:0", "resnet_thing/w:0", "Inception/w:0"]
+    shim.TRAINABLE[:] = []
+    grads = []
+    for i, name in enumerate(names):
+        var = shim.t(f32(3, 4 + i, scale=0.7))
+        var.name = name
+        shim.TRAINABLE.append(var)
+        grads.append(None if i == 3 else shim.t(f32(3, 4 + i, scale=[0.05, 2.0][i % 2])))
+        out["trn_var::" + name] = np.asarray(var)
+        if grads[-1] is not None:
+            out["trn_grad::" + name] = np.asarray(grads[-1])
+    seen = {}
+
+    class FakeOptimizer:
+        def compute_gradients(self, loss, var_list):
+            seen["loss"], seen["vars"] = loss, [v.name for v in var_list]
+            return list(zip(grads, var_list))
+
+    objectives = [types.SimpleNamespace(name="dec_a", loss=shim.t(np.float32(2.5)), gradients=None, weight=None),
+                  types.SimpleNamespace(name="dec_b", loss=shim.t(np.float32(1.25)), gradients=None, weight=0.3)]
+    trainer = object.__new__(GenericTrainer)
+    trainer.__dict__.update(dict(objectives=objectives, l1_weight=1e-4, l2_weight=1e-8, clip_norm=1.0, var_scopes=None,
+                                 var_collection="trainable_variables", optimizer=FakeOptimizer()))
+    l1, l2 = trainer.regularization_losses
+    clipped = trainer.gradients
+    out.update({"trn_l1": np.float32(l1), "trn_l2": np.float32(l2), "trn_diff_loss": np.float32(seen["loss"]),
+                "trn_objective_values": np.asarray([np.float32(v) for v in trainer.objective_values]),
+                "trn_var_list": np.array(seen["vars"]), "trn_clipped_names": np.array([v.name for _, v in clipped])})
+    for grad, var in clipped:
+        out["trn_clipped::" + var.name] = np.asarray(grad)
+    ex = object.__new__(GenericTrainer.Executable)
+    ex._executor, ex.summaries = trainer, False
+    ex.collect_results([{"losses": [2.5, 1.25, float(l1), float(l2)], "batch_size": 7}])
+    out["trn_loss_names"] = np.array(list(ex.result.losses))
+    trainer2 = object.__new__(GenericTrainer)
+    trainer2.__dict__.update(dict(var_scopes=["enc", "dec/state"], var_collection="trainable_variables"))
+    out["trn_scoped_var_list"] = np.array([v.name for v in trainer2.var_list])
     np.savez_compressed(os.path.join(HERE, "tf_shim_golden.npz"), **out)
     print(sorted(out))
 

@@ -103,6 +103,7 @@ class _Namespace(types.ModuleType):
 VARIABLES = {}      # full variable name -> numpy array (layer_norm gamma / beta ...)
 DENSE = {}          # dense layer name -> (kernel, bias or None)
 USED = []           # full names of the dense kernels that were looked up (checks the naming scheme)
+TRAINABLE = []      # what tf.trainable_variables() returns: T arrays with a `.name`
 _scope = []
 GLOBAL_STEP = [0]
 
@@ -304,6 +305,16 @@ def _bidirectional_dynamic_rnn(cell_fw, cell_bw, inputs, sequence_length=None, d
     return (out_fw, out_bw), (st_fw, st_bw)
 
 
+def _sequence_loss(logits, targets, weights, average_across_timesteps=True, average_across_batch=True,
+                   softmax_loss_function=None, name=None):
+    """tf.contrib.seq2seq.sequence_loss as TensorFlow documents it (library code, restated), for the
+    only way the reference calls it: no averaging, default loss => weights * sparse softmax xent."""
+    assert not average_across_timesteps and not average_across_batch and softmax_loss_function is None
+    logprobs = np.asarray(_log_softmax(logits))
+    picked = np.take_along_axis(logprobs, np.asarray(targets)[..., None].astype(np.int64), -1)[..., 0]
+    return t(-picked * np.asarray(weights, np.float32), np.float32)
+
+
 def _while_loop(cond, body, loop_vars, shape_invariants=None, **kwargs):
     """tf.while_loop run eagerly: the loop variables are one (named) tuple passed unpacked."""
     state = loop_vars
@@ -402,6 +413,14 @@ def install():
     tf.reverse_sequence = _reverse_sequence
     tf.not_equal = lambda a, b: t(np.not_equal(a, b))
     tf.while_loop = _while_loop
+    tf.trainable_variables = lambda: list(TRAINABLE)
+    tf.get_collection = lambda key, scope=None: [v for v in TRAINABLE if scope is None or v.name.startswith(scope)]
+    tf.GraphKeys = types.SimpleNamespace(TRAINABLE_VARIABLES="trainable_variables")
+    # tf.clip_by_norm as documented: t * clip_norm / max(l2norm(t), clip_norm)
+    tf.clip_by_norm = lambda g, clip, axes=None, name=None: t(
+        np.asarray(g) * clip / max(float(np.sqrt(np.sum(np.square(np.asarray(g, np.float32))))), clip), np.float32)
+    tf.contrib.seq2seq = _Namespace("tensorflow.contrib.seq2seq")
+    tf.contrib.seq2seq.sequence_loss = _sequence_loss
     tf.control_dependencies = _name_scope_cm
     tf.squeeze = lambda x, axis=None: t(np.squeeze(np.asarray(x), axis=axis))
     tf.orthogonal_initializer = lambda *a, **k: None

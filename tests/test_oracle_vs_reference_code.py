@@ -287,11 +287,21 @@ def test_whole_attention_decoder(tag, maxout, use_mask):
     if use_mask:
         assert float(np.abs(G[key + "att_weights"][:, 3, 1:]).max()) == 0.0     # padded source positions
 
-    run = O.decoder_greedy(p, spec, enc)
+    run = O.decoder_greedy(p, spec, enc, gold)
     key = dname + "_run_"
     assert np.array_equal(run["output_symbols"].numpy(), G[key + "symbols"])
     assert np.array_equal(run["runtime_mask"].numpy(), G[key + "out_mask"])
     assert np.abs(run["runtime_logits"].numpy() - G[key + "logits"]).max() < 5e-6
+    # the loss tensors (autoregressive.py:292-371) over tf.contrib.seq2seq.sequence_loss restated by the
+    # shim: [B, T] xents weighted by the gold mask, token-mean train loss, run-time xents cut to
+    # min(gold, decoded) steps and divided by the number of DECODED (not gold) unfinished positions
+    assert np.abs(train["train_xents"].numpy() - G[dname + "_train_xents"]).max() < 1e-5
+    assert abs(float(train["train_loss"]) - float(G[dname + "_train_loss"])) < 1e-5
+    assert np.array_equal(train["train_mask"].numpy(), G[dname + "_train_mask"])
+    assert np.abs(run["runtime_xents"].numpy() - G[dname + "_runtime_xents"]).max() < 1e-5
+    assert abs(float(run["runtime_loss"]) - float(G[dname + "_runtime_loss"])) < 1e-5
+    assert np.array_equal(run["decoded"].numpy(), G[dname + "_decoded"])
+    assert np.abs(run["runtime_logprobs"].numpy() - G[dname + "_runtime_logprobs"]).max() < 1e-5
 
 
 @pytest.mark.parametrize("tag,layers,residual,layer_norm,final_norm,scale", [
@@ -447,3 +457,36 @@ def test_whole_beam_search_over_the_transformer_decoder(tag, table):
     assert np.array_equal(got["lengths"].numpy(), G[pre + "lengths"])
     assert np.array_equal(got["finished"].numpy(), G[pre + "finished"])
     assert np.abs(got["scores"].numpy() - G[pre + "scores"]).max() < 2e-5
+
+
+def test_trainer_host_logic():
+    """GenericTrainer.regularization_losses / differentiable_loss_sum / gradients / collect_results
+    (trainers/generic_trainer.py:27-50,84-195) around an optimizer stand-in: which variables are
+    regularised ([Bb]ias anywhere in the name and vgg/Inception/resnet prefixes are not; LayerNorm
+    gains and
+    `state_to_word_b` are), loss = sum w_i * objective_i + l1_weight * L1 + l2_weight * L2 with weight None == 1,
+    tf.clip_by_norm PER TENSOR (not global), None gradients dropped, names of the fetched losses."""
+    from neuralmonkey_b200.params import is_regularizable
+    variables = {k[len("trn_var::"):]: _t(k) for k in G.files if k.startswith("trn_var::")}
+    l1, l2 = O.regularization(variables)
+    assert abs(float(l1) - float(G["trn_l1"])) < 1e-4 * float(G["trn_l1"])
+    assert abs(float(l2) - float(G["trn_l2"])) < 1e-4 * float(G["trn_l2"])
+    # `state_to_word_b` IS regularised: the filter is the regex on the name, and that name has no "bias"
+    want_reg = {"enc/rnn/gates/kernel:0", "dec/state_to_word_W:0", "dec/state_to_word_b:0", "enc/LayerNorm/gamma:0"}
+    assert {n for n in variables if O.is_regularizable(n)} == want_reg
+    assert {n for n in variables if is_regularizable(n)} == want_reg            # the product's arena flags
+    assert np.array_equal(G["trn_objective_values"][:2], np.array([2.5, 1.25], np.float32))
+    want_loss = 2.5 * 1.0 + 1.25 * 0.3 + 1e-4 * float(G["trn_l1"]) + 1e-8 * float(G["trn_l2"])
+    assert abs(float(G["trn_diff_loss"]) - want_loss) < 1e-5
+    clipped = G["trn_clipped_names"].tolist()
+    assert "dec/attn_bias:0" not in clipped and len(clipped) == len(variables) - 1
+    some_clipped = some_kept = False
+    for name in clipped:
+        grad = _t("trn_grad::" + name)
+        got = O.clip_by_norm(grad, 1.0)
+        assert np.abs(got.numpy() - G["trn_clipped::" + name]).max() < 1e-6
+        norm = float(grad.pow(2).sum().sqrt())
+        some_clipped |= norm > 1.0
+        some_kept |= norm < 1.0 and np.array_equal(G["trn_clipped::" + name], grad.numpy())
+    assert some_clipped and some_kept
+    assert G["trn_loss_names"].tolist() == ["dec_a", "dec_b", "L1", "L2"]
