@@ -70,11 +70,17 @@ class Decoder(AutoregressiveDecoder):
         if self._rnn_cell_str not in RNN_CELL_TYPES:
             raise ValueError("RNN cell must be a either 'GRU', 'LSTM', or 'NematusGRU'. Not {}"
                              .format(self._rnn_cell_str))
-        if self._rnn_cell_str != "GRU" or conditional_gru or attention_on_input:
+        if attention_on_input:
+            # the reference itself cannot build this option: input_plus_attention reads
+            # `feedables.prev_contexts` (decoder.py:273), which does not exist (the contexts are in
+            # `feedables.other`) - tests/test_oracle_vs_reference_code.py records the AttributeError
+            raise NotImplementedError("attention_on_input=True fails in the reference while the graph is "
+                                      "built (decoders/decoder.py:273); it is not supported here either")
+        if self._rnn_cell_str != "GRU" or conditional_gru:
             raise NotImplementedError(
-                "rnn_cell={}, conditional_gru={}, attention_on_input={}: outside the B200 hot path "
-                "built so far (GRU, no conditional GRU, no input feeding; SURVEY.md 8(f) N4)"
-                .format(rnn_cell, conditional_gru, attention_on_input))
+                "rnn_cell={}, conditional_gru={}: outside the B200 hot path built so far (GRU, no "
+                "conditional GRU; SURVEY.md 8(f) N4 - the oracle already restates both variants)"
+                .format(rnn_cell, conditional_gru))
         for att in self.attentions:
             if hasattr(att, "set_query_size"):
                 att.set_query_size(self.rnn_size)

@@ -207,28 +207,79 @@ class RNNDecoderSpec:
     """Static configuration of decoders.decoder.Decoder for the oracle."""
 
     def __init__(self, prefix: str, att_prefix: str, max_output_len: int,
-                 output_projection: str = "tanh", supress_unk: bool = False) -> None:
+                 output_projection: str = "tanh", supress_unk: bool = False, rnn_cell: str = "GRU",
+                 conditional_gru: bool = False, encoder_projection: str = "linear",
+                 rnn_size: Optional[int] = None, mlp_layers: int = 0) -> None:
         self.prefix = prefix
         self.att_prefix = att_prefix
         self.max_output_len = max_output_len
-        self.output_projection = output_projection  # "tanh" | "maxout"
+        self.output_projection = output_projection  # "tanh" | "maxout" | "nematus" | "mlp"
         self.supress_unk = supress_unk
+        self.rnn_cell = rnn_cell                    # "GRU" | "NematusGRU"
+        self.conditional_gru = conditional_gru
+        self.encoder_projection = encoder_projection  # "linear" | "nematus" | "concat" | "empty"
+        self.rnn_size = rnn_size                    # only read by the "empty" projection
+        self.mlp_layers = mlp_layers
 
 
-def decoder_initial_state(p: Params, spec: RNNDecoderSpec, enc_output: torch.Tensor) -> torch.Tensor:
-    """linear_encoder_projection (encoder_projection.py:47-73); dropout off."""
-    pre = spec.prefix + "/initial_state/encoders_projection/"
-    return enc_output @ p[pre + "kernel"] + p[pre + "bias"]
+def _dense(p: Params, scope: str, x: torch.Tensor) -> torch.Tensor:
+    """tf.layers.dense under `scope`; the bias is used when the layer has one."""
+    y = x @ p[scope + "/kernel"]
+    return y + p[scope + "/bias"] if scope + "/bias" in p else y
+
+
+def nematus_gru_cell(p: Params, scope: str, x: torch.Tensor, h: torch.Tensor) -> torch.Tensor:
+    """NematusGRUCell.call (nn/ortho_gru_cell.py:72-105): separate input and state projections, the
+    reset gate applied AFTER the state projection of the candidate:
+        [r, u] = sigmoid(state_proj_g(h) + input_proj_g(x));  c = tanh(state_proj_c(h) * r + input_proj_c(x))
+        h' = u * h + (1 - u) * c
+    Which of the projections carry a bias (use_state_bias / use_input_bias) shows in the parameters."""
+    gates = torch.sigmoid(_dense(p, scope + "gates/state_proj", h) + _dense(p, scope + "gates/input_proj", x))
+    size = h.shape[1]
+    r, u = gates[:, :size], gates[:, size:]
+    c = torch.tanh(_dense(p, scope + "candidate/state_proj", h) * r + _dense(p, scope + "candidate/input_proj", x))
+    return u * h + (1 - u) * c
+
+
+def decoder_initial_state(p: Params, spec: RNNDecoderSpec, enc_output: Optional[torch.Tensor],
+                          enc: Optional[Dict[str, torch.Tensor]] = None, bsz: int = 0) -> torch.Tensor:
+    """Decoder.initial_state (decoder.py:226-251) over the encoder projections
+    (encoder_projection.py:30-145); dropout off.
+        linear   dense(concatenated encoder outputs)                      (:47-73)
+        concat   the concatenated encoder outputs themselves             (:76-96)
+        nematus  tanh(dense(mask-weighted MEAN of the temporal states)) (:99-145)
+        empty    zeros(rnn_size), tiled over the batch                   (:30-44, decoder.py:245-250)"""
+    scope = spec.prefix + "/initial_state/encoders_projection"
+    if spec.encoder_projection == "linear":
+        return _dense(p, scope, enc_output)
+    if spec.encoder_projection == "concat":
+        return enc_output
+    if spec.encoder_projection == "nematus":
+        mask = enc["temporal_mask"]
+        means = (enc["temporal_states"] * mask.unsqueeze(2)).sum(1) / mask.sum(1, keepdim=True)
+        return torch.tanh(_dense(p, scope, means))
+    if spec.encoder_projection == "empty":
+        return torch.zeros(bsz, spec.rnn_size)
+    raise ValueError(spec.encoder_projection)
 
 
 def output_projection(p: Params, spec: RNNDecoderSpec, cell_output, embedded_input, context):
-    """nonlinear_output / maxout_output (output_projection.py:115-160, nn/projection.py:7-35)."""
+    """nonlinear_output / maxout_output / nematus_output / mlp_output
+    (output_projection.py:76-188, nn/projection.py:7-57)."""
+    step = spec.prefix + "/attention_decoder/"
+    if spec.output_projection == "nematus":
+        # three separate projections summed, then tanh (:76-112)
+        return torch.tanh(_dense(p, step + "rnn_state", cell_output) + _dense(p, step + "prev_out", embedded_input)
+                          + _dense(p, step + "context", context))
     cat = torch.cat([cell_output, embedded_input, context], 1)
+    if spec.output_projection == "mlp":
+        # multilayer_projection: the activation follows EVERY layer, the last one too (:163-188)
+        for i in range(spec.mlp_layers):
+            cat = torch.tanh(_dense(p, "{}deep_output_mlp/mlp_layer_{}".format(step, i), cat))
+        return cat
     if spec.output_projection == "tanh":
-        pre = spec.prefix + "/attention_decoder/dense/"
-        return torch.tanh(cat @ p[pre + "kernel"] + p[pre + "bias"])
-    pre = spec.prefix + "/attention_decoder/MaxoutProjection/MaxoutProjection/"
-    z = cat @ p[pre + "kernel"] + p[pre + "bias"]
+        return torch.tanh(_dense(p, step + "dense", cat))
+    z = _dense(p, step + "MaxoutProjection/MaxoutProjection", cat)
     size = z.shape[1] // 2
     # reshape [-1,1,2,size] + max_pool over the length-2 axis: first half vs second half
     return torch.maximum(z[:, :size], z[:, size:])
@@ -244,13 +295,26 @@ def state_to_logits(p: Params, spec: RNNDecoderSpec, state: torch.Tensor) -> tor
     return logits
 
 
+def _decoder_cell(p: Params, spec: RNNDecoderSpec, scope: str, x: torch.Tensor, h: torch.Tensor):
+    if spec.rnn_cell == "NematusGRU":
+        return nematus_gru_cell(p, scope, x, h)
+    return gru_cell(x, h, p[scope + "gates/kernel"], p[scope + "gates/bias"],
+                    p[scope + "candidate/kernel"], p[scope + "candidate/bias"])
+
+
 def decoder_step(p: Params, spec: RNNDecoderSpec, embedded_input, prev_output, hidden, states, mask):
-    """Decoder.next_state, GRU branch, attention_on_input=False, no conditional GRU
-    (decoder.py:279-358); dropout off so prev_rnn_output == cell_output."""
-    pre = spec.prefix + "/attention_decoder/OrthoGRUCell/"
-    cell_output = gru_cell(embedded_input, prev_output, p[pre + "gates/kernel"], p[pre + "gates/bias"],
-                           p[pre + "candidate/kernel"], p[pre + "candidate/bias"])
+    """Decoder.next_state, GRU / NematusGRU branch, attention_on_input=False (decoder.py:279-358; the
+    reference cannot build attention_on_input=True - `feedables.prev_contexts`, :273, does not exist);
+    dropout off so prev_rnn_output == cell_output.  With `conditional_gru` the context is run through
+    a second cell (scope `cond_gru_2_cell`) whose state is the first cell's output, and ITS output is
+    what the projection, the history and the next step see - the attention was queried with the first
+    cell's output (:303-325)."""
+    step = spec.prefix + "/attention_decoder/"
+    first = step + ("nematus_gru_cell/" if spec.rnn_cell == "NematusGRU" else "OrthoGRUCell/")
+    cell_output = _decoder_cell(p, spec, first, embedded_input, prev_output)
     context, weights = bahdanau_step(p, spec.att_prefix, cell_output, hidden, states, mask)
+    if spec.conditional_gru:
+        cell_output = _decoder_cell(p, spec, step + "cond_gru_2_cell/", context, cell_output)
     output = output_projection(p, spec, cell_output, embedded_input, context)
     return output, cell_output, context, weights
 
@@ -295,7 +359,7 @@ def decoder_train(p: Params, spec: RNNDecoderSpec, enc: Dict[str, torch.Tensor],
     _steps, bsz = train_inputs.shape
     states, mask = enc["temporal_states"], enc["temporal_mask"]
     hidden = bahdanau_precompute(p, spec.att_prefix, states)
-    rnn = {"prev": decoder_initial_state(p, spec, enc["output"])}
+    rnn = {"prev": decoder_initial_state(p, spec, enc.get("output"), enc, bsz)}
 
     def next_output(embedded, _finished):
         output, rnn["prev"], _ctx, w = decoder_step(p, spec, embedded, rnn["prev"], hidden, states, mask)
@@ -325,7 +389,7 @@ def decoder_greedy(p: Params, spec: RNNDecoderSpec, enc: Dict[str, torch.Tensor]
     states, mask = enc["temporal_states"], enc["temporal_mask"]
     bsz = states.shape[0]
     hidden = bahdanau_precompute(p, spec.att_prefix, states)
-    rnn = {"prev": decoder_initial_state(p, spec, enc["output"])}
+    rnn = {"prev": decoder_initial_state(p, spec, enc.get("output"), enc, bsz)}
 
     def next_output(embedded, _finished):
         output, rnn["prev"], _ctx, _w = decoder_step(p, spec, embedded, rnn["prev"], hidden, states, mask)

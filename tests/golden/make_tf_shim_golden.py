@@ -420,6 +420,125 @@ def main():
     rnn_decoder_case("maxout", hsz=7, esz=5, maxout=True, use_mask=True)
     rnn_decoder_case("tanh", hsz=6, esz=6, maxout=False, use_mask=False, short_gold=True)
 
+    # ---- decoder variants: NematusGRUCell (the reference's own cell code, nn/ortho_gru_cell.py:
+    #      57-105), the conditional GRU (decoder.py:303-325), attention_on_input (:264-277), nematus_output /
+    #      mlp_output (output_projection.py:76-112,163-188), nematus_projection / concat / empty initial states
+    #      (encoder_projection.py:30-145) ------------------------------------------------------------------------
+    from neuralmonkey.decoders.output_projection import nematus_output, mlp_output
+    from neuralmonkey.decoders.encoder_projection import (nematus_projection, concat_encoder_projection,
+                                                          empty_initial_state)
+
+    def rnn_variant_case(tag, cell, conditional, att_on_input, out_proj, enc_proj, hsz=7, esz=5):
+        nb, tx, csz, asz, vsz, max_len = 3, 5, 10, 8, 12, 5
+        if enc_proj == "concat":
+            hsz = csz
+        dname, aname = "vd_" + tag, "va_" + tag
+        first = len(shim.VARIABLES)
+        var = shim.VARIABLES
+        var[aname + "/Attention/attn_query_projection"] = f32(hsz, asz, scale=0.5)
+        var[aname + "/attn_key_projection"] = f32(csz, asz, scale=0.5)
+        var[aname + "/attn_similarity_v"] = f32(asz, scale=0.7)
+        var[aname + "/attn_projection_bias"] = f32(asz, scale=0.3)
+        var[aname + "/attn_bias"] = f32(scale=0.3)
+        if enc_proj in ("linear", "nematus"):
+            var[dname + "/initial_state/encoders_projection/kernel"] = f32(csz, hsz, scale=0.4)
+            var[dname + "/initial_state/encoders_projection/bias"] = f32(hsz, scale=0.3)
+        step = dname + "/attention_decoder/"
+
+        def nematus_cell(scope, in_dim, state_bias, input_bias):
+            for part, width in (("gates", 2 * hsz), ("candidate", hsz)):
+                var[scope + part + "/input_proj/kernel"] = f32(in_dim, width, scale=0.5)
+                var[scope + part + "/state_proj/kernel"] = f32(hsz, width, scale=0.5)
+                if input_bias:
+                    var[scope + part + "/input_proj/bias"] = f32(width, scale=0.3)
+                if state_bias:
+                    var[scope + part + "/state_proj/bias"] = f32(width, scale=0.3)
+
+        def tf_cell(scope, in_dim):
+            var[scope + "gates/kernel"], var[scope + "gates/bias"] = f32(in_dim + hsz, 2 * hsz, scale=0.5), 1.0 + f32(2 * hsz, scale=0.2)
+            var[scope + "candidate/kernel"], var[scope + "candidate/bias"] = f32(in_dim + hsz, hsz, scale=0.5), f32(hsz, scale=0.2)
+
+        if cell == "NematusGRU":
+            nematus_cell(step + "nematus_gru_cell/", esz, False, True)
+            if conditional:
+                nematus_cell(step + "cond_gru_2_cell/", csz, True, False)
+        else:
+            tf_cell(step + "OrthoGRUCell/", esz)
+            if conditional:
+                tf_cell(step + "cond_gru_2_cell/", csz)
+        if att_on_input:
+            var[step + "dense/kernel"], var[step + "dense/bias"] = f32(esz + csz, esz, scale=0.4), f32(esz, scale=0.3)
+        cat = hsz + esz + csz
+        if out_proj == "nematus":
+            for name, width in (("rnn_state", hsz), ("prev_out", esz), ("context", csz)):
+                var[step + name + "/kernel"], var[step + name + "/bias"] = f32(width, esz, scale=0.4), f32(esz, scale=0.3)
+            spec_out = nematus_output(esz)
+        elif out_proj == "mlp":
+            var[step + "deep_output_mlp/mlp_layer_0/kernel"], var[step + "deep_output_mlp/mlp_layer_0/bias"] = f32(cat, 9, scale=0.4), f32(9, scale=0.3)
+            var[step + "deep_output_mlp/mlp_layer_1/kernel"], var[step + "deep_output_mlp/mlp_layer_1/bias"] = f32(9, esz, scale=0.4), f32(esz, scale=0.3)
+            spec_out = mlp_output([9, esz])
+        else:
+            var[step + "MaxoutProjection/MaxoutProjection/kernel"] = f32(cat, 2 * esz, scale=0.4)
+            var[step + "MaxoutProjection/MaxoutProjection/bias"] = f32(2 * esz, scale=0.3)
+            spec_out = maxout_output(esz)
+        for name in list(var)[first:]:
+            out["vv::" + name] = var[name]
+        states, enc_out = f32(nb, tx, csz), f32(nb, csz)
+        amask = np.array([[1, 1, 1, 1, 0], [1, 1, 1, 1, 1], [1, 1, 0, 0, 0]], np.float32)
+        dec_w, dec_b, table = f32(esz, vsz, scale=0.8), f32(vsz, scale=0.3), f32(vsz, esz)
+        gold = np.array([[5, 6, 7, 2, 0], [7, 8, 9, 4, 2], [4, 2, 0, 0, 0]], np.int64).T
+        pre = "vd_{}_".format(tag)
+        out.update({pre + "states": states, pre + "enc_out": enc_out, pre + "mask": amask, pre + "w": dec_w,
+                    pre + "b": dec_b, pre + "table": table, pre + "gold": gold})
+        att = object.__new__(Attention)
+        att.__dict__.update(dict(
+            _variable_scope=shim.VarScope(aname), _reuse=None, _name=aname, _state_size=asz, batch_size=nb,
+            _histories={}, _attention_states_cached_placeholder=shim.t(states),
+            _attention_mask_cached_placeholder=shim.t(amask), context_vector_size=csz))
+        encoder = types.SimpleNamespace(output=shim.t(enc_out), temporal_states=shim.t(states),
+                                        temporal_mask=shim.t(amask))
+        rd = object.__new__(Decoder)
+        rd.__dict__.update(dict(
+            vocabulary=list(range(vsz)), supress_unk=False, max_output_len=max_len, batch_size=nb, label_smoothing=None,
+            dropout_keep_prob=1.0, train_mode=None, _embedding_size=esz, embeddings_source=None,
+            _variable_scope=shim.VarScope(dname), _reuse=None, _name=dname,
+            _decoding_w_cached_placeholder=shim.t(dec_w), _decoding_b_cached_placeholder=shim.t(dec_b),
+            _embedding_matrix_cached_placeholder=shim.t(table),
+            _go_symbols_cached_placeholder=shim.t(np.full((nb,), 1, np.int64)),
+            _train_inputs_cached_placeholder=shim.t(gold), encoders=[] if enc_proj == "empty" else [encoder],
+            _output_projection_spec=spec_out, _conditional_gru=conditional, _attention_on_input=att_on_input,
+            _rnn_cell_str=cell, _rnn_size=None if enc_proj == "concat" else hsz,
+            _encoder_projection={"linear": None, "nematus": nematus_projection(), "concat": None,
+                                 "empty": None}[enc_proj],
+            attentions=[att], step_scope=shim.VarScope(dname + "/attention_decoder"),
+            encoder_states=lambda: [], encoder_masks=lambda: []))
+        rd.input_projection = (rd.input_plus_attention if att_on_input
+                               else (lambda *args: LoopState(*args).feedables.embedded_input))
+        shim.USED[:] = []
+        shim.GRUCell.CALLS[:] = []
+        out[pre + "initial_state"] = np.asarray(rd.initial_state)
+        out[pre + "train_logits"] = np.asarray(rd.train_logits)
+        out[pre + "train_rnn_outputs"] = np.asarray(rd.train_loop_result.histories.other.rnn_outputs)
+        out[pre + "train_loss"] = np.asarray(rd.train_loss)
+        out[pre + "run_logits"] = np.asarray(rd.runtime_logits)
+        out[pre + "run_symbols"] = np.asarray(rd.runtime_loop_result.histories.output_symbols)
+        out[pre + "dense_names"] = np.array(sorted(set(shim.USED)))
+        out[pre + "cell_scopes"] = np.array(sorted({c[0] for c in shim.GRUCell.CALLS}))
+
+    rnn_variant_case("nematus", "NematusGRU", True, False, "nematus", "nematus")
+    rnn_variant_case("cond_gru", "GRU", True, False, "mlp", "concat")
+    rnn_variant_case("nematus_plain", "NematusGRU", False, False, "maxout", "empty")
+    # attention_on_input=True cannot be built in the reference: input_plus_attention reads
+    # `feedables.prev_contexts` (decoder.py:273), which lives in `feedables.other` -> AttributeError
+    try:
+        rnn_variant_case("input_feeding", "GRU", False, True, "maxout", "linear")
+        out["attention_on_input_error"] = np.array("")
+    except AttributeError as exc:
+        out["attention_on_input_error"] = np.array(str(exc))
+        for key in [k for k in out if k.startswith("vd_input_feeding_") or k.startswith("vv::vd_input_feeding")
+                    or k.startswith("vv::va_input_feeding")]:
+            del out[key]
+
     # ---- a whole beam search: BeamSearchDecoder.get_initial_loop_state / loop_continue_criterion / get_body
     #      (decoders/beam_search_decoder.py:218-558) around the reference's own attention Decoder, one
     #      sentence (the reference's RNN decoder does not tile the encoder states to the beam) --------------

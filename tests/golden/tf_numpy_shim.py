@@ -150,8 +150,10 @@ def _dense(inputs, units, activation=None, use_bias=True, name=None, **kwargs):
     if full + "/kernel" in VARIABLES:
         kernel, bias = VARIABLES[full + "/kernel"], VARIABLES.get(full + "/bias")
         USED.append(full + "/kernel")
-    else:
+    elif name in DENSE:
         kernel, bias = DENSE[name]
+    else:
+        raise KeyError("dense layer '{}' was not provided to the shim".format(full))
     assert kernel.shape[1] == units
     out = np.asarray(inputs) @ kernel
     if use_bias and bias is not None:
@@ -249,10 +251,17 @@ class GRUCell:
         return self._num_units
 
     def __call__(self, inputs, state, scope=None):
-        with _scope_cm(scope or "gru_cell"):
-            wg, bg = _get_variable("gates/kernel"), _get_variable("gates/bias")
-            wc, bc = _get_variable("candidate/kernel"), _get_variable("candidate/bias")
+        # Layer.__call__: open the given scope, or the layer's default name (snake-cased class name -
+        # TensorFlow-internal naming, not visible in the reference), then run `call`
+        import re
+        default = re.sub("([a-z])([A-Z])", r"\1_\2", re.sub("(.)([A-Z][a-z0-9]+)", r"\1_\2", type(self).__name__)).lower()
+        with _scope_cm(scope or default):
             GRUCell.CALLS.append((_full_name(""), tuple(np.shape(inputs)), tuple(np.shape(state))))
+            return self.call(inputs, state)
+
+    def call(self, inputs, state):
+        wg, bg = _get_variable("gates/kernel"), _get_variable("gates/bias")
+        wc, bc = _get_variable("candidate/kernel"), _get_variable("candidate/bias")
         x, h = np.asarray(inputs, np.float32), np.asarray(state, np.float32)
         assert h.shape[1] == self._num_units and wg.shape == (x.shape[1] + h.shape[1], 2 * h.shape[1])
         gates = 1.0 / (1.0 + np.exp(-(np.concatenate([x, h], 1) @ wg + bg)))
@@ -413,6 +422,8 @@ def install():
     tf.reverse_sequence = _reverse_sequence
     tf.not_equal = lambda a, b: t(np.not_equal(a, b))
     tf.while_loop = _while_loop
+    tf.sigmoid = lambda x: t(1.0 / (1.0 + np.exp(-np.asarray(x, np.float32))), np.float32)
+    tf.split = lambda value, num_or_size_splits, axis=0: [t(p) for p in np.split(np.asarray(value), num_or_size_splits, axis=axis)]
     tf.trainable_variables = lambda: list(TRAINABLE)
     tf.get_collection = lambda key, scope=None: [v for v in TRAINABLE if scope is None or v.name.startswith(scope)]
     tf.GraphKeys = types.SimpleNamespace(TRAINABLE_VARIABLES="trainable_variables")

@@ -490,3 +490,40 @@ def test_trainer_host_logic():
         some_kept |= norm < 1.0 and np.array_equal(G["trn_clipped::" + name], grad.numpy())
     assert some_clipped and some_kept
     assert G["trn_loss_names"].tolist() == ["dec_a", "dec_b", "L1", "L2"]
+
+
+@pytest.mark.parametrize("tag,cell,conditional,out_proj,enc_proj", [
+    ("nematus", "NematusGRU", True, "nematus", "nematus"),
+    ("cond_gru", "GRU", True, "mlp", "concat"),
+    ("nematus_plain", "NematusGRU", False, "maxout", "empty")])
+def test_decoder_variants(tag, cell, conditional, out_proj, enc_proj):
+    """The decoder variants of SURVEY.md 8(f) N4, the reference's Decoder run whole with them:
+    NematusGRUCell (the reference's OWN cell code: nn/ortho_gru_cell.py:57-105), the conditional GRU
+    (decoder.py:303-325), nematus_output / mlp_output (output_projection.py:76-112,163-188), and the
+    nematus / concat / empty initial states (encoder_projection.py:30-145)."""
+    dname, aname, pre = "vd_" + tag, "va_" + tag, "vd_{}_".format(tag)
+    p = {k[4:]: _t(k) for k in G.files if k.startswith("vv::" + dname + "/") or k.startswith("vv::" + aname + "/")}
+    p[dname + "/word_embeddings"] = _t(pre + "table")
+    p[dname + "/state_to_word_W"], p[dname + "/state_to_word_b"] = _t(pre + "w"), _t(pre + "b")
+    spec = O.RNNDecoderSpec(dname, aname, max_output_len=5, output_projection=out_proj, rnn_cell=cell,
+                            conditional_gru=conditional, encoder_projection=enc_proj, rnn_size=7, mlp_layers=2)
+    enc = {"temporal_states": _t(pre + "states"), "temporal_mask": _t(pre + "mask"), "output": _t(pre + "enc_out")}
+    gold = torch.from_numpy(G[pre + "gold"])
+    init = O.decoder_initial_state(p, spec, enc["output"], enc, bsz=3)
+    assert np.abs(init.numpy() - G[pre + "initial_state"]).max() < 2e-6
+    train = O.decoder_train(p, spec, enc, gold)
+    assert np.abs(train["train_logits"].numpy() - G[pre + "train_logits"]).max() < 1e-5
+    assert np.abs(train["rnn_outputs"].numpy() - G[pre + "train_rnn_outputs"]).max() < 1e-5
+    assert abs(float(train["train_loss"]) - float(G[pre + "train_loss"])) < 1e-5
+    run = O.decoder_greedy(p, spec, enc)
+    assert np.array_equal(run["output_symbols"].numpy(), G[pre + "run_symbols"])
+    assert np.abs(run["runtime_logits"].numpy() - G[pre + "run_logits"]).max() < 1e-5
+    # every dense layer the reference asked for is a parameter the oracle read, under that name
+    assert {n for n in G[pre + "dense_names"].tolist()} <= set(p)
+
+
+def test_attention_on_input_cannot_be_built_in_the_reference():
+    """Decoder.input_plus_attention reads `feedables.prev_contexts` (decoders/decoder.py:273); the
+    contexts live in `feedables.other`, so attention_on_input=True raises while the graph is built.
+    The product therefore rejects the option instead of guessing a behaviour."""
+    assert "prev_contexts" in str(G["attention_on_input_error"])
