@@ -64,15 +64,34 @@ def gru_cell(x: torch.Tensor, h: torch.Tensor, wg: torch.Tensor, bg: torch.Tenso
     return u * h + (1 - u) * c
 
 
-def dynamic_gru(x: torch.Tensor, lengths: Optional[torch.Tensor], wg, bg, wc, bc,
+def _dense(p: Params, scope: str, x: torch.Tensor) -> torch.Tensor:
+    """tf.layers.dense under `scope`; the bias is used when the layer has one."""
+    y = x @ p[scope + "/kernel"]
+    return y + p[scope + "/bias"] if scope + "/bias" in p else y
+
+
+def nematus_gru_cell(p: Params, scope: str, x: torch.Tensor, h: torch.Tensor) -> torch.Tensor:
+    """NematusGRUCell.call (nn/ortho_gru_cell.py:72-105): separate input and state projections, the
+    reset gate applied AFTER the state projection of the candidate:
+        [r, u] = sigmoid(state_proj_g(h) + input_proj_g(x));  c = tanh(state_proj_c(h) * r + input_proj_c(x))
+        h' = u * h + (1 - u) * c
+    Which of the projections carry a bias (use_state_bias / use_input_bias) shows in the parameters."""
+    gates = torch.sigmoid(_dense(p, scope + "gates/state_proj", h) + _dense(p, scope + "gates/input_proj", x))
+    size = h.shape[1]
+    r, u = gates[:, :size], gates[:, size:]
+    c = torch.tanh(_dense(p, scope + "candidate/state_proj", h) * r + _dense(p, scope + "candidate/input_proj", x))
+    return u * h + (1 - u) * c
+
+
+def dynamic_rnn(cell: Callable, size: int, x: torch.Tensor, lengths: Optional[torch.Tensor],
                 h0: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor]:
-    """tf.nn.dynamic_rnn(GRUCell, x, sequence_length=lengths)."""
+    """tf.nn.dynamic_rnn(cell, x, sequence_length=lengths) for a cell `h' = cell(x_t, h)` whose output
+    is its state: past a sentence's length the output is zero and the state is carried."""
     bsz, steps, _ = x.shape
-    size = wc.shape[1]
     h = h0 if h0 is not None else x.new_zeros(bsz, size)
     outs = []
     for t in range(steps):
-        new_h = gru_cell(x[:, t], h, wg, bg, wc, bc)
+        new_h = cell(x[:, t], h)
         if lengths is not None:
             live = (t < lengths).to(x.dtype).unsqueeze(1)
             outs.append(new_h * live)
@@ -81,6 +100,12 @@ def dynamic_gru(x: torch.Tensor, lengths: Optional[torch.Tensor], wg, bg, wc, bc
             outs.append(new_h)
             h = new_h
     return torch.stack(outs, 1), h
+
+
+def dynamic_gru(x: torch.Tensor, lengths: Optional[torch.Tensor], wg, bg, wc, bc,
+                h0: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+    """tf.nn.dynamic_rnn(GRUCell, x, sequence_length=lengths)."""
+    return dynamic_rnn(lambda xt, h: gru_cell(xt, h, wg, bg, wc, bc), wc.shape[1], x, lengths, h0)
 
 
 def reverse_sequence(x: torch.Tensor, lengths: torch.Tensor) -> torch.Tensor:
@@ -130,21 +155,30 @@ def _cell_params(p: Params, scope: str) -> Tuple:
     return tuple(p[scope + n] for n in ("gates/kernel", "gates/bias", "candidate/kernel", "candidate/bias"))
 
 
-def rnn_layer(p: Params, scope: str, x: torch.Tensor, lengths: torch.Tensor, direction: str):
-    """rnn_layer (encoders/recurrent.py:71-110), GRU cells; variable scopes as TensorFlow names them:
-    <scope>/bidirectional_rnn/{fw,bw}/OrthoGRUCell or <scope>/rnn/OrthoGRUCell."""
+def rnn_layer(p: Params, scope: str, x: torch.Tensor, lengths: torch.Tensor, direction: str,
+              cell_type: str = "GRU", size: int = 0):
+    """rnn_layer (encoders/recurrent.py:71-110); variable scopes as TensorFlow names them:
+    <scope>/bidirectional_rnn/{fw,bw}/<cell> or <scope>/rnn/<cell>, <cell> = OrthoGRUCell (the scope
+    the reference passes, nn/ortho_gru_cell.py:51) or nematus_gru_cell (TensorFlow's default name for
+    the layer class; `size` is needed for that cell only)."""
+    def run(cell_scope, inputs):
+        if cell_type == "NematusGRU":
+            cell_scope += "nematus_gru_cell/"
+            return dynamic_rnn(lambda xt, h: nematus_gru_cell(p, cell_scope, xt, h), size, inputs, lengths)
+        return dynamic_gru(inputs, lengths, *_cell_params(p, cell_scope + "OrthoGRUCell/"))
+
     if direction == "bidirectional":
-        base = scope + "/bidirectional_rnn/{}/OrthoGRUCell/"
-        return bidirectional_gru(x, lengths, _cell_params(p, base.format("fw")), _cell_params(p, base.format("bw")))
-    cell = _cell_params(p, scope + "/rnn/OrthoGRUCell/")
+        out_fw, fin_fw = run(scope + "/bidirectional_rnn/fw/", x)
+        out_bw_rev, fin_bw = run(scope + "/bidirectional_rnn/bw/", reverse_sequence(x, lengths))
+        return (torch.cat([out_fw, reverse_sequence(out_bw_rev, lengths)], 2), torch.cat([fin_fw, fin_bw], 1))
     if direction == "backward":
-        out_rev, final = dynamic_gru(reverse_sequence(x, lengths), lengths, *cell)
+        out_rev, final = run(scope + "/rnn/", reverse_sequence(x, lengths))
         return reverse_sequence(out_rev, lengths), final
-    return dynamic_gru(x, lengths, *cell)
+    return run(scope + "/rnn/", x)
 
 
 def recurrent_encoder(p: Params, prefix: str, inputs: torch.Tensor, mask: torch.Tensor,
-                      rnn_layers: Sequence[Tuple[int, str]] = ((0, "bidirectional"),),
+                      rnn_layers: Sequence[Tuple] = ((0, "bidirectional"),),
                       add_residual: bool = False, add_layer_norm: bool = False,
                       include_final_layer_norm: bool = True) -> Dict[str, torch.Tensor]:
     """RecurrentEncoder.rnn (encoders/recurrent.py:180-218), dropout off.  Layer i lives in scope
@@ -154,11 +188,13 @@ def recurrent_encoder(p: Params, prefix: str, inputs: torch.Tensor, mask: torch.
     state with the SAME variables (:215-216)."""
     lengths = mask.sum(1).to(torch.int64)             # model/stateful.py:56-62
     layer_input, layer_final = inputs, inputs[:, -1]
-    for i, (_size, direction) in enumerate(rnn_layers):
+    for i, layer in enumerate(rnn_layers):
+        size, direction = layer[0], layer[1]
+        cell_type = layer[2] if len(layer) > 2 else "GRU"
         scope = "{}/rnn_{}_{}".format(prefix, i, direction)
         if add_layer_norm:
             layer_input = layer_norm(layer_input, p[scope + "/LayerNorm/gamma"], p[scope + "/LayerNorm/beta"])
-        layer_output, layer_final_output = rnn_layer(p, scope, layer_input, lengths, direction)
+        layer_output, layer_final_output = rnn_layer(p, scope, layer_input, lengths, direction, cell_type, size)
         if add_residual and layer_input.shape[-1] == layer_output.shape[-1]:
             layer_input = layer_input + layer_output
             layer_final = layer_final + layer_final_output
@@ -220,25 +256,6 @@ class RNNDecoderSpec:
         self.encoder_projection = encoder_projection  # "linear" | "nematus" | "concat" | "empty"
         self.rnn_size = rnn_size                    # only read by the "empty" projection
         self.mlp_layers = mlp_layers
-
-
-def _dense(p: Params, scope: str, x: torch.Tensor) -> torch.Tensor:
-    """tf.layers.dense under `scope`; the bias is used when the layer has one."""
-    y = x @ p[scope + "/kernel"]
-    return y + p[scope + "/bias"] if scope + "/bias" in p else y
-
-
-def nematus_gru_cell(p: Params, scope: str, x: torch.Tensor, h: torch.Tensor) -> torch.Tensor:
-    """NematusGRUCell.call (nn/ortho_gru_cell.py:72-105): separate input and state projections, the
-    reset gate applied AFTER the state projection of the candidate:
-        [r, u] = sigmoid(state_proj_g(h) + input_proj_g(x));  c = tanh(state_proj_c(h) * r + input_proj_c(x))
-        h' = u * h + (1 - u) * c
-    Which of the projections carry a bias (use_state_bias / use_input_bias) shows in the parameters."""
-    gates = torch.sigmoid(_dense(p, scope + "gates/state_proj", h) + _dense(p, scope + "gates/input_proj", x))
-    size = h.shape[1]
-    r, u = gates[:, :size], gates[:, size:]
-    c = torch.tanh(_dense(p, scope + "candidate/state_proj", h) * r + _dense(p, scope + "candidate/input_proj", x))
-    return u * h + (1 - u) * c
 
 
 def decoder_initial_state(p: Params, spec: RNNDecoderSpec, enc_output: Optional[torch.Tensor],

@@ -596,11 +596,19 @@ def main():
         for i, (vs_, es_) in enumerate(zip(vocab_sizes, emb_sizes)):
             var["{}_input/embedding_matrix_{}".format(name, i)] = f32(vs_, es_)
         in_dim = sum(emb_sizes)
-        for i, (size, direction) in enumerate(layers):
+        for i, layer in enumerate(layers):
+            size, direction = layer[0], layer[1]
             scope = "{}/rnn_{}_{}".format(name, i, direction)
-            cells = ([scope + "/bidirectional_rnn/fw/OrthoGRUCell/", scope + "/bidirectional_rnn/bw/OrthoGRUCell/"]
-                     if direction == "bidirectional" else [scope + "/rnn/OrthoGRUCell/"])
+            cname = "nematus_gru_cell/" if len(layers[i]) > 2 and layers[i][2] == "NematusGRU" else "OrthoGRUCell/"
+            cells = ([scope + "/bidirectional_rnn/fw/" + cname, scope + "/bidirectional_rnn/bw/" + cname]
+                     if direction == "bidirectional" else [scope + "/rnn/" + cname])
             for cell in cells:
+                if cname == "nematus_gru_cell/":        # RNN_CELL_TYPES["NematusGRU"](size): input bias only
+                    for part, width in (("gates", 2 * size), ("candidate", size)):
+                        var[cell + part + "/input_proj/kernel"] = f32(in_dim, width, scale=0.5)
+                        var[cell + part + "/input_proj/bias"] = f32(width, scale=0.3)
+                        var[cell + part + "/state_proj/kernel"] = f32(size, width, scale=0.5)
+                    continue
                 var[cell + "gates/kernel"], var[cell + "gates/bias"] = f32(in_dim + size, 2 * size, scale=0.5), 1.0 + f32(2 * size, scale=0.2)
                 var[cell + "candidate/kernel"], var[cell + "candidate/bias"] = f32(in_dim + size, size, scale=0.5), f32(size, scale=0.2)
             if layer_norm_:
@@ -635,6 +643,8 @@ def main():
     recurrent_case("deep", [3, 1], [(4, "forward"), (4, "backward"), (2, "bidirectional"), (3, "bidirectional")],
                    True, True, True, True)
     recurrent_case("plain", [4], [(3, "backward"), (3, "forward")], True, False, False, False)
+    recurrent_case("nematus", [5], [(4, "bidirectional", "NematusGRU"), (3, "forward", "NematusGRU")],
+                   False, False, True, False)
 
     # ---- the trainer's host logic: GenericTrainer.regularization_losses / differentiable_loss_sum /
     #      gradients (per-tensor clip_by_norm) / collect_results (trainers/generic_trainer.py:84-195,27-50),

@@ -307,7 +307,8 @@ def test_whole_attention_decoder(tag, maxout, use_mask):
 @pytest.mark.parametrize("tag,layers,residual,layer_norm,final_norm,scale", [
     ("sentence", [(4, "bidirectional")], False, False, True, False),
     ("deep", [(4, "forward"), (4, "backward"), (2, "bidirectional"), (3, "bidirectional")], True, True, True, True),
-    ("plain", [(3, "backward"), (3, "forward")], True, False, False, False)])
+    ("plain", [(3, "backward"), (3, "forward")], True, False, False, False),
+    ("nematus", [(4, "bidirectional", "NematusGRU"), (3, "forward", "NematusGRU")], False, False, True, False)])
 def test_recurrent_encoder(tag, layers, residual, layer_norm, final_norm, scale):
     """model/sequence.py EmbeddedFactorSequence.temporal_states / temporal_mask (:170-199) and
     encoders/recurrent.py RecurrentEncoder.rnn + rnn_layer (:71-110,180-218) run whole: factor lookup,
@@ -327,7 +328,7 @@ def test_recurrent_encoder(tag, layers, residual, layer_norm, final_norm, scale)
     assert np.abs(enc["output"].numpy() - G[name + "_output"]).max() < 5e-6
     assert np.array_equal(enc["temporal_mask"].numpy(), G[name + "_enc_mask"])
     # the scopes the reference called its cells in are the ones the oracle reads its parameters from
-    cell_scopes = {k[: k.index("gates/kernel")] for k in p if k.endswith("gates/kernel")}
+    cell_scopes = {k[: k.index("gates/")] for k in p if "/gates/" in k}
     assert set(G[name + "_cell_scopes"].tolist()) == cell_scopes
 
 
