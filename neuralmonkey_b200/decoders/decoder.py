@@ -8,6 +8,10 @@ into the recurrence (decoder.py:264-277,288-297), so
   3. the deep-output projection is one GEMM over T*B rows,
 and the base class adds the fused vocabulary projection + loss.  The runtime (greedy / beam)
 path steps through `next_state`, using the same kernels with T = 1.
+
+Variants (behind NMB200_UNVERIFIED - see nn/variants.py): with `conditional_gru`
+or `rnn_cell="NematusGRU"` the context feeds the recurrence, so training steps through time with the
+same `_variant_step` the runtime uses (teacher-forced inputs), one set of T = 1 launches per step.
 """
 from typing import Any, List, NamedTuple, Optional, Tuple
 
@@ -27,6 +31,7 @@ from neuralmonkey_b200.model.parameterized import InitializerSpecs
 from neuralmonkey_b200.model.sequence import EmbeddedSequence
 from neuralmonkey_b200.model.stateful import Stateful
 from neuralmonkey_b200.nn.utils import dropout, dropout_mask
+from neuralmonkey_b200.nn.variants import NematusGRUCell, require_variant
 from neuralmonkey_b200.vocabulary import Vocabulary
 
 RNN_CELL_TYPES = ("NematusGRU", "GRU", "LSTM")
@@ -76,11 +81,12 @@ class Decoder(AutoregressiveDecoder):
             # `feedables.other`) - tests/test_oracle_vs_reference_code.py records the AttributeError
             raise NotImplementedError("attention_on_input=True fails in the reference while the graph is "
                                       "built (decoders/decoder.py:273); it is not supported here either")
-        if self._rnn_cell_str != "GRU" or conditional_gru:
-            raise NotImplementedError(
-                "rnn_cell={}, conditional_gru={}: outside the B200 hot path built so far (GRU, no "
-                "conditional GRU; SURVEY.md 8(f) N4 - the oracle already restates both variants)"
-                .format(rnn_cell, conditional_gru))
+        if self._rnn_cell_str == "LSTM":
+            raise NotImplementedError("rnn_cell='LSTM' is outside the B200 hot path built so far "
+                                      "(SURVEY.md 8(f) N4)")
+        self._stepwise = self._rnn_cell_str != "GRU" or conditional_gru
+        if self._stepwise:
+            require_variant("Decoder with rnn_cell='{}', conditional_gru={}".format(rnn_cell, conditional_gru))
         for att in self.attentions:
             if hasattr(att, "set_query_size"):
                 att.set_query_size(self.rnn_size)
@@ -130,7 +136,20 @@ class Decoder(AutoregressiveDecoder):
     def output_dimension(self) -> int:
         return self.output_projection_spec[1]
 
+    @property
+    def _nematus_cells(self):
+        """(first cell, conditional cell or None) - _get_rnn_cell / _get_conditional_gru_cell
+        (decoder.py:253-262): the conditional cell carries its bias on the state side."""
+        if "_nematus_cells_cache" not in self.__dict__:
+            ctx_size = sum(a.context_vector_size for a in self.attentions)
+            first = NematusGRUCell(self, "attention_decoder/nematus_gru_cell", self.embedding_size, self.rnn_size)
+            cond = (NematusGRUCell(self, self._COND_SCOPE, ctx_size, self.rnn_size, use_state_bias=True,
+                                   use_input_bias=False) if self._conditional_gru else None)
+            self.__dict__["_nematus_cells_cache"] = (first, cond)
+        return self.__dict__["_nematus_cells_cache"]
+
     _CELL_SCOPE = "attention_decoder/OrthoGRUCell"
+    _COND_SCOPE = "attention_decoder/cond_gru_2_cell"      # the scope decoder.py:324 passes
 
     def declare_variables(self) -> None:
         AutoregressiveDecoder.declare_variables(self)
@@ -139,8 +158,15 @@ class Decoder(AutoregressiveDecoder):
                              "dimension of the input embedding ({})"
                              .format(self.output_dimension, self.embedding_size))
         self.encoder_projection.declare(self, self.rnn_size, self.encoders)
-        gru_cell_variables(self, self._CELL_SCOPE, self.embedding_size, self.rnn_size)
         ctx_size = sum(a.context_vector_size for a in self.attentions)
+        if self._rnn_cell_str == "NematusGRU":
+            for cell in self._nematus_cells:
+                if cell is not None:
+                    cell.declare()
+        else:
+            gru_cell_variables(self, self._CELL_SCOPE, self.embedding_size, self.rnn_size)
+            if self._conditional_gru:
+                gru_cell_variables(self, self._COND_SCOPE, ctx_size, self.rnn_size)
         self.output_projection.declare(self, self.rnn_size + self.embedding_size + ctx_size)
         for att in self.attentions:
             att.ensure_declared()
@@ -156,9 +182,56 @@ class Decoder(AutoregressiveDecoder):
             init = init.unsqueeze(0).expand(self.batch_size, -1).contiguous()
         return init
 
+    # -- variants: one step of decoder.py:279-358 with the context inside the recurrence ---------
+    def _variant_step(self, rnn_input: torch.Tensor, prev_output: torch.Tensor, attend):
+        """(output, dropped cell output, dropped contexts, attention results) of one step.
+        `attend(att, query)` runs one attention.  Order as in the reference: first cell -> attention
+        queried with its RAW output -> (conditional cell over the raw contexts, state = first cell's
+        output) -> dropout on contexts and on the cell output -> deep output."""
+        if self._rnn_cell_str == "NematusGRU":
+            cell_output = self._nematus_cells[0](rnn_input, prev_output)
+        else:
+            cell_output = ops.gru_layer(rnn_input.unsqueeze(1), *gru_cell_tensors(self, self._CELL_SCOPE),
+                                        h0=prev_output)[2][:, 0]
+        attended = [attend(att, cell_output) for att in self.attentions]
+        contexts = [a[0] for a in attended]
+        if self._conditional_gru:
+            cond_input = contexts[0] if len(contexts) == 1 else torch.cat(contexts, -1)
+            if self._rnn_cell_str == "NematusGRU":
+                cell_output = self._nematus_cells[1](cond_input, cell_output)
+            else:
+                cell_output = ops.gru_layer(cond_input.unsqueeze(1), *gru_cell_tensors(self, self._COND_SCOPE),
+                                            h0=cell_output)[2][:, 0]
+        contexts = [dropout(ctx, self.dropout_keep_prob, self.train_mode) for ctx in contexts]
+        cell_output = dropout(cell_output, self.dropout_keep_prob, self.train_mode)
+        output = self.output_projection(self, cell_output, rnn_input, contexts, self.train_mode)
+        return output, cell_output, contexts, attended
+
+    def _train_pass_stepwise(self):
+        fed = self._train_step_inputs_bm
+        emb = self.embed_input_symbols(fed)                # [B,T,E]
+        prev = self.initial_state
+        outputs, cells, weights = [], [], [[] for _ in self.attentions]
+
+        def attend(att, query):
+            ctx, w = att.attention_sequence(query.unsqueeze(1))
+            return ctx[:, 0], w[:, 0]
+
+        for t in range(fed.shape[1]):
+            out, prev, _ctx, attended = self._variant_step(emb[:, t], prev, attend)
+            outputs.append(out)
+            cells.append(prev)
+            for hist, (_c, w) in zip(weights, attended):
+                hist.append(w)
+        for att, hist in zip(self.attentions, weights):
+            att.histories["{}_train".format(self.name)] = torch.stack(hist, 0).detach()
+        return torch.stack(outputs, 1), torch.stack(cells, 1), [torch.stack(h, 1) for h in weights]
+
     # -- training: all steps at once ------------------------------------------------------
     @tensor
     def _train_pass(self):
+        if self._stepwise:
+            return self._train_pass_stepwise()
         fed = self._train_step_inputs_bm                   # [B,T] symbols fed at each step
         bsz, steps = fed.shape
         emb = self.embed_input_symbols(fed)                # [B,T,E] (dropout inside)
@@ -207,6 +280,17 @@ class Decoder(AutoregressiveDecoder):
         rnn_feedables = loop_state.feedables.other
         rnn_histories = loop_state.histories.other
         rnn_input = loop_state.feedables.embedded_input
+        if self._stepwise:
+            states = iter(rnn_histories.attention_histories)
+            output, cell_output, contexts, attended = self._variant_step(
+                rnn_input, rnn_feedables.prev_rnn_output,
+                lambda att, query: att.attention(query, rnn_feedables.prev_rnn_output, rnn_input, next(states)))
+            rnn_histories.rnn_outputs.append(cell_output)
+            return (output,
+                    RNNFeedables(prev_rnn_state=cell_output, prev_rnn_output=cell_output,
+                                 prev_contexts=list(contexts)),
+                    RNNHistories(rnn_outputs=rnn_histories.rnn_outputs,
+                                 attention_histories=[a[1] for a in attended]))
         mask = dropout_mask((rnn_input.shape[0], 1, self.rnn_size), self.dropout_keep_prob,
                             self.train_mode, rnn_input.device)
         dropped, _fin, raw = ops.gru_layer(rnn_input.unsqueeze(1),

@@ -11,7 +11,8 @@ import torch
 from neuralmonkey_b200 import ops, runtime
 from neuralmonkey_b200.model.stateful import Stateful
 from neuralmonkey_b200.nn.utils import dropout
-from neuralmonkey_b200.params import zeros_initializer
+from neuralmonkey_b200.nn.variants import require_variant
+from neuralmonkey_b200.params import block_orthogonal_initializer, zeros_initializer
 
 
 class EncoderProjection:
@@ -86,3 +87,41 @@ concat_encoder_projection = _Concat()
 def linear_encoder_projection(dropout_keep_prob: float) -> EncoderProjection:
     """dropout(dense(concat(encoder outputs), rnn_size)) (encoder_projection.py:47-73)."""
     return _Linear(dropout_keep_prob)
+
+
+class _Nematus(EncoderProjection):
+    def __init__(self, dropout_keep_prob: float) -> None:
+        self.dropout_keep_prob = dropout_keep_prob
+
+    def output_size(self, rnn_size, encoders):
+        return rnn_size
+
+    @staticmethod
+    def _check(encoders):
+        if len(encoders) != 1:
+            raise ValueError("Exactly one encoder required for this type of projection. {} given."
+                             .format(len(encoders)))
+        return encoders[0]
+
+    def declare(self, decoder, rnn_size, encoders):
+        encoder = self._check(encoders)
+        in_size = encoder.dimension
+        # orthogonal when square, otherwise the scope default (encoder_projection.py:131-134)
+        init = block_orthogonal_initializer() if in_size == rnn_size else None
+        decoder.declare("initial_state/encoders_projection/kernel", [in_size, rnn_size], init)
+        decoder.declare("initial_state/encoders_projection/bias", [rnn_size], zeros_initializer())
+
+    def __call__(self, decoder, train_mode, rnn_size, encoders):
+        encoder = self._check(encoders)
+        mask = encoder.temporal_mask
+        means = (encoder.temporal_states * mask.unsqueeze(2)).sum(1) / mask.sum(1, keepdim=True)
+        y = ops.linear(means.contiguous(), decoder.var("initial_state/encoders_projection/kernel"),
+                       decoder.var("initial_state/encoders_projection/bias"), act="tanh")
+        return dropout(y, self.dropout_keep_prob, train_mode)
+
+
+def nematus_projection(dropout_keep_prob: float = 1.0) -> EncoderProjection:
+    """tanh(dense(mean of the encoder's states over its unmasked positions))
+    (encoder_projection.py:99-145)."""
+    require_variant("nematus_projection")
+    return _Nematus(dropout_keep_prob)

@@ -1,0 +1,82 @@
+"""Model variants next to the hot path: the Nematus GRU cell
+(reference: neuralmonkey/nn/ortho_gru_cell.py:57-105) and the switch that guards every variant.
+
+These variants are COMPOSED from operations whose kernels are parity-tested on the GPU (`ops.linear`,
+`ops.gru_layer` with one step, `ops.bahdanau_attention`) plus element-wise torch glue for the gate
+arithmetic; they step through time instead of running the fused sequence kernels.  The oracle restates
+them and is pinned to the reference's own code (tests/test_oracle_vs_reference_code.py), but the
+compositions themselves have not been run on a GPU yet, so they stay behind `NMB200_UNVERIFIED=1`
+(tests/test_gpu_variants.py runs them against the oracle under that switch)."""
+import os
+from typing import Tuple
+
+import torch
+
+from neuralmonkey_b200 import ops
+from neuralmonkey_b200.params import block_orthogonal_initializer, zeros_initializer
+
+
+def variants_enabled() -> bool:
+    return os.environ.get("NMB200_UNVERIFIED", "") == "1"
+
+
+def require_variant(what: str) -> None:
+    if not variants_enabled():
+        raise NotImplementedError(
+            "{}: composed from GPU-verified operations and restated by the oracle, but not yet run on "
+            "a GPU itself (SURVEY.md 8(f) N4); set NMB200_UNVERIFIED=1 to use it".format(what))
+
+
+class NematusGRUCell:
+    """state' = u * state + (1 - u) * tanh(state_proj_c(state) * r + input_proj_c(x)),
+    [r, u] = sigmoid(state_proj_g(state) + input_proj_g(x)): the reset gate is applied AFTER the state
+    projection.  `use_state_bias` / `use_input_bias` as in the reference's constructor (:67-70)."""
+
+    def __init__(self, part, scope: str, input_size: int, size: int, use_state_bias: bool = False,
+                 use_input_bias: bool = True) -> None:
+        self.part, self.scope, self.input_size, self.size = part, scope, input_size, size
+        self.use_state_bias, self.use_input_bias = use_state_bias, use_input_bias
+
+    def declare(self) -> None:
+        for gate, width in (("gates", 2 * self.size), ("candidate", self.size)):
+            pre = "{}/{}/".format(self.scope, gate)
+            self.part.declare(pre + "input_proj/kernel", [self.input_size, width])
+            if self.use_input_bias:
+                self.part.declare(pre + "input_proj/bias", [width], zeros_initializer())
+            self.part.declare(pre + "state_proj/kernel", [self.size, width], block_orthogonal_initializer())
+            if self.use_state_bias:
+                self.part.declare(pre + "state_proj/bias", [width], zeros_initializer())
+
+    def _proj(self, gate: str, side: str, x: torch.Tensor, biased: bool) -> torch.Tensor:
+        pre = "{}/{}/{}/".format(self.scope, gate, side)
+        return ops.linear(x, self.part.var(pre + "kernel"), self.part.var(pre + "bias") if biased else None)
+
+    def input_projections(self, x: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+        """The input halves for any number of leading dims (all time steps in one GEMM each)."""
+        return (self._proj("gates", "input_proj", x, self.use_input_bias),
+                self._proj("candidate", "input_proj", x, self.use_input_bias))
+
+    def step(self, gates_in: torch.Tensor, cand_in: torch.Tensor, state: torch.Tensor) -> torch.Tensor:
+        gates = torch.sigmoid(self._proj("gates", "state_proj", state, self.use_state_bias) + gates_in)
+        reset, update = gates[:, :self.size], gates[:, self.size:]
+        cand = torch.tanh(self._proj("candidate", "state_proj", state, self.use_state_bias) * reset + cand_in)
+        return update * state + (1.0 - update) * cand
+
+    def __call__(self, x: torch.Tensor, state: torch.Tensor) -> torch.Tensor:
+        gates_in, cand_in = self.input_projections(x)
+        return self.step(gates_in, cand_in, state)
+
+    def sequence(self, x: torch.Tensor, lengths: torch.Tensor, reverse: bool) -> Tuple[torch.Tensor, torch.Tensor]:
+        """dynamic_rnn over [batch, time, input] with `sequence_length`: zero outputs and a carried state
+        past each length; `reverse` walks every sentence backwards inside its length, which is what
+        reverse_sequence -> dynamic_rnn -> reverse_sequence computes (recurrent.py:96-104)."""
+        bsz, steps, _ = x.shape
+        gates_in, cand_in = self.input_projections(x)
+        state = torch.zeros(bsz, self.size, device=x.device, dtype=torch.float32)
+        outputs = [None] * steps
+        for t in (range(steps - 1, -1, -1) if reverse else range(steps)):
+            live = (lengths > t).to(torch.float32).unsqueeze(1)
+            new = self.step(gates_in[:, t], cand_in[:, t], state)
+            outputs[t] = new * live
+            state = new * live + state * (1.0 - live)
+        return torch.stack(outputs, 1), state

@@ -69,6 +69,22 @@ def orthogonal_initializer() -> Initializer:
     return init
 
 
+def block_orthogonal_initializer() -> Initializer:
+    """The reference's own `orthogonal_initializer()` (nn/ortho_gru_cell.py:4-37): a [dim, m*dim] kernel
+    is m independent dim x dim orthogonal blocks side by side (the left singular vectors of a normal
+    matrix there; the Q factor of one here - both are Haar-distributed orthogonal matrices)."""
+    square = orthogonal_initializer()
+
+    def init(shape, gen):
+        if len(shape) != 2:
+            raise ValueError("Orthogonal initializer only works with 2D matrices.")
+        rows, cols = shape
+        if cols % rows != 0:
+            raise ValueError("Shape {} is not compatible with orthogonal initializer.".format(str(shape)))
+        return torch.cat([square((rows, rows), gen) for _ in range(cols // rows)], 1).contiguous()
+    return init
+
+
 def variance_scaling_initializer(scale: float = 1.0, mode: str = "fan_avg",
                                  distribution: str = "uniform") -> Initializer:
     """tf.variance_scaling_initializer (encoders/transformer.py:152-153)."""

@@ -1,0 +1,107 @@
+"""CPU stand-ins for `neuralmonkey_b200.ops` - TEST INFRASTRUCTURE ONLY.
+
+The product has no CPU execution path (ops call the CUDA library and fail loudly without it).  To check
+the HOST side of the model parts without a GPU - which tensors they feed to which operation, variable
+names, teacher forcing, loop bookkeeping, the step-wise variants - the `cpu_model` fixture of
+tests/test_host_model_cpu.py swaps every `ops.<name>` the model parts call for the function of the same
+name and signature below, written with the oracle's arithmetic, and points `runtime.device()` at the CPU.
+Nothing outside tests/ imports this module; the kernels themselves are tested in tests/test_gpu_*.py."""
+import math
+from typing import Optional
+
+import torch
+
+from oracle import nm_oracle as O
+
+_ACT = {None: lambda x: x, "tanh": torch.tanh, "relu": torch.relu, "sigmoid": torch.sigmoid}
+
+
+def linear(x, w, b=None, act=None):
+    y = x @ w
+    if b is not None:
+        y = y + b
+    return _ACT[act](y)
+
+
+def embed(ids, table, mask=None):
+    out = table[ids]
+    return out if mask is None else out * mask.unsqueeze(-1)
+
+
+def maxout(z):
+    size = z.shape[-1] // 2
+    return torch.maximum(z[..., :size], z[..., size:])
+
+
+def layer_norm(x, gamma, beta, eps=1e-6):
+    return O.layer_norm(x, gamma, beta, eps)
+
+
+def gru_layer(x, gates_kernel, gates_bias, cand_kernel, cand_bias, h0=None, lengths=None, reverse=False,
+              drop_mask=None, sm_budget=0):
+    full = torch.full((x.shape[0],), x.shape[1], dtype=torch.int64)
+    lens = full if lengths is None else lengths.to(torch.int64)
+    inputs = O.reverse_sequence(x, lens) if reverse else x
+    raw, final = O.dynamic_gru(inputs, None if lengths is None else lens, gates_kernel, gates_bias,
+                               cand_kernel, cand_bias, h0)
+    if reverse:
+        raw = O.reverse_sequence(raw, lens)
+    return (raw if drop_mask is None else raw * drop_mask), final, raw
+
+
+def bahdanau_attention(keys, values, mask, qproj, v, bias):
+    energies = (v * torch.tanh(keys.unsqueeze(1) + qproj.unsqueeze(2))).sum(-1) + bias
+    weights = torch.softmax(energies, dim=-1)
+    if mask is not None:
+        weights = weights * mask.unsqueeze(1)
+        weights = weights / (weights.sum(-1, keepdim=True) + 1e-8)
+    return torch.einsum("bqt,btc->bqc", weights, values), weights
+
+
+def logits_xent(x, w, b, targets, weights, unk_index=-1, trans_w=False, keep_logits=False):
+    logits = x @ (w.t() if trans_w else w)
+    if b is not None:
+        logits = logits + b
+    if unk_index >= 0:
+        pen = torch.zeros(logits.shape[-1], dtype=logits.dtype)
+        pen[unk_index] = -1e9
+        logits = logits + pen
+    lse = torch.logsumexp(logits, dim=-1)
+    xent = (lse - logits.gather(1, targets.unsqueeze(1)).squeeze(1)) * weights
+    return xent, lse, torch.argmax(logits, dim=-1), (logits if keep_logits else None)
+
+
+def log_softmax_from_lse(logits, lse):
+    return logits - lse.unsqueeze(-1)
+
+
+def mha_core(q, k, v, key_mask, causal, heads):
+    bsz, tq, dim = q.shape
+    tk, dh = k.shape[1], dim // heads
+
+    def split(x):
+        return x.reshape(bsz, x.shape[1], heads, dh).transpose(1, 2)
+    energies = split(q) @ split(k).transpose(-1, -2) / math.sqrt(dh)
+    if causal:      # mask_future: tf.where(lower triangle, e, -1e9)
+        tri = torch.tril(torch.ones(tq, tk, dtype=torch.bool))
+        energies = torch.where(tri, energies, torch.full_like(energies, -1e9))
+    if key_mask is not None:
+        m = key_mask.unsqueeze(1).unsqueeze(1)
+        energies = energies * m + (1.0 - m) * -1e9
+    weights = torch.softmax(energies, dim=-1)
+    return (weights @ split(v)).transpose(1, 2).reshape(bsz, tq, dim), weights
+
+
+def beam_step(logprobs, logprob_sum, lengths, finished, alpha):
+    scores, words, beams, lsum, lens, fin = O.beam_step(logprobs, logprob_sum, lengths.to(torch.int32),
+                                                        finished.to(torch.bool), alpha)
+    return scores, words, beams, lsum, lens, fin.to(torch.uint8)
+
+
+def beam_gather(x, beam_ids, bsz, k):
+    flat = (torch.arange(bsz).unsqueeze(1) * k + beam_ids.to(torch.int64)).reshape(-1)
+    return x[flat]
+
+
+STAND_INS = ("linear", "embed", "maxout", "layer_norm", "gru_layer", "bahdanau_attention", "logits_xent",
+             "log_softmax_from_lse", "mha_core", "beam_step", "beam_gather")

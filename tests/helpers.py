@@ -87,4 +87,4 @@ def rel_err(a: torch.Tensor, b: torch.Tensor) -> float:
 
 
 def max_abs(a: torch.Tensor, b: torch.Tensor) -> float:
-    return float((a.double().cpu() - b.double().cpu()).abs().max())
+    return float((a.detach().double().cpu() - b.detach().double().cpu()).abs().max())

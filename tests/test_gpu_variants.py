@@ -1,0 +1,69 @@
+"""The step-wise model variants (Nematus GRU cell, conditional GRU, nematus / mlp
+deep outputs, nematus initial state) on the GPU against the oracle.
+
+These variants are compositions of GPU-verified operations that have themselves not been run on a GPU
+yet (nn/variants.py), so both the product and this file sit behind NMB200_UNVERIFIED=1:
+
+    NMB200_UNVERIFIED=1 python -m pytest tests/test_gpu_variants.py -m gpu -q
+
+Their host logic is already checked on the CPU over stand-in operations
+(tests/test_host_model_cpu.py::test_decoder_and_encoder_variants)."""
+import os
+
+import pytest
+import torch
+
+from oracle import nm_oracle as O
+from tests.helpers import feed, max_abs, oracle_params_for, random_batch
+from tests.test_host_model_cpu import _build_variant
+
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.skipif(os.environ.get("NMB200_UNVERIFIED") != "1",
+                                 reason="variants not yet verified on a GPU; set NMB200_UNVERIFIED=1")]
+
+
+@pytest.mark.parametrize("backend,tol", [("simt", 5e-5), ("auto", 1e-2)])
+@pytest.mark.parametrize("cell,conditional,out_proj,enc_proj,enc_cell", [
+    ("NematusGRU", True, "nematus", "nematus", "NematusGRU"),
+    ("GRU", True, "mlp", "linear", "GRU"),
+    ("NematusGRU", False, "maxout", "linear", "NematusGRU")])
+def test_variants_against_oracle(cell, conditional, out_proj, enc_proj, enc_cell, backend, tol):
+    from neuralmonkey_b200 import ops
+    try:
+        ops.set_gemm_backend(backend)
+        model = _build_variant(cell, conditional, out_proj, enc_proj, enc_cell)
+        params = oracle_params_for(model)
+        model["arena"].load_dict(params)
+        src, tgt = random_batch(5, 8, 7, 30, 40, seed=1)
+        feed(model, src, tgt, train=True)
+        enc, dec = model["enc"], model["dec"]
+        spec = O.RNNDecoderSpec("decoder", "attention", 10, out_proj, False, cell, conditional, enc_proj, 8, 2)
+        p64 = {n: v.double().requires_grad_(True) for n, v in params.items()}
+
+        def oracle_encoder(pp):
+            seq = O.embedded_sequence(pp, "sentence_encoder_input", [src])
+            return O.recurrent_encoder(pp, "sentence_encoder", seq["temporal_states"], seq["temporal_mask"],
+                                       [(5, "bidirectional", enc_cell)])
+        odec = O.decoder_train(p64, spec, oracle_encoder(p64), tgt.t())
+        assert max_abs(enc.temporal_states, oracle_encoder(p64)["temporal_states"]) < tol
+        assert max_abs(dec.train_output_states, odec["train_output_states"]) < tol
+        assert abs(float(dec.train_loss) - float(odec["train_loss"])) < max(tol, 1e-5)
+        arena = model["arena"]
+        arena.zero_grad()
+        dec.train_loss.backward()
+        odec["train_loss"].backward()
+        gtol = 3e-4 if backend == "simt" else 2e-2
+        for name, grad in arena.named_grads().items():
+            want = p64[name].grad
+            want = torch.zeros_like(p64[name]) if want is None else want
+            err = float((grad.double().cpu() - want.reshape(grad.shape)).norm())
+            assert err <= gtol * float(want.norm()) + 1e-6, (name, err, float(want.norm()))
+        feed(model, src, tgt, train=False)
+        og = O.decoder_greedy(params, spec, oracle_encoder(params))
+        assert max_abs(dec.runtime_logits, og["runtime_logits"]) < 10 * tol
+        if backend == "simt":
+            assert bool((dec.runtime_symbols.cpu() == og["output_symbols"]).all())
+        out = model["trainer"].train_step()          # one optimizer step through the arena
+        assert float(out["losses"][0]) > 0.0
+    finally:
+        ops.set_gemm_backend("auto")

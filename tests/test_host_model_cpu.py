@@ -1,0 +1,267 @@
+"""The HOST side of the model parts, run on the CPU over stand-in operations (tests/cpu_ops.py) and
+compared with the oracle: which tensors go to which operation, variable names, teacher forcing, the
+decoding loops, beam-search bookkeeping, and the step-wise decoder / encoder variants.  The CUDA
+kernels are not involved here (tests/test_gpu_*.py test those through the C ABI); what this guards is
+the Python around them, which can regress without a GPU in the loop."""
+import pytest
+import torch
+
+from oracle import nm_oracle as O
+from tests import cpu_ops
+from tests.helpers import (build_bahdanau, feed, max_abs, oracle_params_for, oracle_spec, random_batch)
+
+TOY = dict(vs=60, vt=70, es=11, he=7, et=9, hd=8, out=9, maxout=True, max_len=10, supress_unk=True)
+
+
+@pytest.fixture
+def cpu_model(monkeypatch):
+    from neuralmonkey_b200 import ops, runtime
+    for name in cpu_ops.STAND_INS:
+        monkeypatch.setattr(ops, name, getattr(cpu_ops, name))
+    monkeypatch.setattr(runtime, "_device", torch.device("cpu"))
+    monkeypatch.setenv("NMB200_UNVERIFIED", "1")
+    yield
+    runtime.reset()
+
+
+def _grads(model):
+    return {n: model["arena"].get(n).grad for n in model["arena"].train_names}
+
+
+def test_bahdanau_training_pass_and_gradients(cpu_model):
+    model = build_bahdanau(**TOY)
+    params = oracle_params_for(model)
+    model["arena"].load_dict(params)
+    src, tgt = random_batch(6, 8, 7, TOY["vs"], TOY["vt"], seed=0)
+    feed(model, src, tgt, train=True)
+    enc, dec = model["enc"], model["dec"]
+    spec = oracle_spec(True, 10, True)
+    p = {n: v.clone().requires_grad_(True) for n, v in params.items()}
+    oenc = O.sentence_encoder(p, "sentence_encoder", src)
+    odec = O.decoder_train(p, spec, oenc, tgt.t())
+    assert max_abs(enc.temporal_states, oenc["temporal_states"]) < 1e-5
+    assert max_abs(dec.train_output_states, odec["train_output_states"]) < 1e-5
+    assert max_abs(dec.train_xents, odec["train_xents"]) < 1e-4
+    assert abs(float(dec.train_loss) - float(odec["train_loss"])) < 1e-5
+    dec.train_loss.backward()
+    odec["train_loss"].backward()
+    for name, grad in _grads(model).items():
+        want = p[name].grad if p[name].grad is not None else torch.zeros_like(p[name])
+        got = grad if grad is not None else torch.zeros_like(p[name])
+        assert float((got - want.reshape(got.shape)).norm()) <= 1e-4 * float(want.norm()) + 1e-7, name
+
+
+def test_bahdanau_greedy_decoding(cpu_model):
+    model = build_bahdanau(**TOY)
+    params = oracle_params_for(model)
+    model["arena"].load_dict(params)
+    src, tgt = random_batch(6, 8, 7, TOY["vs"], TOY["vt"], seed=3)
+    feed(model, src, tgt, train=False)
+    dec = model["dec"]
+    og = O.decoder_greedy(params, oracle_spec(True, 10, True), O.sentence_encoder(params, "sentence_encoder", src),
+                          tgt.t())
+    assert dec.runtime_logits.shape == og["runtime_logits"].shape
+    keep = torch.ones(TOY["vt"], dtype=torch.bool)
+    keep[3] = False
+    assert max_abs(dec.runtime_logits[..., keep], og["runtime_logits"][..., keep]) < 1e-4
+    assert bool((dec.runtime_symbols == og["output_symbols"]).all())
+    assert bool((dec.runtime_mask == og["runtime_mask"]).all())
+
+
+@pytest.mark.parametrize("beam,bsz", [(3, 1), (4, 3)])
+def test_beam_search_over_the_rnn_decoder(cpu_model, beam, bsz):
+    from neuralmonkey_b200.decoders import BeamSearchDecoder
+    from neuralmonkey_b200.runners.beamsearch_runner import select_hypotheses
+    model = build_bahdanau(**TOY)
+    params = oracle_params_for(model)
+    model["arena"].load_dict(params)
+    src, _tgt = random_batch(bsz, 8, 7, TOY["vs"], TOY["vt"], seed=9)
+    bs = BeamSearchDecoder(name="bs", parent_decoder=model["dec"], beam_size=beam, max_steps=8,
+                           length_normalization=1.0)
+    bs.use_cuda_graph = False
+    feed(model, src, None, train=False)
+    bs.reset_batch()
+    bs.batch_size = bsz
+    out = bs.outputs
+    spec = oracle_spec()
+    oenc = O.sentence_encoder(params, "sentence_encoder", src)
+    states = oenc["temporal_states"].repeat_interleave(beam, 0)
+    mask = oenc["temporal_mask"].repeat_interleave(beam, 0)
+    hidden = O.bahdanau_precompute(params, "attention", states)
+    emb = params["decoder/word_embeddings"]
+    prev0 = O.decoder_initial_state(params, spec, oenc["output"]).repeat_interleave(beam, 0)
+
+    def run(embedded, prev):
+        output, cell, _c, _w = O.decoder_step(params, spec, embedded, prev, hidden, states, mask)
+        return cell, torch.log_softmax(O.state_to_logits(params, spec, output), -1)
+
+    prev1, first = run(emb[torch.full((bsz * beam,), O.START, dtype=torch.int64)], prev0)
+    want = O.beam_search(lambda prev, words, _f: run(emb[words], prev), prev1, first, beam, 8, 1.0,
+                         lambda st, idx: st[idx])
+    got = out.last_search_step_output
+    assert bool((got.token_ids[1:] == want["token_ids"]).all())
+    assert max_abs(got.scores, want["scores"]) < 1e-4
+    assert bool((out.last_search_state.lengths == want["lengths"]).all())
+    assert bool((out.last_search_state.finished.to(torch.bool) == want["finished"]).all())
+    words, _loss = select_hypotheses(got.scores.numpy(), got.token_ids.numpy(), 1,
+                                     model["dec"].vocabulary.index_to_word)
+    assert len(words) == bsz
+
+
+def _transformer(tie=True, supress_unk=False, bsz=5, seed=0):
+    from tests.test_gpu_transformer import CFG, build_transformer
+    model = build_transformer(**CFG, tie=tie, supress_unk=supress_unk)
+    params = oracle_params_for(model, scale=0.2)
+    for name in params:
+        if name.endswith("gamma"):
+            params[name] = 1.0 + params[name]
+    model["arena"].load_dict(params)
+    src, tgt = random_batch(bsz, 8, 7, CFG["vs"], CFG["vt"], seed=seed)
+    return model, params, src, tgt, CFG
+
+
+@pytest.mark.parametrize("tie", [True, False])
+def test_transformer_training_pass_and_gradients(cpu_model, tie):
+    from tests.test_gpu_transformer import feed_transformer, oracle_encoder
+    model, params, src, tgt, cfg = _transformer(tie=tie, supress_unk=not tie)
+    feed_transformer(model, src, tgt, train=True)
+    enc, dec = model["enc"], model["dec"]
+    spec = O.TransformerDecoderSpec("decoder", cfg["depth"], cfg["heads"], cfg["heads"], cfg["max_len"], tie, not tie)
+    p = {n: v.clone().requires_grad_(True) for n, v in params.items()}
+    oenc = oracle_encoder(p, src, cfg)
+    odec = O.transformer_decoder_train(p, spec, oenc, tgt)
+    assert max_abs(enc.temporal_states, oenc["states"]) < 5e-5
+    assert max_abs(dec.train_output_states.transpose(0, 1), odec["states"]) < 5e-5
+    assert abs(float(dec.train_loss) - float(odec["loss"])) < 1e-4
+    dec.train_loss.backward()
+    odec["loss"].backward()
+    for name, grad in _grads(model).items():
+        want = p[name].grad if p[name].grad is not None else torch.zeros_like(p[name])
+        got = grad if grad is not None else torch.zeros_like(p[name])
+        assert float((got - want.reshape(got.shape)).norm()) <= 1e-3 * float(want.norm()) + 1e-6, name
+
+
+@pytest.mark.parametrize("kv_cache", [True, False])
+def test_transformer_greedy_and_beam_search(cpu_model, kv_cache):
+    from neuralmonkey_b200.decoders import BeamSearchDecoder
+    from tests.test_gpu_transformer import _oracle_transformer_beam, feed_transformer, oracle_encoder
+    model, params, src, tgt, cfg = _transformer(seed=2, bsz=3)
+    model["dec"].use_kv_cache = kv_cache
+    feed_transformer(model, src, tgt, train=False)
+    dec = model["dec"]
+    spec = O.TransformerDecoderSpec("decoder", cfg["depth"], cfg["heads"], cfg["heads"], cfg["max_len"], True, False)
+    oenc = oracle_encoder(params, src, cfg)
+    og = O.transformer_decoder_greedy(params, spec, oenc)
+    assert dec.runtime_logits.shape == og["logits"].shape
+    assert max_abs(dec.runtime_logits, og["logits"]) < 2e-4
+    assert bool((dec.runtime_symbols == og["symbols"]).all())
+    assert bool((dec.runtime_mask == og["mask"]).all())
+    bs = BeamSearchDecoder(name="bs", parent_decoder=dec, beam_size=4, max_steps=7, length_normalization=0.6)
+    bs.use_cuda_graph = False
+    feed_transformer(model, src, None, train=False)
+    bs.reset_batch()
+    bs.batch_size = 3
+    out = bs.outputs
+    want = _oracle_transformer_beam(params, spec, oenc, 4, 7, 0.6)
+    assert bool((out.last_search_step_output.token_ids[1:] == want["token_ids"]).all())
+    assert max_abs(out.last_search_step_output.scores, want["scores"]) < 2e-4
+    assert bool((out.last_search_state.lengths == want["lengths"]).all())
+
+
+def _build_variant(cell, conditional, out_proj, enc_proj, enc_cell):
+    from neuralmonkey_b200 import runtime, tf
+    from neuralmonkey_b200.attention import Attention
+    from neuralmonkey_b200.decoders import Decoder
+    from neuralmonkey_b200.decoders.encoder_projection import nematus_projection
+    from neuralmonkey_b200.decoders.output_projection import maxout_output, mlp_output, nematus_output
+    from neuralmonkey_b200.encoders import SentenceEncoder
+    from neuralmonkey_b200.trainers import CrossEntropyTrainer
+    from neuralmonkey_b200.vocabulary import Vocabulary
+    runtime.reset()
+    src_vocab = Vocabulary(["s{}".format(i) for i in range(26)])
+    tgt_vocab = Vocabulary(["t{}".format(i) for i in range(36)])
+    enc = SentenceEncoder(name="sentence_encoder", vocabulary=src_vocab, data_id="source", embedding_size=6,
+                          rnn_size=5, max_input_len=10, rnn_cell=enc_cell)
+    att = Attention(name="attention", encoder=enc)
+    projection = {"maxout": maxout_output, "nematus": nematus_output, "mlp": lambda n: mlp_output([11, n])}[out_proj](9)
+    dec = Decoder(encoders=[enc], vocabulary=tgt_vocab, data_id="target", name="decoder", max_output_len=10,
+                  rnn_size=10 if enc_proj == "concat" else 8, embedding_size=9, attentions=[att],
+                  output_projection=projection, rnn_cell=cell, conditional_gru=conditional,
+                  encoder_projection=nematus_projection() if enc_proj == "nematus" else None)
+    trainer = CrossEntropyTrainer(decoders=[dec], optimizer=tf.AdamOptimizer(learning_rate=1e-3))
+    for part in trainer.parameterizeds:
+        part.ensure_declared()
+    runtime.arena().finalize(runtime.device())
+    return {"enc": enc, "att": att, "dec": dec, "trainer": trainer, "arena": runtime.arena()}
+
+
+@pytest.mark.parametrize("cell,conditional,out_proj,enc_proj,enc_cell", [
+    ("NematusGRU", True, "nematus", "nematus", "NematusGRU"),      # tests/small.ini / tests/nematus.ini
+    ("GRU", True, "mlp", "linear", "GRU"),
+    ("NematusGRU", False, "maxout", "linear", "NematusGRU")])
+def test_decoder_and_encoder_variants(cpu_model, cell, conditional, out_proj, enc_proj, enc_cell):
+    """The step-wise variants (nn/variants.py, decoders/decoder.py `_variant_step`): the Nematus cell in
+    encoder and decoder, the conditional GRU, nematus / mlp deep outputs, the nematus initial state -
+    training pass, every gradient, greedy decoding and beam search against the oracle, whose
+    restatement of these variants is pinned to the reference's own code."""
+    from neuralmonkey_b200.decoders import BeamSearchDecoder
+    model = _build_variant(cell, conditional, out_proj, enc_proj, enc_cell)
+    params = oracle_params_for(model)
+    model["arena"].load_dict(params)
+    src, tgt = random_batch(5, 8, 7, 30, 40, seed=1)
+    feed(model, src, tgt, train=True)
+    enc, dec = model["enc"], model["dec"]
+    spec = O.RNNDecoderSpec("decoder", "attention", 10, out_proj, False, cell, conditional, enc_proj, 8, 2)
+    p = {n: v.clone().requires_grad_(True) for n, v in params.items()}
+
+    def oracle_encoder(pp):
+        seq = O.embedded_sequence(pp, "sentence_encoder_input", [src])
+        return O.recurrent_encoder(pp, "sentence_encoder", seq["temporal_states"], seq["temporal_mask"],
+                                   [(5, "bidirectional", enc_cell)])
+    oenc = oracle_encoder(p)
+    odec = O.decoder_train(p, spec, oenc, tgt.t())
+    assert max_abs(enc.temporal_states, oenc["temporal_states"]) < 1e-5
+    assert max_abs(enc.output, oenc["output"]) < 1e-5
+    assert max_abs(dec.train_output_states, odec["train_output_states"]) < 1e-5
+    assert max_abs(dec.train_rnn_outputs, odec["rnn_outputs"]) < 1e-5
+    assert abs(float(dec.train_loss) - float(odec["train_loss"])) < 1e-5
+    dec.train_loss.backward()
+    odec["train_loss"].backward()
+    for name, grad in _grads(model).items():
+        want = p[name].grad if p[name].grad is not None else torch.zeros_like(p[name])
+        got = grad if grad is not None else torch.zeros_like(p[name])
+        assert float((got - want.reshape(got.shape)).norm()) <= 1e-4 * float(want.norm()) + 1e-7, name
+    # greedy decoding and a beam search step through the same `_variant_step`
+    feed(model, src, tgt, train=False)
+    og = O.decoder_greedy(params, spec, oracle_encoder(params))
+    assert max_abs(dec.runtime_logits, og["runtime_logits"]) < 1e-4
+    assert bool((dec.runtime_symbols == og["output_symbols"]).all())
+    bs = BeamSearchDecoder(name="bs", parent_decoder=dec, beam_size=3, max_steps=6, length_normalization=1.0)
+    bs.use_cuda_graph = False
+    feed(model, src[:1], None, train=False)
+    bs.reset_batch()
+    bs.batch_size = 1
+    out = bs.outputs
+    oenc1 = {k: v[:1] for k, v in oracle_encoder(params).items()}
+    states, mask = oenc1["temporal_states"].repeat_interleave(3, 0), oenc1["temporal_mask"].repeat_interleave(3, 0)
+    hidden = O.bahdanau_precompute(params, "attention", states)
+    emb = params["decoder/word_embeddings"]
+
+    def run(embedded, prev):
+        output, cell_out, _c, _w = O.decoder_step(params, spec, embedded, prev, hidden, states, mask)
+        return cell_out, torch.log_softmax(O.state_to_logits(params, spec, output), -1)
+
+    prev0 = O.decoder_initial_state(params, spec, oenc1["output"], oenc1, 1).repeat_interleave(3, 0)
+    prev1, first = run(emb[torch.full((3,), O.START, dtype=torch.int64)], prev0)
+    want = O.beam_search(lambda prev, words, _f: run(emb[words], prev), prev1, first, 3, 6, 1.0,
+                         lambda st, idx: st[idx])
+    assert bool((out.last_search_step_output.token_ids[1:] == want["token_ids"]).all())
+    assert max_abs(out.last_search_step_output.scores, want["scores"]) < 1e-4
+
+
+def test_variants_are_refused_without_the_switch(cpu_model, monkeypatch):
+    monkeypatch.delenv("NMB200_UNVERIFIED")
+    with pytest.raises(NotImplementedError, match="NMB200_UNVERIFIED"):
+        _build_variant("NematusGRU", True, "maxout", "linear", "GRU")
+    with pytest.raises(NotImplementedError, match="NMB200_UNVERIFIED"):
+        _build_variant("GRU", False, "nematus", "linear", "GRU")
