@@ -371,25 +371,15 @@ class AutoregressiveDecoder(ModelPart):
         """argmax over logits[:, :, 1:] + 1 (autoregressive.py:341-349)."""
         logits = self.runtime_logits
         steps, bsz, vocab = logits.shape
-        dev = logits.device
-        lse = torch.empty(steps * bsz, device=dev, dtype=torch.float32)
-        arg = torch.empty(steps * bsz, device=dev, dtype=torch.int64)
-        from neuralmonkey_b200 import lib
         # columns 1..V-1 of every row: same buffer, pointer advanced by one float, ld = V
-        lib.call("nm_xent_fwd", lib.ptr(logits) + 4, None, None, lib.ptr(lse), None, lib.ptr(arg),
-                 steps * bsz, vocab - 1, vocab, lib.stream())
+        _lse, _xent, arg = ops.xent_rows(logits.reshape(steps * bsz, vocab), want_argmax=True, first_col=1)
         return (arg + 1).view(steps, bsz)
 
     @tensor
     def _runtime_lse(self) -> torch.Tensor:
         logits = self.runtime_logits
         steps, bsz, vocab = logits.shape
-        dev = logits.device
-        lse = torch.empty(steps * bsz, device=dev, dtype=torch.float32)
-        from neuralmonkey_b200 import lib
-        lib.call("nm_xent_fwd", lib.ptr(logits), None, None, lib.ptr(lse), None, None, steps * bsz,
-                 vocab, vocab, lib.stream())
-        return lse
+        return ops.xent_rows(logits.reshape(steps * bsz, vocab))[0]
 
     @tensor
     def runtime_logprobs(self) -> torch.Tensor:
@@ -404,15 +394,10 @@ class AutoregressiveDecoder(ModelPart):
         targets = self.train_inputs
         min_time = min(targets.shape[0], logits.shape[0])
         bsz, vocab = logits.shape[1], logits.shape[2]
-        dev = logits.device
         lg = logits[:min_time].reshape(min_time * bsz, vocab)
-        lse = torch.empty(min_time * bsz, device=dev, dtype=torch.float32)
-        xent = torch.empty(min_time * bsz, device=dev, dtype=torch.float32)
         tg = targets[:min_time].reshape(-1).contiguous()
         wt = self.train_mask[:min_time].reshape(-1).contiguous()
-        from neuralmonkey_b200 import lib
-        lib.call("nm_xent_fwd", lib.ptr(lg), lib.ptr(tg), lib.ptr(wt), lib.ptr(lse), lib.ptr(xent),
-                 None, min_time * bsz, vocab, vocab, lib.stream())
+        _lse, xent, _arg = ops.xent_rows(lg, tg, wt)
         return xent.view(min_time, bsz).t()
 
     @tensor

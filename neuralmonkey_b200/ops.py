@@ -539,6 +539,21 @@ def mha_core(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, key_mask: Option
 # ---------------------------------------------------------------------------
 # non-differentiable helpers
 # ---------------------------------------------------------------------------
+def xent_rows(logits: torch.Tensor, targets: Optional[torch.Tensor] = None,
+              weights: Optional[torch.Tensor] = None, want_argmax: bool = False, first_col: int = 0):
+    """Row statistics of materialised logits [M, V] (contiguous rows) over columns first_col..V-1:
+    (lse [M], weighted xent [M] or None without targets, first-index argmax [M] int64 relative to
+    first_col or None).  One `nm_xent_fwd` launch; the column offset is pointer arithmetic with ld = V."""
+    m, v = logits.shape
+    dev = logits.device
+    lse = torch.empty(m, device=dev, dtype=torch.float32)
+    xent = torch.empty(m, device=dev, dtype=torch.float32) if targets is not None else None
+    arg = torch.empty(m, device=dev, dtype=torch.int64) if want_argmax else None
+    call("nm_xent_fwd", ptr(logits) + 4 * first_col, ptr(targets), ptr(weights), ptr(lse), ptr(xent),
+         ptr(arg), m, v - first_col, v, lib.stream())
+    return lse, xent, arg
+
+
 def log_softmax_from_lse(logits: torch.Tensor, lse: torch.Tensor) -> torch.Tensor:
     m, v = logits.shape
     out = torch.empty_like(logits)

@@ -27,12 +27,8 @@ class GreedyRunner(BaseRunner):
             # feedback symbols without the `* unfinished` masking (runner.py:45-49)
             logits = decoder.runtime_logits
             steps, bsz, vocab = logits.shape
-            import torch
-            from neuralmonkey_b200 import lib
-            arg = torch.empty(steps * bsz, device=logits.device, dtype=torch.int64)
-            lse = torch.empty(steps * bsz, device=logits.device, dtype=torch.float32)
-            lib.call("nm_xent_fwd", lib.ptr(logits), None, None, lib.ptr(lse), None, lib.ptr(arg),
-                     steps * bsz, vocab, vocab, lib.stream())
+            from neuralmonkey_b200 import ops
+            _lse, _xent, arg = ops.xent_rows(logits.reshape(steps * bsz, vocab), want_argmax=True)
             symbols = arg.view(steps, bsz).cpu().numpy()
             train_loss = runtime_loss = 0.0
             if self.compute_losses:

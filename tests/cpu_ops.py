@@ -103,5 +103,44 @@ def beam_gather(x, beam_ids, bsz, k):
     return x[flat]
 
 
-STAND_INS = ("linear", "embed", "maxout", "layer_norm", "gru_layer", "bahdanau_attention", "logits_xent",
+def xent_rows(logits, targets=None, weights=None, want_argmax=False, first_col=0):
+    part = logits[:, first_col:]
+    lse = torch.logsumexp(part, dim=-1)
+    xent = None
+    if targets is not None:
+        xent = (lse - part.gather(1, targets.unsqueeze(1)).squeeze(1)) * weights
+    return lse, xent, (torch.argmax(part, dim=-1) if want_argmax else None)
+
+
+def adam_kernel(trainer, grad_scale, denominator, lr_t, lr_t_dev):
+    """Stand-in for GenericTrainer._adam_kernel (`nm_clip_adam_step`): gradients arrive in the `.grad` of
+    the arena's views here (plain autograd), not in the arena's gradient buffer.  Same order as the
+    kernel: scale, add the L1 / L2 terms of the regularised variables, clip per tensor, TF-Adam."""
+    from neuralmonkey_b200 import runtime
+    arena, opt = runtime.arena(), trainer.optimizer
+    scale = float(grad_scale) / (float(denominator) if denominator is not None else 1.0)
+    if not hasattr(trainer, "_l1l2_buf"):
+        trainer._l1l2_buf = torch.zeros(2)
+    l1 = l2 = 0.0
+    with torch.no_grad():
+        for name in arena.train_names:
+            var = arena.get(name)
+            grad = (var.grad if var.grad is not None else torch.zeros_like(var)) * scale
+            var.grad = None
+            if O.is_regularizable(name):
+                l1 += float(var.abs().sum())
+                l2 += float((var ** 2).sum())
+                grad = grad + trainer.l1_weight * torch.sign(var) + 2.0 * trainer.l2_weight * var
+            if trainer.clip_norm:
+                grad = O.clip_by_norm(grad, float(trainer.clip_norm))
+            info = arena.variables[name]
+            m = arena.adam_m[info.offset:info.offset + var.numel()].view(var.shape)
+            v = arena.adam_v[info.offset:info.offset + var.numel()].view(var.shape)
+            m.mul_(opt.beta1).add_(grad, alpha=1 - opt.beta1)
+            v.mul_(opt.beta2).addcmul_(grad, grad, value=1 - opt.beta2)
+            var.sub_((float(lr_t_dev) if lr_t_dev is not None else lr_t) * m / (v.sqrt() + opt.epsilon))
+    trainer._l1l2_buf[0], trainer._l1l2_buf[1] = l1, l2
+
+
+STAND_INS = ("xent_rows", "linear", "embed", "maxout", "layer_norm", "gru_layer", "bahdanau_attention", "logits_xent",
              "log_softmax_from_lse", "mha_core", "beam_step", "beam_gather")

@@ -265,3 +265,64 @@ def test_variants_are_refused_without_the_switch(cpu_model, monkeypatch):
         _build_variant("NematusGRU", True, "maxout", "linear", "GRU")
     with pytest.raises(NotImplementedError, match="NMB200_UNVERIFIED"):
         _build_variant("GRU", False, "nematus", "linear", "GRU")
+
+
+def _cli(monkeypatch, module, argv):
+    import importlib
+    import sys
+    monkeypatch.setattr(sys, "argv", argv)
+    importlib.import_module(module).main()
+
+
+@pytest.mark.parametrize("which", ["bahdanau", "transformer"])
+def test_experiments_end_to_end_on_the_cpu(cpu_model, monkeypatch, tmp_path, which):
+    """The INIs of tests/test_gpu_cli.py through `neuralmonkey_b200.train.main` / `run.main` in this
+    process, on the CPU over the stand-in operations: configuration, datasets and bucketing, feeding, the
+    training loop with validation, runners, evaluators, writers, checkpoints, the `.best` bookkeeping,
+    loading the variables back for neuralmonkey-run.  (The GPU test runs the same INIs through the real
+    entry points; this one keeps the host side honest between GPU sessions.)"""
+    import json
+    import os
+    from neuralmonkey_b200.trainers.generic_trainer import GenericTrainer
+    from tests import test_gpu_cli as cli
+    monkeypatch.setattr(GenericTrainer, "_adam_kernel", cpu_ops.adam_kernel)
+    monkeypatch.setenv("NEURALMONKEY_STRICT", "1")
+    data, out = str(tmp_path / "data"), str(tmp_path / "out")
+    cli._write_data(data)
+    ini = tmp_path / "exp.ini"
+    template = cli.INI if which == "bahdanau" else cli.TRANSFORMER_INI
+    ini.write_text(template.format(out=out, data=data, epochs=2))
+    _cli(monkeypatch, "neuralmonkey_b200.train", ["neuralmonkey-train", str(ini)])
+    log_text = open(os.path.join(out, "experiment.log")).read()
+    assert "Validation (epoch" in log_text
+    for name in ("experiment.ini", "original.ini", "variables.data.best", "variables.data.final"):
+        assert os.path.exists(os.path.join(out, name)), name
+    if which == "bahdanau":
+        assert os.path.exists(os.path.join(out, "variables.data"))
+        losses = [float(line.split("train_xent: ")[1].split()[0]) for line in log_text.splitlines()
+                  if " train " in line and "train_xent: " in line]
+        assert len(losses) >= 2 and losses[-1] < losses[0], losses
+        assert len(open(os.path.join(out, "val.out")).read().splitlines()) == 30
+        run_ini = tmp_path / "run.ini"
+        run_ini.write_text("""
+[main]
+test_datasets=[<val_data>]
+
+[batching]
+class=dataset.BatchingScheme
+batch_size=7
+
+[val_data]
+class=dataset.load
+series=["source", "target"]
+data=["{data}/val.src", "{data}/val.tgt"]
+outputs=[("target", "{out}/run.out")]
+batching=<batching>
+""".format(data=data, out=out))
+        _cli(monkeypatch, "neuralmonkey_b200.run",
+             ["neuralmonkey-run", str(ini), str(run_ini), "--json", str(tmp_path / "res.json")])
+        results = json.load(open(tmp_path / "res.json"))
+        assert "target/SacreBLEU" in results[0] and "target/runtime_xent" in results[0]
+        assert len(open(os.path.join(out, "run.out")).read().splitlines()) == 30
+    else:
+        assert "target_beam.rank001/BLEU" in log_text and "beam_search_score" in log_text
