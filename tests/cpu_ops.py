@@ -103,6 +103,15 @@ def beam_gather(x, beam_ids, bsz, k):
     return x[flat]
 
 
+def conv3x3_bias_relu(x, w, b):
+    y = torch.nn.functional.conv2d(x.permute(0, 3, 1, 2), w.permute(3, 2, 0, 1), b, padding=1)   # NHWC x HWIO
+    return torch.relu(y).permute(0, 2, 3, 1).contiguous()
+
+
+def maxpool2x2(x):
+    return torch.nn.functional.max_pool2d(x.permute(0, 3, 1, 2), 2, 2).permute(0, 2, 3, 1).contiguous()
+
+
 def xent_rows(logits, targets=None, weights=None, want_argmax=False, first_col=0):
     part = logits[:, first_col:]
     lse = torch.logsumexp(part, dim=-1)
@@ -142,5 +151,5 @@ def adam_kernel(trainer, grad_scale, denominator, lr_t, lr_t_dev):
     trainer._l1l2_buf[0], trainer._l1l2_buf[1] = l1, l2
 
 
-STAND_INS = ("xent_rows", "linear", "embed", "maxout", "layer_norm", "gru_layer", "bahdanau_attention", "logits_xent",
+STAND_INS = ("xent_rows", "conv3x3_bias_relu", "maxpool2x2", "linear", "embed", "maxout", "layer_norm", "gru_layer", "bahdanau_attention", "logits_xent",
              "log_softmax_from_lse", "mha_core", "beam_step", "beam_gather")

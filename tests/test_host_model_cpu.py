@@ -10,6 +10,8 @@ from oracle import nm_oracle as O
 from tests import cpu_ops
 from tests.helpers import (build_bahdanau, feed, max_abs, oracle_params_for, oracle_spec, random_batch)
 
+pytestmark = pytest.mark.filterwarnings("ignore:Converting a tensor with requires_grad")
+
 TOY = dict(vs=60, vt=70, es=11, he=7, et=9, hd=8, out=9, maxout=True, max_len=10, supress_unk=True)
 
 
@@ -326,3 +328,29 @@ batching=<batching>
         assert len(open(os.path.join(out, "run.out")).read().splitlines()) == 30
     else:
         assert "target_beam.rank001/BLEU" in log_text and "beam_search_score" in log_text
+
+
+def test_captioning_model_with_the_frozen_vgg_encoder(cpu_model, monkeypatch):
+    from neuralmonkey_b200.trainers.generic_trainer import GenericTrainer
+    from tests.test_gpu_imagenet import _params, build_captioning
+    monkeypatch.setattr(GenericTrainer, "_adam_kernel", cpu_ops.adam_kernel)
+    model = build_captioning()
+    params = _params(model)
+    enc, att, dec = model["enc"], model["att"], model["dec"]
+    images = torch.randn(3, 32, 32, 3, generator=torch.Generator().manual_seed(2))
+    _src, tgt = random_batch(3, 4, 6, 50, 50, seed=3)
+    enc.feed_images(images, train=True)
+    att.reset_batch()
+    att.train_mode, att.batch_size = True, 3
+    dec.feed_ids(tgt, 3, train=True)
+    oenc = O.vgg_features(params, "vgg_16", images, "vgg_16/conv5/conv5_3")
+    assert max_abs(enc.spatial_states, oenc["spatial_states"]) < 1e-4 * float(oenc["spatial_states"].abs().max())
+    odec = O.decoder_train(params, O.RNNDecoderSpec("decoder", "attention", 8, "tanh", False), oenc, tgt.t())
+    assert abs(float(dec.train_loss) - float(odec["train_loss"])) < 1e-4
+    arena = model["arena"]
+    assert not any(n.startswith("vgg_16") for n in arena.train_names)
+    before = arena.state_dict()
+    model["trainer"].train_step()
+    after = arena.state_dict()
+    assert all(torch.equal(before[n], after[n]) for n in before if n.startswith("vgg_16"))
+    assert not torch.equal(before["decoder/state_to_word_W"], after["decoder/state_to_word_W"])
