@@ -19,6 +19,7 @@
 // Descriptor bit layouts follow the PTX ISA "tcgen05 shared memory descriptor" and
 // "instruction descriptor" tables (as restated in CUTLASS cute/arch/mma_sm100_desc.hpp).
 #include <cuda.h>
+#include <cuda_fp16.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -252,16 +253,134 @@ __device__ __forceinline__ void epilogue_chunk_atomic(const TcEpilogue& e, const
     }
 }
 
+// ---------------------------------------------------------------------------
+// epilogues of the fp16-operand instances (ESZ == 2)
+// ---------------------------------------------------------------------------
+// Transposed store of a warp's 32x32 chunk: lane = row, so for one column the 32 lanes write 32
+// consecutive elements of the transposed matrix - a full segment without any staging.
+template <typename T>
+__device__ __forceinline__ void store32_transposed(T* __restrict__ ct, int64_t ldt, int64_t row, int col0,
+                                                   int64_t M, int ncols, const float (&x)[32], float beta) {
+  if (row >= M) return;
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    if (j < ncols) {
+      T* dst = ct + (int64_t)(col0 + j) * ldt + row;
+      if constexpr (sizeof(T) == 2) {
+        *dst = __float2half_rn(x[j]);
+      } else {
+        *dst = (beta != 0.f) ? (x[j] + *dst) : x[j];
+      }
+    }
+  }
+}
+
+// Row-major fp16 store of a warp's 32x32 chunk through the per-warp staging tile (32 rows x 64 B,
+// 16-byte slots XOR-swizzled): every store instruction then writes eight full 64-byte row segments.
+__device__ __forceinline__ void store32_half_coalesced(float* __restrict__ stage, __half* __restrict__ C,
+                                                       int64_t ldc, int64_t row_base, int col0, int64_t M,
+                                                       const float (&x)[32], int lane) {
+  uint4* st4 = reinterpret_cast<uint4*>(stage);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    __half2 h0 = __floats2half2_rn(x[8 * j], x[8 * j + 1]), h1 = __floats2half2_rn(x[8 * j + 2], x[8 * j + 3]);
+    __half2 h2 = __floats2half2_rn(x[8 * j + 4], x[8 * j + 5]), h3 = __floats2half2_rn(x[8 * j + 6], x[8 * j + 7]);
+    uint4 v;
+    v.x = *reinterpret_cast<uint32_t*>(&h0); v.y = *reinterpret_cast<uint32_t*>(&h1);
+    v.z = *reinterpret_cast<uint32_t*>(&h2); v.w = *reinterpret_cast<uint32_t*>(&h3);
+    st4[lane * 4 + (j ^ ((lane >> 1) & 3))] = v;     // rows 2q, 2q+1 share a swizzle: conflict-free both ways
+  }
+  __syncwarp();
+  const int sub = lane >> 2, slot = lane & 3;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int r = 8 * i + sub;
+    const uint4 v = st4[r * 4 + (slot ^ ((r >> 1) & 3))];
+    const int64_t grow = row_base + r;
+    if (grow < M) *reinterpret_cast<uint4*>(C + grow * ldc + col0 + 8 * slot) = v;
+  }
+  __syncwarp();
+}
+
+// TC_EPI_XENT_BWD16: (softmax - onehot) * row weight, stored as fp16 row-major and transposed.
+// The row weight is the 0/1 mask here (the caller applies the upstream scale in the consumers), so
+// the stored values lie in [-1, 1] and fp16 keeps TF32's 10 mantissa bits for them.
+__device__ __forceinline__ void epilogue_chunk_xent_bwd16(const TcEpilogue& e, const TcExt& ext, float (&x)[32],
+                                                          int64_t row, int col0, int64_t M, int N, int target,
+                                                          float row_lse2, float row_w,
+                                                          float* __restrict__ stage, int lane) {
+  if (col0 >= N) return;                                     // warp-uniform
+  const int ncols = min(32, N - col0);
+  float b[32];
+  load_bias32(e.bias, col0, ncols, b);
+#pragma unroll
+  for (int j = 0; j < 32; ++j) x[j] += b[j];
+  const int unk_rel = (int)e.unk_index - col0;
+  if (unk_rel >= 0 && unk_rel < 32) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j)
+      if (j == unk_rel) x[j] += -1e9f;
+  }
+#pragma unroll
+  for (int j = 0; j < 32; ++j) x[j] = exp2f(fmaf(x[j], TC_LOG2E, -row_lse2)) * row_w;
+  const int t_rel = target - col0;
+  if (t_rel >= 0 && t_rel < ncols) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j)
+      if (j == t_rel) x[j] -= row_w;
+  }
+  __half* c16 = reinterpret_cast<__half*>(ext.C16);
+  const bool vec_ok = ncols == 32 && ((ext.ldc16 & 7) == 0) && ((reinterpret_cast<uintptr_t>(c16) & 15) == 0);
+  if (vec_ok) {
+    store32_half_coalesced(stage, c16, ext.ldc16, row - lane, col0, M, x, lane);
+  } else if (row < M) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j)
+      if (j < ncols) c16[row * ext.ldc16 + col0 + j] = __float2half_rn(x[j]);
+  }
+  if (ext.C16T)
+    store32_transposed(reinterpret_cast<__half*>(ext.C16T), ext.ldc16t, row, col0, M, ncols, x, 0.f);
+}
+
+// TC_EPI_DENSE of the fp16 instances: C (or C^T) = alpha * row_scale[m] * acc + bias (+ C).
+__device__ __forceinline__ void epilogue_chunk_dense16(const TcEpilogue& e, const TcExt& ext, float (&x)[32],
+                                                       int64_t row, int col0, int64_t M, int N, float factor,
+                                                       bool vec_ok, float* __restrict__ stage, int lane,
+                                                       RowStats& st) {
+#pragma unroll
+  for (int j = 0; j < 32; ++j) x[j] *= factor;
+  if (!ext.transposed) {
+    epilogue_chunk<TC_EPI_DENSE>(e, x, row, col0, M, N, st, -1, 0.f, 0.f, vec_ok, stage, lane);
+    return;
+  }
+  if (col0 >= N) return;
+  const int ncols = min(32, N - col0);
+  if (e.bias) {
+    float b[32];
+    load_bias32(e.bias, col0, ncols, b);
+#pragma unroll
+    for (int j = 0; j < 32; ++j) x[j] += b[j];
+  }
+  store32_transposed(e.C, e.ldc, row, col0, M, ncols, x, e.beta);
+}
+
 // smem descriptor fields of an MN-major operand tile (bytes); a kernel argument so a
 // diagnostic run can probe them (NMB200_MN_* environment variables), fixed otherwise.
 struct MnDesc {
   uint32_t layout, sbo, lbo, kadv;
 };
 
-template <int BN, bool A_MN, bool B_MN, int MODE>
+// ESZ = operand element size: 4 = fp32 consumed as TF32 (kind::tf32), 2 = fp16 (kind::f16, K-major
+// operands only).  A k-block is 128 bytes of K either way (32 or 64 elements) and one instruction
+// consumes 32 of them, so the smem ring, the descriptors and the TMEM layout are the same.
+template <int BN, bool A_MN, bool B_MN, int MODE, int ESZ = 4>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
-               int64_t M, int64_t N, int64_t K, TcEpilogue epi, MnDesc mn, int splits, int kb_per_split) {
+               int64_t M, int64_t N, int64_t K, TcEpilogue epi, MnDesc mn, int splits, int kb_per_split,
+               TcExt ext) {
+  static_assert(ESZ == 4 || (ESZ == 2 && !A_MN && !B_MN), "fp16 operands are K-major only");
+  static_assert(ESZ == 2 || MODE != TC_EPI_XENT_BWD16, "the fp16 epilogue belongs to the fp16 instances");
+  constexpr int BK = 128 / ESZ;                // elements per 128-byte k-block
   using Cfg = TcCfg<BN>;
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
@@ -281,7 +400,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   // epilogue adds its partial tile into C with red.global.add (weight-gradient products
   // have tiny outputs and very long K: without this only a handful of SMs would work)
   const int64_t num_tiles = tiles_m * tiles_n * splits;
-  const int num_kb_total = (int)((K + TC_BK - 1) / TC_BK);  // host guarantees no empty split
+  const int num_kb_total = (int)((K + BK - 1) / BK);  // host guarantees no empty split
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) {
@@ -322,7 +441,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           const uint32_t a_dst = smem_base + stage * Cfg::STAGE_BYTES;
           const uint32_t b_dst = a_dst + TC_A_BYTES;
           mbar_expect_tx(full_bar(stage), (uint32_t)Cfg::STAGE_BYTES);
-          const int32_t k0 = kb * TC_BK;
+          const int32_t k0 = kb * BK;
           if (!A_MN) {
             tma_load_2d(a_dst, &map_a, full_bar(stage), k0, m0);  // box {32 k, 128 rows}
           } else {
@@ -346,7 +465,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     if (lane == 0) {
       // instruction descriptor: c=F32 [4,6)=1, a=TF32 [7,10)=2, b=TF32 [10,13)=2,
       // a_major bit15, b_major bit16, N>>3 [17,23), M>>4 [24,29)
-      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((A_MN ? 1u : 0u) << 15) |
+      constexpr uint32_t FMT = ESZ == 4 ? 2u : 0u;   // TF32 = 2, F16 = 0
+      const uint32_t idesc = (1u << 4) | (FMT << 7) | (FMT << 10) | ((A_MN ? 1u : 0u) << 15) |
                              ((B_MN ? 1u : 0u) << 16) | ((uint32_t)(BN >> 3) << 17) |
                              ((uint32_t)(TC_BM >> 4) << 24);
       int stage = 0;
@@ -378,7 +498,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                                      : smem_desc(a_addr + k * 32, 16, 1024, SMEM_LAYOUT_SW128);
             const uint64_t db = B_MN ? smem_desc(b_addr + k * mn.kadv, mn.lbo, mn.sbo, mn.layout)
                                      : smem_desc(b_addr + k * 32, 16, 1024, SMEM_LAYOUT_SW128);
-            umma_tf32(d_tmem, da, db, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+            if (ESZ == 4)
+              umma_tf32(d_tmem, da, db, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+            else
+              umma_f16(d_tmem, da, db, idesc, (kb > 0 || k > 0) ? 1u : 0u);
           }
           umma_commit(empty_bar(stage));  // frees this smem stage when the MMAs retire
           if (++stage == STAGES) { stage = 0; phase ^= 1u; }
@@ -416,18 +539,35 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           row_lse2 = epi.lse[row] * TC_LOG2E;
           row_w = (epi.weights ? epi.weights[row] : 1.f) * epi.scale[0];
         }
+        if (MODE == TC_EPI_XENT_BWD16) {
+          row_lse2 = epi.lse[row] * TC_LOG2E;
+          row_w = epi.weights ? epi.weights[row] : 1.f;
+        }
+      }
+      float factor16 = 1.f;
+      if (ESZ == 2 && MODE == TC_EPI_DENSE) {
+        if (ext.alpha) factor16 = ext.alpha[0];
+        if (ext.row_scale && row < M) factor16 *= ext.row_scale[row];
       }
       const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN);
 #pragma unroll 1
       for (int c = half; c < BN / 32; c += 2) {
         float v[32];
         tmem_ld32(t_row + (uint32_t)(c * 32), v);
+        if constexpr (MODE == TC_EPI_XENT_BWD16) {
+          epilogue_chunk_xent_bwd16(epi, ext, v, row, (int)(tn * BN) + c * 32, M, n32, target, row_lse2,
+                                    row_w, stage, lane);
+        } else if constexpr (ESZ == 2 && MODE == TC_EPI_DENSE) {
+          epilogue_chunk_dense16(epi, ext, v, row, (int)(tn * BN) + c * 32, M, n32, factor16, vec_ok,
+                                 stage, lane, st);
+        } else {
         if (MODE == TC_EPI_DENSE && splits > 1)
           epilogue_chunk_atomic(epi, v, row, (int)(tn * BN) + c * 32, M, n32, split == 0,
                                 vec_ok && ((reinterpret_cast<uintptr_t>(epi.bias) & 15) == 0), stage, lane);
         else
           epilogue_chunk<MODE>(epi, v, row, (int)(tn * BN) + c * 32, M, n32, st, target, row_lse2,
                                row_w, vec_ok, stage, lane);
+        }
       }
       if (MODE == TC_EPI_XENT_FWD && row < M)
         epi.part[(row * tiles_n + tn) * 2 + half] =
@@ -539,8 +679,45 @@ static int launch_cfg(const CUtensorMap& ma, const CUtensorMap& mb, int64_t M, i
   const int64_t grid = tiles < sm_count() ? tiles : sm_count();
   if (kb_per_split <= 0) kb_per_split = (int)ceil_div(K, TC_BK);
   kern<<<(unsigned)grid, TC_THREADS, Cfg::SMEM_BYTES, s>>>(ma, mb, M, N, K, epi, mn_desc_config(),
-                                                           splits, kb_per_split);
+                                                           splits, kb_per_split, TcExt{});
   NM_LAUNCH_CHECK("tc_gemm_kernel");
+  return NM_OK;
+}
+
+// fp16 operands (both K-major): no split-K, one wave structure as above
+template <int BN, int MODE>
+static int launch_cfg16(const CUtensorMap& ma, const CUtensorMap& mb, int64_t M, int64_t N, int64_t K,
+                        const TcEpilogue& epi, const TcExt& ext, cudaStream_t s) {
+  using Cfg = TcCfg<BN>;
+  auto kern = tc_gemm_kernel<BN, false, false, MODE, 2>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    NM_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    attr_done = true;
+  }
+  const int64_t tiles = ceil_div(M, TC_BM) * ceil_div(N, BN);
+  const int64_t grid = tiles < sm_count() ? tiles : sm_count();
+  kern<<<(unsigned)grid, TC_THREADS, Cfg::SMEM_BYTES, s>>>(ma, mb, M, N, K, epi, MnDesc{0, 0, 0, 0}, 1,
+                                                           (int)ceil_div(K, 64), ext);
+  NM_LAUNCH_CHECK("tc_gemm_kernel(fp16)");
+  return NM_OK;
+}
+
+// 2-D fp16 tensor [rows, cols] with row pitch ld (elements); box = {64 k, box_rows}, 128-byte swizzle.
+static int make_map16(CUtensorMap* map, const void* base, int64_t rows, int64_t cols, int64_t ld,
+                      uint32_t box_rows) {
+  EncodeTiledFn fn = get_encode_fn();
+  NM_REQUIRE(fn != nullptr, NM_E_NO_DEVICE, "tc_gemm16: cuTensorMapEncodeTiled not available");
+  const cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  const cuuint64_t gstride[1] = {(cuuint64_t)ld * 2};
+  const cuuint32_t box[2] = {64, box_rows};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), gdim, gstride, box,
+                        estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  NM_REQUIRE(r == CUDA_SUCCESS, NM_E_INVALID,
+             "tc_gemm16: cuTensorMapEncodeTiled failed (%d) rows=%lld cols=%lld ld=%lld", (int)r,
+             (long long)rows, (long long)cols, (long long)ld);
   return NM_OK;
 }
 
@@ -624,6 +801,28 @@ int tc_gemm_launch(int transA, int transB, int64_t M, int64_t N, int64_t K, cons
   if (bn == 160) NM_TC_DISPATCH(160, TC_EPI_DENSE);
   NM_TC_DISPATCH(256, TC_EPI_DENSE);
 #undef NM_TC_DISPATCH
+}
+
+int tc_gemm16_launch(int64_t M, int64_t N, int64_t K, const void* A, int64_t lda, const void* B,
+                     int64_t ldb, const TcEpilogue& epi, const TcExt& ext, cudaStream_t s) {
+  NM_REQUIRE(M >= 1 && N >= 1 && K >= 1 && M <= 0x7fffffffLL && N <= 0x7fffffffLL && K <= 0x7fffffffLL,
+             NM_E_INVALID, "tc_gemm16: bad shape %lld x %lld x %lld", (long long)M, (long long)N, (long long)K);
+  NM_REQUIRE((lda & 7) == 0 && (ldb & 7) == 0 && (reinterpret_cast<uintptr_t>(A) & 15) == 0 &&
+                 (reinterpret_cast<uintptr_t>(B) & 15) == 0,
+             NM_E_INVALID, "tc_gemm16: fp16 operands need 16-byte aligned bases and row pitches");
+  const int bn = (epi.mode == TC_EPI_DENSE) ? pick_bn(M, N, K) : TC_XENT_BN;
+  CUtensorMap ma, mb;
+  int rc = make_map16(&ma, A, M, K, lda, TC_BM);
+  if (rc) return rc;
+  rc = make_map16(&mb, B, N, K, ldb, (uint32_t)bn);
+  if (rc) return rc;
+  if (epi.mode == TC_EPI_XENT_FWD) return launch_cfg16<256, TC_EPI_XENT_FWD>(ma, mb, M, N, K, epi, ext, s);
+  if (epi.mode == TC_EPI_XENT_BWD16) return launch_cfg16<256, TC_EPI_XENT_BWD16>(ma, mb, M, N, K, epi, ext, s);
+  NM_REQUIRE(epi.mode == TC_EPI_DENSE, NM_E_INVALID, "tc_gemm16: unsupported epilogue %d", epi.mode);
+  if (bn == 64) return launch_cfg16<64, TC_EPI_DENSE>(ma, mb, M, N, K, epi, ext, s);
+  if (bn == 128) return launch_cfg16<128, TC_EPI_DENSE>(ma, mb, M, N, K, epi, ext, s);
+  if (bn == 160) return launch_cfg16<160, TC_EPI_DENSE>(ma, mb, M, N, K, epi, ext, s);
+  return launch_cfg16<256, TC_EPI_DENSE>(ma, mb, M, N, K, epi, ext, s);
 }
 
 }  // namespace nm

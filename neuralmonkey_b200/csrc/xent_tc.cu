@@ -108,4 +108,30 @@ int nm_logits_xent_bwd(const float* X, int64_t ldx, const float* W, int64_t ldw,
   return tc_gemm_launch(0, transW, M, V, K, X, ldx, W, ldw, epi, (cudaStream_t)stream);
 }
 
+// fp16 operands (X16 [M,K], WT16 [V,K], both K-major): see xent16.cu
+int nm_logits_xent_fwd16(const void* X16, int64_t ldx, const void* WT16, int64_t ldw, const float* b,
+                         int64_t unk_index, const int64_t* targets, const float* weights, float* lse,
+                         float* xent, int64_t* argmax, float* part, float* logits_out, int64_t ldl,
+                         int64_t M, int64_t V, int64_t K, void* stream) {
+  NM_REQUIRE(X16 && WT16 && lse && part, NM_E_INVALID, "nm_logits_xent_fwd16: null pointer");
+  NM_REQUIRE(M > 0 && V > 0 && K > 0 && ldx >= K && ldw >= K, NM_E_INVALID, "nm_logits_xent_fwd16: bad sizes");
+  NM_REQUIRE(!logits_out || ldl >= V, NM_E_INVALID, "nm_logits_xent_fwd16: ldl < V");
+  cudaStream_t s = (cudaStream_t)stream;
+  TcEpilogue epi{};
+  epi.mode = TC_EPI_XENT_FWD;
+  epi.C = logits_out;
+  epi.ldc = ldl;
+  epi.bias = b;
+  epi.unk_index = unk_index;
+  epi.targets = targets;
+  epi.part = reinterpret_cast<float4*>(part);
+  const int rc = tc_gemm16_launch(M, V, K, X16, ldx, WT16, ldw, epi, TcExt{}, s);
+  if (rc) return rc;
+  const int64_t tiles_n = 2 * ceil_div(V, TC_XENT_BN);
+  xent_combine_kernel<<<(unsigned)ceil_div(M, 8), 256, 0, s>>>(reinterpret_cast<const float4*>(part), M,
+                                                              tiles_n, targets, weights, lse, xent, argmax);
+  NM_LAUNCH_CHECK("nm_logits_xent_fwd16(combine)");
+  return NM_OK;
+}
+
 }  // extern "C"

@@ -390,6 +390,89 @@ def bahdanau_attention(keys: torch.Tensor, values: torch.Tensor, mask: Optional[
 # ---------------------------------------------------------------------------
 # K5/K6 vocabulary projection + cross-entropy
 # ---------------------------------------------------------------------------
+def _xent16_enabled() -> bool:
+    """NMB200_XENT16=1: the vocabulary projection with fp16 operands and fp16 dlogits (csrc/xent16.cu).
+    Written and compiled, numerics settled on the CPU (tools/fp16_dlogits_study.py), NOT yet run on a
+    GPU - hence opt-in; tests/test_gpu_xent16.py is its parity test."""
+    import os
+    return os.environ.get("NMB200_XENT16", "") == "1"
+
+
+def _pad8(n: int) -> int:
+    return (n + 7) // 8 * 8
+
+
+class _LogitsXent16(torch.autograd.Function):
+    """The fp16-operand variant of _LogitsXent for W stored [K,V] with the bias right behind it in the
+    gradient buffer (the layout the decoders declare).  Same results within TF32-class rounding."""
+
+    @staticmethod
+    def forward(ctx, x, w, b, targets, weights, unk_index, keep_logits):
+        x2 = x.reshape(-1, x.shape[-1])
+        x2, ldx = _rows(x2)
+        m, k = x2.shape
+        v = w.size(1)
+        dev = x.device
+        kpad = _pad8(k)
+        targets = targets.reshape(-1).contiguous()
+        weights = weights.reshape(-1).contiguous()
+        w2, ldw = _rows(w)
+        x16 = torch.empty(m, kpad, device=dev, dtype=torch.float16)
+        call("nm_cast_f16", ptr(x2), ldx, ptr(x16), kpad, m, k, None, 0, 0, lib.stream())
+        wt16 = torch.empty(v, kpad, device=dev, dtype=torch.float16)
+        call("nm_cast_f16", ptr(w2), ldw, ptr(wt16), kpad, k, v, None, 1, 0, lib.stream())
+        lse = torch.empty(m, device=dev, dtype=torch.float32)
+        xent = torch.empty(m, device=dev, dtype=torch.float32)
+        argmax = torch.empty(m, device=dev, dtype=torch.int64)
+        logits = torch.empty(m, v, device=dev, dtype=torch.float32) if keep_logits else None
+        part = torch.empty(lib.load().nm_logits_xent_scratch(m, v), device=dev, dtype=torch.float32)
+        call("nm_logits_xent_fwd16", ptr(x16), kpad, ptr(wt16), kpad, ptr(b), unk_index, ptr(targets),
+             ptr(weights), ptr(lse), ptr(xent), ptr(argmax), ptr(part), ptr(logits), v, m, v, k,
+             lib.stream())
+        ctx.save_for_backward(x2, w2, b, targets, weights, lse, x16, wt16)
+        ctx.cfg = (unk_index, x.shape)
+        ctx.sinks = (_sink(w), _sink(b) if b is not None else None)
+        ctx.mark_non_differentiable(lse, argmax)
+        if keep_logits:
+            ctx.mark_non_differentiable(logits)
+        return xent, lse, argmax, logits
+
+    @staticmethod
+    def backward(ctx, dxent, _dlse, _dargmax, _dlogits):
+        x2, w2, b, targets, weights, lse, x16, wt16 = ctx.saved_tensors
+        unk_index, in_shape = ctx.cfg
+        m, k = x2.shape
+        v = w2.size(1)
+        dev = x2.device
+        kpad, vpad, mpad = _pad8(k), _pad8(v), _pad8(m)
+        _, ldx = _rows(x2)
+        _, ldw = _rows(w2)
+        # (softmax - onehot) * mask in fp16, row-major and transposed; values in [-1, 1]
+        dl16 = torch.empty(m, vpad, device=dev, dtype=torch.float16)
+        dlt16 = torch.empty(v, mpad, device=dev, dtype=torch.float16)
+        call("nm_logits_xent_bwd16", ptr(x16), kpad, ptr(wt16), kpad, ptr(b), unk_index, ptr(targets),
+             ptr(weights), ptr(lse), ptr(dl16), vpad, ptr(dlt16), mpad, m, v, k, lib.stream())
+        upstream = dxent.reshape(-1).to(torch.float32).contiguous()    # per-row factor, applied in fp32
+        dx = None
+        if ctx.needs_input_grad[0]:
+            w16 = torch.empty(k, vpad, device=dev, dtype=torch.float16)
+            call("nm_cast_f16", ptr(w2), ldw, ptr(w16), vpad, k, v, None, 0, 0, lib.stream())
+            dx = torch.empty(m, k, device=dev, dtype=torch.float32)
+            call("nm_gemm_f16", m, k, v, ptr(dl16), vpad, ptr(w16), vpad, ptr(dx), k, None,
+                 ptr(upstream), 0.0, 0, lib.stream())
+            dx = dx.view(in_shape)
+        w_sink, _b_sink = ctx.sinks
+        # dW^T [V, K+1] = dlT16 . [X * upstream/smax, upstream/smax]^T, times smax, stored transposed
+        # straight into the gradient buffer ([K+1, V]: the weight rows, then the bias row)
+        smax = upstream.abs().amax().clamp_min(1e-30).reshape(1)
+        xt16 = torch.empty(k + 1, mpad, device=dev, dtype=torch.float16)
+        call("nm_cast_f16", ptr(x2), ldx, ptr(xt16), mpad, m, k, ptr(upstream / smax), 1, 1, lib.stream())
+        sink_aug = torch.as_strided(w_sink, (k + 1, v), (v, 1))
+        call("nm_gemm_f16", v, k + 1, m, ptr(dlt16), mpad, ptr(xt16), mpad, ptr(sink_aug), v, ptr(smax),
+             None, 1.0, 1, lib.stream())
+        return dx, None, None, None, None, None, None
+
+
 class _LogitsXent(torch.autograd.Function):
     """xent[m] = (logsumexp(x@W+b) - (x@W+b)[target]) * weights[m]; also lse and argmax."""
 
@@ -493,6 +576,13 @@ def logits_xent(x: torch.Tensor, w: torch.Tensor, b: Optional[torch.Tensor], tar
     """Vocabulary projection + masked cross-entropy (decoders/autoregressive.py:288-316,450-459).
 
     Returns (xent [M], lse [M], argmax [M] int64, logits [M,V] or None)."""
+    if (_xent16_enabled() and not trans_w and b is not None and _GEMM_BACKEND != lib.GEMM_SIMT
+            and w.requires_grad and b.requires_grad):
+        w_sink, b_sink = _sink(w), _sink(b)
+        k, v = w.shape
+        if (w_sink is not None and b_sink is not None and w_sink.is_contiguous()
+                and b_sink.data_ptr() == w_sink.data_ptr() + 4 * k * v):
+            return _LogitsXent16.apply(x, w, b, targets, weights, unk_index, keep_logits)
     return _LogitsXent.apply(x, w, b, targets, weights, unk_index, trans_w, keep_logits)
 
 
