@@ -1,7 +1,7 @@
 """Encoder-decoder attention combination for the Transformer decoder
-(reference: neuralmonkey/attention/transformer_cross_layer.py:10-147): `single`, `serial`
-and `parallel`.  `flat` and `hierarchical` are multi-source strategies outside the hot path
-(one encoder)."""
+(reference: neuralmonkey/attention/transformer_cross_layer.py:10-263): `single`, `serial`,
+`parallel`, and the two further multi-source strategies `flat` and `hierarchical` (compositions of
+`single`; behind NMB200_UNVERIFIED until they have run on a GPU - SURVEY.md 8(f) N4)."""
 from typing import List
 
 import torch
@@ -31,12 +31,17 @@ def single(part, scope: str, queries: torch.Tensor, states: torch.Tensor, mask: 
     return ctx
 
 
-def declare_cross(part, scope: str, strategy: str, dim: int, heads: List[int]) -> None:
+def declare_cross(part, scope: str, strategy: str, dim: int, heads: List[int], heads_hier: int = None) -> None:
     from neuralmonkey_b200.encoders.transformer import declare_layer_norm
-    if strategy == "parallel":
+    if strategy == "flat":          # one attention over the concatenated encoders, in `scope` itself
+        declare_single(part, scope, dim, heads[0], True)
+        return
+    if strategy in ("parallel", "hierarchical"):
         declare_layer_norm(part, scope, dim)
     for i, n_heads in enumerate(heads):
         declare_single(part, "{}/enc_{}".format(scope, i), dim, n_heads, strategy == "serial")
+    if strategy == "hierarchical":
+        declare_single(part, scope + "/enc_hier", dim, heads_hier, False)
 
 
 def serial(part, scope: str, queries, encoder_states, encoder_masks, heads, attention_keep_probs,
@@ -59,3 +64,29 @@ def parallel(part, scope: str, queries, encoder_states, encoder_masks, heads, at
         total = total + single(part, "{}/enc_{}".format(scope, i), normalized, states, mask, n_heads,
                                akp, keep_prob, normalize=False, residual=False)
     return total
+
+
+def flat(part, scope: str, queries, encoder_states, encoder_masks, heads, attention_keep_probs,
+         keep_prob) -> torch.Tensor:
+    """States and masks concatenated along time, one attention over the lot (:228-263)."""
+    return single(part, scope, queries, torch.cat(list(encoder_states), 1), torch.cat(list(encoder_masks), 1),
+                  heads[0], attention_keep_probs[0], keep_prob)
+
+
+def hierarchical(part, scope: str, queries, encoder_states, encoder_masks, heads, heads_hier,
+                 attention_keep_probs, keep_prob) -> torch.Tensor:
+    """Per-encoder contexts of the normalised queries, then a second attention of every query position
+    over its own contexts ([batch*time, n_encoders, dim], all-ones mask, scope enc_hier), dropout,
+    residual (:147-225)."""
+    from neuralmonkey_b200.encoders.transformer import scoped_layer_norm
+    normalized = scoped_layer_norm(part, scope, queries)
+    contexts = [single(part, "{}/enc_{}".format(scope, i), normalized, states, mask, n_heads, akp, keep_prob,
+                       normalize=False, residual=False)
+                for i, (states, mask, n_heads, akp) in enumerate(zip(encoder_states, encoder_masks, heads,
+                                                                     attention_keep_probs))]
+    bsz, steps, dim = queries.shape
+    stacked = torch.stack(contexts, 2).reshape(bsz * steps, len(contexts), dim)
+    ones = torch.ones(bsz * steps, len(contexts), device=queries.device, dtype=torch.float32)
+    ctx = single(part, scope + "/enc_hier", normalized.reshape(bsz * steps, 1, dim), stacked, ones, heads_hier,
+                 keep_prob, 1.0, normalize=False, use_dropout=False, residual=False)
+    return dropout(ctx.reshape(bsz, steps, dim), keep_prob, part.train_mode) + queries

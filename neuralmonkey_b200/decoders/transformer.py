@@ -17,7 +17,9 @@ from neuralmonkey_b200 import ops, runtime
 from neuralmonkey_b200.attention.base_attention import (Attendable, get_attention_mask,
                                                         get_attention_states)
 from neuralmonkey_b200.attention.scaled_dot_product import attention, declare_attention
-from neuralmonkey_b200.attention.transformer_cross_layer import declare_cross, parallel, serial
+from neuralmonkey_b200.attention.transformer_cross_layer import (declare_cross, flat, hierarchical,
+                                                                parallel, serial)
+from neuralmonkey_b200.nn.variants import require_variant
 from neuralmonkey_b200.decoders.autoregressive import (AutoregressiveDecoder, DecoderFeedables,
                                                        LoopState)
 from neuralmonkey_b200.decorators import tensor
@@ -94,9 +96,8 @@ class TransformerDecoder(AutoregressiveDecoder):
             raise ValueError("For the flat attention combination strategy, only a single value is "
                              "permitted in n_heads_enc.")
         if self.attention_combination_strategy in ("flat", "hierarchical"):
-            raise NotImplementedError(
-                "attention_combination_strategy='{}' (multi-source) is outside the B200 hot path; "
-                "use 'serial' or 'parallel'".format(self.attention_combination_strategy))
+            require_variant("attention_combination_strategy='{}'".format(self.attention_combination_strategy))
+            self.use_kv_cache = False      # these strategies decode by re-running the prefix
         self._default_initializer = variance_scaling_initializer(mode="fan_avg", distribution="uniform")
 
     @property
@@ -131,7 +132,7 @@ class TransformerDecoder(AutoregressiveDecoder):
             declare_attention(self, scope + "/self_attention", dim, dim, self.n_heads_self,
                               self.use_att_transform_bias)
             declare_cross(self, scope + "/encdec_attention", self.attention_combination_strategy, dim,
-                          self.n_heads_enc)
+                          self.n_heads_enc, self.n_heads_hier)
             declare_feedforward(self, scope + "/feedforward", dim, self.ff_hidden_size)
         self.declare("LayerNorm/gamma", [dim], ones_initializer())
         self.declare("LayerNorm/beta", [dim], zeros_initializer())
@@ -140,7 +141,12 @@ class TransformerDecoder(AutoregressiveDecoder):
     def _stack(self, inputs: torch.Tensor, mask: torch.Tensor) -> torch.Tensor:
         states = inputs
         enc_states, enc_masks = self.encoder_states(), self.encoder_masks()
-        combine = serial if self.attention_combination_strategy == "serial" else parallel
+        strategy = self.attention_combination_strategy
+        if strategy == "hierarchical":
+            def combine(part, scope, queries, states, masks, heads, akps, keep_prob):
+                return hierarchical(part, scope, queries, states, masks, heads, self.n_heads_hier, akps, keep_prob)
+        else:
+            combine = {"serial": serial, "parallel": parallel, "flat": flat}[strategy]
         for i in range(self.depth):
             scope = "layer_{}".format(i)
             normalized = scoped_layer_norm(self, scope + "/self_attention", states)

@@ -519,8 +519,52 @@ class TransformerDecoderSpec:
         self.max_len, self.tie_embeddings, self.supress_unk = max_len, tie_embeddings, supress_unk
 
 
-def transformer_decoder_stack(p: Params, spec: TransformerDecoderSpec, inputs, mask, enc_states, enc_mask):
-    """TransformerDecoder.layer (decoders/transformer.py:270-387), serial strategy, one encoder."""
+def cross_attention(p: Params, scope: str, queries, enc_states: Sequence[torch.Tensor],
+                    enc_masks: Sequence[torch.Tensor], heads: Sequence[int], strategy: str = "serial",
+                    heads_hier: Optional[int] = None) -> torch.Tensor:
+    """The encoder-attention sublayer of a Transformer decoder layer over one or more encoders
+    (attention/transformer_cross_layer.py:12-263; dropout callbacks = identity).
+        serial        one `single` after the other (own LayerNorm and residual each), scopes enc_<i>
+        parallel      one shared LayerNorm of the queries, sum of the per-encoder contexts + residual
+        flat          states and masks concatenated on the time axis, one `single` in `scope` itself
+        hierarchical  as parallel, but the contexts are attended over (scope enc_hier: queries
+                      [B*T,1,d], keys = values = the stacked contexts [B*T,n,d], all-ones mask)"""
+    def single(sc, q, states, mask, n_heads, normalize=True, residual=True):
+        nq = _scoped_ln(p, sc, q) if normalize else q
+        ctx, _ = multihead_attention(p, sc, nq, states, states, mask, n_heads)
+        return ctx + q if residual else ctx
+
+    if strategy == "serial":
+        x = queries
+        for i, (states, mask, n_heads) in enumerate(zip(enc_states, enc_masks, heads)):
+            x = single("{}/enc_{}".format(scope, i), x, states, mask, n_heads)
+        return x
+    if strategy == "flat":
+        return single(scope, queries, torch.cat(list(enc_states), 1), torch.cat(list(enc_masks), 1), heads[0])
+    normalized = _scoped_ln(p, scope, queries)
+    contexts = [single("{}/enc_{}".format(scope, i), normalized, states, mask, n_heads, False, False)
+                for i, (states, mask, n_heads) in enumerate(zip(enc_states, enc_masks, heads))]
+    if strategy == "parallel":
+        return sum(contexts) + queries
+    if strategy == "hierarchical":
+        bsz, steps, dim = queries.shape
+        stacked = torch.stack(contexts, 2).reshape(bsz * steps, len(contexts), dim)
+        ones = torch.ones(bsz * steps, len(contexts), dtype=queries.dtype)
+        ctx = single(scope + "/enc_hier", normalized.reshape(bsz * steps, 1, dim), stacked, ones, heads_hier,
+                     False, False)
+        return ctx.reshape(bsz, steps, dim) + queries
+    raise ValueError(strategy)
+
+
+def transformer_decoder_stack(p: Params, spec: TransformerDecoderSpec, inputs, mask, enc_states, enc_mask,
+                              strategy: str = "serial", heads_enc: Optional[Sequence[int]] = None,
+                              heads_hier: Optional[int] = None):
+    """TransformerDecoder.layer (decoders/transformer.py:270-387).  `enc_states` / `enc_mask` are one
+    tensor each (one encoder, the serial strategy) or lists (multi-source, any strategy)."""
+    many = isinstance(enc_states, (list, tuple))
+    states = list(enc_states) if many else [enc_states]
+    masks = list(enc_mask) if many else [enc_mask]
+    heads = list(heads_enc) if heads_enc is not None else [spec.heads_enc] * len(states)
     x = inputs
     for i in range(spec.depth):
         scope = "{}/layer_{}".format(spec.prefix, i)
@@ -528,10 +572,7 @@ def transformer_decoder_stack(p: Params, spec: TransformerDecoderSpec, inputs, m
         ctx, _ = multihead_attention(p, scope + "/self_attention", normalized, normalized, normalized,
                                      mask, spec.heads_self, masked=True)
         x = ctx + x
-        cross = scope + "/encdec_attention/enc_0"
-        normalized = _scoped_ln(p, cross, x)
-        ctx, _ = multihead_attention(p, cross, normalized, enc_states, enc_states, enc_mask, spec.heads_enc)
-        x = ctx + x
+        x = cross_attention(p, scope + "/encdec_attention", x, states, masks, heads, strategy, heads_hier)
         x = transformer_feedforward(p, scope + "/feedforward", x)
     return _scoped_ln(p, spec.prefix, x)
 

@@ -646,6 +646,36 @@ def main():
     recurrent_case("nematus", [5], [(4, "bidirectional", "NematusGRU"), (3, "forward", "NematusGRU")],
                    False, False, True, False)
 
+    # ---- multi-source Transformer decoder layers: the four encoder-attention combination strategies
+    #      (attention/transformer_cross_layer.py:12-263) over two encoders; the variables are drawn on demand
+    #      and recorded, so the names are the reference's -----------------------------------------------------------
+    enc_a, mask_a = f32(3, 5, dim), np.array([[1, 1, 1, 1, 1], [1, 1, 1, 0, 0], [1, 0, 0, 0, 0]], np.float32)
+    enc_b, mask_b = f32(3, 4, dim), np.array([[1, 1, 0, 0], [1, 1, 1, 1], [1, 1, 1, 0]], np.float32)
+    ms_in = f32(3, 6, dim)
+    ms_mask = np.array([[1, 1, 1, 1, 1, 1], [1, 1, 1, 1, 0, 0], [1, 1, 0, 0, 0, 0]], np.float32)
+    out.update({"ms_enc_a": enc_a, "ms_mask_a": mask_a, "ms_enc_b": enc_b, "ms_mask_b": mask_b, "ms_in": ms_in,
+                "ms_mask": ms_mask})
+    shim.AUTO[0] = np.random.RandomState(23)
+    for strategy in ("serial", "parallel", "flat", "hierarchical"):
+        name = "tms_" + strategy
+        first = len(shim.VARIABLES)
+        ms = object.__new__(TransformerDecoder)
+        ms.__dict__.update(dict(
+            encoders=[None, None], ff_hidden_size=ff, n_heads_self=heads, depth=2,
+            n_heads_enc=[3, 3] if strategy == "flat" else [3, 2], attention_dropout_keep_prob=[1.0, 1.0],
+            self_att_dropout_keep_prob=1.0, dropout_keep_prob=1.0, use_att_transform_bias=False,
+            attention_combination_strategy=strategy, n_heads_hier=4 if strategy == "hierarchical" else None,
+            encoder_states=lambda: [shim.t(enc_a), shim.t(enc_b)],
+            encoder_masks=lambda: [shim.t(mask_a), shim.t(mask_b)],
+            _embedding_size=dim, embeddings_source=None, train_mode=None,
+            _variable_scope=shim.VarScope(name), _reuse=None, _name=name))
+        with ms.use_scope():
+            last = ms.layer(2, shim.t(ms_in), shim.t(ms_mask))
+        out[name + "_states"] = np.asarray(last.temporal_states)
+        for vname in list(shim.VARIABLES)[first:]:
+            out["mv::" + vname] = shim.VARIABLES[vname]
+    shim.AUTO[0] = None
+
     # ---- the trainer's host logic: GenericTrainer.regularization_losses / differentiable_loss_sum /
     #      gradients (per-tensor clip_by_norm) / collect_results (trainers/generic_trainer.py:84-195,27-50),
     #      around an optimizer stand-in that hands back given gradients -------------------------------------------

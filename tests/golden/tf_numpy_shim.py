@@ -136,10 +136,21 @@ def _full_name(name):
     return "/".join([s for s in _scope if s] + [name])
 
 
+AUTO = [None]       # a numpy RandomState: variables nobody provided are then drawn on demand and recorded
+
+
+def _auto(full, shape, ones=False):
+    if AUTO[0] is None:
+        raise KeyError("variable '{}' was not provided to the shim".format(full))
+    value = np.asarray(AUTO[0].randn(*[int(d) for d in shape]) * 0.3, np.float32)
+    VARIABLES[full] = value + 1.0 if ones else value
+    return VARIABLES[full]
+
+
 def _get_variable(name, shape=None, dtype=None, initializer=None, **kwargs):
     full = _full_name(name)
     if full not in VARIABLES:
-        raise KeyError("variable '{}' was not provided to the shim".format(full))
+        _auto(full, shape, ones=name == "gamma")
     return t(VARIABLES[full], np.float32)
 
 
@@ -150,10 +161,12 @@ def _dense(inputs, units, activation=None, use_bias=True, name=None, **kwargs):
     if full + "/kernel" in VARIABLES:
         kernel, bias = VARIABLES[full + "/kernel"], VARIABLES.get(full + "/bias")
         USED.append(full + "/kernel")
-    elif name in DENSE:
+    elif name in DENSE and AUTO[0] is None:
         kernel, bias = DENSE[name]
     else:
-        raise KeyError("dense layer '{}' was not provided to the shim".format(full))
+        kernel = _auto(full + "/kernel", (np.shape(inputs)[-1], units))
+        bias = _auto(full + "/bias", (units,)) if use_bias else None
+        USED.append(full + "/kernel")
     assert kernel.shape[1] == units
     out = np.asarray(inputs) @ kernel
     if use_bias and bias is not None:
@@ -422,6 +435,7 @@ def install():
     tf.reverse_sequence = _reverse_sequence
     tf.not_equal = lambda a, b: t(np.not_equal(a, b))
     tf.while_loop = _while_loop
+    tf.ones = lambda shape, dtype=None, name=None: t(np.ones([int(d) for d in shape], dtype or np.float32))
     tf.sigmoid = lambda x: t(1.0 / (1.0 + np.exp(-np.asarray(x, np.float32))), np.float32)
     tf.split = lambda value, num_or_size_splits, axis=0: [t(p) for p in np.split(np.asarray(value), num_or_size_splits, axis=axis)]
     tf.trainable_variables = lambda: list(TRAINABLE)

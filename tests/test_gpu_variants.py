@@ -15,7 +15,7 @@ import torch
 
 from oracle import nm_oracle as O
 from tests.helpers import feed, max_abs, oracle_params_for, random_batch
-from tests.test_host_model_cpu import _build_variant
+from tests.test_host_model_cpu import _build_variant, check_multi_source
 
 pytestmark = [pytest.mark.gpu,
               pytest.mark.skipif(os.environ.get("NMB200_UNVERIFIED") != "1",
@@ -65,5 +65,19 @@ def test_variants_against_oracle(cell, conditional, out_proj, enc_proj, enc_cell
             assert bool((dec.runtime_symbols.cpu() == og["output_symbols"]).all())
         out = model["trainer"].train_step()          # one optimizer step through the arena
         assert float(out["losses"][0]) > 0.0
+    finally:
+        ops.set_gemm_backend("auto")
+
+
+@pytest.mark.parametrize("backend,tol,gtol", [("simt", 1e-4, 1e-3), ("auto", 3e-2, 2e-2)])
+@pytest.mark.parametrize("strategy", ["serial", "parallel", "flat", "hierarchical"])
+def test_multi_source_transformer_decoder(strategy, backend, tol, gtol):
+    from neuralmonkey_b200 import ops
+    try:
+        ops.set_gemm_backend(backend)
+
+        def grads_of(model):
+            return model["arena"].named_grads()
+        check_multi_source(strategy, grads_of, tol, gtol)
     finally:
         ops.set_gemm_backend("auto")

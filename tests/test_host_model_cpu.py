@@ -354,3 +354,102 @@ def test_captioning_model_with_the_frozen_vgg_encoder(cpu_model, monkeypatch):
     after = arena.state_dict()
     assert all(torch.equal(before[n], after[n]) for n in before if n.startswith("vgg_16"))
     assert not torch.equal(before["decoder/state_to_word_W"], after["decoder/state_to_word_W"])
+
+
+@pytest.mark.parametrize("strategy", ["serial", "parallel", "flat", "hierarchical"])
+def test_multi_source_transformer_decoder(cpu_model, strategy):
+    """Two Transformer encoders under one decoder with each attention_combination_strategy: training
+    pass, gradients and greedy decoding against the oracle (whose four strategies are pinned to the
+    reference's own code)."""
+    check_multi_source(strategy, _grads, 5e-5, 1e-3)
+
+
+def check_multi_source(strategy, grads_of, tol, gtol):
+    from neuralmonkey_b200 import runtime, tf
+    from neuralmonkey_b200.decoders import TransformerDecoder
+    from neuralmonkey_b200.encoders import TransformerEncoder
+    from neuralmonkey_b200.model.sequence import EmbeddedSequence
+    from neuralmonkey_b200.trainers import CrossEntropyTrainer
+    from neuralmonkey_b200.vocabulary import Vocabulary
+    runtime.reset()
+    dim, ff, depth, heads = 24, 40, 2, 4
+    vocabs = [Vocabulary(["a{}".format(i) for i in range(26)]), Vocabulary(["b{}".format(i) for i in range(20)])]
+    tgt_vocab = Vocabulary(["t{}".format(i) for i in range(36)])
+    seqs = [EmbeddedSequence(name="input_{}".format(i), vocabulary=v, data_id="source_{}".format(i),
+                             embedding_size=dim, max_length=9, scale_embeddings_by_depth=True)
+            for i, v in enumerate(vocabs)]
+    encs = [TransformerEncoder(name="encoder_{}".format(i), input_sequence=s, ff_hidden_size=ff, depth=depth,
+                               n_heads=heads) for i, s in enumerate(seqs)]
+    heads_enc = 4 if strategy == "flat" else [4, 2]
+    dec = TransformerDecoder(name="decoder", encoders=encs, vocabulary=tgt_vocab, data_id="target",
+                             ff_hidden_size=ff, n_heads_self=heads, n_heads_enc=heads_enc, depth=depth,
+                             max_output_len=8, embedding_size=dim, tie_embeddings=True,
+                             attention_combination_strategy=strategy,
+                             n_heads_hier=3 if strategy == "hierarchical" else None)
+    trainer = CrossEntropyTrainer(decoders=[dec], optimizer=tf.AdamOptimizer(learning_rate=1e-3))
+    for part in trainer.parameterizeds:
+        part.ensure_declared()
+    runtime.arena().finalize(runtime.device())
+    model = {"arena": runtime.arena()}
+    params = oracle_params_for(model, scale=0.2)
+    for name in params:
+        if name.endswith("gamma"):
+            params[name] = 1.0 + params[name]
+    model["arena"].load_dict(params)
+    src_a, tgt = random_batch(4, 7, 6, 30, 40, seed=5)
+    src_b, _ = random_batch(4, 5, 6, 24, 40, seed=6)
+
+    def feed_all(train, targets):
+        for seq, enc, src in zip(seqs, encs, (src_a, src_b)):
+            seq.feed_ids([src], train=train)
+            enc.reset_batch()
+            enc.train_mode, enc.batch_size = train, 4
+        dec.feed_ids(targets, 4, train=train)
+
+    def oracle_encoders(pp):
+        outs = []
+        for i, src in enumerate((src_a, src_b)):
+            emb = pp["input_{}/embedding_matrix_0".format(i)]
+            mask = (src != 0).to(emb.dtype)
+            outs.append(O.transformer_encoder(pp, "encoder_{}".format(i), emb[src] * (mask * dim ** 0.5).unsqueeze(-1),
+                                              mask, depth, heads))
+        return [o["states"] for o in outs], [o["mask"] for o in outs]
+
+    spec = O.TransformerDecoderSpec("decoder", depth, heads, heads, 8, True, False)
+    kw = dict(strategy=strategy, heads_enc=[4, 4] if strategy == "flat" else [4, 2],
+              heads_hier=3 if strategy == "hierarchical" else None)
+    feed_all(True, tgt)
+    p = {n: v.clone().requires_grad_(True) for n, v in params.items()}
+    states, masks = oracle_encoders(p)
+    emb = p["decoder/word_embeddings"]
+    go = torch.full((4, 1), O.START, dtype=torch.int64)
+    want = O.transformer_decoder_stack(p, spec, emb[torch.cat([go, tgt[:, :-1]], 1)], (tgt != 0).to(emb.dtype),
+                                       states, masks, **kw)
+    assert max_abs(dec.train_output_states.transpose(0, 1), want) < tol
+    logp = torch.log_softmax(O.transformer_logits(p, spec, want), -1)
+    tmask = (tgt != 0).to(emb.dtype)
+    want_loss = (-(logp.gather(2, tgt.unsqueeze(2)).squeeze(2)) * tmask).sum() / tmask.sum()
+    assert abs(float(dec.train_loss) - float(want_loss)) < max(1e-4, tol)
+    dec.train_loss.backward()
+    want_loss.backward()
+    for name, grad in grads_of(model).items():
+        ref = p[name].grad if p[name].grad is not None else torch.zeros_like(p[name])
+        got = grad.cpu() if grad is not None else torch.zeros_like(p[name])
+        assert float((got - ref.reshape(got.shape)).norm()) <= gtol * float(ref.norm()) + 1e-6, name
+    if tol > 1e-3:
+        return                      # tensor-core engines: near-ties may flip an argmax
+    # greedy decoding: the product re-runs the prefix (or uses its KV cache for serial / parallel)
+    feed_all(False, tgt)
+    states, masks = oracle_encoders(params)
+    seq = torch.zeros(4, 0, dim)
+    mask_seq = torch.zeros(4, 0)
+    finished = torch.zeros(4, dtype=torch.bool)
+    symbols = torch.full((4,), O.START, dtype=torch.int64)
+    table = params["decoder/word_embeddings"]
+    for step in range(dec.runtime_symbols.shape[0]):
+        seq = torch.cat([seq, table[symbols].unsqueeze(1)], 1)
+        mask_seq = torch.cat([mask_seq, (~finished).float().unsqueeze(1)], 1)
+        out = O.transformer_decoder_stack(params, spec, seq, mask_seq, states, masks, **kw)[:, -1]
+        symbols = O.transformer_logits(params, spec, out).argmax(-1) * (~finished).long()
+        finished = finished | (symbols == O.END)
+        assert bool((dec.runtime_symbols[step].cpu() == symbols).all()), step

@@ -528,3 +528,25 @@ def test_attention_on_input_cannot_be_built_in_the_reference():
     contexts live in `feedables.other`, so attention_on_input=True raises while the graph is built.
     The product therefore rejects the option instead of guessing a behaviour."""
     assert "prev_contexts" in str(G["attention_on_input_error"])
+
+
+@pytest.mark.parametrize("strategy", ["serial", "parallel", "flat", "hierarchical"])
+def test_multi_source_cross_attention_strategies(strategy):
+    """TransformerDecoder.layer over TWO encoders with each attention_combination_strategy
+    (attention/transformer_cross_layer.py:12-263): scopes enc_<i> / enc_hier, where the LayerNorms sit,
+    what the residual adds, the time-axis concatenation of `flat`, the [B*T, n, d] second attention of
+    `hierarchical`.  The variables were drawn when the reference asked for them, so their names are the
+    reference's."""
+    name = "tms_" + strategy
+    p = {k[4:]: _t(k) for k in G.files if k.startswith("mv::" + name + "/")}
+    spec = O.TransformerDecoderSpec(name, 2, 3, 3, 9)
+    states = O.transformer_decoder_stack(
+        p, spec, _t("ms_in"), _t("ms_mask"), [_t("ms_enc_a"), _t("ms_enc_b")], [_t("ms_mask_a"), _t("ms_mask_b")],
+        strategy=strategy, heads_enc=[3, 3] if strategy == "flat" else [3, 2],
+        heads_hier=4 if strategy == "hierarchical" else None)
+    assert np.abs(states.numpy() - G[name + "_states"]).max() < 3e-5
+    scopes = {k.split("/encdec_attention/")[1].split("/")[0] for k in p
+              if "/layer_0/encdec_attention/" in k and k.endswith("/kernel")}
+    assert scopes == {"serial": {"enc_0", "enc_1"}, "parallel": {"enc_0", "enc_1"},
+                      "flat": {"keys_proj", "output_proj", "query_proj", "vals_proj"},
+                      "hierarchical": {"enc_0", "enc_1", "enc_hier"}}[strategy]
