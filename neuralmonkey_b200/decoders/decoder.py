@@ -31,7 +31,7 @@ from neuralmonkey_b200.model.parameterized import InitializerSpecs
 from neuralmonkey_b200.model.sequence import EmbeddedSequence
 from neuralmonkey_b200.model.stateful import Stateful
 from neuralmonkey_b200.nn.utils import dropout, dropout_mask
-from neuralmonkey_b200.nn.variants import NematusGRUCell, require_variant
+from neuralmonkey_b200.nn.variants import LSTMCell, NematusGRUCell, require_variant
 from neuralmonkey_b200.vocabulary import Vocabulary
 
 RNN_CELL_TYPES = ("NematusGRU", "GRU", "LSTM")
@@ -81,9 +81,6 @@ class Decoder(AutoregressiveDecoder):
             # `feedables.other`) - tests/test_oracle_vs_reference_code.py records the AttributeError
             raise NotImplementedError("attention_on_input=True fails in the reference while the graph is "
                                       "built (decoders/decoder.py:273); it is not supported here either")
-        if self._rnn_cell_str == "LSTM":
-            raise NotImplementedError("rnn_cell='LSTM' is outside the B200 hot path built so far "
-                                      "(SURVEY.md 8(f) N4)")
         self._stepwise = self._rnn_cell_str != "GRU" or conditional_gru
         if self._stepwise:
             require_variant("Decoder with rnn_cell='{}', conditional_gru={}".format(rnn_cell, conditional_gru))
@@ -148,6 +145,10 @@ class Decoder(AutoregressiveDecoder):
             self.__dict__["_nematus_cells_cache"] = (first, cond)
         return self.__dict__["_nematus_cells_cache"]
 
+    @property
+    def _lstm_cell(self) -> LSTMCell:
+        return LSTMCell(self, "attention_decoder/lstm_cell", self.embedding_size, self.rnn_size)
+
     _CELL_SCOPE = "attention_decoder/OrthoGRUCell"
     _COND_SCOPE = "attention_decoder/cond_gru_2_cell"      # the scope decoder.py:324 passes
 
@@ -159,7 +160,9 @@ class Decoder(AutoregressiveDecoder):
                              .format(self.output_dimension, self.embedding_size))
         self.encoder_projection.declare(self, self.rnn_size, self.encoders)
         ctx_size = sum(a.context_vector_size for a in self.attentions)
-        if self._rnn_cell_str == "NematusGRU":
+        if self._rnn_cell_str == "LSTM":
+            self._lstm_cell.declare()
+        elif self._rnn_cell_str == "NematusGRU":
             for cell in self._nematus_cells:
                 if cell is not None:
                     cell.declare()
@@ -188,14 +191,19 @@ class Decoder(AutoregressiveDecoder):
         `attend(att, query)` runs one attention.  Order as in the reference: first cell -> attention
         queried with its RAW output -> (conditional cell over the raw contexts, state = first cell's
         output) -> dropout on contexts and on the cell output -> deep output."""
-        if self._rnn_cell_str == "NematusGRU":
+        next_c = None
+        if self._rnn_cell_str == "LSTM":
+            # the LSTM branch (decoder.py:326-339): the loop carries (prev_rnn_state = c, prev_rnn_output = h);
+            # `prev_output` is that pair here.  The conditional cell belongs to the GRU branch only.
+            next_c, cell_output = self._lstm_cell(rnn_input, prev_output[0], prev_output[1])
+        elif self._rnn_cell_str == "NematusGRU":
             cell_output = self._nematus_cells[0](rnn_input, prev_output)
         else:
             cell_output = ops.gru_layer(rnn_input.unsqueeze(1), *gru_cell_tensors(self, self._CELL_SCOPE),
                                         h0=prev_output)[2][:, 0]
         attended = [attend(att, cell_output) for att in self.attentions]
         contexts = [a[0] for a in attended]
-        if self._conditional_gru:
+        if self._conditional_gru and next_c is None:
             cond_input = contexts[0] if len(contexts) == 1 else torch.cat(contexts, -1)
             if self._rnn_cell_str == "NematusGRU":
                 cell_output = self._nematus_cells[1](cond_input, cell_output)
@@ -205,12 +213,14 @@ class Decoder(AutoregressiveDecoder):
         contexts = [dropout(ctx, self.dropout_keep_prob, self.train_mode) for ctx in contexts]
         cell_output = dropout(cell_output, self.dropout_keep_prob, self.train_mode)
         output = self.output_projection(self, cell_output, rnn_input, contexts, self.train_mode)
-        return output, cell_output, contexts, attended
+        return output, (cell_output if next_c is None else (next_c, cell_output)), contexts, attended
 
     def _train_pass_stepwise(self):
         fed = self._train_step_inputs_bm
         emb = self.embed_input_symbols(fed)                # [B,T,E]
         prev = self.initial_state
+        if self._rnn_cell_str == "LSTM":
+            prev = (prev, prev)
         outputs, cells, weights = [], [], [[] for _ in self.attentions]
 
         def attend(att, query):
@@ -220,7 +230,7 @@ class Decoder(AutoregressiveDecoder):
         for t in range(fed.shape[1]):
             out, prev, _ctx, attended = self._variant_step(emb[:, t], prev, attend)
             outputs.append(out)
-            cells.append(prev)
+            cells.append(prev[1] if isinstance(prev, tuple) else prev)
             for hist, (_c, w) in zip(weights, attended):
                 hist.append(w)
         for att, hist in zip(self.attentions, weights):
@@ -282,12 +292,16 @@ class Decoder(AutoregressiveDecoder):
         rnn_input = loop_state.feedables.embedded_input
         if self._stepwise:
             states = iter(rnn_histories.attention_histories)
-            output, cell_output, contexts, attended = self._variant_step(
-                rnn_input, rnn_feedables.prev_rnn_output,
+            prev = rnn_feedables.prev_rnn_output
+            if self._rnn_cell_str == "LSTM":
+                prev = (rnn_feedables.prev_rnn_state, rnn_feedables.prev_rnn_output)
+            output, carried, contexts, attended = self._variant_step(
+                rnn_input, prev,
                 lambda att, query: att.attention(query, rnn_feedables.prev_rnn_output, rnn_input, next(states)))
+            next_state, cell_output = carried if isinstance(carried, tuple) else (carried, carried)
             rnn_histories.rnn_outputs.append(cell_output)
             return (output,
-                    RNNFeedables(prev_rnn_state=cell_output, prev_rnn_output=cell_output,
+                    RNNFeedables(prev_rnn_state=next_state, prev_rnn_output=cell_output,
                                  prev_contexts=list(contexts)),
                     RNNHistories(rnn_outputs=rnn_histories.rnn_outputs,
                                  attention_histories=[a[1] for a in attended]))

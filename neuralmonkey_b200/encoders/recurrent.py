@@ -3,8 +3,8 @@
 `rnn_layer` runs a (bi)directional length-masked GRU over the whole sequence: the input
 half of both GRUCell matmuls is one tensor-core GEMM over all B*T rows, the recurrence
 is the K2 sequence kernel (`ops.gru_layer`).  The GRU cell is the one the five target configs use;
-"NematusGRU" (tests/small.ini, tests/nematus.ini) steps through time with `nn.variants.NematusGRUCell`
-behind the NMB200_UNVERIFIED switch; "LSTM" raises.
+"NematusGRU" and "LSTM" (tests/small.ini, tests/nematus.ini) step through time with the cells of
+`nn/variants.py` behind the NMB200_UNVERIFIED switch.
 """
 from typing import List, NamedTuple, Tuple, Union
 
@@ -17,7 +17,7 @@ from neuralmonkey_b200.model.parameterized import InitializerSpecs
 from neuralmonkey_b200.model.sequence import EmbeddedFactorSequence, EmbeddedSequence
 from neuralmonkey_b200.model.stateful import TemporalStateful, TemporalStatefulWithOutput
 from neuralmonkey_b200.nn.utils import dropout
-from neuralmonkey_b200.nn.variants import NematusGRUCell, require_variant
+from neuralmonkey_b200.nn.variants import LSTMCell, NematusGRUCell, require_variant
 from neuralmonkey_b200.params import (constant_initializer, ones_initializer,
                                       orthogonal_initializer, zeros_initializer)
 from neuralmonkey_b200.vocabulary import Vocabulary
@@ -77,22 +77,22 @@ class RecurrentEncoder(ModelPart, TemporalStatefulWithOutput):
             raise ValueError("When using residual connectiong, all layers must have the same "
                              "size, but are {}.".format(layer_sizes))
         for spec in self.rnn_specs:
-            if spec.cell_type == "NematusGRU":
-                require_variant("RecurrentEncoder with rnn_cell='NematusGRU'")
-            elif spec.cell_type != "GRU":
-                raise NotImplementedError(
-                    "RNN cell '{}' is outside the B200 hot path built so far (GRU, NematusGRU)"
-                    .format(spec.cell_type))
+            if spec.cell_type != "GRU":
+                require_variant("RecurrentEncoder with rnn_cell='{}'".format(spec.cell_type))
         self._layer_sizes = layer_sizes
 
     def _cell_scopes(self, i: int, spec: RNNSpec) -> List[str]:
         base = "rnn_{}_{}".format(i, spec.direction)
         # OrthoGRUCell passes its scope itself (nn/ortho_gru_cell.py:51); NematusGRUCell gets
         # TensorFlow's default layer name, the snake-cased class name
-        cell = "nematus_gru_cell" if spec.cell_type == "NematusGRU" else "OrthoGRUCell"
+        cell = {"NematusGRU": "nematus_gru_cell", "LSTM": "lstm_cell", "GRU": "OrthoGRUCell"}[spec.cell_type]
         if spec.direction == "bidirectional":
             return [base + "/bidirectional_rnn/fw/" + cell, base + "/bidirectional_rnn/bw/" + cell]
         return [base + "/rnn/" + cell]
+
+    def _variant_cell(self, spec: RNNSpec, scope: str, in_dim: int):
+        cls = NematusGRUCell if spec.cell_type == "NematusGRU" else LSTMCell
+        return cls(self, scope, in_dim, spec.size)
 
     def declare_variables(self) -> None:
         if hasattr(self.input_sequence, "ensure_declared"):
@@ -100,8 +100,8 @@ class RecurrentEncoder(ModelPart, TemporalStatefulWithOutput):
         in_dim = self.input_sequence.dimension
         for i, spec in enumerate(self.rnn_specs):
             for scope in self._cell_scopes(i, spec):
-                if spec.cell_type == "NematusGRU":
-                    NematusGRUCell(self, scope, in_dim, spec.size).declare()
+                if spec.cell_type != "GRU":
+                    self._variant_cell(spec, scope, in_dim).declare()
                 else:
                     gru_cell_variables(self, scope, in_dim, spec.size)
             if self.add_layer_norm:
@@ -127,9 +127,9 @@ class RecurrentEncoder(ModelPart, TemporalStatefulWithOutput):
                    lengths: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
         """rnn_layer (recurrent.py:71-110)."""
         scopes = self._cell_scopes(i, spec)
-        if spec.cell_type == "NematusGRU":
+        if spec.cell_type != "GRU":
             in_dim = layer_input.shape[-1]
-            runs = [NematusGRUCell(self, scope, in_dim, spec.size).sequence(layer_input, lengths, reverse)
+            runs = [self._variant_cell(spec, scope, in_dim).sequence(layer_input, lengths, reverse)
                     for scope, reverse in zip(scopes, {"bidirectional": (False, True), "forward": (False,),
                                                        "backward": (True,)}[spec.direction])]
             return torch.cat([r[0] for r in runs], 2), torch.cat([r[1] for r in runs], 1)

@@ -4,6 +4,10 @@ served by the same corpus-BLEU on the already tokenised series; ROUGE-L is the L
 from typing import List
 
 from neuralmonkey_b200.evaluators.bleu import BLEU, BLEU1, BLEU2, BLEU4, BLEUEvaluator
+from neuralmonkey_b200.evaluators.metrics import (AverageEvaluator, ChrFEvaluator, EditDistanceEvaluator,
+                                                  MeanSquaredErrorEvaluator,
+                                                  PairwiseMeanSquaredErrorEvaluator, TEREvaluator,
+                                                  WEREvaluator)
 
 
 class AccuracyEvaluator:
@@ -70,3 +74,9 @@ class RougeLEvaluator:
 Accuracy = AccuracyEvaluator()
 ROUGE_L = RougeLEvaluator()
 SacreBLEU = BLEUEvaluator(n=4, name="SacreBLEU")
+ChrF3 = ChrFEvaluator(beta=3)
+EditDistance = EditDistanceEvaluator("Edit distance")
+WER = WEREvaluator("WER")
+TER = TEREvaluator("TER")
+MSE = MeanSquaredErrorEvaluator("MeanSquaredError")
+PairwiseMSE = PairwiseMeanSquaredErrorEvaluator("PairwiseMeanSquaredError")

@@ -80,3 +80,35 @@ class NematusGRUCell:
             outputs[t] = new * live
             state = new * live + state * (1.0 - live)
         return torch.stack(outputs, 1), state
+
+
+class LSTMCell:
+    """tf.nn.rnn_cell.LSTMCell with its defaults (what RNN_CELL_TYPES["LSTM"] builds: no peepholes, no
+    projection, forget_bias = 1): [i, j, f, o] = [x, h] . kernel + bias; c' = sigmoid(f + 1) * c +
+    sigmoid(i) * tanh(j); h' = sigmoid(o) * tanh(c')."""
+
+    def __init__(self, part, scope: str, input_size: int, size: int) -> None:
+        self.part, self.scope, self.input_size, self.size = part, scope, input_size, size
+
+    def declare(self) -> None:
+        self.part.declare(self.scope + "/kernel", [self.input_size + self.size, 4 * self.size])
+        self.part.declare(self.scope + "/bias", [4 * self.size], zeros_initializer())
+
+    def __call__(self, x: torch.Tensor, c: torch.Tensor, h: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+        z = ops.linear(torch.cat([x, h], 1), self.part.var(self.scope + "/kernel"), self.part.var(self.scope + "/bias"))
+        i, j, f, o = z.chunk(4, dim=1)
+        new_c = torch.sigmoid(f + 1.0) * c + torch.sigmoid(i) * torch.tanh(j)
+        return new_c, torch.sigmoid(o) * torch.tanh(new_c)
+
+    def sequence(self, x: torch.Tensor, lengths: torch.Tensor, reverse: bool) -> Tuple[torch.Tensor, torch.Tensor]:
+        """dynamic_rnn semantics as NematusGRUCell.sequence; the final state handed on is h
+        (encoders/recurrent.py:91-93,106-107)."""
+        bsz, steps, _ = x.shape
+        c = h = torch.zeros(bsz, self.size, device=x.device, dtype=torch.float32)
+        outputs = [None] * steps
+        for t in (range(steps - 1, -1, -1) if reverse else range(steps)):
+            live = (lengths > t).to(torch.float32).unsqueeze(1)
+            new_c, new_h = self(x[:, t], c, h)
+            outputs[t] = new_h * live
+            c, h = new_c * live + c * (1.0 - live), new_h * live + h * (1.0 - live)
+        return torch.stack(outputs, 1), h

@@ -83,6 +83,15 @@ def nematus_gru_cell(p: Params, scope: str, x: torch.Tensor, h: torch.Tensor) ->
     return u * h + (1 - u) * c
 
 
+def lstm_cell(p: Params, scope: str, x: torch.Tensor, c: torch.Tensor, h: torch.Tensor):
+    """tf.nn.rnn_cell.LSTMCell with its defaults (no peepholes, forget_bias = 1): gate order i, j, f, o
+    in one [in + H, 4H] kernel; returns (c', h')."""
+    z = torch.cat([x, h], 1) @ p[scope + "kernel"] + p[scope + "bias"]
+    i, j, f, o = z.chunk(4, dim=1)
+    new_c = torch.sigmoid(f + 1.0) * c + torch.sigmoid(i) * torch.tanh(j)
+    return new_c, torch.sigmoid(o) * torch.tanh(new_c)
+
+
 def dynamic_rnn(cell: Callable, size: int, x: torch.Tensor, lengths: Optional[torch.Tensor],
                 h0: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor]:
     """tf.nn.dynamic_rnn(cell, x, sequence_length=lengths) for a cell `h' = cell(x_t, h)` whose output
@@ -162,6 +171,16 @@ def rnn_layer(p: Params, scope: str, x: torch.Tensor, lengths: torch.Tensor, dir
     the reference passes, nn/ortho_gru_cell.py:51) or nematus_gru_cell (TensorFlow's default name for
     the layer class; `size` is needed for that cell only)."""
     def run(cell_scope, inputs):
+        if cell_type == "LSTM":      # state (c, h), both carried past the length; the layer's final state is h
+            cell_scope += "lstm_cell/"
+            c = h = inputs.new_zeros(inputs.shape[0], size)
+            outs = []
+            for t in range(inputs.shape[1]):
+                new_c, new_h = lstm_cell(p, cell_scope, inputs[:, t], c, h)
+                live = (t < lengths).to(inputs.dtype).unsqueeze(1)
+                outs.append(new_h * live)
+                c, h = new_c * live + c * (1 - live), new_h * live + h * (1 - live)
+            return torch.stack(outs, 1), h
         if cell_type == "NematusGRU":
             cell_scope += "nematus_gru_cell/"
             return dynamic_rnn(lambda xt, h: nematus_gru_cell(p, cell_scope, xt, h), size, inputs, lengths)
@@ -327,6 +346,15 @@ def decoder_step(p: Params, spec: RNNDecoderSpec, embedded_input, prev_output, h
     what the projection, the history and the next step see - the attention was queried with the first
     cell's output (:303-325)."""
     step = spec.prefix + "/attention_decoder/"
+    if spec.rnn_cell == "LSTM":
+        # the LSTM branch (:326-339): the loop carries (prev_rnn_state = c, prev_rnn_output = h), both
+        # initialised with the initial state; `prev_output` is that pair here, and so is the second
+        # return value.  No conditional cell in this branch.
+        prev_c, prev_h = prev_output if isinstance(prev_output, tuple) else (prev_output, prev_output)
+        new_c, cell_output = lstm_cell(p, step + "lstm_cell/", embedded_input, prev_c, prev_h)
+        context, weights = bahdanau_step(p, spec.att_prefix, cell_output, hidden, states, mask)
+        output = output_projection(p, spec, cell_output, embedded_input, context)
+        return output, (new_c, cell_output), context, weights
     first = step + ("nematus_gru_cell/" if spec.rnn_cell == "NematusGRU" else "OrthoGRUCell/")
     cell_output = _decoder_cell(p, spec, first, embedded_input, prev_output)
     context, weights = bahdanau_step(p, spec.att_prefix, cell_output, hidden, states, mask)
@@ -380,7 +408,7 @@ def decoder_train(p: Params, spec: RNNDecoderSpec, enc: Dict[str, torch.Tensor],
 
     def next_output(embedded, _finished):
         output, rnn["prev"], _ctx, w = decoder_step(p, spec, embedded, rnn["prev"], hidden, states, mask)
-        return output, (w, rnn["prev"])
+        return output, (w, rnn["prev"][1] if isinstance(rnn["prev"], tuple) else rnn["prev"])
 
     hist = autoregressive_loop(next_output, lambda o: state_to_logits(p, spec, o), lambda ids: emb[ids], bsz,
                                spec.max_output_len, train_inputs)

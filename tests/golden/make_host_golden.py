@@ -130,6 +130,22 @@ def main():
             ev = BLEUEvaluator(n=n, deduplicate=dedup)
             out["bleu_{}_{}".format(n, int(dedup))] = float(ev(HYPS, REFS))
     out["bleu_identity"] = float(BLEUEvaluator()(REFS, REFS))
+    # ---- further evaluators (chrf.py, edit_distance.py, mse.py, average.py; wer.py and ter.py need the
+    #      third-party pyter and are not run) ------------------------------------------------------------
+    from neuralmonkey.evaluators.chrf import ChrF3, ChrFEvaluator
+    from neuralmonkey.evaluators.edit_distance import EditDistance
+    from neuralmonkey.evaluators.mse import MSE, PairwiseMSE
+    from neuralmonkey.evaluators.average import AverageEvaluator
+    out["more_evaluators"] = {
+        "chrf3": float(ChrF3(HYPS, REFS)), "chrf3_name": ChrF3.name,
+        "chrf_default": float(ChrFEvaluator()(HYPS, REFS)),
+        "chrf_ignored": float(ChrFEvaluator(n=3, beta=2.0, ignored_symbols=[" ", "a"])(HYPS, REFS)),
+        "chrf_per_sentence": [float(ChrF3.score_instance(h, r)) for h, r in zip(HYPS + [[]], REFS + [[]])],
+        "edit_distance": float(EditDistance(HYPS, REFS)), "edit_distance_name": EditDistance.name,
+        "mse": float(MSE([[1.0, 2.0, 3.0], [0.5, 0.5, 0.5]], [[1.5, 2.0, 1.0], [0.0, 1.0, 0.5]])), "mse_name": MSE.name,
+        "pairwise_mse": float(PairwiseMSE([[1.0, 2.0, 3.0], [0.5]], [[1.5, 2.0, 1.0], [0.0]])),
+        "pairwise_mse_name": PairwiseMSE.name,
+        "average": float(AverageEvaluator("avg")([1.0, 2.5, 4.0], [0.0, 0.0, 0.0]))}
     # ---- helpers -----------------------------------------------------------------------------------
     from neuralmonkey.processors import helpers as H
     out["char_based"] = [H.preprocess_char_based(s) for s in SENTENCES]

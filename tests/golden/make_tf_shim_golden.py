@@ -458,7 +458,9 @@ def main():
             var[scope + "gates/kernel"], var[scope + "gates/bias"] = f32(in_dim + hsz, 2 * hsz, scale=0.5), 1.0 + f32(2 * hsz, scale=0.2)
             var[scope + "candidate/kernel"], var[scope + "candidate/bias"] = f32(in_dim + hsz, hsz, scale=0.5), f32(hsz, scale=0.2)
 
-        if cell == "NematusGRU":
+        if cell == "LSTM":
+            var[step + "lstm_cell/kernel"], var[step + "lstm_cell/bias"] = f32(esz + hsz, 4 * hsz, scale=0.5), f32(4 * hsz, scale=0.3)
+        elif cell == "NematusGRU":
             nematus_cell(step + "nematus_gru_cell/", esz, False, True)
             if conditional:
                 nematus_cell(step + "cond_gru_2_cell/", csz, True, False)
@@ -528,6 +530,7 @@ def main():
     rnn_variant_case("nematus", "NematusGRU", True, False, "nematus", "nematus")
     rnn_variant_case("cond_gru", "GRU", True, False, "mlp", "concat")
     rnn_variant_case("nematus_plain", "NematusGRU", False, False, "maxout", "empty")
+    rnn_variant_case("lstm", "LSTM", False, False, "maxout", "linear")
     # attention_on_input=True cannot be built in the reference: input_plus_attention reads
     # `feedables.prev_contexts` (decoder.py:273), which lives in `feedables.other` -> AttributeError
     try:
@@ -599,10 +602,14 @@ def main():
         for i, layer in enumerate(layers):
             size, direction = layer[0], layer[1]
             scope = "{}/rnn_{}_{}".format(name, i, direction)
-            cname = "nematus_gru_cell/" if len(layers[i]) > 2 and layers[i][2] == "NematusGRU" else "OrthoGRUCell/"
+            ctype = layers[i][2] if len(layers[i]) > 2 else "GRU"
+            cname = {"NematusGRU": "nematus_gru_cell/", "LSTM": "lstm_cell/", "GRU": "OrthoGRUCell/"}[ctype]
             cells = ([scope + "/bidirectional_rnn/fw/" + cname, scope + "/bidirectional_rnn/bw/" + cname]
                      if direction == "bidirectional" else [scope + "/rnn/" + cname])
             for cell in cells:
+                if cname == "lstm_cell/":
+                    var[cell + "kernel"], var[cell + "bias"] = f32(in_dim + size, 4 * size, scale=0.5), f32(4 * size, scale=0.3)
+                    continue
                 if cname == "nematus_gru_cell/":        # RNN_CELL_TYPES["NematusGRU"](size): input bias only
                     for part, width in (("gates", 2 * size), ("candidate", size)):
                         var[cell + part + "/input_proj/kernel"] = f32(in_dim, width, scale=0.5)
@@ -645,6 +652,10 @@ def main():
     recurrent_case("plain", [4], [(3, "backward"), (3, "forward")], True, False, False, False)
     recurrent_case("nematus", [5], [(4, "bidirectional", "NematusGRU"), (3, "forward", "NematusGRU")],
                    False, False, True, False)
+    # the encoder of the reference's tests/nematus.ini: an LSTM layer under two Nematus GRU layers
+    recurrent_case("mixed", [5], [(4, "forward", "LSTM"), (4, "backward", "NematusGRU"),
+                                  (3, "bidirectional", "NematusGRU"), (2, "bidirectional", "LSTM")],
+                   True, True, True, False)
 
     # ---- multi-source Transformer decoder layers: the four encoder-attention combination strategies
     #      (attention/transformer_cross_layer.py:12-263) over two encoders; the variables are drawn on demand

@@ -284,19 +284,48 @@ class GRUCell:
         return new_h, new_h
 
 
+LSTMStateTuple = __import__("collections").namedtuple("LSTMStateTuple", ["c", "h"])
+
+
+class LSTMCell(GRUCell):
+    """tf.nn.rnn_cell.LSTMCell with its defaults (no peepholes, no projection, forget_bias = 1), as
+    PUBLISHED by TensorFlow 1.x - library code restated, like GRUCell above:
+        [i, j, f, o] = [x, h] . kernel + bias;  c' = sigmoid(f + 1) * c + sigmoid(i) * tanh(j);
+        h' = sigmoid(o) * tanh(c');  output h', state (c', h')"""
+
+    @property
+    def state_size(self):
+        return LSTMStateTuple(self._num_units, self._num_units)
+
+    def call(self, inputs, state):
+        c, h = (np.asarray(s, np.float32) for s in state)
+        kernel, bias = _get_variable("kernel"), _get_variable("bias")
+        z = np.concatenate([np.asarray(inputs, np.float32), h], 1) @ kernel + bias
+        i, j, f, o = np.split(z, 4, axis=1)
+        sig = lambda v: 1.0 / (1.0 + np.exp(-v))
+        new_c = sig(f + 1.0) * c + sig(i) * np.tanh(j)
+        new_h = sig(o) * np.tanh(new_c)
+        return t(new_h, np.float32), LSTMStateTuple(t(new_c, np.float32), t(new_h, np.float32))
+
+
 def _rnn_loop(cell, inputs, lengths):
     """The recurrence of tf.nn.dynamic_rnn as TensorFlow documents it (library code, restated): zero
     initial state; past a sentence's length the output is zero and the state is carried unchanged."""
     x = np.asarray(inputs, np.float32)
     lengths = np.full((x.shape[0],), x.shape[1]) if lengths is None else np.asarray(lengths)
-    state = np.zeros((x.shape[0], cell.state_size), np.float32)
+    tupled = isinstance(cell.state_size, tuple)
+    sizes = cell.state_size if tupled else (cell.state_size,)
+    state = [np.zeros((x.shape[0], n), np.float32) for n in sizes]
     outputs = []
     for step in range(x.shape[1]):
-        out, new = cell(t(x[:, step]), t(state))
+        fed = type(cell.state_size)(*[t(s) for s in state]) if tupled else t(state[0])
+        out, new = cell(t(x[:, step]), fed)
         alive = (step < lengths)[:, None]
-        state = np.where(alive, np.asarray(new), state)
+        new = list(new) if tupled else [new]
+        state = [np.where(alive, np.asarray(n), s) for n, s in zip(new, state)]
         outputs.append(np.where(alive, np.asarray(out), 0.0))
-    return t(np.stack(outputs, 1), np.float32), t(state, np.float32)
+    final = type(cell.state_size)(*[t(s, np.float32) for s in state]) if tupled else t(state[0], np.float32)
+    return t(np.stack(outputs, 1), np.float32), final
 
 
 def _reverse_sequence(x, lengths, seq_axis=1, batch_axis=0):
@@ -426,7 +455,8 @@ def install():
     tf.contrib.rnn = _Namespace("tensorflow.contrib.rnn")
     tf.contrib.rnn.GRUCell = GRUCell
     tf.contrib.rnn.RNNCell = GRUCell
-    tf.contrib.rnn.LSTMCell = type("LSTMCell", (), {})
+    tf.contrib.rnn.LSTMCell = LSTMCell
+    tf.contrib.rnn.LSTMStateTuple = LSTMStateTuple
     tf.nn.rnn_cell = _Namespace("tensorflow.nn.rnn_cell")
     tf.nn.rnn_cell.RNNCell = GRUCell
     tf.nn.rnn_cell.LSTMCell = tf.contrib.rnn.LSTMCell

@@ -26,7 +26,8 @@ pytestmark = [pytest.mark.gpu,
 @pytest.mark.parametrize("cell,conditional,out_proj,enc_proj,enc_cell", [
     ("NematusGRU", True, "nematus", "nematus", "NematusGRU"),
     ("GRU", True, "mlp", "linear", "GRU"),
-    ("NematusGRU", False, "maxout", "linear", "NematusGRU")])
+    ("NematusGRU", False, "maxout", "linear", "NematusGRU"),
+    ("LSTM", False, "maxout", "linear", "LSTM")])
 def test_variants_against_oracle(cell, conditional, out_proj, enc_proj, enc_cell, backend, tol):
     from neuralmonkey_b200 import ops
     try:

@@ -182,3 +182,30 @@ def test_greedy_runner_postprocessing_matches_reference(runner_golden, tmp_path)
         assert outputs == want["outputs"] and want["size"] == symbols.shape[1]
         assert sorted(want["losses"]) == sorted("target/" + n for n in object.__new__(GreedyRunner).loss_names)
         assert abs(want["losses"]["target/train_xent"] - want["train_xent"][0]) < 1e-12
+
+
+def test_further_evaluators_match_reference(golden):
+    """chrF (also per sentence, incl. two empty sentences), the difflib edit distance, the two mean
+    squared errors and the averaging evaluator against the reference's own classes, names included.
+    (`compare_scores` of the reference's error-rate evaluators calls zero-argument `super()` inside a
+    staticmethod and raises; here smaller-is-better is simply implemented.)"""
+    from neuralmonkey_b200 import evaluators as E
+    want = golden["more_evaluators"]
+    hyps, refs = golden["inputs"]["hyps"], golden["inputs"]["refs"]
+    assert E.ChrF3(hyps, refs) == pytest.approx(want["chrf3"], rel=1e-12) and E.ChrF3.name == want["chrf3_name"]
+    assert E.ChrFEvaluator()(hyps, refs) == pytest.approx(want["chrf_default"], rel=1e-12)
+    assert E.ChrFEvaluator(n=3, beta=2.0, ignored_symbols=[" ", "a"])(hyps, refs) == pytest.approx(
+        want["chrf_ignored"], rel=1e-12)
+    got = [E.ChrF3.score_instance(h, r) for h, r in zip(hyps + [[]], refs + [[]])]
+    assert got == pytest.approx(want["chrf_per_sentence"], rel=1e-12)
+    assert E.EditDistance(hyps, refs) == pytest.approx(want["edit_distance"], rel=1e-12)
+    assert E.EditDistance.name == want["edit_distance_name"]
+    assert E.EditDistance.compare_scores(0.1, 0.3) == 1 and E.ChrF3.compare_scores(0.1, 0.3) == -1
+    assert E.MSE([[1.0, 2.0, 3.0], [0.5, 0.5, 0.5]], [[1.5, 2.0, 1.0], [0.0, 1.0, 0.5]]) == pytest.approx(want["mse"])
+    assert E.MSE.name == want["mse_name"] and E.PairwiseMSE.name == want["pairwise_mse_name"]
+    assert E.PairwiseMSE([[1.0, 2.0, 3.0], [0.5]], [[1.5, 2.0, 1.0], [0.0]]) == pytest.approx(want["pairwise_mse"])
+    assert E.AverageEvaluator("avg")([1.0, 2.5, 4.0], [0.0, 0.0, 0.0]) == pytest.approx(want["average"])
+    # word error rate: Levenshtein over words, summed, over the summed reference lengths
+    assert E.WER([["a", "b"], []], [["a", "c", "d"], ["x"]]) == pytest.approx((2 + 1) / 4)
+    with pytest.raises(ImportError, match="pyter"):
+        E.TER([["a"]], [["b"]])

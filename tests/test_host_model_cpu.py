@@ -200,7 +200,8 @@ def _build_variant(cell, conditional, out_proj, enc_proj, enc_cell):
 @pytest.mark.parametrize("cell,conditional,out_proj,enc_proj,enc_cell", [
     ("NematusGRU", True, "nematus", "nematus", "NematusGRU"),      # tests/small.ini / tests/nematus.ini
     ("GRU", True, "mlp", "linear", "GRU"),
-    ("NematusGRU", False, "maxout", "linear", "NematusGRU")])
+    ("NematusGRU", False, "maxout", "linear", "NematusGRU"),
+    ("LSTM", False, "maxout", "linear", "LSTM")])
 def test_decoder_and_encoder_variants(cpu_model, cell, conditional, out_proj, enc_proj, enc_cell):
     """The step-wise variants (nn/variants.py, decoders/decoder.py `_variant_step`): the Nematus cell in
     encoder and decoder, the conditional GRU, nematus / mlp deep outputs, the nematus initial state -
@@ -256,7 +257,7 @@ def test_decoder_and_encoder_variants(cpu_model, cell, conditional, out_proj, en
     prev0 = O.decoder_initial_state(params, spec, oenc1["output"], oenc1, 1).repeat_interleave(3, 0)
     prev1, first = run(emb[torch.full((3,), O.START, dtype=torch.int64)], prev0)
     want = O.beam_search(lambda prev, words, _f: run(emb[words], prev), prev1, first, 3, 6, 1.0,
-                         lambda st, idx: st[idx])
+                         lambda st, idx: tuple(x[idx] for x in st) if isinstance(st, tuple) else st[idx])
     assert bool((out.last_search_step_output.token_ids[1:] == want["token_ids"]).all())
     assert max_abs(out.last_search_step_output.scores, want["scores"]) < 1e-4
 

@@ -308,7 +308,9 @@ def test_whole_attention_decoder(tag, maxout, use_mask):
     ("sentence", [(4, "bidirectional")], False, False, True, False),
     ("deep", [(4, "forward"), (4, "backward"), (2, "bidirectional"), (3, "bidirectional")], True, True, True, True),
     ("plain", [(3, "backward"), (3, "forward")], True, False, False, False),
-    ("nematus", [(4, "bidirectional", "NematusGRU"), (3, "forward", "NematusGRU")], False, False, True, False)])
+    ("nematus", [(4, "bidirectional", "NematusGRU"), (3, "forward", "NematusGRU")], False, False, True, False),
+    ("mixed", [(4, "forward", "LSTM"), (4, "backward", "NematusGRU"), (3, "bidirectional", "NematusGRU"),
+               (2, "bidirectional", "LSTM")], True, True, True, False)])
 def test_recurrent_encoder(tag, layers, residual, layer_norm, final_norm, scale):
     """model/sequence.py EmbeddedFactorSequence.temporal_states / temporal_mask (:170-199) and
     encoders/recurrent.py RecurrentEncoder.rnn + rnn_layer (:71-110,180-218) run whole: factor lookup,
@@ -328,7 +330,8 @@ def test_recurrent_encoder(tag, layers, residual, layer_norm, final_norm, scale)
     assert np.abs(enc["output"].numpy() - G[name + "_output"]).max() < 5e-6
     assert np.array_equal(enc["temporal_mask"].numpy(), G[name + "_enc_mask"])
     # the scopes the reference called its cells in are the ones the oracle reads its parameters from
-    cell_scopes = {k[: k.index("gates/")] for k in p if "/gates/" in k}
+    cell_scopes = {k[: k.index("gates/")] for k in p if "/gates/" in k} | {
+        k[: -len("kernel")] for k in p if k.endswith("lstm_cell/kernel")}
     assert set(G[name + "_cell_scopes"].tolist()) == cell_scopes
 
 
@@ -496,7 +499,8 @@ def test_trainer_host_logic():
 @pytest.mark.parametrize("tag,cell,conditional,out_proj,enc_proj", [
     ("nematus", "NematusGRU", True, "nematus", "nematus"),
     ("cond_gru", "GRU", True, "mlp", "concat"),
-    ("nematus_plain", "NematusGRU", False, "maxout", "empty")])
+    ("nematus_plain", "NematusGRU", False, "maxout", "empty"),
+    ("lstm", "LSTM", False, "maxout", "linear")])
 def test_decoder_variants(tag, cell, conditional, out_proj, enc_proj):
     """The decoder variants of SURVEY.md 8(f) N4, the reference's Decoder run whole with them:
     NematusGRUCell (the reference's OWN cell code: nn/ortho_gru_cell.py:57-105), the conditional GRU
