@@ -66,8 +66,8 @@ class AutoregressiveDecoder(ModelPart):
         if self.dropout_keep_prob < 0.0 or self.dropout_keep_prob > 1.0:
             raise ValueError("Dropout keep probability must be a real number in the interval [0,1].")
         if self.label_smoothing:
-            raise NotImplementedError(
-                "label_smoothing is outside the B200 hot path built so far (SURVEY.md trap 14)")
+            from neuralmonkey_b200.nn.variants import require_variant
+            require_variant("label_smoothing")
         self._train_ids_host = None  # type: Optional[torch.Tensor]
 
     # -- static configuration ----------------------------------------------------------
@@ -233,6 +233,19 @@ class AutoregressiveDecoder(ModelPart):
         bsz, steps, dim = states.shape
         targets = self._train_targets_bm[:, :steps]
         weights = self._train_mask_bm[:, :steps]
+        if self.label_smoothing:
+            # What the reference computes (autoregressive.py:294-310, SURVEY.md trap 14): tf.losses.
+            # softmax_cross_entropy reduces the smoothed cross-entropies to ONE scalar - their mean over
+            # ALL positions, padding (target <pad>) included - and sequence_loss multiplies it by the mask.
+            flat = states.reshape(bsz * steps, dim)
+            every = torch.ones(bsz * steps, device=flat.device, dtype=torch.float32)
+            plain, lse, argmax, _ = ops.logits_xent(flat, self.decoding_w, self.decoding_b,
+                                                    targets.reshape(-1), every, self._unk_index,
+                                                    self._w_transposed)
+            term = ops.smoothing_term(flat, self.decoding_w, self.decoding_b, targets.reshape(-1),
+                                      self._unk_index, self._w_transposed)
+            scalar = (plain + float(self.label_smoothing) * term).mean()
+            return scalar * weights, lse.view(bsz, steps), argmax.view(bsz, steps)
         xent, lse, argmax, _ = ops.logits_xent(
             states.reshape(bsz * steps, dim), self.decoding_w, self.decoding_b,
             targets.reshape(-1), weights.reshape(-1), self._unk_index, self._w_transposed)

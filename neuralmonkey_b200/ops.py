@@ -390,6 +390,56 @@ def bahdanau_attention(keys: torch.Tensor, values: torch.Tensor, mask: Optional[
 # ---------------------------------------------------------------------------
 # K5/K6 vocabulary projection + cross-entropy
 # ---------------------------------------------------------------------------
+class _SmoothingTerm(torch.autograd.Function):
+    """logit[m, target[m]] - mean_v logit[m, v] for logits = x @ W + b (+ -1e9 on the <unk> column) without
+    materialising them: label smoothing adds `eps` times this to the plain cross-entropy
+    (xent_smoothed = lse - (1 - eps) * logit_t - eps * mean_v logit = xent + eps * (logit_t - mean_v logit)).
+    Host-level torch arithmetic on [M, K] tensors (a gather of M weight columns and a mean column); the
+    weight / bias gradients are accumulated into the arena's gradient buffer like every other op's."""
+
+    @staticmethod
+    def forward(ctx, x, w, b, targets, unk_index, trans_w):
+        vocab = w.size(0) if trans_w else w.size(1)
+        cols = w.index_select(0, targets) if trans_w else w.index_select(1, targets).t()
+        wmean = w.mean(0 if trans_w else 1)
+        value = (x * cols).sum(1) - x @ wmean
+        if b is not None:
+            value = value + b.index_select(0, targets) - b.mean()
+        if unk_index >= 0:
+            value = value - 1e9 * (targets == unk_index).to(value.dtype) + 1e9 / vocab
+        ctx.save_for_backward(x, cols, wmean, targets)
+        ctx.cfg = (vocab, trans_w, b is not None, w.shape)
+        ctx.sinks = (_sink(w), _sink(b) if b is not None else None)
+        return value
+
+    @staticmethod
+    def backward(ctx, g):
+        x, cols, wmean, targets = ctx.saved_tensors
+        vocab, trans_w, has_bias, w_shape = ctx.cfg
+        w_sink, b_sink = ctx.sinks
+        dx = g.unsqueeze(1) * (cols - wmean) if ctx.needs_input_grad[0] else None
+        gx = x * g.unsqueeze(1)                                    # [M, K]
+        dw = w_sink if w_sink is not None else torch.zeros(w_shape, device=x.device, dtype=torch.float32)
+        if trans_w:                                                 # W is [V, K]
+            dw.index_add_(0, targets, gx)
+            dw.sub_((gx.sum(0) / vocab).unsqueeze(0))
+        else:                                                       # W is [K, V]
+            dw.index_add_(1, targets, gx.t().contiguous())
+            dw.sub_((gx.sum(0) / vocab).unsqueeze(1))
+        db = None
+        if has_bias:
+            db = b_sink if b_sink is not None else torch.zeros(vocab, device=x.device, dtype=torch.float32)
+            db.index_add_(0, targets, g)
+            db.sub_(g.sum() / vocab)
+        return (dx, None if w_sink is not None else dw, None if (b_sink is not None or not has_bias) else db,
+                None, None, None)
+
+
+def smoothing_term(x: torch.Tensor, w: torch.Tensor, b: Optional[torch.Tensor], targets: torch.Tensor,
+                   unk_index: int = -1, trans_w: bool = False) -> torch.Tensor:
+    return _SmoothingTerm.apply(x, w, b, targets, unk_index, trans_w)
+
+
 def _xent16_enabled() -> bool:
     """NMB200_XENT16=1: the vocabulary projection with fp16 operands and fp16 dlogits (csrc/xent16.cu).
     Written and compiled, numerics settled on the CPU (tools/fp16_dlogits_study.py), NOT yet run on a

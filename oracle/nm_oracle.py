@@ -394,8 +394,26 @@ def autoregressive_loop(next_output: Callable, to_logits: Callable, embed: Calla
     return hist
 
 
+def sequence_xents(logits: torch.Tensor, targets: torch.Tensor, mask: torch.Tensor,
+                   label_smoothing: Optional[float] = None) -> torch.Tensor:
+    """train_xents (autoregressive.py:292-310) for logits [.., V], targets and mask of the leading shape.
+
+    Without smoothing: per-position cross-entropy times the mask.  WITH `label_smoothing` the reference
+    hands sequence_loss a function built on `tf.losses.softmax_cross_entropy`, which smooths the labels to
+    onehot * (1 - s) + s / V but then REDUCES to one scalar - the mean over ALL positions, padding
+    included, their target being <pad> - and sequence_loss multiplies that scalar by the mask.  So every
+    unmasked position carries the same number, and train_loss (sum / sum(mask)) is that number."""
+    logprobs = torch.log_softmax(logits, dim=-1)
+    if not label_smoothing:
+        return -logprobs.gather(-1, targets.unsqueeze(-1)).squeeze(-1) * mask
+    vocab = logits.shape[-1]
+    smoothed = torch.nn.functional.one_hot(targets, vocab).to(logits.dtype) * (1.0 - label_smoothing) \
+        + label_smoothing / vocab
+    return -(smoothed * logprobs).sum(-1).mean() * mask
+
+
 def decoder_train(p: Params, spec: RNNDecoderSpec, enc: Dict[str, torch.Tensor],
-                  train_inputs: torch.Tensor) -> Dict[str, torch.Tensor]:
+                  train_inputs: torch.Tensor, label_smoothing: Optional[float] = None) -> Dict[str, torch.Tensor]:
     """decoding_loop(train_mode=True) + train_xents/train_loss (autoregressive.py:292-316,532-562).
 
     train_inputs: [T, B] int64 = padded references with </s> appended (feed_dict :579-582),
@@ -416,9 +434,8 @@ def decoder_train(p: Params, spec: RNNDecoderSpec, enc: Dict[str, torch.Tensor],
     att_weights, rnn_outputs = [e[0] for e in hist["extra"]], [e[1] for e in hist["extra"]]
     logits_t = torch.stack(logits_hist, 0)                       # [T,B,V]
     train_mask = sentence_mask(train_inputs, logits_t.dtype)     # [T,B]
-    logprobs = torch.log_softmax(logits_t, dim=-1)
-    xents = -logprobs.gather(2, train_inputs[:logits_t.shape[0]].unsqueeze(-1)).squeeze(-1)
-    xents = xents * train_mask[:logits_t.shape[0]]
+    xents = sequence_xents(logits_t, train_inputs[:logits_t.shape[0]], train_mask[:logits_t.shape[0]],
+                           label_smoothing)
     loss = xents.sum() / train_mask.sum()
     return {"train_logits": logits_t, "train_xents": xents.t(), "train_loss": loss,
             "train_mask": train_mask, "train_output_states": torch.stack(out_states, 0),
@@ -619,7 +636,7 @@ def transformer_logits(p: Params, spec: TransformerDecoderSpec, states: torch.Te
 
 
 def transformer_decoder_train(p: Params, spec: TransformerDecoderSpec, enc: Dict[str, torch.Tensor],
-                              tgt_ids: torch.Tensor) -> Dict[str, torch.Tensor]:
+                              tgt_ids: torch.Tensor, label_smoothing: Optional[float] = None) -> Dict[str, torch.Tensor]:
     """train_loop_result (decoders/transformer.py:389-447) + train_xents / train_loss
     (autoregressive.py:292-316).  tgt_ids [B,T] incl. </s>.  Inputs are embedded WITHOUT a
     position signal: the base-class `embed_input_symbols` is what the reference calls."""
@@ -630,8 +647,7 @@ def transformer_decoder_train(p: Params, spec: TransformerDecoderSpec, enc: Dict
     mask = (tgt_ids != PAD).to(emb.dtype)
     states = transformer_decoder_stack(p, spec, inputs, mask, enc["states"], enc["mask"])
     logits = transformer_logits(p, spec, states)
-    logprobs = torch.log_softmax(logits, dim=-1)
-    xent = -logprobs.gather(2, tgt_ids.unsqueeze(2)).squeeze(2) * mask
+    xent = sequence_xents(logits, tgt_ids, mask, label_smoothing)
     return {"states": states, "logits": logits, "xents": xent, "loss": xent.sum() / mask.sum(),
             "loss_sum": xent.sum(), "count": mask.sum()}
 

@@ -394,6 +394,17 @@ def main():
                 return
             if mode == "loss":                   # the lazily built loss tensors (autoregressive.py:292-371)
                 key = "rd_{}_".format(tag)
+                # label smoothing (:294-300): tf.losses.softmax_cross_entropy reduces to ONE scalar, which
+                # sequence_loss then multiplies by the weights
+                smooth = object.__new__(Decoder)
+                smooth.__dict__.update(rd.__dict__)
+                smooth.__dict__.pop("_train_xents_cached_placeholder", None)
+                smooth.__dict__.pop("_train_loss_cached_placeholder", None)
+                smooth.label_smoothing = 0.1
+                smooth._train_loop_result_cached_placeholder = rd.train_loop_result
+                smooth._train_logits_cached_placeholder = rd.train_logits
+                out[key + "smooth_train_xents"] = np.asarray(smooth.train_xents)
+                out[key + "smooth_train_loss"] = np.asarray(smooth.train_loss)
                 for attr in ("train_xents", "train_loss", "train_mask", "runtime_xents", "runtime_loss", "decoded",
                              "runtime_logprobs", "runtime_mask"):
                     out[key + attr] = np.asarray(getattr(rd, attr))

@@ -225,8 +225,9 @@ def _top_k(values, k):
 
 
 def _one_hot(index, depth, dtype=np.float32, on_value=1.0, off_value=0.0):
-    out = np.full((depth,), off_value, dtype=dtype)
-    out[int(index)] = on_value
+    idx = np.asarray(index).astype(np.int64)
+    out = np.full(idx.shape + (int(depth),), off_value, dtype=dtype)
+    np.put_along_axis(out, idx[..., None], on_value, axis=-1)
     return t(out)
 
 
@@ -356,14 +357,32 @@ def _bidirectional_dynamic_rnn(cell_fw, cell_bw, inputs, sequence_length=None, d
     return (out_fw, out_bw), (st_fw, st_bw)
 
 
+def _softmax_cross_entropy(onehot_labels, logits, weights=1.0, label_smoothing=0, **kwargs):
+    """tf.losses.softmax_cross_entropy as TensorFlow documents it (library code, restated): the labels are
+    smoothed to onehot * (1 - s) + s / num_classes, and the result is REDUCED to one scalar - the mean over
+    the rows (reduction SUM_BY_NONZERO_WEIGHTS with weights 1)."""
+    onehot = np.asarray(onehot_labels, np.float32)
+    if label_smoothing:
+        onehot = onehot * (1.0 - label_smoothing) + label_smoothing / onehot.shape[-1]
+    losses = -(onehot * np.asarray(_log_softmax(logits))).sum(-1)
+    return t(np.float32(losses.mean()), np.float32)
+
+
 def _sequence_loss(logits, targets, weights, average_across_timesteps=True, average_across_batch=True,
                    softmax_loss_function=None, name=None):
-    """tf.contrib.seq2seq.sequence_loss as TensorFlow documents it (library code, restated), for the
-    only way the reference calls it: no averaging, default loss => weights * sparse softmax xent."""
-    assert not average_across_timesteps and not average_across_batch and softmax_loss_function is None
-    logprobs = np.asarray(_log_softmax(logits))
-    picked = np.take_along_axis(logprobs, np.asarray(targets)[..., None].astype(np.int64), -1)[..., 0]
-    return t(-picked * np.asarray(weights, np.float32), np.float32)
+    """tf.contrib.seq2seq.sequence_loss as TensorFlow documents it (library code, restated), without
+    averaging: logits and targets are flattened, the loss function is applied (default: sparse softmax
+    cross-entropy per row), the result is multiplied by the flattened weights and reshaped to [B, T]."""
+    assert not average_across_timesteps and not average_across_batch
+    lg = np.asarray(logits, np.float32)
+    flat_logits, flat_targets = lg.reshape(-1, lg.shape[-1]), np.asarray(targets).reshape(-1)
+    if softmax_loss_function is None:
+        logprobs = np.asarray(_log_softmax(t(flat_logits)))
+        crossent = -np.take_along_axis(logprobs, flat_targets[:, None].astype(np.int64), -1)[:, 0]
+    else:
+        crossent = np.asarray(softmax_loss_function(labels=t(flat_targets), logits=t(flat_logits)))
+    crossent = crossent * np.asarray(weights, np.float32).reshape(-1)
+    return t(crossent.reshape(lg.shape[0], lg.shape[1]), np.float32)
 
 
 def _while_loop(cond, body, loop_vars, shape_invariants=None, **kwargs):
@@ -476,6 +495,8 @@ def install():
         np.asarray(g) * clip / max(float(np.sqrt(np.sum(np.square(np.asarray(g, np.float32))))), clip), np.float32)
     tf.contrib.seq2seq = _Namespace("tensorflow.contrib.seq2seq")
     tf.contrib.seq2seq.sequence_loss = _sequence_loss
+    tf.losses = _Namespace("tensorflow.losses")
+    tf.losses.softmax_cross_entropy = _softmax_cross_entropy
     tf.control_dependencies = _name_scope_cm
     tf.squeeze = lambda x, axis=None: t(np.squeeze(np.asarray(x), axis=axis))
     tf.orthogonal_initializer = lambda *a, **k: None

@@ -15,7 +15,7 @@ import torch
 
 from oracle import nm_oracle as O
 from tests.helpers import feed, max_abs, oracle_params_for, random_batch
-from tests.test_host_model_cpu import _build_variant, check_multi_source
+from tests.test_host_model_cpu import _build_variant, check_label_smoothing, check_multi_source
 
 pytestmark = [pytest.mark.gpu,
               pytest.mark.skipif(os.environ.get("NMB200_UNVERIFIED") != "1",
@@ -80,5 +80,16 @@ def test_multi_source_transformer_decoder(strategy, backend, tol, gtol):
         def grads_of(model):
             return model["arena"].named_grads()
         check_multi_source(strategy, grads_of, tol, gtol)
+    finally:
+        ops.set_gemm_backend("auto")
+
+
+@pytest.mark.parametrize("backend,tol,gtol", [("simt", 5e-5, 3e-4), ("auto", 1e-2, 2e-2)])
+@pytest.mark.parametrize("tie", [False, True])
+def test_label_smoothing(tie, backend, tol, gtol):
+    from neuralmonkey_b200 import ops
+    try:
+        ops.set_gemm_backend(backend)
+        check_label_smoothing(tie, tol, gtol)
     finally:
         ops.set_gemm_backend("auto")

@@ -454,3 +454,55 @@ def check_multi_source(strategy, grads_of, tol, gtol):
         symbols = O.transformer_logits(params, spec, out).argmax(-1) * (~finished).long()
         finished = finished | (symbols == O.END)
         assert bool((dec.runtime_symbols[step].cpu() == symbols).all()), step
+
+
+@pytest.mark.parametrize("tie", [False, True])
+def test_label_smoothing_follows_the_reference(cpu_model, tie):
+    """label_smoothing as the reference computes it (SURVEY.md trap 14, pinned in
+    test_oracle_vs_reference_code.py): ONE scalar - the mean over all positions, padding included, of the
+    smoothed cross-entropy - times the mask.  The product adds eps * (logit_target - mean logit) to the
+    fused plain cross-entropy; loss and every gradient against the oracle."""
+    check_label_smoothing(tie, 1e-5, 1e-4)
+
+
+def check_label_smoothing(tie, tol, gtol):
+    from neuralmonkey_b200 import runtime, tf
+    from neuralmonkey_b200.attention import Attention
+    from neuralmonkey_b200.decoders import Decoder
+    from neuralmonkey_b200.encoders import SentenceEncoder
+    from neuralmonkey_b200.trainers import CrossEntropyTrainer
+    from neuralmonkey_b200.vocabulary import Vocabulary
+    runtime.reset()
+    src_vocab = Vocabulary(["s{}".format(i) for i in range(26)])
+    tgt_vocab = Vocabulary(["t{}".format(i) for i in range(36)])
+    enc = SentenceEncoder(name="sentence_encoder", vocabulary=src_vocab, data_id="source", embedding_size=6,
+                          rnn_size=5, max_input_len=10)
+    att = Attention(name="attention", encoder=enc)
+    dec = Decoder(encoders=[enc], vocabulary=tgt_vocab, data_id="target", name="decoder", max_output_len=10,
+                  rnn_size=8, embedding_size=8, attentions=[att], label_smoothing=0.1, tie_embeddings=tie,
+                  supress_unk=False)
+    trainer = CrossEntropyTrainer(decoders=[dec], optimizer=tf.AdamOptimizer(learning_rate=1e-3))
+    for part in trainer.parameterizeds:
+        part.ensure_declared()
+    runtime.arena().finalize(runtime.device())
+    model = {"enc": enc, "att": att, "dec": dec, "arena": runtime.arena()}
+    params = oracle_params_for(model)
+    model["arena"].load_dict(params)
+    src, tgt = random_batch(5, 8, 7, 30, 40, seed=1)
+    feed(model, src, tgt, train=True)
+    p = {n: v.clone().requires_grad_(True) for n, v in params.items()}
+    if tie:      # the oracle's RNN decoder reads state_to_word_W / b: the transposed embeddings, zero bias
+        p["decoder/state_to_word_W"] = p["decoder/word_embeddings"].t()
+        p["decoder/state_to_word_b"] = torch.zeros(40)
+    spec = O.RNNDecoderSpec("decoder", "attention", 10, "tanh", False)
+    odec = O.decoder_train(p, spec, O.sentence_encoder(p, "sentence_encoder", src), tgt.t(), label_smoothing=0.1)
+    assert max_abs(dec.train_xents, odec["train_xents"]) < tol
+    assert abs(float(dec.train_loss) - float(odec["train_loss"])) < tol
+    model["arena"].zero_grad()
+    dec.train_loss.backward()
+    odec["train_loss"].backward()
+    for name in model["arena"].train_names:
+        view = model["arena"].get(name)   # CPU stand-ins leave gradients in .grad, the real ops in the arena
+        got = ((view.grad if view.grad is not None else torch.zeros_like(view)) + model["arena"].grad(name)).cpu()
+        want = p[name].grad if p[name].grad is not None else torch.zeros_like(p[name])
+        assert float((got - want.reshape(got.shape)).norm()) <= gtol * float(want.norm()) + 1e-7, name

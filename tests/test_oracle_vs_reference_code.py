@@ -298,6 +298,11 @@ def test_whole_attention_decoder(tag, maxout, use_mask):
     assert np.abs(train["train_xents"].numpy() - G[dname + "_train_xents"]).max() < 1e-5
     assert abs(float(train["train_loss"]) - float(G[dname + "_train_loss"])) < 1e-5
     assert np.array_equal(train["train_mask"].numpy(), G[dname + "_train_mask"])
+    # label smoothing: one scalar (the mean over ALL positions of the smoothed cross-entropy) times the mask
+    smooth = O.decoder_train(p, spec, enc, gold, label_smoothing=0.1)
+    assert np.abs(smooth["train_xents"].numpy() - G[dname + "_smooth_train_xents"]).max() < 1e-5
+    assert abs(float(smooth["train_loss"]) - float(G[dname + "_smooth_train_loss"])) < 1e-5
+    assert len(set(np.round(G[dname + "_smooth_train_xents"][G[dname + "_smooth_train_xents"] > 0], 4))) == 1
     assert np.abs(run["runtime_xents"].numpy() - G[dname + "_runtime_xents"]).max() < 1e-5
     assert abs(float(run["runtime_loss"]) - float(G[dname + "_runtime_loss"])) < 1e-5
     assert np.array_equal(run["decoded"].numpy(), G[dname + "_decoded"])
