@@ -228,6 +228,20 @@ class ParameterArena:
     def zero_grad(self) -> None:
         self.grad_buffer.zero_()
 
+    def fold_autograd_grads(self) -> int:
+        """Every op writes its weight gradients straight into the gradient buffer (`nm_grad` sinks).  If a
+        model part uses a parameter in a plain torch expression instead, autograd leaves that gradient
+        in the view's `.grad`, where the optimizer kernel would never see it: add it to the buffer.
+        Returns how many views carried one (0 on every path built from the library's ops)."""
+        folded = 0
+        for name in self.train_names:
+            view = self._views[name]
+            if view.grad is not None:
+                view.nm_grad.add_(view.grad)
+                view.grad = None
+                folded += 1
+        return folded
+
     @property
     def allreduce_view(self) -> torch.Tensor:
         """Gradients + stat slots: the one buffer a data-parallel step exchanges."""

@@ -75,6 +75,7 @@ class GenericTrainer(GraphExecutor, Feedable):
             loss_sum, count = exact
             w = self.objectives[0].weight
             (loss_sum if w is None else loss_sum * w).backward()
+            arena.fold_autograd_grads()
             arena.stats[0].copy_(loss_sum.detach())
             arena.stats[1].copy_(count.detach())
             return {"exact": True}
@@ -86,6 +87,7 @@ class GenericTrainer(GraphExecutor, Feedable):
             term = obj.loss * w
             total = term if total is None else total + term
         total.backward()
+        arena.fold_autograd_grads()
         return {"exact": False}
 
     # -- CUDA-graph replay of a whole step -------------------------------------------------------

@@ -122,8 +122,8 @@ def xent_rows(logits, targets=None, weights=None, want_argmax=False, first_col=0
 
 
 def adam_kernel(trainer, grad_scale, denominator, lr_t, lr_t_dev):
-    """Stand-in for GenericTrainer._adam_kernel (`nm_clip_adam_step`): gradients arrive in the `.grad` of
-    the arena's views here (plain autograd), not in the arena's gradient buffer.  Same order as the
+    """Stand-in for GenericTrainer._adam_kernel (`nm_clip_adam_step`) over the arena's gradient buffer
+    (the stand-in ops leave their gradients in `.grad`; the trainer folds those in).  Same order as the
     kernel: scale, add the L1 / L2 terms of the regularised variables, clip per tensor, TF-Adam."""
     from neuralmonkey_b200 import runtime
     arena, opt = runtime.arena(), trainer.optimizer
@@ -134,8 +134,7 @@ def adam_kernel(trainer, grad_scale, denominator, lr_t, lr_t_dev):
     with torch.no_grad():
         for name in arena.train_names:
             var = arena.get(name)
-            grad = (var.grad if var.grad is not None else torch.zeros_like(var)) * scale
-            var.grad = None
+            grad = arena.grad(name) * scale           # the trainer folded the autograd gradients in
             if O.is_regularizable(name):
                 l1 += float(var.abs().sum())
                 l2 += float((var ** 2).sum())

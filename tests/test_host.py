@@ -151,3 +151,16 @@ def test_bench_reference_arm_prints_the_contract_line():
     assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["value"] == line["value"]
     assert line["e2e"]["value"] == line["value"] and line["e2e"]["h2d_bytes_per_step"] == 0
     assert line["e2e"]["d2h_bytes_per_step"] == 0
+
+
+def test_arena_folds_gradients_left_by_plain_autograd():
+    arena = ParameterArena()
+    arena.declare("a/kernel", [3, 4], normal_initializer())
+    arena.declare("a/bias", [4], zeros_initializer())
+    arena.finalize(torch.device("cpu"))
+    kernel = arena.get("a/kernel")
+    (kernel * 2.0).sum().backward()              # a torch expression on a parameter: gradient in .grad
+    arena.grad("a/kernel").fill_(1.0)            # something an op already accumulated
+    assert arena.fold_autograd_grads() == 1
+    assert kernel.grad is None and torch.equal(arena.grad("a/kernel"), torch.full((3, 4), 3.0))
+    assert arena.fold_autograd_grads() == 0
