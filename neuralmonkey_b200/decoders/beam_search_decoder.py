@@ -10,9 +10,9 @@ step on the re-ordered beam.  The host loop reads one device flag per step (all 
 Differences kept deliberately small: decoder *histories* (logits/attention weights of every
 step) are not re-gathered each step - the reference never finalises them for beam search
 either (:372-374) - and only the last step's logits are kept alive, so a beam of 12 over a
-32k vocabulary does not hold steps*batch*beam*V floats.  Ensembling by re-feeding the loop
-state one step at a time (`max_steps` placeholder, beamsearch_runner.py:48-78) is a
-multi-session feature outside the hot path.
+32k vocabulary does not hold steps*batch*beam*V floats.  Ensembling, which the reference does by
+re-feeding the loop state one step at a time (`max_steps` placeholder, beamsearch_runner.py:48-78), is
+`ensemble_outputs`: the same schedule in one loop.
 """
 from typing import Any, List, NamedTuple
 
@@ -106,8 +106,23 @@ class BeamSearchDecoder(ModelPart):
                                        token_ids=symbols.view(1, bsz, k))
         return BeamSearchLoopState(search_state, search_results, dec_next)
 
+    def _select(self, state: SearchState):
+        """Steps (1)-(8) of the beam body on the shared search state: the K12 kernel."""
+        return ops.beam_step(state.prev_logprobs, state.logprob_sum, state.lengths,
+                             state.finished.to(torch.uint8), self.length_normalization)
+
+    def _advance(self, dec_ls: LoopState, words, beams, finished, bsz: int):
+        """Re-order one decoder's feedables to the selected beams, feed the chosen words, step it."""
+        k = self.beam_size
+        gathered = map_structure(
+            lambda x: ops.beam_gather(x, beams, bsz, k)
+            if x.dim() >= 1 and x.shape[0] == bsz * k and x.numel() > 0 else x, dec_ls.feedables)
+        gathered = gathered._replace(
+            embedded_input=self.parent_decoder.embed_input_symbols(words.view(-1)),
+            finished=finished.view(-1))
+        return self._decoder_step(dec_ls._replace(feedables=gathered))
+
     def decoding_loop(self, initial: BeamSearchLoopState) -> BeamSearchOutput:
-        parent = self.parent_decoder
         k = self.beam_size
         bsz = initial.search_state.logprob_sum.shape[0]
         dev = runtime.device()
@@ -119,26 +134,70 @@ class BeamSearchDecoder(ModelPart):
         written = 1
         # loop_continue_criterion (:330-355): decoder step - 1 < max_steps and not all finished
         while dec_ls.feedables.step - 1 < self.max_steps and not bool(state.finished.all()):
-            scores, words, beams, lsum, lens, fin = ops.beam_step(
-                state.prev_logprobs, state.logprob_sum, state.lengths,
-                state.finished.to(torch.uint8), self.length_normalization)
+            scores, words, beams, lsum, lens, fin = self._select(state)
             finished = fin.to(torch.bool)
-            gathered = map_structure(
-                lambda x: ops.beam_gather(x, beams, bsz, k)
-                if x.dim() >= 1 and x.shape[0] == bsz * k and x.numel() > 0 else x, dec_ls.feedables)
-            gathered = gathered._replace(
-                embedded_input=parent.embed_input_symbols(words.view(-1)),
-                finished=finished.view(-1))
             history = ops.beam_gather(history, beams, bsz, k)
             history[:, written] = words.view(-1)
             written += 1
-            dec_ls, logprobs, _ = self._decoder_step(dec_ls._replace(feedables=gathered))
+            dec_ls, logprobs, _ = self._advance(dec_ls, words, beams, finished, bsz)
             state = SearchState(logprob_sum=lsum, prev_logprobs=logprobs, lengths=lens,
                                 finished=finished)
         token_ids = history[:, :written].view(bsz, k, written).permute(2, 0, 1).contiguous()
         return BeamSearchOutput(
             last_search_step_output=SearchResults(scores=scores, token_ids=token_ids),
             last_dec_loop_state=dec_ls, last_search_state=state, attention_loop_states=[])
+
+    def ensemble_outputs(self, activate, num_sessions: int) -> BeamSearchOutput:
+        """The search over an ensemble (runners/beamsearch_runner.py:44-118 drive it through placeholders
+        one step at a time; this is the same schedule in one loop).  `activate(i)` switches the model
+        parts to session i.  Every session runs its own decoder (own parameters, own encoder states, own
+        recurrent state); the search state is ONE: after each decoder step the sessions' next-token
+        log-probabilities are averaged in probability space, logsumexp - log(n) (:50-54), and the next
+        selection is made on that average - so all sessions follow the same beam."""
+        parent = self.parent_decoder
+        k = self.beam_size
+        enc_states, enc_masks = parent.encoder_states, parent.encoder_masks
+        log_n = float(torch.log(torch.tensor(float(num_sessions))))
+
+        def on_session(index, fn):
+            activate(index)
+            tiled_states = [self.expand_to_beam(s) for s in enc_states()]
+            tiled_masks = [self.expand_to_beam(m) if m is not None else None for m in enc_masks()]
+            parent.encoder_states, parent.encoder_masks = (lambda: tiled_states), (lambda: tiled_masks)
+            try:
+                with torch.no_grad():
+                    return fn()
+            finally:
+                parent.encoder_states, parent.encoder_masks = enc_states, enc_masks
+
+        initial = [on_session(i, self.get_initial_loop_state) for i in range(num_sessions)]
+        dec_ls = [init.decoder_loop_state for init in initial]
+
+        def average(logprobs):
+            return torch.logsumexp(torch.stack(logprobs, 0), dim=0) - log_n
+
+        state = initial[0].search_state._replace(
+            prev_logprobs=average([init.search_state.prev_logprobs for init in initial]))
+        scores = initial[0].search_results.scores
+        bsz = state.logprob_sum.shape[0]
+        history = torch.zeros(bsz * k, self.max_steps + 1, dtype=torch.int64, device=runtime.device())
+        history[:, 0] = initial[0].search_results.token_ids.reshape(-1)
+        written = 1
+        while dec_ls[0].feedables.step - 1 < self.max_steps and not bool(state.finished.all()):
+            scores, words, beams, lsum, lens, fin = self._select(state)
+            finished = fin.to(torch.bool)
+            history = ops.beam_gather(history, beams, bsz, k)
+            history[:, written] = words.view(-1)
+            written += 1
+            stepped = [on_session(i, lambda i=i: self._advance(dec_ls[i], words, beams, finished, bsz))
+                       for i in range(num_sessions)]
+            dec_ls = [s[0] for s in stepped]
+            state = SearchState(logprob_sum=lsum, prev_logprobs=average([s[1] for s in stepped]),
+                                lengths=lens, finished=finished)
+        token_ids = history[:, :written].view(bsz, k, written).permute(2, 0, 1).contiguous()
+        return BeamSearchOutput(
+            last_search_step_output=SearchResults(scores=scores, token_ids=token_ids),
+            last_dec_loop_state=dec_ls[0], last_search_state=state, attention_loop_states=[])
 
     # Replay one captured CUDA graph per step when the parent is a Transformer decoder with a KV
     # cache (decoders/beam_graph.py); False falls back to the step-by-step host loop.

@@ -42,6 +42,12 @@ class GraphExecutor(GenericModelPart):
             """Compute and set the result for the batch currently fed."""
             raise NotImplementedError()
 
+        def execute_sessions(self, activate, num_sessions: int) -> None:
+            """Ensembles (`num_sessions > 1`): `activate(i)` switches the model parts to session i;
+            run on every session and combine (the reference's next_to_execute / collect_results)."""
+            raise NotImplementedError("{} cannot combine the outputs of several sessions".format(
+                type(self.executor).__name__))
+
     def __init__(self, dependencies: Set[GenericModelPart]) -> None:
         self._dependencies = dependencies
         self._feedables, self._parameterizeds = self.get_dependencies()

@@ -36,9 +36,19 @@ class BeamSearchRunner(BaseRunner):
     class Executable(BaseRunner.Executable):
         def execute(self) -> None:
             runner = self.executor
-            if self.num_sessions != 1:
-                raise NotImplementedError("beam search ensembles (num_sessions > 1) are not built")
             output = runner.decoder.outputs.last_search_step_output
+            decoded_tokens, loss = select_hypotheses(
+                output.scores.cpu().numpy(), output.token_ids.cpu().numpy(), runner.rank,
+                runner.decoder.vocabulary.index_to_word)
+            if runner.postprocess is not None:
+                decoded_tokens = runner.postprocess(decoded_tokens)
+            self.set_runner_result(outputs=decoded_tokens, losses=[loss])
+
+        def execute_sessions(self, activate, num_sessions: int) -> None:
+            """Ensembled search (beamsearch_runner.py:44-118): one beam, every session steps its own
+            decoder on it, the next-token log-probabilities are averaged in probability space."""
+            runner = self.executor
+            output = runner.decoder.ensemble_outputs(activate, num_sessions).last_search_step_output
             decoded_tokens, loss = select_hypotheses(
                 output.scores.cpu().numpy(), output.token_ids.cpu().numpy(), runner.rank,
                 runner.decoder.vocabulary.index_to_word)

@@ -11,6 +11,9 @@ class DatasetRunner(GraphExecutor, Feedable):
             outputs = {s: list(batch.get_series(s)) for s in batch.series} if batch is not None else {}
             self.set_result(outputs, {}, len(batch) if batch is not None else 0, [])
 
+        def execute_sessions(self, activate, num_sessions: int) -> None:
+            self.execute()            # the input series do not depend on the session
+
     def __init__(self) -> None:
         GraphExecutor.__init__(self, set())
         Feedable.__init__(self)

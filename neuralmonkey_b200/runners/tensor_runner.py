@@ -11,7 +11,8 @@ from neuralmonkey_b200.runners.base_runner import BaseRunner
 
 class TensorRunner(BaseRunner):
     class Executable(BaseRunner.Executable):
-        def execute(self) -> None:
+        def _fetch(self) -> List:
+            """The tensors of the active session as a batch of per-instance values."""
             runner = self.executor
             fetched = {}
             for part, name, bdim in zip(runner.modelparts, runner.tensor_names, runner.batch_dims):
@@ -20,10 +21,27 @@ class TensorRunner(BaseRunner):
                     value = np.moveaxis(value, bdim, 0)
                 fetched[name] = value
             if len(fetched) == 1 and runner.single_tensor:
-                outputs = list(next(iter(fetched.values())))
+                return list(next(iter(fetched.values())))
+            n = len(next(iter(fetched.values())))
+            return [{k: v[i] for k, v in fetched.items()} for i in range(n)]
+
+        def execute(self) -> None:
+            outputs = self._fetch()
+            self.set_runner_result(outputs=outputs, losses=[], size=len(outputs))
+
+        def execute_sessions(self, activate, num_sessions: int) -> None:
+            """tensor_runner.py:26-40: with `select_session` the tensors of that session, otherwise every
+            instance gets the tuple of its values in all sessions."""
+            select = self.executor.select_session
+            if select is not None:
+                activate(select)
+                outputs = self._fetch()
             else:
-                n = len(next(iter(fetched.values())))
-                outputs = [{k: v[i] for k, v in fetched.items()} for i in range(n)]
+                sessions = []
+                for index in range(num_sessions):
+                    activate(index)
+                    sessions.append(self._fetch())
+                outputs = list(zip(*sessions))
             self.set_runner_result(outputs=outputs, losses=[], size=len(outputs))
 
     # pylint: disable=too-many-arguments
@@ -45,6 +63,7 @@ class TensorRunner(BaseRunner):
         self.tensor_names = tensors
         self.batch_dims = batch_dims
         self.single_tensor = single_tensor
+        self.select_session = select_session
         self._dependencies = set(modelparts)
         self._feedables, self._parameterizeds = self.get_dependencies()
 

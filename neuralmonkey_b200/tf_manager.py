@@ -5,9 +5,15 @@ The class keeps its historical name because every Neural Monkey INI instantiates
 to the feedables and runs the executables of the given trainers / runners on the CUDA
 kernels; the n-best checkpoint bookkeeping (`variables.data[.i]`, `variables.data.best`) is
 kept; checkpoints are `torch.save`d {TF-style variable name: tensor} dictionaries.
+
+"Sessions" (`num_sessions > 1`, tf_manager.py:78-79,179-180) are model ENSEMBLES in the reference: N
+checkpoints of the same graph, run one after the other on every batch.  Here a session is one flat
+copy of the parameter buffer; activating it copies it into the arena (every variable is a view of that
+buffer) and swaps in that session's cache of per-batch tensors, so the model parts compute with those
+parameters.  Only runners support several sessions, as in the reference.
 """
 import os
-from typing import Any, List, Set, Union
+from typing import Any, List, Optional, Set, Union
 
 import numpy as np
 import torch
@@ -26,9 +32,9 @@ class TensorFlowManager:
                  enable_tf_debug: bool = False) -> None:
         if num_sessions < 1:
             raise ValueError("num_sessions must be positive")
-        if num_sessions != 1:
-            raise NotImplementedError("model ensembles (num_sessions > 1) are not built yet")
         self.num_sessions = num_sessions
+        self._session_params = None   # type: Optional[List[torch.Tensor]]
+        self._session_caches = []     # type: List[dict]
         self.num_threads = num_threads  # host threads only matter for the CPU reference
         self.saver_max_to_keep = save_n_best
         self.minimize_metric = minimize_metric
@@ -39,7 +45,25 @@ class TensorFlowManager:
         self.saved_scores = [init_score for _ in range(self.saver_max_to_keep)]
         self.best_vars_file = None
         self.variables_files = []  # type: List[str]
-        self.sessions = [self]  # kept for code that iterates over sessions
+        self.sessions = [self] * num_sessions  # kept for code that iterates over sessions
+
+    # -- sessions (ensembles) ------------------------------------------------------------------------
+    def _session_buffers(self) -> List[torch.Tensor]:
+        if self._session_params is None:
+            params = runtime.arena().params
+            self._session_params = [params.detach().clone() for _ in range(self.num_sessions)]
+        return self._session_params
+
+    def activate_session(self, index: int, parts=()) -> None:
+        """Make session `index` the one the model parts compute with: its parameters into the arena,
+        its per-batch tensor caches into the parts."""
+        if self.num_sessions == 1:
+            return
+        with torch.no_grad():
+            runtime.arena().params.copy_(self._session_buffers()[index])
+        caches = self._session_caches[index]
+        for part in parts:
+            part.__dict__["_batch_cache"] = caches.setdefault(id(part), {})
 
     @property
     def best_score(self) -> float:
@@ -93,6 +117,17 @@ class TensorFlowManager:
             feedable.feed_dict(batch, train)
         executables = [runner.get_executable(compute_losses=compute_losses, summaries=summaries,
                                              num_sessions=self.num_sessions) for runner in runners]
+        if self.num_sessions > 1:
+            # every executable sees the batch once per session and combines what the sessions produced
+            # (base_runner.py collect_results protocol); trainers refuse several sessions themselves
+            parts = set(feedables)
+            for runner in runners:
+                parts |= set(getattr(runner, "parameterizeds", ())) | set(getattr(runner, "feedables", ()))
+                parts.add(getattr(runner, "decoder", runner))
+            self._session_caches = [dict() for _ in range(self.num_sessions)]
+            for executable in executables:
+                executable.execute_sessions(lambda i: self.activate_session(i, parts), self.num_sessions)
+            return [executable.result for executable in executables]
         for i, executable in enumerate(executables):
             if train and i > 0:
                 # several trainers on one batch (tests/bahdanau.ini:12): the reference runs their
@@ -111,7 +146,8 @@ class TensorFlowManager:
             raise Exception("Provided {} files for restoring {} sessions.".format(
                 len(variable_files), self.num_sessions))
         arena = runtime.arena()
-        for path in variable_files:
+        for index, path in enumerate(variable_files):
+            self.activate_session(index)
             torch.save({"variables": arena.state_dict(), "adam_m": arena.moment_dict(arena.adam_m),
                         "adam_v": arena.moment_dict(arena.adam_v)}, path)
 
@@ -122,11 +158,13 @@ class TensorFlowManager:
             raise Exception("Provided {} files for restoring {} sessions.".format(
                 len(variable_files), self.num_sessions))
         arena = runtime.arena()
-        for path in variable_files:
+        for index, path in enumerate(variable_files):
             log("Loading variables from {}".format(path))
             ckpt = torch.load(path, map_location="cpu")
             arena.load_dict(ckpt["variables"])
-            if isinstance(ckpt.get("adam_m"), dict):   # optimizer moments, keyed by variable name
+            if self.num_sessions > 1:                   # one flat copy of the parameters per session
+                self._session_buffers()[index].copy_(arena.params.detach())
+            elif isinstance(ckpt.get("adam_m"), dict):   # optimizer moments, keyed by variable name
                 arena.load_moments(arena.adam_m, ckpt["adam_m"])
                 arena.load_moments(arena.adam_v, ckpt["adam_v"])
 

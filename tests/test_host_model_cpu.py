@@ -506,3 +506,188 @@ def check_label_smoothing(tie, tol, gtol):
         got = ((view.grad if view.grad is not None else torch.zeros_like(view)) + model["arena"].grad(name)).cpu()
         want = p[name].grad if p[name].grad is not None else torch.zeros_like(p[name])
         assert float((got - want.reshape(got.shape)).norm()) <= gtol * float(want.norm()) + 1e-7, name
+
+
+def _two_sessions(model, params_a, params_b, runners, batch_feed):
+    """A TensorFlowManager with two sessions holding params_a / params_b, executed on the fed batch."""
+    from neuralmonkey_b200.tf_manager import TensorFlowManager
+    manager = TensorFlowManager(num_sessions=2, num_threads=1)
+    arena = model["arena"]
+    for index, params in enumerate((params_a, params_b)):
+        arena.load_dict(params)
+        manager._session_buffers()[index].copy_(arena.params.detach())
+
+    class _Feed:                      # the manager feeds through `feed_dict`; the test feeds tensors directly
+        def feed_dict(self, _batch, _train):
+            batch_feed()
+    return manager.execute(None, {_Feed()}, runners, train=False, compute_losses=False, summaries=False)
+
+
+def test_greedy_runner_over_two_sessions(cpu_model):
+    """GreedyRunner with num_sessions = 2 (runner.py:33-62): every session decodes on its own, the
+    fetched log-probabilities are combined with logaddexp per step and the argmax is decoded."""
+    import numpy as np
+    from neuralmonkey_b200.runners import GreedyRunner
+    model = build_bahdanau(**TOY)
+    params_a, params_b = oracle_params_for(model, seed=7), oracle_params_for(model, seed=8)
+    src, tgt = random_batch(5, 8, 7, TOY["vs"], TOY["vt"], seed=3)
+    runner = GreedyRunner(output_series="target", decoder=model["dec"])
+    result, = _two_sessions(model, params_a, params_b, [runner], lambda: feed(model, src, tgt, train=False))
+    spec = oracle_spec(True, 10, True)
+    logprobs = [O.decoder_greedy(p, spec, O.sentence_encoder(p, "sentence_encoder", src))["runtime_logprobs"].numpy()
+                for p in (params_a, params_b)]
+    steps = logprobs[0].shape[0]
+    summed = [np.logaddexp(logprobs[0][t], logprobs[1][t]) if t < logprobs[1].shape[0] else logprobs[0][t]
+              for t in range(steps)]
+    want = model["dec"].vocabulary.vectors_to_sentences([np.argmax(s, axis=1) for s in summed])
+    assert result.outputs["target"] == want
+    # the ensemble of a model with itself decodes what the model decodes
+    same, = _two_sessions(model, params_a, params_a, [runner], lambda: feed(model, src, tgt, train=False))
+    single = model["dec"].vocabulary.vectors_to_sentences([np.argmax(s, axis=1) for s in logprobs[0]])
+    assert same.outputs["target"] == single
+
+
+@pytest.mark.parametrize("parent", ["rnn", "transformer"])
+def test_beam_search_over_two_sessions(cpu_model, parent):
+    """BeamSearchRunner with num_sessions = 2 (beamsearch_runner.py:44-118): one beam, each session steps
+    its own decoder, next-token log-probabilities averaged in probability space.  Against the oracle's
+    beam search over a pair of decoders, and the reference's own check (tests/tests_run.sh:40-50): the
+    ensemble of a model with itself scores what the single model scores."""
+    import math
+    from neuralmonkey_b200.decoders import BeamSearchDecoder
+    from neuralmonkey_b200.runners import BeamSearchRunner
+    beam, max_steps, alpha = 3, 6, 1.0
+    if parent == "rnn":
+        model = build_bahdanau(**TOY)
+        params_a, params_b = oracle_params_for(model, seed=7), oracle_params_for(model, seed=8)
+        src, _ = random_batch(1, 8, 7, TOY["vs"], TOY["vt"], seed=9)
+        feeder = lambda: feed(model, src, None, train=False)
+        spec = oracle_spec()
+
+        def session(p):
+            oenc = O.sentence_encoder(p, "sentence_encoder", src)
+            states, mask = oenc["temporal_states"].repeat_interleave(beam, 0), oenc["temporal_mask"].repeat_interleave(beam, 0)
+            hidden = O.bahdanau_precompute(p, "attention", states)
+            emb = p["decoder/word_embeddings"]
+
+            def run(words, prev, _finished=None):
+                output, cell, _c, _w = O.decoder_step(p, spec, emb[words], prev, hidden, states, mask)
+                return cell, torch.log_softmax(O.state_to_logits(p, spec, output), -1)
+            prev0 = O.decoder_initial_state(p, spec, oenc["output"]).repeat_interleave(beam, 0)
+            return run, prev0
+    else:
+        from tests.test_gpu_transformer import feed_transformer, oracle_encoder
+        model, params_a, src, _tgt, cfg = _transformer(seed=2, bsz=2)
+        params_b = oracle_params_for(model, scale=0.2, seed=11)
+        for name in params_b:
+            if name.endswith("gamma"):
+                params_b[name] = 1.0 + params_b[name]
+        model["dec"].use_kv_cache = True
+        feeder = lambda: feed_transformer(model, src, None, train=False)
+        spec = O.TransformerDecoderSpec("decoder", cfg["depth"], cfg["heads"], cfg["heads"], cfg["max_len"], True, False)
+
+        def session(p):
+            oenc = oracle_encoder(p, src, cfg)
+            states, emask = oenc["states"].repeat_interleave(beam, 0), oenc["mask"].repeat_interleave(beam, 0)
+            emb = p["decoder/word_embeddings"]
+
+            def run(words, prev, finished=None):      # prev = (sequence so far, its key mask)
+                live = torch.ones(len(words)) if finished is None else (~finished).to(emb.dtype)
+                seq = torch.cat([prev[0], emb[words].unsqueeze(1)], 1)
+                mask = torch.cat([prev[1], live.unsqueeze(1)], 1)
+                out = O.transformer_decoder_stack(p, spec, seq, mask, states, emask)
+                return (seq, mask), torch.log_softmax(O.transformer_logits(p, spec, out[:, -1]), -1)
+            rows = states.shape[0]
+            return run, (torch.zeros(rows, 0, emb.shape[1]), torch.zeros(rows, 0))
+    bs = BeamSearchDecoder(name="bs", parent_decoder=model["dec"], beam_size=beam, max_steps=max_steps,
+                           length_normalization=alpha)
+    bs.use_cuda_graph = False
+    runner = BeamSearchRunner(output_series="target", decoder=bs, rank=1)
+
+    def feed_all():
+        feeder()
+        bs.reset_batch()
+        bs.batch_size = src.shape[0]
+
+    def oracle_ensemble(param_sets):
+        sessions = [session(p) for p in param_sets]
+        rows = src.shape[0] * beam
+        start = torch.full((rows,), O.START, dtype=torch.int64)
+        firsts = [run(start, prev0) for run, prev0 in sessions]
+        average = lambda lps: torch.logsumexp(torch.stack(lps, 0), 0) - math.log(len(lps))
+
+        def step_fn(states, words, finished):
+            outs = [run(words, st, finished) for (run, _p), st in zip(sessions, states)]
+            return [o[0] for o in outs], average([o[1] for o in outs])
+
+        def gather(states, idx):
+            return [tuple(x[idx] for x in st) if isinstance(st, tuple) else st[idx] for st in states]
+        return O.beam_search(step_fn, [f[0] for f in firsts], average([f[1] for f in firsts]), beam, max_steps,
+                             alpha, gather)
+
+    result, = _two_sessions(model, params_a, params_b, [runner], feed_all)
+    want = oracle_ensemble([params_a, params_b])
+    vocab = model["dec"].vocabulary
+    for b in range(src.shape[0]):
+        toks = []
+        for t in want["token_ids"][:, b, 0].tolist():
+            if t == O.END:
+                break
+            toks.append(vocab.index_to_word[t])
+        assert result.outputs["target"][b] == toks
+    assert abs(result.losses["target/beam_search_score"] - float(want["scores"][:, 0].sum())) < 1e-3
+    # the reference's ensemble test: a model ensembled with itself scores what it scores alone
+    twice, = _two_sessions(model, params_a, params_a, [runner], feed_all)
+    model["arena"].load_dict(params_a)
+    feed_all()
+    alone = runner.get_executable(compute_losses=False, summaries=False, num_sessions=1)
+    alone.execute()
+    assert twice.outputs["target"] == alone.result.outputs["target"]
+    assert abs(twice.losses["target/beam_search_score"] - alone.result.losses["target/beam_search_score"]) < 1e-4
+
+
+def test_ensemble_of_a_model_with_itself_through_neuralmonkey_run(cpu_model, monkeypatch, tmp_path):
+    """The reference's ensemble check (tests/tests_run.sh:40-50) end to end: train the Transformer +
+    beam search experiment, then `neuralmonkey-run` it once alone and once as an ensemble of two copies
+    of the same variables (tf_manager.num_sessions=2, `variables=[v, v]` in the datasets INI): the
+    beam-search scores and the BLEU agree."""
+    import json
+    import os
+    from neuralmonkey_b200.trainers.generic_trainer import GenericTrainer
+    from tests import test_gpu_cli as cli
+    monkeypatch.setattr(GenericTrainer, "_adam_kernel", cpu_ops.adam_kernel)
+    data, out = str(tmp_path / "data"), str(tmp_path / "out")
+    cli._write_data(data)
+    ini = tmp_path / "exp.ini"
+    text = cli.TRANSFORMER_INI.format(out=out, data=data, epochs=1)
+    ini.write_text(text)
+    _cli(monkeypatch, "neuralmonkey_b200.train", ["neuralmonkey-train", str(ini)])
+    variables = os.path.join(out, "variables.data.final")
+    ensemble_ini = tmp_path / "ensemble.ini"
+    assert "num_sessions=1" in text
+    ensemble_ini.write_text(text.replace("num_sessions=1", "num_sessions=2"))
+    results = {}
+    for name, config, files in (("single", ini, [variables]), ("ensemble", ensemble_ini, [variables, variables])):
+        run_ini = tmp_path / (name + "_data.ini")
+        run_ini.write_text("""
+[main]
+test_datasets=[<val_data>]
+variables={files}
+
+[batching]
+class=dataset.BatchingScheme
+batch_size=10
+
+[val_data]
+class=dataset.load
+series=["source", "target"]
+data=["{data}/val.src", "{data}/val.tgt"]
+batching=<batching>
+""".format(files=json.dumps(files), data=data))
+        _cli(monkeypatch, "neuralmonkey_b200.run",
+             ["neuralmonkey-run", str(config), str(run_ini), "--json", str(tmp_path / (name + ".json"))])
+        results[name] = json.load(open(tmp_path / (name + ".json")))[0]
+    key = "target_beam.rank001/beam_search_score"
+    assert key in results["single"]
+    assert abs(results["single"][key] - results["ensemble"][key]) < 1e-3 * max(1.0, abs(results["single"][key]))
+    assert results["single"]["target_beam.rank001/BLEU-4"] == pytest.approx(results["ensemble"]["target_beam.rank001/BLEU-4"])
