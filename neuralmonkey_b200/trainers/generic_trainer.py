@@ -51,15 +51,35 @@ class GenericTrainer(GraphExecutor, Feedable):
         self.optimizer = optimizer if optimizer is not None else self.default_optimizer()
         self.global_step = 0
         self.batches_per_update = 1
-        if var_scopes is not None:
-            raise NotImplementedError(
-                "var_scopes: per-scope training is outside the B200 hot path built so far")
         if clip_norm is not None and clip_norm <= 0.0:
             raise ValueError("clip_norm must be positive")
 
     @property
     def var_list(self) -> List[str]:
-        return list(getattr(runtime.arena(), "train_names", []))
+        """Names of the variables this trainer updates: all trainable ones, or with `var_scopes` those
+        whose name starts with one of the scopes (tf.get_collection(collection, scope) matches the scope
+        as a regular expression at the start of the name; generic_trainer.py:196-205)."""
+        names = list(getattr(runtime.arena(), "train_names", []))
+        if self.var_scopes is None:
+            return names
+        return [n for n in names if any(re.match(scope, n) for scope in self.var_scopes)]
+
+    def _scope_restriction(self, base_flags: torch.Tensor):
+        """(segment flags, gradient mask) that keep the variables outside `var_scopes` untouched: their
+        gradients are zeroed and their segments flagged lazy-only, so the optimizer kernel skips every
+        one of their elements (moments included) and adds no regularisation term to them.  (The reported
+        L1 / L2 values then cover the trained variables only.)"""
+        if not hasattr(self, "_scope_state"):
+            arena = runtime.arena()
+            included = set(self.var_list)
+            keep = torch.tensor([1 if n in included else 0 for n in arena.train_names] or [0],
+                                dtype=torch.uint8, device=base_flags.device)
+            flags = torch.where(keep.bool(), base_flags, torch.full_like(base_flags, 2))
+            lengths = (arena.seg_off[1:] - arena.seg_off[:-1]).to(keep.device)
+            mask = torch.repeat_interleave(keep.to(torch.float32), lengths)
+            self._scope_state = (flags, mask)
+            self._excluded = [n for n in arena.train_names if n not in included]
+        return self._scope_state
 
     # -- one optimisation step ---------------------------------------------------------------
     def _backward(self) -> Dict[str, torch.Tensor]:
@@ -210,6 +230,9 @@ class GenericTrainer(GraphExecutor, Feedable):
                                     dtype=torch.uint8, device=arena.seg_reg.device)
                 self._lazy_flags = arena.seg_reg | lazy
             seg_flags = self._lazy_flags
+        if self.var_scopes is not None:
+            seg_flags, mask = self._scope_restriction(seg_flags)
+            arena.grads.mul_(mask)
         call("nm_clip_adam_step", ptr(arena.params), ptr(arena.grads), ptr(arena.adam_m),
              ptr(arena.adam_v), ptr(arena.seg_off), ptr(seg_flags), ptr(arena.seg_norms), n,
              len(arena.train_names), float(grad_scale), ptr(denominator), float(lr_t),

@@ -132,7 +132,7 @@ def adam_kernel(trainer, grad_scale, denominator, lr_t, lr_t_dev):
         trainer._l1l2_buf = torch.zeros(2)
     l1 = l2 = 0.0
     with torch.no_grad():
-        for name in arena.train_names:
+        for name in trainer.var_list:                 # with var_scopes: only the variables in scope
             var = arena.get(name)
             grad = arena.grad(name) * scale           # the trainer folded the autograd gradients in
             if O.is_regularizable(name):

@@ -93,3 +93,33 @@ def test_label_smoothing(tie, backend, tol, gtol):
         check_label_smoothing(tie, tol, gtol)
     finally:
         ops.set_gemm_backend("auto")
+
+
+def test_var_scopes_through_the_optimizer_kernel():
+    """var_scopes on the GPU: the variables outside the scopes keep their bits (values and Adam moments),
+    the ones inside move - the restriction rides on the kernel's lazy flag and a gradient mask."""
+    from neuralmonkey_b200 import ops, tf
+    from neuralmonkey_b200.trainers import CrossEntropyTrainer
+    from tests.helpers import build_bahdanau
+    try:
+        ops.set_gemm_backend("simt")
+        cfg = dict(vs=60, vt=70, es=11, he=7, et=9, hd=8, out=9, maxout=True, max_len=10, supress_unk=True)
+        model = build_bahdanau(**cfg)
+        scoped = CrossEntropyTrainer(decoders=[model["dec"]], optimizer=tf.AdamOptimizer(learning_rate=1e-2),
+                                     var_scopes=["decoder"], l2_weight=1e-3, clip_norm=1.0)
+        arena = model["arena"]
+        arena.load_dict(oracle_params_for(model))
+        src, tgt = random_batch(6, 8, 7, cfg["vs"], cfg["vt"], seed=0)
+        before = arena.state_dict()
+        for _ in range(2):
+            feed(model, src, tgt, train=True)
+            scoped.train_step()
+        after = arena.state_dict()
+        for name in arena.train_names:
+            if name.startswith("decoder"):
+                assert not torch.equal(before[name], after[name]), name
+            else:
+                assert torch.equal(before[name], after[name]), name
+        assert float(arena.adam_m.abs().sum()) > 0.0
+    finally:
+        ops.set_gemm_backend("auto")

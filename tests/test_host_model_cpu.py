@@ -691,3 +691,34 @@ batching=<batching>
     assert key in results["single"]
     assert abs(results["single"][key] - results["ensemble"][key]) < 1e-3 * max(1.0, abs(results["single"][key]))
     assert results["single"]["target_beam.rank001/BLEU-4"] == pytest.approx(results["ensemble"]["target_beam.rank001/BLEU-4"])
+
+
+def test_var_scopes_restrict_the_update(cpu_model, monkeypatch):
+    """GenericTrainer(var_scopes=[...]) (generic_trainer.py:196-205): only variables whose name starts
+    with one of the scopes are in `var_list` and move; the segment flags / gradient mask handed to the
+    optimizer kernel exclude exactly the others."""
+    from neuralmonkey_b200 import runtime, tf
+    from neuralmonkey_b200.trainers import CrossEntropyTrainer
+    from neuralmonkey_b200.trainers.generic_trainer import GenericTrainer
+    monkeypatch.setattr(GenericTrainer, "_adam_kernel", cpu_ops.adam_kernel)
+    model = build_bahdanau(**TOY)
+    scoped = CrossEntropyTrainer(decoders=[model["dec"]], optimizer=tf.AdamOptimizer(learning_rate=1e-2),
+                                 var_scopes=["decoder", "attention/attn_sim"])
+    arena = model["arena"]
+    arena.load_dict(oracle_params_for(model))
+    names = arena.train_names
+    assert scoped.var_list == [n for n in names if n.startswith("decoder") or n.startswith("attention/attn_sim")]
+    flags, mask = scoped._scope_restriction(arena.seg_reg)
+    for i, name in enumerate(names):
+        inside = name in scoped.var_list
+        assert int(flags[i]) == (int(arena.seg_reg[i]) if inside else 2), name
+        lo, hi = int(arena.seg_off[i]), int(arena.seg_off[i + 1])
+        assert float(mask[lo:hi].min()) == float(mask[lo:hi].max()) == (1.0 if inside else 0.0)
+    src, tgt = random_batch(6, 8, 7, TOY["vs"], TOY["vt"], seed=0)
+    before = arena.state_dict()
+    feed(model, src, tgt, train=True)
+    scoped.train_step()
+    after = arena.state_dict()
+    for name in names:
+        moved = not torch.equal(before[name], after[name])
+        assert moved == (name in scoped.var_list and not name.endswith("attn_bias")) or name.endswith("attn_bias"), name
