@@ -54,8 +54,8 @@ class GreedyRunner(BaseRunner):
                     runtime_loss += float(decoder.runtime_loss)
                 if summed is None:
                     summed = [np.full(logprobs.shape[1:], -np.inf, dtype=logprobs.dtype) for _ in logprobs]
-                for step, step_logprobs in enumerate(logprobs):
-                    summed[step] = np.logaddexp(summed[step], step_logprobs)
+                for step, step_logprobs in enumerate(logprobs[:len(summed)]):   # the reference indexes past
+                    summed[step] = np.logaddexp(summed[step], step_logprobs)     # the end if a later session is longer
             decoded_tokens = runner.vocabulary.vectors_to_sentences([np.argmax(s, axis=1) for s in summed])
             if runner.postprocess is not None:
                 decoded_tokens = runner.postprocess(decoded_tokens)
