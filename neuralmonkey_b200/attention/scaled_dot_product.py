@@ -11,7 +11,8 @@ from typing import Optional, Tuple
 import torch
 
 from neuralmonkey_b200 import ops
-from neuralmonkey_b200.nn.utils import dropout
+from neuralmonkey_b200.nn.utils import dropout, dropout_mask
+from neuralmonkey_b200.nn.variants import require_variant
 from neuralmonkey_b200.params import zeros_initializer
 
 
@@ -51,10 +52,13 @@ def attention(part, scope: str, queries: torch.Tensor, keys: torch.Tensor, value
 
     if num_heads > 1:
         queries, keys, values = proj(queries, "query_proj"), proj(keys, "keys_proj"), proj(values, "vals_proj")
+    drop = None
     if attention_dropout_keep_prob < 1.0 and train_mode:
-        raise NotImplementedError("attention dropout inside the fused attention core is not built; "
-                                  "set attention_dropout_keep_prob=1.0")
-    context, weights = ops.mha_core(queries, keys, values, keys_mask, masked, num_heads)
+        # dropout on the attention weights (:208-214), inside the fused core: the mask rides along
+        require_variant("attention_dropout_keep_prob < 1")
+        drop = dropout_mask((queries.shape[0], num_heads, queries.shape[1], keys.shape[1]),
+                            attention_dropout_keep_prob, train_mode, queries.device)
+    context, weights = ops.mha_core(queries, keys, values, keys_mask, masked, num_heads, drop)
     if num_heads > 1:
         context = proj(context, "output_proj")
     return context, weights

@@ -163,11 +163,16 @@ __device__ __forceinline__ void mt_load_head(float* dst, int pitch, const float*
   }
 }
 
-template <int NJ>
+// DROP: attention-weight dropout (scaled_dot_product.py:208-214: weights = dropout(softmax(E)), context =
+// weights . V).  `drop` is the mask already scaled by 1/keep_prob, [B, heads, Tq, Tk]; `probs` keeps the
+// UNdropped softmax, which is what the backward of the softmax needs.  A trailing parameter and a
+// template flag, so the instances without dropout are the code they were.
+template <int NJ, bool DROP = false>
 __global__ void __launch_bounds__(MT_THREADS)
 mha_fwd_tile_kernel(const float* __restrict__ q, const float* __restrict__ k, const float* __restrict__ v,
                     const float* __restrict__ key_mask, int causal, float* __restrict__ out,
-                    float* __restrict__ probs, int Tq, int Tk, int heads, int dh) {
+                    float* __restrict__ probs, int Tq, int Tk, int heads, int dh,
+                    const float* __restrict__ drop) {
   extern __shared__ float smem[];
   constexpr int TKP = 8 * NJ;
   const int kp = dh + 1;
@@ -223,7 +228,11 @@ mha_fwd_tile_kernel(const float* __restrict__ q, const float* __restrict__ k, co
   for (int jj = 0; jj < NJ; ++jj) {
     const int j = jg + 8 * jj;
     const float p = acc[jj] / sum;
-    Ps[i * (TKP + 1) + j] = p;
+    float pd = p;
+    if (DROP) {
+      if (i < nq && j < Tk) pd = p * drop[(((int64_t)b * heads + h) * Tq + tq) * Tk + j];
+    }
+    Ps[i * (TKP + 1) + j] = pd;
     if (i < nq && j < Tk) pr[j] = p;
   }
   __syncwarp();
@@ -247,12 +256,12 @@ mha_fwd_tile_kernel(const float* __restrict__ q, const float* __restrict__ k, co
 }
 
 // backward A (per block of query rows): dE -> de_out, dq
-template <int NJ>
+template <int NJ, bool DROP = false>
 __global__ void __launch_bounds__(MT_THREADS)
 mha_bwd_q_tile_kernel(const float* __restrict__ k, const float* __restrict__ v,
                       const float* __restrict__ key_mask, int causal, const float* __restrict__ probs,
                       const float* __restrict__ dout, float* __restrict__ dq, float* __restrict__ de_out,
-                      int Tq, int Tk, int heads, int dh) {
+                      int Tq, int Tk, int heads, int dh, const float* __restrict__ drop) {
   extern __shared__ float smem[];
   constexpr int TKP = 8 * NJ;
   const int kp = dh + 1;
@@ -281,6 +290,13 @@ mha_bwd_q_tile_kernel(const float* __restrict__ k, const float* __restrict__ v,
     const float ov = Os[i * kp + d];
 #pragma unroll
     for (int jj = 0; jj < NJ; ++jj) acc[jj] = fmaf(ov, Vs[(jg + 8 * jj) * kp + d], acc[jj]);
+  }
+  if (DROP) {   // d(dropped weights) -> d(softmax): times the same mask
+#pragma unroll
+    for (int jj = 0; jj < NJ; ++jj) {
+      const int j = jg + 8 * jj;
+      if (i < nq && j < Tk) acc[jj] *= drop[(((int64_t)b * heads + h) * Tq + tq) * Tk + j];
+    }
   }
   float dot = 0.f;
 #pragma unroll
@@ -321,10 +337,12 @@ mha_bwd_q_tile_kernel(const float* __restrict__ k, const float* __restrict__ v,
 }
 
 // backward B (per block of 32 key rows): dk, dv.  smem: Qs[Tq][dh] (scaled) | Os[Tq][dh] | Et[Tq][33] | Pt[Tq][33]
+template <bool DROP = false>
 __global__ void __launch_bounds__(MT_THREADS)
 mha_bwd_kv_tile_kernel(const float* __restrict__ q, const float* __restrict__ probs,
                        const float* __restrict__ de, const float* __restrict__ dout,
-                       float* __restrict__ dk, float* __restrict__ dv, int Tq, int Tk, int heads, int dh) {
+                       float* __restrict__ dk, float* __restrict__ dv, int Tq, int Tk, int heads, int dh,
+                       const float* __restrict__ drop) {
   extern __shared__ float smem[];
   float* Qs = smem;
   float* Os = Qs + Tq * dh;
@@ -342,7 +360,11 @@ mha_bwd_kv_tile_kernel(const float* __restrict__ q, const float* __restrict__ pr
     const int i = idx >> 5, jl = idx & 31;
     const bool ok = jl < nj;
     Et[i * 33 + jl] = ok ? eb[(int64_t)i * Tk + jl] : 0.f;
-    Pt[i * 33 + jl] = ok ? pb[(int64_t)i * Tk + jl] : 0.f;
+    float pv = ok ? pb[(int64_t)i * Tk + jl] : 0.f;
+    if (DROP) {   // dV sees the dropped weights
+      if (ok) pv *= drop[((int64_t)b * heads + h) * Tq * Tk + j0 + (int64_t)i * Tk + jl];
+    }
+    Pt[i * 33 + jl] = pv;
   }
   __syncthreads();
   const int jl = threadIdx.x >> 3, dg = threadIdx.x & 7;
@@ -393,9 +415,9 @@ using namespace nm;
 
 extern "C" {
 
-int nm_mha_fwd(const float* q, const float* k, const float* v, const float* key_mask, int causal,
-               float* out, float* probs, int64_t B, int64_t Tq, int64_t Tk, int64_t heads,
-               int64_t dh, void* stream) {
+static int mha_fwd_impl(const float* q, const float* k, const float* v, const float* key_mask, int causal,
+                        float* out, float* probs, int64_t B, int64_t Tq, int64_t Tk, int64_t heads,
+                        int64_t dh, const float* drop, void* stream) {
   NM_REQUIRE(q && k && v && out && probs, NM_E_INVALID, "nm_mha_fwd: null pointer");
   NM_REQUIRE(B > 0 && Tq > 0 && Tk > 0 && heads > 0 && dh > 0, NM_E_INVALID, "nm_mha_fwd: bad sizes");
   NM_REQUIRE(B <= 65535 && heads <= 65535, NM_E_UNSUPPORTED, "nm_mha_fwd: grid too large");
@@ -405,16 +427,25 @@ int nm_mha_fwd(const float* q, const float* k, const float* v, const float* key_
     cudaStream_t s = (cudaStream_t)stream;
 #define NM_MT_FWD(NJ)                                                                              \
   {                                                                                                \
-    int rc = mt_set_smem(mha_fwd_tile_kernel<NJ>, sm);                                             \
-    if (rc != NM_OK) return rc;                                                                    \
-    mha_fwd_tile_kernel<NJ><<<grid, MT_THREADS, sm, s>>>(q, k, v, key_mask, causal, out, probs,    \
-                                                         (int)Tq, (int)Tk, (int)heads, (int)dh);   \
+    if (drop) {                                                                                    \
+      int rc = mt_set_smem(mha_fwd_tile_kernel<NJ, true>, sm);                                     \
+      if (rc != NM_OK) return rc;                                                                  \
+      mha_fwd_tile_kernel<NJ, true><<<grid, MT_THREADS, sm, s>>>(q, k, v, key_mask, causal, out,   \
+          probs, (int)Tq, (int)Tk, (int)heads, (int)dh, drop);                                     \
+    } else {                                                                                       \
+      int rc = mt_set_smem(mha_fwd_tile_kernel<NJ>, sm);                                           \
+      if (rc != NM_OK) return rc;                                                                  \
+      mha_fwd_tile_kernel<NJ><<<grid, MT_THREADS, sm, s>>>(q, k, v, key_mask, causal, out, probs,  \
+          (int)Tq, (int)Tk, (int)heads, (int)dh, nullptr);                                         \
+    }                                                                                              \
   }
     if (Tk <= 64) NM_MT_FWD(8) else if (Tk <= 128) NM_MT_FWD(16) else NM_MT_FWD(32)
 #undef NM_MT_FWD
     NM_LAUNCH_CHECK("nm_mha_fwd(tile)");
     return NM_OK;
   }
+  NM_REQUIRE(!drop, NM_E_UNSUPPORTED, "nm_mha_fwd: attention dropout needs the tiled kernels "
+             "(dh %% 8 == 0, dh <= 128, 8 <= Tq <= 256, Tk <= 256)");
   const size_t smem = sizeof(float) * (size_t)(dh + Tk);
   NM_REQUIRE(smem <= 48 * 1024, NM_E_UNSUPPORTED, "nm_mha_fwd: Tk+dh too large for this kernel");
   dim3 grid((unsigned)Tq, (unsigned)heads, (unsigned)B);
@@ -425,10 +456,23 @@ int nm_mha_fwd(const float* q, const float* k, const float* v, const float* key_
   return NM_OK;
 }
 
-int nm_mha_bwd(const float* q, const float* k, const float* v, const float* key_mask, int causal,
-               const float* probs, const float* dout, float* dq, float* dk, float* dv,
-               float* de_work, int64_t B, int64_t Tq, int64_t Tk, int64_t heads, int64_t dh,
-               void* stream) {
+int nm_mha_fwd(const float* q, const float* k, const float* v, const float* key_mask, int causal,
+               float* out, float* probs, int64_t B, int64_t Tq, int64_t Tk, int64_t heads,
+               int64_t dh, void* stream) {
+  return mha_fwd_impl(q, k, v, key_mask, causal, out, probs, B, Tq, Tk, heads, dh, nullptr, stream);
+}
+
+int nm_mha_fwd_drop(const float* q, const float* k, const float* v, const float* key_mask, int causal,
+                    const float* drop_mask, float* out, float* probs, int64_t B, int64_t Tq, int64_t Tk,
+                    int64_t heads, int64_t dh, void* stream) {
+  NM_REQUIRE(drop_mask, NM_E_INVALID, "nm_mha_fwd_drop: null mask");
+  return mha_fwd_impl(q, k, v, key_mask, causal, out, probs, B, Tq, Tk, heads, dh, drop_mask, stream);
+}
+
+static int mha_bwd_impl(const float* q, const float* k, const float* v, const float* key_mask, int causal,
+                        const float* probs, const float* dout, float* dq, float* dk, float* dv,
+                        float* de_work, int64_t B, int64_t Tq, int64_t Tk, int64_t heads, int64_t dh,
+                        const float* drop, void* stream) {
   NM_REQUIRE(q && k && v && probs && dout && dq && dk && dv && de_work, NM_E_INVALID,
              "nm_mha_bwd: null pointer");
   NM_REQUIRE(B > 0 && Tq > 0 && Tk > 0 && heads > 0 && dh > 0, NM_E_INVALID, "nm_mha_bwd: bad sizes");
@@ -439,23 +483,38 @@ int nm_mha_bwd(const float* q, const float* k, const float* v, const float* key_
     dim3 gq((unsigned)((Tq + MT_QB - 1) / MT_QB), (unsigned)heads, (unsigned)B);
 #define NM_MT_BWD(NJ)                                                                                 \
   {                                                                                                   \
-    int rc = mt_set_smem(mha_bwd_q_tile_kernel<NJ>, sm);                                              \
-    if (rc != NM_OK) return rc;                                                                       \
-    mha_bwd_q_tile_kernel<NJ><<<gq, MT_THREADS, sm, s>>>(k, v, key_mask, causal, probs, dout, dq,      \
-                                                        de_work, (int)Tq, (int)Tk, (int)heads, (int)dh); \
+    if (drop) {                                                                                       \
+      int rc = mt_set_smem(mha_bwd_q_tile_kernel<NJ, true>, sm);                                      \
+      if (rc != NM_OK) return rc;                                                                     \
+      mha_bwd_q_tile_kernel<NJ, true><<<gq, MT_THREADS, sm, s>>>(k, v, key_mask, causal, probs, dout,  \
+          dq, de_work, (int)Tq, (int)Tk, (int)heads, (int)dh, drop);                                  \
+    } else {                                                                                          \
+      int rc = mt_set_smem(mha_bwd_q_tile_kernel<NJ>, sm);                                            \
+      if (rc != NM_OK) return rc;                                                                     \
+      mha_bwd_q_tile_kernel<NJ><<<gq, MT_THREADS, sm, s>>>(k, v, key_mask, causal, probs, dout, dq,    \
+          de_work, (int)Tq, (int)Tk, (int)heads, (int)dh, nullptr);                                   \
+    }                                                                                                 \
   }
     if (Tk <= 64) NM_MT_BWD(8) else if (Tk <= 128) NM_MT_BWD(16) else NM_MT_BWD(32)
 #undef NM_MT_BWD
     NM_LAUNCH_CHECK("nm_mha_bwd(q tile)");
     const size_t sk = mt_smem_kv(Tq, dh);
-    int rc = mt_set_smem(mha_bwd_kv_tile_kernel, sk);
-    if (rc != NM_OK) return rc;
     dim3 gk((unsigned)((Tk + MT_QB - 1) / MT_QB), (unsigned)heads, (unsigned)B);
-    mha_bwd_kv_tile_kernel<<<gk, MT_THREADS, sk, s>>>(q, probs, de_work, dout, dk, dv, (int)Tq, (int)Tk,
-                                                      (int)heads, (int)dh);
+    if (drop) {
+      int rc = mt_set_smem(mha_bwd_kv_tile_kernel<true>, sk);
+      if (rc != NM_OK) return rc;
+      mha_bwd_kv_tile_kernel<true><<<gk, MT_THREADS, sk, s>>>(q, probs, de_work, dout, dk, dv, (int)Tq,
+                                                              (int)Tk, (int)heads, (int)dh, drop);
+    } else {
+      int rc = mt_set_smem(mha_bwd_kv_tile_kernel<false>, sk);
+      if (rc != NM_OK) return rc;
+      mha_bwd_kv_tile_kernel<false><<<gk, MT_THREADS, sk, s>>>(q, probs, de_work, dout, dk, dv, (int)Tq,
+                                                               (int)Tk, (int)heads, (int)dh, nullptr);
+    }
     NM_LAUNCH_CHECK("nm_mha_bwd(kv tile)");
     return NM_OK;
   }
+  NM_REQUIRE(!drop, NM_E_UNSUPPORTED, "nm_mha_bwd: attention dropout needs the tiled kernels");
   const size_t smem = sizeof(float) * (size_t)(dh + Tk);
   NM_REQUIRE(smem <= 48 * 1024, NM_E_UNSUPPORTED, "nm_mha_bwd: Tk+dh too large for this kernel");
   dim3 grid_q((unsigned)Tq, (unsigned)heads, (unsigned)B);
@@ -467,6 +526,23 @@ int nm_mha_bwd(const float* q, const float* k, const float* v, const float* key_
                                                    (int)heads, (int)dh);
   NM_LAUNCH_CHECK("nm_mha_bwd(kv)");
   return NM_OK;
+}
+
+int nm_mha_bwd(const float* q, const float* k, const float* v, const float* key_mask, int causal,
+               const float* probs, const float* dout, float* dq, float* dk, float* dv,
+               float* de_work, int64_t B, int64_t Tq, int64_t Tk, int64_t heads, int64_t dh,
+               void* stream) {
+  return mha_bwd_impl(q, k, v, key_mask, causal, probs, dout, dq, dk, dv, de_work, B, Tq, Tk, heads, dh,
+                      nullptr, stream);
+}
+
+int nm_mha_bwd_drop(const float* q, const float* k, const float* v, const float* key_mask, int causal,
+                    const float* drop_mask, const float* probs, const float* dout, float* dq, float* dk,
+                    float* dv, float* de_work, int64_t B, int64_t Tq, int64_t Tk, int64_t heads,
+                    int64_t dh, void* stream) {
+  NM_REQUIRE(drop_mask, NM_E_INVALID, "nm_mha_bwd_drop: null mask");
+  return mha_bwd_impl(q, k, v, key_mask, causal, probs, dout, dq, dk, dv, de_work, B, Tq, Tk, heads, dh,
+                      drop_mask, stream);
 }
 
 }  // extern "C"

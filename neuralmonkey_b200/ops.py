@@ -670,9 +670,46 @@ class _MHA(torch.autograd.Function):
         return dq, dk, dv, None, None, None
 
 
+class _MHADrop(torch.autograd.Function):
+    """_MHA with attention-weight dropout: `drop_mask` [B, heads, Tq, Tk] holds 0 or 1/keep_prob."""
+
+    @staticmethod
+    def forward(ctx, q, k, v, key_mask, causal, heads, drop_mask):
+        bsz, tq, d = q.shape
+        tk = k.size(1)
+        q, k, v = q.contiguous(), k.contiguous(), v.contiguous()
+        mask_c = key_mask.contiguous() if key_mask is not None else None
+        drop_c = drop_mask.to(torch.float32).contiguous()
+        out = torch.empty_like(q)
+        probs = torch.empty(bsz, heads, tq, tk, device=q.device, dtype=torch.float32)
+        call("nm_mha_fwd_drop", ptr(q), ptr(k), ptr(v), ptr(mask_c), int(causal), ptr(drop_c), ptr(out),
+             ptr(probs), bsz, tq, tk, heads, d // heads, lib.stream())
+        ctx.save_for_backward(q, k, v, mask_c, probs, drop_c)
+        ctx.cfg = (causal, heads)
+        ctx.mark_non_differentiable(probs)
+        return out, probs
+
+    @staticmethod
+    def backward(ctx, dout, _dprobs):
+        q, k, v, mask, probs, drop_c = ctx.saved_tensors
+        causal, heads = ctx.cfg
+        bsz, tq, d = q.shape
+        tk = k.size(1)
+        dout = dout.contiguous()
+        dq, dk, dv = torch.empty_like(q), torch.empty_like(k), torch.empty_like(v)
+        work = torch.empty_like(probs)
+        call("nm_mha_bwd_drop", ptr(q), ptr(k), ptr(v), ptr(mask), int(causal), ptr(drop_c), ptr(probs),
+             ptr(dout), ptr(dq), ptr(dk), ptr(dv), ptr(work), bsz, tq, tk, heads, d // heads, lib.stream())
+        return dq, dk, dv, None, None, None, None
+
+
 def mha_core(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, key_mask: Optional[torch.Tensor],
-             causal: bool, heads: int) -> Tuple[torch.Tensor, torch.Tensor]:
-    """softmax(mask(q/sqrt(dh) k^T)) v per head (attention/scaled_dot_product.py:184-214)."""
+             causal: bool, heads: int, drop_mask: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+    """softmax(mask(q/sqrt(dh) k^T)) v per head (attention/scaled_dot_product.py:184-214).  With
+    `drop_mask` ([B, heads, Tq, Tk], 0 or 1/keep_prob) the context is (softmax * drop_mask) v; the
+    returned weights are the undropped softmax."""
+    if drop_mask is not None:
+        return _MHADrop.apply(q, k, v, key_mask, causal, heads, drop_mask)
     return _MHA.apply(q, k, v, key_mask, causal, heads)
 
 

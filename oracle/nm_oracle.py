@@ -498,8 +498,10 @@ def _split_for_heads(x: torch.Tensor, heads: int, head_dim: int) -> torch.Tensor
 
 
 def multihead_attention(p: Params, scope: str, queries, keys, values, keys_mask, heads: int,
-                        masked: bool = False, use_bias: bool = False):
-    """attention() (scaled_dot_product.py:98-226); dropout callback = identity."""
+                        masked: bool = False, use_bias: bool = False, drop_mask=None):
+    """attention() (scaled_dot_product.py:98-226).  The dropout callback is the identity, or - with
+    `drop_mask` [B, heads, Tq, Tk] holding 0 or 1/keep_prob - a multiplication of the softmax weights
+    by that mask before they are applied to the values (:208-214)."""
     dim = queries.shape[-1]
     head_dim = dim // heads
 
@@ -521,6 +523,8 @@ def multihead_attention(p: Params, scope: str, queries, keys, values, keys_mask,
         m = keys_mask.to(energies.dtype).unsqueeze(1).unsqueeze(1)
         energies = energies * m + (1.0 - m) * -INF
     weights = torch.softmax(energies, dim=-1)
+    if drop_mask is not None:
+        weights = weights * drop_mask
     context = (weights @ v).permute(0, 2, 1, 3).reshape(queries.shape[0], queries.shape[1], dim)
     if heads > 1:
         context = dense(context, "output_proj")

@@ -75,7 +75,7 @@ def log_softmax_from_lse(logits, lse):
     return logits - lse.unsqueeze(-1)
 
 
-def mha_core(q, k, v, key_mask, causal, heads):
+def mha_core(q, k, v, key_mask, causal, heads, drop_mask=None):
     bsz, tq, dim = q.shape
     tk, dh = k.shape[1], dim // heads
 
@@ -89,7 +89,8 @@ def mha_core(q, k, v, key_mask, causal, heads):
         m = key_mask.unsqueeze(1).unsqueeze(1)
         energies = energies * m + (1.0 - m) * -1e9
     weights = torch.softmax(energies, dim=-1)
-    return (weights @ split(v)).transpose(1, 2).reshape(bsz, tq, dim), weights
+    applied = weights if drop_mask is None else weights * drop_mask
+    return (applied @ split(v)).transpose(1, 2).reshape(bsz, tq, dim), weights
 
 
 def beam_step(logprobs, logprob_sum, lengths, finished, alpha):

@@ -59,6 +59,13 @@ def main():
     smask = np.array([[1, 1, 1, 1, 0, 0], [1, 1, 1, 1, 1, 1]], np.float32)
     ctx, weights = sdp.attention(shim.t(qs), shim.t(qs), shim.t(qs), shim.t(smask), 3, lambda x: x, masked=True)
     out.update({"self_q": qs, "self_mask": smask, "self_ctx": np.asarray(ctx), "self_w": np.asarray(weights)})
+    # attention-weight dropout: the callback receives the softmax weights; here it applies a FIXED mask
+    # (0 or 1/keep_prob), so that where the dropout sits is pinned without a random stream
+    drop_rng = np.random.RandomState(3)
+    drop = (drop_rng.rand(2, 3, 6, 6) < 0.7).astype(np.float32) / 0.7
+    ctx, weights = sdp.attention(shim.t(qs), shim.t(qs), shim.t(qs), shim.t(smask), 3,
+                                 lambda w: shim.t(np.asarray(w) * drop), masked=True)
+    out.update({"drop_mask": drop, "drop_ctx": np.asarray(ctx), "drop_w": np.asarray(weights)})
 
     # ---- tf_utils ------------------------------------------------------------------------------------
     from neuralmonkey import tf_utils

@@ -722,3 +722,32 @@ def test_var_scopes_restrict_the_update(cpu_model, monkeypatch):
     for name in names:
         moved = not torch.equal(before[name], after[name])
         assert moved == (name in scoped.var_list and not name.endswith("attn_bias")) or name.endswith("attn_bias"), name
+
+
+def test_attention_dropout_rides_into_the_fused_core(cpu_model, monkeypatch):
+    """attention(..., attention_dropout_keep_prob < 1) in train mode: the mask drawn for the weights
+    [batch, heads, time_q, time_k] is handed to the attention core, which applies it between the softmax
+    and the values - against the oracle with the same mask (whose placement is pinned to the reference)."""
+    import types
+    from neuralmonkey_b200.attention import scaled_dot_product as sdp
+    g = torch.Generator().manual_seed(4)
+    dim, heads = 12, 3
+    kernels = {n: torch.randn(dim, dim, generator=g) * 0.3 for n in ("query_proj", "keys_proj", "vals_proj", "output_proj")}
+    part = types.SimpleNamespace(var=lambda name: kernels[name.split("/")[1]].requires_grad_(True), train_mode=True)
+    q, k = torch.randn(2, 5, dim, generator=g), torch.randn(2, 7, dim, generator=g)
+    key_mask = torch.tensor([[1, 1, 1, 1, 1, 0, 0], [1, 1, 1, 0, 0, 0, 0]], dtype=torch.float32)
+    mask = (torch.rand(2, heads, 5, 7, generator=g) < 0.8).float() / 0.8
+    seen = {}
+
+    def fixed_mask(shape, keep_prob, train_mode, device):
+        seen["shape"], seen["keep"] = tuple(shape), keep_prob
+        return mask
+    monkeypatch.setattr(sdp, "dropout_mask", fixed_mask)
+    ctx, _w = sdp.attention(part, "s", q, k, k, key_mask, heads, False, 0.8, True, False)
+    assert seen == {"shape": (2, heads, 5, 7), "keep": 0.8}
+    p = {"s/{}/kernel".format(n): v.detach() for n, v in kernels.items()}
+    want, _ = O.multihead_attention(p, "s", q, k, k, key_mask, heads, drop_mask=mask)
+    assert max_abs(ctx, want) < 1e-5
+    # evaluation mode: no mask at all
+    ctx_eval, _ = sdp.attention(part, "s", q, k, k, key_mask, heads, False, 0.8, False, False)
+    assert max_abs(ctx_eval, O.multihead_attention(p, "s", q, k, k, key_mask, heads)[0]) < 1e-5

@@ -52,6 +52,12 @@ def test_multi_head_cross_and_masked_self_attention():
     ctx, weights = O.multihead_attention(p, "s", qs, qs, qs, _t("self_mask"), heads=3, masked=True)
     assert np.abs(ctx.numpy() - G["self_ctx"]).max() < 5e-6
     assert np.abs(weights.numpy() - G["self_w"]).max() < 2e-6
+    # dropout on the attention weights (:208-214): after the softmax, before the values; the reference
+    # returns the DROPPED weights
+    ctx, weights = O.multihead_attention(p, "s", qs, qs, qs, _t("self_mask"), heads=3, masked=True,
+                                         drop_mask=_t("drop_mask"))
+    assert np.abs(ctx.numpy() - G["drop_ctx"]).max() < 5e-6
+    assert np.abs(weights.numpy() - G["drop_w"]).max() < 2e-6
 
 
 def test_layer_norm_and_maxout():
