@@ -164,3 +164,26 @@ def test_arena_folds_gradients_left_by_plain_autograd():
     assert arena.fold_autograd_grads() == 1
     assert kernel.grad is None and torch.equal(arena.grad("a/kernel"), torch.full((3, 4), 3.0))
     assert arena.fold_autograd_grads() == 0
+
+
+def test_checkpoint_averaging_script(tmp_path):
+    """scripts/avg_checkpoints.py (the reference's command line): the mean of every variable."""
+    import subprocess
+    import sys
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    paths = []
+    for i in range(3):
+        path = str(tmp_path / "variables.data.{}".format(i))
+        torch.save({"variables": {"a/kernel": torch.full((2, 3), float(i)), "a/bias": torch.arange(3.0) * i},
+                    "adam_m": {}, "adam_v": {}}, path)
+        paths.append(path)
+    out = str(tmp_path / "variables.data.avg")
+    res = subprocess.run([sys.executable, os.path.join(root, "scripts", "avg_checkpoints.py")] + paths + [out],
+                         capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr
+    avg = torch.load(out)["variables"]
+    assert torch.equal(avg["a/kernel"], torch.full((2, 3), 1.0)) and torch.equal(avg["a/bias"], torch.arange(3.0))
+    res = subprocess.run([sys.executable, os.path.join(root, "scripts", "avg_checkpoints.py"),
+                          str(tmp_path / "nope"), out], capture_output=True, text=True)
+    assert res.returncode != 0 and "do not exist" in res.stderr
