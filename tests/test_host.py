@@ -187,3 +187,57 @@ def test_checkpoint_averaging_script(tmp_path):
     res = subprocess.run([sys.executable, os.path.join(root, "scripts", "avg_checkpoints.py"),
                           str(tmp_path / "nope"), out], capture_output=True, text=True)
     assert res.returncode != 0 and "do not exist" in res.stderr
+
+
+_DP_WORKER = r"""
+import os, sys, torch
+sys.path.insert(0, {root!r})
+from neuralmonkey_b200 import distributed, ops, runtime
+from neuralmonkey_b200.trainers.generic_trainer import GenericTrainer
+from tests import cpu_ops
+from tests.helpers import build_bahdanau, feed, oracle_params_for, random_batch
+for name in cpu_ops.STAND_INS:
+    setattr(ops, name, getattr(cpu_ops, name))
+runtime._device = torch.device("cpu")
+GenericTrainer._adam_kernel = cpu_ops.adam_kernel
+world = int(os.environ.get("WORLD_SIZE", "1"))
+if world > 1:
+    distributed.init_from_env(backend="gloo")
+cfg = dict(vs=60, vt=70, es=11, he=7, et=9, hd=8, out=9, maxout=True, max_len=10, supress_unk=True)
+model = build_bahdanau(**cfg, lr=1e-2, clip=1.0, l2=1e-3)
+model["arena"].load_dict(oracle_params_for(model))
+losses = []
+for step in range(3):
+    src, tgt = random_batch(8, 8, 7, cfg["vs"], cfg["vt"], seed=40 + step)
+    if world > 1:                         # every rank takes its slice of the SAME global batch
+        lo, hi = distributed.shard_bounds(8, world)[distributed.rank():distributed.rank() + 2]
+        src, tgt = src[lo:hi], tgt[lo:hi]
+    feed(model, src, tgt, train=True)
+    losses.append(float(model["trainer"].train_step()["losses"][0]))
+if distributed.rank() == 0:
+    torch.save({{"params": model["arena"].state_dict(), "losses": losses}}, {out!r} + str(world))
+print("rank", distributed.rank(), "done")
+"""
+
+
+def test_two_rank_data_parallel_training_equals_the_single_process_run(tmp_path):
+    """the global batch split by sentence over 2 ranks (gloo, CPU stand-in ops), un-normalised
+    loss sums and token counts all-reduced with the gradients, the division by the GLOBAL count inside the
+    optimizer step - three steps give the losses and parameters of one process on the whole batch."""
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    script = tmp_path / "dp_worker.py"
+    script.write_text(_DP_WORKER.format(root=root, out=str(tmp_path / "result")))
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1")
+    single = subprocess.run([sys.executable, str(script)], capture_output=True, text=True, timeout=300,
+                            env=dict(env, WORLD_SIZE="1"), cwd=root)
+    assert single.returncode == 0, single.stdout + single.stderr
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+           "--master-addr", "127.0.0.1", "--master-port", "29613", str(script)]
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=300, env=env, cwd=root)
+    assert res.returncode == 0, res.stdout + res.stderr
+    one, two = torch.load(str(tmp_path / "result1")), torch.load(str(tmp_path / "result2"))
+    assert one["losses"] == pytest.approx(two["losses"], abs=1e-5)
+    for name, want in one["params"].items():
+        if name.endswith("attn_bias"):
+            continue
+        assert float((two["params"][name] - want).abs().max()) < 2e-5, name
