@@ -241,3 +241,44 @@ def test_two_rank_data_parallel_training_equals_the_single_process_run(tmp_path)
         if name.endswith("attn_bias"):
             continue
         assert float((two["params"][name] - want).abs().max()) < 2e-5, name
+
+
+_DP_CLI_WORKER = r"""
+import os, sys, torch
+sys.path.insert(0, {root!r})
+from neuralmonkey_b200 import ops, runtime
+from neuralmonkey_b200.trainers.generic_trainer import GenericTrainer
+from tests import cpu_ops
+for name in cpu_ops.STAND_INS:
+    setattr(ops, name, getattr(cpu_ops, name))
+runtime._device = torch.device("cpu")
+GenericTrainer._adam_kernel = cpu_ops.adam_kernel
+sys.argv = ["neuralmonkey-train", {ini!r}]
+from neuralmonkey_b200.train import main
+main()
+"""
+
+
+def test_two_rank_training_through_the_entry_point(tmp_path):
+    """`torchrun --nproc-per-node 2 neuralmonkey-train INI` (gloo, CPU stand-in ops): every rank takes its
+    share of each batch, rank 0 alone logs, validates and writes the checkpoints and outputs."""
+    from tests import test_gpu_cli as cli
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    data, out = str(tmp_path / "data"), str(tmp_path / "out")
+    cli._write_data(data)
+    ini = tmp_path / "exp.ini"
+    ini.write_text(cli.INI.format(out=out, data=data, epochs=2))
+    script = tmp_path / "worker.py"
+    script.write_text(_DP_CLI_WORKER.format(root=root, ini=str(ini)))
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", NEURALMONKEY_STRICT="1")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+           "--master-addr", "127.0.0.1", "--master-port", "29617", str(script)]
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env, cwd=root)
+    assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
+    log_text = open(os.path.join(out, "experiment.log")).read()
+    assert "Validation (epoch" in log_text and "Training finished" in log_text
+    losses = [float(line.split("train_xent: ")[1].split()[0]) for line in log_text.splitlines()
+              if " train " in line and "train_xent: " in line]
+    assert len(losses) >= 2 and losses[-1] < losses[0], losses
+    assert len(open(os.path.join(out, "val.out")).read().splitlines()) == 30
+    assert os.path.exists(os.path.join(out, "variables.data.final"))
