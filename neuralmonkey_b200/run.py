@@ -1,11 +1,17 @@
-"""neuralmonkey-run entry point (behaviour of neuralmonkey/run.py:14-92)."""
+"""neuralmonkey-run entry point (behaviour of neuralmonkey/run.py:14-92): load a trained experiment,
+read a second INI naming the test datasets (and optionally the variable files), decode / evaluate each
+dataset, optionally dump the evaluation results as JSON."""
 import argparse
 import json
 import os
+from typing import Any, Dict, List, Optional
 
 from neuralmonkey_b200.config.configuration import Configuration
+from neuralmonkey_b200.dataset import Dataset
 from neuralmonkey_b200.experiment import Experiment
 from neuralmonkey_b200.logging import log
+
+_SGE_VARIABLES = ("SGE_TASK_FIRST", "SGE_TASK_LAST", "SGE_TASK_STEPSIZE", "SGE_TASK_ID")
 
 
 def load_runtime_config(config_path: str) -> Configuration:
@@ -18,44 +24,54 @@ def load_runtime_config(config_path: str) -> Configuration:
     return cfg
 
 
+def _cli() -> argparse.ArgumentParser:
+    cli = argparse.ArgumentParser(description="Runs a model on the given datasets.")
+    cli.add_argument("config", metavar="INI-FILE", help="the configuration file of the experiment")
+    cli.add_argument("datasets", metavar="INI-TEST-DATASETS", help="the configuration of the test datasets")
+    cli.add_argument("--json", type=str, help="write the evaluation results to this file")
+    cli.add_argument("-g", "--grid", dest="grid", action="store_true",
+                     help="look at the SGE variables for slicing the data")
+    return cli
+
+
+def _grid_slice(dataset: Dataset) -> Dataset:
+    """The part of the dataset this Sun Grid Engine array task is responsible for."""
+    if any(name not in os.environ for name in _SGE_VARIABLES):
+        raise EnvironmentError("Some SGE environment variables are missing")
+    step = int(os.environ["SGE_TASK_STEPSIZE"])
+    first = int(os.environ["SGE_TASK_ID"]) - 1
+    last = int(os.environ["SGE_TASK_LAST"]) - 1
+    length = min(step, last - first + 1) if first + step > last else step
+    log("Running grid task {} starting at {} with step {}".format(first // length, first, length))
+    return dataset.subset(first, length)
+
+
 def main() -> None:
-    parser = argparse.ArgumentParser(description="Runs a model on the given datasets.")
-    parser.add_argument("config", metavar="INI-FILE", help="the configuration file of the experiment")
-    parser.add_argument("datasets", metavar="INI-TEST-DATASETS",
-                        help="the configuration of the test datasets")
-    parser.add_argument("--json", type=str, help="write the evaluation results to this file")
-    parser.add_argument("-g", "--grid", dest="grid", action="store_true",
-                        help="look at the SGE variables for slicing the data")
-    args = parser.parse_args()
+    args = _cli().parse_args()
     exp = Experiment(config_path=args.config)
     exp.build_model()
-    datasets_model = load_runtime_config(args.datasets)
-    exp.load_variables(datasets_model.model.variables)
-    test_datasets = datasets_model.model.test_datasets
-    if args.grid and len(test_datasets) > 1:
+    runtime_cfg = load_runtime_config(args.datasets)
+    exp.load_variables(runtime_cfg.model.variables)
+    datasets = runtime_cfg.model.test_datasets
+    if args.grid and len(datasets) > 1:
         raise ValueError("Only one test dataset supported when using --grid")
-    results = []
-    for dataset in test_datasets:
+    batch_size = exp.config.args.batch_size
+    results = []  # type: List[Dict[str, Any]]
+    for dataset in datasets:
         if args.grid:
-            if "SGE_TASK_FIRST" not in os.environ or "SGE_TASK_LAST" not in os.environ \
-                    or "SGE_TASK_STEPSIZE" not in os.environ or "SGE_TASK_ID" not in os.environ:
-                raise EnvironmentError("Some SGE environment variables are missing")
-            length = int(os.environ["SGE_TASK_STEPSIZE"])
-            start = int(os.environ["SGE_TASK_ID"]) - 1
-            end = int(os.environ["SGE_TASK_LAST"]) - 1
-            if start + length > end:
-                length = end - start + 1
-            log("Running grid task {} starting at {} with step {}".format(
-                start // length, start, length))
-            dataset = dataset.subset(start, length)
+            dataset = _grid_slice(dataset)
         if exp.config.args.evaluation is None:
-            exp.run_model(dataset, write_out=True, batch_size=exp.config.args.batch_size)
+            exp.run_model(dataset, write_out=True, batch_size=batch_size)
         else:
-            results.append(exp.evaluate(dataset, write_out=True, batch_size=exp.config.args.batch_size))
-    if args.json:
-        with open(args.json, "w") as f_out:
-            json.dump(results, f_out)
-            f_out.write("\n")
+            results.append(exp.evaluate(dataset, write_out=True, batch_size=batch_size))
+    _dump(results, args.json)
+
+
+def _dump(results: List[Dict[str, Any]], path: Optional[str]) -> None:
+    if path:
+        with open(path, "w") as handle:
+            json.dump(results, handle)
+            handle.write("\n")
 
 
 if __name__ == "__main__":
