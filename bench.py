@@ -280,8 +280,12 @@ def run_b200(args):
         mm = re.match(r"nm_gemm\[(\w\w) (\d+)x(\d+)x(\d+)\]", name)
         if mm:
             fl = 2.0 * int(mm.group(2)) * int(mm.group(3)) * int(mm.group(4))
-        elif name in ("nm_logits_xent_fwd", "nm_logits_xent_bwd"):
+        elif name in ("nm_logits_xent_fwd", "nm_logits_xent_bwd", "nm_logits_xent_fwd16", "nm_logits_xent_bwd16"):
             fl = 2.0 * m * k * v
+        else:
+            mm = re.match(r"nm_gemm_f16\[(\d+)x(\d+)x(\d+)\]", name)     # NMB200_XENT16=1: kind::f16 instances
+            if mm:
+                fl = 2.0 * int(mm.group(1)) * int(mm.group(2)) * int(mm.group(3))
         if fl is None:
             continue
         calls = d["calls"]
@@ -289,7 +293,8 @@ def run_b200(args):
         fam_ms += d["ms"]
         instances.append({"call": name, "launches_per_step": calls // prof_steps,
                           "ms_per_launch": d["ms"] / calls, "tflops": fl / (d["ms"] / calls * 1e-3) / 1e12,
-                          "traffic": XENT_TRAFFIC.get(name)})
+                          "traffic": XENT_TRAFFIC.get(name),
+                          "kind": "f16" if ("16" in name.split("[")[0]) else "tf32"})
     instances.sort(key=lambda e: -e["ms_per_launch"] * e["launches_per_step"])
     roof = None
     if fam_ms > 0:
