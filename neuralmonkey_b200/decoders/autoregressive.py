@@ -131,6 +131,12 @@ class AutoregressiveDecoder(ModelPart):
     def _unk_index(self) -> int:
         return UNK_TOKEN_INDEX if self.supress_unk else -1
 
+    @property
+    def _train_unk_index(self) -> int:
+        """The <unk> column suppressed in the TRAINING logits: the same as at run time for decoders whose
+        training pass goes through get_body (autoregressive.py:450-459)."""
+        return self._unk_index
+
     # -- feeding -------------------------------------------------------------------------
     @property
     def input_types(self) -> Dict[str, Any]:
@@ -240,15 +246,15 @@ class AutoregressiveDecoder(ModelPart):
             flat = states.reshape(bsz * steps, dim)
             every = torch.ones(bsz * steps, device=flat.device, dtype=torch.float32)
             plain, lse, argmax, _ = ops.logits_xent(flat, self.decoding_w, self.decoding_b,
-                                                    targets.reshape(-1), every, self._unk_index,
+                                                    targets.reshape(-1), every, self._train_unk_index,
                                                     self._w_transposed)
             term = ops.smoothing_term(flat, self.decoding_w, self.decoding_b, targets.reshape(-1),
-                                      self._unk_index, self._w_transposed)
+                                      self._train_unk_index, self._w_transposed)
             scalar = (plain + float(self.label_smoothing) * term).mean()
             return scalar * weights, lse.view(bsz, steps), argmax.view(bsz, steps)
         xent, lse, argmax, _ = ops.logits_xent(
             states.reshape(bsz * steps, dim), self.decoding_w, self.decoding_b,
-            targets.reshape(-1), weights.reshape(-1), self._unk_index, self._w_transposed)
+            targets.reshape(-1), weights.reshape(-1), self._train_unk_index, self._w_transposed)
         return xent.view(bsz, steps), lse.view(bsz, steps), argmax.view(bsz, steps)
 
     @tensor
@@ -279,7 +285,7 @@ class AutoregressiveDecoder(ModelPart):
             states.reshape(bsz * steps, dim), self.decoding_w.detach(),
             self.decoding_b.detach() if self.decoding_b is not None else None,
             self._train_targets_bm[:, :steps].reshape(-1),
-            self._train_mask_bm[:, :steps].reshape(-1), self._unk_index, self._w_transposed,
+            self._train_mask_bm[:, :steps].reshape(-1), self._train_unk_index, self._w_transposed,
             keep_logits=True)
         return logits.view(bsz, steps, -1).transpose(0, 1)
 

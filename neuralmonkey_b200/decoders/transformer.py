@@ -162,6 +162,12 @@ class TransformerDecoder(AutoregressiveDecoder):
         return scoped_layer_norm(self, "", states)
 
     # -- training -----------------------------------------------------------------------------
+    @property
+    def _train_unk_index(self) -> int:
+        """train_loop_result computes the training logits itself (decoders/transformer.py:409-419) and
+        never adds the -1e9 <unk> column; `supress_unk` only acts in the run-time loops."""
+        return -1
+
     @tensor
     def train_input_symbols(self) -> torch.Tensor:
         """[batch, time]: <s> followed by the gold symbols but the last (:258-268)."""

@@ -626,13 +626,16 @@ def transformer_decoder_stack(p: Params, spec: TransformerDecoderSpec, inputs, m
     return _scoped_ln(p, spec.prefix, x)
 
 
-def transformer_logits(p: Params, spec: TransformerDecoderSpec, states: torch.Tensor) -> torch.Tensor:
-    """decoding_w / decoding_b (autoregressive.py:228-243) + supress_unk (:450-459)."""
+def transformer_logits(p: Params, spec: TransformerDecoderSpec, states: torch.Tensor,
+                       training: bool = False) -> torch.Tensor:
+    """decoding_w / decoding_b (autoregressive.py:228-243) + supress_unk (:450-459).  The -1e9 <unk>
+    column belongs to get_body's state_to_logits, i.e. to the run-time loops; the Transformer's training
+    pass computes its logits itself (decoders/transformer.py:409-419) and never adds it (`training`)."""
     if spec.tie_embeddings:
         logits = states @ p[spec.prefix + "/word_embeddings"].t()
     else:
         logits = states @ p[spec.prefix + "/state_to_word_W"] + p[spec.prefix + "/state_to_word_b"]
-    if spec.supress_unk:
+    if spec.supress_unk and not training:
         pen = torch.zeros(logits.shape[-1], dtype=logits.dtype)
         pen[UNK] = -INF
         logits = logits + pen
@@ -650,7 +653,7 @@ def transformer_decoder_train(p: Params, spec: TransformerDecoderSpec, enc: Dict
     inputs = emb[torch.cat([go, tgt_ids[:, :-1]], dim=1)]
     mask = (tgt_ids != PAD).to(emb.dtype)
     states = transformer_decoder_stack(p, spec, inputs, mask, enc["states"], enc["mask"])
-    logits = transformer_logits(p, spec, states)
+    logits = transformer_logits(p, spec, states, training=True)
     xent = sequence_xents(logits, tgt_ids, mask, label_smoothing)
     return {"states": states, "logits": logits, "xents": xent, "loss": xent.sum() / mask.sum(),
             "loss_sum": xent.sum(), "count": mask.sum()}

@@ -227,6 +227,16 @@ def main():
     out["tloop_train_logits"] = np.asarray(train_ls.histories.logits)
     out["tloop_train_states"] = np.asarray(train_ls.histories.output_states)
     out["tloop_train_input_symbols"] = np.asarray(dec.train_input_symbols)
+    # supress_unk: the training pass computes its logits itself (:409-419) and never adds the -1e9 <unk>
+    # column that get_body's state_to_logits adds at run time (autoregressive.py:454-457)
+    unk_dec = object.__new__(TransformerDecoder)
+    unk_dec.__dict__.update({k: v for k, v in dec.__dict__.items() if not k.endswith("_cached_placeholder")
+                             or k in ("_embedding_matrix_cached_placeholder", "_go_symbols_cached_placeholder",
+                                      "_train_inputs_cached_placeholder")})
+    unk_dec.supress_unk = True
+    out["tloop_unk_train_logits"] = np.asarray(unk_dec.train_loop_result.histories.logits)
+    unk_run = unk_dec.decoding_loop(train_mode=False)
+    out["tloop_unk_run_logits"] = np.asarray(unk_run.histories.logits)
     run_ls = dec.decoding_loop(train_mode=False)
     out["tloop_run_logits"] = np.asarray(run_ls.histories.logits)
     out["tloop_run_symbols"] = np.asarray(run_ls.histories.output_symbols)

@@ -565,3 +565,18 @@ def test_multi_source_cross_attention_strategies(strategy):
     assert scopes == {"serial": {"enc_0", "enc_1"}, "parallel": {"enc_0", "enc_1"},
                       "flat": {"keys_proj", "output_proj", "query_proj", "vals_proj"},
                       "hierarchical": {"enc_0", "enc_1", "enc_hier"}}[strategy]
+
+
+def test_transformer_training_logits_ignore_supress_unk():
+    """supress_unk lives in get_body's state_to_logits (autoregressive.py:454-457): the Transformer's
+    training pass computes its logits itself and carries no -1e9 <unk> column, its run-time loop does."""
+    p, spec, enc = _transformer_setup()
+    spec.supress_unk = True
+    gold = torch.from_numpy(G["tloop_gold"]).t().contiguous()
+    train = O.transformer_decoder_train(p, spec, enc, gold)
+    assert np.abs(train["logits"].transpose(0, 1).numpy() - G["tloop_unk_train_logits"]).max() < 5e-5
+    assert np.array_equal(G["tloop_unk_train_logits"], G["tloop_train_logits"])
+    run = O.transformer_decoder_greedy(p, spec, enc)
+    keep = np.arange(G["tloop_unk_run_logits"].shape[-1]) != O.UNK
+    assert np.abs(run["logits"].numpy()[..., keep] - G["tloop_unk_run_logits"][..., keep]).max() < 5e-5
+    assert float(G["tloop_unk_run_logits"][..., O.UNK].max()) < -1e8 and float(run["logits"][..., O.UNK].max()) < -1e8
