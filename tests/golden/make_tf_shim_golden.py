@@ -715,6 +715,39 @@ def main():
             out["mv::" + vname] = shim.VARIABLES[vname]
     shim.AUTO[0] = None
 
+    # ---- TransformerEncoder with its options: target-space embedding, projection biases, no position signal,
+    #      cross-attention to another encoder (encoders/transformer.py:170-330); variables drawn on demand --------
+    tx_in = f32(3, 6, dim)
+    tx_mask = np.array([[1, 1, 1, 1, 1, 1], [1, 1, 1, 1, 0, 0], [1, 1, 0, 0, 0, 0]], np.float32)
+    tx_other, tx_other_mask = f32(3, 4, dim), np.array([[1, 1, 1, 0], [1, 1, 1, 1], [1, 0, 0, 0]], np.float32)
+    out.update({"tx_in": tx_in, "tx_mask": tx_mask, "tx_other": tx_other, "tx_other_mask": tx_other_mask})
+    from neuralmonkey.model.stateful import TemporalStateful
+
+    class _OtherEncoder(TemporalStateful):
+        temporal_states = property(lambda self: shim.t(tx_other))
+        temporal_mask = property(lambda self: shim.t(tx_other_mask))
+
+    shim.AUTO[0] = np.random.RandomState(29)
+    tf_mod = sys.modules["tensorflow"]
+    tf_mod.gather = lambda params, indices: shim.t(np.asarray(params)[int(np.asarray(indices))])
+    tf_mod.variance_scaling_initializer = lambda *a, **k: None
+    for case, opts in (("space", dict(target_space_id=5, use_att_transform_bias=True, use_positional_encoding=True,
+                                      input_for_cross_attention=None, n_cross_att_heads=None)),
+                       ("cross", dict(target_space_id=None, use_att_transform_bias=False, use_positional_encoding=False,
+                                      input_for_cross_attention=_OtherEncoder(), n_cross_att_heads=2))):
+        name = "tx_" + case
+        first = len(shim.VARIABLES)
+        enc2 = object.__new__(TransformerEncoder)
+        enc2.__dict__.update(dict(
+            input_sequence=types.SimpleNamespace(temporal_states=shim.t(tx_in), temporal_mask=shim.t(tx_mask), dimension=dim),
+            ff_hidden_size=ff, depth=2, n_heads=heads, dropout_keep_prob=1.0, attention_dropout_keep_prob=1.0,
+            train_mode=None, _variable_scope=shim.VarScope(name), _reuse=None, _name=name, **opts))
+        out[name + "_states"] = np.asarray(enc2.temporal_states)
+        out[name + "_output"] = np.asarray(enc2.output)
+        for vname in list(shim.VARIABLES)[first:]:
+            out["xv::" + vname] = shim.VARIABLES[vname]
+    shim.AUTO[0] = None
+
     # ---- the trainer's host logic: GenericTrainer.regularization_losses / differentiable_loss_sum /
     #      gradients (per-tensor clip_by_norm) / collect_results (trainers/generic_trainer.py:84-195,27-50),
     #      around an optimizer stand-in that hands back given gradients -------------------------------------------

@@ -751,3 +751,281 @@ def test_attention_dropout_rides_into_the_fused_core(cpu_model, monkeypatch):
     # evaluation mode: no mask at all
     ctx_eval, _ = sdp.attention(part, "s", q, k, k, key_mask, heads, False, 0.8, False, False)
     assert max_abs(ctx_eval, O.multihead_attention(p, "s", q, k, k, key_mask, heads)[0]) < 1e-5
+
+
+@pytest.mark.parametrize("case", ["space", "cross"])
+def test_transformer_encoder_options_against_the_reference_run(cpu_model, case):
+    """The PRODUCT's TransformerEncoder (over stand-in ops) against the outputs of the REFERENCE's
+    TransformerEncoder executed over the numpy TF stand-in (tests/golden/tf_shim_golden.npz), with the
+    variables the reference drew under its own names loaded into the arena: the target-space embedding,
+    projection biases, no position signal, cross-attention to another encoder."""
+    import os
+    import types
+    import numpy as np
+    from neuralmonkey_b200 import runtime
+    from neuralmonkey_b200.encoders import TransformerEncoder
+    from neuralmonkey_b200.model.stateful import TemporalStateful
+    golden = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "tf_shim_golden.npz"))
+    name = "tx_" + case
+    runtime.reset()
+
+    class Sequence(TemporalStateful):
+        def __init__(self, states, mask):
+            self._states, self._mask = torch.from_numpy(states), torch.from_numpy(mask)
+        temporal_states = property(lambda self: self._states)
+        temporal_mask = property(lambda self: self._mask)
+        dimension = property(lambda self: self._states.shape[-1])
+
+    inputs = Sequence(golden["tx_in"], golden["tx_mask"])
+    opts = (dict(target_space_id=5, use_att_transform_bias=True) if case == "space" else
+            dict(use_positional_encoding=False, n_cross_att_heads=2,
+                 input_for_cross_attention=Sequence(golden["tx_other"], golden["tx_other_mask"])))
+    enc = TransformerEncoder(name=name, input_sequence=inputs, ff_hidden_size=20, depth=2, n_heads=3, **opts)
+    enc.ensure_declared()
+    arena = runtime.arena()
+    arena.finalize(runtime.device())
+    reference_vars = {k[4:]: torch.from_numpy(golden[k]) for k in golden.files if k.startswith("xv::" + name + "/")}
+    assert set(arena.order) == set(reference_vars)           # the same variables under the same names
+    arena.load_dict(reference_vars)
+    enc.reset_batch()
+    enc.train_mode, enc.batch_size = False, 3
+    assert max_abs(enc.temporal_states, torch.from_numpy(golden[name + "_states"])) < 3e-5
+    assert max_abs(enc.output, torch.from_numpy(golden[name + "_output"])) < 1e-4
+
+
+def _golden():
+    import os
+    import numpy as np
+    return np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "tf_shim_golden.npz"))
+
+
+@pytest.mark.parametrize("tag,layers,residual,layer_norm,final_norm,scale", [
+    ("sentence", [(4, "bidirectional")], False, False, True, False),
+    ("deep", [(4, "forward"), (4, "backward"), (2, "bidirectional"), (3, "bidirectional")], True, True, True, True),
+    ("plain", [(3, "backward"), (3, "forward")], True, False, False, False),
+    ("nematus", [(4, "bidirectional", "NematusGRU"), (3, "forward", "NematusGRU")], False, False, True, False),
+    ("mixed", [(4, "forward", "LSTM"), (4, "backward", "NematusGRU"), (3, "bidirectional", "NematusGRU"),
+               (2, "bidirectional", "LSTM")], True, True, True, False)])
+def test_recurrent_encoder_against_the_reference_run(cpu_model, tag, layers, residual, layer_norm, final_norm, scale):
+    """The PRODUCT's EmbeddedFactorSequence + RecurrentEncoder against the outputs of the REFERENCE's classes
+    run over the TF stand-in, the reference's variables loaded under the reference's names."""
+    from neuralmonkey_b200 import runtime
+    from neuralmonkey_b200.encoders import RecurrentEncoder
+    from neuralmonkey_b200.model.sequence import EmbeddedFactorSequence
+    from neuralmonkey_b200.vocabulary import Vocabulary
+    golden = _golden()
+    name = "re_" + tag
+    runtime.reset()
+    factors = [torch.from_numpy(f) for f in golden[name + "_ids"]]
+    sizes = [golden["ev::{}_input/embedding_matrix_{}".format(name, i)].shape for i in range(len(factors))]
+    seq = EmbeddedFactorSequence(name=name + "_input",
+                                 vocabularies=[Vocabulary(["w{}".format(j) for j in range(s[0] - 4)]) for s in sizes],
+                                 data_ids=["f{}".format(i) for i in range(len(factors))],
+                                 embedding_sizes=[s[1] for s in sizes], scale_embeddings_by_depth=scale)
+    # the generator drove RecurrentEncoder.rnn directly, past the constructor's check that residual layers
+    # have one width (which the product's constructor repeats): set the flag after construction
+    enc = RecurrentEncoder(name=name, input_sequence=seq, rnn_layers=layers, add_residual=False,
+                           add_layer_norm=layer_norm, include_final_layer_norm=final_norm)
+    enc.add_residual = residual
+    enc.ensure_declared()
+    arena = runtime.arena()
+    arena.finalize(runtime.device())
+    reference_vars = {k[4:]: torch.from_numpy(golden[k]) for k in golden.files
+                      if k.startswith("ev::" + name + "/") or k.startswith("ev::" + name + "_input/")}
+    assert set(arena.order) == set(reference_vars)
+    arena.load_dict(reference_vars)
+    seq.feed_ids(factors, train=False)
+    enc.reset_batch()
+    enc.train_mode, enc.batch_size = False, factors[0].shape[0]
+    assert max_abs(seq.temporal_states, torch.from_numpy(golden[name + "_embedded"])) < 1e-6
+    assert max_abs(enc.temporal_states, torch.from_numpy(golden[name + "_states"])) < 1e-5
+    assert max_abs(enc.output, torch.from_numpy(golden[name + "_output"])) < 1e-5
+
+
+def _stub_encoder(states, mask, output):
+    from neuralmonkey_b200.model.stateful import TemporalStatefulWithOutput
+
+    class Encoder(TemporalStatefulWithOutput):
+        temporal_states = property(lambda self: states)
+        temporal_mask = property(lambda self: mask)
+        output = property(lambda self: output)
+        dimension = property(lambda self: states.shape[-1])
+    return Encoder()
+
+
+@pytest.mark.parametrize("prefix,tag,cell,conditional,out_proj,enc_proj,hsz,esz", [
+    ("r", "maxout", "GRU", False, "maxout", "linear", 7, 5),
+    ("r", "tanh", "GRU", False, "tanh", "linear", 6, 6),
+    ("v", "nematus", "NematusGRU", True, "nematus", "nematus", 7, 5),
+    ("v", "cond_gru", "GRU", True, "mlp", "concat", 10, 5),
+    ("v", "nematus_plain", "NematusGRU", False, "maxout", "empty", 7, 5),
+    ("v", "lstm", "LSTM", False, "maxout", "linear", 7, 5)])
+def test_attention_decoder_against_the_reference_run(cpu_model, prefix, tag, cell, conditional, out_proj, enc_proj,
+                                                     hsz, esz):
+    """The PRODUCT's Attention + Decoder (training pass and greedy loop, over stand-in ops) against the outputs
+    of the REFERENCE's Attention + Decoder run over the TF stand-in - default configuration and every N4
+    variant - with the reference's variables loaded under the reference's names."""
+    golden = _golden()
+    key = "{}d_{}_".format(prefix, tag)
+    g = lambda n: torch.from_numpy(golden[key + n])
+    _att, dec, feed_all = _reference_decoder(prefix, tag, cell, conditional, out_proj, enc_proj, hsz, esz)
+    feed_all(True)
+    assert max_abs(dec.train_logits, g("train_logits")) < 2e-5
+    assert abs(float(dec.train_loss) - float(golden[key + "train_loss"])) < 2e-5
+    feed_all(False)
+    run_logits = g("run_logits")
+    assert dec.runtime_logits.shape == run_logits.shape
+    assert max_abs(dec.runtime_logits, run_logits) < 2e-5
+    assert bool((dec.runtime_symbols == g("run_symbols")).all())
+
+
+def _reference_decoder(prefix, tag, cell, conditional, out_proj, enc_proj, hsz, esz, use_mask=None):
+    """Attention + Decoder of the product holding the variables of one reference run (tf_shim_golden.npz)."""
+    from neuralmonkey_b200 import runtime
+    from neuralmonkey_b200.attention import Attention
+    from neuralmonkey_b200.decoders import Decoder
+    from neuralmonkey_b200.decoders.encoder_projection import nematus_projection
+    from neuralmonkey_b200.decoders.output_projection import maxout_output, mlp_output, nematus_output
+    from neuralmonkey_b200.vocabulary import Vocabulary
+    golden = _golden()
+    dname, aname, key = "{}d_{}".format(prefix, tag), "{}a_{}".format(prefix, tag), "{}d_{}_".format(prefix, tag)
+    varkey = "{}v::".format(prefix)
+    runtime.reset()
+    g = lambda n: torch.from_numpy(golden[key + n])
+    table = g("table")
+    if use_mask is None:
+        use_mask = not (prefix == "r" and tag == "tanh")
+    mask = g("mask") if use_mask else torch.ones(g("states").shape[:2])
+    encoder = _stub_encoder(g("states"), mask, g("enc_out"))
+    vocab = Vocabulary(["t{}".format(i) for i in range(table.shape[0] - 4)])
+    att = Attention(name=aname, encoder=encoder, state_size=8)
+    projection = {"maxout": lambda: maxout_output(esz), "tanh": lambda: None, "nematus": lambda: nematus_output(esz),
+                  "mlp": lambda: mlp_output([9, esz])}[out_proj]()
+    gold = g("gold").t().contiguous()
+    dec = Decoder(encoders=[] if enc_proj == "empty" else [encoder], vocabulary=vocab, data_id="target", name=dname,
+                  max_output_len=gold.shape[1] if prefix == "v" else 6, rnn_size=None if enc_proj == "concat" else hsz,
+                  embedding_size=esz, attentions=[att], output_projection=projection, rnn_cell=cell,
+                  conditional_gru=conditional,
+                  encoder_projection=nematus_projection() if enc_proj == "nematus" else None)
+    for part in (att, dec):
+        part.ensure_declared()
+    arena = runtime.arena()
+    arena.finalize(runtime.device())
+    reference_vars = {k[4:]: torch.from_numpy(golden[k]) for k in golden.files
+                      if k.startswith(varkey + dname + "/") or k.startswith(varkey + aname + "/")}
+    reference_vars[dname + "/word_embeddings"] = table
+    reference_vars[dname + "/state_to_word_W"], reference_vars[dname + "/state_to_word_b"] = g("w"), g("b")
+    assert set(arena.order) == set(reference_vars), set(arena.order) ^ set(reference_vars)
+    arena.load_dict({n: v.reshape(arena.variables[n].shape) for n, v in reference_vars.items()})
+    bsz = gold.shape[0]
+
+    def feed_all(train):
+        att.reset_batch()
+        att.train_mode, att.batch_size = train, bsz
+        dec.feed_ids(gold, bsz, train=train)
+
+    return att, dec, feed_all
+
+
+@pytest.mark.parametrize("search,dtag,out_proj,hsz,esz,use_mask", [
+    ("rnn", "beam", "maxout", 7, 5, True), ("rnn1", "beam1", "tanh", 6, 6, True), ("rnn2", "beam2", "tanh", 6, 6, False)])
+def test_beam_search_over_the_rnn_decoder_against_the_reference_run(cpu_model, search, dtag, out_proj, hsz, esz,
+                                                                    use_mask):
+    """The PRODUCT's BeamSearchDecoder over its attention Decoder against BeamSearchDecoder.outputs of the
+    REFERENCE run to the end over the reference's Decoder (one sentence; early </s>, max_steps reached)."""
+    from neuralmonkey_b200.decoders import BeamSearchDecoder
+    golden = _golden()
+    pre = "bsearch_{}_".format(search)
+    g = lambda n: torch.from_numpy(golden[pre + n])
+    _att, dec, feed_all = _reference_decoder("r", dtag, "GRU", False, out_proj, "linear", hsz, esz, use_mask)
+    bs = BeamSearchDecoder(name="bs", parent_decoder=dec, beam_size=int(golden[pre + "beam"]),
+                           max_steps=int(golden[pre + "max_steps"]), length_normalization=float(golden[pre + "alpha"]))
+    bs.use_cuda_graph = False
+    feed_all(False)
+    bs.reset_batch()
+    bs.batch_size = 1
+    out = bs.outputs
+    assert bool((out.last_search_step_output.token_ids == g("token_ids")).all())
+    assert max_abs(out.last_search_step_output.scores, g("scores")) < 2e-5
+    assert bool((out.last_search_state.lengths == g("lengths")).all())
+    assert bool((out.last_search_state.finished.to(torch.bool) == g("finished")).all())
+
+
+def test_transformer_decoder_against_the_reference_run(cpu_model):
+    """The PRODUCT's TransformerDecoder - training pass, greedy loop (with and without the KV cache) and a
+    whole beam search through BeamSearchDecoder - against the REFERENCE's TransformerDecoder /
+    BeamSearchDecoder.outputs run over the TF stand-in, the reference's variables under its names."""
+    from neuralmonkey_b200 import runtime
+    from neuralmonkey_b200.decoders import BeamSearchDecoder, TransformerDecoder
+    from neuralmonkey_b200.vocabulary import Vocabulary
+    golden = _golden()
+    g = lambda n: torch.from_numpy(golden[n])
+    runtime.reset()
+    encoder = _stub_encoder(g("tenc_states"), g("tenc_mask"), g("tenc_output"))
+    vocab = Vocabulary(["t{}".format(i) for i in range(golden["tloop_table"].shape[0] - 4)])
+    dec = TransformerDecoder(name="tdec", encoders=[encoder], vocabulary=vocab, data_id="target", ff_hidden_size=20,
+                             n_heads_self=3, n_heads_enc=2, depth=2, max_output_len=6, embedding_size=12,
+                             tie_embeddings=True)
+    dec.ensure_declared()
+    arena = runtime.arena()
+    arena.finalize(runtime.device())
+    reference_vars = {k[4:]: g(k) for k in golden.files if k.startswith("tv::tdec/")}
+    reference_vars["tdec/word_embeddings"] = g("tloop_table")
+    assert set(arena.order) == set(reference_vars), set(arena.order) ^ set(reference_vars)
+    arena.load_dict(reference_vars)
+    gold = g("tloop_gold").t().contiguous()
+    dec.feed_ids(gold, 3, train=True)
+    assert max_abs(dec.train_logits, g("tloop_train_logits")) < 5e-5
+    for kv_cache, table, case in ((True, "tloop_table", "run"), (False, "tloop_table", "run"),
+                                  (True, "tloop_table_eos", "run_eos")):
+        arena.load_dict({"tdec/word_embeddings": g(table)})
+        dec.use_kv_cache = kv_cache
+        dec.feed_ids(gold, 3, train=False)
+        assert bool((dec.runtime_symbols == g("tloop_{}_symbols".format(case))).all())
+        assert bool((dec.runtime_mask == g("tloop_{}_mask".format(case))).all())
+        assert max_abs(dec.runtime_logits, g("tloop_{}_logits".format(case))) < 5e-5
+    for tag, table in (("tr", "tloop_table"), ("tr_eos", "tloop_table_eos")):
+        arena.load_dict({"tdec/word_embeddings": g(table)})
+        pre = "bsearch_{}_".format(tag)
+        bs = BeamSearchDecoder(name="bs_" + tag, parent_decoder=dec, beam_size=int(golden[pre + "beam"]),
+                               max_steps=int(golden[pre + "max_steps"]),
+                               length_normalization=float(golden[pre + "alpha"]))
+        bs.use_cuda_graph = False
+        dec.feed_ids(None, 3, train=False)
+        bs.reset_batch()
+        bs.batch_size = 3
+        out = bs.outputs
+        # slot 0 of the reference's history is the first step's greedy symbol - and so is the product's
+        assert bool((out.last_search_step_output.token_ids == g(pre + "token_ids")).all())
+        assert max_abs(out.last_search_step_output.scores, g(pre + "scores")) < 2e-5
+        assert bool((out.last_search_state.lengths == g(pre + "lengths")).all())
+        assert bool((out.last_search_state.finished.to(torch.bool) == g(pre + "finished")).all())
+
+
+@pytest.mark.parametrize("strategy", ["serial", "parallel", "flat", "hierarchical"])
+def test_multi_source_decoder_layers_against_the_reference_run(cpu_model, strategy):
+    """The PRODUCT's TransformerDecoder layer stack over two encoders, each combination strategy, against
+    the REFERENCE's TransformerDecoder.layer run over the TF stand-in (variables and names the reference's)."""
+    from neuralmonkey_b200 import runtime
+    from neuralmonkey_b200.decoders import TransformerDecoder
+    from neuralmonkey_b200.vocabulary import Vocabulary
+    golden = _golden()
+    g = lambda n: torch.from_numpy(golden[n])
+    name = "tms_" + strategy
+    runtime.reset()
+    encoders = [_stub_encoder(g("ms_enc_a"), g("ms_mask_a"), g("ms_enc_a").sum(1)),
+                _stub_encoder(g("ms_enc_b"), g("ms_mask_b"), g("ms_enc_b").sum(1))]
+    dec = TransformerDecoder(name=name, encoders=encoders, vocabulary=Vocabulary(["a", "b", "c"]), data_id="target",
+                             ff_hidden_size=20, n_heads_self=3, n_heads_enc=3 if strategy == "flat" else [3, 2],
+                             depth=2, max_output_len=6, embedding_size=12, tie_embeddings=True,
+                             attention_combination_strategy=strategy,
+                             n_heads_hier=4 if strategy == "hierarchical" else None)
+    dec.ensure_declared()
+    arena = runtime.arena()
+    arena.finalize(runtime.device())
+    reference_vars = {k[4:]: g(k) for k in golden.files if k.startswith("mv::" + name + "/")}
+    assert set(arena.order) - {name + "/word_embeddings"} == set(reference_vars)
+    arena.load_dict(reference_vars)
+    dec.reset_batch()
+    dec.train_mode, dec.batch_size = False, 3
+    assert max_abs(dec._stack(g("ms_in"), g("ms_mask")), g(name + "_states")) < 3e-5
