@@ -42,11 +42,23 @@ def gru_layer(x, gates_kernel, gates_bias, cand_kernel, cand_bias, h0=None, leng
     full = torch.full((x.shape[0],), x.shape[1], dtype=torch.int64)
     lens = full if lengths is None else lengths.to(torch.int64)
     inputs = O.reverse_sequence(x, lens) if reverse else x
-    raw, final = O.dynamic_gru(inputs, None if lengths is None else lens, gates_kernel, gates_bias,
-                               cand_kernel, cand_bias, h0)
-    if reverse:
-        raw = O.reverse_sequence(raw, lens)
-    return (raw if drop_mask is None else raw * drop_mask), final, raw
+    if drop_mask is None:
+        raw, final = O.dynamic_gru(inputs, None if lengths is None else lens, gates_kernel, gates_bias,
+                                   cand_kernel, cand_bias, h0)
+        if reverse:
+            raw = O.reverse_sequence(raw, lens)
+        return raw, final, raw
+    # with a dropout mask the state handed to the next step is the DROPPED output (the reference's decoder
+    # feeds `prev_rnn_output = dropout(cell_output)` back: decoders/decoder.py:330-349), as in nm_gru_seq_fwd
+    assert not reverse and lengths is None
+    h = h0 if h0 is not None else x.new_zeros(x.shape[0], cand_kernel.shape[1])
+    raws, dropped = [], []
+    for t in range(x.shape[1]):
+        new = O.gru_cell(x[:, t], h, gates_kernel, gates_bias, cand_kernel, cand_bias)
+        h = new * drop_mask[:, t]
+        raws.append(new)
+        dropped.append(h)
+    return torch.stack(dropped, 1), h, torch.stack(raws, 1)
 
 
 def bahdanau_attention(keys, values, mask, qproj, v, bias):

@@ -748,6 +748,82 @@ def main():
             out["xv::" + vname] = shim.VARIABLES[vname]
     shim.AUTO[0] = None
 
+    # ---- WHERE dropout is applied: the same parts in training mode with keep_prob 0.5 and a deterministic
+    #      mask (tf_numpy_shim.feature_dropout_mask) in place of tf.nn.dropout -----------------------------------
+    shim.AUTO[0] = np.random.RandomState(31)
+    train_flag = shim.t(np.bool_(True))
+    d_ids = np.array([[4, 5, 6, 7, 8, 3], [3, 4, 5, 0, 0, 0], [8, 7, 0, 0, 0, 0]], np.int64)
+    d_seq = object.__new__(EmbeddedFactorSequence)
+    d_seq.__dict__.update(dict(
+        _variable_scope=shim.VarScope("dr_enc_input"), _reuse=None, _name="dr_enc_input",
+        vocabularies=[list(range(9))], vocabulary_sizes=[9], data_ids=["f0"], embedding_sizes=[6],
+        scale_embeddings_by_depth=False, embeddings_source=None, trainable=True,
+        _input_factor_indices_cached_placeholder=[shim.t(d_ids)]))
+    first = len(shim.VARIABLES)
+    d_enc = object.__new__(RecurrentEncoder)
+    d_enc.__dict__.update(dict(
+        _variable_scope=shim.VarScope("dr_enc"), _reuse=None, _name="dr_enc", input_sequence=d_seq,
+        dropout_keep_prob=0.5, train_mode=train_flag, rnn_specs=[_make_rnn_spec(4, "bidirectional"), _make_rnn_spec(8, "forward")],
+        add_residual=True, add_layer_norm=False, include_final_layer_norm=True))
+    out.update({"dr_ids": d_ids, "dr_enc_states": np.asarray(d_enc.temporal_states), "dr_enc_output": np.asarray(d_enc.output)})
+    d_att = object.__new__(Attention)
+    d_att.__dict__.update(dict(
+        _variable_scope=shim.VarScope("dr_att"), _reuse=None, _name="dr_att", _state_size=7, batch_size=3, _histories={},
+        encoder=d_enc, dropout_keep_prob=0.5, train_mode=train_flag))
+    d_gold = np.array([[5, 6, 7, 2, 0], [7, 8, 9, 4, 2], [4, 2, 0, 0, 0]], np.int64).T
+    d_dec = object.__new__(Decoder)
+    d_dec.__dict__.update(dict(
+        vocabulary=list(range(12)), supress_unk=False, max_output_len=5, batch_size=3, label_smoothing=None,
+        dropout_keep_prob=0.5, train_mode=train_flag, _embedding_size=5, embeddings_source=None, tie_embeddings=False,
+        _variable_scope=shim.VarScope("dr_dec"), _reuse=None, _name="dr_dec",
+        _go_symbols_cached_placeholder=shim.t(np.full((3,), 1, np.int64)),
+        _train_inputs_cached_placeholder=shim.t(d_gold), encoders=[d_enc],
+        _output_projection_spec=maxout_output(5, 0.5), _conditional_gru=False, _attention_on_input=False,
+        _rnn_cell_str="GRU", _rnn_size=6, _encoder_projection=None, attentions=[d_att],
+        step_scope=shim.VarScope("dr_dec/attention_decoder"), encoder_states=lambda: [], encoder_masks=lambda: [],
+        input_projection=lambda *args: LoopState(*args).feedables.embedded_input))
+    out["dr_gold"] = d_gold
+    out["dr_dec_initial_state"] = np.asarray(d_dec.initial_state)
+    out["dr_dec_train_logits"] = np.asarray(d_dec.train_logits)
+    out["dr_dec_train_loss"] = np.asarray(d_dec.train_loss)
+    for vname in list(shim.VARIABLES)[first:]:
+        out["dv::" + vname] = shim.VARIABLES[vname]
+    # the Transformer encoder and the decoder's training pass with dropout 0.5 everywhere, attention weights
+    # included (their callback is the same nn.utils.dropout)
+    first = len(shim.VARIABLES)
+    t_ids = np.array([[4, 5, 6, 7, 8], [3, 4, 5, 0, 0], [8, 0, 0, 0, 0]], np.int64)
+    t_seq = object.__new__(EmbeddedFactorSequence)
+    t_seq.__dict__.update(dict(
+        _variable_scope=shim.VarScope("dt_input"), _reuse=None, _name="dt_input",
+        vocabularies=[list(range(9))], vocabulary_sizes=[9], data_ids=["f0"], embedding_sizes=[dim],
+        scale_embeddings_by_depth=True, embeddings_source=None, trainable=True, dimension=dim,
+        _input_factor_indices_cached_placeholder=[shim.t(t_ids)]))
+    t_enc = object.__new__(TransformerEncoder)
+    t_enc.__dict__.update(dict(
+        input_sequence=t_seq, ff_hidden_size=ff, depth=2, n_heads=heads, dropout_keep_prob=0.5,
+        attention_dropout_keep_prob=0.5, target_space_id=None, use_att_transform_bias=False,
+        use_positional_encoding=True, input_for_cross_attention=None, n_cross_att_heads=None, train_mode=train_flag,
+        _variable_scope=shim.VarScope("dt_enc"), _reuse=None, _name="dt_enc"))
+    out.update({"dt_ids": t_ids, "dt_enc_states": np.asarray(t_enc.temporal_states)})
+    t_gold = np.array([[5, 6, 2, 0], [7, 8, 9, 2], [4, 2, 0, 0]], np.int64).T
+    t_dec = object.__new__(TransformerDecoder)
+    t_dec.__dict__.update(dict(
+        encoders=[t_enc], ff_hidden_size=ff, n_heads_self=heads, n_heads_enc=[2], depth=2,
+        attention_dropout_keep_prob=[0.5], self_att_dropout_keep_prob=0.5, dropout_keep_prob=0.5,
+        use_att_transform_bias=False, attention_combination_strategy="serial", n_heads_hier=None,
+        encoder_states=lambda: [t_enc.temporal_states], encoder_masks=lambda: [t_enc.temporal_mask],
+        _embedding_size=dim, embeddings_source=None, train_mode=train_flag, tie_embeddings=True, label_smoothing=None,
+        vocabulary=list(range(11)), supress_unk=False, max_output_len=4, batch_size=3,
+        _go_symbols_cached_placeholder=shim.t(np.full((3,), 1, np.int64)),
+        _train_inputs_cached_placeholder=shim.t(t_gold),
+        _variable_scope=shim.VarScope("dt_dec"), _reuse=None, _name="dt_dec"))
+    out["dt_gold"] = t_gold
+    out["dt_dec_train_logits"] = np.asarray(t_dec.train_logits)
+    out["dt_dec_train_loss"] = np.asarray(t_dec.train_loss)
+    for vname in list(shim.VARIABLES)[first:]:
+        out["dw::" + vname] = shim.VARIABLES[vname]
+    shim.AUTO[0] = None
+
     # ---- the trainer's host logic: GenericTrainer.regularization_losses / differentiable_loss_sum /
     #      gradients (per-tensor clip_by_norm) / collect_results (trainers/generic_trainer.py:84-195,27-50),
     #      around an optimizer stand-in that hands back given gradients -------------------------------------------

@@ -274,9 +274,10 @@ class GRUCell:
             return self.call(inputs, state)
 
     def call(self, inputs, state):
-        wg, bg = _get_variable("gates/kernel"), _get_variable("gates/bias")
-        wc, bc = _get_variable("candidate/kernel"), _get_variable("candidate/bias")
         x, h = np.asarray(inputs, np.float32), np.asarray(state, np.float32)
+        wide, n = x.shape[1] + h.shape[1], h.shape[1]
+        wg, bg = _get_variable("gates/kernel", [wide, 2 * n]), _get_variable("gates/bias", [2 * n])
+        wc, bc = _get_variable("candidate/kernel", [wide, n]), _get_variable("candidate/bias", [n])
         assert h.shape[1] == self._num_units and wg.shape == (x.shape[1] + h.shape[1], 2 * h.shape[1])
         gates = 1.0 / (1.0 + np.exp(-(np.concatenate([x, h], 1) @ wg + bg)))
         r, u = gates[:, :h.shape[1]], gates[:, h.shape[1]:]
@@ -300,7 +301,8 @@ class LSTMCell(GRUCell):
 
     def call(self, inputs, state):
         c, h = (np.asarray(s, np.float32) for s in state)
-        kernel, bias = _get_variable("kernel"), _get_variable("bias")
+        wide = np.shape(inputs)[1] + h.shape[1]
+        kernel, bias = _get_variable("kernel", [wide, 4 * h.shape[1]]), _get_variable("bias", [4 * h.shape[1]])
         z = np.concatenate([np.asarray(inputs, np.float32), h], 1) @ kernel + bias
         i, j, f, o = np.split(z, 4, axis=1)
         sig = lambda v: 1.0 / (1.0 + np.exp(-v))
@@ -383,6 +385,21 @@ def _sequence_loss(logits, targets, weights, average_across_timesteps=True, aver
         crossent = np.asarray(softmax_loss_function(labels=t(flat_targets), logits=t(flat_logits)))
     crossent = crossent * np.asarray(weights, np.float32).reshape(-1)
     return t(crossent.reshape(lg.shape[0], lg.shape[1]), np.float32)
+
+
+def feature_dropout_mask(shape, keep_prob):
+    """A DETERMINISTIC stand-in for a dropout mask, the same for the reference run and for the product: along
+    the last axis every second entry is dropped, the others scaled by 1/keep_prob.  Random streams cannot
+    be matched, but with this both sides can be compared element by element, which pins WHERE dropout
+    is applied (twice on the initial state, on the GRU output that becomes the next state, ...)."""
+    last = int(shape[-1])
+    pattern = np.where(np.arange(last) % 2 == 0, 1.0 / keep_prob, 0.0).astype(np.float32)
+    return np.broadcast_to(pattern, tuple(int(d) for d in shape)).copy()
+
+
+def _nn_dropout(x, keep_prob, **kwargs):
+    x = np.asarray(x, np.float32)
+    return t(x * feature_dropout_mask(x.shape, keep_prob), np.float32)
 
 
 def _while_loop(cond, body, loop_vars, shape_invariants=None, **kwargs):
@@ -484,6 +501,7 @@ def install():
     tf.reverse_sequence = _reverse_sequence
     tf.not_equal = lambda a, b: t(np.not_equal(a, b))
     tf.while_loop = _while_loop
+    tf.nn.dropout = _nn_dropout
     tf.ones = lambda shape, dtype=None, name=None: t(np.ones([int(d) for d in shape], dtype or np.float32))
     tf.sigmoid = lambda x: t(1.0 / (1.0 + np.exp(-np.asarray(x, np.float32))), np.float32)
     tf.split = lambda value, num_or_size_splits, axis=0: [t(p) for p in np.split(np.asarray(value), num_or_size_splits, axis=axis)]

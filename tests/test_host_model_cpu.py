@@ -1029,3 +1029,102 @@ def test_multi_source_decoder_layers_against_the_reference_run(cpu_model, strate
     dec.reset_batch()
     dec.train_mode, dec.batch_size = False, 3
     assert max_abs(dec._stack(g("ms_in"), g("ms_mask")), g(name + "_states")) < 3e-5
+
+
+def _deterministic_dropout(monkeypatch):
+    """The deterministic mask of tests/golden/tf_numpy_shim.feature_dropout_mask in place of the random one,
+    in every module that draws dropout masks."""
+    import numpy as np
+    from neuralmonkey_b200.attention import scaled_dot_product
+    from neuralmonkey_b200.decoders import decoder as decoder_module
+    from neuralmonkey_b200.nn import utils
+
+    def mask(shape, keep_prob, train_mode, device):
+        if keep_prob >= 1.0 or not train_mode:
+            return None
+        pattern = torch.from_numpy(np.where(np.arange(int(shape[-1])) % 2 == 0, 1.0 / keep_prob, 0.0).astype(np.float32))
+        return pattern.expand(tuple(int(d) for d in shape)).clone()
+    for module in (utils, scaled_dot_product, decoder_module):
+        monkeypatch.setattr(module, "dropout_mask", mask)
+
+
+def test_dropout_placement_against_the_reference_run(cpu_model, monkeypatch):
+    """WHERE dropout is applied.  The reference's RecurrentEncoder + Attention + Decoder ran in training
+    mode with keep_prob 0.5 and a deterministic mask in place of tf.nn.dropout (every second entry of the
+    last axis dropped); the product runs with the same mask.  Equal outputs pin the placement traps: the
+    initial state dropped twice (inside the linear projection and again in `initial_state`), the attention
+    queried with the undropped cell output, the dropped output fed back as the next state, dropout on the
+    attention states, on the contexts and inside the maxout projection, on embeddings and encoder layers."""
+    from neuralmonkey_b200 import runtime
+    from neuralmonkey_b200.attention import Attention
+    from neuralmonkey_b200.decoders import Decoder
+    from neuralmonkey_b200.decoders.output_projection import maxout_output
+    from neuralmonkey_b200.encoders import RecurrentEncoder
+    from neuralmonkey_b200.model.sequence import EmbeddedFactorSequence
+    from neuralmonkey_b200.vocabulary import Vocabulary
+    _deterministic_dropout(monkeypatch)
+    golden = _golden()
+    g = lambda n: torch.from_numpy(golden[n])
+    runtime.reset()
+    seq = EmbeddedFactorSequence(name="dr_enc_input", vocabularies=[Vocabulary(["w{}".format(i) for i in range(5)])],
+                                 data_ids=["f0"], embedding_sizes=[6])
+    enc = RecurrentEncoder(name="dr_enc", input_sequence=seq, rnn_layers=[(4, "bidirectional"), (8, "forward")],
+                           add_residual=True, dropout_keep_prob=0.5)
+    att = Attention(name="dr_att", encoder=enc, state_size=7, dropout_keep_prob=0.5)
+    dec = Decoder(encoders=[enc], vocabulary=Vocabulary(["t{}".format(i) for i in range(8)]), data_id="target",
+                  name="dr_dec", max_output_len=5, dropout_keep_prob=0.5, embedding_size=5, rnn_size=6,
+                  attentions=[att], output_projection=maxout_output(5, 0.5))
+    for part in (enc, att, dec):
+        part.ensure_declared()
+    arena = runtime.arena()
+    arena.finalize(runtime.device())
+    reference_vars = {k[4:]: g(k) for k in golden.files if k.startswith("dv::")}
+    assert set(arena.order) == set(reference_vars), set(arena.order) ^ set(reference_vars)
+    arena.load_dict({n: v.reshape(arena.variables[n].shape) for n, v in reference_vars.items()})
+    seq.feed_ids([g("dr_ids")], train=True)
+    for part in (enc, att):
+        part.reset_batch()
+        part.train_mode, part.batch_size = True, 3
+    dec.feed_ids(g("dr_gold").t().contiguous(), 3, train=True)
+    assert max_abs(enc.temporal_states, g("dr_enc_states")) < 1e-5
+    assert max_abs(enc.output, g("dr_enc_output")) < 1e-5
+    assert max_abs(dec.initial_state, g("dr_dec_initial_state")) < 1e-5
+    assert max_abs(dec.train_logits, g("dr_dec_train_logits")) < 5e-5
+    assert abs(float(dec.train_loss) - float(golden["dr_dec_train_loss"])) < 5e-5
+
+
+def test_transformer_dropout_placement_against_the_reference_run(cpu_model, monkeypatch):
+    """The same for the Transformer: embedded inputs, every sublayer's output, the feed-forward activations
+    and the ATTENTION WEIGHTS (self, masked self and encoder attention) under keep_prob 0.5 with the
+    deterministic mask - encoder states, the decoder's training logits and loss against the reference run."""
+    from neuralmonkey_b200 import runtime
+    from neuralmonkey_b200.decoders import TransformerDecoder
+    from neuralmonkey_b200.encoders import TransformerEncoder
+    from neuralmonkey_b200.model.sequence import EmbeddedSequence
+    from neuralmonkey_b200.vocabulary import Vocabulary
+    _deterministic_dropout(monkeypatch)
+    golden = _golden()
+    g = lambda n: torch.from_numpy(golden[n])
+    runtime.reset()
+    seq = EmbeddedSequence(name="dt_input", vocabulary=Vocabulary(["w{}".format(i) for i in range(5)]), data_id="f0",
+                           embedding_size=12, scale_embeddings_by_depth=True)
+    enc = TransformerEncoder(name="dt_enc", input_sequence=seq, ff_hidden_size=20, depth=2, n_heads=3,
+                             dropout_keep_prob=0.5, attention_dropout_keep_prob=0.5)
+    dec = TransformerDecoder(name="dt_dec", encoders=[enc], vocabulary=Vocabulary(["t{}".format(i) for i in range(7)]),
+                             data_id="target", ff_hidden_size=20, n_heads_self=3, n_heads_enc=2, depth=2,
+                             max_output_len=4, embedding_size=12, tie_embeddings=True, dropout_keep_prob=0.5,
+                             attention_dropout_keep_prob=0.5, self_attention_dropout_keep_prob=0.5)
+    for part in (enc, dec):
+        part.ensure_declared()
+    arena = runtime.arena()
+    arena.finalize(runtime.device())
+    reference_vars = {k[4:]: g(k) for k in golden.files if k.startswith("dw::")}
+    assert set(arena.order) == set(reference_vars), set(arena.order) ^ set(reference_vars)
+    arena.load_dict(reference_vars)
+    seq.feed_ids([g("dt_ids")], train=True)
+    enc.reset_batch()
+    enc.train_mode, enc.batch_size = True, 3
+    dec.feed_ids(g("dt_gold").t().contiguous(), 3, train=True)
+    assert max_abs(enc.temporal_states, g("dt_enc_states")) < 3e-5
+    assert max_abs(dec.train_logits, g("dt_dec_train_logits")) < 1e-4
+    assert abs(float(dec.train_loss) - float(golden["dt_dec_train_loss"])) < 1e-4
