@@ -43,6 +43,12 @@ def all_reduce_sum(buf: torch.Tensor) -> None:
         dist.all_reduce(buf, op=dist.ReduceOp.SUM)
 
 
+def barrier() -> None:
+    """All ranks wait here (no-op for one rank): e.g. before reading a checkpoint rank 0 has just written."""
+    if world_size() > 1:
+        dist.barrier()
+
+
 def shard_bounds(n_items: int, n_ranks: int) -> List[int]:
     """Contiguous split of n_items sentences into n_ranks shards, sizes differing by <= 1."""
     base, extra = divmod(n_items, n_ranks)

@@ -103,6 +103,7 @@ class Experiment:
         log("Saving final variables in {}".format(final_variables))
         if main:
             self.model.tf_manager.save(final_variables)
+        distributed.barrier()        # the other ranks must not read checkpoints rank 0 is still writing
         if self.model.test_datasets:
             if os.path.exists(self.get_path("variables.data.best")):
                 self.model.tf_manager.restore_best_vars()
