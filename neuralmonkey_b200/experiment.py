@@ -13,7 +13,8 @@ from neuralmonkey_b200 import distributed, runtime
 from neuralmonkey_b200.config.configuration import Configuration
 from neuralmonkey_b200.config.normalize import normalize_configuration
 from neuralmonkey_b200.dataset import Dataset
-from neuralmonkey_b200.learning_utils import evaluation, run_on_dataset, training_loop
+from neuralmonkey_b200.learning_utils import (evaluation, print_final_evaluation, run_on_dataset,
+                                              training_loop)
 from neuralmonkey_b200.logging import Logging, log
 from neuralmonkey_b200.runners.dataset_runner import DatasetRunner
 
@@ -146,8 +147,7 @@ class Experiment:
                                                                    log_progress)
         eval_result = evaluation(self.model.evaluation, f_dataset, execution_results, output_data)
         if eval_result:
-            log("{} evaluation: {}".format(name or dataset.name, "  ".join(
-                "{}: {:.4g}".format(k, v) for k, v in sorted(eval_result.items()))), color="blue")
+            print_final_evaluation(eval_result, name or dataset.name)
         return eval_result
 
     def get_path(self, filename: str, cont_index: int = None) -> str:

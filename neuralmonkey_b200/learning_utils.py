@@ -204,47 +204,70 @@ def evaluation(evaluators, batch, execution_results, result_data) -> Dict[str, f
     return eval_result
 
 
+def _format_evaluation_line(evaluation_res: Dict[str, float], main_metric: str) -> str:
+    """`name: value` pairs in the order they were computed (runner losses, then the evaluators), four
+    spaces apart, the main metric moved to the end (learning_utils.py:504-516)."""
+    others = ["{}: {:.4g}".format(name, value) for name, value in evaluation_res.items() if name != main_metric]
+    return "    ".join(others) + "    {}: {:.4g}".format(main_metric, evaluation_res[main_metric])
+
+
 def _log_evaluation(main_metric: str, eval_result: Dict[str, float], seen_instances: int, epoch: int,
                     max_epochs: int, execution_results, train: bool = False,
                     dataset_name: str = None, rate: float = None) -> None:
+    """One line per logged batch / validation, as _log_continuous_evaluation writes it (:470-502): yellow for
+    training batches, blue for validation.  (TensorBoard summaries are out of scope.)"""
     if distributed.rank() != 0:
         return
-    color, prefix = ("yellow", "train") if train else ("blue", "val")
-    if dataset_name is not None:
-        prefix += "_" + dataset_name
-    parts = ["{}: {:.4g}".format(name, value) for name, value in sorted(eval_result.items())
-             if name != main_metric]
-    if main_metric in eval_result:
-        parts.append("{}: {:.4g}".format(main_metric, eval_result[main_metric]))
-    if train and execution_results:
-        for res in execution_results:
-            if res is not None:
-                parts.extend("{}: {:.4g}".format(k, v) for k, v in sorted(res.losses.items()))
-    if rate is not None:
-        parts.append("{:.0f} instances/s".format(rate))
-    log("Epoch {}/{}  Instances {}  {}  {}".format(epoch, max_epochs, seen_instances, prefix,
-                                                  "  ".join(parts)), color=color)
+    log("Epoch {}/{}  Instances {}  {}".format(epoch, max_epochs, seen_instances,
+                                              _format_evaluation_line(eval_result, main_metric)),
+        color="yellow" if train else "blue")
+
+
+def print_final_evaluation(eval_result: Dict[str, float], name: str = None) -> None:
+    """The aligned table printed after a test set was evaluated (learning_utils.py:519-530)."""
+    if name is not None:
+        log("Model evaluated on '{}'".format(name))
+    for eval_name, value in eval_result.items():
+        log("... {}:{} {:.4g}".format(eval_name, " " * (22 - len(eval_name)), value))
+    log_print("")
+
+
+def _data_item_to_str(item: Any) -> str:
+    if isinstance(item, list):
+        return " ".join(_data_item_to_str(i) for i in item)
+    if isinstance(item, dict):
+        rows = ["{}: {}".format(_data_item_to_str(k), _data_item_to_str(v)) for k, v in item.items()]
+        return "{\n      " + "\n      ".join(rows) + "\n    }"
+    if isinstance(item, np.ndarray) and item.ndim > 1:
+        return "[numpy tensor, shape {}]".format(item.shape)
+    return str(item)
 
 
 def _print_examples(dataset: Dict[str, List[Any]], outputs: Dict[str, List[Any]],
                     val_preview_input_series: Optional[List[str]] = None,
                     val_preview_output_series: Optional[List[str]] = None,
                     num_examples: int = 15) -> None:
-    def fmt(item: Any) -> str:
-        if isinstance(item, (list, tuple)):
-            return " ".join(str(i) for i in item)
-        if isinstance(item, np.ndarray):
-            return "array of shape {}".format(item.shape)
-        return str(item)
-    in_series = val_preview_input_series or sorted(dataset.keys())
-    out_series = val_preview_output_series or sorted(outputs.keys())
-    size = min(len(v) for v in dataset.values()) if dataset else 0
+    """The validation preview (learning_utils.py:548-613): per example its number, the source series
+    (in the dataset, not produced), the produced series, and `<series> (ref)` for produced series that
+    the dataset also holds - each group sorted by name."""
     log_print("Examples:")
-    for i in range(min(num_examples, size)):
-        for s in in_series:
-            if s in dataset:
-                log_print("  {} (input): {}".format(s, fmt(dataset[s][i])))
-        for s in out_series:
-            if s in outputs and i < len(outputs[s]):
-                log_print("  {} (output): {}".format(s, fmt(outputs[s][i])))
+    assert outputs
+    sources = [s for s in dataset if s not in outputs]
+    targets = [s for s in dataset if s in outputs]
+    produced = list(outputs.keys())
+    if val_preview_input_series is not None:
+        sources = [s for s in sources if s in val_preview_input_series]
+        targets = [s for s in targets if s in val_preview_input_series]
+    if val_preview_output_series is not None:
+        produced = [s for s in produced if s in val_preview_output_series]
+    columns = {s: list(dataset[s]) for s in sources + targets}
+    results = {s: list(outputs[s]) for s in produced}
+    for i in range(min(len(next(iter(dataset.values()))), num_examples)):
+        log_print("  [{}]".format(i + 1))
+        for series in sorted(sources):
+            log_print("  {}: {}".format(series, _data_item_to_str(columns[series][i])))
+        for series in sorted(produced):
+            log_print("  {}: {}".format(series, _data_item_to_str(results[series][i])))
+        for series in sorted(targets):
+            log_print("  {} (ref): {}".format(series, _data_item_to_str(columns[series][i])))
         log_print("")

@@ -92,6 +92,46 @@ def main():
         cases.append({"finished": finished, "n_token_rows": n_tok, "max_steps": max_steps,
                       "is_finished": bool(ex._is_finished(res))})
     out["beam_is_finished"] = cases
+
+    # ---- learning_utils.py: result joining, evaluation dictionary, log line formats, the validation preview ----
+    from collections import OrderedDict
+    from neuralmonkey import learning_utils as LU
+    from neuralmonkey.runners.base_runner import ExecutionResult
+    printed = []
+    LU.log_print = printed.append
+    LU.log = lambda message, color=None: printed.append(message)
+    results = [ExecutionResult({"target": [["a", "b"], ["c"]]}, {"target/xent": 2.0}, 2, []),
+               ExecutionResult({"target": [["d"]]}, {"target/xent": 5.0}, 1, [])]
+    joined = LU.join_execution_results(results)
+    out["lu_join"] = {"outputs": joined.outputs, "losses": joined.losses, "size": joined.size}
+    arrays = [ExecutionResult({"enc": [np.ones(3), np.zeros(3)]}, {}, 2, []), ExecutionResult({"enc": [np.ones(3)]}, {}, 1, [])]
+    out["lu_join_arrays_shape"] = list(LU.join_execution_results(arrays).outputs["enc"].shape)
+
+    class Exact:
+        name = "exact"
+
+        def __call__(self, hyp, ref):
+            return float(np.mean([h == r for h, r in zip(hyp, ref)]))
+    batch = {"target": [["a", "b"], ["x"], ["d"]], "source": [["s1"], ["s2"], ["s3"]]}
+    evaluated = LU.evaluation([("target", "target", Exact()), ("missing", "target", Exact()), ("target", "nothere", Exact())],
+                              batch, [joined], {"target": joined.outputs["target"]})
+    out["lu_evaluation"] = list(evaluated.items())
+    line = OrderedDict([("target/xent", 3.0), ("target/BLEU", 12.3456789), ("target/exact", 2.0 / 3), ("big", 123456.789)])
+    out["lu_format_line"] = LU._format_evaluation_line(line, "target/BLEU")
+    del printed[:]
+    LU.print_final_evaluation(line, "test_0")
+    out["lu_final_evaluation"] = list(printed)
+    items = [["a", "b"], {"k": ["v", "w"], "n": 3}, np.zeros((2, 3)), np.arange(3), 4.5, "text", [["x"], ["y", "z"]]]
+    out["lu_data_item_to_str"] = [LU._data_item_to_str(i) for i in items]
+    del printed[:]
+    LU._print_examples({"source": [["s1"], ["s2", "s2"], ["s3"]], "target": [["t1"], ["t2"], ["t3"]], "extra": [1, 2, 3]},
+                       {"target": [["o1"], ["o2"], ["o3"]], "rep": [np.zeros((2, 2)), np.zeros((2, 2)), np.zeros((2, 2))]},
+                       num_examples=2)
+    out["lu_examples_all"] = list(printed)
+    del printed[:]
+    LU._print_examples({"source": [["s1"]], "target": [["t1"]], "extra": [1]}, {"target": [["o1"]], "rep": [7]},
+                       val_preview_input_series=["source", "target"], val_preview_output_series=["target"])
+    out["lu_examples_selected"] = list(printed)
     with open(os.path.join(HERE, "runner_golden.json"), "w") as f:
         json.dump(out, f, indent=1)
     print(json.dumps(out["beam"]["ranks"], indent=1)[:1500])

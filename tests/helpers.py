@@ -88,3 +88,18 @@ def rel_err(a: torch.Tensor, b: torch.Tensor) -> float:
 
 def max_abs(a: torch.Tensor, b: torch.Tensor) -> float:
     return float((a.detach().double().cpu() - b.detach().double().cpu()).abs().max())
+
+
+def training_log_values(log_text: str, name: str):
+    """The values of `name` on the lines logged for TRAINING batches: "Epoch e/m  Instances n  ..." lines
+    that are not the result line of a validation (the first such line after a "Validation (epoch" header)."""
+    values, in_validation = [], False
+    for line in log_text.splitlines():
+        if "Validation (epoch" in line:
+            in_validation = True
+        elif "  Instances " in line and "Epoch " in line:
+            if in_validation:
+                in_validation = False
+            elif name + ": " in line:
+                values.append(float(line.split(name + ": ")[1].split()[0]))
+    return values

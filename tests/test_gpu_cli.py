@@ -11,6 +11,8 @@ import sys
 
 import pytest
 
+from tests.helpers import training_log_values
+
 pytestmark = pytest.mark.gpu
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -191,8 +193,7 @@ def test_train_and_run_entry_points(tmp_path):
     log_text = open(os.path.join(out, "experiment.log")).read()
     assert "Validation (epoch" in log_text and "target/SacreBLEU" in log_text
     # the loss must have gone down during the three epochs
-    losses = [float(line.split("train_xent: ")[1].split()[0]) for line in log_text.splitlines()
-              if " train " in line and "train_xent: " in line]
+    losses = training_log_values(log_text, "target/train_xent")
     assert len(losses) >= 3 and losses[-1] < losses[0], losses
     assert len(open(os.path.join(out, "val.out")).read().splitlines()) == 30
 
@@ -347,7 +348,7 @@ def test_transformer_beam_search_experiment(tmp_path):
     assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
     log_text = open(os.path.join(out, "experiment.log")).read()
     assert "Validation (epoch" in log_text and "target_beam.rank001/BLEU" in log_text
-    train_lines = [line for line in log_text.splitlines() if " train " in line]
-    assert len(train_lines) >= 3, log_text[-2000:]
+    train_values = training_log_values(log_text, "target_beam.rank001/beam_search_score")
+    assert len(train_values) >= 3, log_text[-2000:]
     assert "beam_search_score" in log_text
     assert os.path.exists(os.path.join(out, "variables.data.best"))

@@ -6,6 +6,8 @@ import sys
 import pytest
 import torch
 
+from tests.helpers import training_log_values
+
 from neuralmonkey_b200 import distributed
 from neuralmonkey_b200.params import ParameterArena, normal_initializer, zeros_initializer
 from neuralmonkey_b200.vocabulary import (END_TOKEN, PAD_TOKEN, Vocabulary, from_wordlist, pad_batch,
@@ -277,8 +279,7 @@ def test_two_rank_training_through_the_entry_point(tmp_path):
     assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
     log_text = open(os.path.join(out, "experiment.log")).read()
     assert "Validation (epoch" in log_text and "Training finished" in log_text
-    losses = [float(line.split("train_xent: ")[1].split()[0]) for line in log_text.splitlines()
-              if " train " in line and "train_xent: " in line]
+    losses = training_log_values(log_text, "target/train_xent")
     assert len(losses) >= 2 and losses[-1] < losses[0], losses
     assert len(open(os.path.join(out, "val.out")).read().splitlines()) == 30
     assert os.path.exists(os.path.join(out, "variables.data.final"))

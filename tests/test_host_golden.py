@@ -209,3 +209,47 @@ def test_further_evaluators_match_reference(golden):
     assert E.WER([["a", "b"], []], [["a", "c", "d"], ["x"]]) == pytest.approx((2 + 1) / 4)
     with pytest.raises(ImportError, match="pyter"):
         E.TER([["a"]], [["b"]])
+
+
+def test_learning_utils_helpers_match_reference(runner_golden, monkeypatch):
+    """join_execution_results, evaluation, the "Epoch e/m  Instances n  ..." line, the final evaluation table,
+    `_data_item_to_str` and the validation preview against the reference's learning_utils.py run here."""
+    from collections import OrderedDict
+    from neuralmonkey_b200 import learning_utils as LU
+    from neuralmonkey_b200.runners.base_runner import ExecutionResult
+    want = runner_golden
+    printed = []
+    monkeypatch.setattr(LU, "log_print", printed.append)
+    monkeypatch.setattr(LU, "log", lambda message, color=None: printed.append(message))
+    results = [ExecutionResult({"target": [["a", "b"], ["c"]]}, {"target/xent": 2.0}, 2, []),
+               ExecutionResult({"target": [["d"]]}, {"target/xent": 5.0}, 1, [])]
+    joined = LU.join_execution_results(results)
+    assert {"outputs": joined.outputs, "losses": joined.losses, "size": joined.size} == want["lu_join"]
+    arrays = [ExecutionResult({"enc": [np.ones(3), np.zeros(3)]}, {}, 2, []), ExecutionResult({"enc": [np.ones(3)]}, {}, 1, [])]
+    assert list(LU.join_execution_results(arrays).outputs["enc"].shape) == want["lu_join_arrays_shape"]
+
+    class Exact:
+        name = "exact"
+
+        def __call__(self, hyp, ref):
+            return float(np.mean([h == r for h, r in zip(hyp, ref)]))
+    batch = {"target": [["a", "b"], ["x"], ["d"]], "source": [["s1"], ["s2"], ["s3"]]}
+    evaluated = LU.evaluation([("target", "target", Exact()), ("missing", "target", Exact()), ("target", "nothere", Exact())],
+                              batch, [joined], {"target": joined.outputs["target"]})
+    assert [list(item) for item in evaluated.items()] == want["lu_evaluation"]
+    line = OrderedDict([("target/xent", 3.0), ("target/BLEU", 12.3456789), ("target/exact", 2.0 / 3), ("big", 123456.789)])
+    assert LU._format_evaluation_line(line, "target/BLEU") == want["lu_format_line"]
+    del printed[:]
+    LU.print_final_evaluation(line, "test_0")
+    assert printed == want["lu_final_evaluation"]
+    items = [["a", "b"], {"k": ["v", "w"], "n": 3}, np.zeros((2, 3)), np.arange(3), 4.5, "text", [["x"], ["y", "z"]]]
+    assert [LU._data_item_to_str(i) for i in items] == want["lu_data_item_to_str"]
+    del printed[:]
+    LU._print_examples({"source": [["s1"], ["s2", "s2"], ["s3"]], "target": [["t1"], ["t2"], ["t3"]], "extra": [1, 2, 3]},
+                       {"target": [["o1"], ["o2"], ["o3"]], "rep": [np.zeros((2, 2)), np.zeros((2, 2)), np.zeros((2, 2))]},
+                       num_examples=2)
+    assert printed == want["lu_examples_all"]
+    del printed[:]
+    LU._print_examples({"source": [["s1"]], "target": [["t1"]], "extra": [1]}, {"target": [["o1"]], "rep": [7]},
+                       val_preview_input_series=["source", "target"], val_preview_output_series=["target"])
+    assert printed == want["lu_examples_selected"]

@@ -8,7 +8,8 @@ import torch
 
 from oracle import nm_oracle as O
 from tests import cpu_ops
-from tests.helpers import (build_bahdanau, feed, max_abs, oracle_params_for, oracle_spec, random_batch)
+from tests.helpers import (build_bahdanau, feed, max_abs, oracle_params_for, oracle_spec, random_batch,
+                           training_log_values)
 
 pytestmark = pytest.mark.filterwarnings("ignore:Converting a tensor with requires_grad")
 
@@ -302,8 +303,7 @@ def test_experiments_end_to_end_on_the_cpu(cpu_model, monkeypatch, tmp_path, whi
         assert os.path.exists(os.path.join(out, name)), name
     if which == "bahdanau":
         assert os.path.exists(os.path.join(out, "variables.data"))
-        losses = [float(line.split("train_xent: ")[1].split()[0]) for line in log_text.splitlines()
-                  if " train " in line and "train_xent: " in line]
+        losses = training_log_values(log_text, "target/train_xent")
         assert len(losses) >= 2 and losses[-1] < losses[0], losses
         assert len(open(os.path.join(out, "val.out")).read().splitlines()) == 30
         run_ini = tmp_path / "run.ini"
