@@ -75,6 +75,8 @@ def training_loop(cfg: Namespace) -> None:
                         log(header, color="blue")
                         _print_examples(f_val, outputs, cfg.val_preview_input_series,
                                         cfg.val_preview_output_series, cfg.val_preview_num_examples)
+                        log_print("")
+                        log(header, color="blue")       # the reference repeats the header below the preview
                         if val_id == len(cfg.val_datasets) - 1:
                             score = val_eval[cfg.main_metric]
                             if distributed.rank() == 0:
