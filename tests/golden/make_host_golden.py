@@ -130,6 +130,25 @@ def main():
             ev = BLEUEvaluator(n=n, deduplicate=dedup)
             out["bleu_{}_{}".format(n, int(dedup))] = float(ev(HYPS, REFS))
     out["bleu_identity"] = float(BLEUEvaluator()(REFS, REFS))
+    # the corpus of the reference's own unit test (neuralmonkey/tests/test_bleu.py): the 4-gram precision is
+    # zero, so the mteval-v13a smoothing acts; plus empty sides and several references per sentence
+    ut_hyp = [d.split() for d in ("colorful thoughts furiously sleep", "little piglet slept all night",
+                                  "working working working working working be be be be be be be", "ich bin walrus",
+                                  "walrus for pr\u00e4sident")]
+    ut_ref = [r.split() for r in ("the colorless ideas slept furiously", "pooh slept all night",
+                                  "working class hero is something to be", "I am the working class walrus",
+                                  "walrus for president")]
+    multi_ref = [["a", "b", "|", "a", "c", "d"], ["x", "|", "x", "y"]]
+    multi_hyp = [["a", "c"], ["x", "x", "y"]]
+    out["bleu_unit_test"] = {
+        "hyp": ut_hyp, "ref": ut_ref,
+        "scores": {"{}_{}".format(n, int(d)): float(BLEUEvaluator(n=n, deduplicate=d)(ut_hyp, ut_ref))
+                   for n in (1, 2, 4) for d in (False, True)},
+        "empty_sentence": float(BLEUEvaluator()(ut_hyp + [["something"]], ut_ref + [[]])),
+        "empty_decoded": float(BLEUEvaluator()([[] for _ in ut_hyp], ut_ref)),
+        "empty_reference": float(BLEUEvaluator()(ut_hyp, [[] for _ in ut_ref])),
+        "multi_hyp": multi_hyp, "multi_ref": multi_ref,
+        "multi": float(BLEUEvaluator(n=2, multiple_references_separator="|")(multi_hyp, multi_ref))}
     # ---- further evaluators (chrf.py, edit_distance.py, mse.py, average.py; wer.py and ter.py need the
     #      third-party pyter and are not run) ------------------------------------------------------------
     from neuralmonkey.evaluators.chrf import ChrF3, ChrFEvaluator

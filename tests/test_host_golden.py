@@ -66,6 +66,18 @@ def test_bleu_matches_reference(golden):
             got = BLEUEvaluator(n=n, deduplicate=dedup)(hyps, refs)
             assert got == pytest.approx(golden["bleu_{}_{}".format(n, int(dedup))], rel=1e-9), (n, dedup)
     assert BLEUEvaluator()(refs, refs) == pytest.approx(golden["bleu_identity"])
+    # the reference's unit-test corpus: a zero 4-gram precision (mteval-v13a smoothing), empty sides, the
+    # unclipped "modified" precision, several references per sentence
+    ut = golden["bleu_unit_test"]
+    for key, want in ut["scores"].items():
+        n, dedup = key.split("_")
+        assert BLEUEvaluator(n=int(n), deduplicate=bool(int(dedup)))(ut["hyp"], ut["ref"]) == pytest.approx(want, rel=1e-12)
+    assert 5 < ut["scores"]["4_0"] < 25                                   # test_bleu.py: 15 +- 10
+    assert BLEUEvaluator()(ut["hyp"] + [["something"]], ut["ref"] + [[]]) == pytest.approx(ut["empty_sentence"], rel=1e-12)
+    assert BLEUEvaluator()([[] for _ in ut["hyp"]], ut["ref"]) == ut["empty_decoded"] == 0.0
+    assert BLEUEvaluator()(ut["hyp"], [[] for _ in ut["ref"]]) == pytest.approx(ut["empty_reference"], rel=1e-12)
+    assert BLEUEvaluator(n=2, multiple_references_separator="|")(ut["multi_hyp"], ut["multi_ref"]) == pytest.approx(
+        ut["multi"], rel=1e-12)
 
 
 def test_char_helpers_match_reference(golden):

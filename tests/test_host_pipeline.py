@@ -66,7 +66,10 @@ def test_bleu_matches_hand_computation():
     bleu = BLEUEvaluator()
     ref = [["the", "cat", "sat", "on", "the", "mat"]]
     assert abs(bleu(ref, ref) - 100.0) < 1e-9
-    assert bleu([["dog"]], ref) == 0.0
+    # nothing matches: unigram precision 0 -> smoothed to 1 / (2 * 1); orders 2-4 have no hypothesis n-gram
+    # and count as 1; brevity penalty exp(1 - 6/1)  (mteval-v13a smoothing, evaluators/bleu.py:196-208)
+    import math
+    assert bleu([["dog"]], ref) == pytest.approx(100 * math.exp(0.25 * math.log(0.5) + (1 - 6)))
     hyp = [["the", "cat", "sat", "on", "a", "mat"]]
     # precisions 5/6, 3/5, 1/4, 0/3 smoothed by the evaluator: just bounded here
     assert 0.0 <= bleu(hyp, ref) < 100.0
