@@ -8,6 +8,7 @@ from typing import Optional, Tuple
 
 import torch
 
+from neuralmonkey_b200.typecheck import check_argument_types
 from neuralmonkey_b200 import ops
 from neuralmonkey_b200.attention.base_attention import (
     Attendable, BaseAttention, empty_attention_loop_state, get_attention_mask,
@@ -26,6 +27,7 @@ class Attention(BaseAttention):
     def __init__(self, name: str, encoder: Attendable, dropout_keep_prob: float = 1.0,
                  state_size: int = None, reuse: ModelPart = None, save_checkpoint: str = None,
                  load_checkpoint: str = None, initializers: InitializerSpecs = None) -> None:
+        check_argument_types()
         BaseAttention.__init__(self, name, reuse, save_checkpoint, load_checkpoint, initializers)
         self.encoder = encoder
         self.dropout_keep_prob = dropout_keep_prob

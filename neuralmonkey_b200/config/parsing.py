@@ -173,3 +173,8 @@ def write_file(config_dict: Dict[str, Any], config_file: IO[str]) -> None:
     parser = configparser.ConfigParser()
     parser.read_dict(config_dict)
     parser.write(config_file, space_around_delimiters=False)
+
+
+# the reference's (private) names for the same functions: neuralmonkey/tests/test_config.py uses them
+_parse_value = parse_value
+_split_on_commas = split_on_commas

@@ -18,6 +18,7 @@ from typing import Any, List, NamedTuple
 
 import torch
 
+from neuralmonkey_b200.typecheck import check_argument_types
 from neuralmonkey_b200 import ops, runtime
 from neuralmonkey_b200.decoders.autoregressive import (AutoregressiveDecoder, DecoderFeedables,
                                                        LoopState)
@@ -53,6 +54,7 @@ def map_structure(fn, obj):
 class BeamSearchDecoder(ModelPart):
     def __init__(self, name: str, parent_decoder: AutoregressiveDecoder, beam_size: int,
                  max_steps: int, length_normalization: float) -> None:
+        check_argument_types()
         ModelPart.__init__(self, name)
         self.parent_decoder = parent_decoder
         self.beam_size = beam_size

@@ -17,6 +17,7 @@ from typing import Any, List, NamedTuple, Optional, Tuple
 
 import torch
 
+from neuralmonkey_b200.typecheck import check_argument_types
 from neuralmonkey_b200 import ops, runtime
 from neuralmonkey_b200.attention.base_attention import BaseAttention
 from neuralmonkey_b200.decoders.autoregressive import AutoregressiveDecoder, LoopState
@@ -54,6 +55,7 @@ class Decoder(AutoregressiveDecoder):
                  rnn_cell: str = "GRU", conditional_gru: bool = False, supress_unk: bool = False,
                  reuse: ModelPart = None, save_checkpoint: str = None, load_checkpoint: str = None,
                  initializers: InitializerSpecs = None) -> None:
+        check_argument_types()
         AutoregressiveDecoder.__init__(
             self, name=name, vocabulary=vocabulary, data_id=data_id, max_output_len=max_output_len,
             dropout_keep_prob=dropout_keep_prob, embedding_size=embedding_size,

@@ -13,6 +13,7 @@ from typing import Any, List, NamedTuple, Tuple, Union
 
 import torch
 
+from neuralmonkey_b200.typecheck import check_argument_types
 from neuralmonkey_b200 import ops, runtime
 from neuralmonkey_b200.attention.base_attention import (Attendable, get_attention_mask,
                                                         get_attention_states)
@@ -55,6 +56,7 @@ class TransformerDecoder(AutoregressiveDecoder):
                  use_att_transform_bias: bool = False, supress_unk: bool = False,
                  reuse: ModelPart = None, save_checkpoint: str = None, load_checkpoint: str = None,
                  initializers: InitializerSpecs = None) -> None:
+        check_argument_types()
         AutoregressiveDecoder.__init__(
             self, name=name, vocabulary=vocabulary, data_id=data_id, max_output_len=max_output_len,
             dropout_keep_prob=dropout_keep_prob, embedding_size=embedding_size,

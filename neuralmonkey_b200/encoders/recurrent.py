@@ -18,6 +18,7 @@ from neuralmonkey_b200.model.sequence import EmbeddedFactorSequence, EmbeddedSeq
 from neuralmonkey_b200.model.stateful import TemporalStateful, TemporalStatefulWithOutput
 from neuralmonkey_b200.nn.utils import dropout
 from neuralmonkey_b200.nn.variants import LSTMCell, NematusGRUCell, require_variant
+from neuralmonkey_b200.typecheck import check_argument_types
 from neuralmonkey_b200.params import (constant_initializer, ones_initializer,
                                       orthogonal_initializer, zeros_initializer)
 from neuralmonkey_b200.vocabulary import Vocabulary
@@ -62,6 +63,7 @@ class RecurrentEncoder(ModelPart, TemporalStatefulWithOutput):
                  include_final_layer_norm: bool = True, dropout_keep_prob: float = 1.0,
                  reuse: ModelPart = None, save_checkpoint: str = None, load_checkpoint: str = None,
                  initializers: InitializerSpecs = None) -> None:
+        check_argument_types()
         ModelPart.__init__(self, name, reuse, save_checkpoint, load_checkpoint, initializers)
         self.input_sequence = input_sequence
         self.dropout_keep_prob = dropout_keep_prob
@@ -188,6 +190,7 @@ class SentenceEncoder(RecurrentEncoder):
                  load_checkpoint: str = None, initializers: InitializerSpecs = None,
                  embedding_initializer=None) -> None:
         """Embedded input sequence + one RNN layer (recurrent.py:236-314)."""
+        check_argument_types()
         s_ckp = "input_{}".format(save_checkpoint) if save_checkpoint else None
         l_ckp = "input_{}".format(load_checkpoint) if load_checkpoint else None
         emb_initializers = None
@@ -218,6 +221,7 @@ class FactoredEncoder(RecurrentEncoder):
                  load_checkpoint: str = None, initializers: InitializerSpecs = None,
                  input_initializers: InitializerSpecs = None) -> None:
         """Multi-factor input sequence + one RNN layer (recurrent.py:317-385)."""
+        check_argument_types()
         s_ckp = "input_{}".format(save_checkpoint) if save_checkpoint else None
         l_ckp = "input_{}".format(load_checkpoint) if load_checkpoint else None
         input_sequence = EmbeddedFactorSequence(

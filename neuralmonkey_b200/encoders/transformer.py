@@ -7,6 +7,7 @@ from typing import List, NamedTuple
 
 import torch
 
+from neuralmonkey_b200.typecheck import check_argument_types
 from neuralmonkey_b200 import ops, runtime
 from neuralmonkey_b200.attention.base_attention import (Attendable, get_attention_mask,
                                                         get_attention_states)
@@ -80,6 +81,7 @@ class TransformerEncoder(ModelPart, TemporalStatefulWithOutput):
                  input_for_cross_attention: Attendable = None, n_cross_att_heads: int = None,
                  reuse: ModelPart = None, save_checkpoint: str = None, load_checkpoint: str = None,
                  initializers: InitializerSpecs = None) -> None:
+        check_argument_types()
         ModelPart.__init__(self, name, reuse, save_checkpoint, load_checkpoint, initializers)
         self.input_sequence = input_sequence
         self.ff_hidden_size = ff_hidden_size

@@ -74,9 +74,8 @@ class RougeLEvaluator:
 Accuracy = AccuracyEvaluator()
 ROUGE_L = RougeLEvaluator()
 SacreBLEU = BLEUEvaluator(n=4, name="SacreBLEU")
-ChrF3 = ChrFEvaluator(beta=3)
-EditDistance = EditDistanceEvaluator("Edit distance")
-WER = WEREvaluator("WER")
-TER = TEREvaluator("TER")
-MSE = MeanSquaredErrorEvaluator("MeanSquaredError")
-PairwiseMSE = PairwiseMeanSquaredErrorEvaluator("PairwiseMeanSquaredError")
+from neuralmonkey_b200.evaluators.chrf import ChrF3  # noqa: E402
+from neuralmonkey_b200.evaluators.edit_distance import EditDistance  # noqa: E402
+from neuralmonkey_b200.evaluators.mse import MSE, PairwiseMSE  # noqa: E402
+from neuralmonkey_b200.evaluators.ter import TER  # noqa: E402
+from neuralmonkey_b200.evaluators.wer import WER  # noqa: E402

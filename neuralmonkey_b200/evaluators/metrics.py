@@ -57,13 +57,21 @@ class ChrFEvaluator(_Metric):
                        for m in range(1, self.n + 1)]
 
     @staticmethod
-    def _overlap(counted: List[Counter], other: List[Counter]) -> float:
+    def _overlap(counted, other) -> float:
         ratios = []
         for own, theirs in zip(counted, other):
             total = sum(own.values())
             matched = sum(min(c, theirs[g]) for g, c in own.items() if g in theirs)
             ratios.append(matched / total if total else 1.0)
         return sum(ratios) / len(ratios)
+
+    def chr_p(self, hyp_ngrams, ref_ngrams) -> float:
+        """Character n-gram precision from per-order count dictionaries (evaluators/chrf.py:77-89)."""
+        return self._overlap(hyp_ngrams, ref_ngrams)
+
+    def chr_r(self, hyp_ngrams, ref_ngrams) -> float:
+        """Character n-gram recall (evaluators/chrf.py:63-75)."""
+        return self._overlap(ref_ngrams, hyp_ngrams)
 
     def score_instance(self, hypothesis: List[str], reference: List[str]) -> float:
         hyp_chars, hyp = self._orders(hypothesis)

@@ -7,6 +7,7 @@ from typing import Any, Dict, List, Optional
 
 import torch
 
+from neuralmonkey_b200.typecheck import check_argument_types
 from neuralmonkey_b200 import ops, runtime
 from neuralmonkey_b200.decorators import tensor
 from neuralmonkey_b200.model.model_part import ModelPart
@@ -33,6 +34,7 @@ class EmbeddedFactorSequence(Sequence):
                  trainable: bool = True, embeddings_source: "EmbeddedFactorSequence" = None,
                  reuse: ModelPart = None, save_checkpoint: str = None, load_checkpoint: str = None,
                  initializers: InitializerSpecs = None) -> None:
+        check_argument_types()
         Sequence.__init__(self, name, max_length, reuse, save_checkpoint, load_checkpoint,
                           initializers)
         self.vocabularies = vocabularies
@@ -141,6 +143,7 @@ class EmbeddedSequence(EmbeddedFactorSequence):
                  trainable: bool = True, embeddings_source: "EmbeddedSequence" = None,
                  reuse: ModelPart = None, save_checkpoint: str = None, load_checkpoint: str = None,
                  initializers: InitializerSpecs = None) -> None:
+        check_argument_types()
         EmbeddedFactorSequence.__init__(
             self, name=name, vocabularies=[vocabulary], data_ids=[data_id],
             embedding_sizes=[embedding_size], max_length=max_length,
