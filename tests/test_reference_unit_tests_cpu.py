@@ -54,6 +54,13 @@ def reference_tests(monkeypatch):
         del sys.modules[name]
     tf = types.ModuleType("tensorflow")              # the tests call tf.reset_default_graph() around cases
     tf.reset_default_graph = lambda: None
+    tf.test = types.SimpleNamespace(TestCase=unittest.TestCase)
+
+    class Graph:                                     # test_vocabulary builds its vocabulary inside one
+        def as_default(self):
+            import contextlib
+            return contextlib.nullcontext()
+    tf.Graph = Graph
     sys.modules["tensorflow"] = tf
     package = types.ModuleType("neuralmonkey.tests")
     package.__path__ = [REFERENCE_TESTS]
@@ -99,5 +106,23 @@ def test_reference_sentence_encoder_constructor_test_passes(reference_tests):
     is outside the hot path: its module is stubbed so that the file imports)."""
     result = reference_tests("test_encoders_init", only=["TestEncodersInit.test_sentence_encoder"],
                              stubs=[("neuralmonkey.encoders.sentence_cnn_encoder", {"SentenceCNNEncoder": object})])
+    problems = [trace.strip().splitlines()[-1] for _case, trace in result.failures + result.errors]
+    assert not problems and result.testsRun == 1, problems
+
+
+def test_reference_vocabulary_tests_pass(reference_tests):
+    """neuralmonkey/tests/test_vocabulary.py without its two session-bound cases (string -> index lookup
+    tables are TensorFlow ops there; here the conversion is host code, covered by the golden tests)."""
+    result = reference_tests("test_vocabulary", only=["TestVocabulary.test_all_words_in", "TestVocabulary.test_unknown_word",
+                                                      "TestVocabulary.test_padding", "TestVocabulary.test_weights"])
+    problems = [trace.strip().splitlines()[-1] for _case, trace in result.failures + result.errors]
+    assert not problems and result.testsRun == 4, problems
+
+
+def test_reference_t2t_reader_test_passes(reference_tests):
+    """neuralmonkey/tests/test_readers.py::TestT2TReader (the file's other class tests the string-vector
+    reader, which is outside the hot path: its module is stubbed so that the file imports)."""
+    result = reference_tests("test_readers", only=["TestT2TReader"],
+                             stubs=[("neuralmonkey.readers.string_vector_reader", {"get_string_vector_reader": None})])
     problems = [trace.strip().splitlines()[-1] for _case, trace in result.failures + result.errors]
     assert not problems and result.testsRun == 1, problems
