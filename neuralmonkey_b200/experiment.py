@@ -18,10 +18,12 @@ from neuralmonkey_b200.learning_utils import (evaluation, print_final_evaluation
 from neuralmonkey_b200.logging import Logging, log
 from neuralmonkey_b200.runners.dataset_runner import DatasetRunner
 
+# the reference's list (experiment.py:28-34) plus train_start_offset, which the reference forgets: there
+# `neuralmonkey-run` rejects an INI that sets it ("Unexpected fields")
 _TRAIN_ARGS = ["val_dataset", "trainer", "name", "train_dataset", "epochs", "test_datasets",
                "initial_variables", "validation_period", "val_preview_input_series",
                "val_preview_output_series", "val_preview_num_examples", "logging_period",
-               "visualize_embeddings", "random_seed", "overwrite_output_dir", "train_start_offset"]
+               "visualize_embeddings", "overwrite_output_dir", "train_start_offset"]
 _EXPERIMENT_FILES = ["experiment.log", "experiment.ini", "original.ini", "git_commit", "git_diff",
                      "variables.data.best"]
 
@@ -176,7 +178,6 @@ def create_config(train_mode: bool = True) -> Configuration:
     config.add_argument("postprocess", required=False, default=None)
     config.add_argument("runners")
     config.add_argument("random_seed", required=False, default=2574600)
-    config.add_argument("runners_batch_size", required=False, default=None)
     if train_mode:
         config.add_argument("epochs", cond=lambda x: x >= 0)
         config.add_argument("trainer")
