@@ -73,7 +73,9 @@ class RougeLEvaluator:
 # pylint: disable=invalid-name
 Accuracy = AccuracyEvaluator()
 ROUGE_L = RougeLEvaluator()
-SacreBLEU = BLEUEvaluator(n=4, name="SacreBLEU")
+# the reference names this instance "BLEU" (evaluators/sacrebleu.py:63): its results are logged as <series>/BLEU
+SacreBLEU = BLEUEvaluator(n=4, name="BLEU")
+AccuracySeqLevel = AccuracySeqLevelEvaluator()
 from neuralmonkey_b200.evaluators.chrf import ChrF3  # noqa: E402
 from neuralmonkey_b200.evaluators.edit_distance import EditDistance  # noqa: E402
 from neuralmonkey_b200.evaluators.mse import MSE, PairwiseMSE  # noqa: E402

@@ -191,7 +191,7 @@ def test_train_and_run_entry_points(tmp_path):
                  "variables.data.best", "variables.data.final", "val.out"):
         assert os.path.exists(os.path.join(out, name)), name
     log_text = open(os.path.join(out, "experiment.log")).read()
-    assert "Validation (epoch" in log_text and "target/SacreBLEU" in log_text
+    assert "Validation (epoch" in log_text and "target/BLEU" in log_text
     # the loss must have gone down during the three epochs
     losses = training_log_values(log_text, "target/train_xent")
     assert len(losses) >= 3 and losses[-1] < losses[0], losses
@@ -217,7 +217,7 @@ batching=<batching>
     res = _run(["bin/neuralmonkey-run", str(ini), str(run_ini), "--json", str(tmp_path / "res.json")])
     assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
     results = json.load(open(tmp_path / "res.json"))
-    assert "target/SacreBLEU" in results[0] and "target/runtime_xent" in results[0]
+    assert "target/BLEU" in results[0] and "target/runtime_xent" in results[0]
     assert len(open(os.path.join(out, "run.out")).read().splitlines()) == 30
 
 

@@ -325,7 +325,7 @@ batching=<batching>
         _cli(monkeypatch, "neuralmonkey_b200.run",
              ["neuralmonkey-run", str(ini), str(run_ini), "--json", str(tmp_path / "res.json")])
         results = json.load(open(tmp_path / "res.json"))
-        assert "target/SacreBLEU" in results[0] and "target/runtime_xent" in results[0]
+        assert "target/BLEU" in results[0] and "target/runtime_xent" in results[0]
         assert len(open(os.path.join(out, "run.out")).read().splitlines()) == 30
     else:
         assert "target_beam.rank001/BLEU" in log_text and "beam_search_score" in log_text
@@ -1128,3 +1128,28 @@ def test_transformer_dropout_placement_against_the_reference_run(cpu_model, monk
     assert max_abs(enc.temporal_states, g("dt_enc_states")) < 3e-5
     assert max_abs(dec.train_logits, g("dt_dec_train_logits")) < 1e-4
     assert abs(float(dec.train_loss) - float(golden["dt_dec_train_loss"])) < 1e-4
+
+
+def test_xent_and_plain_runners(cpu_model):
+    """XentRunner: `train_xents` rows as the output series, their mean as the loss (xent_runner.py:13-35).
+    PlainRunner: `decoder.decoded` - argmax over the non-<pad> symbols - through the vocabulary
+    (plain_runner.py:20-58)."""
+    import numpy as np
+    from neuralmonkey_b200.runners import PlainRunner, XentRunner
+    model = build_bahdanau(**TOY)
+    params = oracle_params_for(model)
+    model["arena"].load_dict(params)
+    src, tgt = random_batch(5, 8, 7, TOY["vs"], TOY["vt"], seed=3)
+    spec = oracle_spec(True, 10, True)
+    oenc = O.sentence_encoder(params, "sentence_encoder", src)
+    feed(model, src, tgt, train=False)
+    exe = XentRunner(output_series="xents", decoder=model["dec"]).get_executable(compute_losses=True, num_sessions=1)
+    exe.execute()
+    want = O.decoder_train(params, spec, oenc, tgt.t())["train_xents"].numpy()
+    assert np.abs(np.array(exe.result.outputs["xents"]) - want).max() < 1e-4
+    assert abs(exe.result.losses["xents/xent"] - float(want.mean())) < 1e-5
+    plain = PlainRunner(output_series="target", decoder=model["dec"]).get_executable(compute_losses=True, num_sessions=1)
+    plain.execute()
+    og = O.decoder_greedy(params, spec, oenc, tgt.t())
+    assert plain.result.outputs["target"] == model["dec"].vocabulary.vectors_to_sentences(og["decoded"].numpy())
+    assert sorted(plain.result.losses) == ["target/runtime_loss", "target/train_loss"]
