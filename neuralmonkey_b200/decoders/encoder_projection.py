@@ -28,7 +28,10 @@ class EncoderProjection:
 
 
 def _encoder_output_size(enc: Stateful) -> int:
-    return enc.dimension
+    """Width of `enc.output` (the reference reads it off the tensor's static shape).  It is the part's `dimension`
+    except where `dimension` names the width of the input instead (StatefulFiller with a projection)."""
+    width = getattr(enc, "output_dimension", None)
+    return enc.dimension if width is None else width
 
 
 class _Empty(EncoderProjection):

@@ -1153,3 +1153,94 @@ def test_xent_and_plain_runners(cpu_model):
     og = O.decoder_greedy(params, spec, oenc, tgt.t())
     assert plain.result.outputs["target"] == model["dec"].vocabulary.vectors_to_sentences(og["decoded"].numpy())
     assert sorted(plain.result.losses) == ["target/runtime_loss", "target/train_loss"]
+
+
+def test_numpy_fillers_feed_precomputed_features(cpu_model, tmp_path):
+    """SpatialFiller (1x1 conv projections named as tf.layers numbers them), StatefulFiller and TemporalFiller
+    (encoders/numpy_stateful_filler.py of the reference) through the numpy readers, under the attention decoder."""
+    import numpy as np
+    from neuralmonkey_b200 import runtime
+    from neuralmonkey_b200.attention import Attention
+    from neuralmonkey_b200.dataset import BatchingScheme, Dataset
+    from neuralmonkey_b200.decoders import Decoder
+    from neuralmonkey_b200.encoders.numpy_stateful_filler import SpatialFiller, StatefulFiller, TemporalFiller
+    from neuralmonkey_b200.readers.numpy_reader import from_file_list, single_tensor
+    from neuralmonkey_b200.readers.string_vector_reader import FloatVectorReader, get_string_vector_reader
+    from neuralmonkey_b200.vocabulary import Vocabulary
+    from tests.helpers import oracle_params_for
+
+    rng = np.random.RandomState(5)
+    maps = rng.randn(3, 2, 3, 6).astype(np.float32)
+    names = []
+    for i, m in enumerate(maps):
+        np.savez(tmp_path / "m{}.npz".format(i), m)
+        names.append("m{}".format(i))
+    (tmp_path / "list.txt").write_text("\n".join(names) + "\n")
+    read = from_file_list(str(tmp_path), [2, 3, 6], suffix=".npz")
+    loaded = list(read([str(tmp_path / "list.txt")]))
+    assert np.array_equal(np.stack(loaded), maps)
+    with pytest.raises(ValueError):
+        list(from_file_list(str(tmp_path), [2, 3, 5], suffix=".npz")([str(tmp_path / "list.txt")]))
+    np.save(tmp_path / "a.npy", maps[:2])
+    np.save(tmp_path / "b.npy", maps[2:])
+    assert np.array_equal(single_tensor([str(tmp_path / "a.npy"), str(tmp_path / "b.npy")]), maps)
+    (tmp_path / "vec.txt").write_text("1 2   3.5\n\n 4 -5e3 6\n")
+    vecs = list(FloatVectorReader([str(tmp_path / "vec.txt")]))
+    assert [v.tolist() for v in vecs] == [[1.0, 2.0, 3.5], [4.0, -5000.0, 6.0]] and vecs[0].dtype == np.float32
+    with pytest.raises(ValueError):
+        list(get_string_vector_reader(np.int32, columns=2)([str(tmp_path / "vec.txt")]))
+
+    runtime.reset()
+    vocab = Vocabulary(["t{}".format(i) for i in range(20)])
+    enc = SpatialFiller(name="maps", input_shape=[2, 3, 6], data_id="maps", projection_dim=5, ff_hidden_dim=7)
+    vec = StatefulFiller(name="vec", dimension=4, data_id="vec", output_shape=3)
+    plain = SpatialFiller(name="plain", input_shape=[2, 3, 6], data_id="maps")
+    seq = TemporalFiller(name="seq", data_id="seq", input_size=2, max_input_len=3)
+    att = Attention(name="attention", encoder=enc, state_size=6)
+    dec = Decoder(encoders=[enc, vec], vocabulary=vocab, data_id="target", name="decoder", max_output_len=5,
+                  rnn_size=8, embedding_size=8, attentions=[att])
+    for part in (enc, vec, plain, seq, att, dec):
+        part.ensure_declared()
+    arena = runtime.arena()
+    arena.finalize(runtime.device())
+    assert {"maps/conv2d/kernel", "maps/conv2d/bias", "maps/conv2d_1/kernel", "maps/conv2d_1/bias",
+            "vec/dense/kernel", "vec/dense/bias"} <= set(arena.train_names)
+    assert not any(n.startswith(("plain/", "seq/")) for n in arena.train_names)
+    assert float(arena.get("maps/conv2d/bias").abs().max()) == 0.0          # tf.layers defaults
+    limit = (6.0 / (6 + 7)) ** 0.5
+    assert 0.5 * limit < float(arena.get("maps/conv2d/kernel").abs().max()) <= limit
+    params = oracle_params_for({"arena": arena}, scale=0.3)
+    arena.load_dict(params)
+
+    sequences = [rng.randn(n, 2).astype(np.float32) for n in (4, 1, 2)]
+    vectors = rng.randn(3, 4).astype(np.float32)
+    data = Dataset("toy", {"maps": lambda: iter(maps), "vec": lambda: iter(vectors), "seq": lambda: iter(sequences)},
+                   BatchingScheme(batch_size=3))
+    for part in (enc, vec, plain, seq):
+        part.feed_dict(data, train=True)
+    k1, b1 = params["maps/conv2d/kernel"].reshape(6, 7), params["maps/conv2d/bias"]
+    k2, b2 = params["maps/conv2d_1/kernel"].reshape(7, 5), params["maps/conv2d_1/bias"]
+    want = torch.relu(torch.from_numpy(maps) @ k1 + b1) @ k2 + b2
+    assert max_abs(enc.spatial_states, want) < 1e-5 and enc.dimension == 5
+    assert max_abs(enc.output, want.mean(dim=(1, 2))) < 1e-5
+    assert tuple(enc.spatial_mask.shape) == (3, 2, 3) and float(enc.spatial_mask.min()) == 1.0
+    assert torch.equal(plain.spatial_states.cpu(), torch.from_numpy(maps)) and plain.dimension == 6
+    want_vec = torch.from_numpy(vectors) @ params["vec/dense/kernel"] + params["vec/dense/bias"]
+    assert max_abs(vec.output, want_vec) < 1e-5
+    assert tuple(seq.temporal_states.shape) == (3, 3, 2)                      # clipped to max_input_len
+    assert seq.temporal_mask.cpu().tolist() == [[1, 1, 1], [1, 0, 0], [1, 1, 0]]
+    assert float(seq.temporal_states[1, 1:].abs().max()) == 0.0
+
+    _src, tgt = random_batch(3, 4, 5, 20, 20, seed=4)
+    att.reset_batch()
+    att.train_mode, att.batch_size = True, 3
+    dec.feed_ids(tgt, 3, train=True)
+    # the initial state projects the concatenated outputs of both encoders (encoder_projection.py:47-73)
+    oenc = {"output": torch.cat([want.mean(dim=(1, 2)), want_vec], dim=1),
+            "temporal_states": want.reshape(3, 6, 5), "temporal_mask": torch.ones(3, 6)}
+    odec = O.decoder_train(params, O.RNNDecoderSpec("decoder", "attention", 8, "tanh", False), oenc, tgt.t())
+    assert abs(float(dec.train_loss) - float(odec["train_loss"])) < 1e-4
+    float(dec.train_loss)
+    dec.train_loss.backward()
+    arena.fold_autograd_grads()
+    runtime.reset()

@@ -58,3 +58,115 @@ def test_reference_ini_trains_unchanged(monkeypatch, tmp_path, name):
         assert os.path.exists(os.path.join(out, "encoded.npy"))
     if name == "beamsearch":
         assert "beam_search_score" in log_text
+
+
+_FEATURES_INI = """
+[main]
+name="captioning over pre-extracted feature maps"
+tf_manager=<tf_manager>
+output="{out}"
+overwrite_output_dir=True
+batch_size=2
+epochs=2
+train_dataset=<train_data>
+val_dataset=<val_data>
+trainer=<trainer>
+runners=[<runner>]
+postprocess=None
+evaluation=[("target", evaluators.BLEU)]
+logging_period=1
+validation_period=5
+random_seed=1234
+
+[tf_manager]
+class=tf_manager.TensorFlowManager
+num_threads=4
+num_sessions=1
+
+[numpy_reader]
+class=readers.numpy_reader.from_file_list
+prefix="tests/data/flickr30k"
+shape=[8, 8, 2048]
+
+[train_data]
+class=dataset.load
+series=["target", "images"]
+data=["tests/data/flickr30k/train.de", ("tests/data/flickr30k/train_images.npz.txt", <numpy_reader>)]
+
+[val_data]
+class=dataset.load
+series=["target", "images"]
+data=["tests/data/flickr30k/val.de", ("tests/data/flickr30k/val_images.npz.txt", <numpy_reader>)]
+
+[imagenet]
+class=encoders.numpy_stateful_filler.SpatialFiller
+name="imagenet"
+input_shape=[8, 8, 2048]
+data_id="images"
+projection_dim=6
+ff_hidden_dim=9
+
+[decoder_vocabulary]
+class=vocabulary.from_wordlist
+path="tests/data/decoder_vocab.tsv"
+
+[attention]
+class=attention.Attention
+name="attention"
+encoder=<imagenet>
+state_size=5
+
+[decoder]
+class=decoders.decoder.Decoder
+name="decoder"
+attentions=[<attention>]
+encoders=[<imagenet>]
+rnn_size=3
+embedding_size=3
+dropout_keep_prob=0.5
+data_id="target"
+max_output_len=3
+vocabulary=<decoder_vocabulary>
+
+[trainer]
+class=trainers.cross_entropy_trainer.CrossEntropyTrainer
+decoders=[<decoder>]
+l2_weight=1.0e-8
+clip_norm=1.0
+
+[runner]
+class=runners.GreedyRunner
+decoder=<decoder>
+output_series="target"
+"""
+
+
+def test_captioning_over_the_reference_feature_files(monkeypatch, tmp_path):
+    """The image half of the reference's tests/flat-multiattention.ini - `readers.numpy_reader.from_file_list`
+    over its flickr30k .npz feature maps into a `SpatialFiller` - under the attention decoder of the hot path
+    (the FlatMultiAttention wrapper of that INI is outside it)."""
+    from neuralmonkey_b200 import ops, runtime
+    from neuralmonkey_b200.trainers.generic_trainer import GenericTrainer
+    for op in cpu_ops.STAND_INS:
+        monkeypatch.setattr(ops, op, getattr(cpu_ops, op))
+    monkeypatch.setattr(runtime, "_device", torch.device("cpu"))
+    monkeypatch.setattr(GenericTrainer, "_adam_kernel", cpu_ops.adam_kernel)
+    monkeypatch.setenv("NEURALMONKEY_STRICT", "1")
+    monkeypatch.chdir(REFERENCE)
+    out = str(tmp_path / "features")
+    ini = tmp_path / "features.ini"
+    ini.write_text(_FEATURES_INI.format(out=out))
+    monkeypatch.setattr(sys, "argv", ["neuralmonkey-train", str(ini)])
+    try:
+        from neuralmonkey_b200.train import main
+        main()
+        names = set(runtime.arena().names) if hasattr(runtime.arena(), "names") else set()
+    finally:
+        runtime.reset()
+    log_text = open(os.path.join(out, "experiment.log")).read()
+    assert "Training finished" in log_text and "Validation (epoch" in log_text and "target/BLEU" in log_text
+    assert os.path.exists(os.path.join(out, "variables.data.final"))
+    saved = torch.load(os.path.join(out, "variables.data.final"), weights_only=False) \
+        if not names else None
+    keys = names or set(saved.get("variables", saved).keys())
+    assert {"imagenet/conv2d/kernel", "imagenet/conv2d_1/kernel"} <= keys
