@@ -1244,3 +1244,34 @@ def test_numpy_fillers_feed_precomputed_features(cpu_model, tmp_path):
     dec.train_loss.backward()
     arena.fold_autograd_grads()
     runtime.reset()
+
+
+def test_recurrent_encoder_over_a_temporal_filler(cpu_model):
+    """`RecurrentEncoder(input_sequence=<TemporalFiller>)` - the encoder of the reference's audio INIs
+    (tests/audio-classifier.ini:53-62, tests/ctc.ini:55-64) - against the oracle on ragged numeric sequences."""
+    import numpy as np
+    from neuralmonkey_b200 import runtime
+    from neuralmonkey_b200.dataset import BatchingScheme, Dataset
+    from neuralmonkey_b200.encoders import RecurrentEncoder
+    from neuralmonkey_b200.encoders.numpy_stateful_filler import TemporalFiller
+    from tests.helpers import oracle_params_for
+    runtime.reset()
+    seq = TemporalFiller(name="input_seq", data_id="features", input_size=4)
+    enc = RecurrentEncoder(name="encoder", input_sequence=seq, rnn_layers=[(5, "bidirectional"), (6, "backward")])
+    for part in (seq, enc):
+        part.ensure_declared()
+    arena = runtime.arena()
+    arena.finalize(runtime.device())
+    params = oracle_params_for({"arena": arena}, scale=0.3)
+    arena.load_dict(params)
+    rng = np.random.RandomState(1)
+    series = [rng.randn(n, 4).astype(np.float32) for n in (5, 2, 3)]
+    data = Dataset("toy", {"features": lambda: iter(series)}, BatchingScheme(batch_size=3))
+    seq.feed_dict(data, train=False)
+    enc.feed_dict(data, train=False)
+    want = O.recurrent_encoder(params, "encoder", seq.temporal_states, seq.temporal_mask,
+                               [(5, "bidirectional", "GRU"), (6, "backward", "GRU")], False, False, True)
+    assert max_abs(enc.temporal_states, want["temporal_states"]) < 1e-5
+    assert max_abs(enc.output, want["output"]) < 1e-5
+    assert torch.equal(enc.temporal_mask.cpu(), seq.temporal_mask.cpu())
+    runtime.reset()
