@@ -1,27 +1,31 @@
-"""Vectors written as whitespace-separated numbers, one per line
-(reference: neuralmonkey/readers/string_vector_reader.py:6-46)."""
+"""Numeric vectors stored as text, one whitespace-separated vector per non-empty line (optionally gzipped).
+Same entry points as neuralmonkey/readers/string_vector_reader.py:6-38 of the reference."""
 import gzip
-from typing import Iterable, List, Type
+from typing import Iterator, List, Optional, Type
 
 import numpy as np
 
 
-def get_string_vector_reader(dtype: Type = np.float32, columns: int = None):
-    def parse(line: str, lineno: int, path: str) -> np.ndarray:
-        numbers = line.split()
-        if columns is not None and len(numbers) != columns:
-            raise ValueError("Wrong number of columns ({}) on line {}, file {}".format(
-                len(numbers), lineno, path))
-        return np.array(numbers, dtype=dtype)
+class _VectorLines:
+    def __init__(self, dtype: Type, columns: Optional[int]) -> None:
+        self.dtype, self.columns = dtype, columns
 
-    def reader(files: List[str]) -> Iterable[np.ndarray]:
+    def __call__(self, files: List[str]) -> Iterator[np.ndarray]:
         for path in files:
-            opener = (lambda p: gzip.open(p, "rt")) if path.endswith(".gz") else open
-            with opener(path) as f_data:
-                for lineno, line in enumerate(f_data, 1):
-                    if line.strip():
-                        yield parse(line, lineno, path)
-    return reader
+            handle = gzip.open(path, "rt") if path.endswith(".gz") else open(path)
+            with handle:
+                for lineno, text in enumerate(handle, start=1):
+                    fields = text.split()
+                    if not fields:
+                        continue
+                    if self.columns is not None and len(fields) != self.columns:
+                        raise ValueError("Wrong number of columns ({}) on line {}, file {}".format(
+                            len(fields), lineno, path))
+                    yield np.array(fields, dtype=self.dtype)
+
+
+def get_string_vector_reader(dtype: Type = np.float32, columns: int = None):
+    return _VectorLines(dtype, columns)
 
 
 # pylint: disable=invalid-name

@@ -119,10 +119,8 @@ def test_reference_vocabulary_tests_pass(reference_tests):
     assert not problems and result.testsRun == 4, problems
 
 
-def test_reference_t2t_reader_test_passes(reference_tests):
-    """neuralmonkey/tests/test_readers.py::TestT2TReader (the file's other class tests the string-vector
-    reader, which is outside the hot path: its module is stubbed so that the file imports)."""
-    result = reference_tests("test_readers", only=["TestT2TReader"],
-                             stubs=[("neuralmonkey.readers.string_vector_reader", {"get_string_vector_reader": None})])
+def test_reference_reader_tests_pass(reference_tests):
+    """neuralmonkey/tests/test_readers.py: the tensor2tensor text reader and the string-vector reader."""
+    result = reference_tests("test_readers")
     problems = [trace.strip().splitlines()[-1] for _case, trace in result.failures + result.errors]
-    assert not problems and result.testsRun == 1, problems
+    assert not problems and result.testsRun == 3, problems
