@@ -346,6 +346,70 @@ int nm_im2col3x3(const float* x, float* cols, int64_t N, int64_t H, int64_t W,
 int nm_maxpool2x2_fwd(const float* x, float* y, int64_t N, int64_t H, int64_t W,
                       int64_t C, void* stream);
 
+/* ---- K4 (inference): the fused attention-decoder step ---------------------------------
+ * Replaces ONE iteration of the decoding while_loop between the previous symbol and the vector the
+ * vocabulary projection consumes: embed_input_symbols (decoders/autoregressive.py:269-272),
+ * Decoder.next_state with a GRU cell (decoders/decoder.py:279-358: GRUCell on [emb; h], TF-1.12 gate
+ * order, candidate on r*h), Attention.attention (attention/feed_forward.py:125-166: query projection,
+ * energies, softmax over ALL Tx, mask, +1e-8 renormalisation, context) and the deep output
+ * (decoders/output_projection.py:115-160: tanh/relu/sigmoid dense, or maxout).  Inference only:
+ * no dropout.  One kernel launch; exact fp32.
+ *   rows            hypotheses (batch, or batch*beam beam-minor); `group` consecutive rows share
+ *                   encoder row (row / group): 1 for greedy decoding, the beam size for beam search
+ *                   - the encoder tensors are NOT tiled;
+ *   symbols [rows] i64 + emb_table [V,E], or x_in [rows,E] (already embedded; then symbols is ignored);
+ *   h_prev [rows,H]; parent [rows] i32 or NULL: row r continues hypothesis
+ *                   (r/group)*group + parent[r] of the previous step (the gather_flat of
+ *                   beam_search_decoder.py:499-532 folded into the load); h_out must not alias h_prev;
+ *   Wg [E+H,2H], bg [2H], Wc [E+H,H], bc [H]  (gates/candidate kernels of the GRUCell);
+ *   Wq [H,A], bq [A], v [A], att_bias [1];  keys [NB,Tx,A] (hidden_features), values [NB,Tx,C]
+ *                   (attention_states), mask [NB,Tx] fp32 or NULL, NB = rows/group;
+ *   Wo [H+E+C, O] (or [H+E+C, 2*O] with maxout != 0), bo; act = NM_ACT_* (ignored with maxout).
+ * Outputs: h_out [rows,H]; out [rows,O]; optional x_out [rows,E] (embedded input), ctx_out [rows,C],
+ * weights_out [rows,Tx].  16-byte loads and TMA-staged key/value tiles need E,H,A,C,O % 4 == 0 and
+ * 16-byte aligned bases; other shapes take a scalar variant of the same kernel. */
+int nm_attn_decoder_step_fwd(const int64_t* symbols, const float* emb_table, const float* x_in,
+                             const float* h_prev, const int32_t* parent, const float* Wg, const float* bg,
+                             const float* Wc, const float* bc, const float* Wq, const float* bq,
+                             const float* v, const float* att_bias, const float* keys,
+                             const float* values, const float* mask, const float* Wo, const float* bo,
+                             float* x_out, float* h_out, float* ctx_out, float* weights_out, float* out,
+                             int64_t rows, int64_t group, int64_t E, int64_t H, int64_t A, int64_t C,
+                             int64_t Tx, int64_t O, int act, int maxout, void* stream);
+
+/* ---- K5/K6 at run time: logits, argmax and the symbol bookkeeping of one decoding step ------
+ * Replaces get_body of decoders/autoregressive.py:446-480 after next_state: logits = X.W + b
+ * (+ -1e9 at unk_index >= 0), lse[m], argmax[m] (first index), and - when symbols_out is given -
+ *   symbol = finished_in[m] ? 0 : argmax;  finished_out = finished_in | (symbol == 2);
+ *   mask_out = !finished_out;  *unfinished_count += number of rows still unfinished.
+ * finished_in/finished_out (u8) may alias.  backend NM_GEMM_AUTO/TC: the tcgen05 GEMM with the
+ * softmax-partials epilogue + one combine kernel (`part`: nm_logits_xent_scratch(M,V) floats;
+ * logits_out optional).  NM_GEMM_SIMT: exact fp32 CUDA-core GEMM into logits_out (required) + one
+ * row kernel.  With targets [M] (gold symbols of this step) xent[m] = (lse - logit[target]) * weights[m]
+ * (runtime_xents, autoregressive.py:351-366).  lse / argmax / xent / the bookkeeping outputs may be NULL. */
+int nm_decode_logits_step(const float* X, int64_t ldx, const float* W, int64_t ldw, int transW,
+                          const float* b, int64_t unk_index, const uint8_t* finished_in,
+                          const int64_t* targets, const float* weights, float* lse, int64_t* argmax,
+                          float* xent, int64_t* symbols_out, uint8_t* finished_out, uint8_t* mask_out,
+                          int32_t* unfinished_count, float* part, float* logits_out, int64_t ldl,
+                          int64_t M, int64_t V, int64_t K, int backend, void* stream);
+
+/* nm_beam_step reading LOGITS [B,k,V] and their logsumexp [B,k]: log-prob = logit - lse, the
+ * subtraction nm_log_softmax performs, so the selected indices and scores are bit-identical while
+ * the [B,k,V] log-prob tensor (beam_search_decoder.py:537-544) is never written.  unfinished_count
+ * (device int32, may be NULL) += hypotheses still unfinished after this step (the loop criterion of
+ * beam_search_decoder.py:330-355 without a host round trip per step). */
+int nm_beam_step_logits(const float* logits, const float* lse, const float* logprob_sum,
+                        const int32_t* lengths, const uint8_t* finished, float alpha, float* scores,
+                        int64_t* word_ids, int32_t* beam_ids, float* logprob_sum_out,
+                        int32_t* lengths_out, uint8_t* finished_out, int32_t* unfinished_count,
+                        void* scratch, int64_t B, int64_t k, int64_t V, void* stream);
+/* token_ids [steps+1, B, k] of the surviving hypotheses from the per-step records words
+ * [steps,B,k] i64 / parents [steps,B,k] i32 and first_symbols [B,k] (slot 0): what re-gathering
+ * the whole token history at every step computes (beam_search_decoder.py:546-551). */
+int nm_beam_backtrack(const int64_t* first_symbols, const int64_t* words, const int32_t* parents,
+                      int64_t* token_ids, int64_t B, int64_t k, int64_t steps, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -53,19 +53,28 @@ __device__ __forceinline__ float length_penalty(int32_t len, float alpha) {
   return (float)pow((double)x, (double)alpha);
 }
 
-__device__ __forceinline__ float cand_hyp(const float* __restrict__ logprobs,
+// `lse` (may be null): the rows of `logprobs` hold LOGITS and log-prob = logit - lse[row], the
+// same subtraction nm_log_softmax performs - the [B,k,V] log-prob tensor then never exists.
+__device__ __forceinline__ float cand_hyp(const float* __restrict__ logprobs, const float* __restrict__ lse,
                                           const float* __restrict__ logprob_sum,
                                           const uint8_t* __restrict__ finished, int64_t b, int64_t k,
                                           int64_t V, int32_t flat) {
   const int64_t j = flat / V, w = flat - j * V;
   const bool fin = finished[b * k + j] != 0;
-  const float lp = fin ? (w == 0 ? 0.f : -BEAM_INF) : logprobs[(b * k + j) * V + w];
+  float lp;
+  if (fin) {
+    lp = (w == 0 ? 0.f : -BEAM_INF);
+  } else {
+    lp = logprobs[(b * k + j) * V + w];
+    if (lse) lp = lp - lse[b * k + j];
+  }
   return logprob_sum[b * k + j] + lp;
 }
 
 // phase 1: grid (chunks, B).  cand_s/cand_i: [B, chunks, k]
 __global__ void __launch_bounds__(BEAM_THREADS)
-beam_local_topk_kernel(const float* __restrict__ logprobs, const float* __restrict__ logprob_sum,
+beam_local_topk_kernel(const float* __restrict__ logprobs, const float* __restrict__ lse,
+                       const float* __restrict__ logprob_sum,
                        const int32_t* __restrict__ lengths, const uint8_t* __restrict__ finished,
                        float alpha, float* __restrict__ cand_s, int32_t* __restrict__ cand_i,
                        int64_t k, int64_t V) {
@@ -86,7 +95,7 @@ beam_local_topk_kernel(const float* __restrict__ logprobs, const float* __restri
     const int64_t flat = base + it * BEAM_THREADS + threadIdx.x;  // coalesced
     if (flat < total) {
       const int64_t j = flat / V;
-      sc[it] = cand_hyp(logprobs, logprob_sum, finished, b, k, V, (int32_t)flat) / pen[j];
+      sc[it] = cand_hyp(logprobs, lse, logprob_sum, finished, b, k, V, (int32_t)flat) / pen[j];
     } else {
       sc[it] = -INFINITY;
     }
@@ -117,12 +126,13 @@ beam_local_topk_kernel(const float* __restrict__ logprobs, const float* __restri
 // phase 2: grid (B).  Merges chunks*k candidates, writes all outputs.
 __global__ void __launch_bounds__(BEAM_THREADS)
 beam_merge_kernel(const float* __restrict__ cand_s, const int32_t* __restrict__ cand_i,
-                  int64_t chunks, const float* __restrict__ logprobs,
+                  int64_t chunks, const float* __restrict__ logprobs, const float* __restrict__ lse,
                   const float* __restrict__ logprob_sum, const int32_t* __restrict__ lengths,
                   const uint8_t* __restrict__ finished, float* __restrict__ scores,
                   int64_t* __restrict__ word_ids, int32_t* __restrict__ beam_ids,
                   float* __restrict__ logprob_sum_out, int32_t* __restrict__ lengths_out,
-                  uint8_t* __restrict__ finished_out, int64_t k, int64_t V) {
+                  uint8_t* __restrict__ finished_out, int32_t* __restrict__ unfinished, int64_t k,
+                  int64_t V) {
   __shared__ float sm_s[32];
   __shared__ int32_t sm_i[32];
   const int64_t b = blockIdx.x;
@@ -151,10 +161,11 @@ beam_merge_kernel(const float* __restrict__ cand_s, const int32_t* __restrict__ 
       scores[o] = win.s;
       word_ids[o] = w;
       beam_ids[o] = (int32_t)j;
-      logprob_sum_out[o] = cand_hyp(logprobs, logprob_sum, finished, b, k, V, flat);
+      logprob_sum_out[o] = cand_hyp(logprobs, lse, logprob_sum, finished, b, k, V, flat);
       const int32_t fin = finished[b * k + j] ? 1 : 0;
       lengths_out[o] = lengths[b * k + j] + 1 - fin;
       finished_out[o] = (fin || w == 2) ? 1 : 0;  // END_TOKEN_INDEX = 2
+      if (unfinished && !(fin || w == 2)) atomicAdd(unfinished, 1);
     }
   }
 }
@@ -190,11 +201,11 @@ int64_t nm_beam_scratch(int64_t B, int64_t k, int64_t V) {
   return 2 * B * ceil_div(k * V, BEAM_CHUNK) * k;  // 4-byte words: scores then indices
 }
 
-int nm_beam_step(const float* logprobs, const float* logprob_sum, const int32_t* lengths,
-                 const uint8_t* finished, float alpha, float* scores, int64_t* word_ids,
-                 int32_t* beam_ids, float* logprob_sum_out, int32_t* lengths_out,
-                 uint8_t* finished_out, void* scratch, int64_t B, int64_t k, int64_t V,
-                 void* stream) {
+static int beam_step_impl(const float* logprobs, const float* lse, const float* logprob_sum,
+                          const int32_t* lengths, const uint8_t* finished, float alpha, float* scores,
+                          int64_t* word_ids, int32_t* beam_ids, float* logprob_sum_out, int32_t* lengths_out,
+                          uint8_t* finished_out, int32_t* unfinished, void* scratch, int64_t B, int64_t k,
+                          int64_t V, void* stream) {
   NM_REQUIRE(logprobs && logprob_sum && lengths && finished && scores && word_ids && beam_ids &&
                  logprob_sum_out && lengths_out && finished_out && scratch,
              NM_E_INVALID, "nm_beam_step: null pointer");
@@ -207,14 +218,34 @@ int nm_beam_step(const float* logprobs, const float* logprob_sum, const int32_t*
   float* cand_s = reinterpret_cast<float*>(scratch);
   int32_t* cand_i = reinterpret_cast<int32_t*>(scratch) + B * chunks * k;
   dim3 grid1((unsigned)chunks, (unsigned)B);
-  beam_local_topk_kernel<<<grid1, BEAM_THREADS, 0, s>>>(logprobs, logprob_sum, lengths, finished, alpha,
+  beam_local_topk_kernel<<<grid1, BEAM_THREADS, 0, s>>>(logprobs, lse, logprob_sum, lengths, finished, alpha,
                                                         cand_s, cand_i, k, V);
   NM_LAUNCH_CHECK("nm_beam_step(local)");
-  beam_merge_kernel<<<(unsigned)B, BEAM_THREADS, 0, s>>>(cand_s, cand_i, chunks, logprobs, logprob_sum,
+  beam_merge_kernel<<<(unsigned)B, BEAM_THREADS, 0, s>>>(cand_s, cand_i, chunks, logprobs, lse, logprob_sum,
                                                          lengths, finished, scores, word_ids, beam_ids,
-                                                         logprob_sum_out, lengths_out, finished_out, k, V);
+                                                         logprob_sum_out, lengths_out, finished_out, unfinished,
+                                                         k, V);
   NM_LAUNCH_CHECK("nm_beam_step(merge)");
   return NM_OK;
+}
+
+int nm_beam_step(const float* logprobs, const float* logprob_sum, const int32_t* lengths,
+                 const uint8_t* finished, float alpha, float* scores, int64_t* word_ids,
+                 int32_t* beam_ids, float* logprob_sum_out, int32_t* lengths_out,
+                 uint8_t* finished_out, void* scratch, int64_t B, int64_t k, int64_t V,
+                 void* stream) {
+  return beam_step_impl(logprobs, nullptr, logprob_sum, lengths, finished, alpha, scores, word_ids, beam_ids,
+                        logprob_sum_out, lengths_out, finished_out, nullptr, scratch, B, k, V, stream);
+}
+
+int nm_beam_step_logits(const float* logits, const float* lse, const float* logprob_sum,
+                        const int32_t* lengths, const uint8_t* finished, float alpha, float* scores,
+                        int64_t* word_ids, int32_t* beam_ids, float* logprob_sum_out, int32_t* lengths_out,
+                        uint8_t* finished_out, int32_t* unfinished_count, void* scratch, int64_t B,
+                        int64_t k, int64_t V, void* stream) {
+  NM_REQUIRE(lse, NM_E_INVALID, "nm_beam_step_logits: null lse");
+  return beam_step_impl(logits, lse, logprob_sum, lengths, finished, alpha, scores, word_ids, beam_ids,
+                        logprob_sum_out, lengths_out, finished_out, unfinished_count, scratch, B, k, V, stream);
 }
 
 int nm_beam_gather(const void* x, const int32_t* beam_ids, void* out, int64_t B, int64_t k,

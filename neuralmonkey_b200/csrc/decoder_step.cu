@@ -1,0 +1,702 @@
+// K4 (inference): ONE launch per decoding step of the RNN attention decoder - everything
+// Decoder.next_state (decoders/decoder.py:279-358 of the reference) does between the previous
+// symbol and the vector the vocabulary projection consumes:
+//
+//   x      = word_embeddings[symbol]                         (autoregressive.py:269-272)
+//   [r,u]  = sigmoid([x,h].W_g + b_g)                        (TF-1.12 GRUCell, ortho_gru_cell.py:44-53)
+//   c      = tanh([x, r*h].W_c + b_c);  h' = u*h + (1-u)*c
+//   y      = h'.W_q + b_p                                    (feed_forward.py:131-137)
+//   e_t    = sum_a v_a tanh(keys[t,a] + y_a) + b;  w = softmax(e) over ALL Tx, then *mask,
+//            / (sum + 1e-8);  ctx = sum_t w_t values[t]       (feed_forward.py:139-156)
+//   out    = tanh([h', x, ctx].W_o + b_o)   or maxout        (output_projection.py:115-160)
+//
+// Inference only (no dropout).  Exact fp32 on the CUDA cores: the step is a chain of five
+// dependent matrix-vector products per hypothesis, i.e. latency- and weight-streaming bound, not
+// tensor-pipe bound, and greedy / beam token parity wants fp32.
+//
+// Work split.  A thread-block CLUSTER of CL CTAs (1, 2, 4 or 8) owns DS_R = 8 rows (hypotheses).
+// Every product is split over the cluster by OUTPUT columns: a CTA streams only 1/CL of each
+// weight matrix (coalesced 16-byte loads, 8 in flight per thread) and multiplies it with all 8 rows
+// held transposed in shared memory ([k][row]: two LDS.128 feed 32 FMAs); the K range of a column
+// group is split over the threads of the CTA and reduced through shared memory in a fixed order
+// (deterministic).  The slices a CTA produces (r*h, h', the query projection, the context) are
+// written straight into the peers' shared memory (DSMEM) and a cluster barrier separates the phases.
+// The attention itself is split by rows: each CTA attends for 8/CL rows.  Its key / value tiles
+// are staged by 1-D TMA (cp.async.bulk + mbarrier ring) - the first ring of tiles is requested
+// before the GRU phases start, so the HBM-bound part of the step hides behind the latency-bound
+// part - and hypotheses of one sentence (beam search: `group` rows share an encoder row) reuse a
+// staged tile.  The softmax over Tx is a warp-shuffle reduction.
+#include <cooperative_groups.h>
+#include <stdlib.h>
+
+#include "common.cuh"
+#include "tc_ptx.cuh"
+
+namespace cg = cooperative_groups;
+
+namespace nm {
+
+constexpr int DS_R = 8;          // rows per cluster
+constexpr int DS_THREADS = 512;
+constexpr int DS_WARPS = DS_THREADS / 32;
+constexpr int DS_UNROLL = 8;     // weight rows in flight per thread
+constexpr int DS_SLOTS = 4;      // TMA ring depth
+constexpr int DS_RED_FLOATS = 352 * 32;   // K-split reduction scratch (see ds_panel)
+constexpr int DS_MAX_KSPLIT = 16;
+
+struct DecStep {
+  int rows, E, H, A, C, Tx, O, group, act, maxout;
+  int cl;            // cluster size
+  int tck, tcv;      // time steps per staged keys / values tile (TMA path)
+  int slot_floats;   // floats per ring slot (TMA path)
+  const int64_t* symbols;
+  const float* table;
+  const float* x_in;
+  const float* h_prev;
+  const int32_t* parent;
+  const float *Wg, *bg, *Wc, *bc, *Wq, *bq, *v, *abias;
+  const float *keys, *values, *mask;
+  const float *Wo, *bo;
+  float *x_out, *h_out, *ctx_out, *w_out, *out;
+};
+
+// Shared-memory carve-up (float offsets), the same arithmetic on host and device.
+struct DsLayout {
+  int xT, hT, rhT, hnT, ctxT, ug, res, red, qs, es, vs, ring, bars, total;
+  int res_ld;
+};
+
+__host__ __device__ inline int ds_align4(int x) { return (x + 3) & ~3; }
+
+__host__ __device__ inline DsLayout ds_layout(const DecStep& p, bool tma) {
+  DsLayout L;
+  const int rpc = DS_R / p.cl;
+  int maxn = 2 * p.H;
+  if (p.A > maxn) maxn = p.A;
+  const int no = (p.maxout ? 2 : 1) * p.O;
+  if (no > maxn) maxn = no;
+  L.res_ld = ds_align4((maxn + p.cl - 1) / p.cl + 16);
+  int o = 0;
+  L.xT = o;   o += ds_align4(p.E * DS_R);
+  L.hT = o;   o += ds_align4(p.H * DS_R);
+  L.rhT = o;  o += ds_align4(p.H * DS_R);
+  L.hnT = o;  o += ds_align4(p.H * DS_R);
+  L.ctxT = o; o += ds_align4(p.C * DS_R);
+  L.ug = o;   o += ds_align4(DS_R * ((p.H + p.cl - 1) / p.cl + 8));
+  L.res = o;  o += DS_R * L.res_ld;
+  L.red = o;  o += DS_RED_FLOATS;
+  L.qs = o;   o += ds_align4(rpc * p.A);
+  L.es = o;   o += ds_align4(rpc * p.Tx);
+  L.vs = o;   o += ds_align4(p.A);
+  L.ring = o; o += tma ? DS_SLOTS * p.slot_floats : 0;
+  L.bars = o; o += 4 * DS_SLOTS;            // DS_SLOTS mbarriers (8 bytes each) + padding
+  L.total = o;
+  return L;
+}
+
+__device__ __forceinline__ float ds_fast_tanh(float x) {   // the form attention.cu uses
+  return 1.f - __fdividef(2.f, 1.f + __expf(2.f * x));
+}
+
+__device__ __forceinline__ void bulk_load_1d(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(src)), "r"(bytes), "r"(bar)
+      : "memory");
+}
+
+struct DsSeg {
+  const float* inT;   // [len][DS_R] in shared memory
+  int len;
+};
+
+// res[r][local column] = sum_k in[r][k] * W[k][column] for this CTA's columns: two ranges of
+// G-wide column groups (nA groups from column colA, nB groups from column colB); local columns are
+// range A first, then range B.  K = sum of the segment lengths, weight row of segment element i =
+// (start of the segment in the virtual K range) + i.
+template <int G>
+__device__ __forceinline__ void ds_panel(const DsSeg* segs, int nseg, int K, const float* __restrict__ W,
+                                         int ldw, int colA, int nA, int colB, int nB,
+                                         float* __restrict__ res, int res_ld, float* __restrict__ red) {
+  const int ng = nA + nB;
+  constexpr int RG = DS_R * G;
+  for (int gb = 0; gb < ng; gb += DS_THREADS) {
+    const int nb = min(DS_THREADS, ng - gb);
+    int ksplit = DS_THREADS / nb;
+    if (ksplit > DS_MAX_KSPLIT) ksplit = DS_MAX_KSPLIT;
+    if (ksplit > K) ksplit = K > 0 ? K : 1;
+    const int g = threadIdx.x % nb, ks = threadIdx.x / nb;
+    const bool active = ks < ksplit;
+    const int gg = gb + g;
+    const int col = gg < nA ? colA + gg * G : colB + (gg - nA) * G;
+    const int kper = (K + ksplit - 1) / ksplit;
+    const int k0 = ks * kper;
+    const int k1 = min(K, k0 + kper);
+    float acc[DS_R][G];
+#pragma unroll
+    for (int r = 0; r < DS_R; ++r)
+#pragma unroll
+      for (int c = 0; c < G; ++c) acc[r][c] = 0.f;
+    if (active) {
+      int start = 0;
+      for (int s = 0; s < nseg; ++s) {
+        const int len = segs[s].len;
+        const int lo = max(k0, start), hi = min(k1, start + len);
+        if (lo < hi) {
+          const float* wp = W + (int64_t)lo * ldw + col;
+          const float* ip = segs[s].inT + (lo - start) * DS_R;
+          int k = lo;
+          for (; k + DS_UNROLL <= hi; k += DS_UNROLL) {
+            float w[DS_UNROLL][G];
+#pragma unroll
+            for (int u = 0; u < DS_UNROLL; ++u) {
+              if constexpr (G == 4) {
+                const float4 t = __ldg(reinterpret_cast<const float4*>(wp + (int64_t)u * ldw));
+                w[u][0] = t.x; w[u][1] = t.y; w[u][2] = t.z; w[u][3] = t.w;
+              } else {
+                w[u][0] = __ldg(wp + (int64_t)u * ldw);
+              }
+            }
+#pragma unroll
+            for (int u = 0; u < DS_UNROLL; ++u) {
+              const float4 i0 = *reinterpret_cast<const float4*>(ip + u * DS_R);
+              const float4 i1 = *reinterpret_cast<const float4*>(ip + u * DS_R + 4);
+              const float in[DS_R] = {i0.x, i0.y, i0.z, i0.w, i1.x, i1.y, i1.z, i1.w};
+#pragma unroll
+              for (int r = 0; r < DS_R; ++r)
+#pragma unroll
+                for (int c = 0; c < G; ++c) acc[r][c] = fmaf(in[r], w[u][c], acc[r][c]);
+            }
+            wp += (int64_t)DS_UNROLL * ldw;
+            ip += DS_UNROLL * DS_R;
+          }
+          for (; k < hi; ++k) {
+            float w[G];
+            if constexpr (G == 4) {
+              const float4 t = __ldg(reinterpret_cast<const float4*>(wp));
+              w[0] = t.x; w[1] = t.y; w[2] = t.z; w[3] = t.w;
+            } else {
+              w[0] = __ldg(wp);
+            }
+            const float4 i0 = *reinterpret_cast<const float4*>(ip);
+            const float4 i1 = *reinterpret_cast<const float4*>(ip + 4);
+            const float in[DS_R] = {i0.x, i0.y, i0.z, i0.w, i1.x, i1.y, i1.z, i1.w};
+#pragma unroll
+            for (int r = 0; r < DS_R; ++r)
+#pragma unroll
+              for (int c = 0; c < G; ++c) acc[r][c] = fmaf(in[r], w[c], acc[r][c]);
+            wp += ldw;
+            ip += DS_R;
+          }
+        }
+        start += len;
+      }
+    }
+    if (ksplit == 1) {
+      if (active) {
+#pragma unroll
+        for (int r = 0; r < DS_R; ++r)
+#pragma unroll
+          for (int c = 0; c < G; ++c) res[r * res_ld + gg * G + c] = acc[r][c];
+      }
+    } else {
+      // K-split reduction in a fixed order: upper half of the slices into the lower half, then the
+      // lower half through shared memory.  Element-major layout (slot fastest): conflict-free.
+      const int half = (ksplit + 1) >> 1;
+      const int S = half * nb;     // S * RG <= DS_RED_FLOATS for every (nb, ksplit) this loop can produce
+      if (active && ks >= half) {
+        const int slot = (ks - half) * nb + g;
+#pragma unroll
+        for (int r = 0; r < DS_R; ++r)
+#pragma unroll
+          for (int c = 0; c < G; ++c) red[(r * G + c) * S + slot] = acc[r][c];
+      }
+      __syncthreads();
+      if (active && ks < half && ks + half < ksplit) {
+        const int slot = ks * nb + g;
+#pragma unroll
+        for (int r = 0; r < DS_R; ++r)
+#pragma unroll
+          for (int c = 0; c < G; ++c) acc[r][c] += red[(r * G + c) * S + slot];
+      }
+      __syncthreads();
+      if (active && ks < half) {
+        const int slot = ks * nb + g;
+#pragma unroll
+        for (int r = 0; r < DS_R; ++r)
+#pragma unroll
+          for (int c = 0; c < G; ++c) red[(r * G + c) * S + slot] = acc[r][c];
+      }
+      __syncthreads();
+      for (int idx = threadIdx.x; idx < nb * RG; idx += DS_THREADS) {
+        const int e = idx / nb, g2 = idx - e * nb;
+        float sum = 0.f;
+        for (int h = 0; h < half; ++h) sum += red[e * S + h * nb + g2];
+        res[(e / G) * res_ld + (gb + g2) * G + (e % G)] = sum;
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// The slice of `total` G-wide groups CTA `rank` of `cl` owns: [first, first + count).
+__device__ __forceinline__ void ds_slice(int total, int cl, int rank, int& first, int& count) {
+  const int per = (total + cl - 1) / cl;
+  first = min(total, rank * per);
+  count = min(total, first + per) - first;
+}
+
+template <int G>
+__global__ void __launch_bounds__(DS_THREADS, 1) attn_decoder_step_kernel(const DecStep p) {
+  constexpr bool TMA = (G == 4);
+  cg::cluster_group cluster = cg::this_cluster();
+  const int CL = p.cl;
+  const int rank = (int)cluster.block_rank();
+  const int row0 = (int)(blockIdx.x / CL) * DS_R;
+  const int rpc = DS_R / CL;                   // rows this CTA attends for
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const DsLayout L = ds_layout(p, TMA);
+
+  extern __shared__ __align__(128) float smem[];
+  float* xT = smem + L.xT;
+  float* hT = smem + L.hT;
+  float* rhT = smem + L.rhT;
+  float* hnT = smem + L.hnT;
+  float* ctxT = smem + L.ctxT;
+  float* ugs = smem + L.ug;
+  float* res = smem + L.res;
+  float* red = smem + L.red;
+  float* qs = smem + L.qs;
+  float* es = smem + L.es;
+  float* vs = smem + L.vs;
+  float* ring = smem + L.ring;
+  const uint32_t bar0 = smem_u32(smem + L.bars);
+  const int res_ld = L.res_ld;
+
+  // ---- attention schedule of this CTA: runs of owned rows that share an encoder row -------------
+  // (at most rpc runs; computed redundantly by every thread: a handful of integer operations)
+  const int my0 = row0 + rank * rpc;                      // first global row this CTA attends for
+  const int nmy = max(0, min(rpc, p.rows - my0));         // valid ones
+  const int nk = TMA ? (p.Tx + p.tck - 1) / p.tck : 1;    // tiles per run: keys, then values
+  const int nv = TMA ? (p.Tx + p.tcv - 1) / p.tcv : 1;
+  int nruns = 0;
+  {
+    int prev = -1;
+    for (int j = 0; j < nmy; ++j) {
+      const int e = (my0 + j) / p.group;
+      if (e != prev) { ++nruns; prev = e; }
+    }
+  }
+  const int ntiles = nruns * (nk + nv);
+
+  // tile i of the schedule -> source address and size (TMA path only)
+  auto tile_src = [&](int i, const float*& src, uint32_t& bytes) {
+    const int run = i / (nk + nv), j = i - run * (nk + nv);
+    int e = -1, seen = -1, prev = -1;
+    for (int q = 0; q < nmy; ++q) {
+      const int eq = (my0 + q) / p.group;
+      if (eq != prev) { ++seen; prev = eq; }
+      if (seen == run) { e = eq; break; }
+    }
+    if (j < nk) {
+      const int t0 = j * p.tck, nt = min(p.tck, p.Tx - t0);
+      src = p.keys + ((int64_t)e * p.Tx + t0) * p.A;
+      bytes = (uint32_t)(nt * p.A * 4);
+    } else {
+      const int t0 = (j - nk) * p.tcv, nt = min(p.tcv, p.Tx - t0);
+      src = p.values + ((int64_t)e * p.Tx + t0) * p.C;
+      bytes = (uint32_t)(nt * p.C * 4);
+    }
+  };
+  auto issue_tile = [&](int i) {   // one thread
+    const float* src;
+    uint32_t bytes;
+    tile_src(i, src, bytes);
+    const int slot = i % DS_SLOTS;
+    mbar_expect_tx(bar0 + 8u * slot, bytes);
+    bulk_load_1d(smem_u32(ring + slot * p.slot_floats), src, bytes, bar0 + 8u * slot);
+  };
+
+  if (TMA && tid == 0) {
+    for (int s = 0; s < DS_SLOTS; ++s) mbar_init(bar0 + 8u * s, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  __syncthreads();
+  if (TMA && tid == 0) {
+    const int first = min(ntiles, DS_SLOTS);
+    for (int i = 0; i < first; ++i) issue_tile(i);   // in flight while the GRU phases run
+  }
+
+  // ---- phase 0: inputs of the 8 rows, transposed into shared memory -----------------------------
+  for (int idx = tid; idx < DS_R * p.E; idx += DS_THREADS) {
+    const int r = idx / p.E, k = idx - r * p.E;
+    const int grow = row0 + r;
+    float val = 0.f;
+    if (grow < p.rows) {
+      val = p.x_in ? p.x_in[(int64_t)grow * p.E + k] : p.table[(int64_t)p.symbols[grow] * p.E + k];
+      if (p.x_out && rank == 0) p.x_out[(int64_t)grow * p.E + k] = val;
+    }
+    xT[k * DS_R + r] = val;
+  }
+  for (int idx = tid; idx < DS_R * p.H; idx += DS_THREADS) {
+    const int r = idx / p.H, k = idx - r * p.H;
+    const int grow = row0 + r;
+    float val = 0.f;
+    if (grow < p.rows) {
+      const int src = p.parent ? (grow / p.group) * p.group + p.parent[grow] : grow;
+      val = p.h_prev[(int64_t)src * p.H + k];
+    }
+    hT[k * DS_R + r] = val;
+  }
+  for (int a = tid; a < p.A; a += DS_THREADS) vs[a] = p.v[a];
+  __syncthreads();
+  cluster.sync();   // every CTA of the cluster has started: its shared memory may be written remotely
+
+  // ---- phase 1: gates of this CTA's hidden units -------------------------------------------------
+  int uf, un;   // first unit group / number of unit groups
+  ds_slice((p.H + G - 1) / G, CL, rank, uf, un);
+  const int u0 = uf * G;
+  const int nu = min(p.H, u0 + un * G) - u0;   // units this CTA owns (0 when H is small and CL large)
+  {
+    const DsSeg segs[2] = {{xT, p.E}, {hT, p.H}};
+    ds_panel<G>(segs, 2, p.E + p.H, p.Wg, 2 * p.H, u0, un, p.H + u0, un, res, res_ld, red);
+    for (int idx = tid; idx < DS_R * nu; idx += DS_THREADS) {
+      const int r = idx / nu, ul = idx - r * nu;
+      const int u = u0 + ul;
+      const float rr = sigmoidf_(res[r * res_ld + ul] + p.bg[u]);
+      const float uu = sigmoidf_(res[r * res_ld + un * G + ul] + p.bg[p.H + u]);
+      ugs[r * nu + ul] = uu;
+      const float rh = rr * hT[u * DS_R + r];
+      for (int c = 0; c < CL; ++c) cluster.map_shared_rank(rhT, c)[u * DS_R + r] = rh;
+    }
+  }
+  cluster.sync();
+
+  // ---- phase 2: candidate and new state ------------------------------------------------------------
+  {
+    const DsSeg segs[2] = {{xT, p.E}, {rhT, p.H}};
+    ds_panel<G>(segs, 2, p.E + p.H, p.Wc, p.H, u0, un, 0, 0, res, res_ld, red);
+    for (int idx = tid; idx < DS_R * nu; idx += DS_THREADS) {
+      const int r = idx / nu, ul = idx - r * nu;
+      const int u = u0 + ul;
+      const float c = tanhf(res[r * res_ld + ul] + p.bc[u]);
+      const float uu = ugs[r * nu + ul];
+      const float hn = uu * hT[u * DS_R + r] + (1.f - uu) * c;
+      for (int cc = 0; cc < CL; ++cc) cluster.map_shared_rank(hnT, cc)[u * DS_R + r] = hn;
+      if (row0 + r < p.rows) p.h_out[(int64_t)(row0 + r) * p.H + u] = hn;
+    }
+  }
+  cluster.sync();
+
+  // ---- phase 3: query projection, delivered to the CTA that attends for the row --------------------
+  {
+    int af, an;
+    ds_slice((p.A + G - 1) / G, CL, rank, af, an);
+    const int a0 = af * G;
+    const int na = min(p.A, a0 + an * G) - a0;
+    const DsSeg segs[1] = {{hnT, p.H}};
+    ds_panel<G>(segs, 1, p.H, p.Wq, p.A, a0, an, 0, 0, res, res_ld, red);
+    for (int idx = tid; idx < DS_R * na; idx += DS_THREADS) {
+      const int r = idx / na, al = idx - r * na;
+      const int a = a0 + al;
+      const float q = res[r * res_ld + al] + p.bq[a];
+      cluster.map_shared_rank(qs, r / rpc)[(r % rpc) * p.A + a] = q;
+    }
+  }
+  cluster.sync();
+
+  // ---- phase 4: attention for the rows this CTA owns ---------------------------------------------------
+  {
+    const float abias = p.abias[0];
+    int tile = 0;          // position in the TMA schedule
+    int j0 = 0;            // first row (local to this CTA) of the current run
+    while (j0 < nmy) {
+      const int e = (my0 + j0) / p.group;
+      int cnt = 1;
+      while (j0 + cnt < nmy && (my0 + j0 + cnt) / p.group == e) ++cnt;
+      // energies: one warp per time step, lanes over A; the rows of the run share the key loads
+      for (int kt = 0; kt < nk; ++kt) {
+        const float* kc;
+        int t0, nt;
+        if (TMA) {
+          mbar_wait(bar0 + 8u * (tile % DS_SLOTS), (uint32_t)((tile / DS_SLOTS) & 1));
+          kc = ring + (tile % DS_SLOTS) * p.slot_floats;
+          t0 = kt * p.tck;
+          nt = min(p.tck, p.Tx - t0);
+        } else {
+          kc = p.keys + (int64_t)e * p.Tx * p.A;
+          t0 = 0;
+          nt = p.Tx;
+        }
+        for (int tl = warp; tl < nt; tl += DS_WARPS) {
+          float acc[DS_R];
+#pragma unroll
+          for (int j = 0; j < DS_R; ++j) acc[j] = 0.f;
+          const float* kr = kc + tl * p.A;
+          if constexpr (G == 4) {
+            for (int a4 = lane; a4 < p.A / 4; a4 += 32) {
+              const float4 k4 = *reinterpret_cast<const float4*>(kr + 4 * a4);
+              const float4 v4 = *reinterpret_cast<const float4*>(vs + 4 * a4);
+#pragma unroll
+              for (int j = 0; j < DS_R; ++j) {
+                if (j < cnt) {
+                  const float4 q4 = *reinterpret_cast<const float4*>(qs + (j0 + j) * p.A + 4 * a4);
+                  acc[j] = fmaf(v4.x, ds_fast_tanh(k4.x + q4.x), acc[j]);
+                  acc[j] = fmaf(v4.y, ds_fast_tanh(k4.y + q4.y), acc[j]);
+                  acc[j] = fmaf(v4.z, ds_fast_tanh(k4.z + q4.z), acc[j]);
+                  acc[j] = fmaf(v4.w, ds_fast_tanh(k4.w + q4.w), acc[j]);
+                }
+              }
+            }
+          } else {
+            for (int a = lane; a < p.A; a += 32) {
+              const float k = kr[a], vv = vs[a];
+#pragma unroll
+              for (int j = 0; j < DS_R; ++j)
+                if (j < cnt) acc[j] = fmaf(vv, ds_fast_tanh(k + qs[(j0 + j) * p.A + a]), acc[j]);
+            }
+          }
+#pragma unroll
+          for (int j = 0; j < DS_R; ++j) {
+            if (j < cnt) {
+              const float en = warp_sum(acc[j]) + abias;
+              if (lane == 0) es[(j0 + j) * p.Tx + t0 + tl] = en;
+            }
+          }
+        }
+        __syncthreads();   // the tile is consumed (and, after the last one, the energies are complete)
+        if (TMA) {
+          if (tid == 0 && tile + DS_SLOTS < ntiles) issue_tile(tile + DS_SLOTS);
+          ++tile;
+        }
+      }
+      // softmax over ALL Tx, then mask and renormalise: one warp per row of the run
+      for (int j = warp; j < cnt; j += DS_WARPS) {
+        float* er = es + (j0 + j) * p.Tx;
+        const int64_t grow = my0 + j0 + j;
+        float mx = -INFINITY;
+        for (int t = lane; t < p.Tx; t += 32) mx = fmaxf(mx, er[t]);
+        mx = warp_max(mx);
+        float s = 0.f;
+        for (int t = lane; t < p.Tx; t += 32) s += expf(er[t] - mx);
+        s = warp_sum(s);
+        float ws = 0.f;
+        for (int t = lane; t < p.Tx; t += 32) {
+          float pr = expf(er[t] - mx) / s;
+          if (p.mask) pr *= p.mask[(int64_t)e * p.Tx + t];
+          er[t] = pr;
+          ws += pr;
+        }
+        if (p.mask) {
+          const float norm = warp_sum(ws) + 1e-8f;
+          for (int t = lane; t < p.Tx; t += 32) er[t] = er[t] / norm;
+        }
+        __syncwarp();
+        if (p.w_out)
+          for (int t = lane; t < p.Tx; t += 32) p.w_out[grow * p.Tx + t] = er[t];
+      }
+      __syncthreads();
+      // context: thread = (column group, time sub-slice); partial sums stay in registers over the tiles
+      const int ncg = (p.C + G - 1) / G;          // host guarantees ncg <= DS_THREADS
+      const int nts = DS_THREADS / ncg;           // time sub-slices
+      const int cgi = tid % ncg, ts = tid / ncg;
+      const bool cact = ts < nts;
+      float cacc[DS_R][G];
+#pragma unroll
+      for (int j = 0; j < DS_R; ++j)
+#pragma unroll
+        for (int c = 0; c < G; ++c) cacc[j][c] = 0.f;
+      for (int vt = 0; vt < nv; ++vt) {
+        const float* vc;
+        int t0, nt;
+        if (TMA) {
+          mbar_wait(bar0 + 8u * (tile % DS_SLOTS), (uint32_t)((tile / DS_SLOTS) & 1));
+          vc = ring + (tile % DS_SLOTS) * p.slot_floats;
+          t0 = vt * p.tcv;
+          nt = min(p.tcv, p.Tx - t0);
+        } else {
+          vc = p.values + (int64_t)e * p.Tx * p.C;
+          t0 = 0;
+          nt = p.Tx;
+        }
+        if (cact) {
+          for (int tl = ts; tl < nt; tl += nts) {
+            float val[G];
+            if constexpr (G == 4) {
+              const float4 t4 = *reinterpret_cast<const float4*>(vc + tl * p.C + 4 * cgi);
+              val[0] = t4.x; val[1] = t4.y; val[2] = t4.z; val[3] = t4.w;
+            } else {
+              val[0] = vc[tl * p.C + cgi];
+            }
+#pragma unroll
+            for (int j = 0; j < DS_R; ++j) {
+              if (j < cnt) {
+                const float wt = es[(j0 + j) * p.Tx + t0 + tl];
+#pragma unroll
+                for (int c = 0; c < G; ++c) cacc[j][c] = fmaf(wt, val[c], cacc[j][c]);
+              }
+            }
+          }
+        }
+        __syncthreads();
+        if (TMA) {
+          if (tid == 0 && tile + DS_SLOTS < ntiles) issue_tile(tile + DS_SLOTS);
+          ++tile;
+        }
+      }
+      // reduce the time sub-slices row by row (fixed order), broadcast the context to the cluster
+#pragma unroll
+      for (int j = 0; j < DS_R; ++j) {
+        if (j < cnt) {      // uniform across the CTA
+          if (cact) {
+#pragma unroll
+            for (int c = 0; c < G; ++c) red[(ts * ncg + cgi) * G + c] = cacc[j][c];
+          }
+          __syncthreads();
+          for (int col = tid; col < p.C; col += DS_THREADS) {
+            const int g2 = col / G, c = col - g2 * G;
+            float sum = 0.f;
+            for (int s2 = 0; s2 < nts; ++s2) sum += red[(s2 * ncg + g2) * G + c];
+            const int rl = rank * rpc + j0 + j;          // row index inside the cluster
+            for (int cc = 0; cc < CL; ++cc) cluster.map_shared_rank(ctxT, cc)[col * DS_R + rl] = sum;
+            if (p.ctx_out) p.ctx_out[(int64_t)(my0 + j0 + j) * p.C + col] = sum;
+          }
+          __syncthreads();
+        }
+      }
+      j0 += cnt;
+    }
+    // rows beyond `rows` (tail cluster): their context columns must be defined for the last product
+    for (int idx = tid; idx < (rpc - nmy) * p.C; idx += DS_THREADS) {
+      const int jj = nmy + idx / p.C, col = idx % p.C;
+      const int rl = rank * rpc + jj;
+      for (int cc = 0; cc < CL; ++cc) cluster.map_shared_rank(ctxT, cc)[col * DS_R + rl] = 0.f;
+    }
+  }
+  cluster.sync();
+
+  // ---- phase 5: deep output ---------------------------------------------------------------------------
+  {
+    int of, on;
+    ds_slice((p.O + G - 1) / G, CL, rank, of, on);
+    const int o0 = of * G;
+    const int no = min(p.O, o0 + on * G) - o0;
+    const DsSeg segs[3] = {{hnT, p.H}, {xT, p.E}, {ctxT, p.C}};
+    const int ldo = (p.maxout ? 2 : 1) * p.O;
+    ds_panel<G>(segs, 3, p.H + p.E + p.C, p.Wo, ldo, o0, on, p.O + o0, p.maxout ? on : 0, res, res_ld, red);
+    for (int idx = tid; idx < DS_R * no; idx += DS_THREADS) {
+      const int r = idx / no, ol = idx - r * no;
+      const int o = o0 + ol;
+      if (row0 + r >= p.rows) continue;
+      float y = res[r * res_ld + ol] + p.bo[o];
+      if (p.maxout) {
+        const float y2 = res[r * res_ld + on * G + ol] + p.bo[p.O + o];
+        y = fmaxf(y, y2);
+      } else {
+        y = apply_act(y, p.act);
+      }
+      p.out[(int64_t)(row0 + r) * p.O + o] = y;
+    }
+  }
+}
+
+}  // namespace nm
+
+using namespace nm;
+
+extern "C" {
+
+int nm_attn_decoder_step_fwd(const int64_t* symbols, const float* emb_table, const float* x_in,
+                             const float* h_prev, const int32_t* parent, const float* Wg, const float* bg,
+                             const float* Wc, const float* bc, const float* Wq, const float* bq,
+                             const float* v, const float* att_bias, const float* keys,
+                             const float* values, const float* mask, const float* Wo, const float* bo,
+                             float* x_out, float* h_out, float* ctx_out, float* weights_out, float* out,
+                             int64_t rows, int64_t group, int64_t E, int64_t H, int64_t A, int64_t C,
+                             int64_t Tx, int64_t O, int act, int maxout, void* stream) {
+  NM_REQUIRE((symbols && emb_table) || x_in, NM_E_INVALID,
+             "nm_attn_decoder_step_fwd: need symbols + emb_table, or x_in");
+  NM_REQUIRE(h_prev && Wg && bg && Wc && bc && Wq && bq && v && att_bias && keys && values && Wo && bo &&
+                 h_out && out,
+             NM_E_INVALID, "nm_attn_decoder_step_fwd: null pointer");
+  NM_REQUIRE(h_prev != h_out, NM_E_INVALID, "nm_attn_decoder_step_fwd: h_out must not alias h_prev");
+  NM_REQUIRE(rows > 0 && group > 0 && E > 0 && H > 0 && A > 0 && C > 0 && Tx > 0 && O > 0, NM_E_INVALID,
+             "nm_attn_decoder_step_fwd: bad sizes");
+  NM_REQUIRE(rows < (1 << 24) && Tx < (1 << 20), NM_E_UNSUPPORTED, "nm_attn_decoder_step_fwd: too large");
+  DecStep p{};
+  p.rows = (int)rows; p.E = (int)E; p.H = (int)H; p.A = (int)A; p.C = (int)C; p.Tx = (int)Tx; p.O = (int)O;
+  p.group = (int)group; p.act = act; p.maxout = maxout ? 1 : 0;
+  p.symbols = x_in ? nullptr : symbols; p.table = emb_table; p.x_in = x_in; p.h_prev = h_prev; p.parent = parent;
+  p.Wg = Wg; p.bg = bg; p.Wc = Wc; p.bc = bc; p.Wq = Wq; p.bq = bq; p.v = v; p.abias = att_bias;
+  p.keys = keys; p.values = values; p.mask = mask; p.Wo = Wo; p.bo = bo;
+  p.x_out = x_out; p.h_out = h_out; p.ctx_out = ctx_out; p.w_out = weights_out; p.out = out;
+
+  // vector path: every row the kernel reads with 16-byte loads is 16-byte aligned
+  auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+  const bool vec = (E % 4 == 0) && (H % 4 == 0) && (A % 4 == 0) && (C % 4 == 0) && (O % 4 == 0) &&
+                   al16(Wg) && al16(Wc) && al16(Wq) && al16(Wo) && al16(keys) && al16(values);
+  const int g = vec ? 4 : 1;
+  NM_REQUIRE(ceil_div(C, g) <= DS_THREADS, NM_E_UNSUPPORTED,
+             "nm_attn_decoder_step_fwd: context size %lld too large for one CTA", (long long)C);
+
+  // cluster size: as many CTAs as fill the chip, at most 8, at least one attended row per CTA
+  const int64_t clusters = ceil_div(rows, DS_R);
+  int cl = 8;
+  while (cl > 1 && clusters * cl > (int64_t)sm_count()) cl >>= 1;
+  const char* env = getenv("NMB200_DECSTEP_CLUSTER");
+  if (env && *env) {
+    const int want = atoi(env);
+    if (want == 1 || want == 2 || want == 4 || want == 8) cl = want;
+  }
+  p.cl = cl;
+
+  // ring slots: as large as the shared memory left over allows, whole time steps of keys / values
+  size_t smem_bytes = 0;
+  if (vec) {
+    p.slot_floats = 0;
+    const DsLayout base = ds_layout(p, true);
+    const int64_t avail = (int64_t)(227 * 1024 - 1024) / 4 - base.total;
+    int64_t slot = avail / DS_SLOTS;
+    slot -= slot % 32;                                       // 128-byte granularity
+    const int64_t need = (A > C ? A : C);
+    NM_REQUIRE(slot >= need, NM_E_UNSUPPORTED,
+               "nm_attn_decoder_step_fwd: sizes leave no room for a key/value tile in shared memory");
+    int64_t cap = 8192;                                      // 32 KB per tile is plenty
+    if (slot > cap) slot = cap - cap % 32;
+    if (slot < need) slot = (need + 31) / 32 * 32;
+    p.slot_floats = (int)slot;
+    p.tck = (int)(slot / A); if (p.tck > Tx) p.tck = (int)Tx;
+    p.tcv = (int)(slot / C); if (p.tcv > Tx) p.tcv = (int)Tx;
+    smem_bytes = sizeof(float) * (size_t)ds_layout(p, true).total;
+  } else {
+    p.slot_floats = 0; p.tck = (int)Tx; p.tcv = (int)Tx;
+    smem_bytes = sizeof(float) * (size_t)ds_layout(p, false).total;
+  }
+  NM_REQUIRE(smem_bytes <= 227 * 1024, NM_E_UNSUPPORTED,
+             "nm_attn_decoder_step_fwd: needs %zu bytes of shared memory", smem_bytes);
+
+  auto kern = vec ? attn_decoder_step_kernel<4> : attn_decoder_step_kernel<1>;
+  static bool attr_done[2] = {false, false};
+  if (!attr_done[vec ? 1 : 0]) {
+    NM_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_done[vec ? 1 : 0] = true;
+  }
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)(clusters * cl));
+  cfg.blockDim = dim3(DS_THREADS);
+  cfg.dynamicSmemBytes = smem_bytes;
+  cfg.stream = (cudaStream_t)stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = (unsigned)cl;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  NM_CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, p));
+  NM_LAUNCH_CHECK("nm_attn_decoder_step_fwd");
+  return NM_OK;
+}
+
+}  // extern "C"

@@ -369,21 +369,56 @@ class AutoregressiveDecoder(ModelPart):
         return loop_state
 
     @tensor
+    def _runtime(self) -> Dict[str, Any]:
+        """The histories of the greedy loop, stacked time-major.  Subclasses with a fused decoding engine
+        override this (decoders/decoder.py); `logits` may then be None: they are re-computed from the
+        output states by ONE batched projection when somebody asks for them, `xent` / `argmax` / `lse` come
+        from the fused step."""
+        hist = self.runtime_loop_result.histories
+        return {"logits": torch.stack(hist.logits, 0), "output_states": torch.stack(hist.output_states, 0),
+                "symbols": torch.stack(hist.output_symbols, 0), "mask": torch.stack(hist.output_mask, 0)}
+
+    @tensor
     def runtime_logits(self) -> torch.Tensor:
-        return torch.stack(self.runtime_loop_result.histories.logits, 0)
+        logits = self._runtime["logits"]
+        if logits is None:
+            # the same GEMM instances the steps ran, over all steps at once: bit-identical values
+            states = self._runtime["output_states"]
+            steps, bsz, dim = states.shape
+            with torch.no_grad():
+                dummy_t = torch.zeros(steps * bsz, dtype=torch.int64, device=states.device)
+                dummy_w = torch.zeros(steps * bsz, dtype=torch.float32, device=states.device)
+                _, _, _, logits = ops.logits_xent(
+                    states.reshape(steps * bsz, dim), self.decoding_w.detach(),
+                    self.decoding_b.detach() if self.decoding_b is not None else None, dummy_t, dummy_w,
+                    self._unk_index, self._w_transposed, keep_logits=True)
+            logits = logits.view(steps, bsz, -1)
+        return logits
 
     @tensor
     def runtime_output_states(self) -> torch.Tensor:
-        return torch.stack(self.runtime_loop_result.histories.output_states, 0)
+        return self._runtime["output_states"]
 
     @tensor
     def runtime_mask(self) -> torch.Tensor:
-        return torch.stack(self.runtime_loop_result.histories.output_mask, 0)
+        return self._runtime["mask"]
 
     @tensor
     def runtime_symbols(self) -> torch.Tensor:
         """[time, batch] greedy symbols (argmax over the full vocabulary, PAD once finished)."""
-        return torch.stack(self.runtime_loop_result.histories.output_symbols, 0)
+        return self._runtime["symbols"]
+
+    @tensor
+    def runtime_argmax(self) -> torch.Tensor:
+        """[time, batch] argmax of the step's logits over the full vocabulary WITHOUT the `* unfinished`
+        masking: what GreedyRunner's host-side np.argmax over runtime_logprobs yields (runners/runner.py:49)."""
+        arg = self._runtime.get("argmax")
+        if arg is not None:
+            return arg
+        logits = self.runtime_logits
+        steps, bsz, vocab = logits.shape
+        _lse, _xent, arg = ops.xent_rows(logits.reshape(steps * bsz, vocab), want_argmax=True)
+        return arg.view(steps, bsz)
 
     @tensor
     def decoded(self) -> torch.Tensor:
@@ -396,6 +431,9 @@ class AutoregressiveDecoder(ModelPart):
 
     @tensor
     def _runtime_lse(self) -> torch.Tensor:
+        lse = self._runtime.get("lse")
+        if lse is not None:
+            return lse.reshape(-1)
         logits = self.runtime_logits
         steps, bsz, vocab = logits.shape
         return ops.xent_rows(logits.reshape(steps * bsz, vocab))[0]
@@ -409,6 +447,9 @@ class AutoregressiveDecoder(ModelPart):
     @tensor
     def runtime_xents(self) -> torch.Tensor:
         """[batch, min_time] (autoregressive.py:351-366)."""
+        xent = self._runtime.get("xent")
+        if xent is not None:
+            return xent.t()
         logits = self.runtime_logits
         targets = self.train_inputs
         min_time = min(targets.shape[0], logits.shape[0])

@@ -231,9 +231,32 @@ class BeamSearchDecoder(ModelPart):
                                           lengths=res["lengths"], finished=res["finished"]),
             attention_loop_states=[])
 
+    use_fused_step = True
+
+    def _fused_outputs(self, engine) -> BeamSearchOutput:
+        parent = self.parent_decoder
+        res = engine.beam(self.beam_size, self.max_steps, self.length_normalization)
+        dev = runtime.device()
+        feedables = DecoderFeedables(step=res["steps"] + 1, finished=res["finished"].view(-1),
+                                     embedded_input=torch.zeros(0, device=dev), other=None)
+        dec_ls = LoopState(histories=parent.get_initial_histories(), constants=None, feedables=feedables)
+        logprobs = ops.log_softmax_from_lse(res["logits"].reshape(-1, res["logits"].shape[-1]),
+                                            res["lse"].reshape(-1)).view(res["logits"].shape)
+        return BeamSearchOutput(
+            last_search_step_output=SearchResults(scores=res["scores"], token_ids=res["token_ids"]),
+            last_dec_loop_state=dec_ls,
+            last_search_state=SearchState(logprob_sum=res["logprob_sum"], prev_logprobs=logprobs,
+                                          lengths=res["lengths"], finished=res["finished"]),
+            attention_loop_states=[])
+
     @tensor
     def outputs(self) -> BeamSearchOutput:
         parent = self.parent_decoder
+        engine = getattr(parent, "decode_engine", None) if self.use_fused_step else None
+        if engine is not None:
+            # RNN parent: the fused step kernel follows the beam indices itself and reads the UN-tiled
+            # encoder tensors (`group` = beam size), so nothing is tiled or re-gathered here
+            return self._fused_outputs(engine)
         enc_states, enc_masks = parent.encoder_states, parent.encoder_masks
         # beam-tiled encoder tensors for the duration of the search (:174-186)
         tiled_states = [self.expand_to_beam(s) for s in enc_states()]

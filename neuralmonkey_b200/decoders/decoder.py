@@ -328,6 +328,36 @@ class Decoder(AutoregressiveDecoder):
                                      attention_histories=att_loop_states)
         return output, new_feedables, new_histories
 
+    # -- runtime: the whole greedy loop on the fused step kernel -------------------------------------
+    use_fused_decoding = True
+
+    @property
+    def decode_engine(self):
+        """The RNNDecodeEngine of this decoder, or None when its structure is outside what the fused
+        step covers (decoders/rnn_decode.py)."""
+        from neuralmonkey_b200.decoders import rnn_decode
+        if not self.use_fused_decoding or not rnn_decode.supported(self):
+            return None
+        if "_decode_engine" not in self.__dict__:
+            self.__dict__["_decode_engine"] = rnn_decode.RNNDecodeEngine(self)
+        return self.__dict__["_decode_engine"]
+
+    @tensor
+    def _runtime(self):
+        engine = self.decode_engine
+        if engine is None or (self.train_mode and self.dropout_keep_prob < 1.0):
+            return AutoregressiveDecoder._runtime.fget(self)
+        gold = gold_mask = None
+        if self._train_ids_host is not None:
+            gold, gold_mask = self.train_inputs, self.train_mask
+        res = engine.greedy(self.max_output_len, gold, gold_mask)
+        key = "{}_run".format(self.name)
+        self.attentions[0].histories[key] = res["weights"]
+        self.attentions[0].visualize_attention(key)
+        return {"logits": None, "output_states": res["output_states"], "symbols": res["symbols"],
+                "mask": res["mask"], "argmax": res["argmax"], "lse": res["lse"], "xent": res["xent"],
+                "rnn_outputs": res["rnn_outputs"], "contexts": res["contexts"]}
+
     def finalize_loop(self, final_loop_state: LoopState, train_mode: bool) -> None:
         for att_state, attn_obj in zip(final_loop_state.histories.other.attention_histories,
                                        self.attentions):

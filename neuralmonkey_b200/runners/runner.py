@@ -23,11 +23,9 @@ class GreedyRunner(BaseRunner):
             decoder = runner.decoder
             # argmax over the full vocabulary of the (single-session) log-probs == the greedy
             # feedback symbols without the `* unfinished` masking (runner.py:45-49)
-            logits = decoder.runtime_logits
-            steps, bsz, vocab = logits.shape
-            from neuralmonkey_b200 import ops
-            _lse, _xent, arg = ops.xent_rows(logits.reshape(steps * bsz, vocab), want_argmax=True)
-            symbols = arg.view(steps, bsz).cpu().numpy()
+            arg = decoder.runtime_argmax                      # [time, batch], computed on the device
+            bsz = arg.shape[1]
+            symbols = arg.cpu().numpy()
             train_loss = runtime_loss = 0.0
             if self.compute_losses:
                 train_loss = float(decoder.train_loss)

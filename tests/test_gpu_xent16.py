@@ -64,8 +64,10 @@ def test_gemm_f16(m, n, k, transposed, beta):
     want = (want.t() if transposed else want) + beta * c0.double()
     c = c0.clone().cuda()
     ad, bd = a.cuda(), b.cuda()
+    alpha_d, scale_d = alpha.cuda(), row_scale.cuda()      # kept alive: the call only sees raw pointers
     lib.call("nm_gemm_f16", m, n, k, lib.ptr(ad), kp, lib.ptr(bd), kp, lib.ptr(c), c.stride(0),
-             lib.ptr(alpha.cuda()), lib.ptr(row_scale.cuda()), beta, transposed, lib.stream())
+             lib.ptr(alpha_d), lib.ptr(scale_d), beta, transposed, lib.stream())
+    torch.cuda.synchronize()
     assert _rel(c, want) < 1e-5
 
 
