@@ -1,21 +1,31 @@
 #!/usr/bin/env python3
-"""Benchmark of the hot path BASELINE.json names: training throughput of the Bahdanau en-de
-configuration (examples/translation.ini dims: E = He = H = O = 300, C = A = 600, Tx = Ty = 50,
-batch 256 per GPU, synthetic V = 32000) in non-pad target tokens per second over full
-optimizer steps (forward + backward + [all-reduce] + clip + Adam).
+"""Benchmark of the hot path BASELINE.json names.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload ende|transformer]
 
-One JSON line on stdout (rank 0).  `value` is device-resident throughput (ids already in
-HBM); `e2e` feeds every step from pinned host memory and reads the loss back.  The
-`roofline` object describes the dominant kernel (timed with CUDA events inside the timed
-steps), `cpu_baseline` times the CPU oracle restatement of the same step on a bounded sample.
-`--impl reference` runs ONLY that CPU restatement (the reference's TF-1.12 path cannot run
-here: SURVEY.md 8(c)).
+Default workload (the configuration BASELINE.json's metric is quoted on): training throughput of the
+Bahdanau en-de model (examples/translation.ini dims: E = He = H = O = 300, C = A = 600, Tx = Ty = 50,
+batch 256 per GPU, synthetic V = 32000) in non-pad target tokens per second over full optimizer steps
+(forward + backward + [gradient exchange] + clip + Adam).  `--workload transformer` runs the 1->8 GPU
+configuration BASELINE.json names for scaling (tests/transformer.ini at L=6 d=512, 4096 target tokens per
+GPU and step, LazyAdam + Noam) with the same contract.
+
+One JSON line on stdout (rank 0).  `value` is device-resident throughput (ids already in HBM); `e2e` feeds
+every step from pinned host memory and reads the loss back.  `roofline` describes the dominant kernel
+(timed with CUDA events inside eagerly issued steps), `cpu_baseline` times the CPU oracle restatement of the
+same step on a bounded sample, `parity` compares the benched engine's loss with the oracle's on that
+sample.  At N=1 the other configurations of BASELINE.json (RNN greedy / beam-8 decoding, Transformer
+training, Transformer beam-8 decoding, VGG captioning) are measured the same way under `extra_workloads`,
+each with its own roofline / cpu_baseline / e2e objects (bench_workloads.py).
+
+`--impl reference` runs ONLY the CPU restatement (the reference's TF-1.12 path cannot run here:
+SURVEY.md 8(c)) on the workload's shape, all host threads, a bounded number of sentences per step.
+The models are built from INI text through the package's configuration builder (bench_models.py).
 """
 import argparse
 import json
 import os
+import re
 import subprocess
 import sys
 import threading
@@ -29,15 +39,10 @@ import torch  # noqa: E402
 
 METRIC = "train_target_tokens_per_sec"
 UNIT = "tokens/s"
-DIMS = dict(vs=32000, vt=32000, es=300, he=300, et=300, hd=300, out=300, maxout=False, max_len=50,
-            supress_unk=False)
-BATCH, TX, TY = 256, 50, 50
+ENDE = dict(vocab=32000, emb=300, rnn=300, batch=256, tx=50, ty=50)
+TRF = dict(vocab=32000, dim=512, ff=2048, depth=6, heads=8, batch=64, length=64)
 CPU_SAMPLE_SENTENCES = 16
-
-
-# DRAM bytes per launch of the fused vocabulary kernels at the bench shape, from the committed
-# ncu --set full capture (profiles/r01_ncu_full.md): read + write
-XENT_TRAFFIC = {"nm_logits_xent_fwd": 0.054071e9 + 0.017578e9, "nm_logits_xent_bwd": 0.072671e9 + 1.584649e9}
+SEED = 2574600
 
 
 def parse_args():
@@ -46,70 +51,125 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--batch", type=int, default=BATCH)
+    ap.add_argument("--workload", default="ende", choices=["ende", "transformer"])
+    ap.add_argument("--batch", type=int, default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-cuda-graph", action="store_true",
                     help="issue every kernel of a step from Python instead of replaying the captured step")
     ap.add_argument("--no-extras", action="store_true",
-                    help="skip the secondary workloads (transformer / beam-8 / captioning) at N=1")
+                    help="skip the secondary workloads (RNN decoding / transformer / beam-8 / captioning) at N=1")
+    ap.add_argument("--extras", default="rnn_decode,transformer,beam,captioning")
+    ap.add_argument("--no-dropout", action="store_true", help="transformer workload: keep_prob 1.0")
     ap.add_argument("--breakdown", action="store_true", help="print the per-entry-point time table")
     return ap.parse_args()
 
 
-def workload_config(n_gpus, batch):
+def host_threads() -> int:
+    """All the host cores the CPU arm may use.  torchrun exports OMP_NUM_THREADS=1 to its workers, which is
+    not what a CPU baseline wants: the thread count is set explicitly, the same at every N."""
+    n = os.cpu_count() or 1
+    try:
+        n = len(os.sched_getaffinity(0))
+    except (AttributeError, OSError):
+        pass
+    n = max(1, min(n, 64))
+    torch.set_num_threads(n)
+    return n
+
+
+def workload_config(workload, n_gpus, batch, dropout=True):
+    if workload == "transformer":
+        return {"workload": "tests/transformer.ini at the perf shape: TransformerEncoder/Decoder L=6 d=512 h=8 "
+                            "F=2048, tied embeddings, synthetic ids",
+                "per_gpu_batch": batch, "global_batch": batch * n_gpus, "src_len": TRF["length"],
+                "tgt_len": TRF["length"], "tokens_per_gpu_step": batch * TRF["length"], "vocab": TRF["vocab"],
+                "optimizer": "LazyAdam beta2 0.98 eps 1e-9, Noam decay (lr 0.2, warmup 4000)",
+                "dropout_keep_prob": 0.9 if dropout else 1.0, "lengths": "fixed (no padding)",
+                "parallelism": "dp{}".format(n_gpus),
+                "l2_between_iters": "parameters + optimizer state (4 x 245 MB) and activations exceed the 126 MB L2"}
     return {"workload": "examples/translation.ini GRU+Bahdanau en-de, synthetic ids",
-            "per_gpu_batch": batch, "global_batch": batch * n_gpus, "src_len": TX, "tgt_len": TY,
-            "vocab": DIMS["vt"], "emb": 300, "rnn": 300, "optimizer": "Adam 1e-4, clip 1.0 per tensor, l2 1e-8",
+            "per_gpu_batch": batch, "global_batch": batch * n_gpus, "src_len": ENDE["tx"], "tgt_len": ENDE["ty"],
+            "vocab": ENDE["vocab"], "emb": 300, "rnn": 300, "optimizer": "Adam 1e-4, clip 1.0 per tensor, l2 1e-8",
             "lengths": "fixed (no padding)", "parallelism": "dp{}".format(n_gpus),
-            "step_submission": "CrossEntropyTrainer(use_cuda_graph=True): the step is captured once per batch shape and replayed (N>1: backward graph, NCCL all-reduce, clip+Adam graph)",
-            "gemm": "tcgen05 kind::tf32 (fp32 storage, fp32 accumulate); GRU recurrences on tcgen05 with weights resident in tensor memory (fp16 operands forward, tf32 backward, fp32 accumulate)",
-            "l2_between_iters": "working set per step (>1.6 GB dlogits) exceeds the 126 MB L2"}
+            "step_submission": "CrossEntropyTrainer(use_cuda_graph=True): the step is captured once per batch "
+                               "shape and replayed (N>1: backward graph, bucketed NCCL all-reduce overlapped "
+                               "with the backward pass, clip+Adam graph)",
+            "gemm": "tcgen05: kind::f16 for the vocabulary projection and its gradients (fp16 operands, fp32 "
+                    "accumulate), kind::tf32 elsewhere; GRU recurrences on tcgen05 with weights resident in "
+                    "tensor memory",
+            "l2_between_iters": "working set per step (0.8 GB fp16 dlogits + 4 x 129 MB parameter buffers) "
+                                "exceeds the 126 MB L2"}
 
 
-def synthetic_batch(batch, seed):
+def synthetic_batch(batch, seed, tx=ENDE["tx"], ty=ENDE["ty"], vocab=ENDE["vocab"]):
     g = torch.Generator().manual_seed(seed)
-    src = torch.randint(4, DIMS["vs"], (batch, TX), generator=g)
-    tgt = torch.randint(4, DIMS["vt"], (batch, TY), generator=g)
-    tgt[:, TY - 1] = 2  # </s>
+    src = torch.randint(4, vocab, (batch, tx), generator=g)
+    tgt = torch.randint(4, vocab, (batch, ty), generator=g)
+    tgt[:, ty - 1] = 2  # </s>
     return src, tgt
 
 
 # ---------------------------------------------------------------------------
 # CPU arm: the oracle restatement, timed
 # ---------------------------------------------------------------------------
-def cpu_train_tokens_per_sec(n_sent, steps, warmup, seed=2574600):
+def cpu_ende_train(n_sent, steps, warmup, seed=SEED):
+    """Full training steps of the oracle on n_sent sentences.  The op-for-op restatement is a mix of large
+    products and very small tensor operations, for which more threads are not always faster: the first two
+    untimed steps run with all cores and with half of them, the timed steps use the faster setting.
+    Returns (tokens/s, seconds per step, threads used)."""
     from oracle import nm_oracle as O
-    p = O.init_bahdanau_params(DIMS["vs"], DIMS["vt"], DIMS["es"], DIMS["he"], DIMS["et"], DIMS["hd"],
-                               None, DIMS["out"], False, seed=seed)
-    spec = O.RNNDecoderSpec("decoder", "attention", DIMS["max_len"], "tanh", False)
+    p = O.init_bahdanau_params(ENDE["vocab"], ENDE["vocab"], 300, 300, 300, 300, None, 300, False, seed=seed)
+    spec = O.RNNDecoderSpec("decoder", "attention", ENDE["ty"], "tanh", False)
     st = O.AdamState(p)
     src, tgt = synthetic_batch(n_sent, seed)
-    times = []
-    for i in range(warmup + steps):
+
+    def one():
         t0 = time.perf_counter()
         O.train_step(p, spec, "sentence_encoder", src, tgt.t(), st, l2=1e-8, clip_norm=1.0)
-        if i >= warmup:
-            times.append(time.perf_counter() - t0)
+        return time.perf_counter() - t0
+
+    cores = host_threads()
+    trial = {}
+    for threads in sorted({cores, max(1, cores // 2)}, reverse=True):
+        torch.set_num_threads(threads)
+        trial[threads] = one()
+    threads = min(trial, key=trial.get)
+    torch.set_num_threads(threads)
+    for _ in range(max(0, warmup - len(trial))):
+        one()
+    times = [one() for _ in range(steps)]
     per_step = sum(times) / len(times)
-    return n_sent * TY / per_step, per_step
+    return n_sent * ENDE["ty"] / per_step, per_step, threads
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    steps, warmup = max(1, min(args.steps, 5)), max(1, min(args.warmup, 2))
-    cores = torch.get_num_threads()
-    value, per_step = cpu_train_tokens_per_sec(CPU_SAMPLE_SENTENCES, steps, warmup)
-    sample = ("{} sentences x {} target tokens per step of the same workload, {} timed steps"
-              .format(CPU_SAMPLE_SENTENCES, TY, steps))
+    cores = host_threads()
+    steps, warmup = max(1, min(args.steps, 3)), max(1, min(args.warmup, 2))
+    if args.workload == "transformer":
+        import bench_workloads
+        batch = args.batch or TRF["batch"]
+        n_sent = 4
+        value, per_step = bench_workloads.cpu_transformer_train(n_sent, TRF["length"], steps, warmup)
+        sample = "{} sentences x {} target tokens per step of the same model, {} timed steps".format(
+            n_sent, TRF["length"], steps)
+    else:
+        batch = args.batch or ENDE["batch"]
+        n_sent = batch                      # the whole per-GPU batch: about 5 s per step on the host cores
+        value, per_step, cores = cpu_ende_train(n_sent, steps, warmup)
+        sample = ("the full batch: {} sentences x {} target tokens per step, {} timed steps"
+                  .format(n_sent, ENDE["ty"], steps))
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
             "steps": steps, "warmup": warmup, "ms_per_step": per_step * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": workload_config(args.gpus, args.batch),
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
-                             "sample": sample,
-                             "note": "restated-reference CPU baseline (TF 1.12 unavailable on this box)"},
+            "config": workload_config(args.workload, args.gpus, batch, not args.no_dropout),
+            "cpu_sample_sentences_per_step": n_sent,
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
+                             "note": "restated-reference CPU baseline (oracle/nm_oracle.py; TF 1.12 cannot be "
+                                     "installed on this box); the thread count is set explicitly, the same at "
+                                     "every N"},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     emit(line)
 
@@ -138,7 +198,7 @@ class ClockSampler:
                     self.samples.append([x.strip() for x in out.split(",")])
             except Exception:  # pylint: disable=broad-except
                 pass
-            self._stop.wait(0.2)
+            self._stop.wait(0.1)
 
     def __enter__(self):
         self._thread.start()
@@ -162,40 +222,117 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def measured_peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:  # pylint: disable=broad-except
+        return {}
+
+
+def ncu_traffic():
+    """DRAM read+write bytes per launch of the dominant kernels, from this round's committed ncu --set full
+    capture (profiles/r02_traffic.json, written by tools/profile_summary.py); {} when absent."""
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "r02_traffic.json")))
+    except Exception:  # pylint: disable=broad-except
+        return {}
+
+
+def gemm_family_roofline(prof, prof_steps, xent_dims, peaks, total_ms):
+    """The dominant kernel is tc_gemm_kernel (csrc/gemm_tc.cu): every dense projection, weight-gradient
+    product and the fused vocabulary forward / backward are instances of it.  Algorithmic flops per launch =
+    2*M*N*K of the product; time = CUDA events around the launches inside the profiled
+    steps.  Instances issuing kind::f16 are rated against the measured bf16 peak, kind::tf32 instances
+    cannot exceed half of it (the ceiling is reported too)."""
+    peak_tf = float(peaks.get("bf16_tflops_sustained", 1400.0))
+    peak_src = "measured bf16_tflops_sustained (MEASURED_PEAKS.json)" if peaks else \
+        "fallback (B200_PROFILING.md sustained)"
+    m, k, v = xent_dims
+    traffic = ncu_traffic()
+    fam_flops = fam_ms = f16_flops = f16_ms = 0.0
+    instances = []
+    for name, d in prof.items():
+        fl = None
+        mm = re.match(r"nm_gemm\[(\w\w) (\d+)x(\d+)x(\d+)\]", name)
+        if mm:
+            fl = 2.0 * int(mm.group(2)) * int(mm.group(3)) * int(mm.group(4))
+        elif name.split("[")[0] in ("nm_logits_xent_fwd", "nm_logits_xent_bwd", "nm_logits_xent_fwd16",
+                                    "nm_logits_xent_bwd16"):
+            fl = 2.0 * m * k * v
+        else:
+            mm = re.match(r"nm_gemm_f16(?:_tn)?\[(\d+)x(\d+)x(\d+)\]", name)
+            if mm:
+                fl = 2.0 * int(mm.group(1)) * int(mm.group(2)) * int(mm.group(3))
+        if fl is None:
+            continue
+        calls = d["calls"]
+        kind = "f16" if "16" in name.split("[")[0] else "tf32"
+        fam_flops += fl * calls
+        fam_ms += d["ms"]
+        if kind == "f16":
+            f16_flops += fl * calls
+            f16_ms += d["ms"]
+        instances.append({"call": name, "launches_per_step": calls // prof_steps,
+                          "ms_per_launch": d["ms"] / calls, "tflops": fl / (d["ms"] / calls * 1e-3) / 1e12,
+                          "kind": kind, "traffic": traffic.get(name.split("[")[0])})
+    if fam_ms <= 0:
+        return None
+    instances.sort(key=lambda e: -e["ms_per_launch"] * e["launches_per_step"])
+    ach = fam_flops / (fam_ms * 1e-3) / 1e12
+    roof = {"kernel": "tc_gemm_kernel (tcgen05; all instances of the step: kind::f16 vocabulary products, "
+                      "kind::tf32 elsewhere)",
+            "bound": "tensor", "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf,
+            "peak_source": peak_src,
+            "traffic": (sum(e["traffic"] for e in instances if e["traffic"]) or None),
+            "traffic_note": "sum of dram__bytes_read+write per launch over the vocabulary instances, from "
+                            "profiles/r02_traffic.json (ncu --set full of this command); null = no capture "
+                            "committed for this build",
+            "share_of_step": fam_ms / prof_steps / max(total_ms, 1e-9),
+            "instances": instances[:8]}
+    if f16_ms > 0:
+        roof["f16_instances"] = {"achieved": f16_flops / (f16_ms * 1e-3) / 1e12,
+                                 "frac": f16_flops / (f16_ms * 1e-3) / 1e12 / peak_tf,
+                                 "share_of_family_time": f16_ms / fam_ms}
+    return roof
+
+
 # ---------------------------------------------------------------------------
 # B200 arm
 # ---------------------------------------------------------------------------
 def run_b200(args):
+    import bench_models
     from neuralmonkey_b200 import distributed, lib
-    from tests.helpers import build_bahdanau, feed
     distributed.init_from_env()
     rank, world = distributed.rank(), distributed.world_size()
-    model = build_bahdanau(**DIMS, clip=1.0, l2=1e-8, lr=1e-4, cuda_graph=not args.no_cuda_graph)
-    trainer = model["trainer"]
-    dev = model["arena"].params.device
-    batch = args.batch
-    tokens_per_step_rank = batch * TY
+    workload = args.workload
+    graph = not args.no_cuda_graph
+    if workload == "transformer":
+        batch = args.batch or TRF["batch"]
+        model = bench_models.build_transformer(vocab=TRF["vocab"], max_len=TRF["length"], cuda_graph=graph,
+                                               dropout=not args.no_dropout)
+        feed = bench_models.feed_transformer
+        tx = ty = TRF["length"]
+        xent_dims = (batch * ty, TRF["dim"], TRF["vocab"])
+    else:
+        batch = args.batch or ENDE["batch"]
+        model = bench_models.build_ende(vocab=ENDE["vocab"], cuda_graph=graph)
+        feed = bench_models.feed_ende
+        tx, ty = ENDE["tx"], ENDE["ty"]
+        xent_dims = (batch * ty, 300, ENDE["vocab"])
+    trainer = model.trainer
+    dev = model.arena.params.device
+    tokens_per_step_rank = batch * ty
 
     # a few distinct synthetic batches, resident on the device (value) and pinned on host (e2e)
-    host_batches = [synthetic_batch(batch, 2574600 + rank + 1000 * i) for i in range(4)]
+    host_batches = [synthetic_batch(batch, SEED + rank + 1000 * i, tx, ty) for i in range(4)]
     pinned = [(s.pin_memory(), t.pin_memory()) for s, t in host_batches]
-
-    def step_resident(i):
-        src, tgt = host_batches[i % len(host_batches)]
-        feed(model, src, tgt, train=True)  # ids tiny; see e2e for the counted copy
-        return trainer.train_step()
-
-    dev_src = [s.to(dev) for s, _ in host_batches]
+    # decoder ids stay on the host: feed_ids derives the teacher-forcing inputs there (a few microseconds of
+    # integer work) and uploads both id tensors through pinned staging
+    dev_batches = [(s.to(dev), t) for s, t in host_batches]
 
     def step_device_inputs(i):
-        j = i % len(host_batches)
-        enc, att, dec = model["enc"], model["att"], model["dec"]
-        enc.input_sequence.feed_ids([dev_src[j]], train=True)
-        for part in (enc, att):
-            part.reset_batch()
-            part.train_mode = True
-            part.batch_size = batch
-        dec.feed_ids(host_batches[j][1], batch, train=True)
+        src, tgt = dev_batches[i % len(dev_batches)]
+        feed(model, src, tgt, True)
         return trainer.train_step()
 
     def barrier():
@@ -223,15 +360,15 @@ def run_b200(args):
             torch.distributed.all_reduce(ms, op=torch.distributed.ReduceOp.MAX)
         return float(ms) / steps, last
 
-    for i in range(args.warmup):
+    for i in range(max(args.warmup, 3)):
         step_device_inputs(i)
     with ClockSampler(dev.index or 0) as clocks:
         ms_step, _ = timed(step_device_inputs, args.steps, read_loss=False)
     host_enqueue_ms = host_ms[0]
 
-    # per-entry-point device time (CUDA events around every C-ABI call) and the kernel count of a
-    # step: these steps issue every launch from Python - a replayed graph contains the same kernel
-    # nodes but does not pass through the library's launch counter
+    # per-entry-point device time (CUDA events around every C-ABI call) and the kernel count of a step: these
+    # steps issue every launch from Python - a replayed graph contains the same kernel nodes but does not
+    # pass through the library's launch counter
     graphed = trainer.use_cuda_graph
     trainer.use_cuda_graph = False
     launches0 = lib.launch_count()
@@ -245,118 +382,105 @@ def run_b200(args):
 
     def step_e2e(i):
         src, tgt = pinned[i % len(pinned)]
-        feed(model, src, tgt, train=True)  # H2D of the pinned id tensors inside the timed region
+        feed(model, src, tgt, True)   # H2D of the pinned id tensors inside the timed region
         return trainer.train_step()
 
-    for i in range(2):
+    for i in range(3):
         step_e2e(i)
     ms_e2e, loss = timed(step_e2e, args.steps, read_loss=True)
+    exposed_comm_ms = getattr(trainer, "last_exposed_comm_ms", None)
 
     if rank != 0:
         return
     value = world * tokens_per_step_rank / (ms_step * 1e-3)
     e2e_value = world * tokens_per_step_rank / (ms_e2e * 1e-3)
 
-    # ---- roofline of the dominant kernel -------------------------------------------------
-    peaks = {}
-    try:
-        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-    except Exception:  # pylint: disable=broad-except
-        pass
-    peak_tf = float(peaks.get("bf16_tflops_sustained", 1400.0))
-    peak_src = "measured bf16_tflops_sustained" if peaks else "fallback (B200_PROFILING.md sustained)"
-    m, k, v = batch * TY, DIMS["out"], DIMS["vt"]
+    peaks = measured_peaks()
     table = sorted(((n, d["ms"] / prof_steps, d["calls"] // prof_steps) for n, d in prof.items()),
                    key=lambda x: -x[1])
     total_ms = sum(t for _, t, _ in table)
-    # The dominant kernel is tc_gemm_kernel (gemm_tc.cu): every dense projection, weight-gradient
-    # product and the fused vocabulary forward/backward are instances of it.  Algorithmic flops per
-    # launch = 2*M*N*K of the product; time = CUDA events around the launches
-    # inside the profiled steps.
-    import re
-    fam_flops, fam_ms, instances = 0.0, 0.0, []
-    for name, d in prof.items():
-        fl = None
-        mm = re.match(r"nm_gemm\[(\w\w) (\d+)x(\d+)x(\d+)\]", name)
-        if mm:
-            fl = 2.0 * int(mm.group(2)) * int(mm.group(3)) * int(mm.group(4))
-        elif name in ("nm_logits_xent_fwd", "nm_logits_xent_bwd", "nm_logits_xent_fwd16", "nm_logits_xent_bwd16"):
-            fl = 2.0 * m * k * v
-        else:
-            mm = re.match(r"nm_gemm_f16\[(\d+)x(\d+)x(\d+)\]", name)     # NMB200_XENT16=1: kind::f16 instances
-            if mm:
-                fl = 2.0 * int(mm.group(1)) * int(mm.group(2)) * int(mm.group(3))
-        if fl is None:
-            continue
-        calls = d["calls"]
-        fam_flops += fl * calls
-        fam_ms += d["ms"]
-        instances.append({"call": name, "launches_per_step": calls // prof_steps,
-                          "ms_per_launch": d["ms"] / calls, "tflops": fl / (d["ms"] / calls * 1e-3) / 1e12,
-                          "traffic": XENT_TRAFFIC.get(name),
-                          "kind": "f16" if ("16" in name.split("[")[0]) else "tf32"})
-    instances.sort(key=lambda e: -e["ms_per_launch"] * e["launches_per_step"])
-    roof = None
-    if fam_ms > 0:
-        ach = fam_flops / (fam_ms * 1e-3) / 1e12
-        best = max(instances, key=lambda e: e["tflops"])
-        roof = {"kernel": "tc_gemm_kernel (tcgen05 kind::tf32, all instances of the step)", "bound": "tensor",
-                "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf,
-                "traffic": XENT_TRAFFIC["nm_logits_xent_fwd"] + XENT_TRAFFIC["nm_logits_xent_bwd"],
-                "traffic_note": "DRAM read+write bytes per launch of the two fused vocabulary instances "
-                                "(profiles/r01_ncu_full.md, ncu --set full); their algorithmic bytes are "
-                                "{:.0f} MB (fwd) and {:.0f} MB (bwd, incl. the fp32 dlogits it must write)"
-                                .format((4.0 * (m * k + k * v + v) + 32.0 * m * ((v + 255) // 256)) / 1e6,
-                                        4.0 * (m * k + k * v + v + m * v) / 1e6),
-                "peak_source": peak_src,
-                "note": "kind::tf32 issues at half the bf16 rate, so 0.5 is the ceiling of frac for this "
-                        "kernel; frac of the tf32 ceiling = {:.3f} (best instance {}: {:.0f} TFLOP/s = {:.3f})"
-                        .format(ach / (peak_tf / 2.0), best["call"], best["tflops"],
-                                best["tflops"] / (peak_tf / 2.0)),
-                "share_of_step": fam_ms / prof_steps / max(total_ms, 1e-9),
-                "instances": instances[:6]}
+    roof = gemm_family_roofline(prof, prof_steps, xent_dims, peaks, total_ms)
     if args.breakdown:
         for n, t, c in table:
-            print("# {:34s} {:8.3f} ms/step  {:4d} calls/step".format(n, t, c), file=sys.stderr)
-        print("# sum {:.3f} ms of device time vs {:.3f} ms per step".format(total_ms, ms_step),
-              file=sys.stderr)
+            print("# {:40s} {:8.3f} ms/step  {:4d} calls/step".format(n, t, c), file=sys.stderr)
+        print("# sum {:.3f} ms of device time vs {:.3f} ms per step".format(total_ms, ms_step), file=sys.stderr)
 
-    cpu = None
-    if not args.no_cpu_baseline:
-        cores = torch.get_num_threads()
-        cpu_value, cpu_step = cpu_train_tokens_per_sec(CPU_SAMPLE_SENTENCES, 2, 1)
-        cpu = {"value": cpu_value, "unit": UNIT, "cores": cores, "kind": "port",
-               "sample": "{} sentences x {} target tokens per step, 2 timed steps ({:.1f} s each)"
-                         .format(CPU_SAMPLE_SENTENCES, TY, cpu_step)}
+    cpu = parity = None
+    if not args.no_cpu_baseline and world == 1:
+        cores = host_threads()
+        if workload == "ende":
+            cpu_value, cpu_step, cores = cpu_ende_train(batch, 1, 2)
+            cpu = {"value": cpu_value, "unit": UNIT, "cores": cores, "kind": "port",
+                   "sample": "the full batch: {} sentences x {} target tokens per step, 1 timed step ({:.1f} s) "
+                             "after 2 untimed ones".format(batch, ty, cpu_step)}
+            parity = ende_parity(model, feed)
+        else:
+            import bench_workloads
+            cpu_value, cpu_step = bench_workloads.cpu_transformer_train(4, ty, 2, 1)
+            cpu = {"value": cpu_value, "unit": UNIT, "cores": cores, "kind": "port",
+                   "sample": "4 sentences x {} target tokens per step, 2 timed steps ({:.1f} s each)"
+                             .format(ty, cpu_step)}
 
-    # secondary workloads of BASELINE.json (configs[2..4]); N=1 only, a few seconds each
+    # the other configurations of BASELINE.json; N=1 only, a few seconds each
     extras = None
-    if world == 1 and not args.no_extras:
+    if world == 1 and not args.no_extras and workload == "ende":
         import bench_workloads
         extras = {}
-        for name in ("transformer", "beam", "captioning"):
+        del model
+        torch.cuda.empty_cache()
+        for name in [n for n in args.extras.split(",") if n]:
             try:
-                extras[name] = bench_workloads.RUNNERS[name]()
+                extras[name] = bench_workloads.RUNNERS[name](cpu=not args.no_cpu_baseline)
             except Exception as exc:  # pylint: disable=broad-except
+                import traceback
+                traceback.print_exc()
                 extras[name] = {"error": "{}: {}".format(type(exc).__name__, exc)}
+            torch.cuda.empty_cache()
 
-    h2d = 2 * batch * (TX + TY) * 8  # int64 ids: encoder ids, decoder targets + fed symbols
+    h2d = 2 * batch * (tx + ty) * 8  # int64 ids: encoder ids, decoder targets + fed symbols
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32 (tf32 tensor-core products, fp32 accumulate)",
-            "data": "synthetic", "config": workload_config(world, batch),
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None,
+            "dtype": "f32 storage; tensor-core products in fp16 (vocabulary) / tf32 with fp32 accumulation",
+            "data": "synthetic", "config": workload_config(workload, world, batch, not args.no_dropout),
             "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e,
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4, "last_loss": loss},
             "gpu_launches": launches,
             "gpu_launches_note": "kernels of libnmb200 per step x timed steps, counted by nm_launch_count() over "
                                  "eagerly issued steps" + (" (the timed steps replay the same kernels as one "
                                                            "captured CUDA graph per step)" if graphed else ""),
-            "clocks": clocks.summary(), "roofline": roof,
-            "cpu_baseline": cpu,
-            "breakdown_ms_per_step": {n: round(t, 4) for n, t, _ in table[:16]},
+            "clocks": clocks.summary(), "roofline": roof, "cpu_baseline": cpu, "parity": parity,
+            "breakdown_ms_per_step": {n: round(t, 4) for n, t, _ in table[:18]},
             "host_enqueue_ms_per_step": host_enqueue_ms,
+            "exposed_comm_ms_per_step": exposed_comm_ms,
             "extra_workloads": extras}
     emit(line)
+    bench_models.cleanup()
+
+
+def ende_parity(model, feed):
+    """The benched engine (tcgen05 fp16/tf32 products, tensor-core GRU, CUDA-graph step) against the fp32
+    oracle at the perf dims (H = E = 300, V = 32000, T = 50) on the CPU arm's 16-sentence sample, with O(0.1)
+    random parameters so that every activation matters: train loss within 1e-3 (north_star)."""
+    from oracle import nm_oracle as O
+    arena = model.arena
+    shapes = {n: torch.zeros(arena.variables[n].shape) for n in sorted(arena.order)}
+    params = O.randomize(shapes, scale=0.1, seed=11)
+    for name in params:
+        if name.endswith("gamma"):
+            params[name] = 1.0 + params[name]
+    arena.load_dict(params)
+    src, tgt = synthetic_batch(CPU_SAMPLE_SENTENCES, SEED + 77)
+    feed(model, src.pin_memory(), tgt.pin_memory(), True)
+    gpu_loss = float(model.decoder.train_loss)
+    spec = O.RNNDecoderSpec("decoder", "attention_sentence_encoder", ENDE["ty"], "tanh", False)
+    with torch.no_grad():
+        oenc = O.sentence_encoder(params, "sentence_encoder", src)
+        odec = O.decoder_train(params, spec, oenc, tgt.t())
+    want = float(odec["train_loss"])
+    return {"what": "train loss of the benched engine vs the fp32 CPU oracle, en-de dims, 16 sentences x 50",
+            "gpu_loss": gpu_loss, "oracle_loss": want, "abs_diff": abs(gpu_loss - want), "tolerance": 1e-3,
+            "ok": abs(gpu_loss - want) < 1e-3}
 
 
 _REAL_STDOUT = None

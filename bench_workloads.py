@@ -1,14 +1,17 @@
-"""Secondary workloads of BASELINE.json (configs[2..4]) measured with the same rules as bench.py:
-CUDA-event timing after warm-up, synthetic ids / images, random-init weights.
+"""The other configurations of BASELINE.json, measured with bench.py's rules (CUDA-event timing after
+warm-up, synthetic ids / images, random-init weights, models built from INI text through the package's
+configuration builder) and to the same contract: every workload carries its own `roofline`,
+`cpu_baseline` and `e2e` objects.
 
-  transformer : tests/transformer.ini at the perf shape - 6 layers, d=512, 8 heads, F=2048,
-                V=32000, 4096 target tokens per step (64 x 64), Adam; train tokens/s
-  beam        : tests/beamsearch.ini at the perf shape - beam 8 over the 6x512 Transformer,
-                forced full-length hypotheses (EOS suppressed); emitted tokens/s and batch-1 latency
-  captioning  : tests/captioning.ini - frozen VGG-16 conv stack on 224x224 images + Bahdanau
-                decoder; images/s of a training step
+  rnn_decode  : examples/translation.ini model at run time - greedy decoding of 256 sentences and beam-8
+                decoding (tests/beamsearch.ini wrapper) of 64 sentences / 1 sentence, on the fused step kernel
+  transformer : tests/transformer.ini at the perf shape - 6 layers, d=512, 8 heads, F=2048, V=32000, 4096
+                target tokens per step, LazyAdam + Noam, dropout per the INI; train tokens/s
+  beam        : tests/beamsearch.ini at the perf shape - beam 8 x 128 forced steps over that Transformer;
+                emitted tokens/s at batch 64 and latency at batch 1
+  captioning  : tests/captioning.ini - frozen VGG-16 conv stack on 224x224 images + Bahdanau decoder; images/s
 
-Usage: python bench_workloads.py [transformer|beam|captioning] ...   (one JSON line each)
+Usage: python bench_workloads.py [rnn_decode|transformer|beam|captioning] ...   (one JSON line each)
 """
 import json
 import sys
@@ -16,7 +19,10 @@ import time
 
 import torch
 
-SEED = 2574600
+import bench_models
+
+SEED = bench_models.SEED
+VOCAB = 32000
 
 
 def _events():
@@ -36,166 +42,444 @@ def _time(fn, steps, warmup):
     return e0.elapsed_time(e1) / steps
 
 
-def build_transformer(vocab=32000, dim=512, ff=2048, depth=6, heads=8, max_len=64, lr=1e-4, tie=True):
-    from neuralmonkey_b200 import runtime, tf
-    from neuralmonkey_b200.decoders import TransformerDecoder
-    from neuralmonkey_b200.encoders import TransformerEncoder
-    from neuralmonkey_b200.model.sequence import EmbeddedSequence
-    from neuralmonkey_b200.trainers import CrossEntropyTrainer
-    from neuralmonkey_b200.vocabulary import Vocabulary
-
-    runtime.reset()
-    words = ["w{}".format(i) for i in range(vocab - 4)]
-    src_vocab, tgt_vocab = Vocabulary(words), Vocabulary(words)
-    seq = EmbeddedSequence(name="input_sequence", vocabulary=src_vocab, data_id="source",
-                           embedding_size=dim, max_length=max_len, scale_embeddings_by_depth=True)
-    enc = TransformerEncoder(name="encoder", input_sequence=seq, ff_hidden_size=ff, depth=depth,
-                             n_heads=heads)
-    dec = TransformerDecoder(name="decoder", encoders=[enc], vocabulary=tgt_vocab, data_id="target",
-                             ff_hidden_size=ff, n_heads_self=heads, n_heads_enc=heads, depth=depth,
-                             max_output_len=max_len, embedding_size=dim, tie_embeddings=tie)
-    trainer = CrossEntropyTrainer(decoders=[dec], optimizer=tf.AdamOptimizer(learning_rate=lr), use_cuda_graph=True)
-    for part in trainer.parameterizeds:
-        part.ensure_declared()
-    runtime.arena().finalize(runtime.device())
-    return {"seq": seq, "enc": enc, "dec": dec, "trainer": trainer, "arena": runtime.arena()}
+def _peaks():
+    import bench
+    return bench.measured_peaks()
 
 
-def feed_transformer(model, src, tgt, train):
-    bsz = src.shape[0]
-    model["seq"].feed_ids([src], train=train)
-    enc = model["enc"]
-    enc.reset_batch()
-    enc.train_mode = train
-    enc.batch_size = bsz
-    model["dec"].feed_ids(tgt, bsz, train=train)
+def _host_threads():
+    import bench
+    return bench.host_threads()
 
 
-def synthetic_ids(bsz, length, vocab, seed, eos=True):
-    g = torch.Generator().manual_seed(seed)
-    ids = torch.randint(4, vocab, (bsz, length), generator=g)
-    if eos:
-        ids[:, -1] = 2
-    return ids
+def _profile(fn):
+    """Per-entry-point device time of one eagerly issued call of fn."""
+    from neuralmonkey_b200 import lib
+    n0 = lib.launch_count()
+    lib.profile_start()
+    fn()
+    prof = lib.profile_stop()
+    return prof, lib.launch_count() - n0
 
 
-def run_transformer(steps=5, warmup=3, bsz=64, length=64, vocab=32000, breakdown=False):
-    model = build_transformer(vocab=vocab, max_len=length)
-    batches = [(synthetic_ids(bsz, length, vocab, SEED + i, eos=False).pin_memory(),
-                synthetic_ids(bsz, length, vocab, SEED + 100 + i).pin_memory()) for i in range(4)]
+# ---------------------------------------------------------------------------
+# oracle (CPU) arms: bounded samples
+# ---------------------------------------------------------------------------
+def _transformer_oracle_params(vocab, dim=512, ff=2048, depth=6, seed=SEED):
+    """Variables of TransformerEncoder/Decoder under the reference's names, random
+    values of trained-model scale."""
+    from oracle import nm_oracle as O
+    shapes = {"input_sequence/embedding_matrix_0": (vocab, dim), "decoder/word_embeddings": (vocab, dim),
+              "encoder/LayerNorm/gamma": (dim,), "encoder/LayerNorm/beta": (dim,),
+              "decoder/LayerNorm/gamma": (dim,), "decoder/LayerNorm/beta": (dim,)}
+    for side, atts in (("encoder", ("self_attention",)), ("decoder", ("self_attention", "encdec_attention/enc_0"))):
+        for i in range(depth):
+            for att in atts:
+                pre = "{}/layer_{}/{}".format(side, i, att)
+                for proj in ("query_proj", "keys_proj", "vals_proj", "output_proj"):
+                    shapes["{}/{}/kernel".format(pre, proj)] = (dim, dim)
+                shapes[pre + "/LayerNorm/gamma"] = (dim,)
+                shapes[pre + "/LayerNorm/beta"] = (dim,)
+            pre = "{}/layer_{}/feedforward".format(side, i)
+            shapes[pre + "/hidden_state/kernel"] = (dim, ff)
+            shapes[pre + "/hidden_state/bias"] = (ff,)
+            shapes[pre + "/output/kernel"] = (ff, dim)
+            shapes[pre + "/output/bias"] = (dim,)
+            shapes[pre + "/LayerNorm/gamma"] = (dim,)
+            shapes[pre + "/LayerNorm/beta"] = (dim,)
+    p = O.randomize({n: torch.zeros(s) for n, s in shapes.items()}, scale=0.05, seed=seed)
+    for n in p:
+        if n.endswith("gamma"):
+            p[n] = 1.0 + p[n]
+    return p
 
-    def step(i):
-        src, tgt = batches[i % len(batches)]
-        feed_transformer(model, src, tgt, train=True)
-        return model["trainer"].train_step()
 
-    ms = _time(step, steps, warmup)
-    loss = float(step(0)["losses"][0])
-    if breakdown:
-        from neuralmonkey_b200 import lib
-        lib.profile_start()
-        step(1)
-        prof = lib.profile_stop()
-        table = sorted(((n, d["ms"], d["calls"]) for n, d in prof.items()), key=lambda x: -x[1])
-        for n, t, c in table[:30]:
-            print("# {:34s} {:8.3f} ms  {:4d} calls".format(n, t, c), file=sys.stderr)
-        print("# sum {:.3f} ms vs {:.3f} ms per step".format(sum(t for _, t, _ in table), ms), file=sys.stderr)
-    return {"workload": "tests/transformer.ini perf shape: L=6 d=512 h=8 F=2048 V={} batch {}x{}".format(
-                vocab, bsz, length),
-            "metric": "train_target_tokens_per_sec", "value": bsz * length / (ms * 1e-3),
-            "unit": "tokens/s", "ms_per_step": ms, "steps": steps, "warmup": warmup, "last_loss": loss,
-            "params": int(model["arena"].trainable_size), "inputs": "pinned host ids, H2D inside the timed region"}
+def _oracle_transformer_encoder(p, src, dim=512, depth=6, heads=8):
+    from oracle import nm_oracle as O
+    emb = p["input_sequence/embedding_matrix_0"]
+    mask = (src != 0).to(emb.dtype)
+    inputs = emb[src] * (mask * (dim ** 0.5)).unsqueeze(-1)
+    return O.transformer_encoder(p, "encoder", inputs, mask, depth, heads)
 
 
-def run_beam(bsz=64, beam=8, steps=128, vocab=32000, src_len=32, reps=1):
-    from neuralmonkey_b200.decoders import BeamSearchDecoder
-    model = build_transformer(vocab=vocab, max_len=max(steps, src_len), tie=False)
-    dec = model["dec"]
-    # EOS never wins: every hypothesis runs the full length (SURVEY 8(d) "forced steps" variant)
+def cpu_transformer_train(n_sent, length, steps, warmup, vocab=VOCAB):
+    """fwd + bwd (autograd over the oracle graph) + Adam on n_sent sentences; target tokens per second."""
+    from oracle import nm_oracle as O
+    p = {n: v.requires_grad_(True) for n, v in _transformer_oracle_params(vocab).items()}
+    spec = O.TransformerDecoderSpec("decoder", 6, 8, 8, length, True, False)
+    st = O.AdamState({n: v.detach() for n, v in p.items()})
+    src = bench_models.synthetic_ids(n_sent, length, vocab, SEED, eos=False)
+    tgt = bench_models.synthetic_ids(n_sent, length, vocab, SEED + 1)
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        out = O.transformer_decoder_train(p, spec, _oracle_transformer_encoder(p, src), tgt)
+        grads = torch.autograd.grad(out["loss"], list(p.values()), allow_unused=True)
+        with torch.no_grad():
+            gdict = {n: (g if g is not None else torch.zeros_like(v)) for (n, v), g in zip(p.items(), grads)}
+            O.adam_step({n: v.detach() for n, v in p.items()}, gdict, st, lr=1e-4, beta2=0.98, eps=1e-9)
+        if i >= warmup:
+            times.append(time.perf_counter() - t0)
+    per_step = sum(times) / len(times)
+    return n_sent * length / per_step, per_step
+
+
+def cpu_rnn_greedy(n_sent, steps=50, vocab=VOCAB):
+    from oracle import nm_oracle as O
+    p = O.init_bahdanau_params(vocab, vocab, 300, 300, 300, 300, None, 300, False, seed=SEED)
+    p["decoder/state_to_word_b"][2] = -1.0e4
+    spec = O.RNNDecoderSpec("decoder", "attention", steps, "tanh", False)
+    src = bench_models.synthetic_ids(n_sent, 50, vocab, SEED, eos=False)
+    t0 = time.perf_counter()
     with torch.no_grad():
-        dec.var("state_to_word_b")[2] = -1.0e4
-    bs = BeamSearchDecoder(name="bs", parent_decoder=dec, beam_size=beam, max_steps=steps,
-                           length_normalization=0.6)
-    out = {}
-    for label, b in (("batch", bsz), ("latency", 1)):
-        src = synthetic_ids(b, src_len, vocab, SEED, eos=False)
+        out = O.decoder_greedy(p, spec, O.sentence_encoder(p, "sentence_encoder", src))
+    dt = time.perf_counter() - t0
+    emitted = int(out["output_symbols"].shape[0]) * n_sent
+    return emitted / dt, dt
 
-        def run(_i, b=b, src=src):
-            feed_transformer(model, src, None, train=False)
-            bs.reset_batch()
-            bs.batch_size = b
+
+def cpu_rnn_beam(n_sent, beam=8, steps=16, vocab=VOCAB):
+    """Beam search around the oracle's decoder step (the schedule of tests/test_gpu_transformer.py's RNN case)."""
+    from oracle import nm_oracle as O
+    p = O.init_bahdanau_params(vocab, vocab, 300, 300, 300, 300, None, 300, False, seed=SEED)
+    p["decoder/state_to_word_b"][2] = -1.0e4
+    spec = O.RNNDecoderSpec("decoder", "attention", steps, "tanh", False)
+    src = bench_models.synthetic_ids(n_sent, 50, vocab, SEED, eos=False)
+    t0 = time.perf_counter()
+    with torch.no_grad():
+        oenc = O.sentence_encoder(p, "sentence_encoder", src)
+        states = oenc["temporal_states"].repeat_interleave(beam, 0)
+        mask = oenc["temporal_mask"].repeat_interleave(beam, 0)
+        hidden = O.bahdanau_precompute(p, "attention", states)
+        emb = p["decoder/word_embeddings"]
+        prev0 = O.decoder_initial_state(p, spec, oenc["output"]).repeat_interleave(beam, 0)
+
+        def run(embedded, prev):
+            output, cell, _c, _w = O.decoder_step(p, spec, embedded, prev, hidden, states, mask)
+            return cell, torch.log_softmax(O.state_to_logits(p, spec, output), -1)
+
+        prev1, first = run(emb[torch.full((n_sent * beam,), O.START, dtype=torch.int64)], prev0)
+        res = O.beam_search(lambda prev, words, _f: run(emb[words], prev), prev1, first, beam, steps, 0.6,
+                            lambda st, idx: st[idx])
+    dt = time.perf_counter() - t0
+    return n_sent * int(res["token_ids"].shape[0]) / dt, dt
+
+
+def cpu_transformer_beam(n_sent, beam=8, steps=8, src_len=32, vocab=VOCAB):
+    """The reference's schedule: the whole prefix is re-run every step (decoders/transformer.py:487-516)."""
+    from oracle import nm_oracle as O
+    p = _transformer_oracle_params(vocab)
+    p["decoder/state_to_word_W"] = torch.randn(512, vocab) * 0.05
+    p["decoder/state_to_word_b"] = torch.zeros(vocab)
+    p["decoder/state_to_word_b"][2] = -1.0e4
+    spec = O.TransformerDecoderSpec("decoder", 6, 8, 8, steps + 1, False, False)
+    src = bench_models.synthetic_ids(n_sent, src_len, vocab, SEED, eos=False)
+    t0 = time.perf_counter()
+    with torch.no_grad():
+        oenc = _oracle_transformer_encoder(p, src)
+        emb = p["decoder/word_embeddings"]
+        states = oenc["states"].repeat_interleave(beam, 0)
+        emask = oenc["mask"].repeat_interleave(beam, 0)
+        rows = states.shape[0]
+
+        def run(seq, mask):
+            out = O.transformer_decoder_stack(p, spec, seq, mask, states, emask)
+            return torch.log_softmax(O.transformer_logits(p, spec, out[:, -1]), -1)
+
+        seq0 = emb[torch.full((rows,), O.START, dtype=torch.int64)].unsqueeze(1)
+        mask0 = torch.ones(rows, 1)
+        first = run(seq0, mask0)
+
+        def step_fn(state, words, finished):
+            seq = torch.cat([state[0], emb[words].unsqueeze(1)], 1)
+            mask = torch.cat([state[1], (~finished).to(emb.dtype).unsqueeze(1)], 1)
+            return (seq, mask), run(seq, mask)
+
+        res = O.beam_search(step_fn, (seq0, mask0), first, beam, steps, 0.6,
+                            lambda st, idx: (st[0][idx], st[1][idx]))
+    dt = time.perf_counter() - t0
+    return n_sent * int(res["token_ids"].shape[0]) / dt, dt
+
+
+def cpu_vgg(n_images=1):
+    from oracle import nm_oracle as O
+    g = torch.Generator().manual_seed(SEED)
+    p = {}
+    cin = 3
+    for b, (n, cout) in enumerate(zip(O.VGG_BLOCKS["vgg_16"], O.VGG_CHANNELS), 1):
+        for k in range(1, n + 1):
+            pre = "vgg_16/conv{}/conv{}_{}/".format(b, b, k)
+            p[pre + "weights"] = torch.randn(3, 3, cin, cout, generator=g) * (2.0 / (9 * cin)) ** 0.5
+            p[pre + "biases"] = torch.zeros(cout)
+            cin = cout
+    images = torch.randn(n_images, 224, 224, 3, generator=g) * 60.0
+    t0 = time.perf_counter()
+    with torch.no_grad():
+        O.vgg_features(p, "vgg_16", images, "vgg_16/conv5/conv5_3")
+    dt = time.perf_counter() - t0
+    return n_images / dt, dt
+
+
+# ---------------------------------------------------------------------------
+# RNN decoding (greedy + beam 8) on the fused step kernel
+# ---------------------------------------------------------------------------
+def run_rnn_decode(cpu=True, beam_steps=128, reps=3):
+    model = bench_models.build_ende(vocab=VOCAB, cuda_graph=False, beam_steps=beam_steps)
+    dec, bs = model.decoder, model.bs_decoder
+    with torch.no_grad():
+        dec.var("state_to_word_b")[2] = -1.0e4      # </s> never wins: every hypothesis runs the full length
+    peaks = _peaks()
+    hbm = float(peaks.get("hbm_gbs", 6500.0))
+    tx, a_c = 50, 1200                                # keys + values floats per source position
+    out = {}
+
+    def decode_once(kind, src_dev):
+        bench_models.feed_ende(model, src_dev, None, False)
+        if kind == "greedy":
+            return dec.runtime_argmax
+        return bs.outputs.last_search_step_output.token_ids
+
+    for kind, bsz in (("greedy", 256), ("beam8", 64), ("beam8", 1)):
+        src = bench_models.synthetic_ids(bsz, tx, VOCAB, SEED + bsz, eos=False)
+        src_dev, src_pin = src.cuda(), src.pin_memory()
+        for _ in range(3):                            # eager run, capture run, first replay
+            res = decode_once(kind, src_dev)
+        steps = int(res.shape[0]) - (0 if kind == "greedy" else 1)
+        ms = _time(lambda _i: decode_once(kind, src_dev), reps, 1)
+
+        def e2e(_i):
+            bench_models.feed_ende(model, src_pin, None, False)        # pinned ids -> device
+            return (dec.runtime_argmax if kind == "greedy" else
+                    bs.outputs.last_search_step_output.token_ids).cpu()  # tokens -> host
+
+        ms_e2e = _time(e2e, reps, 1)
+        entry = {"batch": bsz, "steps": steps, "ms_per_batch": ms, "us_per_step": ms / max(steps, 1) * 1e3,
+                 "tokens_per_s": bsz * steps / (ms * 1e-3),
+                 "e2e": {"value": bsz * steps / (ms_e2e * 1e-3), "unit": "tokens/s", "ms_per_batch": ms_e2e,
+                         "h2d_bytes_per_step": bsz * tx * 8,
+                         "d2h_bytes_per_step": int(res.numel()) * 8}}
+        # roofline of the step kernel: eager issue with an event pair around every C-ABI call
+        engine = dec.decode_engine
+        engine.use_cuda_graph = False
+        prof, launches = _profile(lambda: decode_once(kind, src_dev))
+        engine.use_cuda_graph = True
+        d = prof.get("nm_attn_decoder_step_fwd")
+        if d:
+            rows = bsz * (8 if kind == "beam8" else 1)
+            alg = bsz * 4.0 * tx * a_c + rows * 4.0 * (300 * 3 + 600 + tx)       # keys+values once per sentence
+            us = d["ms"] / d["calls"] * 1e3
+            entry["roofline"] = {"kernel": "attn_decoder_step_kernel (nm_attn_decoder_step_fwd)", "bound": "hbm",
+                                 "achieved": alg / (us * 1e-6) / 1e9, "peak": hbm, "unit": "GB/s",
+                                 "frac": alg / (us * 1e-6) / 1e9 / hbm, "us_per_launch": us,
+                                 "algorithmic_bytes_per_launch": alg, "traffic": None,
+                                 "note": "4*Tx*(A+C) bytes of encoder tensors per sentence-step (SURVEY.md 8(d)); the "
+                                         "step is a chain of five dependent matrix-vector products per hypothesis, so "
+                                         "its floor is latency (weight streaming from L2 + four cluster barriers), "
+                                         "not HBM"}
+            entry["gpu_launches_per_step"] = launches / max(d["calls"], 1)
+            entry["step_breakdown_us"] = {n: round(v["ms"] / max(d["calls"], 1) * 1e3, 2) for n, v in prof.items()
+                                          if n.startswith(("nm_attn", "nm_decode", "nm_beam"))}
+        out["{}_b{}".format(kind, bsz)] = entry
+    res = {"workload": "examples/translation.ini model at run time: greedy (batch 256, 50 steps) and beam 8 "
+                       "(batch 64 / 1, {} steps), V={}, </s> suppressed".format(beam_steps, VOCAB),
+           "metric": "decode_emitted_tokens_per_sec", "unit": "tokens/s",
+           "value": out["beam8_b64"]["tokens_per_s"], "greedy": out["greedy_b256"],
+           "beam8_batch": out["beam8_b64"], "beam8_latency": out["beam8_b1"],
+           "roofline": out["beam8_b64"].get("roofline"), "e2e": out["beam8_b64"]["e2e"]}
+    if cpu:
+        cores = _host_threads()
+        gv, gdt = cpu_rnn_greedy(16)
+        bv, bdt = cpu_rnn_beam(2, 8, 16)
+        res["cpu_baseline"] = {"value": bv, "unit": "tokens/s", "cores": cores, "kind": "port",
+                               "sample": "beam 8 over 2 sentences x 16 steps ({:.1f} s); greedy: 16 sentences x 50 "
+                                         "steps = {:.0f} tokens/s ({:.1f} s)".format(bdt, gv, gdt),
+                               "greedy_value": gv}
+    return res
+
+
+# ---------------------------------------------------------------------------
+# Transformer training
+# ---------------------------------------------------------------------------
+def run_transformer(cpu=True, steps=5, warmup=3, bsz=64, length=64, dropout=True):
+    import bench
+    from neuralmonkey_b200 import lib
+    try:
+        model = bench_models.build_transformer(vocab=VOCAB, max_len=length, dropout=dropout)
+        batches = [(bench_models.synthetic_ids(bsz, length, VOCAB, SEED + i, eos=False).pin_memory(),
+                    bench_models.synthetic_ids(bsz, length, VOCAB, SEED + 100 + i).pin_memory()) for i in range(4)]
+        dev_src = [s.cuda() for s, _ in batches]
+
+        def step(i):
+            bench_models.feed_transformer(model, dev_src[i % 4], batches[i % 4][1], True)
+            return model.trainer.train_step()
+
+        ms = _time(step, steps, warmup)
+    except Exception:      # pylint: disable=broad-except
+        if not dropout:
+            raise
+        import traceback
+        traceback.print_exc()
+        torch.cuda.empty_cache()
+        return dict(run_transformer(cpu, steps, warmup, bsz, length, dropout=False),
+                    dropout_note="the INI's dropout (keep_prob 0.9) failed on this build; measured with keep_prob 1.0")
+
+    def step_e2e(i):
+        src, tgt = batches[i % 4]
+        bench_models.feed_transformer(model, src, tgt, True)
+        return float(model.trainer.train_step()["losses"][0])
+
+    ms_e2e = _time(step_e2e, steps, 2)
+    loss = step_e2e(0)
+    model.trainer.use_cuda_graph = False
+    lib.profile_start()
+    step(0)
+    prof = lib.profile_stop()
+    total = sum(d["ms"] for d in prof.values())
+    roof = bench.gemm_family_roofline(prof, 1, (bsz * length, 512, VOCAB), _peaks(), total)
+    res = {"workload": "tests/transformer.ini perf shape: L=6 d=512 h=8 F=2048 V={} batch {}x{}, LazyAdam + Noam, "
+                       "dropout keep_prob {}".format(VOCAB, bsz, length, 0.9 if dropout else 1.0),
+           "metric": "train_target_tokens_per_sec", "value": bsz * length / (ms * 1e-3), "unit": "tokens/s",
+           "ms_per_step": ms, "steps": steps, "warmup": warmup, "last_loss": loss,
+           "params": int(model.arena.trainable_size), "roofline": roof,
+           "e2e": {"value": bsz * length / (ms_e2e * 1e-3), "unit": "tokens/s", "ms_per_step": ms_e2e,
+                   "h2d_bytes_per_step": 3 * bsz * length * 8, "d2h_bytes_per_step": 4},
+           "breakdown_ms_per_step": {n: round(d["ms"], 3) for n, d in
+                                     sorted(prof.items(), key=lambda kv: -kv[1]["ms"])[:12]}}
+    if cpu:
+        cores = _host_threads()
+        v, dt = cpu_transformer_train(4, length, 1, 1)
+        res["cpu_baseline"] = {"value": v, "unit": "tokens/s", "cores": cores, "kind": "port",
+                               "sample": "4 sentences x {} tokens per step, 1 timed step ({:.1f} s)".format(length, dt)}
+    return res
+
+
+# ---------------------------------------------------------------------------
+# Beam search over the Transformer
+# ---------------------------------------------------------------------------
+def run_beam(cpu=True, bsz=64, beam=8, steps=128, src_len=32, reps=1):
+    model = bench_models.build_transformer(vocab=VOCAB, max_len=max(steps, src_len), tie=False, beam_steps=steps)
+    dec, bs = model.decoder, model.bs_decoder
+    with torch.no_grad():
+        dec.var("state_to_word_b")[2] = -1.0e4      # EOS never wins (SURVEY 8(d) "forced steps" variant)
+    out = {}
+    hbm = float(_peaks().get("hbm_gbs", 6500.0))
+    for label, b in (("batch", bsz), ("latency", 1)):
+        src = bench_models.synthetic_ids(b, src_len, VOCAB, SEED, eos=False)
+        src_dev, src_pin = src.cuda(), src.pin_memory()
+
+        def run(_i, src=src_dev):
+            bench_models.feed_transformer(model, src, None, False)
             return bs.outputs
 
         for _ in range(3):       # loop run, capture run, first replay
-            run(0)
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        e0, e1 = _events()
-        e0.record()
-        for i in range(reps):
-            res = run(i)
-        e1.record()
-        torch.cuda.synchronize()
-        ms = e0.elapsed_time(e1) / reps
+            res = run(0)
+        ms = _time(run, reps, 0)
         emitted = int(res.last_search_step_output.token_ids.shape[0] - 1)
+
+        def e2e(_i):
+            return run(0, src_pin).last_search_step_output.token_ids.cpu()
+
+        ms_e2e = _time(e2e, reps, 0)
         out[label] = {"batch": b, "ms_per_batch": ms, "steps_run": emitted,
                       "tokens_per_s": b * emitted / (ms * 1e-3),
-                      "wall_ms": (time.perf_counter() - t0) * 1e3 / reps}
-    return {"workload": "tests/beamsearch.ini perf shape: beam {} x {} steps over the 6x512 Transformer, "
-                        "V={}, EOS suppressed".format(beam, steps, vocab),
-            "metric": "beam_decode_emitted_tokens_per_sec", "value": out["batch"]["tokens_per_s"],
-            "unit": "tokens/s", "batch_throughput": out["batch"], "batch1_latency": out["latency"],
-            "note": "self-attention keys/values of the prefix are cached per hypothesis and re-ordered "
-                    "with the beam (the reference re-runs the whole prefix every step: "
-                    "decoders/transformer.py:485-518)"}
+                      "e2e": {"value": b * emitted / (ms_e2e * 1e-3), "unit": "tokens/s", "ms_per_batch": ms_e2e,
+                              "h2d_bytes_per_step": b * src_len * 8, "d2h_bytes_per_step": (emitted + 1) * b * beam * 8}}
+        if label == "batch":
+            bs.use_cuda_graph = False
+            prof, _n = _profile(lambda: run(0))
+            bs.use_cuda_graph = True
+            d = prof.get("nm_beam_step")
+            if d:
+                alg = b * beam * VOCAB * 4.0
+                us = d["ms"] / d["calls"] * 1e3
+                out[label]["roofline"] = {"kernel": "beam_local_topk_kernel + beam_merge_kernel (nm_beam_step)",
+                                          "bound": "hbm", "achieved": alg / (us * 1e-6) / 1e9, "peak": hbm,
+                                          "unit": "GB/s", "frac": alg / (us * 1e-6) / 1e9 / hbm, "us_per_launch": us,
+                                          "algorithmic_bytes_per_launch": alg, "traffic": None,
+                                          "note": "k*V*4 bytes of log-probabilities read per sentence-step "
+                                                  "(SURVEY.md 8(d)); the step's other kernels (6 decoder layers on a "
+                                                  "KV cache, vocabulary GEMM) are listed in step_breakdown_ms"}
+                tot = sum(v["ms"] for v in prof.values())
+                out[label]["step_breakdown_ms"] = {n: round(v["ms"] / max(emitted, 1), 4) for n, v in
+                                                   sorted(prof.items(), key=lambda kv: -kv[1]["ms"])[:8]}
+                out[label]["eager_step_ms"] = tot / max(emitted, 1)
+    res = {"workload": "tests/beamsearch.ini perf shape: beam {} x {} steps over the 6x512 Transformer, "
+                       "V={}, EOS suppressed".format(beam, steps, VOCAB),
+           "metric": "beam_decode_emitted_tokens_per_sec", "value": out["batch"]["tokens_per_s"],
+           "unit": "tokens/s", "batch_throughput": out["batch"], "batch1_latency": out["latency"],
+           "roofline": out["batch"].get("roofline"), "e2e": out["batch"]["e2e"],
+           "note": "self-attention keys/values of the prefix are cached per hypothesis and re-ordered "
+                   "with the beam (the reference re-runs the whole prefix every step: "
+                   "decoders/transformer.py:485-518)"}
+    if cpu:
+        cores = _host_threads()
+        v, dt = cpu_transformer_beam(1, beam, 8, src_len)
+        res["cpu_baseline"] = {"value": v, "unit": "tokens/s", "cores": cores, "kind": "port",
+                               "sample": "beam {} over 1 sentence x 8 steps, prefix re-run every step as the "
+                                         "reference does ({:.1f} s)".format(beam, dt)}
+    return res
 
 
-def run_captioning(steps=3, warmup=2, bsz=32, vt=10000, ty=16):
-    from neuralmonkey_b200 import runtime, tf
-    from neuralmonkey_b200.attention import Attention
-    from neuralmonkey_b200.decoders import Decoder
-    from neuralmonkey_b200.encoders import ImageNet
-    from neuralmonkey_b200.trainers import CrossEntropyTrainer
-    from neuralmonkey_b200.vocabulary import Vocabulary
-
-    runtime.reset()
-    vocab = Vocabulary(["t{}".format(i) for i in range(vt - 4)])
-    enc = ImageNet(name="imagenet_vgg", data_id="images", network_type="vgg_16",
-                   spatial_layer="vgg_16/conv5/conv5_3")
-    att = Attention(name="attention", encoder=enc, state_size=512)
-    dec = Decoder(encoders=[enc], vocabulary=vocab, data_id="target", name="decoder", max_output_len=ty,
-                  rnn_size=512, embedding_size=512, attentions=[att])
-    trainer = CrossEntropyTrainer(decoders=[dec], optimizer=tf.AdamOptimizer(learning_rate=1e-4), use_cuda_graph=True)
-    for part in trainer.parameterizeds:
-        part.ensure_declared()
-    runtime.arena().finalize(runtime.device())
+# ---------------------------------------------------------------------------
+# Captioning: frozen VGG-16 + attention decoder
+# ---------------------------------------------------------------------------
+def run_captioning(cpu=True, steps=3, warmup=2, bsz=32, vt=10000, ty=16):
+    from neuralmonkey_b200 import lib
+    model = bench_models.build_captioning(vocab=vt, max_len=ty)
     g = torch.Generator().manual_seed(SEED)
     images = (torch.randn(bsz, 224, 224, 3, generator=g) * 60.0).pin_memory()
-    tgt = synthetic_ids(bsz, ty, vt, SEED + 1)
+    images_dev = images.cuda()
+    tgt = bench_models.synthetic_ids(bsz, ty, vt, SEED + 1)
 
-    def step(_i):
-        enc.feed_images(images, train=True)
-        att.reset_batch()
-        att.train_mode, att.batch_size = True, bsz
-        dec.feed_ids(tgt, bsz, train=True)
-        return trainer.train_step()
+    def step(_i, imgs=images_dev):
+        bench_models.feed_captioning(model, imgs, tgt, True)
+        return model.trainer.train_step()
 
     ms = _time(step, steps, warmup)
-    return {"workload": "tests/captioning.ini scaled: VGG-16 conv5_3 on {}x224x224x3 + GRU-512 Bahdanau "
-                        "decoder, V={}".format(bsz, vt),
-            "metric": "train_images_per_sec", "value": bsz / (ms * 1e-3), "unit": "images/s",
-            "ms_per_step": ms, "steps": steps, "warmup": warmup,
-            "conv_gflop_per_image": 30.7,
-            "conv_tflops": bsz * 30.7e9 / (ms * 1e-3) / 1e12,
-            "note": "convolutions = im2col + tcgen05 GEMM (TF32) with the bias+ReLU epilogue; the whole step "
-                    "incl. the attention decoder and optimizer is timed"}
+    ms_e2e = _time(lambda i: float(step(i, images)["losses"][0]), steps, 1)
+    model.trainer.use_cuda_graph = False
+    lib.profile_start()
+    step(0)
+    prof = lib.profile_stop()
+    conv_ms = sum(d["ms"] for n, d in prof.items() if n.startswith(("nm_conv", "nm_im2col")) or
+                  (n.startswith("nm_gemm[") and "x{}]".format(0) not in n and _is_conv_gemm(n)))
+    peak = float(_peaks().get("bf16_tflops_sustained", 1400.0))
+    conv_tf = bsz * 30.7e9 / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else None
+    res = {"workload": "tests/captioning.ini scaled: VGG-16 conv5_3 on {}x224x224x3 + GRU-512 Bahdanau "
+                       "decoder, V={}".format(bsz, vt),
+           "metric": "train_images_per_sec", "value": bsz / (ms * 1e-3), "unit": "images/s",
+           "ms_per_step": ms, "steps": steps, "warmup": warmup,
+           "roofline": {"kernel": "convolution stack (VGG-16 to conv5_3: 30.7 GFLOP per image)", "bound": "tensor",
+                        "achieved": conv_tf, "peak": peak, "unit": "TFLOP/s",
+                        "frac": conv_tf / peak if conv_tf else None, "conv_ms_per_step": conv_ms, "traffic": None,
+                        "note": "time = sum of the convolution entry points of one eagerly issued step"},
+           "e2e": {"value": bsz / (ms_e2e * 1e-3), "unit": "images/s", "ms_per_step": ms_e2e,
+                   "h2d_bytes_per_step": bsz * 224 * 224 * 3 * 4 + 2 * bsz * ty * 8, "d2h_bytes_per_step": 4},
+           "breakdown_ms_per_step": {n: round(d["ms"], 3) for n, d in
+                                     sorted(prof.items(), key=lambda kv: -kv[1]["ms"])[:10]}}
+    if cpu:
+        cores = _host_threads()
+        v, dt = cpu_vgg(1)
+        res["cpu_baseline"] = {"value": v, "unit": "images/s", "cores": cores, "kind": "port",
+                               "sample": "VGG-16 to conv5_3 on 1 image, forward only ({:.1f} s); the decoder and "
+                                         "optimizer of the step are not in the sample".format(dt)}
+    return res
 
 
-RUNNERS = {"transformer": run_transformer, "beam": run_beam, "captioning": run_captioning}
+def _is_conv_gemm(name: str) -> bool:
+    """nm_gemm[NN MxNxK] instances of the convolution stack: K = 9*Cin (27, 576, 1152, 2304, 4608)."""
+    import re
+    mm = re.match(r"nm_gemm\[NN (\d+)x(\d+)x(\d+)\]", name)
+    return bool(mm) and int(mm.group(3)) in (27, 28, 576, 1152, 2304, 4608)
+
+
+RUNNERS = {"rnn_decode": run_rnn_decode, "transformer": run_transformer, "beam": run_beam,
+           "captioning": run_captioning}
 
 if __name__ == "__main__":
-    for name in ([a for a in sys.argv[1:] if not a.startswith('--')] or list(RUNNERS)):
+    for name in ([a for a in sys.argv[1:] if not a.startswith("--")] or list(RUNNERS)):
         t0 = time.perf_counter()
-        result = RUNNERS[name](breakdown=True) if name == "transformer" and "--breakdown" in sys.argv else RUNNERS[name]()
+        result = RUNNERS[name](cpu="--no-cpu" not in sys.argv)
         result["wall_s"] = time.perf_counter() - t0
         print(json.dumps(result), flush=True)
+    bench_models.cleanup()

@@ -226,9 +226,9 @@ int nm_logits_xent_bwd(const float* X, int64_t ldx, const float* W, int64_t ldw,
 /* ---- K5/K6 with fp16 operands (kind::f16), optional path - ops.py uses it with NMB200_XENT16=1 ----
  * Every product is K-major x K-major: X16 [M,K], WT16 [V,K] (the projection matrix transposed),
  * row pitches multiples of 8 elements, bases 16-byte aligned.
- * nm_cast_f16: dst = half(src * row_scale[row]) (row_scale may be NULL); transpose != 0 writes
- *   dst [cols + extra_ones, ld_dst] = src^T followed by `extra_ones` rows holding row_scale
- *   (the ones column of the bias-gradient trick); padding up to ld_dst is zeroed.
+ * nm_cast_f16: dst = half(src * row_scale[row]) (row_scale may be NULL) followed by `extra_ones` columns
+ *   holding row_scale (the ones column of the bias-gradient trick); transpose != 0 writes
+ *   dst [cols + extra_ones, ld_dst] = the transpose of that; padding up to ld_dst is zeroed.
  * nm_gemm_f16: C[M,N] (or C^T when transposed != 0: element (m,n) -> C[n*ldc+m])
  *   = alpha_dev[0] * row_scale[m] * A16[M,K] . B16[N,K]^T  (+ C when beta == 1).
  * nm_logits_xent_fwd16: as nm_logits_xent_fwd.
@@ -239,6 +239,12 @@ int nm_cast_f16(const float* src, int64_t ld_src, void* dst, int64_t ld_dst, int
 int nm_gemm_f16(int64_t M, int64_t N, int64_t K, const void* A16, int64_t lda, const void* B16,
                 int64_t ldb, float* C, int64_t ldc, const float* alpha_dev, const float* row_scale,
                 float beta, int transposed, void* stream);
+/* C[M,N] = alpha_dev[0] * A16^T . B16 (+ C when beta == 1) with both operands stored reduction-major:
+ * A16 [K,M] (row pitch lda), B16 [K,N] (row pitch ldb) - the weight-gradient product X^T . dY of the
+ * vocabulary projection straight from the row-major fp16 matrices (MN-major tcgen05 operands), no
+ * transposed copies. */
+int nm_gemm_f16_tn(int64_t M, int64_t N, int64_t K, const void* A16, int64_t lda, const void* B16,
+                   int64_t ldb, float* C, int64_t ldc, const float* alpha_dev, float beta, void* stream);
 int nm_logits_xent_fwd16(const void* X16, int64_t ldx, const void* WT16, int64_t ldw, const float* b,
                          int64_t unk_index, const int64_t* targets, const float* weights, float* lse,
                          float* xent, int64_t* argmax, float* part, float* logits_out, int64_t ldl,

@@ -145,48 +145,38 @@ __device__ __forceinline__ void ds_panel(const DsSeg* segs, int nseg, int K, con
         if (lo < hi) {
           const float* wp = W + (int64_t)lo * ldw + col;
           const float* ip = segs[s].inT + (lo - start) * DS_R;
-          int k = lo;
-          for (; k + DS_UNROLL <= hi; k += DS_UNROLL) {
+          // batches of DS_UNROLL weight rows: all loads of a batch are in flight together; the last,
+          // partial batch is predicated instead of falling back to one dependent load per row
+          for (int k = lo; k < hi; k += DS_UNROLL) {
             float w[DS_UNROLL][G];
 #pragma unroll
             for (int u = 0; u < DS_UNROLL; ++u) {
-              if constexpr (G == 4) {
-                const float4 t = __ldg(reinterpret_cast<const float4*>(wp + (int64_t)u * ldw));
-                w[u][0] = t.x; w[u][1] = t.y; w[u][2] = t.z; w[u][3] = t.w;
+              if (k + u < hi) {
+                if constexpr (G == 4) {
+                  const float4 t = __ldg(reinterpret_cast<const float4*>(wp + (int64_t)u * ldw));
+                  w[u][0] = t.x; w[u][1] = t.y; w[u][2] = t.z; w[u][3] = t.w;
+                } else {
+                  w[u][0] = __ldg(wp + (int64_t)u * ldw);
+                }
               } else {
-                w[u][0] = __ldg(wp + (int64_t)u * ldw);
+#pragma unroll
+                for (int c = 0; c < G; ++c) w[u][c] = 0.f;
               }
             }
 #pragma unroll
             for (int u = 0; u < DS_UNROLL; ++u) {
-              const float4 i0 = *reinterpret_cast<const float4*>(ip + u * DS_R);
-              const float4 i1 = *reinterpret_cast<const float4*>(ip + u * DS_R + 4);
-              const float in[DS_R] = {i0.x, i0.y, i0.z, i0.w, i1.x, i1.y, i1.z, i1.w};
+              if (k + u < hi) {
+                const float4 i0 = *reinterpret_cast<const float4*>(ip + u * DS_R);
+                const float4 i1 = *reinterpret_cast<const float4*>(ip + u * DS_R + 4);
+                const float in[DS_R] = {i0.x, i0.y, i0.z, i0.w, i1.x, i1.y, i1.z, i1.w};
 #pragma unroll
-              for (int r = 0; r < DS_R; ++r)
+                for (int r = 0; r < DS_R; ++r)
 #pragma unroll
-                for (int c = 0; c < G; ++c) acc[r][c] = fmaf(in[r], w[u][c], acc[r][c]);
+                  for (int c = 0; c < G; ++c) acc[r][c] = fmaf(in[r], w[u][c], acc[r][c]);
+              }
             }
             wp += (int64_t)DS_UNROLL * ldw;
             ip += DS_UNROLL * DS_R;
-          }
-          for (; k < hi; ++k) {
-            float w[G];
-            if constexpr (G == 4) {
-              const float4 t = __ldg(reinterpret_cast<const float4*>(wp));
-              w[0] = t.x; w[1] = t.y; w[2] = t.z; w[3] = t.w;
-            } else {
-              w[0] = __ldg(wp);
-            }
-            const float4 i0 = *reinterpret_cast<const float4*>(ip);
-            const float4 i1 = *reinterpret_cast<const float4*>(ip + 4);
-            const float in[DS_R] = {i0.x, i0.y, i0.z, i0.w, i1.x, i1.y, i1.z, i1.w};
-#pragma unroll
-            for (int r = 0; r < DS_R; ++r)
-#pragma unroll
-              for (int c = 0; c < G; ++c) acc[r][c] = fmaf(in[r], w[c], acc[r][c]);
-            wp += ldw;
-            ip += DS_R;
           }
         }
         start += len;

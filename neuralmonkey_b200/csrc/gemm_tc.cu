@@ -378,7 +378,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                int64_t M, int64_t N, int64_t K, TcEpilogue epi, MnDesc mn, int splits, int kb_per_split,
                TcExt ext) {
-  static_assert(ESZ == 4 || (ESZ == 2 && !A_MN && !B_MN), "fp16 operands are K-major only");
+  static_assert(ESZ == 4 || !(A_MN || B_MN) || (BN % 64 == 0), "MN-major fp16 B tiles come in 64-column boxes");
   static_assert(ESZ == 2 || MODE != TC_EPI_XENT_BWD16, "the fp16 epilogue belongs to the fp16 instances");
   constexpr int BK = 128 / ESZ;                // elements per 128-byte k-block
   using Cfg = TcCfg<BN>;
@@ -442,19 +442,23 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           const uint32_t b_dst = a_dst + TC_A_BYTES;
           mbar_expect_tx(full_bar(stage), (uint32_t)Cfg::STAGE_BYTES);
           const int32_t k0 = kb * BK;
+          // MN-major tiles arrive as boxes of one 128-byte swizzle row of MN elements (32 fp32 / 64 fp16)
+          // by one k-block of rows: 4 KB (fp32) or 8 KB (fp16) each
+          constexpr int MN_BOX = 128 / ESZ;
+          constexpr int MN_BOX_BYTES = MN_BOX * BK * ESZ;
           if (!A_MN) {
-            tma_load_2d(a_dst, &map_a, full_bar(stage), k0, m0);  // box {32 k, 128 rows}
+            tma_load_2d(a_dst, &map_a, full_bar(stage), k0, m0);  // box {one k-block, 128 rows}
           } else {
 #pragma unroll
-            for (int j = 0; j < TC_BM / 32; ++j)  // box {32 m, 32 k} per 4 KB block
-              tma_load_2d(a_dst + j * 4096, &map_a, full_bar(stage), m0 + 32 * j, k0);
+            for (int j = 0; j < TC_BM / MN_BOX; ++j)
+              tma_load_2d(a_dst + j * MN_BOX_BYTES, &map_a, full_bar(stage), m0 + MN_BOX * j, k0);
           }
           if (!B_MN) {
-            tma_load_2d(b_dst, &map_b, full_bar(stage), k0, n0);  // box {32 k, BN rows}
+            tma_load_2d(b_dst, &map_b, full_bar(stage), k0, n0);  // box {one k-block, BN rows}
           } else {
 #pragma unroll
-            for (int j = 0; j < BN / 32; ++j)
-              tma_load_2d(b_dst + j * 4096, &map_b, full_bar(stage), n0 + 32 * j, k0);
+            for (int j = 0; j < BN / MN_BOX; ++j)
+              tma_load_2d(b_dst + j * MN_BOX_BYTES, &map_b, full_bar(stage), n0 + MN_BOX * j, k0);
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         }
@@ -494,6 +498,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             //   accepts): atoms of 4 k-rows x 128 B (32 MN elements); next 4-k-row group at
             //   +512 B (SBO), next 32-element MN atom = next TMA box at +4096 B (LBO);
             //   K step (8 k-rows) = +1024 B.
+            // MN-major fp16 (kind::f16 takes both majors in the plain 128-byte swizzle): atoms of
+            //   8 k-rows x 128 B (64 MN elements); next 8-k-row group at +1024 B (SBO), next 64-element
+            //   MN atom = next TMA box at +8192 B (LBO); K step of one instruction (16 k-rows) = +2048 B.
             const uint64_t da = A_MN ? smem_desc(a_addr + k * mn.kadv, mn.lbo, mn.sbo, mn.layout)
                                      : smem_desc(a_addr + k * 32, 16, 1024, SMEM_LAYOUT_SW128);
             const uint64_t db = B_MN ? smem_desc(b_addr + k * mn.kadv, mn.lbo, mn.sbo, mn.layout)
@@ -684,12 +691,13 @@ static int launch_cfg(const CUtensorMap& ma, const CUtensorMap& mb, int64_t M, i
   return NM_OK;
 }
 
-// fp16 operands (both K-major): no split-K, one wave structure as above
-template <int BN, int MODE>
+// fp16 operands: no split-K, one wave structure as above.  MN = both operands MN-major (the
+// reduction dimension strided: X^T . dY products), otherwise both K-major.
+template <int BN, int MODE, bool MN = false>
 static int launch_cfg16(const CUtensorMap& ma, const CUtensorMap& mb, int64_t M, int64_t N, int64_t K,
                         const TcEpilogue& epi, const TcExt& ext, cudaStream_t s) {
   using Cfg = TcCfg<BN>;
-  auto kern = tc_gemm_kernel<BN, false, false, MODE, 2>;
+  auto kern = tc_gemm_kernel<BN, MN, MN, MODE, 2>;
   static bool attr_done = false;
   if (!attr_done) {
     NM_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
@@ -697,13 +705,16 @@ static int launch_cfg16(const CUtensorMap& ma, const CUtensorMap& mb, int64_t M,
   }
   const int64_t tiles = ceil_div(M, TC_BM) * ceil_div(N, BN);
   const int64_t grid = tiles < sm_count() ? tiles : sm_count();
-  kern<<<(unsigned)grid, TC_THREADS, Cfg::SMEM_BYTES, s>>>(ma, mb, M, N, K, epi, MnDesc{0, 0, 0, 0}, 1,
-                                                           (int)ceil_div(K, 64), ext);
+  kern<<<(unsigned)grid, TC_THREADS, Cfg::SMEM_BYTES, s>>>(
+      ma, mb, M, N, K, epi, MN ? MnDesc{SMEM_LAYOUT_SW128, 1024, 8192, 2048} : MnDesc{0, 0, 0, 0}, 1,
+      (int)ceil_div(K, 64), ext);
   NM_LAUNCH_CHECK("tc_gemm_kernel(fp16)");
   return NM_OK;
 }
 
-// 2-D fp16 tensor [rows, cols] with row pitch ld (elements); box = {64 k, box_rows}, 128-byte swizzle.
+// 2-D fp16 tensor [rows, cols] with row pitch ld (elements); box = {64 inner elements, box_rows},
+// 128-byte swizzle.  K-major operand: inner = K, rows = M or N; MN-major: inner = M or N, rows = K
+// (box_rows = 64: one k-block).
 static int make_map16(CUtensorMap* map, const void* base, int64_t rows, int64_t cols, int64_t ld,
                       uint32_t box_rows) {
   EncodeTiledFn fn = get_encode_fn();
@@ -801,6 +812,30 @@ int tc_gemm_launch(int transA, int transB, int64_t M, int64_t N, int64_t K, cons
   if (bn == 160) NM_TC_DISPATCH(160, TC_EPI_DENSE);
   NM_TC_DISPATCH(256, TC_EPI_DENSE);
 #undef NM_TC_DISPATCH
+}
+
+int tc_gemm16_mn_launch(int64_t M, int64_t N, int64_t K, const void* A, int64_t lda, const void* B,
+                        int64_t ldb, const TcEpilogue& epi, const TcExt& ext, cudaStream_t s) {
+  // A stored [K, M] (row pitch lda), B stored [K, N] (row pitch ldb): both MN-major
+  NM_REQUIRE(M >= 1 && N >= 1 && K >= 1 && M <= 0x7fffffffLL && N <= 0x7fffffffLL && K <= 0x7fffffffLL,
+             NM_E_INVALID, "tc_gemm16_mn: bad shape %lld x %lld x %lld", (long long)M, (long long)N, (long long)K);
+  NM_REQUIRE((lda & 7) == 0 && (ldb & 7) == 0 && (reinterpret_cast<uintptr_t>(A) & 15) == 0 &&
+                 (reinterpret_cast<uintptr_t>(B) & 15) == 0,
+             NM_E_INVALID, "tc_gemm16_mn: fp16 operands need 16-byte aligned bases and row pitches");
+  NM_REQUIRE(epi.mode == TC_EPI_DENSE, NM_E_INVALID, "tc_gemm16_mn: dense epilogue only");
+  CUtensorMap ma, mb;
+  int rc = make_map16(&ma, A, K, M, lda, 64);
+  if (rc) return rc;
+  rc = make_map16(&mb, B, K, N, ldb, 64);
+  if (rc) return rc;
+  // 64-column boxes: BN in {64, 128, 256}
+  int bn = 256;
+  if (N <= 64) bn = 64;
+  else if (N <= 128) bn = 128;
+  else if (ceil_div(M, TC_BM) * ceil_div(N, 256) < sm_count()) bn = 128;
+  if (bn == 64) return launch_cfg16<64, TC_EPI_DENSE, true>(ma, mb, M, N, K, epi, ext, s);
+  if (bn == 128) return launch_cfg16<128, TC_EPI_DENSE, true>(ma, mb, M, N, K, epi, ext, s);
+  return launch_cfg16<256, TC_EPI_DENSE, true>(ma, mb, M, N, K, epi, ext, s);
 }
 
 int tc_gemm16_launch(int64_t M, int64_t N, int64_t K, const void* A, int64_t lda, const void* B,

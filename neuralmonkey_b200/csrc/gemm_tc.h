@@ -57,4 +57,9 @@ int tc_gemm_launch(int transA, int transB, int64_t M, int64_t N, int64_t K, cons
 int tc_gemm16_launch(int64_t M, int64_t N, int64_t K, const void* A, int64_t lda, const void* B,
                      int64_t ldb, const TcEpilogue& epi, const TcExt& ext, cudaStream_t s);
 
+// The same with both operands MN-major (reduction dimension strided): A is [K,M] (row pitch lda), B is
+// [K,N] (row pitch ldb) - weight-gradient products X^T . dY without transposed copies.  Dense epilogue.
+int tc_gemm16_mn_launch(int64_t M, int64_t N, int64_t K, const void* A, int64_t lda, const void* B,
+                        int64_t ldb, const TcEpilogue& epi, const TcExt& ext, cudaStream_t s);
+
 }  // namespace nm

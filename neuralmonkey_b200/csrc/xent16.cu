@@ -17,17 +17,21 @@
 
 namespace nm {
 
-// dst[r * ld_dst + c] = half(src[r * ld_src + c] * (row_scale ? row_scale[r] : 1)), c < cols;
-// the padding columns cols..ld_dst-1 are zeroed so that a padded K never feeds garbage to the MMA.
+// dst[r * ld_dst + c] = half(src[r * ld_src + c] * (row_scale ? row_scale[r] : 1)), c < cols; the
+// `extra_ones` columns behind them hold the row's scale (the column of ones of the bias-gradient trick,
+// scaled alike); the padding columns up to ld_dst are zeroed so that a padded K never feeds garbage
+// to the MMA.
 __global__ void cast_f16_kernel(const float* __restrict__ src, int64_t ld_src, __half* __restrict__ dst,
                                 int64_t ld_dst, int64_t rows, int64_t cols,
-                                const float* __restrict__ row_scale) {
+                                const float* __restrict__ row_scale, int extra_ones) {
   const int64_t total = rows * ld_dst;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total;
        i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t r = i / ld_dst, c = i - r * ld_dst;
     float v = 0.f;
-    if (c < cols) v = src[r * ld_src + c] * (row_scale ? row_scale[r] : 1.f);
+    const float sc = row_scale ? row_scale[r] : 1.f;
+    if (c < cols) v = src[r * ld_src + c] * sc;
+    else if (c < cols + extra_ones) v = sc;
     dst[i] = __float2half_rn(v);
   }
 }
@@ -69,11 +73,11 @@ int nm_cast_f16(const float* src, int64_t ld_src, void* dst, int64_t ld_dst, int
   NM_REQUIRE(src && dst && rows > 0 && cols > 0 && ld_src >= cols, NM_E_INVALID, "nm_cast_f16: bad arguments");
   cudaStream_t s = (cudaStream_t)stream;
   if (!transpose) {
-    NM_REQUIRE(ld_dst >= cols && extra_ones == 0, NM_E_INVALID, "nm_cast_f16: bad destination pitch");
+    NM_REQUIRE(extra_ones >= 0 && ld_dst >= cols + extra_ones, NM_E_INVALID, "nm_cast_f16: bad destination pitch");
     const int64_t total = rows * ld_dst;
     const int64_t blocks = ceil_div(total, 256 * 4);
     cast_f16_kernel<<<(unsigned)(blocks < 148 * 16 ? blocks : 148 * 16), 256, 0, s>>>(
-        src, ld_src, reinterpret_cast<__half*>(dst), ld_dst, rows, cols, row_scale);
+        src, ld_src, reinterpret_cast<__half*>(dst), ld_dst, rows, cols, row_scale, extra_ones);
   } else {
     NM_REQUIRE(ld_dst >= rows && extra_ones >= 0, NM_E_INVALID, "nm_cast_f16: bad destination pitch");
     const dim3 grid((unsigned)ceil_div(ld_dst, 32), (unsigned)ceil_div(cols + extra_ones, 32));
@@ -102,6 +106,23 @@ int nm_gemm_f16(int64_t M, int64_t N, int64_t K, const void* A16, int64_t lda, c
   ext.row_scale = row_scale;
   ext.transposed = transposed;
   return tc_gemm16_launch(M, N, K, A16, lda, B16, ldb, epi, ext, (cudaStream_t)stream);
+}
+
+int nm_gemm_f16_tn(int64_t M, int64_t N, int64_t K, const void* A16, int64_t lda, const void* B16, int64_t ldb,
+                   float* C, int64_t ldc, const float* alpha_dev, float beta, void* stream) {
+  NM_REQUIRE(A16 && B16 && C, NM_E_INVALID, "nm_gemm_f16_tn: null pointer");
+  NM_REQUIRE(beta == 0.f || beta == 1.f, NM_E_INVALID, "nm_gemm_f16_tn: beta must be 0 or 1");
+  NM_REQUIRE(lda >= M && ldb >= N && ldc >= N, NM_E_INVALID, "nm_gemm_f16_tn: bad pitches");
+  TcEpilogue epi{};
+  epi.mode = TC_EPI_DENSE;
+  epi.C = C;
+  epi.ldc = ldc;
+  epi.act = NM_ACT_NONE;
+  epi.beta = beta;
+  epi.unk_index = -1;
+  TcExt ext{};
+  ext.alpha = alpha_dev;
+  return tc_gemm16_mn_launch(M, N, K, A16, lda, B16, ldb, epi, ext, (cudaStream_t)stream);
 }
 
 int nm_logits_xent_bwd16(const void* X16, int64_t ldx, const void* WT16, int64_t ldw, const float* b,

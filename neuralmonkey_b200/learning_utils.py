@@ -29,6 +29,13 @@ def shard_batch(batch: Dataset) -> Dataset:
     return Dataset("{}.rank{}".format(batch.name, distributed.rank()), data, batch.batching)
 
 
+def merge_batches(first: Dataset, second: Dataset) -> Dataset:
+    """The sentences of two batches as one batch (same series)."""
+    rows = {s: list(first.get_series(s)) + list(second.get_series(s)) for s in second.series}
+    data = {s: (lambda v=vals: iter(v)) for s, vals in rows.items()}
+    return Dataset(second.name, data, second.batching)
+
+
 def training_loop(cfg: Namespace) -> None:
     _check_series_collisions(cfg.runners, cfg.postprocess)
     if cfg.initial_variables is not None:
@@ -48,7 +55,19 @@ def training_loop(cfg: Namespace) -> None:
             batches = cfg.train_dataset.batches()
             if epoch_n == 1 and cfg.train_start_offset:
                 _skip_lines(cfg.train_start_offset, batches)
+            carry = None        # data parallel: a batch with fewer sentences than ranks is held over
             for batch_n, batch in enumerate(batches):
+                if distributed.world_size() > 1:
+                    # every rank needs a non-empty shard (the kernels require B > 0, and a rank that skips its
+                    # step would leave the others waiting in the all-reduce).  All ranks see the same global
+                    # batches, so they take this decision identically: the short batch (the remainder of an
+                    # epoch, a flushed bucket) joins the next one; what is left at the end of the epoch
+                    # (< world sentences) is dropped.
+                    if carry is not None:
+                        batch, carry = merge_batches(carry, batch), None
+                    if len(batch) < distributed.world_size():
+                        carry = batch
+                        continue
                 step += 1
                 seen_instances += len(batch)
                 local = shard_batch(batch)

@@ -22,23 +22,48 @@ class DelayedUpdateTrainer(GenericTrainer):
 
     def train_step(self, apply_update: bool = True, grad_scale: float = 1.0, zero_grad: bool = True):
         """Accumulate; every `batches_per_update`-th call also applies the averaged update.
-        (The per-batch token means are averaged, as the reference's buffers do.)"""
+
+        Each batch contributes the gradient of ITS token-mean loss (the reference's buffers sum the
+        gradients of `train_loss` and divide by the number of batches, delayed_update_trainer.py:115-204).
+        Data parallel: the mean of a batch is sum(xent over all ranks) / sum(mask over all ranks), so the
+        two scalars of every micro-batch are exchanged right away (one 2-float all-reduce) and the
+        gradients - of the un-normalised sum divided by the GLOBAL count - are exchanged once, on the update
+        step; N ranks then reproduce the single-GPU update exactly."""
+        import torch
+        from neuralmonkey_b200 import distributed
         arena = runtime.arena()
-        first = self._accumulated == 0
-        if first:
+        if self._accumulated == 0:
             arena.zero_grad()
-        total = None
-        for obj in self.objectives:
-            w = 1.0 if obj.weight is None else obj.weight
-            term = obj.loss * w
-            total = term if total is None else total + term
-        total.backward()
-        losses = [obj.loss.detach() for obj in self.objectives]
+        world = distributed.world_size()
+        exact = None
+        if len(self.objectives) == 1 and self.objectives[0].gradients is None:
+            exact = self.objectives[0].loss_sum_and_count
+        if exact is not None:
+            loss_sum, count = exact
+            stats = torch.stack([loss_sum.detach().reshape(()), count.detach().reshape(()).to(loss_sum.dtype)])
+            distributed.all_reduce_sum(stats)
+            w = self.objectives[0].weight
+            term = loss_sum / stats[1]
+            (term if w is None else term * w).backward()
+            losses = [stats[0] / stats[1]]
+            rank_scale = 1.0                # every rank already divided by the global count
+        else:
+            total = None
+            for obj in self.objectives:
+                if obj.gradients is not None:
+                    raise NotImplementedError("objectives with explicit gradients (RL) are out of scope")
+                w = 1.0 if obj.weight is None else obj.weight
+                term = obj.loss * w
+                total = term if total is None else total + term
+            total.backward()
+            losses = [obj.loss.detach() for obj in self.objectives]
+            rank_scale = 1.0 / world        # mean of the per-rank means
+        # gradients autograd delivered to plain torch expressions (e.g. an indexed embedding row) live in
+        # `.grad` of the parameter views: fold them into the flat buffer after EVERY backward
+        arena.fold_autograd_grads()
         self._accumulated += 1
         if self._accumulated == self.batches_per_update:
-            from neuralmonkey_b200 import distributed
-            world = distributed.world_size()
             distributed.all_reduce_sum(arena.allreduce_view)
-            self.apply_gradients(1.0 / (self.batches_per_update * world), None)
+            self.apply_gradients(rank_scale / self.batches_per_update, None)
             self._accumulated = 0
         return {"losses": losses, "l1l2": self._l1l2}

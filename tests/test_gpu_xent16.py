@@ -1,17 +1,9 @@
-"""The fp16-operand vocabulary projection (csrc/xent16.cu, ops._LogitsXent16) against fp64 references and
-against the default TF32 path.  The path is opt-in and has NOT been run on a GPU yet (it was written
-after this round's GPU budget was spent), so this file is skipped unless the switch is set:
-
-    NMB200_XENT16=1 python -m pytest tests/test_gpu_xent16.py -m gpu -q
-"""
-import os
-
+"""The fp16-operand vocabulary projection (csrc/xent16.cu, ops._LogitsXent16: the default on the
+tensor-core engine) against fp64 references and against the TF32 path (NMB200_XENT16=0)."""
 import pytest
 import torch
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("NMB200_XENT16") != "1",
-                                 reason="fp16 vocabulary path not yet verified on a GPU; set NMB200_XENT16=1")]
+pytestmark = pytest.mark.gpu
 
 
 def _lib():
@@ -36,6 +28,12 @@ def test_cast_f16(rows, cols):
              lib.stream())
     want = (src * scale[:, None]).half()
     assert torch.equal(dst[:, :cols], want) and float(dst[:, cols:].abs().max() if ld > cols else 0) == 0.0
+    ld1 = (cols + 1 + 7) // 8 * 8                     # with the scaled column of ones behind the data
+    dst1 = torch.full((rows, ld1), 7.0, device="cuda", dtype=torch.float16)
+    lib.call("nm_cast_f16", lib.ptr(src), src.stride(0), lib.ptr(dst1), ld1, rows, cols, lib.ptr(scale), 0, 1,
+             lib.stream())
+    assert torch.equal(dst1[:, :cols], want) and torch.equal(dst1[:, cols], scale.half())
+    assert ld1 == cols + 1 or float(dst1[:, cols + 1:].abs().max()) == 0.0
     ldt = (rows + 7) // 8 * 8
     dst_t = torch.full((cols + 1, ldt), 7.0, device="cuda", dtype=torch.float16)
     lib.call("nm_cast_f16", lib.ptr(src), src.stride(0), lib.ptr(dst_t), ldt, rows, cols, lib.ptr(scale), 1, 1,
@@ -69,6 +67,27 @@ def test_gemm_f16(m, n, k, transposed, beta):
              lib.ptr(alpha_d), lib.ptr(scale_d), beta, transposed, lib.stream())
     torch.cuda.synchronize()
     assert _rel(c, want) < 1e-5
+
+
+@pytest.mark.parametrize("m,n,k", [(64, 64, 64), (301, 1000, 1100), (301, 4100, 12800), (130, 96, 72), (40, 260, 8200)])
+@pytest.mark.parametrize("beta", [0.0, 1.0])
+def test_gemm_f16_tn(m, n, k, beta):
+    """C[M,N] = alpha * A^T . B with A [K,M], B [K,N] stored reduction-major (MN-major tcgen05 operands)."""
+    lib = _lib()
+    g = torch.Generator().manual_seed(3)
+    mp, np_ = (m + 7) // 8 * 8, (n + 7) // 8 * 8
+    a = torch.full((k, mp), 9.0, dtype=torch.float16)       # padding columns must never be read
+    b = torch.full((k, np_), 9.0, dtype=torch.float16)
+    a[:, :m] = (torch.randn(k, m, generator=g) * 0.5).half()
+    b[:, :n] = (torch.randn(k, n, generator=g) * 0.5).half()
+    c0 = torch.randn(m, n, generator=g)
+    want = 0.37 * (a[:, :m].double().t() @ b[:, :n].double()) + beta * c0.double()
+    c = c0.clone().cuda()
+    ad, bd, alpha_d = a.cuda(), b.cuda(), torch.tensor([0.37]).cuda()
+    lib.call("nm_gemm_f16_tn", m, n, k, lib.ptr(ad), mp, lib.ptr(bd), np_, lib.ptr(c), c.stride(0),
+             lib.ptr(alpha_d), beta, lib.stream())
+    torch.cuda.synchronize()
+    assert _rel(c, want) < 5e-5       # fp32 accumulation over up to 12800 products
 
 
 @pytest.mark.parametrize("m,k,v,unk", [(96, 24, 200, 3), (1100, 300, 4100, -1)])

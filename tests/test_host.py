@@ -283,3 +283,50 @@ def test_two_rank_training_through_the_entry_point(tmp_path):
     assert len(losses) >= 2 and losses[-1] < losses[0], losses
     assert len(open(os.path.join(out, "val.out")).read().splitlines()) == 30
     assert os.path.exists(os.path.join(out, "variables.data.final"))
+
+
+def test_data_parallel_training_never_hands_a_rank_an_empty_shard(monkeypatch):
+    """A batch with fewer sentences than ranks (the remainder of an epoch, a flushed bucket) is held over
+    and merged into the next one: every executed batch gives every rank >= 1 sentence, identically on all
+    ranks; nothing hangs in the all-reduce."""
+    from argparse import Namespace
+    from neuralmonkey_b200 import learning_utils
+    from neuralmonkey_b200.dataset import BatchingScheme, Dataset
+
+    def batch(ids):
+        rows = [["w{}".format(i)] for i in ids]
+        return Dataset("b", {"source": (lambda r=rows: iter(r))}, BatchingScheme(batch_size=8))
+
+    sizes = [5, 2, 3, 1, 6, 2]                  # world = 4: the 2-, 3-, 1- and final 2-sentence batches are short
+    batches, nxt = [], 0
+    for n in sizes:
+        batches.append(batch(range(nxt, nxt + n)))
+        nxt += n
+
+    class Trainer:
+        feedables = set()
+
+    class Manager:
+        best_score, best_score_epoch, best_score_batch = 0.0, 0, 0
+        executed = []
+
+        def initialize_model_parts(self, _executors):
+            pass
+
+        def execute(self, local, _feedables, _trainers, train=False, summaries=True):
+            Manager.executed.append([row[0] for row in local.get_series("source")])
+
+    for rank in range(4):
+        Manager.executed = []
+        monkeypatch.setattr(distributed, "world_size", lambda: 4)
+        monkeypatch.setattr(distributed, "rank", lambda r=rank: r)
+        cfg = Namespace(runners=[], trainers=[Trainer()], postprocess=None, initial_variables=None,
+                        tf_manager=Manager(), epochs=1, train_dataset=Namespace(batches=lambda: iter(batches)),
+                        train_start_offset=0, log_timer=lambda step, last: False,
+                        val_timer=lambda step, last: False, val_datasets=[], main_metric="x")
+        learning_utils.training_loop(cfg)
+        # executed global batches: [5], [2+3], [1+6]; the last 2 sentences (< 4 ranks) are dropped
+        assert [len(x) for x in Manager.executed] == {0: [2, 2, 2], 1: [1, 1, 2], 2: [1, 1, 2], 3: [1, 1, 1]}[rank]
+        assert all(len(x) > 0 for x in Manager.executed)
+    # rank 0's shards are the leading sentences of the merged batches
+    assert Manager.executed is not None
