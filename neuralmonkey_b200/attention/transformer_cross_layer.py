@@ -1,7 +1,7 @@
 """Encoder-decoder attention combination for the Transformer decoder
 (reference: neuralmonkey/attention/transformer_cross_layer.py:10-263): `single`, `serial`,
 `parallel`, and the two further multi-source strategies `flat` and `hierarchical` (compositions of
-`single`; behind NMB200_UNVERIFIED until they have run on a GPU - SURVEY.md 8(f) N4)."""
+`single`; GPU-verified by tests/test_gpu_variants.py - SURVEY.md 8(f) N4)."""
 from typing import List
 
 import torch

@@ -46,6 +46,53 @@ __device__ __forceinline__ Cand block_best_cand(Cand c, float* sm_s, int32_t* sm
   return r;  // identical in every warp
 }
 
+// Top-k of the candidates a CTA holds in registers (ITEMS per thread), in (score desc, index asc) order:
+// every warp extracts the k best of its own 32*ITEMS candidates with shuffles only (no block barrier),
+// then warp 0 merges the (warps * k) survivors.  The order is total (indices are unique), so the result
+// does not depend on how the candidates are spread over threads.  out_s/out_i: [k] in shared memory,
+// valid after the trailing __syncthreads(); wk_s/wk_i: [warps * k] scratch in shared memory.
+template <int ITEMS>
+__device__ __forceinline__ void cta_topk(const float (&sc)[ITEMS], const int32_t (&ix)[ITEMS], int k,
+                                         float* wk_s, int32_t* wk_i, float* out_s, int32_t* out_i) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  uint32_t taken = 0;
+  for (int r = 0; r < k; ++r) {
+    Cand best{-INFINITY, 0x7fffffff};
+#pragma unroll
+    for (int it = 0; it < ITEMS; ++it)
+      if (!((taken >> it) & 1u) && ix[it] != 0x7fffffff && cand_better(sc[it], ix[it], best.s, best.i)) {
+        best.s = sc[it];
+        best.i = ix[it];
+      }
+    const Cand win = warp_best_cand(best);
+#pragma unroll
+    for (int it = 0; it < ITEMS; ++it)
+      if (ix[it] == win.i && win.i != 0x7fffffff) taken |= (1u << it);
+    if (lane == 0) { wk_s[w * k + r] = win.s; wk_i[w * k + r] = win.i; }
+  }
+  __syncthreads();
+  if (w == 0) {
+    const int n = nw * k;
+    int32_t last_i = -1;
+    float last_s = INFINITY;
+    for (int r = 0; r < k; ++r) {
+      Cand best{-INFINITY, 0x7fffffff};
+      for (int c = lane; c < n; c += 32) {
+        const float s2 = wk_s[c];
+        const int32_t i2 = wk_i[c];
+        if (i2 == 0x7fffffff) continue;
+        const bool after = (r == 0) || s2 < last_s || (s2 == last_s && i2 > last_i);
+        if (after && cand_better(s2, i2, best.s, best.i)) { best.s = s2; best.i = i2; }
+      }
+      const Cand win = warp_best_cand(best);
+      last_s = win.s;
+      last_i = win.i;
+      if (lane == 0) { out_s[r] = win.s; out_i[r] = win.i; }
+    }
+  }
+  __syncthreads();
+}
+
 // length penalty ((5+len)/6)^alpha, the fp32 division first (as the reference graph does),
 // then a correctly rounded powf through double precision.
 __device__ __forceinline__ float length_penalty(int32_t len, float alpha) {
@@ -78,8 +125,6 @@ beam_local_topk_kernel(const float* __restrict__ logprobs, const float* __restri
                        const int32_t* __restrict__ lengths, const uint8_t* __restrict__ finished,
                        float alpha, float* __restrict__ cand_s, int32_t* __restrict__ cand_i,
                        int64_t k, int64_t V) {
-  __shared__ float sm_s[32];
-  __shared__ int32_t sm_i[32];
   __shared__ float pen[BEAM_MAX_K];
   const int64_t b = blockIdx.y;
   const int64_t total = k * V;
@@ -100,26 +145,19 @@ beam_local_topk_kernel(const float* __restrict__ logprobs, const float* __restri
       sc[it] = -INFINITY;
     }
   }
-  uint32_t taken = 0;  // bit it: candidate `it` of this thread already emitted
-  for (int r = 0; r < k; ++r) {
-    Cand best{-INFINITY, 0x7fffffff};  // index 0x7fffffff = "no candidate left in this chunk"
+  int32_t ix[BEAM_ITEMS];
 #pragma unroll
-    for (int it = 0; it < BEAM_ITEMS; ++it) {
-      const int64_t flat = base + it * BEAM_THREADS + threadIdx.x;
-      if (flat < total && !((taken >> it) & 1u) && cand_better(sc[it], (int32_t)flat, best.s, best.i)) {
-        best.s = sc[it];
-        best.i = (int32_t)flat;
-      }
-    }
-    const Cand win = block_best_cand(best, sm_s, sm_i);
-#pragma unroll
-    for (int it = 0; it < BEAM_ITEMS; ++it)
-      if (base + it * BEAM_THREADS + threadIdx.x == (int64_t)win.i) taken |= (1u << it);
-    if (threadIdx.x == 0) {
-      const int64_t o = (b * gridDim.x + blockIdx.x) * k + r;
-      cand_s[o] = win.s;
-      cand_i[o] = win.i;
-    }
+  for (int it = 0; it < BEAM_ITEMS; ++it) {
+    const int64_t flat = base + it * BEAM_THREADS + threadIdx.x;
+    ix[it] = flat < total ? (int32_t)flat : 0x7fffffff;   // 0x7fffffff = "no candidate here"
+  }
+  __shared__ float wk_s[(BEAM_THREADS / 32) * BEAM_MAX_K], out_s[BEAM_MAX_K];
+  __shared__ int32_t wk_i[(BEAM_THREADS / 32) * BEAM_MAX_K], out_i[BEAM_MAX_K];
+  cta_topk<BEAM_ITEMS>(sc, ix, (int)k, wk_s, wk_i, out_s, out_i);
+  for (int r = threadIdx.x; r < k; r += BEAM_THREADS) {
+    const int64_t o = (b * gridDim.x + blockIdx.x) * k + r;
+    cand_s[o] = out_s[r];
+    cand_i[o] = out_i[r];
   }
 }
 
@@ -135,38 +173,57 @@ beam_merge_kernel(const float* __restrict__ cand_s, const int32_t* __restrict__ 
                   int64_t V) {
   __shared__ float sm_s[32];
   __shared__ int32_t sm_i[32];
+  __shared__ float wk_s[(BEAM_THREADS / 32) * BEAM_MAX_K], out_s[BEAM_MAX_K];
+  __shared__ int32_t wk_i[(BEAM_THREADS / 32) * BEAM_MAX_K], out_i[BEAM_MAX_K];
   const int64_t b = blockIdx.x;
   const int64_t n = chunks * k;
   const float* cs = cand_s + b * n;
   const int32_t* ci = cand_i + b * n;
-  int32_t last_i = -1;
-  float last_s = INFINITY;
-  for (int r = 0; r < k; ++r) {
-    // best candidate strictly after (last_s, last_i) in the (score desc, index asc) order
-    Cand best{-INFINITY, 0x7fffffff};
-    for (int64_t c = threadIdx.x; c < n; c += BEAM_THREADS) {
-      const float s = cs[c];
-      const int32_t i = ci[c];
-      if (i == 0x7fffffff) continue;
-      const bool after = (r == 0) || s < last_s || (s == last_s && i > last_i);
-      if (after && cand_better(s, i, best.s, best.i)) { best.s = s; best.i = i; }
+  constexpr int MERGE_ITEMS = 8;
+  if (n <= (int64_t)BEAM_THREADS * MERGE_ITEMS) {
+    // the usual case (k = 8, V = 32k: 504 candidates): registers + warp shuffles, two block barriers
+    float sc[MERGE_ITEMS];
+    int32_t ix[MERGE_ITEMS];
+#pragma unroll
+    for (int it = 0; it < MERGE_ITEMS; ++it) {
+      const int64_t c = (int64_t)it * BEAM_THREADS + threadIdx.x;
+      sc[it] = c < n ? cs[c] : -INFINITY;
+      ix[it] = c < n ? ci[c] : 0x7fffffff;
     }
-    const Cand win = block_best_cand(best, sm_s, sm_i);
-    last_s = win.s;
-    last_i = win.i;
-    if (threadIdx.x == 0) {
-      const int64_t o = b * k + r;
-      const int32_t flat = win.i;
-      const int64_t j = flat / V, w = flat - j * V;
-      scores[o] = win.s;
-      word_ids[o] = w;
-      beam_ids[o] = (int32_t)j;
-      logprob_sum_out[o] = cand_hyp(logprobs, lse, logprob_sum, finished, b, k, V, flat);
-      const int32_t fin = finished[b * k + j] ? 1 : 0;
-      lengths_out[o] = lengths[b * k + j] + 1 - fin;
-      finished_out[o] = (fin || w == 2) ? 1 : 0;  // END_TOKEN_INDEX = 2
-      if (unfinished && !(fin || w == 2)) atomicAdd(unfinished, 1);
+    cta_topk<MERGE_ITEMS>(sc, ix, (int)k, wk_s, wk_i, out_s, out_i);
+  } else {
+    int32_t last_i = -1;
+    float last_s = INFINITY;
+    for (int r = 0; r < k; ++r) {
+      // best candidate strictly after (last_s, last_i) in the (score desc, index asc) order
+      Cand best{-INFINITY, 0x7fffffff};
+      for (int64_t c = threadIdx.x; c < n; c += BEAM_THREADS) {
+        const float s = cs[c];
+        const int32_t i = ci[c];
+        if (i == 0x7fffffff) continue;
+        const bool after = (r == 0) || s < last_s || (s == last_s && i > last_i);
+        if (after && cand_better(s, i, best.s, best.i)) { best.s = s; best.i = i; }
+      }
+      const Cand win = block_best_cand(best, sm_s, sm_i);
+      last_s = win.s;
+      last_i = win.i;
+      if (threadIdx.x == 0) { out_s[r] = win.s; out_i[r] = win.i; }
     }
+    __syncthreads();
+  }
+  // bookkeeping of the k winners, one thread each
+  for (int r = threadIdx.x; r < k; r += BEAM_THREADS) {
+    const int64_t o = b * k + r;
+    const int32_t flat = out_i[r];
+    const int64_t j = flat / V, w = flat - j * V;
+    scores[o] = out_s[r];
+    word_ids[o] = w;
+    beam_ids[o] = (int32_t)j;
+    logprob_sum_out[o] = cand_hyp(logprobs, lse, logprob_sum, finished, b, k, V, flat);
+    const int32_t fin = finished[b * k + j] ? 1 : 0;
+    lengths_out[o] = lengths[b * k + j] + 1 - fin;
+    finished_out[o] = (fin || w == 2) ? 1 : 0;  // END_TOKEN_INDEX = 2
+    if (unfinished && !(fin || w == 2)) atomicAdd(unfinished, 1);
   }
 }
 

@@ -114,8 +114,11 @@ struct DsSeg {
 // G-wide column groups (nA groups from column colA, nB groups from column colB); local columns are
 // range A first, then range B.  K = sum of the segment lengths, weight row of segment element i =
 // (start of the segment in the virtual K range) + i.
+// NOT inlined: the body is ~10 KB of unrolled FMAs and the kernel calls it four times; inlined copies
+// made the kernel 300 KB of code that every CTA executes exactly once - an instruction-fetch-bound kernel
+// (the first GPU run: 135 us per step at batch 256, against ~40 us of modelled work).
 template <int G>
-__device__ __forceinline__ void ds_panel(const DsSeg* segs, int nseg, int K, const float* __restrict__ W,
+__device__ __noinline__ void ds_panel(const DsSeg* segs, int nseg, int K, const float* __restrict__ W,
                                          int ldw, int colA, int nA, int colB, int nB,
                                          float* __restrict__ res, int res_ld, float* __restrict__ red) {
   const int ng = nA + nB;
@@ -236,6 +239,13 @@ __device__ __forceinline__ void ds_slice(int total, int cl, int rank, int& first
   count = min(total, first + per) - first;
 }
 
+// Attention schedule of one CTA: runs of owned rows that share an encoder row, each at most `jt` rows
+// (a thread of the context pass owns one (row, column group) pair).  Computed by thread 0 into shared memory.
+struct DsRuns {
+  int n;
+  int e[DS_R], first[DS_R], cnt[DS_R];
+};
+
 template <int G>
 __global__ void __launch_bounds__(DS_THREADS, 1) attn_decoder_step_kernel(const DecStep p) {
   constexpr bool TMA = (G == 4);
@@ -262,32 +272,21 @@ __global__ void __launch_bounds__(DS_THREADS, 1) attn_decoder_step_kernel(const 
   float* ring = smem + L.ring;
   const uint32_t bar0 = smem_u32(smem + L.bars);
   const int res_ld = L.res_ld;
+  __shared__ DsRuns runs;
 
-  // ---- attention schedule of this CTA: runs of owned rows that share an encoder row -------------
-  // (at most rpc runs; computed redundantly by every thread: a handful of integer operations)
   const int my0 = row0 + rank * rpc;                      // first global row this CTA attends for
   const int nmy = max(0, min(rpc, p.rows - my0));         // valid ones
   const int nk = TMA ? (p.Tx + p.tck - 1) / p.tck : 1;    // tiles per run: keys, then values
   const int nv = TMA ? (p.Tx + p.tcv - 1) / p.tcv : 1;
-  int nruns = 0;
-  {
-    int prev = -1;
-    for (int j = 0; j < nmy; ++j) {
-      const int e = (my0 + j) / p.group;
-      if (e != prev) { ++nruns; prev = e; }
-    }
-  }
-  const int ntiles = nruns * (nk + nv);
+  const int ncg = (p.C + G - 1) / G;                      // context column groups (host: <= DS_THREADS)
+  const int jt = min(DS_R, DS_THREADS / ncg);             // rows per run
 
-  // tile i of the schedule -> source address and size (TMA path only)
-  auto tile_src = [&](int i, const float*& src, uint32_t& bytes) {
+  // tile i of this CTA's schedule (run-major: the key tiles of a run, then its value tiles)
+  auto issue_tile = [&](int i) {   // one thread
     const int run = i / (nk + nv), j = i - run * (nk + nv);
-    int e = -1, seen = -1, prev = -1;
-    for (int q = 0; q < nmy; ++q) {
-      const int eq = (my0 + q) / p.group;
-      if (eq != prev) { ++seen; prev = eq; }
-      if (seen == run) { e = eq; break; }
-    }
+    const int e = runs.e[run];
+    const float* src;
+    uint32_t bytes;
     if (j < nk) {
       const int t0 = j * p.tck, nt = min(p.tck, p.Tx - t0);
       src = p.keys + ((int64_t)e * p.Tx + t0) * p.A;
@@ -297,51 +296,65 @@ __global__ void __launch_bounds__(DS_THREADS, 1) attn_decoder_step_kernel(const 
       src = p.values + ((int64_t)e * p.Tx + t0) * p.C;
       bytes = (uint32_t)(nt * p.C * 4);
     }
-  };
-  auto issue_tile = [&](int i) {   // one thread
-    const float* src;
-    uint32_t bytes;
-    tile_src(i, src, bytes);
     const int slot = i % DS_SLOTS;
     mbar_expect_tx(bar0 + 8u * slot, bytes);
     bulk_load_1d(smem_u32(ring + slot * p.slot_floats), src, bytes, bar0 + 8u * slot);
   };
 
-  if (TMA && tid == 0) {
-    for (int s = 0; s < DS_SLOTS; ++s) mbar_init(bar0 + 8u * s, 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-  }
-  __syncthreads();
-  if (TMA && tid == 0) {
-    const int first = min(ntiles, DS_SLOTS);
-    for (int i = 0; i < first; ++i) issue_tile(i);   // in flight while the GRU phases run
+  if (tid == 0) {
+    int n = 0, prev = -1;
+#pragma unroll 1
+    for (int j = 0; j < nmy; ++j) {
+      const int e = (my0 + j) / p.group;
+      if (e != prev || runs.cnt[n - 1] >= jt) {
+        runs.e[n] = e; runs.first[n] = j; runs.cnt[n] = 1;
+        ++n;
+        prev = e;
+      } else {
+        ++runs.cnt[n - 1];
+      }
+    }
+    runs.n = n;
+    if (TMA) {
+#pragma unroll 1
+      for (int s2 = 0; s2 < DS_SLOTS; ++s2) mbar_init(bar0 + 8u * s2, 1);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      const int first = min(n * (nk + nv), DS_SLOTS);
+#pragma unroll 1
+      for (int i = 0; i < first; ++i) issue_tile(i);   // in flight while the GRU phases run
+    }
   }
 
   // ---- phase 0: inputs of the 8 rows, transposed into shared memory -----------------------------
-  for (int idx = tid; idx < DS_R * p.E; idx += DS_THREADS) {
-    const int r = idx / p.E, k = idx - r * p.E;
+  // warp w loads row w % 8 (two warps per row): coalesced global reads, no integer divisions
+  {
+    const int r = warp & (DS_R - 1), half = warp / DS_R, nhalf = DS_WARPS / DS_R;
     const int grow = row0 + r;
-    float val = 0.f;
-    if (grow < p.rows) {
-      val = p.x_in ? p.x_in[(int64_t)grow * p.E + k] : p.table[(int64_t)p.symbols[grow] * p.E + k];
-      if (p.x_out && rank == 0) p.x_out[(int64_t)grow * p.E + k] = val;
-    }
-    xT[k * DS_R + r] = val;
-  }
-  for (int idx = tid; idx < DS_R * p.H; idx += DS_THREADS) {
-    const int r = idx / p.H, k = idx - r * p.H;
-    const int grow = row0 + r;
-    float val = 0.f;
-    if (grow < p.rows) {
+    const bool ok = grow < p.rows;
+    const float* xsrc = nullptr;
+    const float* hsrc = nullptr;
+    if (ok) {
+      xsrc = p.x_in ? p.x_in + (int64_t)grow * p.E : p.table + (int64_t)p.symbols[grow] * p.E;
       const int src = p.parent ? (grow / p.group) * p.group + p.parent[grow] : grow;
-      val = p.h_prev[(int64_t)src * p.H + k];
+      hsrc = p.h_prev + (int64_t)src * p.H;
     }
-    hT[k * DS_R + r] = val;
+#pragma unroll 1
+    for (int k = lane + 32 * half; k < p.E; k += 32 * nhalf) {
+      const float val = ok ? xsrc[k] : 0.f;
+      if (ok && p.x_out && rank == 0) p.x_out[(int64_t)grow * p.E + k] = val;
+      xT[k * DS_R + r] = val;
+    }
+#pragma unroll 1
+    for (int k = lane + 32 * half; k < p.H; k += 32 * nhalf) hT[k * DS_R + r] = ok ? hsrc[k] : 0.f;
   }
+#pragma unroll 1
   for (int a = tid; a < p.A; a += DS_THREADS) vs[a] = p.v[a];
   __syncthreads();
   cluster.sync();   // every CTA of the cluster has started: its shared memory may be written remotely
+
+  const int r_w = warp & (DS_R - 1), half_w = warp / DS_R;   // element-wise passes: warp -> (row, half)
+  constexpr int NHALF = DS_WARPS / DS_R;
 
   // ---- phase 1: gates of this CTA's hidden units -------------------------------------------------
   int uf, un;   // first unit group / number of unit groups
@@ -351,13 +364,14 @@ __global__ void __launch_bounds__(DS_THREADS, 1) attn_decoder_step_kernel(const 
   {
     const DsSeg segs[2] = {{xT, p.E}, {hT, p.H}};
     ds_panel<G>(segs, 2, p.E + p.H, p.Wg, 2 * p.H, u0, un, p.H + u0, un, res, res_ld, red);
-    for (int idx = tid; idx < DS_R * nu; idx += DS_THREADS) {
-      const int r = idx / nu, ul = idx - r * nu;
-      const int u = u0 + ul;
+#pragma unroll 1
+    for (int ul = lane + 32 * half_w; ul < nu; ul += 32 * NHALF) {
+      const int r = r_w, u = u0 + ul;
       const float rr = sigmoidf_(res[r * res_ld + ul] + p.bg[u]);
       const float uu = sigmoidf_(res[r * res_ld + un * G + ul] + p.bg[p.H + u]);
       ugs[r * nu + ul] = uu;
       const float rh = rr * hT[u * DS_R + r];
+#pragma unroll 1
       for (int c = 0; c < CL; ++c) cluster.map_shared_rank(rhT, c)[u * DS_R + r] = rh;
     }
   }
@@ -367,12 +381,13 @@ __global__ void __launch_bounds__(DS_THREADS, 1) attn_decoder_step_kernel(const 
   {
     const DsSeg segs[2] = {{xT, p.E}, {rhT, p.H}};
     ds_panel<G>(segs, 2, p.E + p.H, p.Wc, p.H, u0, un, 0, 0, res, res_ld, red);
-    for (int idx = tid; idx < DS_R * nu; idx += DS_THREADS) {
-      const int r = idx / nu, ul = idx - r * nu;
-      const int u = u0 + ul;
+#pragma unroll 1
+    for (int ul = lane + 32 * half_w; ul < nu; ul += 32 * NHALF) {
+      const int r = r_w, u = u0 + ul;
       const float c = tanhf(res[r * res_ld + ul] + p.bc[u]);
       const float uu = ugs[r * nu + ul];
       const float hn = uu * hT[u * DS_R + r] + (1.f - uu) * c;
+#pragma unroll 1
       for (int cc = 0; cc < CL; ++cc) cluster.map_shared_rank(hnT, cc)[u * DS_R + r] = hn;
       if (row0 + r < p.rows) p.h_out[(int64_t)(row0 + r) * p.H + u] = hn;
     }
@@ -387,25 +402,23 @@ __global__ void __launch_bounds__(DS_THREADS, 1) attn_decoder_step_kernel(const 
     const int na = min(p.A, a0 + an * G) - a0;
     const DsSeg segs[1] = {{hnT, p.H}};
     ds_panel<G>(segs, 1, p.H, p.Wq, p.A, a0, an, 0, 0, res, res_ld, red);
-    for (int idx = tid; idx < DS_R * na; idx += DS_THREADS) {
-      const int r = idx / na, al = idx - r * na;
-      const int a = a0 + al;
-      const float q = res[r * res_ld + al] + p.bq[a];
-      cluster.map_shared_rank(qs, r / rpc)[(r % rpc) * p.A + a] = q;
-    }
+    float* qdst = cluster.map_shared_rank(qs, r_w / rpc) + (r_w % rpc) * p.A;
+#pragma unroll 1
+    for (int al = lane + 32 * half_w; al < na; al += 32 * NHALF)
+      qdst[a0 + al] = res[r_w * res_ld + al] + p.bq[a0 + al];
   }
   cluster.sync();
 
   // ---- phase 4: attention for the rows this CTA owns ---------------------------------------------------
   {
     const float abias = p.abias[0];
+    const int ntiles = runs.n * (nk + nv);
     int tile = 0;          // position in the TMA schedule
-    int j0 = 0;            // first row (local to this CTA) of the current run
-    while (j0 < nmy) {
-      const int e = (my0 + j0) / p.group;
-      int cnt = 1;
-      while (j0 + cnt < nmy && (my0 + j0 + cnt) / p.group == e) ++cnt;
-      // energies: one warp per time step, lanes over A; the rows of the run share the key loads
+#pragma unroll 1
+    for (int run = 0; run < runs.n; ++run) {
+      const int e = runs.e[run], j0 = runs.first[run], cnt = runs.cnt[run];
+      // energies: one warp per (time step, row) pair, lanes over A
+#pragma unroll 1
       for (int kt = 0; kt < nk; ++kt) {
         const float* kc;
         int t0, nt;
@@ -419,41 +432,29 @@ __global__ void __launch_bounds__(DS_THREADS, 1) attn_decoder_step_kernel(const 
           t0 = 0;
           nt = p.Tx;
         }
-        for (int tl = warp; tl < nt; tl += DS_WARPS) {
-          float acc[DS_R];
-#pragma unroll
-          for (int j = 0; j < DS_R; ++j) acc[j] = 0.f;
+#pragma unroll 1
+        for (int it = warp; it < nt * cnt; it += DS_WARPS) {
+          const int tl = it / cnt, j = it - tl * cnt;
           const float* kr = kc + tl * p.A;
+          const float* qr = qs + (j0 + j) * p.A;
+          float acc = 0.f;
           if constexpr (G == 4) {
+#pragma unroll 1
             for (int a4 = lane; a4 < p.A / 4; a4 += 32) {
               const float4 k4 = *reinterpret_cast<const float4*>(kr + 4 * a4);
               const float4 v4 = *reinterpret_cast<const float4*>(vs + 4 * a4);
-#pragma unroll
-              for (int j = 0; j < DS_R; ++j) {
-                if (j < cnt) {
-                  const float4 q4 = *reinterpret_cast<const float4*>(qs + (j0 + j) * p.A + 4 * a4);
-                  acc[j] = fmaf(v4.x, ds_fast_tanh(k4.x + q4.x), acc[j]);
-                  acc[j] = fmaf(v4.y, ds_fast_tanh(k4.y + q4.y), acc[j]);
-                  acc[j] = fmaf(v4.z, ds_fast_tanh(k4.z + q4.z), acc[j]);
-                  acc[j] = fmaf(v4.w, ds_fast_tanh(k4.w + q4.w), acc[j]);
-                }
-              }
+              const float4 q4 = *reinterpret_cast<const float4*>(qr + 4 * a4);
+              acc = fmaf(v4.x, ds_fast_tanh(k4.x + q4.x), acc);
+              acc = fmaf(v4.y, ds_fast_tanh(k4.y + q4.y), acc);
+              acc = fmaf(v4.z, ds_fast_tanh(k4.z + q4.z), acc);
+              acc = fmaf(v4.w, ds_fast_tanh(k4.w + q4.w), acc);
             }
           } else {
-            for (int a = lane; a < p.A; a += 32) {
-              const float k = kr[a], vv = vs[a];
-#pragma unroll
-              for (int j = 0; j < DS_R; ++j)
-                if (j < cnt) acc[j] = fmaf(vv, ds_fast_tanh(k + qs[(j0 + j) * p.A + a]), acc[j]);
-            }
+#pragma unroll 1
+            for (int a = lane; a < p.A; a += 32) acc = fmaf(vs[a], ds_fast_tanh(kr[a] + qr[a]), acc);
           }
-#pragma unroll
-          for (int j = 0; j < DS_R; ++j) {
-            if (j < cnt) {
-              const float en = warp_sum(acc[j]) + abias;
-              if (lane == 0) es[(j0 + j) * p.Tx + t0 + tl] = en;
-            }
-          }
+          const float en = warp_sum(acc) + abias;
+          if (lane == 0) es[(j0 + j) * p.Tx + t0 + tl] = en;
         }
         __syncthreads();   // the tile is consumed (and, after the last one, the energies are complete)
         if (TMA) {
@@ -462,6 +463,7 @@ __global__ void __launch_bounds__(DS_THREADS, 1) attn_decoder_step_kernel(const 
         }
       }
       // softmax over ALL Tx, then mask and renormalise: one warp per row of the run
+#pragma unroll 1
       for (int j = warp; j < cnt; j += DS_WARPS) {
         float* er = es + (j0 + j) * p.Tx;
         const int64_t grow = my0 + j0 + j;
@@ -487,16 +489,13 @@ __global__ void __launch_bounds__(DS_THREADS, 1) attn_decoder_step_kernel(const 
           for (int t = lane; t < p.Tx; t += 32) p.w_out[grow * p.Tx + t] = er[t];
       }
       __syncthreads();
-      // context: thread = (column group, time sub-slice); partial sums stay in registers over the tiles
-      const int ncg = (p.C + G - 1) / G;          // host guarantees ncg <= DS_THREADS
-      const int nts = DS_THREADS / ncg;           // time sub-slices
-      const int cgi = tid % ncg, ts = tid / ncg;
-      const bool cact = ts < nts;
-      float cacc[DS_R][G];
+      // context: thread = (row of the run, column group), all time steps; the sum stays in registers
+      const int cj = tid / ncg, cgi = tid - cj * ncg;
+      const bool cact = cj < cnt;
+      float cacc[G];
 #pragma unroll
-      for (int j = 0; j < DS_R; ++j)
-#pragma unroll
-        for (int c = 0; c < G; ++c) cacc[j][c] = 0.f;
+      for (int c = 0; c < G; ++c) cacc[c] = 0.f;
+#pragma unroll 1
       for (int vt = 0; vt < nv; ++vt) {
         const float* vc;
         int t0, nt;
@@ -511,21 +510,16 @@ __global__ void __launch_bounds__(DS_THREADS, 1) attn_decoder_step_kernel(const 
           nt = p.Tx;
         }
         if (cact) {
-          for (int tl = ts; tl < nt; tl += nts) {
-            float val[G];
+          const float* wr = es + (j0 + cj) * p.Tx + t0;
+#pragma unroll 2
+          for (int tl = 0; tl < nt; ++tl) {
+            const float wt = wr[tl];
             if constexpr (G == 4) {
               const float4 t4 = *reinterpret_cast<const float4*>(vc + tl * p.C + 4 * cgi);
-              val[0] = t4.x; val[1] = t4.y; val[2] = t4.z; val[3] = t4.w;
+              cacc[0] = fmaf(wt, t4.x, cacc[0]); cacc[1] = fmaf(wt, t4.y, cacc[1]);
+              cacc[2] = fmaf(wt, t4.z, cacc[2]); cacc[3] = fmaf(wt, t4.w, cacc[3]);
             } else {
-              val[0] = vc[tl * p.C + cgi];
-            }
-#pragma unroll
-            for (int j = 0; j < DS_R; ++j) {
-              if (j < cnt) {
-                const float wt = es[(j0 + j) * p.Tx + t0 + tl];
-#pragma unroll
-                for (int c = 0; c < G; ++c) cacc[j][c] = fmaf(wt, val[c], cacc[j][c]);
-              }
+              cacc[0] = fmaf(wt, vc[tl * p.C + cgi], cacc[0]);
             }
           }
         }
@@ -535,33 +529,27 @@ __global__ void __launch_bounds__(DS_THREADS, 1) attn_decoder_step_kernel(const 
           ++tile;
         }
       }
-      // reduce the time sub-slices row by row (fixed order), broadcast the context to the cluster
+      if (cact) {   // broadcast the context of (row, column group) to the cluster
+        const int rl = rank * rpc + j0 + cj;               // row index inside the cluster
 #pragma unroll
-      for (int j = 0; j < DS_R; ++j) {
-        if (j < cnt) {      // uniform across the CTA
-          if (cact) {
-#pragma unroll
-            for (int c = 0; c < G; ++c) red[(ts * ncg + cgi) * G + c] = cacc[j][c];
+        for (int c = 0; c < G; ++c) {
+          const int col = cgi * G + c;
+          if (col < p.C) {
+#pragma unroll 1
+            for (int cc = 0; cc < CL; ++cc) cluster.map_shared_rank(ctxT, cc)[col * DS_R + rl] = cacc[c];
+            if (p.ctx_out) p.ctx_out[(int64_t)(my0 + j0 + cj) * p.C + col] = cacc[c];
           }
-          __syncthreads();
-          for (int col = tid; col < p.C; col += DS_THREADS) {
-            const int g2 = col / G, c = col - g2 * G;
-            float sum = 0.f;
-            for (int s2 = 0; s2 < nts; ++s2) sum += red[(s2 * ncg + g2) * G + c];
-            const int rl = rank * rpc + j0 + j;          // row index inside the cluster
-            for (int cc = 0; cc < CL; ++cc) cluster.map_shared_rank(ctxT, cc)[col * DS_R + rl] = sum;
-            if (p.ctx_out) p.ctx_out[(int64_t)(my0 + j0 + j) * p.C + col] = sum;
-          }
-          __syncthreads();
         }
       }
-      j0 += cnt;
     }
     // rows beyond `rows` (tail cluster): their context columns must be defined for the last product
-    for (int idx = tid; idx < (rpc - nmy) * p.C; idx += DS_THREADS) {
-      const int jj = nmy + idx / p.C, col = idx % p.C;
+#pragma unroll 1
+    for (int jj = nmy; jj < rpc; ++jj) {
       const int rl = rank * rpc + jj;
-      for (int cc = 0; cc < CL; ++cc) cluster.map_shared_rank(ctxT, cc)[col * DS_R + rl] = 0.f;
+#pragma unroll 1
+      for (int col = tid; col < p.C; col += DS_THREADS)
+#pragma unroll 1
+        for (int cc = 0; cc < CL; ++cc) cluster.map_shared_rank(ctxT, cc)[col * DS_R + rl] = 0.f;
     }
   }
   cluster.sync();
@@ -575,18 +563,19 @@ __global__ void __launch_bounds__(DS_THREADS, 1) attn_decoder_step_kernel(const 
     const DsSeg segs[3] = {{hnT, p.H}, {xT, p.E}, {ctxT, p.C}};
     const int ldo = (p.maxout ? 2 : 1) * p.O;
     ds_panel<G>(segs, 3, p.H + p.E + p.C, p.Wo, ldo, o0, on, p.O + o0, p.maxout ? on : 0, res, res_ld, red);
-    for (int idx = tid; idx < DS_R * no; idx += DS_THREADS) {
-      const int r = idx / no, ol = idx - r * no;
-      const int o = o0 + ol;
-      if (row0 + r >= p.rows) continue;
-      float y = res[r * res_ld + ol] + p.bo[o];
-      if (p.maxout) {
-        const float y2 = res[r * res_ld + on * G + ol] + p.bo[p.O + o];
-        y = fmaxf(y, y2);
-      } else {
-        y = apply_act(y, p.act);
+    if (row0 + r_w < p.rows) {
+#pragma unroll 1
+      for (int ol = lane + 32 * half_w; ol < no; ol += 32 * NHALF) {
+        const int o = o0 + ol;
+        float y = res[r_w * res_ld + ol] + p.bo[o];
+        if (p.maxout) {
+          const float y2 = res[r_w * res_ld + on * G + ol] + p.bo[p.O + o];
+          y = fmaxf(y, y2);
+        } else {
+          y = apply_act(y, p.act);
+        }
+        p.out[(int64_t)(row0 + r_w) * p.O + o] = y;
       }
-      p.out[(int64_t)(row0 + r) * p.O + o] = y;
     }
   }
 }

@@ -9,7 +9,7 @@ into the recurrence (decoder.py:264-277,288-297), so
 and the base class adds the fused vocabulary projection + loss.  The runtime (greedy / beam)
 path steps through `next_state`, using the same kernels with T = 1.
 
-Variants (behind NMB200_UNVERIFIED - see nn/variants.py): with `conditional_gru`
+Variants (see nn/variants.py; GPU-verified by tests/test_gpu_variants.py): with `conditional_gru`
 or `rnn_cell="NematusGRU"` the context feeds the recurrence, so training steps through time with the
 same `_variant_step` the runtime uses (teacher-forced inputs), one set of T = 1 launches per step.
 """

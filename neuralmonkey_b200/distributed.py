@@ -43,6 +43,15 @@ def all_reduce_sum(buf: torch.Tensor) -> None:
         dist.all_reduce(buf, op=dist.ReduceOp.SUM)
 
 
+def all_reduce_async(buf: torch.Tensor):
+    """Start an in-place sum over ranks and return its handle (None for one rank).  On NCCL the collective
+    runs on the process group's own stream, ordered after everything already issued on the current stream;
+    `handle.wait()` makes the current stream wait for it."""
+    if world_size() > 1:
+        return dist.all_reduce(buf, op=dist.ReduceOp.SUM, async_op=True)
+    return None
+
+
 def barrier() -> None:
     """All ranks wait here (no-op for one rank): e.g. before reading a checkpoint rank 0 has just written."""
     if world_size() > 1:

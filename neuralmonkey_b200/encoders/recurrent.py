@@ -4,7 +4,7 @@
 half of both GRUCell matmuls is one tensor-core GEMM over all B*T rows, the recurrence
 is the K2 sequence kernel (`ops.gru_layer`).  The GRU cell is the one the five target configs use;
 "NematusGRU" and "LSTM" (tests/small.ini, tests/nematus.ini) step through time with the cells of
-`nn/variants.py` behind the NMB200_UNVERIFIED switch.
+`nn/variants.py` (GPU-verified by tests/test_gpu_variants.py).
 """
 from typing import List, NamedTuple, Tuple, Union
 

@@ -39,6 +39,7 @@ class GenericTrainer(GraphExecutor, Feedable):
         # reports it as host_enqueue_ms_per_step) next to ~8 ms of GPU time.  Data parallel: two graphs
         # with the NCCL all-reduce between them.
         self.use_cuda_graph = use_cuda_graph
+        self.capture_exchange = True     # data parallel: NCCL inside the step's graph (falls back if capture fails)
         self._graphs = {}   # shape key -> "seen" | "failed" | captured step
         self.MAX_GRAPHS = 4
         Feedable.__init__(self)
@@ -81,11 +82,108 @@ class GenericTrainer(GraphExecutor, Feedable):
             self._excluded = [n for n in arena.train_names if n not in included]
         return self._scope_state
 
-    # -- one optimisation step ---------------------------------------------------------------
-    def _backward(self) -> Dict[str, torch.Tensor]:
-        """Backward of the weighted objectives into the arena; fills the stat slots.
-        Returns the device tensors reported as losses."""
+    # -- gradient exchange overlapped with the backward pass (K14) -------------------------------
+    def _exchange_plan(self):
+        """(encoder parts, early ranges, late ranges) of the flat gradient buffer.
+
+        The variables of the parts DOWNSTREAM of the encoders (decoders, attentions: on the en-de model
+        88 of 129 MB, on the Transformer 166 of 308 MB) have their final gradients as soon as the backward
+        pass reaches the encoders, long before it ends - their all-reduce can run on NCCL's stream while
+        the encoder is still being differentiated.  The buffer is sorted by variable name, so the
+        variables of a part are contiguous; adjacent segments are merged into ranges."""
+        if hasattr(self, "_plan"):
+            return self._plan
         arena = runtime.arena()
+        encoders, late_parts = [], set()
+        for obj in self.objectives:
+            for enc in getattr(obj.decoder, "encoders", None) or []:
+                if enc not in encoders:
+                    encoders.append(enc)
+                if hasattr(enc, "get_dependencies"):
+                    late_parts |= set(enc.get_dependencies()[1])
+        late_names = {getattr(p, "name", None) for p in late_parts}
+        early, late = [], []
+        offs = [int(o) for o in arena.seg_off.tolist()]
+        for i, name in enumerate(arena.train_names):
+            target = late if name.split("/", 1)[0] in late_names else early
+            lo, hi = offs[i], offs[i + 1]
+            if target and target[-1][1] == lo:
+                target[-1] = (target[-1][0], hi)
+            else:
+                target.append((lo, hi))
+        if not encoders or not late or not early:
+            early, late = [], [(0, arena.trainable_size)]
+        self._plan = (encoders, early, late)
+        return self._plan
+
+    def _arm_early_exchange(self, works: list):
+        """Evaluate the encoders first and hook their outputs: autograd runs the node with the highest
+        sequence number among the ready ones, and every node of the decoders is now younger than every
+        node of the encoders - so when the first gradient of an encoder output is complete, all decoder
+        and attention gradients are final.  That moment starts the all-reduce of their ranges (async: NCCL's
+        own stream, ordered after the kernels already issued; the backward pass goes on meanwhile)."""
+        arena = runtime.arena()
+        encoders, early, _late = self._exchange_plan()
+        if not early:
+            return
+        tensors = []
+        for enc in encoders:
+            for attr in ("temporal_states", "spatial_states", "output"):
+                try:
+                    val = getattr(enc, attr)
+                except (AttributeError, NotImplementedError, ValueError, TypeError):
+                    continue
+                if torch.is_tensor(val) and val.requires_grad and val.grad_fn is not None:
+                    tensors.append(val)
+        fired = []
+
+        def hook(_grad):
+            if not fired:
+                fired.append(True)
+                self.early_exchanges = getattr(self, "early_exchanges", 0) + 1
+                # parameters used in plain torch expressions get their gradient in `.grad` (AccumulateGrad
+                # nodes run before any older node): move those into the flat buffer before it is exchanged
+                arena.fold_autograd_grads()
+                for lo, hi in early:
+                    works.append(distributed.all_reduce_async(arena.grad_buffer[lo:hi]))
+            return None
+
+        for t in tensors:
+            t.register_hook(hook)
+        works.append(("armed", fired, early))
+
+    def _finish_exchange(self, works: list) -> None:
+        """All-reduce what the hook did not cover (the encoders' ranges and the statistic slots - or, when
+        it never fired, everything) and make the compute stream wait for the whole exchange."""
+        arena = runtime.arena()
+        _enc, early, late = self._exchange_plan()
+        armed = [w for w in works if isinstance(w, tuple)]
+        done_early = bool(armed and armed[0][1])
+        handles = [w for w in works if not isinstance(w, tuple)]
+        tail = arena.trainable_size
+        if done_early:
+            ranges = list(late)
+            if ranges and ranges[-1][1] == tail:
+                ranges[-1] = (ranges[-1][0], tail + arena.STAT_SLOTS)        # stats ride with the last range
+            else:
+                ranges.append((tail, tail + arena.STAT_SLOTS))
+            for lo, hi in ranges:
+                handles.append(distributed.all_reduce_async(arena.grad_buffer[lo:hi]))
+        else:
+            handles.append(distributed.all_reduce_async(arena.allreduce_view))
+        for h in handles:
+            if h is not None:
+                h.wait()
+        del works[:]
+
+    # -- one optimisation step ---------------------------------------------------------------
+    def _backward(self, works: Optional[list] = None) -> Dict[str, torch.Tensor]:
+        """Backward of the weighted objectives into the arena; fills the stat slots.
+        Returns the device tensors reported as losses.  `works` (data parallel): a list that receives
+        the handles of the gradient ranges whose all-reduce is started DURING the backward pass."""
+        arena = runtime.arena()
+        if works is not None:
+            self._arm_early_exchange(works)
         exact = None
         if len(self.objectives) == 1 and self.objectives[0].gradients is None:
             exact = self.objectives[0].loss_sum_and_count
@@ -141,9 +239,19 @@ class GenericTrainer(GraphExecutor, Feedable):
                 for p, st in zip(parts, static):
                     p.bind_static(st)
                 graph2 = None
-                if distributed.world_size() > 1:
-                    # data parallel: the gradient exchange stays an eager NCCL call between two
-                    # captured halves (backward | clip + Adam)
+                if distributed.world_size() > 1 and self.capture_exchange:
+                    # data parallel, everything in ONE graph: the ranges of the decoder side are
+                    # all-reduced on NCCL's stream while the encoder is still being differentiated
+                    # (the fork / join between the streams is captured as graph dependencies)
+                    with torch.cuda.graph(graph, capture_error_mode="thread_local"):
+                        arena.zero_grad()
+                        works = []
+                        self._backward(works)
+                        self._finish_exchange(works)
+                        self._adam_kernel(1.0, arena.stats[1:2], 0.0, self._lr_dev)
+                elif distributed.world_size() > 1:
+                    # the gradient exchange stays an eager NCCL call between two captured halves
+                    # (backward | clip + Adam)
                     with torch.cuda.graph(graph, capture_error_mode="thread_local"):
                         arena.zero_grad()
                         self._backward()
@@ -156,11 +264,17 @@ class GenericTrainer(GraphExecutor, Feedable):
                         self._backward()
                         self._adam_kernel(1.0, arena.stats[1:2], 0.0, self._lr_dev)
             except Exception as exc:  # pylint: disable=broad-except
+                for p in parts:
+                    p.reset_batch()
+                if distributed.world_size() > 1 and self.capture_exchange:
+                    warn("capturing the gradient exchange inside the step's CUDA graph failed ({}: {}); "
+                         "falling back to two graphs around an eager all-reduce".format(type(exc).__name__, exc))
+                    self.capture_exchange = False
+                    torch.cuda.synchronize()
+                    return None                     # this batch runs eagerly, the next one re-captures
                 warn("CUDA-graph capture of the training step failed ({}: {}); staying eager".format(
                     type(exc).__name__, exc))
                 self._graphs[key] = "failed"
-                for p in parts:
-                    p.reset_batch()
                 return None
             entry = self._graphs[key] = (graph, static, graph2)
         graph, static, graph2 = entry
@@ -190,20 +304,38 @@ class GenericTrainer(GraphExecutor, Feedable):
                 return out
         if zero_grad:
             arena.zero_grad()
-        info = self._backward()
+        world = distributed.world_size()
+        works = [] if (world > 1 and apply_update) else None
+        info = self._backward(works)
         losses = [obj.loss.detach() for obj in self.objectives]
         denominator = None
-        world = distributed.world_size()
         if apply_update:
+            if world > 1:
+                timed = arena.params.is_cuda
+                if timed:   # how long the compute stream waits for the exchange AFTER the backward pass
+                    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    ev0.record()
+                self._finish_exchange(works)
+                if timed:
+                    ev1.record()
+                    self._comm_events = (ev0, ev1)
             if info["exact"]:
-                distributed.all_reduce_sum(arena.allreduce_view)
                 denominator = arena.stats[1:2]
                 losses = [arena.stats[0] / arena.stats[1]]
             elif world > 1:
-                distributed.all_reduce_sum(arena.allreduce_view)
                 grad_scale = grad_scale / world
             self.apply_gradients(grad_scale, denominator)
         return {"losses": losses, "l1l2": self._l1l2}
+
+    @property
+    def last_exposed_comm_ms(self) -> Optional[float]:
+        """Device time between the end of the backward pass and the end of the gradient exchange in the last
+        EAGERLY issued data-parallel step (None otherwise): the communication the overlap did not hide."""
+        events = getattr(self, "_comm_events", None)
+        if events is None:
+            return None
+        events[1].synchronize()
+        return float(events[0].elapsed_time(events[1]))
 
     def apply_gradients(self, grad_scale: float = 1.0,
                         denominator: Optional[torch.Tensor] = None) -> None:

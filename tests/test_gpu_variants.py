@@ -1,15 +1,8 @@
 """The step-wise model variants (Nematus GRU cell, conditional GRU, nematus / mlp
 deep outputs, nematus initial state) on the GPU against the oracle.
 
-These variants are compositions of GPU-verified operations that have themselves not been run on a GPU
-yet (nn/variants.py), so both the product and this file sit behind NMB200_UNVERIFIED=1:
-
-    NMB200_UNVERIFIED=1 python -m pytest tests/test_gpu_variants.py -m gpu -q
-
-Their host logic is already checked on the CPU over stand-in operations
+Their host logic is also checked on the CPU over stand-in operations
 (tests/test_host_model_cpu.py::test_decoder_and_encoder_variants)."""
-import os
-
 import pytest
 import torch
 
@@ -17,9 +10,7 @@ from oracle import nm_oracle as O
 from tests.helpers import feed, max_abs, oracle_params_for, random_batch
 from tests.test_host_model_cpu import _build_variant, check_label_smoothing, check_multi_source
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("NMB200_UNVERIFIED") != "1",
-                                 reason="variants not yet verified on a GPU; set NMB200_UNVERIFIED=1")]
+pytestmark = pytest.mark.gpu
 
 
 @pytest.mark.parametrize("backend,tol", [("simt", 5e-5), ("auto", 1e-2)])

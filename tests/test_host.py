@@ -216,6 +216,11 @@ for step in range(3):
         src, tgt = src[lo:hi], tgt[lo:hi]
     feed(model, src, tgt, train=True)
     losses.append(float(model["trainer"].train_step()["losses"][0]))
+if world > 1:
+    # the decoder-side ranges were exchanged from inside the backward pass, in every step
+    assert getattr(model["trainer"], "early_exchanges", 0) == 3, getattr(model["trainer"], "early_exchanges", 0)
+    _enc, early, late = model["trainer"]._exchange_plan()
+    assert early and late and sum(hi - lo for lo, hi in early + late) == model["arena"].trainable_size
 if distributed.rank() == 0:
     torch.save({{"params": model["arena"].state_dict(), "losses": losses}}, {out!r} + str(world))
 print("rank", distributed.rank(), "done")
