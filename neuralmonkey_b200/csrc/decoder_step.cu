@@ -652,13 +652,15 @@ int nm_attn_decoder_step_fwd(const int64_t* symbols, const float* emb_table, con
     p.slot_floats = 0; p.tck = (int)Tx; p.tcv = (int)Tx;
     smem_bytes = sizeof(float) * (size_t)ds_layout(p, false).total;
   }
-  NM_REQUIRE(smem_bytes <= 227 * 1024, NM_E_UNSUPPORTED,
+  // 227 KB per CTA minus the kernel's static shared memory (the run table), rounded up to 1 KB
+  constexpr int DS_MAX_DYN_SMEM = 227 * 1024 - 1024;
+  NM_REQUIRE(smem_bytes <= (size_t)DS_MAX_DYN_SMEM, NM_E_UNSUPPORTED,
              "nm_attn_decoder_step_fwd: needs %zu bytes of shared memory", smem_bytes);
 
   auto kern = vec ? attn_decoder_step_kernel<4> : attn_decoder_step_kernel<1>;
   static bool attr_done[2] = {false, false};
   if (!attr_done[vec ? 1 : 0]) {
-    NM_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    NM_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, DS_MAX_DYN_SMEM));
     attr_done[vec ? 1 : 0] = true;
   }
   cudaLaunchConfig_t cfg{};

@@ -111,7 +111,8 @@ class Experiment:
             if os.path.exists(self.get_path("variables.data.best")):
                 self.model.tf_manager.restore_best_vars()
             for test_id, dataset in enumerate(self.model.test_datasets):
-                self.evaluate(dataset, write_out=True, name="test_{}".format(test_id))
+                # every rank evaluates (the replicas are identical); rank 0 alone writes the output files
+                self.evaluate(dataset, write_out=main, name="test_{}".format(test_id))
         log("Finished.")
         self._vars_loaded = True
 

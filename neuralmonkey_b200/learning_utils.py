@@ -100,6 +100,8 @@ def training_loop(cfg: Namespace) -> None:
                             score = val_eval[cfg.main_metric]
                             if distributed.rank() == 0:
                                 cfg.tf_manager.validation_hook(score, epoch_n, batch_n)
+                            if hasattr(cfg.tf_manager, "sync_validation_state"):
+                                cfg.tf_manager.sync_validation_state()
                             log("best {} on validation: {:.4g} (in epoch {}, after batch number {})"
                                 .format(cfg.main_metric, cfg.tf_manager.best_score,
                                         cfg.tf_manager.best_score_epoch,

@@ -8,6 +8,7 @@ from neuralmonkey_b200.params import ParameterArena
 
 _device = None  # type: Optional[torch.device]
 _arena = None  # type: Optional[ParameterArena]
+_global_step = 0   # tf.train.get_or_create_global_step(): ONE counter shared by every trainer of the experiment
 
 
 def device() -> torch.device:
@@ -32,9 +33,21 @@ def arena() -> ParameterArena:
 
 
 def reset() -> None:
-    """Start a fresh experiment (new arena)."""
-    global _arena
+    """Start a fresh experiment (new arena, global step 0)."""
+    global _arena, _global_step
     _arena = None
+    _global_step = 0
+
+
+def global_step() -> int:
+    """The experiment's global step (reference: generic_trainer.py:193-195 - every trainer's train_op
+    increments the same tf global_step variable, which the learning-rate schedules read and the Saver stores)."""
+    return _global_step
+
+
+def set_global_step(value: int) -> None:
+    global _global_step
+    _global_step = int(value)
 
 
 def to_device(host: torch.Tensor) -> torch.Tensor:

@@ -149,7 +149,8 @@ class TensorFlowManager:
         for index, path in enumerate(variable_files):
             self.activate_session(index)
             torch.save({"variables": arena.state_dict(), "adam_m": arena.moment_dict(arena.adam_m),
-                        "adam_v": arena.moment_dict(arena.adam_v)}, path)
+                        "adam_v": arena.moment_dict(arena.adam_v),
+                        "global_step": runtime.global_step()}, path)   # the Saver stores it too
 
     def restore(self, variable_files: Union[str, List[str]]) -> None:
         if isinstance(variable_files, str):
@@ -167,6 +168,25 @@ class TensorFlowManager:
             elif isinstance(ckpt.get("adam_m"), dict):   # optimizer moments, keyed by variable name
                 arena.load_moments(arena.adam_m, ckpt["adam_m"])
                 arena.load_moments(arena.adam_v, ckpt["adam_v"])
+                # warm moments need the step they belong to: bias correction and lr schedules resume
+                runtime.set_global_step(int(ckpt.get("global_step", 0)))
+
+    def sync_validation_state(self) -> None:
+        """Data parallel: rank 0 alone runs validation_hook (it owns the checkpoint files); the other ranks
+        take over its bookkeeping, so that `best_score*` in their logs and - what matters -
+        restore_best_vars() on them pick the same checkpoint."""
+        from neuralmonkey_b200 import distributed
+        if distributed.world_size() <= 1:
+            return
+        import torch.distributed as dist
+        state = [None]
+        if distributed.rank() == 0:
+            state = [(self.best_score_index, self.best_score_epoch, getattr(self, "best_score_batch", 0),
+                      list(self.saved_scores))]
+        dist.broadcast_object_list(state, src=0)
+        index, epoch, batch, scores = state[0]
+        self.best_score_index, self.best_score_epoch, self.best_score_batch = index, epoch, batch
+        self.saved_scores = list(scores)
 
     def restore_best_vars(self) -> None:
         self.restore(self.variables_files[self.best_score_index])

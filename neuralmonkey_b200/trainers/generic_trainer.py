@@ -50,10 +50,19 @@ class GenericTrainer(GraphExecutor, Feedable):
         self.var_scopes = var_scopes
         self.var_collection = var_collection
         self.optimizer = optimizer if optimizer is not None else self.default_optimizer()
-        self.global_step = 0
         self.batches_per_update = 1
         if clip_norm is not None and clip_norm <= 0.0:
             raise ValueError("clip_norm must be positive")
+
+    @property
+    def global_step(self) -> int:
+        """Shared by all trainers (several trainers alternate on one model in tests/bahdanau.ini): bias
+        correction and learning-rate schedules follow the number of updates of the MODEL."""
+        return runtime.global_step()
+
+    @global_step.setter
+    def global_step(self, value: int) -> None:
+        runtime.set_global_step(value)
 
     @property
     def var_list(self) -> List[str]:
