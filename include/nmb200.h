@@ -156,6 +156,23 @@ int nm_gru_seq_bwd(const float* Wgh, const float* Wch, const int32_t* lengths,
                    const float* dfinal, float* dxproj, float* dh0, float* work,
                    int64_t B, int64_t T, int64_t H, int sm_budget, void* stream);
 
+/* Both directions of a bidirectional layer (tf.nn.bidirectional_dynamic_rnn, encoders/recurrent.py:82-95)
+ * in ONE launch of the tensor-core engine: the clusters of sequence a and of sequence b are co-resident
+ * (each direction alone fills only half of the chip for the length of the sentence).  Same arguments as
+ * nm_gru_seq_fwd / nm_gru_seq_bwd per sequence, without h0 / drop_mask / raw_states (encoder layers have
+ * none); `lengths` is shared.  Falls back to two launches where the tensor-core engine does not apply. */
+int nm_gru_seq_fwd_pair(const float* xproj_a, const float* Wgh_a, const float* Wch_a, int reverse_a,
+                        float* states_a, float* final_a, float* gates_a, float* hprev_a, float* rh_a,
+                        const float* xproj_b, const float* Wgh_b, const float* Wch_b, int reverse_b,
+                        float* states_b, float* final_b, float* gates_b, float* hprev_b, float* rh_b,
+                        const int32_t* lengths, int64_t B, int64_t T, int64_t H, void* stream);
+int nm_gru_seq_bwd_pair(const float* Wgh_a, const float* Wch_a, int reverse_a, const float* gates_a,
+                        const float* hprev_a, const float* dstates_a, const float* dfinal_a,
+                        float* dxproj_a, const float* Wgh_b, const float* Wch_b, int reverse_b,
+                        const float* gates_b, const float* hprev_b, const float* dstates_b,
+                        const float* dfinal_b, float* dxproj_b, const int32_t* lengths, float* work,
+                        int64_t B, int64_t T, int64_t H, void* stream);
+
 /* ---- K4: Bahdanau attention -------------------------------------------------
  * Replaces Attention.attention (attention/feed_forward.py:125-166) for NQ query
  * steps at once (NQ = Ty in teacher-forced training, 1 in step-wise decoding):

@@ -119,28 +119,49 @@ __device__ __forceinline__ float cand_hyp(const float* __restrict__ logprobs, co
 }
 
 // phase 1: grid (chunks, B).  cand_s/cand_i: [B, chunks, k]
+// The per-hypothesis quantities (finished flag, logsumexp, log-prob sum, length penalty) sit in shared
+// memory; a candidate's address is b*k*V + flat, and its hypothesis index needs no 64-bit division: the
+// 4096 candidates of a chunk span at most two hypotheses when V >= 4096 (32-bit division otherwise).
 __global__ void __launch_bounds__(BEAM_THREADS)
 beam_local_topk_kernel(const float* __restrict__ logprobs, const float* __restrict__ lse,
                        const float* __restrict__ logprob_sum,
                        const int32_t* __restrict__ lengths, const uint8_t* __restrict__ finished,
                        float alpha, float* __restrict__ cand_s, int32_t* __restrict__ cand_i,
                        int64_t k, int64_t V) {
-  __shared__ float pen[BEAM_MAX_K];
+  __shared__ float pen[BEAM_MAX_K], s_lse[BEAM_MAX_K], s_lsum[BEAM_MAX_K];
+  __shared__ uint8_t s_fin[BEAM_MAX_K];
   const int64_t b = blockIdx.y;
   const int64_t total = k * V;
   if (threadIdx.x < k) {
     const int32_t fin = finished[b * k + threadIdx.x] ? 1 : 0;
     pen[threadIdx.x] = length_penalty(lengths[b * k + threadIdx.x] + 1 - fin, alpha);
+    s_fin[threadIdx.x] = (uint8_t)fin;
+    s_lse[threadIdx.x] = lse ? lse[b * k + threadIdx.x] : 0.f;
+    s_lsum[threadIdx.x] = logprob_sum[b * k + threadIdx.x];
   }
   __syncthreads();
   float sc[BEAM_ITEMS];
   const int64_t base = (int64_t)blockIdx.x * BEAM_CHUNK;
+  const float* __restrict__ row = logprobs + b * total;
+  const uint32_t v32 = (uint32_t)V;
+  const uint32_t j_first = (uint32_t)base / v32;                    // hypothesis of the chunk's first candidate
+  const uint32_t next_boundary = (j_first + 1u) * v32;
+  const bool two_hyps_at_most = V >= BEAM_CHUNK;
 #pragma unroll
   for (int it = 0; it < BEAM_ITEMS; ++it) {
     const int64_t flat = base + it * BEAM_THREADS + threadIdx.x;  // coalesced
     if (flat < total) {
-      const int64_t j = flat / V;
-      sc[it] = cand_hyp(logprobs, lse, logprob_sum, finished, b, k, V, (int32_t)flat) / pen[j];
+      const uint32_t f32 = (uint32_t)flat;
+      const uint32_t j = two_hyps_at_most ? (f32 >= next_boundary ? j_first + 1u : j_first) : f32 / v32;
+      const uint32_t w = f32 - j * v32;
+      float lp;
+      if (s_fin[j]) {
+        lp = (w == 0 ? 0.f : -BEAM_INF);
+      } else {
+        lp = row[flat];
+        if (lse) lp = lp - s_lse[j];
+      }
+      sc[it] = (s_lsum[j] + lp) / pen[j];        // the arithmetic of cand_hyp, operands from shared memory
     } else {
       sc[it] = -INFINITY;
     }

@@ -41,8 +41,7 @@ constexpr int DS_THREADS = 512;
 constexpr int DS_WARPS = DS_THREADS / 32;
 constexpr int DS_UNROLL = 8;     // weight rows in flight per thread
 constexpr int DS_SLOTS = 4;      // TMA ring depth
-constexpr int DS_RED_FLOATS = 352 * 32;   // K-split reduction scratch (see ds_panel)
-constexpr int DS_MAX_KSPLIT = 16;
+constexpr int DS_RED_FLOATS = 64 * 32;    // K-split scratch of ds_panel: <= 64 partial sums of 32 floats
 
 struct DecStep {
   int rows, E, H, A, C, Tx, O, group, act, maxout;
@@ -114,26 +113,42 @@ struct DsSeg {
 // G-wide column groups (nA groups from column colA, nB groups from column colB); local columns are
 // range A first, then range B.  K = sum of the segment lengths, weight row of segment element i =
 // (start of the segment in the virtual K range) + i.
-// NOT inlined: the body is ~10 KB of unrolled FMAs and the kernel calls it four times; inlined copies
-// made the kernel 300 KB of code that every CTA executes exactly once - an instruction-fetch-bound kernel
-// (the first GPU run: 135 us per step at batch 256, against ~40 us of modelled work).
+//
+// Thread mapping (the first version split K over threads of DIFFERENT warps and reduced through shared
+// memory behind three block barriers: ncu put 27 % of the kernel's samples on those barriers).  A warp owns
+// DS_GW adjacent column groups (64 contiguous bytes of every weight row: full sectors) times DS_KSL
+// k-slices; the k-slices of a group are lanes of ONE warp, so their partial sums meet in three shuffle rounds.
+// When the CTA has fewer group quads than warps, several warps share a quad (K split once more) and a
+// single barrier joins them.  NOT inlined: four call sites, ~10 KB of unrolled FMAs each.
+constexpr int DS_GW = 4;     // column groups per warp
+constexpr int DS_KSL = 8;    // k-slices per warp (DS_GW * DS_KSL = 32 lanes)
+
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+
 template <int G>
 __device__ __noinline__ void ds_panel(const DsSeg* segs, int nseg, int K, const float* __restrict__ W,
-                                         int ldw, int colA, int nA, int colB, int nB,
-                                         float* __restrict__ res, int res_ld, float* __restrict__ red) {
+                                      int ldw, int colA, int nA, int colB, int nB,
+                                      float* __restrict__ res, int res_ld, float* __restrict__ red) {
   const int ng = nA + nB;
   constexpr int RG = DS_R * G;
-  for (int gb = 0; gb < ng; gb += DS_THREADS) {
-    const int nb = min(DS_THREADS, ng - gb);
-    int ksplit = DS_THREADS / nb;
-    if (ksplit > DS_MAX_KSPLIT) ksplit = DS_MAX_KSPLIT;
-    if (ksplit > K) ksplit = K > 0 ? K : 1;
-    const int g = threadIdx.x % nb, ks = threadIdx.x / nb;
-    const bool active = ks < ksplit;
-    const int gg = gb + g;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int gl = lane % DS_GW, ksl = lane / DS_GW;
+  const int nquads = (ng + DS_GW - 1) / DS_GW;
+#pragma unroll 1
+  for (int qb = 0; qb < nquads; qb += DS_WARPS) {
+    const int nq = min(DS_WARPS, nquads - qb);
+    const int wsplit = DS_WARPS / nq;                 // warps sharing one quad (K split across them)
+    const int quad = warp % nq, ws = warp / nq;
+    const int gg = (qb + quad) * DS_GW + gl;          // this lane's column group
+    const bool active = ws < wsplit && gg < ng;
     const int col = gg < nA ? colA + gg * G : colB + (gg - nA) * G;
-    const int kper = (K + ksplit - 1) / ksplit;
-    const int k0 = ks * kper;
+    const int kslices = DS_KSL * wsplit;
+    const int kper = (K + kslices - 1) / kslices;
+    const int k0 = min(K, (ws * DS_KSL + ksl) * kper);
     const int k1 = min(K, k0 + kper);
     float acc[DS_R][G];
 #pragma unroll
@@ -142,14 +157,16 @@ __device__ __noinline__ void ds_panel(const DsSeg* segs, int nseg, int K, const 
       for (int c = 0; c < G; ++c) acc[r][c] = 0.f;
     if (active) {
       int start = 0;
+#pragma unroll 1
       for (int s = 0; s < nseg; ++s) {
         const int len = segs[s].len;
         const int lo = max(k0, start), hi = min(k1, start + len);
         if (lo < hi) {
           const float* wp = W + (int64_t)lo * ldw + col;
-          const float* ip = segs[s].inT + (lo - start) * DS_R;
+          uint32_t ip = smem_u32(segs[s].inT) + (uint32_t)(lo - start) * DS_R * 4u;
           // batches of DS_UNROLL weight rows: all loads of a batch are in flight together; the last,
           // partial batch is predicated instead of falling back to one dependent load per row
+#pragma unroll 1
           for (int k = lo; k < hi; k += DS_UNROLL) {
             float w[DS_UNROLL][G];
 #pragma unroll
@@ -169,8 +186,8 @@ __device__ __noinline__ void ds_panel(const DsSeg* segs, int nseg, int K, const 
 #pragma unroll
             for (int u = 0; u < DS_UNROLL; ++u) {
               if (k + u < hi) {
-                const float4 i0 = *reinterpret_cast<const float4*>(ip + u * DS_R);
-                const float4 i1 = *reinterpret_cast<const float4*>(ip + u * DS_R + 4);
+                const float4 i0 = lds128(ip + u * DS_R * 4);
+                const float4 i1 = lds128(ip + u * DS_R * 4 + 16);
                 const float in[DS_R] = {i0.x, i0.y, i0.z, i0.w, i1.x, i1.y, i1.z, i1.w};
 #pragma unroll
                 for (int r = 0; r < DS_R; ++r)
@@ -179,53 +196,47 @@ __device__ __noinline__ void ds_panel(const DsSeg* segs, int nseg, int K, const 
               }
             }
             wp += (int64_t)DS_UNROLL * ldw;
-            ip += DS_UNROLL * DS_R;
+            ip += DS_UNROLL * DS_R * 4;
           }
         }
         start += len;
       }
     }
-    if (ksplit == 1) {
-      if (active) {
+    // the k-slices of a column group are the lanes gl, gl + 4, ..., gl + 28 of this warp
+#pragma unroll
+    for (int off = DS_GW; off < 32; off <<= 1)
+#pragma unroll
+      for (int r = 0; r < DS_R; ++r)
+#pragma unroll
+        for (int c = 0; c < G; ++c) acc[r][c] += __shfl_xor_sync(0xffffffffu, acc[r][c], off);
+    if (wsplit == 1) {
+      if (active && ksl == 0) {
 #pragma unroll
         for (int r = 0; r < DS_R; ++r)
 #pragma unroll
           for (int c = 0; c < G; ++c) res[r * res_ld + gg * G + c] = acc[r][c];
       }
     } else {
-      // K-split reduction in a fixed order: upper half of the slices into the lower half, then the
-      // lower half through shared memory.  Element-major layout (slot fastest): conflict-free.
-      const int half = (ksplit + 1) >> 1;
-      const int S = half * nb;     // S * RG <= DS_RED_FLOATS for every (nb, ksplit) this loop can produce
-      if (active && ks >= half) {
-        const int slot = (ks - half) * nb + g;
+      // several warps per quad: one barrier joins their partial sums (fixed order: deterministic)
+      const int S = wsplit * nq * DS_GW;              // S * RG <= DS_RED_FLOATS (S <= 64)
+      if (ws < wsplit && ksl == 0) {
+        const int slot = ws * nq * DS_GW + quad * DS_GW + gl;
 #pragma unroll
         for (int r = 0; r < DS_R; ++r)
 #pragma unroll
           for (int c = 0; c < G; ++c) red[(r * G + c) * S + slot] = acc[r][c];
       }
       __syncthreads();
-      if (active && ks < half && ks + half < ksplit) {
-        const int slot = ks * nb + g;
-#pragma unroll
-        for (int r = 0; r < DS_R; ++r)
-#pragma unroll
-          for (int c = 0; c < G; ++c) acc[r][c] += red[(r * G + c) * S + slot];
-      }
-      __syncthreads();
-      if (active && ks < half) {
-        const int slot = ks * nb + g;
-#pragma unroll
-        for (int r = 0; r < DS_R; ++r)
-#pragma unroll
-          for (int c = 0; c < G; ++c) red[(r * G + c) * S + slot] = acc[r][c];
-      }
-      __syncthreads();
-      for (int idx = threadIdx.x; idx < nb * RG; idx += DS_THREADS) {
-        const int e = idx / nb, g2 = idx - e * nb;
-        float sum = 0.f;
-        for (int h = 0; h < half; ++h) sum += red[e * S + h * nb + g2];
-        res[(e / G) * res_ld + (gb + g2) * G + (e % G)] = sum;
+#pragma unroll 1
+      for (int idx = threadIdx.x; idx < nq * DS_GW * RG; idx += DS_THREADS) {
+        const int e = idx / (nq * DS_GW), g2 = idx - e * (nq * DS_GW);
+        const int gout = qb * DS_GW + g2;
+        if (gout < ng) {
+          float sum = 0.f;
+#pragma unroll 1
+          for (int h = 0; h < wsplit; ++h) sum += red[e * S + h * nq * DS_GW + g2];
+          res[(e / G) * res_ld + gout * G + (e % G)] = sum;
+        }
       }
     }
     __syncthreads();
@@ -327,9 +338,10 @@ __global__ void __launch_bounds__(DS_THREADS, 1) attn_decoder_step_kernel(const 
   }
 
   // ---- phase 0: inputs of the 8 rows, transposed into shared memory -----------------------------
-  // warp w loads row w % 8 (two warps per row): coalesced global reads, no integer divisions
+  // lane -> (row = lane & 7, k offset = lane >> 3): the stores walk shared memory linearly (no bank
+  // conflicts); the global side reads 16 contiguous bytes of each of the 8 rows per warp instruction
   {
-    const int r = warp & (DS_R - 1), half = warp / DS_R, nhalf = DS_WARPS / DS_R;
+    const int r = lane & (DS_R - 1);
     const int grow = row0 + r;
     const bool ok = grow < p.rows;
     const float* xsrc = nullptr;
@@ -340,13 +352,13 @@ __global__ void __launch_bounds__(DS_THREADS, 1) attn_decoder_step_kernel(const 
       hsrc = p.h_prev + (int64_t)src * p.H;
     }
 #pragma unroll 1
-    for (int k = lane + 32 * half; k < p.E; k += 32 * nhalf) {
+    for (int k = tid >> 3; k < p.E; k += DS_THREADS / DS_R) {
       const float val = ok ? xsrc[k] : 0.f;
       if (ok && p.x_out && rank == 0) p.x_out[(int64_t)grow * p.E + k] = val;
       xT[k * DS_R + r] = val;
     }
 #pragma unroll 1
-    for (int k = lane + 32 * half; k < p.H; k += 32 * nhalf) hT[k * DS_R + r] = ok ? hsrc[k] : 0.f;
+    for (int k = tid >> 3; k < p.H; k += DS_THREADS / DS_R) hT[k * DS_R + r] = ok ? hsrc[k] : 0.f;
   }
 #pragma unroll 1
   for (int a = tid; a < p.A; a += DS_THREADS) vs[a] = p.v[a];

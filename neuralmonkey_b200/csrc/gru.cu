@@ -281,11 +281,14 @@ TcPlan plan_tc(Kern kern, int64_t B, int64_t H, int sm_budget, int ntiles, int* 
   return p;
 }
 
+// One sequence (args2 == nullptr) or two co-resident ones: clusters [0, nclusters) work on `args`,
+// [nclusters, 2*nclusters) on `*args2`.
 template <class Args, class Kern>
-int launch_tc(Kern kern, const Args& args, const TcPlan& p, cudaStream_t s, const char* name) {
+int launch_tc(Kern kern, const Args& args, const TcPlan& p, cudaStream_t s, const char* name,
+              const Args* args2 = nullptr) {
   NM_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3((unsigned)(p.nclusters * GT_CLUSTER));
+  cfg.gridDim = dim3((unsigned)(p.nclusters * GT_CLUSTER * (args2 ? 2 : 1)));
   cfg.blockDim = dim3(GT_THREADS);
   cfg.dynamicSmemBytes = p.smem;
   cfg.stream = s;
@@ -296,7 +299,7 @@ int launch_tc(Kern kern, const Args& args, const TcPlan& p, cudaStream_t s, cons
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  NM_CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, args));
+  NM_CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, args, args2 ? *args2 : args, p.nclusters));
   NM_LAUNCH_CHECK(name);
   return NM_OK;
 }
@@ -426,6 +429,70 @@ int nm_gru_seq_bwd(const float* Wgh, const float* Wch, const int32_t* lengths,
   count_launches(3 * T - 1);
   NM_LAUNCH_CHECK("nm_gru_seq_bwd");
   return NM_OK;
+}
+
+
+/* ---- both directions of a bidirectional layer in ONE launch (tensor-core engine) ------------------ */
+int nm_gru_seq_fwd_pair(const float* xproj_a, const float* Wgh_a, const float* Wch_a, int reverse_a,
+                        float* states_a, float* final_a, float* gates_a, float* hprev_a, float* rh_a,
+                        const float* xproj_b, const float* Wgh_b, const float* Wch_b, int reverse_b,
+                        float* states_b, float* final_b, float* gates_b, float* hprev_b, float* rh_b,
+                        const int32_t* lengths, int64_t B, int64_t T, int64_t H, void* stream) {
+  NM_REQUIRE(xproj_a && Wgh_a && Wch_a && states_a && final_a && gates_a && hprev_a && rh_a && xproj_b &&
+                 Wgh_b && Wch_b && states_b && final_b && gates_b && hprev_b && rh_b,
+             NM_E_INVALID, "nm_gru_seq_fwd_pair: null pointer");
+  NM_REQUIRE(B > 0 && T > 0 && H > 0, NM_E_INVALID, "nm_gru_seq_fwd_pair: bad sizes");
+  if (tc_path_ok(H) && T * H < (1 << 24)) {
+    static int resident = 0;
+    plan_tc<2>(gru_seq_fwd_tc_kernel, B, H, 0, 2, &resident);                 // fills `resident`
+    const int half_budget = (resident / 2) * GT_CLUSTER;
+    if (half_budget >= GT_CLUSTER) {
+      const TcPlan p = plan_tc<2>(gru_seq_fwd_tc_kernel, B, H, half_budget, 2, &resident);
+      if (2 * p.nclusters <= resident) {                                        // both sequences co-resident
+        GtFwdArgs a{xproj_a, Wgh_a, Wch_a, nullptr, lengths, nullptr, states_a, nullptr, final_a, gates_a,
+                    hprev_a, rh_a, (int)B, (int)T, (int)H, p.Bc, reverse_a, nullptr};
+        GtFwdArgs b{xproj_b, Wgh_b, Wch_b, nullptr, lengths, nullptr, states_b, nullptr, final_b, gates_b,
+                    hprev_b, rh_b, (int)B, (int)T, (int)H, p.Bc, reverse_b, nullptr};
+        return launch_tc(gru_seq_fwd_tc_kernel, a, p, (cudaStream_t)stream, "nm_gru_seq_fwd_pair(tc)", &b);
+      }
+    }
+  }
+  int rc = nm_gru_seq_fwd(xproj_a, Wgh_a, Wch_a, nullptr, lengths, nullptr, reverse_a, states_a, nullptr, final_a,
+                          gates_a, hprev_a, rh_a, B, T, H, 0, stream);
+  if (rc) return rc;
+  return nm_gru_seq_fwd(xproj_b, Wgh_b, Wch_b, nullptr, lengths, nullptr, reverse_b, states_b, nullptr, final_b,
+                        gates_b, hprev_b, rh_b, B, T, H, 0, stream);
+}
+
+int nm_gru_seq_bwd_pair(const float* Wgh_a, const float* Wch_a, int reverse_a, const float* gates_a,
+                        const float* hprev_a, const float* dstates_a, const float* dfinal_a, float* dxproj_a,
+                        const float* Wgh_b, const float* Wch_b, int reverse_b, const float* gates_b,
+                        const float* hprev_b, const float* dstates_b, const float* dfinal_b, float* dxproj_b,
+                        const int32_t* lengths, float* work, int64_t B, int64_t T, int64_t H, void* stream) {
+  NM_REQUIRE(Wgh_a && Wch_a && gates_a && hprev_a && dxproj_a && Wgh_b && Wch_b && gates_b && hprev_b &&
+                 dxproj_b && work,
+             NM_E_INVALID, "nm_gru_seq_bwd_pair: null pointer");
+  NM_REQUIRE(B > 0 && T > 0 && H > 0, NM_E_INVALID, "nm_gru_seq_bwd_pair: bad sizes");
+  if (tc_path_ok(H) && T * H < (1 << 24)) {
+    static int resident = 0;
+    plan_tc<4>(gru_seq_bwd_tc_kernel, B, H, 0, 3, &resident);
+    const int half_budget = (resident / 2) * GT_CLUSTER;
+    if (half_budget >= GT_CLUSTER) {
+      const TcPlan p = plan_tc<4>(gru_seq_bwd_tc_kernel, B, H, half_budget, 3, &resident);
+      if (2 * p.nclusters <= resident) {
+        GtBwdArgs a{Wgh_a, Wch_a, lengths, nullptr, gates_a, hprev_a, dstates_a, nullptr, dfinal_a, dxproj_a,
+                    nullptr, (int)B, (int)T, (int)H, p.Bc, reverse_a};
+        GtBwdArgs b{Wgh_b, Wch_b, lengths, nullptr, gates_b, hprev_b, dstates_b, nullptr, dfinal_b, dxproj_b,
+                    nullptr, (int)B, (int)T, (int)H, p.Bc, reverse_b};
+        return launch_tc(gru_seq_bwd_tc_kernel, a, p, (cudaStream_t)stream, "nm_gru_seq_bwd_pair(tc)", &b);
+      }
+    }
+  }
+  int rc = nm_gru_seq_bwd(Wgh_a, Wch_a, lengths, nullptr, reverse_a, gates_a, hprev_a, dstates_a, nullptr, dfinal_a,
+                          dxproj_a, nullptr, work, B, T, H, 0, stream);
+  if (rc) return rc;
+  return nm_gru_seq_bwd(Wgh_b, Wch_b, lengths, nullptr, reverse_b, gates_b, hprev_b, dstates_b, nullptr, dfinal_b,
+                        dxproj_b, nullptr, work, B, T, H, 0, stream);
 }
 
 }  // extern "C"

@@ -227,7 +227,13 @@ __device__ __forceinline__ void gt_dump_acc(float* __restrict__ P, uint32_t tmem
   }
 }
 
-__global__ void __launch_bounds__(GT_THREADS, 1) gru_seq_fwd_tc_kernel(const GtFwdArgs a) {
+// Two independent sequences can share one launch (the fw and bw directions of a bidirectional layer:
+// clusters [0, split) work on a0, the rest on a1), so that both recurrences are co-resident instead
+// of running back to back on half-empty SMs.  A single sequence passes split = number of clusters.
+__global__ void __launch_bounds__(GT_THREADS, 1) gru_seq_fwd_tc_kernel(const GtFwdArgs a0, const GtFwdArgs a1,
+                                                                      const int split) {
+  const bool second_seq = (int)(blockIdx.x / GT_CLUSTER) >= split;
+  const GtFwdArgs a = second_seq ? a1 : a0;
   constexpr int ESZ = 2;   // fp16 operands
   extern __shared__ uint8_t gt_smem_raw[];
   const GtGeom<ESZ> geo(a.H);
@@ -245,7 +251,7 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gru_seq_fwd_tc_kernel(const GtF
   const int tid = threadIdx.x;
   const int m = tid & 127, half = tid >> 7;
   const int rank = (int)cluster_rank();
-  const int cluster_id = blockIdx.x / GT_CLUSTER;
+  const int cluster_id = (int)(blockIdx.x / GT_CLUSTER) - (second_seq ? split : 0);
   const int b0 = cluster_id * a.Bc;
   const int nb = min(a.Bc, a.B - b0);
   const int H = a.H, T = a.T, UPC = geo.UPC, KP = geo.KP, SBO = geo.SBO;
@@ -468,7 +474,10 @@ struct GtBwdArgs {
   int B, T, H, Bc, reverse;
 };
 
-__global__ void __launch_bounds__(GT_THREADS, 1) gru_seq_bwd_tc_kernel(const GtBwdArgs a) {
+__global__ void __launch_bounds__(GT_THREADS, 1) gru_seq_bwd_tc_kernel(const GtBwdArgs a0, const GtBwdArgs a1,
+                                                                      const int split) {
+  const bool second_seq = (int)(blockIdx.x / GT_CLUSTER) >= split;
+  const GtBwdArgs a = second_seq ? a1 : a0;
   constexpr int ESZ = 4;
   extern __shared__ uint8_t gt_smem_raw[];
   const GtGeom<ESZ> geo(a.H);
@@ -487,7 +496,7 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gru_seq_bwd_tc_kernel(const GtB
   const int tid = threadIdx.x;
   const int m = tid & 127, half = tid >> 7;
   const int rank = (int)cluster_rank();
-  const int cluster_id = blockIdx.x / GT_CLUSTER;
+  const int cluster_id = (int)(blockIdx.x / GT_CLUSTER) - (second_seq ? split : 0);
   const int b0 = cluster_id * a.Bc;
   const int nb = min(a.Bc, a.B - b0);
   const int H = a.H, T = a.T, UPC = geo.UPC, KP = geo.KP, SBO = geo.SBO;

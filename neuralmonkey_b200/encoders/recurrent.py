@@ -136,6 +136,11 @@ class RecurrentEncoder(ModelPart, TemporalStatefulWithOutput):
                                                        "backward": (True,)}[spec.direction])]
             return torch.cat([r[0] for r in runs], 2), torch.cat([r[1] for r in runs], 1)
         if spec.direction == "bidirectional":
+            if hasattr(ops, "gru_bilayer") and lengths is not None:
+                # both recurrences in one launch each way: the directions are independent
+                out_fw, fin_fw, out_bw, fin_bw = ops.gru_bilayer(
+                    layer_input, lengths, gru_cell_tensors(self, scopes[0]), gru_cell_tensors(self, scopes[1]))
+                return torch.cat([out_fw, out_bw], 2), torch.cat([fin_fw, fin_bw], 1)
             out_fw, fin_fw, _ = ops.gru_layer(layer_input, *gru_cell_tensors(self, scopes[0]),
                                            lengths=lengths, reverse=False)
             out_bw, fin_bw, _ = ops.gru_layer(layer_input, *gru_cell_tensors(self, scopes[1]),

@@ -333,6 +333,91 @@ def gru_layer(x: torch.Tensor, gates_kernel: torch.Tensor, gates_bias: torch.Ten
                            drop_mask, sm_budget)
 
 
+class _BiGRULayer(torch.autograd.Function):
+    """Forward and backward direction of a bidirectional GRU layer over the same input, their recurrences
+    in ONE launch each way (nm_gru_seq_fwd_pair / nm_gru_seq_bwd_pair): the two directions are
+    independent, and one direction alone occupies only half of the SMs for T dependent steps."""
+
+    @staticmethod
+    def forward(ctx, x, lengths, wg_f, bg_f, wc_f, bc_f, wg_b, bg_b, wc_b, bc_b):
+        bsz, t, e = x.shape
+        h = wc_f.size(1)
+        x2 = x.reshape(bsz * t, e)
+        dev = x.device
+        saved = []
+        outs = []
+        bufs = []
+        for wg, bg, wc, bc in ((wg_f, bg_f, wc_f, bc_f), (wg_b, bg_b, wc_b, bc_b)):
+            xproj = torch.empty(bsz * t, 3 * h, device=dev, dtype=torch.float32)
+            gemm(x2, wg[:e], xproj[:, :2 * h], bias=bg)
+            gemm(x2, wc[:e], xproj[:, 2 * h:], bias=bc)
+            states = torch.empty(bsz, t, h, device=dev, dtype=torch.float32)
+            final = torch.empty(bsz, h, device=dev, dtype=torch.float32)
+            gates = torch.empty(bsz, t, 3 * h, device=dev, dtype=torch.float32)
+            hprev = torch.empty(bsz, t, h, device=dev, dtype=torch.float32)
+            rh = torch.empty(bsz, t, h, device=dev, dtype=torch.float32)
+            bufs.append((xproj, states, final, gates, hprev, rh))
+        (xp_f, st_f, fi_f, ga_f, hp_f, rh_f), (xp_b, st_b, fi_b, ga_b, hp_b, rh_b) = bufs
+        call("nm_gru_seq_fwd_pair",
+             ptr(xp_f), ptr(wg_f[e:]), ptr(wc_f[e:]), 0, ptr(st_f), ptr(fi_f), ptr(ga_f), ptr(hp_f), ptr(rh_f),
+             ptr(xp_b), ptr(wg_b[e:]), ptr(wc_b[e:]), 1, ptr(st_b), ptr(fi_b), ptr(ga_b), ptr(hp_b), ptr(rh_b),
+             ptr(lengths), bsz, t, h, lib.stream())
+        ctx.save_for_backward(x2, lengths, wg_f, wc_f, wg_b, wc_b, ga_f, hp_f, rh_f, ga_b, hp_b, rh_b)
+        ctx.dims = (bsz, t, e, h)
+        ctx.sinks = tuple(_sink(w) for w in (wg_f, bg_f, wc_f, bc_f, wg_b, bg_b, wc_b, bc_b))
+        return st_f, fi_f, st_b, fi_b
+
+    @staticmethod
+    def backward(ctx, dst_f, dfi_f, dst_b, dfi_b):
+        x2, lengths, wg_f, wc_f, wg_b, wc_b, ga_f, hp_f, rh_f, ga_b, hp_b, rh_b = ctx.saved_tensors
+        bsz, t, e, h = ctx.dims
+        dev = x2.device
+
+        def c(g):
+            return g.contiguous() if g is not None else None
+
+        dst_f, dfi_f, dst_b, dfi_b = c(dst_f), c(dfi_f), c(dst_b), c(dfi_b)
+        dxp_f = torch.empty(bsz * t, 3 * h, device=dev, dtype=torch.float32)
+        dxp_b = torch.empty(bsz * t, 3 * h, device=dev, dtype=torch.float32)
+        work = torch.empty(2 * bsz * h, device=dev, dtype=torch.float32)
+        call("nm_gru_seq_bwd_pair",
+             ptr(wg_f[e:]), ptr(wc_f[e:]), 0, ptr(ga_f), ptr(hp_f), ptr(dst_f), ptr(dfi_f), ptr(dxp_f),
+             ptr(wg_b[e:]), ptr(wc_b[e:]), 1, ptr(ga_b), ptr(hp_b), ptr(dst_b), ptr(dfi_b), ptr(dxp_b),
+             ptr(lengths), ptr(work), bsz, t, h, lib.stream())
+        grads = []
+        dx = torch.empty(bsz * t, e, device=dev, dtype=torch.float32) if ctx.needs_input_grad[0] else None
+        first = True
+        for (wg, wc, hp, rh, dxp, sinks) in ((wg_f, wc_f, hp_f, rh_f, dxp_f, ctx.sinks[:4]),
+                                             (wg_b, wc_b, hp_b, rh_b, dxp_b, ctx.sinks[4:])):
+            sg, sbg, sc, sbc = sinks
+            dzg, dzc = dxp[:, :2 * h], dxp[:, 2 * h:]
+            dwg = sg if sg is not None else torch.empty_like(wg)
+            dwc = sc if sc is not None else torch.empty_like(wc)
+            hp2, rh2 = hp.view(bsz * t, h), rh.view(bsz * t, h)
+            beta = 1.0 if sg is not None else 0.0
+            gemm(x2, dzg, dwg[:e], trans_a=True, beta=beta)
+            gemm(hp2, dzg, dwg[e:], trans_a=True, beta=beta)
+            beta = 1.0 if sc is not None else 0.0
+            gemm(x2, dzc, dwc[:e], trans_a=True, beta=beta)
+            gemm(rh2, dzc, dwc[e:], trans_a=True, beta=beta)
+            dbg = _bias_grad(dzg, sbg)
+            dbc = _bias_grad(dzc, sbc)
+            if dx is not None:
+                gemm(dzg, wg[:e], dx, trans_b=True, beta=0.0 if first else 1.0)
+                gemm(dzc, wc[:e], dx, trans_b=True, beta=1.0)
+                first = False
+            grads += [None if sg is not None else dwg, dbg, None if sc is not None else dwc, dbc]
+        return (dx.view(bsz, t, e) if dx is not None else None, None) + tuple(grads)
+
+
+def gru_bilayer(x: torch.Tensor, lengths: torch.Tensor, cell_fw, cell_bw):
+    """tf.nn.bidirectional_dynamic_rnn over two TF-1.12 GRUCells (encoders/recurrent.py:82-95).  cell_* =
+    (gates kernel, gates bias, candidate kernel, candidate bias).  Returns (outputs fw [B,T,H], final fw [B,H],
+    outputs bw, final bw); the backward direction walks each sentence from its last token
+    (tf.reverse_sequence semantics), outputs at their original time index."""
+    return _BiGRULayer.apply(x, lengths, *cell_fw, *cell_bw)
+
+
 # ---------------------------------------------------------------------------
 # K4 Bahdanau attention
 # ---------------------------------------------------------------------------

@@ -163,5 +163,11 @@ def adam_kernel(trainer, grad_scale, denominator, lr_t, lr_t_dev):
     trainer._l1l2_buf[0], trainer._l1l2_buf[1] = l1, l2
 
 
-STAND_INS = ("xent_rows", "conv3x3_bias_relu", "maxpool2x2", "linear", "embed", "maxout", "layer_norm", "gru_layer", "bahdanau_attention", "logits_xent",
+def gru_bilayer(x, lengths, cell_fw, cell_bw):
+    out_fw, fin_fw, _ = gru_layer(x, *cell_fw, lengths=lengths, reverse=False)
+    out_bw, fin_bw, _ = gru_layer(x, *cell_bw, lengths=lengths, reverse=True)
+    return out_fw, fin_fw, out_bw, fin_bw
+
+
+STAND_INS = ("gru_bilayer", "xent_rows", "conv3x3_bias_relu", "maxpool2x2", "linear", "embed", "maxout", "layer_norm", "gru_layer", "bahdanau_attention", "logits_xent",
              "log_softmax_from_lse", "mha_core", "beam_step", "beam_gather")
