@@ -369,6 +369,25 @@ int nm_im2col3x3(const float* x, float* cols, int64_t N, int64_t H, int64_t W,
 int nm_maxpool2x2_fwd(const float* x, float* y, int64_t N, int64_t H, int64_t W,
                       int64_t C, void* stream);
 
+/* ---- gate arithmetic of the step-wise cell variants ------------------------------
+ * NematusGRUCell (nn/ortho_gru_cell.py:57-105) after its four projections: sg = state_proj_g(state) [B,2H],
+ * gi = input_proj_g(x) [B,2H], sc = state_proj_c(state) [B,H], ci = input_proj_c(x) [B,H]:
+ *   [r,u] = sigmoid(sg + gi);  cand = tanh(sc * r + ci);  out = u * state + (1 - u) * cand
+ * saved [B,3H] = (r, u, cand).  Backward: dgates [B,2H] (gradient of sg AND of gi), dcpre [B,H] (of ci),
+ * dsc [B,H], dstate [B,H] (the direct path only; the projections' backward adds theirs). */
+int nm_nematus_gate_fwd(const float* sg, const float* gi, const float* sc, const float* ci,
+                        const float* state, float* out, float* saved, int64_t B, int64_t H, void* stream);
+int nm_nematus_gate_bwd(const float* dout, const float* saved, const float* sc, const float* state,
+                        float* dgates, float* dcpre, float* dsc, float* dstate, int64_t B, int64_t H,
+                        void* stream);
+/* tf.nn.rnn_cell.LSTMCell with its defaults (encoders/recurrent.py:21, decoders/decoder.py:29; forget_bias 1):
+ * z [B,4H] = (i, j, f, o) = [x, h].kernel + bias;  c' = sigmoid(f + 1) * c + sigmoid(i) * tanh(j);
+ * h' = sigmoid(o) * tanh(c').  saved [B,5H].  Backward: dnew_c / dnew_h may be NULL. */
+int nm_lstm_gate_fwd(const float* z, const float* c, float* new_c, float* new_h, float* saved, int64_t B,
+                     int64_t H, void* stream);
+int nm_lstm_gate_bwd(const float* dnew_c, const float* dnew_h, const float* saved, const float* c,
+                     float* dz, float* dc, int64_t B, int64_t H, void* stream);
+
 /* ---- K4 (inference): the fused attention-decoder step ---------------------------------
  * Replaces ONE iteration of the decoding while_loop between the previous symbol and the vector the
  * vocabulary projection consumes: embed_input_symbols (decoders/autoregressive.py:269-272),
@@ -399,6 +418,10 @@ int nm_attn_decoder_step_fwd(const int64_t* symbols, const float* emb_table, con
                              float* x_out, float* h_out, float* ctx_out, float* weights_out, float* out,
                              int64_t rows, int64_t group, int64_t E, int64_t H, int64_t A, int64_t C,
                              int64_t Tx, int64_t O, int act, int maxout, void* stream);
+
+/* Diagnostic: 8 int64 device counters receiving the cycle counter of CTA 0 at the phase boundaries of the
+ * following nm_attn_decoder_step_fwd launches; NULL switches it off. */
+int nm_attn_decoder_step_debug(void* counters);
 
 /* ---- K5/K6 at run time: logits, argmax and the symbol bookkeeping of one decoding step ------
  * Replaces get_body of decoders/autoregressive.py:446-480 after next_state: logits = X.W + b

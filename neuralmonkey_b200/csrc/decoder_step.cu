@@ -57,6 +57,7 @@ struct DecStep {
   const float *keys, *values, *mask;
   const float *Wo, *bo;
   float *x_out, *h_out, *ctx_out, *w_out, *out;
+  long long* prof;   // diagnostic: 8 clock64 stamps of CTA 0 (phase boundaries), or null
 };
 
 // Shared-memory carve-up (float offsets), the same arithmetic on host and device.
@@ -363,7 +364,10 @@ __global__ void __launch_bounds__(DS_THREADS, 1) attn_decoder_step_kernel(const 
 #pragma unroll 1
   for (int a = tid; a < p.A; a += DS_THREADS) vs[a] = p.v[a];
   __syncthreads();
+  const bool prof = p.prof != nullptr && blockIdx.x == 0 && tid == 0;
+  if (prof) p.prof[0] = clock64();
   cluster.sync();   // every CTA of the cluster has started: its shared memory may be written remotely
+  if (prof) p.prof[1] = clock64();
 
   const int r_w = warp & (DS_R - 1), half_w = warp / DS_R;   // element-wise passes: warp -> (row, half)
   constexpr int NHALF = DS_WARPS / DS_R;
@@ -388,6 +392,7 @@ __global__ void __launch_bounds__(DS_THREADS, 1) attn_decoder_step_kernel(const 
     }
   }
   cluster.sync();
+  if (prof) p.prof[2] = clock64();
 
   // ---- phase 2: candidate and new state ------------------------------------------------------------
   {
@@ -405,6 +410,7 @@ __global__ void __launch_bounds__(DS_THREADS, 1) attn_decoder_step_kernel(const 
     }
   }
   cluster.sync();
+  if (prof) p.prof[3] = clock64();
 
   // ---- phase 3: query projection, delivered to the CTA that attends for the row --------------------
   {
@@ -420,6 +426,7 @@ __global__ void __launch_bounds__(DS_THREADS, 1) attn_decoder_step_kernel(const 
       qdst[a0 + al] = res[r_w * res_ld + al] + p.bq[a0 + al];
   }
   cluster.sync();
+  if (prof) p.prof[4] = clock64();
 
   // ---- phase 4: attention for the rows this CTA owns ---------------------------------------------------
   {
@@ -564,7 +571,9 @@ __global__ void __launch_bounds__(DS_THREADS, 1) attn_decoder_step_kernel(const 
         for (int cc = 0; cc < CL; ++cc) cluster.map_shared_rank(ctxT, cc)[col * DS_R + rl] = 0.f;
     }
   }
+  if (prof) p.prof[5] = clock64();
   cluster.sync();
+  if (prof) p.prof[6] = clock64();
 
   // ---- phase 5: deep output ---------------------------------------------------------------------------
   {
@@ -590,13 +599,24 @@ __global__ void __launch_bounds__(DS_THREADS, 1) attn_decoder_step_kernel(const 
       }
     }
   }
+  if (prof) p.prof[7] = clock64();
 }
 
 }  // namespace nm
 
 using namespace nm;
 
+static long long* g_decstep_prof = nullptr;
+
 extern "C" {
+
+/* Diagnostic: 8 int64 device counters receiving clock64() of CTA 0 at the phase boundaries of the next
+ * nm_attn_decoder_step_fwd launches (inputs staged | cluster up | gates | state | query | attention |
+ * cluster joined | output done).  NULL = off. */
+int nm_attn_decoder_step_debug(void* counters) {
+  g_decstep_prof = reinterpret_cast<long long*>(counters);
+  return NM_OK;
+}
 
 int nm_attn_decoder_step_fwd(const int64_t* symbols, const float* emb_table, const float* x_in,
                              const float* h_prev, const int32_t* parent, const float* Wg, const float* bg,
@@ -622,6 +642,7 @@ int nm_attn_decoder_step_fwd(const int64_t* symbols, const float* emb_table, con
   p.Wg = Wg; p.bg = bg; p.Wc = Wc; p.bc = bc; p.Wq = Wq; p.bq = bq; p.v = v; p.abias = att_bias;
   p.keys = keys; p.values = values; p.mask = mask; p.Wo = Wo; p.bo = bo;
   p.x_out = x_out; p.h_out = h_out; p.ctx_out = ctx_out; p.w_out = weights_out; p.out = out;
+  p.prof = g_decstep_prof;
 
   // vector path: every row the kernel reads with 16-byte loads is 16-byte aligned
   auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };

@@ -481,3 +481,129 @@ int nm_log_softmax(const float* logits, const float* lse, float* logprobs, int64
 }
 
 }  // extern "C"
+
+// ---------------------------------------------------------------------------
+// Gate arithmetic of the step-wise cell variants: one launch per step
+// instead of a chain of element-wise torch kernels.
+// ---------------------------------------------------------------------------
+namespace nm {
+
+// NematusGRUCell (nn/ortho_gru_cell.py:57-105): sg [B,2H] = state_proj_g(state), gi [B,2H] = input_proj_g(x),
+// sc [B,H] = state_proj_c(state), ci [B,H] = input_proj_c(x).
+//   [r,u] = sigmoid(sg + gi);  cand = tanh(sc * r + ci);  new = u * state + (1 - u) * cand
+// saved [B,3H] = (r, u, cand) for the backward pass.
+__global__ void nematus_gate_fwd_kernel(const float* __restrict__ sg, const float* __restrict__ gi,
+                                        const float* __restrict__ sc, const float* __restrict__ ci,
+                                        const float* __restrict__ state, float* __restrict__ out,
+                                        float* __restrict__ saved, int64_t B, int64_t H) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < B * H; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t b = i / H, j = i - b * H;
+    const float r = sigmoidf_(sg[b * 2 * H + j] + gi[b * 2 * H + j]);
+    const float u = sigmoidf_(sg[b * 2 * H + H + j] + gi[b * 2 * H + H + j]);
+    const float cand = tanhf(sc[i] * r + ci[i]);
+    out[i] = u * state[i] + (1.f - u) * cand;
+    saved[b * 3 * H + j] = r;
+    saved[b * 3 * H + H + j] = u;
+    saved[b * 3 * H + 2 * H + j] = cand;
+  }
+}
+
+// dgates [B,2H] is the gradient of BOTH sg and gi, dcpre [B,H] of ci, dsc [B,H] of sc, dstate [B,H].
+__global__ void nematus_gate_bwd_kernel(const float* __restrict__ dout, const float* __restrict__ saved,
+                                        const float* __restrict__ sc, const float* __restrict__ state,
+                                        float* __restrict__ dgates, float* __restrict__ dcpre,
+                                        float* __restrict__ dsc, float* __restrict__ dstate, int64_t B, int64_t H) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < B * H; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t b = i / H, j = i - b * H;
+    const float r = saved[b * 3 * H + j], u = saved[b * 3 * H + H + j], cand = saved[b * 3 * H + 2 * H + j];
+    const float g = dout[i];
+    const float dpre = g * (1.f - u) * (1.f - cand * cand);
+    const float du = g * (state[i] - cand);
+    const float dr = dpre * sc[i];
+    dstate[i] = g * u;
+    dcpre[i] = dpre;
+    dsc[i] = dpre * r;
+    dgates[b * 2 * H + j] = dr * r * (1.f - r);
+    dgates[b * 2 * H + H + j] = du * u * (1.f - u);
+  }
+}
+
+// tf.nn.rnn_cell.LSTMCell defaults: z [B,4H] = (i, j, f, o);  c' = sigmoid(f + 1) * c + sigmoid(i) * tanh(j);
+// h' = sigmoid(o) * tanh(c').  saved [B,5H] = (sig_i, tanh_j, sig_f, sig_o, tanh_c').
+__global__ void lstm_gate_fwd_kernel(const float* __restrict__ z, const float* __restrict__ c,
+                                     float* __restrict__ new_c, float* __restrict__ new_h,
+                                     float* __restrict__ saved, int64_t B, int64_t H) {
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < B * H; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t b = idx / H, j = idx - b * H;
+    const float* zr = z + b * 4 * H;
+    const float si = sigmoidf_(zr[j]), tj = tanhf(zr[H + j]), sf = sigmoidf_(zr[2 * H + j] + 1.f),
+                so = sigmoidf_(zr[3 * H + j]);
+    const float nc = sf * c[idx] + si * tj;
+    const float tc = tanhf(nc);
+    new_c[idx] = nc;
+    new_h[idx] = so * tc;
+    float* sv = saved + b * 5 * H;
+    sv[j] = si; sv[H + j] = tj; sv[2 * H + j] = sf; sv[3 * H + j] = so; sv[4 * H + j] = tc;
+  }
+}
+
+__global__ void lstm_gate_bwd_kernel(const float* __restrict__ dnew_c, const float* __restrict__ dnew_h,
+                                     const float* __restrict__ saved, const float* __restrict__ c,
+                                     float* __restrict__ dz, float* __restrict__ dc, int64_t B, int64_t H) {
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < B * H; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t b = idx / H, j = idx - b * H;
+    const float* sv = saved + b * 5 * H;
+    const float si = sv[j], tj = sv[H + j], sf = sv[2 * H + j], so = sv[3 * H + j], tc = sv[4 * H + j];
+    const float gh = dnew_h ? dnew_h[idx] : 0.f;
+    const float gc = (dnew_c ? dnew_c[idx] : 0.f) + gh * so * (1.f - tc * tc);
+    float* dzr = dz + b * 4 * H;
+    dzr[j] = gc * tj * si * (1.f - si);
+    dzr[H + j] = gc * si * (1.f - tj * tj);
+    dzr[2 * H + j] = gc * c[idx] * sf * (1.f - sf);
+    dzr[3 * H + j] = gh * tc * so * (1.f - so);
+    dc[idx] = gc * sf;
+  }
+}
+
+}  // namespace nm
+
+extern "C" {
+
+int nm_nematus_gate_fwd(const float* sg, const float* gi, const float* sc, const float* ci, const float* state,
+                        float* out, float* saved, int64_t B, int64_t H, void* stream) {
+  NM_REQUIRE(sg && gi && sc && ci && state && out && saved && B > 0 && H > 0, NM_E_INVALID,
+             "nm_nematus_gate_fwd: bad arguments");
+  nm::nematus_gate_fwd_kernel<<<nm::grid_for(B * H, 256), 256, 0, (cudaStream_t)stream>>>(sg, gi, sc, ci, state, out,
+                                                                                         saved, B, H);
+  NM_LAUNCH_CHECK("nm_nematus_gate_fwd");
+  return NM_OK;
+}
+
+int nm_nematus_gate_bwd(const float* dout, const float* saved, const float* sc, const float* state, float* dgates,
+                        float* dcpre, float* dsc, float* dstate, int64_t B, int64_t H, void* stream) {
+  NM_REQUIRE(dout && saved && sc && state && dgates && dcpre && dsc && dstate && B > 0 && H > 0, NM_E_INVALID,
+             "nm_nematus_gate_bwd: bad arguments");
+  nm::nematus_gate_bwd_kernel<<<nm::grid_for(B * H, 256), 256, 0, (cudaStream_t)stream>>>(dout, saved, sc, state, dgates,
+                                                                                         dcpre, dsc, dstate, B, H);
+  NM_LAUNCH_CHECK("nm_nematus_gate_bwd");
+  return NM_OK;
+}
+
+int nm_lstm_gate_fwd(const float* z, const float* c, float* new_c, float* new_h, float* saved, int64_t B, int64_t H,
+                     void* stream) {
+  NM_REQUIRE(z && c && new_c && new_h && saved && B > 0 && H > 0, NM_E_INVALID, "nm_lstm_gate_fwd: bad arguments");
+  nm::lstm_gate_fwd_kernel<<<nm::grid_for(B * H, 256), 256, 0, (cudaStream_t)stream>>>(z, c, new_c, new_h, saved, B, H);
+  NM_LAUNCH_CHECK("nm_lstm_gate_fwd");
+  return NM_OK;
+}
+
+int nm_lstm_gate_bwd(const float* dnew_c, const float* dnew_h, const float* saved, const float* c, float* dz,
+                     float* dc, int64_t B, int64_t H, void* stream) {
+  NM_REQUIRE(saved && c && dz && dc && B > 0 && H > 0, NM_E_INVALID, "nm_lstm_gate_bwd: bad arguments");
+  nm::lstm_gate_bwd_kernel<<<nm::grid_for(B * H, 256), 256, 0, (cudaStream_t)stream>>>(dnew_c, dnew_h, saved, c, dz, dc,
+                                                                                      B, H);
+  NM_LAUNCH_CHECK("nm_lstm_gate_bwd");
+  return NM_OK;
+}
+
+}  // extern "C"

@@ -205,6 +205,69 @@ def maxout(z: torch.Tensor) -> torch.Tensor:
 
 
 # ---------------------------------------------------------------------------
+# gate arithmetic of the step-wise cell variants (N4): one launch per step and direction
+# ---------------------------------------------------------------------------
+class _NematusGate(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, sg, gi, sc, ci, state):
+        sg, gi, sc, ci, state = (t.contiguous() for t in (sg, gi, sc, ci, state))
+        bsz, h = state.shape
+        out = torch.empty_like(state)
+        saved = torch.empty(bsz, 3 * h, device=state.device, dtype=torch.float32)
+        call("nm_nematus_gate_fwd", ptr(sg), ptr(gi), ptr(sc), ptr(ci), ptr(state), ptr(out), ptr(saved), bsz, h,
+             lib.stream())
+        ctx.save_for_backward(saved, sc, state)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        saved, sc, state = ctx.saved_tensors
+        bsz, h = state.shape
+        dout = dout.contiguous()
+        dgates = torch.empty(bsz, 2 * h, device=state.device, dtype=torch.float32)
+        dcpre, dsc, dstate = torch.empty_like(state), torch.empty_like(state), torch.empty_like(state)
+        call("nm_nematus_gate_bwd", ptr(dout), ptr(saved), ptr(sc), ptr(state), ptr(dgates), ptr(dcpre), ptr(dsc),
+             ptr(dstate), bsz, h, lib.stream())
+        return dgates, dgates, dsc, dcpre, dstate
+
+
+def nematus_gru_gate(state_gates: torch.Tensor, input_gates: torch.Tensor, state_cand: torch.Tensor,
+                     input_cand: torch.Tensor, state: torch.Tensor) -> torch.Tensor:
+    """NematusGRUCell after its projections (nn/ortho_gru_cell.py:86-105): [r,u] = sigmoid(state_gates +
+    input_gates); cand = tanh(state_cand * r + input_cand); u * state + (1 - u) * cand."""
+    return _NematusGate.apply(state_gates, input_gates, state_cand, input_cand, state)
+
+
+class _LSTMGate(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, z, c):
+        z, c = z.contiguous(), c.contiguous()
+        bsz, h = c.shape
+        new_c, new_h = torch.empty_like(c), torch.empty_like(c)
+        saved = torch.empty(bsz, 5 * h, device=c.device, dtype=torch.float32)
+        call("nm_lstm_gate_fwd", ptr(z), ptr(c), ptr(new_c), ptr(new_h), ptr(saved), bsz, h, lib.stream())
+        ctx.save_for_backward(saved, c)
+        return new_c, new_h
+
+    @staticmethod
+    def backward(ctx, dnew_c, dnew_h):
+        saved, c = ctx.saved_tensors
+        bsz, h = c.shape
+        dz = torch.empty(bsz, 4 * h, device=c.device, dtype=torch.float32)
+        dc = torch.empty_like(c)
+        call("nm_lstm_gate_bwd", ptr(dnew_c.contiguous() if dnew_c is not None else None),
+             ptr(dnew_h.contiguous() if dnew_h is not None else None), ptr(saved), ptr(c), ptr(dz), ptr(dc), bsz, h,
+             lib.stream())
+        return dz, dc
+
+
+def lstm_gate(z: torch.Tensor, c: torch.Tensor):
+    """tf LSTMCell defaults after the [x, h] projection: z = (i, j, f, o); returns (c', h') with
+    c' = sigmoid(f + 1) * c + sigmoid(i) * tanh(j), h' = sigmoid(o) * tanh(c')."""
+    return _LSTMGate.apply(z, c)
+
+
+# ---------------------------------------------------------------------------
 # K7 layer norm
 # ---------------------------------------------------------------------------
 class _LayerNorm(torch.autograd.Function):

@@ -163,11 +163,25 @@ def adam_kernel(trainer, grad_scale, denominator, lr_t, lr_t_dev):
     trainer._l1l2_buf[0], trainer._l1l2_buf[1] = l1, l2
 
 
+def nematus_gru_gate(state_gates, input_gates, state_cand, input_cand, state):
+    gates = torch.sigmoid(state_gates + input_gates)
+    size = state.shape[1]
+    reset, update = gates[:, :size], gates[:, size:]
+    cand = torch.tanh(state_cand * reset + input_cand)
+    return update * state + (1.0 - update) * cand
+
+
+def lstm_gate(z, c):
+    i, j, f, o = z.chunk(4, dim=1)
+    new_c = torch.sigmoid(f + 1.0) * c + torch.sigmoid(i) * torch.tanh(j)
+    return new_c, torch.sigmoid(o) * torch.tanh(new_c)
+
+
 def gru_bilayer(x, lengths, cell_fw, cell_bw):
     out_fw, fin_fw, _ = gru_layer(x, *cell_fw, lengths=lengths, reverse=False)
     out_bw, fin_bw, _ = gru_layer(x, *cell_bw, lengths=lengths, reverse=True)
     return out_fw, fin_fw, out_bw, fin_bw
 
 
-STAND_INS = ("gru_bilayer", "xent_rows", "conv3x3_bias_relu", "maxpool2x2", "linear", "embed", "maxout", "layer_norm", "gru_layer", "bahdanau_attention", "logits_xent",
+STAND_INS = ("gru_bilayer", "nematus_gru_gate", "lstm_gate", "xent_rows", "conv3x3_bias_relu", "maxpool2x2", "linear", "embed", "maxout", "layer_norm", "gru_layer", "bahdanau_attention", "logits_xent",
              "log_softmax_from_lse", "mha_core", "beam_step", "beam_gather")

@@ -1,0 +1,67 @@
+"""Data parallelism on real GPUs: two ranks over NCCL, each with its slice of the same
+global batch, reproduce the single-GPU run - losses and every parameter after three optimizer steps - with
+the gradient exchange started INSIDE the backward pass (decoder-side ranges first) and, in a second run,
+with the whole step (NCCL included) replayed from one CUDA graph.  Skipped on a one-GPU box."""
+import os
+import subprocess
+import sys
+
+import pytest
+import torch
+
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.skipif(not torch.cuda.is_available() or torch.cuda.device_count() < 2,
+                                 reason="needs two GPUs")]
+
+_WORKER = r"""
+import os, sys, torch
+sys.path.insert(0, {root!r})
+from neuralmonkey_b200 import distributed, ops, runtime
+from tests.helpers import build_bahdanau, feed, oracle_params_for, random_batch
+world = int(os.environ.get("WORLD_SIZE", "1"))
+distributed.init_from_env()
+ops.set_gemm_backend("simt")          # exact fp32: the split of the batch must not change the arithmetic
+cfg = dict(vs=120, vt=200, es=32, he=16, et=32, hd=32, out=32, maxout=False, max_len=12, supress_unk=False)
+model = build_bahdanau(**cfg, lr=1e-2, clip=1.0, l2=1e-3, cuda_graph={graph})
+model["arena"].load_dict(oracle_params_for(model))
+losses = []
+for step in range(4):
+    src, tgt = random_batch(8, 9, 8, cfg["vs"], cfg["vt"], seed=40 + step, ragged=False)
+    if world > 1:
+        lo, hi = distributed.shard_bounds(8, world)[distributed.rank():distributed.rank() + 2]
+        src, tgt = src[lo:hi], tgt[lo:hi]
+    feed(model, src, tgt, train=True)
+    losses.append(float(model["trainer"].train_step()["losses"][0]))
+trainer = model["trainer"]
+if world > 1 and not {graph}:
+    assert getattr(trainer, "early_exchanges", 0) == 4, getattr(trainer, "early_exchanges", 0)
+if distributed.rank() == 0:
+    torch.save({{"params": {{k: v.cpu() for k, v in model["arena"].state_dict().items()}}, "losses": losses,
+                "capture_exchange": trainer.capture_exchange,
+                "graphs": sum(1 for v in trainer._graphs.values() if isinstance(v, tuple))}}, {out!r} + str(world))
+print("rank", distributed.rank(), "done")
+"""
+
+
+@pytest.mark.parametrize("graph", [False, True])
+def test_two_gpus_equal_one_gpu(tmp_path, graph):
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    script = tmp_path / "dp_worker.py"
+    script.write_text(_WORKER.format(root=root, out=str(tmp_path / "result"), graph=graph))
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1")
+    single = subprocess.run([sys.executable, str(script)], capture_output=True, text=True, timeout=600,
+                            env=dict(env, WORLD_SIZE="1"), cwd=root)
+    assert single.returncode == 0, single.stdout[-2000:] + single.stderr[-2000:]
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+           "--master-addr", "127.0.0.1", "--master-port", "29713", str(script)]
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env, cwd=root)
+    assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
+    one, two = torch.load(str(tmp_path / "result1")), torch.load(str(tmp_path / "result2"))
+    assert one["losses"] == pytest.approx(two["losses"], abs=2e-5)
+    for name, want in one["params"].items():
+        if name.endswith("attn_bias"):
+            continue
+        assert float((two["params"][name] - want).abs().max()) < 5e-5, name
+    if graph:
+        assert two["graphs"] >= 1          # the step was captured (with or without NCCL inside)
+        print("NCCL captured inside the step graph:", two["capture_exchange"])

@@ -54,6 +54,8 @@ def test_reference_ini_trains_unchanged_on_the_gpu(tmp_path, name):
     if name == "bahdanau":
         assert os.path.exists(os.path.join(out, "encoded.npy"))
         losses = training_log_values(log_text, "target/train_xent")
-        assert losses and all(l == l and l < 20.0 for l in losses), losses      # finite, sane
+        # finite; NOT small: the INI sets supress_unk=True and the toy references contain <unk>, whose logit
+        # carries -1e9 in training as well (autoregressive.py:454-457) - the reference logs ~3e8 here too
+        assert losses and all(l == l and abs(l) != float("inf") for l in losses), losses
     if name == "beamsearch":
         assert "beam_search_score" in log_text
