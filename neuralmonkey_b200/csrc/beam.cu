@@ -174,7 +174,77 @@ beam_local_topk_kernel(const float* __restrict__ logprobs, const float* __restri
   }
   __shared__ float wk_s[(BEAM_THREADS / 32) * BEAM_MAX_K], out_s[BEAM_MAX_K];
   __shared__ int32_t wk_i[(BEAM_THREADS / 32) * BEAM_MAX_K], out_i[BEAM_MAX_K];
-  cta_topk<BEAM_ITEMS>(sc, ix, (int)k, wk_s, wk_i, out_s, out_i);
+  // Pre-filter (k <= number of warps): every warp's best score is a candidate of its own, so the k-th
+  // largest of the warp maxima is a lower bound of the chunk's k-th best score; only candidates at or
+  // above it can be among the chunk's top k.  They are few (tens), get listed in shared memory and ranked
+  // exactly by ONE warp - unless ties make the list overflow (a chunk inside a finished hypothesis holds
+  // 4096 equal scores), which falls back to the full selection.  Same (score desc, index asc) order either way.
+  constexpr int NW = BEAM_THREADS / 32, LIST_CAP = 32 * BEAM_ITEMS;
+  __shared__ float wmax[NW], list_s[LIST_CAP];
+  __shared__ int32_t list_i[LIST_CAP];
+  __shared__ int list_n;
+  bool done = false;
+  if (k <= NW) {
+    float tmax = sc[0];
+#pragma unroll
+    for (int it = 1; it < BEAM_ITEMS; ++it) tmax = fmaxf(tmax, sc[it]);
+    tmax = warp_max(tmax);
+    if ((threadIdx.x & 31) == 0) wmax[threadIdx.x >> 5] = tmax;
+    if (threadIdx.x == 0) list_n = 0;
+    __syncthreads();
+    float thr;
+    {   // k-th largest of the NW warp maxima (every thread computes it: NW = 8 values)
+      float v[NW];
+#pragma unroll
+      for (int i = 0; i < NW; ++i) v[i] = wmax[i];
+      thr = -INFINITY;
+#pragma unroll
+      for (int i = 0; i < NW; ++i) {
+        int larger = 0;
+#pragma unroll
+        for (int j = 0; j < NW; ++j) larger += (v[j] > v[i]) || (v[j] == v[i] && j < i);
+        if (larger == (int)k - 1) thr = v[i];
+      }
+    }
+#pragma unroll
+    for (int it = 0; it < BEAM_ITEMS; ++it)
+      if (ix[it] != 0x7fffffff && sc[it] >= thr) {
+        const int slot = atomicAdd(&list_n, 1);
+        if (slot < LIST_CAP) { list_s[slot] = sc[it]; list_i[slot] = ix[it]; }
+      }
+    __syncthreads();
+    const int n = list_n;
+    if (n <= LIST_CAP) {
+      done = true;
+      if (threadIdx.x < 32) {          // one warp ranks the listed candidates exactly
+        float ls[BEAM_ITEMS];
+        int32_t li[BEAM_ITEMS];
+#pragma unroll
+        for (int it = 0; it < BEAM_ITEMS; ++it) {
+          const int c = it * 32 + (int)threadIdx.x;
+          ls[it] = c < n ? list_s[c] : -INFINITY;
+          li[it] = c < n ? list_i[c] : 0x7fffffff;
+        }
+        uint32_t taken = 0;
+        for (int r = 0; r < k; ++r) {
+          Cand best{-INFINITY, 0x7fffffff};
+#pragma unroll
+          for (int it = 0; it < BEAM_ITEMS; ++it)
+            if (!((taken >> it) & 1u) && li[it] != 0x7fffffff && cand_better(ls[it], li[it], best.s, best.i)) {
+              best.s = ls[it];
+              best.i = li[it];
+            }
+          const Cand win = warp_best_cand(best);
+#pragma unroll
+          for (int it = 0; it < BEAM_ITEMS; ++it)
+            if (li[it] == win.i && win.i != 0x7fffffff) taken |= (1u << it);
+          if (threadIdx.x == 0) { out_s[r] = win.s; out_i[r] = win.i; }
+        }
+      }
+      __syncthreads();
+    }
+  }
+  if (!done) cta_topk<BEAM_ITEMS>(sc, ix, (int)k, wk_s, wk_i, out_s, out_i);
   for (int r = threadIdx.x; r < k; r += BEAM_THREADS) {
     const int64_t o = (b * gridDim.x + blockIdx.x) * k + r;
     cand_s[o] = out_s[r];

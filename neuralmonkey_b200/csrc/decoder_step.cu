@@ -98,11 +98,31 @@ __device__ __forceinline__ float ds_fast_tanh(float x) {   // the form attention
   return 1.f - __fdividef(2.f, 1.f + __expf(2.f * x));
 }
 
+// Key / value tiles are read once per step and are 15x the size of everything the step re-reads (its
+// weights, the vocabulary matrix of the GEMM that follows): they pass through L2 with evict-first priority so
+// that the re-read data stays resident from one step to the next.
 __device__ __forceinline__ void bulk_load_1d(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  uint64_t policy;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
   asm volatile(
-      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
-      "l"(reinterpret_cast<uint64_t>(src)), "r"(bytes), "r"(bar)
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(src)), "r"(bytes), "r"(bar), "l"(policy)
       : "memory");
+}
+
+// Weights: streamed once per CTA and step (no reuse inside the SM: no L1 allocation), re-read by every cluster
+// and every step (kept in L2: evict-last).
+__device__ __forceinline__ uint64_t l2_evict_last_policy() {
+  uint64_t policy;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(policy));
+  return policy;
+}
+__device__ __forceinline__ float4 ldg_weight4(const float* p, uint64_t policy) {
+  float4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "l"(p), "l"(policy));
+  return v;
 }
 
 struct DsSeg {
@@ -138,6 +158,7 @@ __device__ __noinline__ void ds_panel(const DsSeg* segs, int nseg, int K, const 
   constexpr int RG = DS_R * G;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int gl = lane % DS_GW, ksl = lane / DS_GW;
+  const uint64_t wpolicy = l2_evict_last_policy();
   const int nquads = (ng + DS_GW - 1) / DS_GW;
 #pragma unroll 1
   for (int qb = 0; qb < nquads; qb += DS_WARPS) {
@@ -174,7 +195,7 @@ __device__ __noinline__ void ds_panel(const DsSeg* segs, int nseg, int K, const 
             for (int u = 0; u < DS_UNROLL; ++u) {
               if (k + u < hi) {
                 if constexpr (G == 4) {
-                  const float4 t = __ldg(reinterpret_cast<const float4*>(wp + (int64_t)u * ldw));
+                  const float4 t = ldg_weight4(wp + (int64_t)u * ldw, wpolicy);
                   w[u][0] = t.x; w[u][1] = t.y; w[u][2] = t.z; w[u][3] = t.w;
                 } else {
                   w[u][0] = __ldg(wp + (int64_t)u * ldw);

@@ -1,0 +1,22 @@
+#!/bin/bash
+# ncu evidence for round 2 (numbers printed by a run under ncu are never bench values):
+#   1. launch list of two training steps of the default bench command
+#   2. --set full of every tc_gemm_kernel launch of one training step (dense / xent instances, fp16 and tf32)
+#   3. --set full of the GRU recurrences and the Bahdanau kernels
+#   4. --set full of the decoding kernels (fused step, vocabulary GEMM + combine, beam top-k)
+out=gpurun_out/ncu_r02
+mkdir -p $out
+B="python bench.py --no-cpu-baseline --no-extras"
+ncu --metrics gpu__time_duration.sum --clock-control none -c 1400 --csv --log-file $out/launches.csv \
+    $B --steps 2 --warmup 1 > $out/list.log 2>&1
+echo "launch list exit $?"; wc -l $out/launches.csv
+ncu --set full --clock-control none --import-source on -k regex:tc_gemm_kernel -s 60 -c 50 -o $out/prof_tc_gemm -f \
+    $B --steps 1 --warmup 1 > $out/tc.log 2>&1
+echo "tc capture exit $?"
+ncu --set full --clock-control none --import-source on -k regex:"gru_seq|bahdanau" -s 12 -c 10 -o $out/prof_rnn -f \
+    $B --steps 1 --warmup 1 > $out/rnn.log 2>&1
+echo "rnn capture exit $?"
+ncu --set full --clock-control none --import-source on -k regex:"attn_decoder_step|decode_combine|beam_local|beam_merge" -s 40 -c 8 \
+    -o $out/prof_decode -f python tools/decode_probe.py --no-stepwise > $out/decode.log 2>&1
+echo "decode capture exit $?"
+ls -la $out/*.ncu-rep
