@@ -57,7 +57,7 @@ class _Graphs:
 
 
 class RNNDecodeEngine:
-    CHUNK = 8            # steps per captured graph / per look at the "unfinished" counters
+    CHUNK = 16           # steps per captured graph / per look at the "unfinished" counters
     GRAPH_AFTER = 2      # a shape is captured the second time it is decoded; one-offs run eagerly
 
     def __init__(self, decoder) -> None:
@@ -181,11 +181,22 @@ class RNNDecodeEngine:
                 graphs.run((kind, t, end), chunk)
             else:
                 chunk()
-            done = (counts[t:end] == 0).nonzero()
-            if done.numel() > 0:
-                return t + int(done[0]) + 1
+            # one small device->host copy per chunk (pinned staging, no torch arithmetic on the device)
+            host = self._counts_host(counts.numel())
+            host[t:end].copy_(counts[t:end], non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+            for s in range(t, end):
+                if int(host[s]) == 0:
+                    return s + 1
             t = end
         return steps
+
+    def _counts_host(self, n: int) -> torch.Tensor:
+        buf = self.__dict__.get("_counts_pinned")
+        if buf is None or buf.numel() < n:
+            buf = torch.zeros(max(n, 256), dtype=torch.int32).pin_memory()
+            self.__dict__["_counts_pinned"] = buf
+        return buf
 
     # -- greedy decoding ------------------------------------------------------------------------------
     @torch.no_grad()

@@ -1,6 +1,6 @@
 """Evaluators referenced by the target configs (reference: neuralmonkey/evaluators/).
-BLEU is implemented natively; SacreBLEU (the `sacrebleu` package is not installed here) is
-served by the same corpus-BLEU on the already tokenised series; ROUGE-L is the LCS F-score."""
+BLEU is implemented natively; SacreBLEU restates what the reference's wrapper uses of the `sacrebleu` package
+(not installed here): evaluators/sacrebleu.py; ROUGE-L is the LCS F-score."""
 from typing import List
 
 from neuralmonkey_b200.evaluators.bleu import BLEU, BLEU1, BLEU2, BLEU4, BLEUEvaluator
@@ -74,7 +74,7 @@ class RougeLEvaluator:
 Accuracy = AccuracyEvaluator()
 ROUGE_L = RougeLEvaluator()
 # the reference names this instance "BLEU" (evaluators/sacrebleu.py:63): its results are logged as <series>/BLEU
-SacreBLEU = BLEUEvaluator(n=4, name="BLEU")
+from neuralmonkey_b200.evaluators.sacrebleu import SacreBLEU, SacreBLEUEvaluator  # noqa: E402
 AccuracySeqLevel = AccuracySeqLevelEvaluator()
 from neuralmonkey_b200.evaluators.chrf import ChrF3  # noqa: E402
 from neuralmonkey_b200.evaluators.edit_distance import EditDistance  # noqa: E402

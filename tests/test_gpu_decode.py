@@ -161,7 +161,8 @@ def test_fused_greedy_equals_the_stepwise_loop(cfg, backend):
                 2e-5 if backend == "simt" else 2e-2)
             assert torch.equal(dec.decoded, base["decoded"]) or backend != "simt"
             if rep == 0:    # eager issue: three launches of libnmb200 per step (graph replays are not counted)
-                issued = min(-(-steps // 8) * 8, cfg["max_len"])    # whole chunks of 8 steps are issued
+                chunk = dec.decode_engine.CHUNK
+                issued = min(-(-steps // chunk) * chunk, cfg["max_len"])    # whole chunks of steps are issued
                 assert launched == 3 * issued, (launched, steps)
     finally:
         ops.set_gemm_backend("auto")

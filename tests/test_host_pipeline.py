@@ -190,3 +190,27 @@ def test_rouge_l_and_accuracy_evaluators():
     assert acc([["a", "b"], ["c"]], [["a", "x"], ["c"]]) == pytest.approx(2.0 / 3.0)     # token level
     assert AccuracySeqLevelEvaluator()([["a", "b"], ["c"]], [["a", "x"], ["c"]]) == pytest.approx(0.5)
     assert AccuracyEvaluator(mask_symbol="x")([["a", "b"]], [["a", "x"]]) == pytest.approx(1.0)
+
+
+def test_sacrebleu_evaluator_known_answers():
+    """evaluators.SacreBLEU follows sacrebleu's corpus BLEU (what the reference's wrapper calls with
+    tokenize="none", smooth_method="exp"): a hand-computed corpus - precisions 7/8, 3/6, 2/4, 1/3, brevity
+    penalty exp(1 - 9/8) - the exp smoothing of an order without matches, and the 13a tokenizer."""
+    import math
+    from neuralmonkey_b200.evaluators import SacreBLEU
+    from neuralmonkey_b200.evaluators.sacrebleu import SacreBLEUEvaluator, tokenize_13a
+    hyp = [["the", "cat", "sat", "on", "the", "mat"], ["hello", "world"]]
+    ref = [["the", "cat", "sat", "on", "a", "mat"], ["hello", "there", "world"]]
+    want = 100.0 * math.exp(1 - 9 / 8) * math.exp((math.log(7 / 8) + math.log(3 / 6) + math.log(2 / 4) + math.log(1 / 3)) / 4)
+    assert abs(SacreBLEU(hyp, ref) - want) < 1e-9
+    assert abs(SacreBLEU(ref, ref) - 100.0) < 1e-9
+    assert SacreBLEU.name == "BLEU"
+    # no 4-gram (and no trigram) match: exp smoothing gives 1/(2 t3) and 1/(4 t4) instead of zero
+    short_h, short_r = [["a", "b", "c", "d"]], [["a", "b", "x", "d"]]
+    want = 100.0 * math.exp((math.log(3 / 4) + math.log(1 / 3) + math.log(1 / (2 * 2)) + math.log(1 / (4 * 1))) / 4)
+    assert abs(SacreBLEU(short_h, short_r) - want) < 1e-9
+    assert SacreBLEUEvaluator("x", smooth_method="none")(short_h, short_r) < 1e-6
+    assert tokenize_13a('Hello, world! It costs 3.5$ (approx.) - ok?') == "Hello , world ! It costs 3.5 $ ( approx . ) - ok ?"
+    import pytest
+    with pytest.raises(ValueError):
+        SacreBLEUEvaluator("x", tokenize="intl-unknown")

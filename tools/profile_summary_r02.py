@@ -72,7 +72,8 @@ KEYS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
 doc = ["# ncu --set full captures ({}): `--clock-control none --import-source on`".format(TAG), "",
        "Peaks (MEASURED_PEAKS.json): HBM {:.0f} GB/s, dense bf16 sustained {:.1f} TFLOP/s.".format(PEAK_HBM, PEAK_TF), ""]
 traffic = {}
-for rep, title in (("prof_tc_gemm", "tcgen05 GEMM family, every launch of one training step"),
+for rep, title in (("prof_tc_gemm", "tcgen05 GEMM, the kind::f16 instances (vocabulary projection and its gradients)"),
+                   ("prof_tc_tf32", "tcgen05 GEMM, kind::tf32 instances of one training step (dense projections, weight gradients)"),
                    ("prof_rnn", "GRU recurrences and Bahdanau attention (training)"),
                    ("prof_decode", "decoding: fused step, vocabulary GEMM combine, beam top-k")):
     path = os.path.join(SRC, rep + ".ncu-rep")
