@@ -41,7 +41,7 @@ constexpr int DS_THREADS = 512;
 constexpr int DS_WARPS = DS_THREADS / 32;
 constexpr int DS_UNROLL = 8;     // weight rows in flight per thread
 constexpr int DS_SLOTS = 4;      // TMA ring depth
-constexpr int DS_RED_FLOATS = 64 * 32;    // K-split scratch of ds_panel: <= 64 partial sums of 32 floats
+constexpr int DS_RED_FLOATS = 128 * 32;   // K-split scratch of ds_panel: up to 128 partial sums of 32 floats
 
 struct DecStep {
   int rows, E, H, A, C, Tx, O, group, act, maxout;
@@ -141,8 +141,8 @@ struct DsSeg {
 // k-slices; the k-slices of a group are lanes of ONE warp, so their partial sums meet in three shuffle rounds.
 // When the CTA has fewer group quads than warps, several warps share a quad (K split once more) and a
 // single barrier joins them.  NOT inlined: four call sites, ~10 KB of unrolled FMAs each.
-constexpr int DS_GW = 4;     // column groups per warp
-constexpr int DS_KSL = 8;    // k-slices per warp (DS_GW * DS_KSL = 32 lanes)
+constexpr int DS_GW_MAX = 16;   // a warp owns gw = 2..16 adjacent column groups x (32 / gw) k-slices; gw is
+                                // chosen per call so that as many of the 16 warps as possible have work
 
 __device__ __forceinline__ float4 lds128(uint32_t addr) {
   float4 v;
@@ -157,6 +157,17 @@ __device__ __noinline__ void ds_panel(const DsSeg* segs, int nseg, int K, const 
   const int ng = nA + nB;
   constexpr int RG = DS_R * G;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  // groups per warp: the choice that keeps most warps busy (38 groups: gw = 8 -> 5 quads x 3 warps; gw = 4
+  // would leave 6 of 16 warps idle and every busy lane with twice the k range)
+  int DS_GW = 4, best_busy = 0;
+#pragma unroll
+  for (int cand = 2; cand <= DS_GW_MAX; cand <<= 1) {
+    const int nqc = (ng + cand - 1) / cand;
+    const int busy = nqc >= DS_WARPS ? DS_WARPS : nqc * (DS_WARPS / nqc);
+    const bool fits = nqc >= DS_WARPS || (DS_WARPS / nqc) * nqc * cand * RG <= DS_RED_FLOATS;   // K-split scratch
+    if (fits && (busy > best_busy || (busy == best_busy && cand == 4))) { best_busy = busy; DS_GW = cand; }
+  }
+  const int DS_KSL = 32 / DS_GW;
   const int gl = lane % DS_GW, ksl = lane / DS_GW;
   const uint64_t wpolicy = l2_evict_last_policy();
   const int nquads = (ng + DS_GW - 1) / DS_GW;
@@ -224,13 +235,16 @@ __device__ __noinline__ void ds_panel(const DsSeg* segs, int nseg, int K, const 
         start += len;
       }
     }
-    // the k-slices of a column group are the lanes gl, gl + 4, ..., gl + 28 of this warp
+    // the k-slices of a column group are the lanes gl, gl + gw, gl + 2 gw, ... of this warp
 #pragma unroll
-    for (int off = DS_GW; off < 32; off <<= 1)
+    for (int off = 2; off < 32; off <<= 1) {
+      if (off >= DS_GW) {        // warp-uniform
 #pragma unroll
-      for (int r = 0; r < DS_R; ++r)
+        for (int r = 0; r < DS_R; ++r)
 #pragma unroll
-        for (int c = 0; c < G; ++c) acc[r][c] += __shfl_xor_sync(0xffffffffu, acc[r][c], off);
+          for (int c = 0; c < G; ++c) acc[r][c] += __shfl_xor_sync(0xffffffffu, acc[r][c], off);
+      }
+    }
     if (wsplit == 1) {
       if (active && ksl == 0) {
 #pragma unroll
@@ -240,7 +254,7 @@ __device__ __noinline__ void ds_panel(const DsSeg* segs, int nseg, int K, const 
       }
     } else {
       // several warps per quad: one barrier joins their partial sums (fixed order: deterministic)
-      const int S = wsplit * nq * DS_GW;              // S * RG <= DS_RED_FLOATS (S <= 64)
+      const int S = wsplit * nq * DS_GW;              // S * RG <= DS_RED_FLOATS by the choice of gw above
       if (ws < wsplit && ksl == 0) {
         const int slot = ws * nq * DS_GW + quad * DS_GW + gl;
 #pragma unroll
