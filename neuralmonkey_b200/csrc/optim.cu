@@ -38,7 +38,30 @@ reg_norm_kernel(const float* __restrict__ params, float* __restrict__ grads,
     const int64_t a = max(c0, seg_off[seg]), b = min(c1, seg_off[seg + 1]);
     const bool reg = (seg_reg[seg] & 1) != 0;
     float ss = 0.f;
-    for (int64_t i = a + threadIdx.x; i < b; i += OPT_THREADS) {
+    // segments start on 64-float boundaries and chunks on 8192: [a, b) is 16-byte aligned, so the bulk goes
+    // through 128-bit accesses (four times fewer memory instructions in flight for the same bytes)
+    const bool vec_ok = ((a & 3) == 0) &&
+                        (((reinterpret_cast<uintptr_t>(grads) | reinterpret_cast<uintptr_t>(params)) & 15) == 0);
+    const int64_t nvec = vec_ok ? (b - a) / 4 : 0;     // arbitrary segment tables (tests) take the scalar loop
+    float4* g4 = reinterpret_cast<float4*>(grads + a);
+    const float4* p4 = reinterpret_cast<const float4*>(params + a);
+    for (int64_t i = threadIdx.x; i < nvec; i += OPT_THREADS) {
+      float4 g = g4[i];
+      float gv[4] = {g.x * grad_scale, g.y * grad_scale, g.z * grad_scale, g.w * grad_scale};
+      if (reg) {
+        const float4 p = p4[i];
+        const float pv[4] = {p.x, p.y, p.z, p.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          gv[j] += 2.f * l2 * pv[j] + l1 * (pv[j] > 0.f ? 1.f : (pv[j] < 0.f ? -1.f : 0.f));
+          l1_acc += fabsf(pv[j]);
+          l2_acc += pv[j] * pv[j];
+        }
+      }
+      g4[i] = make_float4(gv[0], gv[1], gv[2], gv[3]);
+      ss += gv[0] * gv[0] + gv[1] * gv[1] + gv[2] * gv[2] + gv[3] * gv[3];
+    }
+    for (int64_t i = a + nvec * 4 + threadIdx.x; i < b; i += OPT_THREADS) {
       float g = grads[i] * grad_scale;
       if (reg) {
         const float p = params[i];
@@ -85,7 +108,32 @@ clip_adam_kernel(float* __restrict__ params, const float* __restrict__ grads, fl
     // entries that received no gradient (embedding rows absent from the batch) keep their
     // moments and value instead of decaying
     const bool lazy = (seg_reg[seg] & 2) != 0;
-    for (int64_t i = a + threadIdx.x; i < b; i += OPT_THREADS) {
+    const bool vec_ok = ((a & 3) == 0) &&
+                        (((reinterpret_cast<uintptr_t>(grads) | reinterpret_cast<uintptr_t>(params) |
+                           reinterpret_cast<uintptr_t>(m) | reinterpret_cast<uintptr_t>(v)) & 15) == 0);
+    const int64_t nvec = vec_ok ? (b - a) / 4 : 0;
+    const float4* g4 = reinterpret_cast<const float4*>(grads + a);
+    float4* m4 = reinterpret_cast<float4*>(m + a);
+    float4* v4 = reinterpret_cast<float4*>(v + a);
+    float4* p4 = reinterpret_cast<float4*>(params + a);
+    for (int64_t i = threadIdx.x; i < nvec; i += OPT_THREADS) {
+      const float4 gq = g4[i];
+      const float gv[4] = {gq.x * scale, gq.y * scale, gq.z * scale, gq.w * scale};
+      if (lazy && gv[0] == 0.f && gv[1] == 0.f && gv[2] == 0.f && gv[3] == 0.f) continue;
+      float4 mq = m4[i], vq = v4[i], pq = p4[i];
+      float mv[4] = {mq.x, mq.y, mq.z, mq.w}, vv[4] = {vq.x, vq.y, vq.z, vq.w}, pv[4] = {pq.x, pq.y, pq.z, pq.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (lazy && gv[j] == 0.f) continue;
+        mv[j] = beta1 * mv[j] + (1.f - beta1) * gv[j];
+        vv[j] = beta2 * vv[j] + (1.f - beta2) * gv[j] * gv[j];
+        pv[j] -= lr_t * mv[j] / (sqrtf(vv[j]) + eps);
+      }
+      m4[i] = make_float4(mv[0], mv[1], mv[2], mv[3]);
+      v4[i] = make_float4(vv[0], vv[1], vv[2], vv[3]);
+      p4[i] = make_float4(pv[0], pv[1], pv[2], pv[3]);
+    }
+    for (int64_t i = a + nvec * 4 + threadIdx.x; i < b; i += OPT_THREADS) {
       const float g = grads[i] * scale;
       if (lazy && g == 0.f) continue;
       const float mi = beta1 * m[i] + (1.f - beta1) * g;
