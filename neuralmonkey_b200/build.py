@@ -65,12 +65,17 @@ def build(force: bool = False, verbose: bool = False) -> str:
                  or any(os.path.getmtime(o) > os.path.getmtime(LIB_PATH)
                         for o in objs))
     if need_link:
-        cmd = [_nvcc(), "-shared", "-o", LIB_PATH] + objs + [
+        # link beside the target and rename: a reader (or a snapshot of the tree) never sees half a library
+        tmp_path = LIB_PATH + ".tmp.{}".format(os.getpid())
+        cmd = [_nvcc(), "-shared", "-o", tmp_path] + objs + [
             "-gencode", "arch=compute_100a,code=sm_100a", "-cudart", "static"]
         res = subprocess.run(cmd, capture_output=True, text=True)
         if res.returncode != 0:
+            if os.path.exists(tmp_path):
+                os.remove(tmp_path)
             raise RuntimeError("link failed:\n{}\n{}".format(
                 res.stdout, res.stderr))
+        os.replace(tmp_path, LIB_PATH)
         if verbose:
             print("linked", LIB_PATH)
     return LIB_PATH

@@ -30,6 +30,12 @@ int nm_gemm_uses_tc(int transA, int transB, int64_t M, int64_t N, int64_t K, int
   return tc_gemm_supported(transA, transB, M, N, K, lda, ldb, ldc, nullptr, nullptr, nullptr) ? 1 : 0;
 }
 
+int nm_gemm_set_pair_mode(int mode) {
+  NM_REQUIRE(mode >= -1 && mode <= 1, NM_E_INVALID, "nm_gemm_set_pair_mode: mode must be -1 (policy), 0 or 1");
+  tc_gemm_set_pair_mode(mode);
+  return NM_OK;
+}
+
 int nm_gemm(int transA, int transB, int64_t M, int64_t N, int64_t K, const float* A, int64_t lda,
             const float* B, int64_t ldb, float* C, int64_t ldc, const float* bias, int act,
             float beta, int backend, void* stream) {

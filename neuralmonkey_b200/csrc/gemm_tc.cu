@@ -37,9 +37,10 @@ constexpr int TC_EPI_WARPS = 8;
 constexpr int TC_A_BYTES = TC_BM * TC_BK * 4;  // 16 KB
 constexpr int TC_SMEM_BUDGET = 200 * 1024;
 
-template <int BN>
+// CTAS = 2: a CTA pair works on one 256 x BN tile (cta_group::2); each CTA stages BN/2 rows of the B tile
+template <int BN, int CTAS = 1>
 struct TcCfg {
-  static constexpr int B_BYTES = BN * TC_BK * 4;
+  static constexpr int B_BYTES = (BN / CTAS) * TC_BK * 4;
   static constexpr int STAGE_BYTES = TC_A_BYTES + B_BYTES;
   static constexpr int STAGES = (TC_SMEM_BUDGET / STAGE_BYTES) > 8 ? 8 : (TC_SMEM_BUDGET / STAGE_BYTES);
   static constexpr int TMEM_COLS = BN <= 64 ? 128 : (BN <= 128 ? 256 : 512);  // 2*BN rounded to a power of two
@@ -373,15 +374,24 @@ struct MnDesc {
 // ESZ = operand element size: 4 = fp32 consumed as TF32 (kind::tf32), 2 = fp16 (kind::f16, K-major
 // operands only).  A k-block is 128 bytes of K either way (32 or 64 elements) and one instruction
 // consumes 32 of them, so the smem ring, the descriptors and the TMEM layout are the same.
-template <int BN, bool A_MN, bool B_MN, int MODE, int ESZ = 4>
+template <int BN, bool A_MN, bool B_MN, int MODE, int ESZ = 4, int CTAS = 1>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                int64_t M, int64_t N, int64_t K, TcEpilogue epi, MnDesc mn, int splits, int kb_per_split,
                TcExt ext) {
   static_assert(ESZ == 4 || !(A_MN || B_MN) || (BN % 64 == 0), "MN-major fp16 B tiles come in 64-column boxes");
   static_assert(ESZ == 2 || MODE != TC_EPI_XENT_BWD16, "the fp16 epilogue belongs to the fp16 instances");
+  static_assert(CTAS == 1 || CTAS == 2, "one CTA or a CTA pair per tile");
+  static_assert(CTAS == 1 || (BN % 64 == 0), "a pair splits the B tile in two halves of whole swizzle atoms");
   constexpr int BK = 128 / ESZ;                // elements per 128-byte k-block
-  using Cfg = TcCfg<BN>;
+  constexpr int BM_T = TC_BM * CTAS;           // rows of one tile (pair: 256, 128 per CTA)
+  constexpr int BN_LOAD = BN / CTAS;           // rows of the B tile this CTA stages
+  using Cfg = TcCfg<BN, CTAS>;
+  // pair mode: rank 0 leads (issues the MMAs, owns the `full` and `tmem_empty` barriers the pair reports to)
+  const uint32_t cta_rank = CTAS == 2 ? cluster_ctarank() : 0u;
+  const bool leader = cta_rank == 0;
+  const int64_t worker = CTAS == 2 ? (int64_t)(blockIdx.x >> 1) : (int64_t)blockIdx.x;
+  const int64_t nworkers = CTAS == 2 ? (int64_t)(gridDim.x >> 1) : (int64_t)gridDim.x;
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;  // SW128 tiles: 1 KB aligned
@@ -394,7 +404,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 4);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int64_t tiles_m = (M + TC_BM - 1) / TC_BM;
+  const int64_t tiles_m = (M + BM_T - 1) / BM_T;
   const int64_t tiles_n = (N + BN - 1) / BN;
   // split-K: the reduction is cut into `splits` slices, each an independent work item whose
   // epilogue adds its partial tile into C with red.global.add (weight-gradient products
@@ -409,19 +419,27 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
-      mbar_init(tempty_bar(a), TC_EPI_WARPS);  // one arrive per epilogue warp
+      mbar_init(tempty_bar(a), TC_EPI_WARPS * CTAS);  // one arrive per epilogue warp (of both CTAs)
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot),
-                 "r"((uint32_t)Cfg::TMEM_COLS)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if constexpr (CTAS == 2) {   // the same warp of both CTAs allocates the pair's columns
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot),
+                   "r"((uint32_t)Cfg::TMEM_COLS)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot),
+                   "r"((uint32_t)Cfg::TMEM_COLS)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   tcgen05_fence_before();
   __syncthreads();
+  if constexpr (CTAS == 2) cluster_sync_all();   // the peer's barriers exist before anything arrives on them
   tcgen05_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
@@ -431,34 +449,40 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int32_t m0 = (int32_t)((tile % tiles_m) * TC_BM);
-        const int32_t n0 = (int32_t)(((tile / tiles_m) % tiles_n) * BN);
+      for (int64_t tile = worker; tile < num_tiles; tile += nworkers) {
+        const int32_t m0 = (int32_t)((tile % tiles_m) * BM_T) + (int32_t)cta_rank * TC_BM;
+        const int32_t n0 = (int32_t)(((tile / tiles_m) % tiles_n) * BN) + (int32_t)cta_rank * BN_LOAD;
         const int kb_begin = (int)(tile / (tiles_m * tiles_n)) * kb_per_split;
         const int kb_end = min(num_kb_total, kb_begin + kb_per_split);
         for (int kb = kb_begin; kb < kb_end; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1u);
           const uint32_t a_dst = smem_base + stage * Cfg::STAGE_BYTES;
           const uint32_t b_dst = a_dst + TC_A_BYTES;
-          mbar_expect_tx(full_bar(stage), (uint32_t)Cfg::STAGE_BYTES);
+          // pair: the leader's barrier counts the bytes of both CTAs
+          if (leader) mbar_expect_tx(full_bar(stage), (uint32_t)(Cfg::STAGE_BYTES * CTAS));
+          const uint32_t full_dst = CTAS == 2 ? mapa_u32(full_bar(stage), 0u) : full_bar(stage);
+          auto tma_load = [&](uint32_t dst, const CUtensorMap* map, int32_t c0, int32_t c1) {
+            if constexpr (CTAS == 2) tma_load_2d_pair(dst, map, full_dst, c0, c1);
+            else tma_load_2d(dst, map, full_dst, c0, c1);
+          };
           const int32_t k0 = kb * BK;
           // MN-major tiles arrive as boxes of one 128-byte swizzle row of MN elements (32 fp32 / 64 fp16)
           // by one k-block of rows: 4 KB (fp32) or 8 KB (fp16) each
           constexpr int MN_BOX = 128 / ESZ;
           constexpr int MN_BOX_BYTES = MN_BOX * BK * ESZ;
           if (!A_MN) {
-            tma_load_2d(a_dst, &map_a, full_bar(stage), k0, m0);  // box {one k-block, 128 rows}
+            tma_load(a_dst, &map_a, k0, m0);  // box {one k-block, 128 rows}
           } else {
 #pragma unroll
             for (int j = 0; j < TC_BM / MN_BOX; ++j)
-              tma_load_2d(a_dst + j * MN_BOX_BYTES, &map_a, full_bar(stage), m0 + MN_BOX * j, k0);
+              tma_load(a_dst + j * MN_BOX_BYTES, &map_a, m0 + MN_BOX * j, k0);
           }
           if (!B_MN) {
-            tma_load_2d(b_dst, &map_b, full_bar(stage), k0, n0);  // box {one k-block, BN rows}
+            tma_load(b_dst, &map_b, k0, n0);  // box {one k-block, BN (pair: BN/2) rows}
           } else {
 #pragma unroll
-            for (int j = 0; j < BN / MN_BOX; ++j)
-              tma_load_2d(b_dst + j * MN_BOX_BYTES, &map_b, full_bar(stage), n0 + MN_BOX * j, k0);
+            for (int j = 0; j < BN_LOAD / MN_BOX; ++j)
+              tma_load(b_dst + j * MN_BOX_BYTES, &map_b, n0 + MN_BOX * j, k0);
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         }
@@ -466,17 +490,17 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
+    if (lane == 0 && leader) {
       // instruction descriptor: c=F32 [4,6)=1, a=TF32 [7,10)=2, b=TF32 [10,13)=2,
       // a_major bit15, b_major bit16, N>>3 [17,23), M>>4 [24,29)
       constexpr uint32_t FMT = ESZ == 4 ? 2u : 0u;   // TF32 = 2, F16 = 0
       const uint32_t idesc = (1u << 4) | (FMT << 7) | (FMT << 10) | ((A_MN ? 1u : 0u) << 15) |
                              ((B_MN ? 1u : 0u) << 16) | ((uint32_t)(BN >> 3) << 17) |
-                             ((uint32_t)(TC_BM >> 4) << 24);
+                             ((uint32_t)(BM_T >> 4) << 24);
       int stage = 0;
       uint32_t phase = 0;
       int64_t it = 0;
-      for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      for (int64_t tile = worker; tile < num_tiles; tile += nworkers, ++it) {
         const int acc = (int)(it & 1);
         const uint32_t acc_phase = (uint32_t)((it >> 1) & 1);
         mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
@@ -505,15 +529,23 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                                      : smem_desc(a_addr + k * 32, 16, 1024, SMEM_LAYOUT_SW128);
             const uint64_t db = B_MN ? smem_desc(b_addr + k * mn.kadv, mn.lbo, mn.sbo, mn.layout)
                                      : smem_desc(b_addr + k * 32, 16, 1024, SMEM_LAYOUT_SW128);
-            if (ESZ == 4)
-              umma_tf32(d_tmem, da, db, idesc, (kb > 0 || k > 0) ? 1u : 0u);
-            else
-              umma_f16(d_tmem, da, db, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+            const uint32_t accum = (kb > 0 || k > 0) ? 1u : 0u;
+            if constexpr (CTAS == 2) {
+              if (ESZ == 4) umma_tf32_pair(d_tmem, da, db, idesc, accum);
+              else umma_f16_pair(d_tmem, da, db, idesc, accum);
+            } else {
+              if (ESZ == 4) umma_tf32(d_tmem, da, db, idesc, accum);
+              else umma_f16(d_tmem, da, db, idesc, accum);
+            }
           }
-          umma_commit(empty_bar(stage));  // frees this smem stage when the MMAs retire
+          // frees this smem stage (of both CTAs) when the MMAs retire
+          if constexpr (CTAS == 2) umma_commit_pair(empty_bar(stage), 3);
+          else umma_commit(empty_bar(stage));
           if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         }
-        umma_commit(tfull_bar(acc));  // accumulator complete -> epilogue
+        // accumulator complete -> epilogue (of both CTAs)
+        if constexpr (CTAS == 2) umma_commit_pair(tfull_bar(acc), 3);
+        else umma_commit(tfull_bar(acc));
       }
     }
   } else {
@@ -529,12 +561,12 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                                             STAGES * Cfg::STAGE_BYTES + 256 + (warp - 2) * 4096);
     const int n32 = (int)N;
     int64_t it = 0;
-    for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+    for (int64_t tile = worker; tile < num_tiles; tile += nworkers, ++it) {
       const int acc = (int)(it & 1);
       const uint32_t acc_phase = (uint32_t)((it >> 1) & 1);
       const int64_t tm = tile % tiles_m, tn = (tile / tiles_m) % tiles_n;
       const int split = (int)(tile / (tiles_m * tiles_n));
-      const int64_t row = tm * TC_BM + quad * 32 + lane;
+      const int64_t row = tm * BM_T + (int64_t)cta_rank * TC_BM + quad * 32 + lane;
       mbar_wait(tfull_bar(acc), acc_phase);
       tcgen05_fence_after();
       RowStats st{-INFINITY, 0.f, -INFINITY, 0x7fffffff};
@@ -581,18 +613,27 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             make_float4(st.mx, st.sum, __int_as_float(st.arg), st.tgt);
       tcgen05_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(tempty_bar(acc));
+      if (lane == 0) {
+        if constexpr (CTAS == 2) mbar_arrive_cluster(mapa_u32(tempty_bar(acc), 0u));   // the leader's barrier
+        else mbar_arrive(tempty_bar(acc));
+      }
     }
   }
 
   // teardown: everyone done with TMEM before dealloc
   tcgen05_fence_before();
   __syncthreads();
+  if constexpr (CTAS == 2) cluster_sync_all();   // the peer is done with this CTA's barriers and with the pair's TMEM
   if (warp == 1) {
     tcgen05_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
-                 "r"((uint32_t)Cfg::TMEM_COLS)
-                 : "memory");
+    if constexpr (CTAS == 2)
+      asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
+                   "r"((uint32_t)Cfg::TMEM_COLS)
+                   : "memory");
+    else
+      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
+                   "r"((uint32_t)Cfg::TMEM_COLS)
+                   : "memory");
   }
 }
 
@@ -672,6 +713,87 @@ bool tc_gemm_supported(int transA, int transB, int64_t M, int64_t N, int64_t K, 
   return true;
 }
 
+constexpr bool TC_PAIR_DEFAULT = false;   // until the pair instances are verified on the GPU: opt-in only
+// NMB200_TC_PAIR: 0 = never, 1 = wherever the shape allows, unset = the policy of pair_wanted()
+static int g_pair_override = -2;   // nm_gemm_set_pair_mode(); -2 = not set
+static int pair_mode() {
+  static const int mode = [] {
+    const char* e = getenv("NMB200_TC_PAIR");
+    return (e && *e) ? atoi(e) : -1;
+  }();
+  return g_pair_override != -2 ? g_pair_override : mode;
+}
+int tc_gemm_set_pair_mode(int mode) {
+  const int before = pair_mode();
+  g_pair_override = mode;
+  return before;
+}
+
+// A CTA pair per 256 x bn tile (cta_group::2): worth it when the product is bound by the bytes the SMs pull
+// from L2 (large M and N), not for the skinny / split-K shapes whose tiles would no longer fill the chip.
+static bool pair_wanted(int64_t M, int64_t N, int64_t K, int bn, int splits) {
+  (void)K;
+  if (bn != 128 && bn != 256) return false;
+  if (sm_count() < 2 || M < 2 * TC_BM) return false;
+  const int mode = pair_mode();
+  if (mode == 0) return false;
+  if (mode == 1) return true;
+  if (!TC_PAIR_DEFAULT) return false;
+  const int64_t pair_tiles = ceil_div(M, 2 * TC_BM) * ceil_div(N, bn) * splits;
+  return splits == 1 && pair_tiles >= (int64_t)(sm_count() / 2);
+}
+
+template <class Kern, class... Args>
+static int launch_pair_kernel(Kern kern, int smem_bytes, int64_t pair_tiles, cudaStream_t s, Args... args) {
+  const int64_t max_pairs = sm_count() / 2;
+  const int64_t pairs = pair_tiles < max_pairs ? pair_tiles : max_pairs;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(2 * pairs));
+  cfg.blockDim = dim3(TC_THREADS);
+  cfg.dynamicSmemBytes = (size_t)smem_bytes;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  NM_CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, args...));
+  NM_LAUNCH_CHECK("tc_gemm_kernel(pair)");
+  return NM_OK;
+}
+
+template <int BN, bool A_MN, bool B_MN, int MODE>
+static int launch_pair(const CUtensorMap& ma, const CUtensorMap& mb, int64_t M, int64_t N, int64_t K,
+                       const TcEpilogue& epi, cudaStream_t s, int splits = 1, int kb_per_split = 0) {
+  using Cfg = TcCfg<BN, 2>;
+  auto kern = tc_gemm_kernel<BN, A_MN, B_MN, MODE, 4, 2>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    NM_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    attr_done = true;
+  }
+  if (kb_per_split <= 0) kb_per_split = (int)ceil_div(K, TC_BK);
+  return launch_pair_kernel(kern, Cfg::SMEM_BYTES, ceil_div(M, 2 * TC_BM) * ceil_div(N, BN) * splits, s, ma, mb, M,
+                            N, K, epi, mn_desc_config(), splits, kb_per_split, TcExt{});
+}
+
+template <int BN, int MODE, bool MN = false>
+static int launch_pair16(const CUtensorMap& ma, const CUtensorMap& mb, int64_t M, int64_t N, int64_t K,
+                         const TcEpilogue& epi, const TcExt& ext, cudaStream_t s) {
+  using Cfg = TcCfg<BN, 2>;
+  auto kern = tc_gemm_kernel<BN, MN, MN, MODE, 2, 2>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    NM_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    attr_done = true;
+  }
+  return launch_pair_kernel(kern, Cfg::SMEM_BYTES, ceil_div(M, 2 * TC_BM) * ceil_div(N, BN), s, ma, mb, M, N, K, epi,
+                            MN ? MnDesc{SMEM_LAYOUT_SW128, 1024, 8192, 2048} : MnDesc{0, 0, 0, 0}, 1,
+                            (int)ceil_div(K, 64), ext);
+}
+
 template <int BN, bool A_MN, bool B_MN, int MODE>
 static int launch_cfg(const CUtensorMap& ma, const CUtensorMap& mb, int64_t M, int64_t N, int64_t K,
                       const TcEpilogue& epi, cudaStream_t s, int splits = 1, int kb_per_split = 0) {
@@ -733,6 +855,12 @@ static int make_map16(CUtensorMap* map, const void* base, int64_t rows, int64_t 
 }
 
 static int pick_bn(int64_t M, int64_t N, int64_t K) {
+  static const int forced = [] {   // NMB200_TC_BN={64,128,160,256}: tile-width experiments (tools/gemm_sweep.py)
+    const char* e = getenv("NMB200_TC_BN");
+    const int v = e ? atoi(e) : 0;
+    return (v == 64 || v == 128 || v == 160 || v == 256) ? v : 0;
+  }();
+  if (forced) return forced;
   if (N <= 64) return 64;
   if (N <= 128) return 128;
   // skinny output, very long reduction (dX of the vocabulary projection: 12800 x 300 x 32000):
@@ -753,33 +881,10 @@ int tc_gemm_launch(int transA, int transB, int64_t M, int64_t N, int64_t K, cons
   //                 transB=1 -> B stored [N,K], K contiguous (K-major).
   const bool a_mn = transA != 0, b_mn = transB == 0;
   const int bn = (epi.mode == TC_EPI_DENSE) ? pick_bn(M, N, K) : TC_XENT_BN;
-  CUtensorMap ma, mb;
-  int rc;
-  if (!a_mn) rc = make_map(&ma, A, M, K, lda, TC_BK, TC_BM, false);
-  else       rc = make_map(&ma, A, K, M, lda, 32, TC_BK, true);
-  if (rc) return rc;
-  if (!b_mn) rc = make_map(&mb, B, N, K, ldb, TC_BK, (uint32_t)bn, false);
-  else       rc = make_map(&mb, B, K, N, ldb, 32, TC_BK, true);
-  if (rc) return rc;
-#define NM_TC_DISPATCH(BN_, MODE_)                                                                     \
-  do {                                                                                                 \
-    if (!a_mn && !b_mn) return launch_cfg<BN_, false, false, MODE_>(ma, mb, M, N, K, epi, s, splits, kb_per);  \
-    if (!a_mn && b_mn) return launch_cfg<BN_, false, true, MODE_>(ma, mb, M, N, K, epi, s, splits, kb_per);    \
-    if (a_mn && !b_mn) return launch_cfg<BN_, true, false, MODE_>(ma, mb, M, N, K, epi, s, splits, kb_per);    \
-    return launch_cfg<BN_, true, true, MODE_>(ma, mb, M, N, K, epi, s, splits, kb_per);                        \
-  } while (0)
-  if (epi.mode == TC_EPI_XENT_FWD) {  // A is always K-major for the vocabulary projection
-    if (b_mn) return launch_cfg<256, false, true, TC_EPI_XENT_FWD>(ma, mb, M, N, K, epi, s);
-    return launch_cfg<256, false, false, TC_EPI_XENT_FWD>(ma, mb, M, N, K, epi, s);
-  }
-  if (epi.mode == TC_EPI_XENT_BWD) {
-    if (b_mn) return launch_cfg<256, false, true, TC_EPI_XENT_BWD>(ma, mb, M, N, K, epi, s);
-    return launch_cfg<256, false, false, TC_EPI_XENT_BWD>(ma, mb, M, N, K, epi, s);
-  }
   // split-K when the output alone cannot occupy the chip (and nothing forbids partial sums)
   int splits = 1;
   int kb_per = (int)ceil_div(K, TC_BK);
-  {
+  if (epi.mode == TC_EPI_DENSE) {
     const int64_t tiles = ceil_div(M, TC_BM) * ceil_div(N, bn);
     const int64_t num_kb = ceil_div(K, TC_BK);
     if (epi.act == NM_ACT_NONE && tiles * 2 <= sm_count() && num_kb >= 16) {
@@ -804,8 +909,52 @@ int tc_gemm_launch(int transA, int transB, int64_t M, int64_t N, int64_t K, cons
         splits = (int)ceil_div(num_kb, kb_per);
       }
     }
-    if (splits > 1 && epi.beta == 0.f)  // partial sums are added: start from zero
-      NM_CUDA_TRY(cudaMemset2DAsync(epi.C, sizeof(float) * epi.ldc, 0, sizeof(float) * N, M, s));
+  }
+  const bool pair = pair_wanted(M, N, K, bn, splits);
+  CUtensorMap ma, mb;
+  int rc;
+  if (!a_mn) rc = make_map(&ma, A, M, K, lda, TC_BK, TC_BM, false);
+  else       rc = make_map(&ma, A, K, M, lda, 32, TC_BK, true);
+  if (rc) return rc;
+  if (!b_mn) rc = make_map(&mb, B, N, K, ldb, TC_BK, (uint32_t)(pair ? bn / 2 : bn), false);
+  else       rc = make_map(&mb, B, K, N, ldb, 32, TC_BK, true);
+  if (rc) return rc;
+  if (splits > 1 && epi.beta == 0.f)  // partial sums are added: start from zero
+    NM_CUDA_TRY(cudaMemset2DAsync(epi.C, sizeof(float) * epi.ldc, 0, sizeof(float) * N, M, s));
+#define NM_TC_DISPATCH_PAIR(BN_, MODE_)                                                                 \
+  do {                                                                                                 \
+    if (!a_mn && !b_mn) return launch_pair<BN_, false, false, MODE_>(ma, mb, M, N, K, epi, s, splits, kb_per); \
+    if (!a_mn && b_mn) return launch_pair<BN_, false, true, MODE_>(ma, mb, M, N, K, epi, s, splits, kb_per);   \
+    if (a_mn && !b_mn) return launch_pair<BN_, true, false, MODE_>(ma, mb, M, N, K, epi, s, splits, kb_per);   \
+    return launch_pair<BN_, true, true, MODE_>(ma, mb, M, N, K, epi, s, splits, kb_per);                       \
+  } while (0)
+  if (pair) {
+    if (epi.mode == TC_EPI_XENT_FWD) {
+      if (b_mn) return launch_pair<256, false, true, TC_EPI_XENT_FWD>(ma, mb, M, N, K, epi, s);
+      return launch_pair<256, false, false, TC_EPI_XENT_FWD>(ma, mb, M, N, K, epi, s);
+    }
+    if (epi.mode == TC_EPI_XENT_BWD) {
+      if (b_mn) return launch_pair<256, false, true, TC_EPI_XENT_BWD>(ma, mb, M, N, K, epi, s);
+      return launch_pair<256, false, false, TC_EPI_XENT_BWD>(ma, mb, M, N, K, epi, s);
+    }
+    if (bn == 128) NM_TC_DISPATCH_PAIR(128, TC_EPI_DENSE);
+    NM_TC_DISPATCH_PAIR(256, TC_EPI_DENSE);
+  }
+#undef NM_TC_DISPATCH_PAIR
+#define NM_TC_DISPATCH(BN_, MODE_)                                                                     \
+  do {                                                                                                 \
+    if (!a_mn && !b_mn) return launch_cfg<BN_, false, false, MODE_>(ma, mb, M, N, K, epi, s, splits, kb_per);  \
+    if (!a_mn && b_mn) return launch_cfg<BN_, false, true, MODE_>(ma, mb, M, N, K, epi, s, splits, kb_per);    \
+    if (a_mn && !b_mn) return launch_cfg<BN_, true, false, MODE_>(ma, mb, M, N, K, epi, s, splits, kb_per);    \
+    return launch_cfg<BN_, true, true, MODE_>(ma, mb, M, N, K, epi, s, splits, kb_per);                        \
+  } while (0)
+  if (epi.mode == TC_EPI_XENT_FWD) {  // A is always K-major for the vocabulary projection
+    if (b_mn) return launch_cfg<256, false, true, TC_EPI_XENT_FWD>(ma, mb, M, N, K, epi, s);
+    return launch_cfg<256, false, false, TC_EPI_XENT_FWD>(ma, mb, M, N, K, epi, s);
+  }
+  if (epi.mode == TC_EPI_XENT_BWD) {
+    if (b_mn) return launch_cfg<256, false, true, TC_EPI_XENT_BWD>(ma, mb, M, N, K, epi, s);
+    return launch_cfg<256, false, false, TC_EPI_XENT_BWD>(ma, mb, M, N, K, epi, s);
   }
   if (bn == 64) NM_TC_DISPATCH(64, TC_EPI_DENSE);
   if (bn == 128) NM_TC_DISPATCH(128, TC_EPI_DENSE);
@@ -833,6 +982,10 @@ int tc_gemm16_mn_launch(int64_t M, int64_t N, int64_t K, const void* A, int64_t 
   if (N <= 64) bn = 64;
   else if (N <= 128) bn = 128;
   else if (ceil_div(M, TC_BM) * ceil_div(N, 256) < sm_count()) bn = 128;
+  if (pair_wanted(M, N, K, bn, 1)) {
+    if (bn == 128) return launch_pair16<128, TC_EPI_DENSE, true>(ma, mb, M, N, K, epi, ext, s);
+    return launch_pair16<256, TC_EPI_DENSE, true>(ma, mb, M, N, K, epi, ext, s);
+  }
   if (bn == 64) return launch_cfg16<64, TC_EPI_DENSE, true>(ma, mb, M, N, K, epi, ext, s);
   if (bn == 128) return launch_cfg16<128, TC_EPI_DENSE, true>(ma, mb, M, N, K, epi, ext, s);
   return launch_cfg16<256, TC_EPI_DENSE, true>(ma, mb, M, N, K, epi, ext, s);
@@ -846,11 +999,19 @@ int tc_gemm16_launch(int64_t M, int64_t N, int64_t K, const void* A, int64_t lda
                  (reinterpret_cast<uintptr_t>(B) & 15) == 0,
              NM_E_INVALID, "tc_gemm16: fp16 operands need 16-byte aligned bases and row pitches");
   const int bn = (epi.mode == TC_EPI_DENSE) ? pick_bn(M, N, K) : TC_XENT_BN;
+  const bool pair = pair_wanted(M, N, K, bn, 1);
   CUtensorMap ma, mb;
   int rc = make_map16(&ma, A, M, K, lda, TC_BM);
   if (rc) return rc;
-  rc = make_map16(&mb, B, N, K, ldb, (uint32_t)bn);
+  rc = make_map16(&mb, B, N, K, ldb, (uint32_t)(pair ? bn / 2 : bn));
   if (rc) return rc;
+  if (pair) {
+    if (epi.mode == TC_EPI_XENT_FWD) return launch_pair16<256, TC_EPI_XENT_FWD>(ma, mb, M, N, K, epi, ext, s);
+    if (epi.mode == TC_EPI_XENT_BWD16) return launch_pair16<256, TC_EPI_XENT_BWD16>(ma, mb, M, N, K, epi, ext, s);
+    NM_REQUIRE(epi.mode == TC_EPI_DENSE, NM_E_INVALID, "tc_gemm16: unsupported epilogue %d", epi.mode);
+    if (bn == 128) return launch_pair16<128, TC_EPI_DENSE>(ma, mb, M, N, K, epi, ext, s);
+    return launch_pair16<256, TC_EPI_DENSE>(ma, mb, M, N, K, epi, ext, s);
+  }
   if (epi.mode == TC_EPI_XENT_FWD) return launch_cfg16<256, TC_EPI_XENT_FWD>(ma, mb, M, N, K, epi, ext, s);
   if (epi.mode == TC_EPI_XENT_BWD16) return launch_cfg16<256, TC_EPI_XENT_BWD16>(ma, mb, M, N, K, epi, ext, s);
   NM_REQUIRE(epi.mode == TC_EPI_DENSE, NM_E_INVALID, "tc_gemm16: unsupported epilogue %d", epi.mode);

@@ -62,4 +62,8 @@ int tc_gemm16_launch(int64_t M, int64_t N, int64_t K, const void* A, int64_t lda
 int tc_gemm16_mn_launch(int64_t M, int64_t N, int64_t K, const void* A, int64_t lda, const void* B,
                         int64_t ldb, const TcEpilogue& epi, const TcExt& ext, cudaStream_t s);
 
+// CTA-pair tiles (cta_group::2, 256 x BN per pair): -1 = the library's policy, 0 = never, 1 = wherever the shape
+// allows.  Returns the previous mode.  Overrides the NMB200_TC_PAIR environment variable.
+int tc_gemm_set_pair_mode(int mode);
+
 }  // namespace nm

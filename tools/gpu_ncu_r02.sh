@@ -23,4 +23,9 @@ echo "rnn capture exit $?"
 ncu --set full --clock-control none -k regex:"attn_decoder_step|decode_combine|beam_local|beam_merge" -s 40 -c 8 \
     -o $out/prof_decode -f python tools/decode_probe.py --no-stepwise > $out/decode.log 2>&1
 echo "decode capture exit $?"
-ls -la $out/*.ncu-rep
+# gpurun brings back at most 64 MiB: keep the raw metric pages as CSV, drop the reports
+for rep in $out/*.ncu-rep; do
+  ncu -i "$rep" --page raw --csv > "${rep%.ncu-rep}.raw.csv" 2>/dev/null
+  rm -f "$rep"
+done
+ls -la $out/

@@ -76,10 +76,13 @@ for rep, title in (("prof_tc_gemm", "tcgen05 GEMM, the kind::f16 instances (voca
                    ("prof_tc_tf32", "tcgen05 GEMM, kind::tf32 instances of one training step (dense projections, weight gradients)"),
                    ("prof_rnn", "GRU recurrences and Bahdanau attention (training)"),
                    ("prof_decode", "decoding: fused step, vocabulary GEMM combine, beam top-k")):
-    path = os.path.join(SRC, rep + ".ncu-rep")
-    if not os.path.exists(path):
+    path, csv_path = os.path.join(SRC, rep + ".ncu-rep"), os.path.join(SRC, rep + ".raw.csv")
+    if os.path.exists(csv_path):        # exported on the GPU box (the reports themselves exceed gpurun's 64 MiB)
+        txt = open(csv_path).read()
+    elif os.path.exists(path):
+        txt = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    else:
         continue
-    txt = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rd = list(csv.reader(io.StringIO(txt)))
     header, units, data = rd[0], rd[1], rd[2:]
     idx = {h: i for i, h in enumerate(header)}
