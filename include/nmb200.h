@@ -92,6 +92,18 @@ int nm_act_bwd(const float* y, const float* dy, float* dx, int64_t n, int act,
 /* out[n] (+)= sum_m x[m,n]  -- bias gradients. accumulate in {0,1}. */
 int nm_colsum(const float* x, int64_t M, int64_t N, int64_t ldx, float* out,
               int accumulate, void* stream);
+/* Dropout (tf.nn.dropout selected by train_mode: nn/utils.py:6-22) in one pass, the keep decisions drawn inside
+ * the kernel (Philox4x32-10; key = seed, counter = (element / 4, site, step)) - no random tensor and no mask in
+ * memory.  `state` = device int64[2] {seed, step}; the host bumps `step` once per training step, `site` numbers
+ * the dropout calls of a step in program order.
+ *   nm_dropout_apply: y[i] = keep_i ? x[i] / keep_prob : 0   (+ residual[i] when residual != NULL); y may alias x.
+ *     The backward pass is the same call on the incoming gradient with the same (site, step).
+ *   nm_dropout_mask:  mask[i] = keep_i ? 1 / keep_prob : 0  (for kernels that take a mask operand: nm_mha_fwd_drop,
+ *     the drop_mask of nm_gru_seq_fwd). */
+int nm_dropout_apply(const float* x, const float* residual, float* y, int64_t n, float keep_prob,
+                     const int64_t* state, int64_t site, void* stream);
+int nm_dropout_mask(float* mask, int64_t n, float keep_prob, const int64_t* state, int64_t site,
+                    void* stream);
 /* maxout of nn/projection.py:7-35: y[m,j] = max(z[m,j], z[m,O+j]); z is [M,2*O].
  * fwd writes y and the uint8 winner (0: first half, 1: second half). */
 int nm_maxout_fwd(const float* z, float* y, uint8_t* which, int64_t M, int64_t O,

@@ -25,10 +25,8 @@ def single(part, scope: str, queries: torch.Tensor, states: torch.Tensor, mask: 
     ctx, _ = attention(part, scope, normalized, states, states, mask, n_heads, False,
                        attention_keep_prob, part.train_mode, False)
     if use_dropout:
-        ctx = dropout(ctx, keep_prob, part.train_mode)
-    if residual:
-        ctx = ctx + queries
-    return ctx
+        return dropout(ctx, keep_prob, part.train_mode, residual=queries if residual else None)
+    return ctx + queries if residual else ctx
 
 
 def declare_cross(part, scope: str, strategy: str, dim: int, heads: List[int], heads_hier: int = None) -> None:
@@ -89,4 +87,4 @@ def hierarchical(part, scope: str, queries, encoder_states, encoder_masks, heads
     ones = torch.ones(bsz * steps, len(contexts), device=queries.device, dtype=torch.float32)
     ctx = single(part, scope + "/enc_hier", normalized.reshape(bsz * steps, 1, dim), stacked, ones, heads_hier,
                  keep_prob, 1.0, normalize=False, use_dropout=False, residual=False)
-    return dropout(ctx.reshape(bsz, steps, dim), keep_prob, part.train_mode) + queries
+    return dropout(ctx.reshape(bsz, steps, dim), keep_prob, part.train_mode, residual=queries)

@@ -155,7 +155,7 @@ class TransformerDecoder(AutoregressiveDecoder):
             ctx, _ = attention(self, scope + "/self_attention", normalized, normalized, normalized,
                                mask, self.n_heads_self, True, self.self_att_dropout_keep_prob,
                                self.train_mode, self.use_att_transform_bias)
-            states = dropout(ctx, self.dropout_keep_prob, self.train_mode) + states
+            states = dropout(ctx, self.dropout_keep_prob, self.train_mode, residual=states)
             states = combine(self, scope + "/encdec_attention", states, enc_states, enc_masks,
                              self.n_heads_enc, self.attention_dropout_keep_prob,
                              self.dropout_keep_prob)

@@ -68,8 +68,7 @@ def feedforward_sublayer(part, scope: str, layer_input: torch.Tensor, keep_prob:
                         part.var(scope + "/hidden_state/bias"), act="relu")
     hidden = dropout(hidden, keep_prob, train_mode)
     out = ops.linear(hidden, part.var(scope + "/output/kernel"), part.var(scope + "/output/bias"))
-    out = dropout(out, keep_prob, train_mode)
-    return out + layer_input
+    return dropout(out, keep_prob, train_mode, residual=layer_input)
 
 
 class TransformerEncoder(ModelPart, TemporalStatefulWithOutput):
@@ -162,7 +161,7 @@ class TransformerEncoder(ModelPart, TemporalStatefulWithOutput):
         ctx, _ = attention(self, scope + "/self_attention", normalized, normalized, normalized, mask,
                            self.n_heads, False, self.attention_dropout_keep_prob, self.train_mode,
                            self.use_att_transform_bias)
-        states = dropout(ctx, self.dropout_keep_prob, self.train_mode) + states
+        states = dropout(ctx, self.dropout_keep_prob, self.train_mode, residual=states)
         if self.input_for_cross_attention is not None:
             enc_states = get_attention_states(self.input_for_cross_attention)
             enc_mask = get_attention_mask(self.input_for_cross_attention)
@@ -171,7 +170,7 @@ class TransformerEncoder(ModelPart, TemporalStatefulWithOutput):
                                enc_mask, self.n_cross_att_heads, False,
                                self.attention_dropout_keep_prob, self.train_mode,
                                self.use_att_transform_bias)
-            states = dropout(ctx, self.dropout_keep_prob, self.train_mode) + states
+            states = dropout(ctx, self.dropout_keep_prob, self.train_mode, residual=states)
         return feedforward_sublayer(self, scope + "/feedforward", states, self.dropout_keep_prob,
                                     self.train_mode)
 

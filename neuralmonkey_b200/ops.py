@@ -176,6 +176,47 @@ def linear(x: torch.Tensor, w: torch.Tensor, b: Optional[torch.Tensor] = None,
     return _Linear.apply(x, w, b, act)
 
 
+class _Dropout(torch.autograd.Function):
+    """y = dropout(x) (+ residual), masks drawn inside the kernel (K15, csrc/dropout.cu); the backward pass
+    re-draws the mask of the same (site, step) instead of reading one."""
+
+    @staticmethod
+    def forward(ctx, x, residual, keep_prob, site):
+        from neuralmonkey_b200 import runtime
+        xc = _f32(x).contiguous()
+        rc = None if residual is None else _f32(residual).expand_as(x).contiguous()
+        y = torch.empty_like(xc)
+        state = runtime.dropout_state()
+        call("nm_dropout_apply", ptr(xc), ptr(rc), ptr(y), xc.numel(), float(keep_prob), ptr(state), int(site),
+             lib.stream())
+        ctx.keep_prob, ctx.site, ctx.state = float(keep_prob), int(site), state
+        ctx.has_residual = residual is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        dyc = dy.contiguous()
+        dx = torch.empty_like(dyc)
+        call("nm_dropout_apply", ptr(dyc), None, ptr(dx), dyc.numel(), ctx.keep_prob, ptr(ctx.state), ctx.site,
+             lib.stream())
+        return dx, (dy if ctx.has_residual else None), None, None
+
+
+def dropout(x: torch.Tensor, keep_prob: float, residual: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """x with each element kept with probability keep_prob and scaled by 1/keep_prob, plus `residual`."""
+    from neuralmonkey_b200 import runtime
+    return _Dropout.apply(x, residual, keep_prob, runtime.next_dropout_site())
+
+
+def dropout_mask(shape, keep_prob: float, device=None) -> torch.Tensor:
+    """A mask tensor (entries 0 or 1/keep_prob) for the kernels that take one as an operand."""
+    from neuralmonkey_b200 import runtime
+    mask = torch.empty(tuple(int(d) for d in shape), device=runtime.device(), dtype=torch.float32)
+    call("nm_dropout_mask", ptr(mask), mask.numel(), float(keep_prob), ptr(runtime.dropout_state()),
+         runtime.next_dropout_site(), lib.stream())
+    return mask
+
+
 class _Maxout(torch.autograd.Function):
     @staticmethod
     def forward(ctx, z):

@@ -34,9 +34,40 @@ def arena() -> ParameterArena:
 
 def reset() -> None:
     """Start a fresh experiment (new arena, global step 0)."""
-    global _arena, _global_step
+    global _arena, _global_step, _dropout_state, _dropout_site
     _arena = None
     _global_step = 0
+    _dropout_state = None
+    _dropout_site = 0
+
+
+# -- dropout random stream (kernel-side Philox: csrc/dropout.cu) ------------------------------------------
+_dropout_state = None  # type: Optional[torch.Tensor]   # device int64 {seed, step}
+_dropout_site = 0      # dropout calls since the last advance, in program order
+
+
+def dropout_state() -> torch.Tensor:
+    """Device {seed, step} the dropout kernels read.  The seed is torch's (the experiment's `random_seed`)."""
+    global _dropout_state
+    if _dropout_state is None:
+        _dropout_state = torch.tensor([torch.initial_seed() & 0x7FFFFFFFFFFFFFFF, 0], dtype=torch.int64,
+                                      device=device())
+    return _dropout_state
+
+
+def advance_dropout() -> None:
+    """New masks from here on: once per training step, BEFORE the step is issued or replayed (the increment is
+    a device operation outside the step's CUDA graph, which reads `step` when it runs)."""
+    global _dropout_site
+    dropout_state()[1:2].add_(1)
+    _dropout_site = 0
+
+
+def next_dropout_site() -> int:
+    """Number of this dropout call within the step (a captured step replays the numbers it was captured with)."""
+    global _dropout_site
+    _dropout_site += 1
+    return _dropout_site
 
 
 def global_step() -> int:

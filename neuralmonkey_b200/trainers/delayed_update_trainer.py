@@ -32,6 +32,8 @@ class DelayedUpdateTrainer(GenericTrainer):
         import torch
         from neuralmonkey_b200 import distributed
         arena = runtime.arena()
+        if arena.params.is_cuda:
+            runtime.advance_dropout()       # new dropout masks for every micro-batch
         if self._accumulated == 0:
             arena.zero_grad()
         world = distributed.world_size()

@@ -305,6 +305,8 @@ class GenericTrainer(GraphExecutor, Feedable):
                    zero_grad: bool = True) -> Dict[str, Any]:
         """Run one step on the batch currently fed to the model parts (train mode)."""
         arena = runtime.arena()
+        if arena.params.is_cuda:
+            runtime.advance_dropout()       # this step's dropout masks (read on the device: also by a replayed graph)
         if (self.use_cuda_graph and apply_update and zero_grad and grad_scale == 1.0
                 and arena.params.is_cuda
                 and len(self.objectives) == 1 and hasattr(type(self.objectives[0].decoder), "train_xent_sum")):

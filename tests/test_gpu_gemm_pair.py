@@ -50,10 +50,10 @@ def test_pair_gemm_equals_single_cta(pair_switch, ta, tb, shape):
     ref = (a.double().t() if ta else a.double()) @ (b.double().t() if tb else b.double())
     assert torch.isfinite(outs[1]).all()
     assert rel_err(outs[1], ref) < 2e-3
-    if k < 8192:                       # split-K adds partial tiles with atomics: order-dependent rounding
-        assert torch.equal(outs[0], outs[1]), float((outs[0] - outs[1]).abs().max())
+    if k <= 512:                       # longer reductions may be cut (split-K: partial tiles meet in atomics,
+        assert torch.equal(outs[0], outs[1]), float((outs[0] - outs[1]).abs().max())   # order-dependent rounding)
     else:
-        assert rel_err(outs[1], outs[0].double()) < 1e-5
+        assert rel_err(outs[1], outs[0].double()) < 1e-6
 
 
 @pytest.mark.parametrize("act", [None, "tanh", "relu"])

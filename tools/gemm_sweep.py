@@ -34,6 +34,16 @@ TRANSFORMER = [
 ]
 
 
+# what a launch costs by itself, one tile per SM with a short and with a long reduction (steady-state rate of the
+# TMA ring per SM), and the same through a pure-L2 operand set
+DIAG = [
+    ("1 tile      ", 0, 1, 128, 128, 32), ("148 tiles k=1 blk", 0, 1, 18944, 128, 32),
+    ("148 tiles K=320 ", 0, 1, 18944, 128, 320), ("148 tiles K=3200", 0, 1, 18944, 128, 3200),
+    ("148 tiles K=320 BN256", 0, 1, 18944, 256, 320), ("148 tiles K=3200 BN256", 0, 1, 18944, 256, 3200),
+    ("4 rounds K=320", 0, 1, 75776, 128, 320), ("4 rounds K=320 MN-B", 0, 0, 75776, 128, 320),
+]
+
+
 def time_shape(ta, tb, m, n, k, reps, act=None, bias=False):
     dev = torch.device("cuda")
     a_shape = (k, m) if ta else (m, k)
@@ -74,6 +84,8 @@ def main():
         shapes += [("ende",) + s for s in ENDE]
     if args.set in ("transformer", "all"):
         shapes += [("transformer",) + s for s in TRANSFORMER]
+    if args.set in ("diag", "all"):
+        shapes += [("diag",) + s for s in DIAG]
     print("NMB200_TC_BN =", os.environ.get("NMB200_TC_BN", "(auto)"))
     for group, label, ta, tb, m, n, k in shapes:
         us = time_shape(ta, tb, m, n, k, args.reps)

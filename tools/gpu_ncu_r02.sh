@@ -11,10 +11,10 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 1400 --csv --log-fi
     $B --steps 2 --warmup 1 > $out/list.log 2>&1
 echo "launch list exit $?"; wc -l $out/launches.csv
 # the report files travel back through gpurun_out/ (64 MiB): two small captures instead of one of every launch
-ncu --set full --clock-control none --kernel-name-base demangled -k regex:"tc_gemm_kernel<.*\(int\)2>" -s 8 -c 8 -o $out/prof_tc_gemm -f \
+ncu --set full --clock-control none --kernel-name-base demangled -k regex:"tc_gemm_kernel<.*\(int\)2, \(int\)1>" -s 8 -c 8 -o $out/prof_tc_gemm -f \
     $B --steps 1 --warmup 1 > $out/tc.log 2>&1
 echo "tc f16 capture exit $?"
-ncu --set full --clock-control none --kernel-name-base demangled -k regex:"tc_gemm_kernel<.*\(int\)4>" -s 60 -c 16 -o $out/prof_tc_tf32 -f \
+ncu --set full --clock-control none --kernel-name-base demangled -k regex:"tc_gemm_kernel<.*\(int\)4, \(int\)1>" -s 60 -c 16 -o $out/prof_tc_tf32 -f \
     $B --steps 1 --warmup 1 > $out/tc32.log 2>&1
 echo "tc tf32 capture exit $?"
 ncu --set full --clock-control none -k regex:"gru_seq|bahdanau" -s 12 -c 10 -o $out/prof_rnn -f \

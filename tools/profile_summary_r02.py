@@ -85,7 +85,16 @@ for rep, title in (("prof_tc_gemm", "tcgen05 GEMM, the kind::f16 instances (voca
         continue
     rd = list(csv.reader(io.StringIO(txt)))
     header, units, data = rd[0], rd[1], rd[2:]
-    idx = {h: i for i, h in enumerate(header)}
+    class _Idx(dict):          # this ncu prefixes some metrics with their unit ("FBSP.TriageCompute.dram__throughput...")
+        def __missing__(self, key):
+            for h, i in self.items():
+                if h.endswith("." + key):
+                    return i
+            for h, i in self.items():
+                if key in h:
+                    return i
+            raise KeyError(key)
+    idx = _Idx({h: i for i, h in enumerate(header)})
     tens = [h for h in header if ("umma" in h or "tensor" in h) and "pct" in h]
     doc += ["## {} (`{}`)".format(title, rep), "",
             "| kernel | us | DRAM rd MB | DRAM wr MB | DRAM % | SM % | tensor pipe % | grid x block | regs |",
@@ -106,7 +115,7 @@ for rep, title in (("prof_tc_gemm", "tcgen05 GEMM, the kind::f16 instances (voca
         g = groups.setdefault(short, [0, 0.0, 0.0, 0.0])
         g[0] += 1; g[1] += us; g[2] += rd_b + wr_b; g[3] = max(g[3], tp if tp == tp else 0.0)
         # map the fp16 vocabulary instances to the entry points bench.py names
-        m = re.search(r"tc_gemm_kernel<(\d+), (\w+), (\w+), (\d+), (\d+)>", short)
+        m = re.search(r"tc_gemm_kernel<(\d+), (\w+), (\w+), (\d+), (\d+)(?:, \d+)?>", short)
         if m:
             bn, a_mn, b_mn, mode, esz = m.groups()
             call = None
