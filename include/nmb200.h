@@ -368,6 +368,24 @@ int nm_mha_bwd_drop(const float* q, const float* k, const float* v, const float*
                     float* dk, float* dv, float* de_work, int64_t B, int64_t Tq, int64_t Tk,
                     int64_t heads, int64_t dh, void* stream);
 
+/* The same attention on the tensor cores: every product a batched tcgen05 GEMM over all (sentence, head)
+ * pairs - P = softmax(mask(Q.K^T/sqrt(dh))) with the softmax in the GEMM epilogue, O = (P*drop).V; backward
+ * dS = P*(dO.V^T*drop - rowsum)/sqrt(dh) in the epilogue, dQ = dS.K, dK = dS^T.Q, dV = (P*drop)^T.dO.  TF32
+ * operands, fp32 accumulation; q/k/v/out and their gradients keep the [B, T, heads*dh] layout (a head is a
+ * column window of the TMA tensor map).  probs, probs_drop and ds_work are [B, heads, Tq32, Tk32] with both
+ * time extents rounded up to 32 and the padding written as zeros; probs_drop (= probs * drop_mask) exists
+ * exactly when drop_mask [B, heads, Tq, Tk] is given.  Supported: dh % 32 == 0, dh <= 128, Tk <= 128
+ * (nm_mha_tc_supported returns 1), otherwise NM_E_UNSUPPORTED - nm_mha_fwd / nm_mha_bwd serve the rest and
+ * remain the exact-fp32 engine. */
+int nm_mha_tc_supported(int64_t B, int64_t Tq, int64_t Tk, int64_t heads, int64_t dh);
+int nm_mha_tc_fwd(const float* q, const float* k, const float* v, const float* key_mask, int causal,
+                  const float* drop_mask, float* out, float* probs, float* probs_drop, int64_t B,
+                  int64_t Tq, int64_t Tk, int64_t heads, int64_t dh, void* stream);
+int nm_mha_tc_bwd(const float* q, const float* k, const float* v, const float* key_mask, int causal,
+                  const float* drop_mask, const float* probs, const float* probs_drop, const float* dout,
+                  float* dq, float* dk, float* dv, float* ds_work, int64_t B, int64_t Tq, int64_t Tk,
+                  int64_t heads, int64_t dh, void* stream);
+
 /* ---- K12: VGG convolution stack primitives (forward only; the encoder is frozen,
  * encoders/imagenet_encoder.py:212,234) -----------------------------------------
  * NHWC fp32; 3x3, stride 1, SAME padding, + bias + ReLU (slim vgg_arg_scope);

@@ -365,6 +365,97 @@ __device__ __forceinline__ void epilogue_chunk_dense16(const TcEpilogue& e, cons
   store32_transposed(e.C, e.ldc, row, col0, M, ncols, x, e.beta);
 }
 
+// ---------------------------------------------------------------------------
+// TC_EPI_SOFTMAX / TC_EPI_DSOFTMAX: one thread owns one query row of one (sentence, head) problem; the whole
+// row of energies sits in this thread's TMEM lane (N <= BN), so the row reductions need no exchange - the lane
+// is simply read again for every pass (tensor memory is next to the SM).  Mask semantics of the reference
+// (scaled_dot_product.py:160-206): causal positions are REPLACED by -1e9, padded keys get x*m + (1-m)*(-1e9),
+// both before the softmax; dropout multiplies the softmax output (:208-214).
+template <int MODE>
+__device__ __forceinline__ void attn_epilogue(const TcEpilogue& e, const TcBatch& bt, uint32_t t_row, int r,
+                                              int M, int N, int o, int p, int64_t c_off) {
+  const int nchunks = (bt.n_pad + 31) >> 5;
+  const float* km = bt.key_mask ? bt.key_mask + (int64_t)o * N : nullptr;
+  const bool row_ok = r < M;
+  const float* dr = (bt.drop && row_ok) ? bt.drop + ((int64_t)p * M + r) * N : nullptr;
+  float* crow = e.C + c_off + (int64_t)r * e.ldc;
+  float v[32];
+  if (MODE == TC_EPI_SOFTMAX) {
+    auto energy = [&](float acc, int col) {
+      float x = acc * bt.scale;
+      if (bt.causal && col > r) x = -1e9f;
+      if (km) {
+        const float m = km[col];
+        x = x * m + (1.f - m) * -1e9f;
+      }
+      return x;
+    };
+    float mx = -INFINITY;
+    for (int c = 0; c < nchunks; ++c) {
+      tmem_ld32(t_row + (uint32_t)(c * 32), v);
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (c * 32 + j < N) mx = fmaxf(mx, energy(v[j], c * 32 + j));
+    }
+    float sum = 0.f;
+    for (int c = 0; c < nchunks; ++c) {
+      tmem_ld32(t_row + (uint32_t)(c * 32), v);
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (c * 32 + j < N) sum += expf(energy(v[j], c * 32 + j) - mx);
+    }
+    float* c2row = bt.C2 ? bt.C2 + c_off + (int64_t)r * e.ldc : nullptr;
+    for (int c = 0; c < nchunks; ++c) {
+      tmem_ld32(t_row + (uint32_t)(c * 32), v);
+      const int ncols = min(32, bt.n_pad - c * 32);
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const int col = c * 32 + j;
+        v[j] = (row_ok && col < N) ? expf(energy(v[j], col) - mx) / sum : 0.f;
+      }
+      if (r < bt.m_pad) store32(crow + c * 32, v, ncols, true);
+      if (c2row) {
+        if (dr) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (c * 32 + j < N) v[j] *= dr[c * 32 + j];
+        }
+        if (r < bt.m_pad) store32(c2row + c * 32, v, ncols, true);
+      }
+    }
+  } else {   // TC_EPI_DSOFTMAX: acc = d(dropped weights)
+    const float* prow = bt.P + c_off + (int64_t)r * e.ldc;
+    float dot = 0.f;
+    for (int c = 0; c < nchunks; ++c) {
+      tmem_ld32(t_row + (uint32_t)(c * 32), v);
+      if (row_ok) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const int col = c * 32 + j;
+          if (col < N) dot = fmaf(v[j] * (dr ? dr[col] : 1.f), prow[col], dot);
+        }
+      }
+    }
+    for (int c = 0; c < nchunks; ++c) {
+      tmem_ld32(t_row + (uint32_t)(c * 32), v);
+      const int ncols = min(32, bt.n_pad - c * 32);
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const int col = c * 32 + j;
+        float g = 0.f;
+        if (row_ok && col < N) {
+          g = prow[col] * (v[j] * (dr ? dr[col] : 1.f) - dot);
+          if (km) g *= km[col];                       // d(x*m + c)/dx = m
+          if (bt.causal && col > r) g = 0.f;          // tf.where: no gradient into replaced entries
+          g *= bt.scale;
+        }
+        v[j] = g;
+      }
+      if (r < bt.m_pad) store32(crow + c * 32, v, ncols, true);
+    }
+  }
+}
+
 // smem descriptor fields of an MN-major operand tile (bytes); a kernel argument so a
 // diagnostic run can probe them (NMB200_MN_* environment variables), fixed otherwise.
 struct MnDesc {
@@ -378,7 +469,7 @@ template <int BN, bool A_MN, bool B_MN, int MODE, int ESZ = 4, int CTAS = 1>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                int64_t M, int64_t N, int64_t K, TcEpilogue epi, MnDesc mn, int splits, int kb_per_split,
-               TcExt ext) {
+               TcExt ext, TcBatch bt) {
   static_assert(ESZ == 4 || !(A_MN || B_MN) || (BN % 64 == 0), "MN-major fp16 B tiles come in 64-column boxes");
   static_assert(ESZ == 2 || MODE != TC_EPI_XENT_BWD16, "the fp16 epilogue belongs to the fp16 instances");
   static_assert(CTAS == 1 || CTAS == 2, "one CTA or a CTA pair per tile");
@@ -409,7 +500,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   // split-K: the reduction is cut into `splits` slices, each an independent work item whose
   // epilogue adds its partial tile into C with red.global.add (weight-gradient products
   // have tiny outputs and very long K: without this only a handful of SMs would work)
-  const int64_t num_tiles = tiles_m * tiles_n * splits;
+  // batched: bt.count independent problems of this M x N x K, each a window of the operand tensors (no split-K)
+  const bool batched = bt.count > 0;
+  const int64_t tiles_per = tiles_m * tiles_n;
+  const int64_t num_tiles = batched ? tiles_per * bt.count : tiles_per * splits;
   const int num_kb_total = (int)((K + BK - 1) / BK);  // host guarantees no empty split
 
   if (threadIdx.x == 0) {
@@ -441,6 +535,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   __syncthreads();
   if constexpr (CTAS == 2) cluster_sync_all();   // the peer's barriers exist before anything arrives on them
   tcgen05_fence_after();
+  // Programmatic dependent launch (NMB200_TC_PDL): everything above - barriers, the TMEM allocation - touches no
+  // global memory and may run while the previous kernel of the stream drains; from here on its results are
+  // needed.  Without the launch attribute both instructions do nothing.
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   uint32_t tmem_base;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
@@ -452,8 +551,18 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       for (int64_t tile = worker; tile < num_tiles; tile += nworkers) {
         const int32_t m0 = (int32_t)((tile % tiles_m) * BM_T) + (int32_t)cta_rank * TC_BM;
         const int32_t n0 = (int32_t)(((tile / tiles_m) % tiles_n) * BN) + (int32_t)cta_rank * BN_LOAD;
-        const int kb_begin = (int)(tile / (tiles_m * tiles_n)) * kb_per_split;
-        const int kb_end = min(num_kb_total, kb_begin + kb_per_split);
+        int kb_begin = (int)(tile / tiles_per) * kb_per_split;
+        int kb_end = min(num_kb_total, kb_begin + kb_per_split);
+        int32_t a_row = 0, a_col = 0, b_row = 0, b_col = 0;   // this problem's operand windows
+        if (batched) {
+          const int prob = (int)(tile / tiles_per), o = prob / bt.inner, i = prob - o * bt.inner;
+          a_row = o * bt.a_row_outer + i * bt.a_row_inner;
+          a_col = i * bt.a_col_inner;
+          b_row = o * bt.b_row_outer + i * bt.b_row_inner;
+          b_col = i * bt.b_col_inner;
+          kb_begin = 0;
+          kb_end = num_kb_total;
+        }
         for (int kb = kb_begin; kb < kb_end; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1u);
           const uint32_t a_dst = smem_base + stage * Cfg::STAGE_BYTES;
@@ -471,18 +580,18 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           constexpr int MN_BOX = 128 / ESZ;
           constexpr int MN_BOX_BYTES = MN_BOX * BK * ESZ;
           if (!A_MN) {
-            tma_load(a_dst, &map_a, k0, m0);  // box {one k-block, 128 rows}
+            tma_load(a_dst, &map_a, k0 + a_col, m0 + a_row);  // box {one k-block, 128 rows}
           } else {
 #pragma unroll
             for (int j = 0; j < TC_BM / MN_BOX; ++j)
-              tma_load(a_dst + j * MN_BOX_BYTES, &map_a, m0 + MN_BOX * j, k0);
+              tma_load(a_dst + j * MN_BOX_BYTES, &map_a, m0 + a_col + MN_BOX * j, k0 + a_row);
           }
           if (!B_MN) {
-            tma_load(b_dst, &map_b, k0, n0);  // box {one k-block, BN (pair: BN/2) rows}
+            tma_load(b_dst, &map_b, k0 + b_col, n0 + b_row);  // box {one k-block, BN (pair: BN/2) rows}
           } else {
 #pragma unroll
             for (int j = 0; j < BN_LOAD / MN_BOX; ++j)
-              tma_load(b_dst + j * MN_BOX_BYTES, &map_b, n0 + MN_BOX * j, k0);
+              tma_load(b_dst + j * MN_BOX_BYTES, &map_b, n0 + b_col + MN_BOX * j, k0 + b_row);
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         }
@@ -506,8 +615,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
         tcgen05_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
-        const int kb_begin = (int)(tile / (tiles_m * tiles_n)) * kb_per_split;
-        const int num_kb = min(num_kb_total, kb_begin + kb_per_split) - kb_begin;
+        const int kb_begin = (int)(tile / tiles_per) * kb_per_split;
+        const int num_kb = batched ? num_kb_total : min(num_kb_total, kb_begin + kb_per_split) - kb_begin;
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(full_bar(stage), phase);
           tcgen05_fence_after();
@@ -565,8 +674,16 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       const int acc = (int)(it & 1);
       const uint32_t acc_phase = (uint32_t)((it >> 1) & 1);
       const int64_t tm = tile % tiles_m, tn = (tile / tiles_m) % tiles_n;
-      const int split = (int)(tile / (tiles_m * tiles_n));
+      const int split = batched ? 0 : (int)(tile / tiles_per);
       const int64_t row = tm * BM_T + (int64_t)cta_rank * TC_BM + quad * 32 + lane;
+      // batched: this problem's output window
+      int prob = 0, prob_o = 0;
+      int64_t c_off = 0;
+      if (batched) {
+        prob = (int)(tile / tiles_per);
+        prob_o = prob / bt.inner;
+        c_off = (int64_t)prob_o * bt.c_outer + (int64_t)(prob - prob_o * bt.inner) * bt.c_inner;
+      }
       mbar_wait(tfull_bar(acc), acc_phase);
       tcgen05_fence_after();
       RowStats st{-INFINITY, 0.f, -INFINITY, 0x7fffffff};
@@ -589,6 +706,13 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         if (ext.row_scale && row < M) factor16 *= ext.row_scale[row];
       }
       const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN);
+      if constexpr (MODE == TC_EPI_SOFTMAX || MODE == TC_EPI_DSOFTMAX) {
+        // whole rows per thread: the first warp of each lane quadrant does the tile (a handful of columns)
+        if (half == 0) attn_epilogue<MODE>(epi, bt, t_row, (int)row, (int)M, n32, prob_o, prob, c_off);
+      } else {
+      TcEpilogue epi_p = epi;               // this problem's window of C
+      if (batched) epi_p.C += c_off;
+      const TcEpilogue& epi = epi_p;
 #pragma unroll 1
       for (int c = half; c < BN / 32; c += 2) {
         float v[32];
@@ -607,6 +731,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           epilogue_chunk<MODE>(epi, v, row, (int)(tn * BN) + c * 32, M, n32, st, target, row_lse2,
                                row_w, vec_ok, stage, lane);
         }
+      }
       }
       if (MODE == TC_EPI_XENT_FWD && row < M)
         epi.part[(row * tiles_n + tn) * 2 + half] =
@@ -776,7 +901,7 @@ static int launch_pair(const CUtensorMap& ma, const CUtensorMap& mb, int64_t M, 
   }
   if (kb_per_split <= 0) kb_per_split = (int)ceil_div(K, TC_BK);
   return launch_pair_kernel(kern, Cfg::SMEM_BYTES, ceil_div(M, 2 * TC_BM) * ceil_div(N, BN) * splits, s, ma, mb, M,
-                            N, K, epi, mn_desc_config(), splits, kb_per_split, TcExt{});
+                            N, K, epi, mn_desc_config(), splits, kb_per_split, TcExt{}, TcBatch{});
 }
 
 template <int BN, int MODE, bool MN = false>
@@ -791,7 +916,36 @@ static int launch_pair16(const CUtensorMap& ma, const CUtensorMap& mb, int64_t M
   }
   return launch_pair_kernel(kern, Cfg::SMEM_BYTES, ceil_div(M, 2 * TC_BM) * ceil_div(N, BN), s, ma, mb, M, N, K, epi,
                             MN ? MnDesc{SMEM_LAYOUT_SW128, 1024, 8192, 2048} : MnDesc{0, 0, 0, 0}, 1,
-                            (int)ceil_div(K, 64), ext);
+                            (int)ceil_div(K, 64), ext, TcBatch{});
+}
+
+// NMB200_TC_PDL=1: launch with programmatic stream serialization, so that a kernel's prologue overlaps the tail of
+// its predecessor (the kernel waits with griddepcontrol.wait before it touches global memory)
+static bool pdl_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("NMB200_TC_PDL");
+    return e && atoi(e) != 0;
+  }();
+  return on;
+}
+
+template <class Kern, class... Args>
+static cudaError_t launch_one(Kern kern, unsigned grid, int smem_bytes, cudaStream_t s, Args... args) {
+  if (!pdl_enabled()) {
+    kern<<<grid, TC_THREADS, smem_bytes, s>>>(args...);
+    return cudaSuccess;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(TC_THREADS);
+  cfg.dynamicSmemBytes = (size_t)smem_bytes;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kern, args...);
 }
 
 template <int BN, bool A_MN, bool B_MN, int MODE>
@@ -807,8 +961,8 @@ static int launch_cfg(const CUtensorMap& ma, const CUtensorMap& mb, int64_t M, i
   const int64_t tiles = ceil_div(M, TC_BM) * ceil_div(N, BN) * splits;
   const int64_t grid = tiles < sm_count() ? tiles : sm_count();
   if (kb_per_split <= 0) kb_per_split = (int)ceil_div(K, TC_BK);
-  kern<<<(unsigned)grid, TC_THREADS, Cfg::SMEM_BYTES, s>>>(ma, mb, M, N, K, epi, mn_desc_config(),
-                                                           splits, kb_per_split, TcExt{});
+  NM_CUDA_TRY(launch_one(kern, (unsigned)grid, Cfg::SMEM_BYTES, s, ma, mb, M, N, K, epi, mn_desc_config(), splits,
+                         kb_per_split, TcExt{}, TcBatch{}));
   NM_LAUNCH_CHECK("tc_gemm_kernel");
   return NM_OK;
 }
@@ -827,9 +981,9 @@ static int launch_cfg16(const CUtensorMap& ma, const CUtensorMap& mb, int64_t M,
   }
   const int64_t tiles = ceil_div(M, TC_BM) * ceil_div(N, BN);
   const int64_t grid = tiles < sm_count() ? tiles : sm_count();
-  kern<<<(unsigned)grid, TC_THREADS, Cfg::SMEM_BYTES, s>>>(
-      ma, mb, M, N, K, epi, MN ? MnDesc{SMEM_LAYOUT_SW128, 1024, 8192, 2048} : MnDesc{0, 0, 0, 0}, 1,
-      (int)ceil_div(K, 64), ext);
+  NM_CUDA_TRY(launch_one(kern, (unsigned)grid, Cfg::SMEM_BYTES, s, ma, mb, M, N, K, epi,
+                         MN ? MnDesc{SMEM_LAYOUT_SW128, 1024, 8192, 2048} : MnDesc{0, 0, 0, 0}, 1,
+                         (int)ceil_div(K, 64), ext, TcBatch{}));
   NM_LAUNCH_CHECK("tc_gemm_kernel(fp16)");
   return NM_OK;
 }
@@ -852,6 +1006,60 @@ static int make_map16(CUtensorMap* map, const void* base, int64_t rows, int64_t 
              "tc_gemm16: cuTensorMapEncodeTiled failed (%d) rows=%lld cols=%lld ld=%lld", (int)r,
              (long long)rows, (long long)cols, (long long)ld);
   return NM_OK;
+}
+
+template <int BN, bool A_MN, bool B_MN, int MODE>
+static int launch_batched(const CUtensorMap& ma, const CUtensorMap& mb, int64_t M, int64_t N, int64_t K,
+                          const TcEpilogue& epi, const TcBatch& bt, cudaStream_t s) {
+  using Cfg = TcCfg<BN>;
+  auto kern = tc_gemm_kernel<BN, A_MN, B_MN, MODE>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    NM_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    attr_done = true;
+  }
+  const int64_t tiles = ceil_div(M, TC_BM) * ceil_div(N, BN) * bt.count;
+  const int64_t grid = tiles < sm_count() ? tiles : sm_count();
+  NM_CUDA_TRY(launch_one(kern, (unsigned)grid, Cfg::SMEM_BYTES, s, ma, mb, M, N, K, epi, mn_desc_config(), 1,
+                         (int)ceil_div(K, TC_BK), TcExt{}, bt));
+  NM_LAUNCH_CHECK("tc_gemm_kernel(batched)");
+  return NM_OK;
+}
+
+int tc_gemm_batched_launch(int transA, int transB, int64_t M, int64_t N, int64_t K, const float* A, int64_t a_rows,
+                           int64_t a_cols, int64_t lda, const float* B, int64_t b_rows, int64_t b_cols,
+                           int64_t ldb, const TcEpilogue& epi, const TcBatch& bt, cudaStream_t s) {
+  const bool a_mn = transA != 0, b_mn = transB == 0;
+  NM_REQUIRE(bt.count >= 1 && bt.inner >= 1 && bt.count % bt.inner == 0, NM_E_INVALID,
+             "tc_gemm_batched: %d problems do not split into groups of %d", bt.count, bt.inner);
+  NM_REQUIRE(M >= 1 && N >= 1 && K >= 1 && (lda & 3) == 0 && (ldb & 3) == 0 &&
+                 (reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(B) & 15) == 0,
+             NM_E_INVALID, "tc_gemm_batched: operands must be 16-byte aligned with 16-byte row pitches");
+  const bool attn = epi.mode == TC_EPI_SOFTMAX || epi.mode == TC_EPI_DSOFTMAX;
+  NM_REQUIRE(attn || epi.mode == TC_EPI_DENSE, NM_E_INVALID, "tc_gemm_batched: unsupported epilogue %d", epi.mode);
+  NM_REQUIRE(((bt.c_outer | bt.c_inner | epi.ldc) & 3) == 0 && (reinterpret_cast<uintptr_t>(epi.C) & 15) == 0,
+             NM_E_INVALID, "tc_gemm_batched: output windows must be 16-byte aligned");
+  const int bn = attn ? 128 : (N <= 64 ? 64 : 128);
+  NM_REQUIRE(!attn || (N <= 128 && bt.n_pad >= N && bt.n_pad <= 128 && bt.m_pad >= M && !a_mn && !b_mn),
+             NM_E_UNSUPPORTED, "tc_gemm_batched: attention epilogues take K-major operands and N <= 128 (N=%lld)",
+             (long long)N);
+  CUtensorMap ma, mb;
+  int rc;
+  if (!a_mn) rc = make_map(&ma, A, a_rows, a_cols, lda, TC_BK, TC_BM, false);
+  else       rc = make_map(&ma, A, a_rows, a_cols, lda, 32, TC_BK, true);
+  if (rc) return rc;
+  if (!b_mn) rc = make_map(&mb, B, b_rows, b_cols, ldb, TC_BK, (uint32_t)bn, false);
+  else       rc = make_map(&mb, B, b_rows, b_cols, ldb, 32, TC_BK, true);
+  if (rc) return rc;
+  if (epi.mode == TC_EPI_SOFTMAX) return launch_batched<128, false, false, TC_EPI_SOFTMAX>(ma, mb, M, N, K, epi, bt, s);
+  if (epi.mode == TC_EPI_DSOFTMAX) return launch_batched<128, false, false, TC_EPI_DSOFTMAX>(ma, mb, M, N, K, epi, bt, s);
+  NM_REQUIRE(b_mn, NM_E_UNSUPPORTED, "tc_gemm_batched: dense products take an MN-major B operand");
+  if (bn == 64) {
+    if (a_mn) return launch_batched<64, true, true, TC_EPI_DENSE>(ma, mb, M, N, K, epi, bt, s);
+    return launch_batched<64, false, true, TC_EPI_DENSE>(ma, mb, M, N, K, epi, bt, s);
+  }
+  if (a_mn) return launch_batched<128, true, true, TC_EPI_DENSE>(ma, mb, M, N, K, epi, bt, s);
+  return launch_batched<128, false, true, TC_EPI_DENSE>(ma, mb, M, N, K, epi, bt, s);
 }
 
 static int pick_bn(int64_t M, int64_t N, int64_t K) {

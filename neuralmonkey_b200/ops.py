@@ -7,6 +7,7 @@ may carry an ``nm_grad`` attribute (a view into the flat gradient arena of
 weight gradients straight into that arena (GEMM epilogue ``beta = 1``) and return
 ``None`` to autograd, so no torch kernels run on the weight-gradient path.
 """
+import os
 from typing import Optional, Tuple
 
 import torch
@@ -902,11 +903,63 @@ class _MHADrop(torch.autograd.Function):
         return dq, dk, dv, None, None, None, None
 
 
+class _MHATensorCore(torch.autograd.Function):
+    """The attention core as batched tcgen05 products (csrc/mha_tc.cu): softmax and its backward in the GEMM
+    epilogues, all (sentence, head) pairs in one launch per product.  TF32 operands."""
+
+    @staticmethod
+    def forward(ctx, q, k, v, key_mask, causal, heads, drop_mask):
+        bsz, tq, d = q.shape
+        tk = k.size(1)
+        q, k, v = q.contiguous(), k.contiguous(), v.contiguous()
+        mask_c = key_mask.contiguous() if key_mask is not None else None
+        drop_c = drop_mask.to(torch.float32).contiguous() if drop_mask is not None else None
+        tqp, tkp = (tq + 31) // 32 * 32, (tk + 31) // 32 * 32
+        out = torch.empty_like(q)
+        probs = torch.empty(bsz, heads, tqp, tkp, device=q.device, dtype=torch.float32)
+        probs_drop = torch.empty_like(probs) if drop_c is not None else None
+        call("nm_mha_tc_fwd", ptr(q), ptr(k), ptr(v), ptr(mask_c), int(causal), ptr(drop_c), ptr(out), ptr(probs),
+             ptr(probs_drop), bsz, tq, tk, heads, d // heads, lib.stream())
+        ctx.save_for_backward(q, k, v, mask_c, probs, probs_drop, drop_c)
+        ctx.cfg = (causal, heads)
+        weights = probs[:, :, :tq, :tk]
+        ctx.mark_non_differentiable(weights)
+        return out, weights
+
+    @staticmethod
+    def backward(ctx, dout, _dprobs):
+        q, k, v, mask, probs, probs_drop, drop_c = ctx.saved_tensors
+        causal, heads = ctx.cfg
+        bsz, tq, d = q.shape
+        tk = k.size(1)
+        dout = dout.contiguous()
+        dq, dk, dv = torch.empty_like(q), torch.empty_like(k), torch.empty_like(v)
+        work = torch.empty_like(probs)
+        call("nm_mha_tc_bwd", ptr(q), ptr(k), ptr(v), ptr(mask), int(causal), ptr(drop_c), ptr(probs),
+             ptr(probs_drop), ptr(dout), ptr(dq), ptr(dk), ptr(dv), ptr(work), bsz, tq, tk, heads, d // heads,
+             lib.stream())
+        return dq, dk, dv, None, None, None, None
+
+
+_MHA_TC_DEFAULT = "0"     # until verified on the GPU: opt-in with NMB200_MHA_TC=1
+
+
+def _mha_on_tensor_cores(bsz: int, tq: int, tk: int, heads: int, dh: int) -> bool:
+    """Tensor-core attention follows the GEMM backend ('simt' = the exact fp32 kernels everywhere); whole
+    sequences only - the single-query steps of the decoding loops stay on the row kernels.  NMB200_MHA_TC=0
+    switches it off."""
+    if _GEMM_BACKEND == lib.GEMM_SIMT or os.environ.get("NMB200_MHA_TC", _MHA_TC_DEFAULT) == "0" or tq < 8:
+        return False
+    return bool(lib.load().nm_mha_tc_supported(bsz, tq, tk, heads, dh))
+
+
 def mha_core(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, key_mask: Optional[torch.Tensor],
              causal: bool, heads: int, drop_mask: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor]:
     """softmax(mask(q/sqrt(dh) k^T)) v per head (attention/scaled_dot_product.py:184-214).  With
     `drop_mask` ([B, heads, Tq, Tk], 0 or 1/keep_prob) the context is (softmax * drop_mask) v; the
     returned weights are the undropped softmax."""
+    if q.is_cuda and _mha_on_tensor_cores(q.shape[0], q.shape[1], k.shape[1], heads, q.shape[2] // heads):
+        return _MHATensorCore.apply(q, k, v, key_mask, causal, heads, drop_mask)
     if drop_mask is not None:
         return _MHADrop.apply(q, k, v, key_mask, causal, heads, drop_mask)
     return _MHA.apply(q, k, v, key_mask, causal, heads)

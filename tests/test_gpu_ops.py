@@ -264,7 +264,11 @@ def test_mha_core_fwd_bwd(causal, use_mask, shape):
         lens = torch.tensor([tk, 3, 1][:bsz])
         mask = (torch.arange(tk).unsqueeze(0) < lens.unsqueeze(1)).float()
     qd, kd, vd = _leaf(q), _leaf(k), _leaf(v)
-    out, probs = ops.mha_core(qd, kd, vd, mask.cuda() if use_mask else None, causal, heads)
+    ops.set_gemm_backend("simt")          # the exact fp32 kernels (tensor-core attention: test_gpu_mha_tc.py)
+    try:
+        out, probs = ops.mha_core(qd, kd, vd, mask.cuda() if use_mask else None, causal, heads)
+    finally:
+        ops.set_gemm_backend("auto")
     q64, k64, v64 = (t.double().requires_grad_(True) for t in (q, k, v))
 
     def split(t):
