@@ -506,6 +506,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   const int64_t num_tiles = batched ? tiles_per * bt.count : tiles_per * splits;
   const int num_kb_total = (int)((K + BK - 1) / BK);  // host guarantees no empty split
 
+  if (threadIdx.x == 32) {   // descriptor fetch off the critical path of the first TMA load
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_a)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_b)) : "memory");
+  }
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(full_bar(s), 1);
