@@ -50,3 +50,26 @@ except Exception as e:
     print("bench pdl unreadable", e)
 PY
 du -sh gpurun_out
+# decoder step with the weights staged by 2-D TMA
+out=gpurun_out/call10
+timeout -k 10 600 python -m pytest tests/test_gpu_decode.py -m gpu -q -x -k "step_kernel" > "$out/decstep_tests.log" 2>&1
+echo "decoder step tests (both weight paths) exit $?" | tee -a "$out/summary.txt"
+tail -n 12 "$out/decstep_tests.log" | cut -c1-220
+NMB200_DECSTEP_WTMA=1 timeout -k 10 300 python tools/decstep_phases.py > "$out/phases_wtma.txt" 2> "$out/phases_wtma.log"
+echo "phases (staged weights) exit $?" | tee -a "$out/summary.txt"
+cat "$out/phases_wtma.txt"
+NMB200_DECSTEP_WTMA=1 timeout -k 10 600 python -m pytest tests/test_gpu_decode.py -m gpu -q > "$out/decode_tests_wtma.log" 2>&1
+echo "decode tests (staged weights) exit $?" | tee -a "$out/summary.txt"
+tail -n 5 "$out/decode_tests_wtma.log" | cut -c1-220
+NMB200_DECSTEP_WTMA=1 timeout -k 10 600 python bench_workloads.py rnn_decode --no-cpu > "$out/rnn_decode_wtma.json" 2> "$out/rnn_decode_wtma.log"
+echo "rnn_decode (staged weights) exit $?" | tee -a "$out/summary.txt"
+python - <<'PY'
+import json
+try:
+    d = [json.loads(l) for l in open("gpurun_out/call10/rnn_decode_wtma.json") if l.startswith("{")][-1]
+    for k in ("greedy", "beam8_batch", "beam8_latency"):
+        e = d[k]; print(k, round(e["us_per_step"], 1), "us/step", round(e["tokens_per_s"]), "tok/s", e.get("step_breakdown_us"))
+except Exception as e:
+    print("rnn_decode unreadable", e)
+PY
+du -sh gpurun_out
