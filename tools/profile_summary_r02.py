@@ -59,6 +59,34 @@ if os.path.exists(path):
         out.append("| `{}` | {} | {:.3f} | {:.1f}% | {:.1f} |".format(name[:110], n, us / 1e3, 100 * us / total, us / n))
     open("profiles/{}_launches.md".format(TAG), "w").write("\n".join(out) + "\n")
 
+# ---- launch list of the Transformer workload (newest call directory that has one) ---------------------------
+import glob
+cands = sorted(glob.glob("gpurun_out/call*/transformer_launches.csv"), key=os.path.getmtime)
+if cands:
+    lines = [l for l in open(cands[-1]) if not l.startswith("==")]
+    rows = []
+    for r in csv.DictReader(io.StringIO("".join(lines))):
+        if r.get("Metric Name") == "gpu__time_duration.sum":
+            rows.append((r["Kernel Name"], to_us(fnum(r["Metric Value"]), r["Metric Unit"])))
+    agg = collections.OrderedDict()
+    for name, us in rows:
+        a = agg.setdefault(re.sub(r"\(.*", "", name)[:110], [0, 0.0])
+        a[0] += 1
+        a[1] += us
+    total = sum(v[1] for v in agg.values())
+    env = ""
+    try:
+        env = open(os.path.join(os.path.dirname(cands[-1]), "transformer_env.txt")).read().strip()
+    except OSError:
+        pass
+    tdoc = ["# ncu launch list ({}): Transformer-base training steps (`bench_workloads.py transformer`) {}".format(TAG, env), "",
+            "{} launches captured (model build, warm-up and timed steps; the capture stops at its launch cap), {:.1f} ms of "
+            "kernel time; per-launch times are cold-cache and serialised, so read the SHARE.".format(len(rows), total / 1e3), "",
+            "| kernel | launches | total ms | share | avg us |", "|---|---|---|---|---|"]
+    for name, (n, us) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:32]:
+        tdoc.append("| `{}` | {} | {:.3f} | {:.1f}% | {:.1f} |".format(name, n, us / 1e3, 100 * us / total, us / n))
+    open("profiles/{}_transformer_launches.md".format(TAG), "w").write("\n".join(tdoc) + "\n")
+
 # ---- full captures ------------------------------------------------------------------------------------
 KEYS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
         "sm__throughput.avg.pct_of_peak_sustained_elapsed", "dram__throughput.avg.pct_of_peak_sustained_elapsed",
