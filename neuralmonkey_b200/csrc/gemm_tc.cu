@@ -371,21 +371,70 @@ __device__ __forceinline__ void epilogue_chunk_dense16(const TcEpilogue& e, cons
 // is simply read again for every pass (tensor memory is next to the SM).  Mask semantics of the reference
 // (scaled_dot_product.py:160-206): causal positions are REPLACED by -1e9, padded keys get x*m + (1-m)*(-1e9),
 // both before the softmax; dropout multiplies the softmax output (:208-214).
+//
+// Everything a row needs from memory - its slice of the dropout mask, of the saved softmax - and everything it
+// writes goes through the warp's staging tile, 32 rows x 32 columns at a time (the inverse of
+// store32_coalesced), so global memory sees full 128-byte row segments; the key mask of the sentence is copied
+// once per tile into the idle partner warp's staging tile.  (The first version read and wrote per-thread rows
+// element by element: 99 us per launch at the bench shape, six times the products themselves.)
+__device__ __forceinline__ void load32_coalesced(float* __restrict__ stage, const float* __restrict__ src,
+                                                 int64_t ld, int64_t row_base, int col0, int64_t M,
+                                                 float (&x)[32], int lane) {
+  float4* st4 = reinterpret_cast<float4*>(stage);
+  const int sub = lane >> 3, slot = lane & 7;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int r = 4 * i + sub;
+    const int64_t grow = row_base + r;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (grow < M) v = *reinterpret_cast<const float4*>(src + grow * ld + col0 + 4 * slot);
+    st4[r * 8 + (slot ^ (r & 7))] = v;
+  }
+  __syncwarp();
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float4 v = st4[lane * 8 + (j ^ (lane & 7))];
+    x[4 * j] = v.x; x[4 * j + 1] = v.y; x[4 * j + 2] = v.z; x[4 * j + 3] = v.w;
+  }
+  __syncwarp();
+}
+
 template <int MODE>
 __device__ __forceinline__ void attn_epilogue(const TcEpilogue& e, const TcBatch& bt, uint32_t t_row, int r,
-                                              int M, int N, int o, int p, int64_t c_off) {
-  const int nchunks = (bt.n_pad + 31) >> 5;
-  const float* km = bt.key_mask ? bt.key_mask + (int64_t)o * N : nullptr;
+                                              int M, int N, int o, int p, int64_t c_off,
+                                              float* __restrict__ stage, int lane) {
+  const int nchunks = bt.n_pad >> 5;                 // n_pad is a multiple of 32
+  float* km_s = stage + 4 * 1024;                    // the partner warp's tile (idle in these modes)
+  const bool has_km = bt.key_mask != nullptr;
+  if (has_km) {
+    const float* km = bt.key_mask + (int64_t)o * N;
+    for (int c = lane; c < nchunks * 32; c += 32) km_s[c] = c < N ? km[c] : 1.f;
+    __syncwarp();
+  }
   const bool row_ok = r < M;
-  const float* dr = (bt.drop && row_ok) ? bt.drop + ((int64_t)p * M + r) * N : nullptr;
-  float* crow = e.C + c_off + (int64_t)r * e.ldc;
+  const int64_t row_base = r - lane;
+  float* cbase = e.C + c_off;
+  const float* dbase = bt.drop ? bt.drop + (int64_t)p * M * N : nullptr;
+  const bool drop_vec = dbase && (N & 3) == 0 && (reinterpret_cast<uintptr_t>(dbase) & 15) == 0;
+  // this row's 32 entries of the dropout mask from column col0 (1 where there is no mask, 0 outside the matrix)
+  auto load_drop = [&](int col0, float (&d)[32]) {
+    if (!dbase) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) d[j] = 1.f;
+    } else if (drop_vec && col0 + 32 <= N) {
+      load32_coalesced(stage, dbase, N, row_base, col0, M, d, lane);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) d[j] = (row_ok && col0 + j < N) ? dbase[(int64_t)r * N + col0 + j] : 0.f;
+    }
+  };
   float v[32];
   if (MODE == TC_EPI_SOFTMAX) {
     auto energy = [&](float acc, int col) {
       float x = acc * bt.scale;
       if (bt.causal && col > r) x = -1e9f;
-      if (km) {
-        const float m = km[col];
+      if (has_km) {
+        const float m = km_s[col];
         x = x * m + (1.f - m) * -1e9f;
       }
       return x;
@@ -404,54 +453,46 @@ __device__ __forceinline__ void attn_epilogue(const TcEpilogue& e, const TcBatch
       for (int j = 0; j < 32; ++j)
         if (c * 32 + j < N) sum += expf(energy(v[j], c * 32 + j) - mx);
     }
-    float* c2row = bt.C2 ? bt.C2 + c_off + (int64_t)r * e.ldc : nullptr;
     for (int c = 0; c < nchunks; ++c) {
       tmem_ld32(t_row + (uint32_t)(c * 32), v);
-      const int ncols = min(32, bt.n_pad - c * 32);
 #pragma unroll
       for (int j = 0; j < 32; ++j) {
         const int col = c * 32 + j;
         v[j] = (row_ok && col < N) ? expf(energy(v[j], col) - mx) / sum : 0.f;
       }
-      if (r < bt.m_pad) store32(crow + c * 32, v, ncols, true);
-      if (c2row) {
-        if (dr) {
+      store32_coalesced(stage, cbase, e.ldc, row_base, c * 32, bt.m_pad, v, lane);   // padding rows: zeros
+      if (bt.C2) {
+        float d[32];
+        load_drop(c * 32, d);
 #pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (c * 32 + j < N) v[j] *= dr[c * 32 + j];
-        }
-        if (r < bt.m_pad) store32(c2row + c * 32, v, ncols, true);
+        for (int j = 0; j < 32; ++j) v[j] *= d[j];
+        store32_coalesced(stage, bt.C2 + c_off, e.ldc, row_base, c * 32, bt.m_pad, v, lane);
       }
     }
   } else {   // TC_EPI_DSOFTMAX: acc = d(dropped weights)
-    const float* prow = bt.P + c_off + (int64_t)r * e.ldc;
+    const float* pbase = bt.P + c_off;
+    float pr[32], d[32];
     float dot = 0.f;
     for (int c = 0; c < nchunks; ++c) {
       tmem_ld32(t_row + (uint32_t)(c * 32), v);
-      if (row_ok) {
+      load32_coalesced(stage, pbase, e.ldc, row_base, c * 32, M, pr, lane);   // zero beyond the rows / columns
+      load_drop(c * 32, d);
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const int col = c * 32 + j;
-          if (col < N) dot = fmaf(v[j] * (dr ? dr[col] : 1.f), prow[col], dot);
-        }
-      }
+      for (int j = 0; j < 32; ++j) dot = fmaf(v[j] * d[j], pr[j], dot);
     }
     for (int c = 0; c < nchunks; ++c) {
       tmem_ld32(t_row + (uint32_t)(c * 32), v);
-      const int ncols = min(32, bt.n_pad - c * 32);
+      load32_coalesced(stage, pbase, e.ldc, row_base, c * 32, M, pr, lane);
+      load_drop(c * 32, d);
 #pragma unroll
       for (int j = 0; j < 32; ++j) {
         const int col = c * 32 + j;
-        float g = 0.f;
-        if (row_ok && col < N) {
-          g = prow[col] * (v[j] * (dr ? dr[col] : 1.f) - dot);
-          if (km) g *= km[col];                       // d(x*m + c)/dx = m
-          if (bt.causal && col > r) g = 0.f;          // tf.where: no gradient into replaced entries
-          g *= bt.scale;
-        }
-        v[j] = g;
+        float g = pr[j] * (v[j] * d[j] - dot);             // pr = 0 in the padding: g = 0 there
+        if (has_km) g *= km_s[col];                         // d(x*m + c)/dx = m
+        if (bt.causal && col > r) g = 0.f;                  // tf.where: no gradient into replaced entries
+        v[j] = row_ok ? g * bt.scale : 0.f;
       }
-      if (r < bt.m_pad) store32(crow + c * 32, v, ncols, true);
+      store32_coalesced(stage, cbase, e.ldc, row_base, c * 32, bt.m_pad, v, lane);
     }
   }
 }
@@ -712,7 +753,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN);
       if constexpr (MODE == TC_EPI_SOFTMAX || MODE == TC_EPI_DSOFTMAX) {
         // whole rows per thread: the first warp of each lane quadrant does the tile (a handful of columns)
-        if (half == 0) attn_epilogue<MODE>(epi, bt, t_row, (int)row, (int)M, n32, prob_o, prob, c_off);
+        if (half == 0) attn_epilogue<MODE>(epi, bt, t_row, (int)row, (int)M, n32, prob_o, prob, c_off, stage, lane);
       } else {
       TcEpilogue epi_p = epi;               // this problem's window of C
       if (batched) epi_p.C += c_off;

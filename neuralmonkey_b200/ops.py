@@ -73,6 +73,49 @@ def _sink(t: torch.Tensor) -> Optional[torch.Tensor]:
     return getattr(t, "nm_grad", None)
 
 
+# -- weight gradients off the critical path ----------------------------------------------------------------
+# The backward pass is a chain: every layer's input gradient feeds the next (older) layer, while its WEIGHT
+# gradient feeds nothing until the optimizer runs.  A trainer may therefore open a window
+# (`weight_grad_stream(True)` ... `join_weight_grads()`) in which the weight / bias gradient products of the dense
+# layers and of the vocabulary projection are issued on a second stream: they fill the SMs the chain leaves idle
+# (launch latencies, short grids, the 120-CTA recurrences) instead of lengthening it.  Both streams only ever ADD
+# into disjoint parts of the flat gradient buffer: a variable's contributions all travel on the same stream.
+# Inside a CUDA-graph capture the fork and the join become graph edges.  Off unless a trainer opens the window
+# (NMB200_WGRAD_STREAM=0 keeps it shut).
+_wg = {"stream": None, "keep": [], "open": False}
+
+
+def weight_grad_stream(enable: bool) -> None:
+    if enable and os.environ.get("NMB200_WGRAD_STREAM", _WGRAD_STREAM_DEFAULT) != "1":
+        enable = False
+    if enable and _wg["stream"] is None:
+        _wg["stream"] = torch.cuda.Stream()
+    _wg["open"] = bool(enable)
+
+
+_WGRAD_STREAM_DEFAULT = "0"    # until measured on the GPU: NMB200_WGRAD_STREAM=1 opts in
+
+
+def join_weight_grads() -> None:
+    """The current stream waits for every weight gradient issued so far (and their operands may be freed)."""
+    if _wg["keep"]:
+        torch.cuda.current_stream().wait_stream(_wg["stream"])
+        del _wg["keep"][:]
+
+
+def _off_the_chain(fn, *operands) -> None:
+    """Run `fn` (kernels that only add into the gradient buffer) on the weight-gradient stream when a trainer
+    has opened the window, else right here.  `operands` are kept alive until the join."""
+    if not _wg["open"]:
+        fn()
+        return
+    side = _wg["stream"]
+    side.wait_stream(torch.cuda.current_stream())      # the operands were produced on the chain's stream
+    with torch.cuda.stream(side):
+        fn()
+    _wg["keep"].append(operands)
+
+
 def _weight_grad(a: torch.Tensor, b: torch.Tensor, trans_a: bool, trans_b: bool,
                  sink: Optional[torch.Tensor], shape) -> Optional[torch.Tensor]:
     """op(a) @ op(b) accumulated into `sink` (returns None) or returned as a new tensor."""
@@ -164,10 +207,19 @@ class _Linear(torch.autograd.Function):
             dx = torch.empty(x2.shape, device=dy.device, dtype=torch.float32)
             gemm(dpre, w, dx, trans_b=True)
             dx = dx.view(ctx.in_shape)
-        if ctx.needs_input_grad[1]:
-            dw = _weight_grad(x2, dpre, True, False, ctx.sinks[0], w.shape)
-        if ctx.has_bias and ctx.needs_input_grad[2]:
-            db = _bias_grad(dpre, ctx.sinks[1])
+        w_sink, b_sink = ctx.sinks
+        want_w, want_b = ctx.needs_input_grad[1], ctx.has_bias and ctx.needs_input_grad[2]
+        if (want_w and w_sink is not None) and (not want_b or b_sink is not None):
+            def into_the_buffer():      # both accumulate into the gradient buffer: nothing to return
+                _weight_grad(x2, dpre, True, False, w_sink, w.shape)
+                if want_b:
+                    _bias_grad(dpre, b_sink)
+            _off_the_chain(into_the_buffer, x2, dpre)
+            return dx, None, None, None
+        if want_w:
+            dw = _weight_grad(x2, dpre, True, False, w_sink, w.shape)
+        if want_b:
+            db = _bias_grad(dpre, b_sink)
         return dx, dw, db, None
 
 
@@ -718,8 +770,8 @@ class _LogitsXent16(torch.autograd.Function):
         xs16 = torch.empty(m, k1pad, device=dev, dtype=torch.float16)
         call("nm_cast_f16", ptr(x2), ldx, ptr(xs16), k1pad, m, k, ptr(upstream / smax), 0, 1, lib.stream())
         sink_aug = torch.as_strided(w_sink, (k + 1, v), (v, 1))
-        call("nm_gemm_f16_tn", k + 1, v, m, ptr(xs16), k1pad, ptr(dl16), vpad, ptr(sink_aug), v, ptr(smax),
-             1.0, lib.stream())
+        _off_the_chain(lambda: call("nm_gemm_f16_tn", k + 1, v, m, ptr(xs16), k1pad, ptr(dl16), vpad, ptr(sink_aug),
+                                    v, ptr(smax), 1.0, lib.stream()), xs16, dl16, smax, sink_aug)
         return dx, None, None, None, None, None, None
 
 

@@ -13,7 +13,7 @@ from typing import Any, Dict, List, Optional, Sequence, Set
 
 import torch
 
-from neuralmonkey_b200 import distributed, lib, runtime, tf
+from neuralmonkey_b200 import distributed, lib, ops, runtime, tf
 from neuralmonkey_b200.lib import call, ptr
 from neuralmonkey_b200.logging import warn
 from neuralmonkey_b200.model.feedable import Feedable
@@ -152,6 +152,7 @@ class GenericTrainer(GraphExecutor, Feedable):
                 self.early_exchanges = getattr(self, "early_exchanges", 0) + 1
                 # parameters used in plain torch expressions get their gradient in `.grad` (AccumulateGrad
                 # nodes run before any older node): move those into the flat buffer before it is exchanged
+                ops.join_weight_grads()            # the decoder-side weight gradients issued on the second stream
                 arena.fold_autograd_grads()
                 for lo, hi in early:
                     works.append(distributed.all_reduce_async(arena.grad_buffer[lo:hi]))
@@ -201,7 +202,12 @@ class GenericTrainer(GraphExecutor, Feedable):
             # optimizer kernel -> N ranks reproduce the single-GPU token mean exactly
             loss_sum, count = exact
             w = self.objectives[0].weight
-            (loss_sum if w is None else loss_sum * w).backward()
+            ops.weight_grad_stream(arena.params.is_cuda)
+            try:
+                (loss_sum if w is None else loss_sum * w).backward()
+            finally:
+                ops.join_weight_grads()
+                ops.weight_grad_stream(False)
             arena.fold_autograd_grads()
             arena.stats[0].copy_(loss_sum.detach())
             arena.stats[1].copy_(count.detach())
@@ -213,7 +219,12 @@ class GenericTrainer(GraphExecutor, Feedable):
             w = 1.0 if obj.weight is None else obj.weight
             term = obj.loss * w
             total = term if total is None else total + term
-        total.backward()
+        ops.weight_grad_stream(arena.params.is_cuda)
+        try:
+            total.backward()
+        finally:
+            ops.join_weight_grads()
+            ops.weight_grad_stream(False)
         arena.fold_autograd_grads()
         return {"exact": False}
 
