@@ -125,7 +125,7 @@ for rep, title in (("prof_tc_gemm", "tcgen05 GEMM, the kind::f16 instances (voca
     idx = _Idx({h: i for i, h in enumerate(header)})
     tens = [h for h in header if ("umma" in h or "tensor" in h) and "pct" in h]
     doc += ["## {} (`{}`)".format(title, rep), "",
-            "| kernel | us | DRAM rd MB | DRAM wr MB | DRAM % | SM % | tensor pipe % | grid x block | regs |",
+            "| kernel | us | DRAM rd MB | DRAM wr MB | DRAM % of measured peak | SM % | tensor pipe % | grid x block | regs |",
             "|---|---|---|---|---|---|---|---|---|"]
     groups = collections.OrderedDict()
     for row in data:
@@ -137,8 +137,8 @@ for rep, title in (("prof_tc_gemm", "tcgen05 GEMM, the kind::f16 instances (voca
         short = re.sub(r"\(.*", "", name)
         short = re.sub(r"\(int\)|\(bool\)", "", short)[:90]
         doc.append("| `{}` | {:.1f} | {:.1f} | {:.1f} | {} | {} | {:.1f} | {} x {} | {} |".format(
-            short, us, rd_b / 1e6, wr_b / 1e6, row[idx["dram__throughput.avg.pct_of_peak_sustained_elapsed"]],
-            row[idx["sm__throughput.avg.pct_of_peak_sustained_elapsed"]], tp, row[idx["launch__grid_size"]],
+            short, us, rd_b / 1e6, wr_b / 1e6, "{:.1f}".format(100.0 * (rd_b + wr_b) / max(us, 1e-9) / 1e3 / PEAK_HBM),
+            "{:.1f}".format(fnum(row[idx["sm__throughput.avg.pct_of_peak_sustained_elapsed"]])), tp, row[idx["launch__grid_size"]],
             row[idx["launch__block_size"]], row[idx["launch__registers_per_thread"]]))
         g = groups.setdefault(short, [0, 0.0, 0.0, 0.0])
         g[0] += 1; g[1] += us; g[2] += rd_b + wr_b; g[3] = max(g[3], tp if tp == tp else 0.0)
