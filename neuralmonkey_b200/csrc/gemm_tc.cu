@@ -62,6 +62,15 @@ struct RowStats {
 
 constexpr float TC_LOG2E = 1.4426950408889634f;
 
+// 2^x as ONE MUFU instruction.  exp2f() wraps the same MUFU.EX2 in a range fix for results below 2^-126
+// (compare, halve, square: three more issue slots per element in epilogues that run once per logit); here such
+// results flush to zero, which is what they contribute to a sum of probabilities anyway.
+__device__ __forceinline__ float fast_ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 __device__ __forceinline__ void load_bias32(const float* __restrict__ bias, int col0, int ncols,
                                             float (&b)[32]) {
   if (bias == nullptr) {
@@ -171,14 +180,14 @@ __device__ __forceinline__ void epilogue_chunk(const TcEpilogue& e, float (&x)[3
 #pragma unroll
       for (int j = 31; j >= 0; --j)
         if (x[j] == cmx) carg = j;  // lowest index among equals
-      st.sum *= exp2f((st.mx - cmx) * TC_LOG2E);
+      st.sum *= fast_ex2((st.mx - cmx) * TC_LOG2E);
       st.mx = cmx;
       st.arg = col0 + carg;
     }
     const float m2 = st.mx * TC_LOG2E;
     float s = 0.f;
 #pragma unroll
-    for (int j = 0; j < 32; ++j) s += exp2f(fmaf(x[j], TC_LOG2E, -m2));
+    for (int j = 0; j < 32; ++j) s += fast_ex2(fmaf(x[j], TC_LOG2E, -m2));
     st.sum += s;
     const int t_rel = target - col0;  // rare: the chunk holding this row's target
     if (t_rel >= 0 && t_rel < ncols) {
@@ -189,7 +198,7 @@ __device__ __forceinline__ void epilogue_chunk(const TcEpilogue& e, float (&x)[3
     if (e.C) store32(e.C + row * e.ldc + col0, x, ncols, vec_ok);
   } else {  // TC_EPI_XENT_BWD: (softmax - onehot) * row weight
 #pragma unroll
-    for (int j = 0; j < 32; ++j) x[j] = exp2f(fmaf(x[j], TC_LOG2E, -row_lse2)) * row_w;
+    for (int j = 0; j < 32; ++j) x[j] = fast_ex2(fmaf(x[j], TC_LOG2E, -row_lse2)) * row_w;
     const int t_rel = target - col0;
     if (t_rel >= 0 && t_rel < ncols) {
 #pragma unroll
@@ -323,7 +332,7 @@ __device__ __forceinline__ void epilogue_chunk_xent_bwd16(const TcEpilogue& e, c
       if (j == unk_rel) x[j] += -1e9f;
   }
 #pragma unroll
-  for (int j = 0; j < 32; ++j) x[j] = exp2f(fmaf(x[j], TC_LOG2E, -row_lse2)) * row_w;
+  for (int j = 0; j < 32; ++j) x[j] = fast_ex2(fmaf(x[j], TC_LOG2E, -row_lse2)) * row_w;
   const int t_rel = target - col0;
   if (t_rel >= 0 && t_rel < ncols) {
 #pragma unroll
