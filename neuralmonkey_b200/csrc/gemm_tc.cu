@@ -437,14 +437,23 @@ __device__ __forceinline__ void attn_epilogue(const TcEpilogue& e, const TcBatch
       for (int j = 0; j < 32; ++j) d[j] = (row_ok && col0 + j < N) ? dbase[(int64_t)r * N + col0 + j] : 0.f;
     }
   };
+  // the rows this tile will read from memory (dropout mask, saved softmax): on their way into L2 while the
+  // tensor-memory passes run
+  if (row_ok) {
+    if (dbase) asm volatile("prefetch.global.L2 [%0];" ::"l"(dbase + (int64_t)r * N) : "memory");
+    if (MODE == TC_EPI_DSOFTMAX) asm volatile("prefetch.global.L2 [%0];" ::"l"(bt.P + c_off + (int64_t)r * e.ldc) : "memory");
+  }
   float v[32];
   if (MODE == TC_EPI_SOFTMAX) {
+    // energies in units of log2: 2^(x*log2e - max) is ONE MUFU instruction (fast_ex2), the masks' -1e9 stays -1e9*log2e
+    const float sc2 = bt.scale * TC_LOG2E;
+    constexpr float MASKED2 = -1e9f * TC_LOG2E;
     auto energy = [&](float acc, int col) {
-      float x = acc * bt.scale;
-      if (bt.causal && col > r) x = -1e9f;
+      float x = acc * sc2;
+      if (bt.causal && col > r) x = MASKED2;
       if (has_km) {
         const float m = km_s[col];
-        x = x * m + (1.f - m) * -1e9f;
+        x = x * m + (1.f - m) * MASKED2;
       }
       return x;
     };
@@ -460,14 +469,15 @@ __device__ __forceinline__ void attn_epilogue(const TcEpilogue& e, const TcBatch
       tmem_ld32(t_row + (uint32_t)(c * 32), v);
 #pragma unroll
       for (int j = 0; j < 32; ++j)
-        if (c * 32 + j < N) sum += expf(energy(v[j], c * 32 + j) - mx);
+        if (c * 32 + j < N) sum += fast_ex2(energy(v[j], c * 32 + j) - mx);
     }
+    const float inv = 1.f / sum;
     for (int c = 0; c < nchunks; ++c) {
       tmem_ld32(t_row + (uint32_t)(c * 32), v);
 #pragma unroll
       for (int j = 0; j < 32; ++j) {
         const int col = c * 32 + j;
-        v[j] = (row_ok && col < N) ? expf(energy(v[j], col) - mx) / sum : 0.f;
+        v[j] = (row_ok && col < N) ? fast_ex2(energy(v[j], col) - mx) * inv : 0.f;
       }
       store32_coalesced(stage, cbase, e.ldc, row_base, c * 32, bt.m_pad, v, lane);   // padding rows: zeros
       if (bt.C2) {

@@ -6,6 +6,8 @@ out=gpurun_out/multi$N
 mkdir -p "$out"
 export PYTHONUNBUFFERED=1
 if [ "$N" = "2" ]; then
+  timeout 300 python -m pytest tests/test_gpu_mha_tc.py -m gpu -q > "$out/mha_tc.log" 2>&1
+  echo "mha tc tests exit $?" | tee -a "$out/summary.txt"
   timeout 900 python -m pytest tests/test_gpu_dp.py -m gpu -q -s > "$out/dp_tests.log" 2>&1
   echo "dp tests exit $?" | tee -a "$out/summary.txt"
 fi
