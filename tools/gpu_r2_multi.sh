@@ -16,8 +16,8 @@ for wl in ende transformer; do
       bench.py --gpus $N --steps 10 --warmup 3 --workload $wl > "$out/bench_${wl}_n$N.json" 2> "$out/bench_${wl}_n$N.log"
   echo "bench $wl N=$N exit $?" | tee -a "$out/summary.txt"
 done
-# the same two workloads on one GPU of the same box, for the ratio
-for wl in ende transformer; do
+# the same two workloads on one GPU of the same box, for the ratio (N = 2 only: a larger box is charged N times)
+[ "$N" = "2" ] && for wl in ende transformer; do
   timeout 600 python bench.py --gpus 1 --steps 10 --warmup 3 --workload $wl --no-extras --no-cpu-baseline > "$out/bench_${wl}_n1.json" 2> "$out/bench_${wl}_n1.log"
   echo "bench $wl N=1 exit $?" | tee -a "$out/summary.txt"
 done
@@ -27,9 +27,10 @@ import json, sys
 out, n = sys.argv[1], sys.argv[2]
 for wl in ("ende", "transformer"):
     try:
-        a = json.load(open("{}/bench_{}_n1.json".format(out, wl))); b = json.load(open("{}/bench_{}_n{}.json".format(out, wl, n)))
-        print(wl, "N=1", round(a["ms_per_step"], 3), "ms", round(a["value"]), "| N=" + n, round(b["ms_per_step"], 3), "ms", round(b["value"]),
-              "| speed-up", round(b["value"] / a["value"], 3), "exposed comm ms", b.get("exposed_comm_ms_per_step"))
+        b = json.load(open("{}/bench_{}_n{}.json".format(out, wl, n)))
+        print(wl, "N=" + n, round(b["ms_per_step"], 3), "ms", round(b["value"]), b["unit"], "exposed comm ms", b.get("exposed_comm_ms_per_step"))
+        a = json.load(open("{}/bench_{}_n1.json".format(out, wl)))
+        print("   N=1", round(a["ms_per_step"], 3), "ms", round(a["value"]), "| speed-up", round(b["value"] / a["value"], 3))
     except Exception as exc:
         print(wl, "failed:", exc)
 PY
