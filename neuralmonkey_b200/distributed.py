@@ -27,6 +27,32 @@ def init_from_env(backend: str = None) -> None:
     os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
     os.environ.setdefault("MASTER_PORT", "29500")
     dist.init_process_group(backend=backend)
+    import atexit
+    atexit.register(shutdown)
+
+
+_cleanups = []    # callables run by shutdown() before the process group goes away
+
+
+def register_cleanup(fn) -> None:
+    """Something that must be released before the communicator is destroyed - a trainer's CUDA graphs that
+    captured collectives: tearing NCCL down under them hangs the process at exit."""
+    if fn not in _cleanups:
+        _cleanups.append(fn)
+
+
+def shutdown() -> None:
+    """Release what was registered, drain the device, destroy the process group.  Registered with atexit by
+    `init_from_env`; idempotent."""
+    while _cleanups:
+        try:
+            _cleanups.pop()()
+        except Exception:  # pylint: disable=broad-except
+            pass
+    if is_initialized():
+        if torch.cuda.is_available():
+            torch.cuda.synchronize()
+        dist.destroy_process_group()
 
 
 def world_size() -> int:

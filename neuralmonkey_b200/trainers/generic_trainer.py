@@ -297,6 +297,8 @@ class GenericTrainer(GraphExecutor, Feedable):
                 self._graphs[key] = "failed"
                 return None
             entry = self._graphs[key] = (graph, static, graph2)
+            if distributed.world_size() > 1:
+                distributed.register_cleanup(self._graphs.clear)   # graphs that captured NCCL go before NCCL does
         graph, static, graph2 = entry
         for (_, d), st in zip(leaves, static):
             for k, t in d.items():

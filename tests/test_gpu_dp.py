@@ -39,7 +39,14 @@ if distributed.rank() == 0:
     torch.save({{"params": {{k: v.cpu() for k, v in model["arena"].state_dict().items()}}, "losses": losses,
                 "capture_exchange": trainer.capture_exchange,
                 "graphs": sum(1 for v in trainer._graphs.values() if isinstance(v, tuple))}}, {out!r} + str(world))
-print("rank", distributed.rank(), "done")
+print("rank", distributed.rank(), "done", flush=True)
+# leaving must not hang (CUDA graphs that captured collectives are released before the communicator); the timer
+# only keeps a regression from costing the whole test timeout - the test asserts the clean path was taken
+import threading
+threading.Timer(60.0, lambda: (print("forced exit", flush=True), os._exit(3))).start()
+distributed.shutdown()
+print("rank", distributed.rank(), "clean exit", flush=True)
+os._exit(0)
 """
 
 
@@ -56,6 +63,7 @@ def test_two_gpus_equal_one_gpu(tmp_path, graph):
            "--master-addr", "127.0.0.1", "--master-port", "29713", str(script)]
     res = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env, cwd=root)
     assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
+    assert res.stdout.count("clean exit") == 2 and "forced exit" not in res.stdout, res.stdout[-2000:]
     one, two = torch.load(str(tmp_path / "result1")), torch.load(str(tmp_path / "result2"))
     assert one["losses"] == pytest.approx(two["losses"], abs=2e-5)
     for name, want in one["params"].items():
