@@ -116,6 +116,31 @@ def _off_the_chain(fn, *operands) -> None:
     _wg["keep"].append(operands)
 
 
+def _gru_weight_grads(x2, hp2, rh2, dzg, dzc, wg, wc, e, sinks):
+    """Weight / bias gradients of one GRU direction (rows [:E] of the kernels from x, rows [E:] from the recurrent
+    operand).  With all four variables in the gradient buffer the six launches leave the backward chain
+    (`_off_the_chain`) and nothing is returned; otherwise (dWg, dbg, dWc, dbc) with None for buffered ones."""
+    sg, sbg, sc, sbc = sinks
+
+    def products(dwg, dwc, beta_g, beta_c):
+        gemm(x2, dzg, dwg[:e], trans_a=True, beta=beta_g)
+        gemm(hp2, dzg, dwg[e:], trans_a=True, beta=beta_g)
+        gemm(x2, dzc, dwc[:e], trans_a=True, beta=beta_c)
+        gemm(rh2, dzc, dwc[e:], trans_a=True, beta=beta_c)
+    if sg is not None and sbg is not None and sc is not None and sbc is not None:
+        def into_the_buffer():
+            products(sg, sc, 1.0, 1.0)
+            _bias_grad(dzg, sbg)
+            _bias_grad(dzc, sbc)
+        _off_the_chain(into_the_buffer, x2, hp2, rh2, dzg, dzc)
+        return None, None, None, None
+    dwg = sg if sg is not None else torch.empty_like(wg)
+    dwc = sc if sc is not None else torch.empty_like(wc)
+    products(dwg, dwc, 1.0 if sg is not None else 0.0, 1.0 if sc is not None else 0.0)
+    return (None if sg is not None else dwg, _bias_grad(dzg, sbg), None if sc is not None else dwc,
+            _bias_grad(dzc, sbc))
+
+
 def _weight_grad(a: torch.Tensor, b: torch.Tensor, trans_a: bool, trans_b: bool,
                  sink: Optional[torch.Tensor], shape) -> Optional[torch.Tensor]:
     """op(a) @ op(b) accumulated into `sink` (returns None) or returned as a new tensor."""
@@ -452,27 +477,15 @@ class _GRULayer(torch.autograd.Function):
              ptr(gates), ptr(hprev), ptr(dstates), ptr(draw), ptr(dfinal), ptr(dxproj), ptr(dh0),
              ptr(work), bsz, t, h, int(ctx.sm_budget), lib.stream())
         dzg, dzc = dxproj[:, :2 * h], dxproj[:, 2 * h:]
-        sg, sbg, sc, sbc = ctx.sinks
-        # weight gradients: rows [:E] from x, rows [E:] from the recurrent operand
-        dwg = sg if sg is not None else torch.empty_like(wg)
-        dwc = sc if sc is not None else torch.empty_like(wc)
-        beta = 1.0 if sg is not None else 0.0
-        hp2, rh2 = hprev.view(bsz * t, h), rh.view(bsz * t, h)
-        gemm(x2, dzg, dwg[:e], trans_a=True, beta=beta)
-        gemm(hp2, dzg, dwg[e:], trans_a=True, beta=beta)
-        beta = 1.0 if sc is not None else 0.0
-        gemm(x2, dzc, dwc[:e], trans_a=True, beta=beta)
-        gemm(rh2, dzc, dwc[e:], trans_a=True, beta=beta)
-        dbg = _bias_grad(dzg, sbg)
-        dbc = _bias_grad(dzc, sbc)
+        dwg, dbg, dwc, dbc = _gru_weight_grads(x2, hprev.view(bsz * t, h), rh.view(bsz * t, h), dzg, dzc, wg, wc, e,
+                                               ctx.sinks)
         dx = None
         if ctx.needs_input_grad[0]:
             dx = torch.empty(bsz * t, e, device=dev, dtype=torch.float32)
             gemm(dzg, wg[:e], dx, trans_b=True)
             gemm(dzc, wc[:e], dx, trans_b=True, beta=1.0)
             dx = dx.view(bsz, t, e)
-        return (dx, None if sg is not None else dwg, dbg, None if sc is not None else dwc, dbc,
-                dh0, None, None, None, None)
+        return (dx, dwg, dbg, dwc, dbc, dh0, None, None, None, None)
 
 
 def gru_layer(x: torch.Tensor, gates_kernel: torch.Tensor, gates_bias: torch.Tensor,
@@ -546,24 +559,12 @@ class _BiGRULayer(torch.autograd.Function):
         first = True
         for (wg, wc, hp, rh, dxp, sinks) in ((wg_f, wc_f, hp_f, rh_f, dxp_f, ctx.sinks[:4]),
                                              (wg_b, wc_b, hp_b, rh_b, dxp_b, ctx.sinks[4:])):
-            sg, sbg, sc, sbc = sinks
             dzg, dzc = dxp[:, :2 * h], dxp[:, 2 * h:]
-            dwg = sg if sg is not None else torch.empty_like(wg)
-            dwc = sc if sc is not None else torch.empty_like(wc)
-            hp2, rh2 = hp.view(bsz * t, h), rh.view(bsz * t, h)
-            beta = 1.0 if sg is not None else 0.0
-            gemm(x2, dzg, dwg[:e], trans_a=True, beta=beta)
-            gemm(hp2, dzg, dwg[e:], trans_a=True, beta=beta)
-            beta = 1.0 if sc is not None else 0.0
-            gemm(x2, dzc, dwc[:e], trans_a=True, beta=beta)
-            gemm(rh2, dzc, dwc[e:], trans_a=True, beta=beta)
-            dbg = _bias_grad(dzg, sbg)
-            dbc = _bias_grad(dzc, sbc)
-            if dx is not None:
+            if dx is not None:      # the chain first: the input gradient is what the older layers wait for
                 gemm(dzg, wg[:e], dx, trans_b=True, beta=0.0 if first else 1.0)
                 gemm(dzc, wc[:e], dx, trans_b=True, beta=1.0)
                 first = False
-            grads += [None if sg is not None else dwg, dbg, None if sc is not None else dwc, dbc]
+            grads += list(_gru_weight_grads(x2, hp.view(bsz * t, h), rh.view(bsz * t, h), dzg, dzc, wg, wc, e, sinks))
         return (dx.view(bsz, t, e) if dx is not None else None, None) + tuple(grads)
 
 
