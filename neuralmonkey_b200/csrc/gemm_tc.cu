@@ -185,10 +185,15 @@ __device__ __forceinline__ void epilogue_chunk(const TcEpilogue& e, float (&x)[3
       st.arg = col0 + carg;
     }
     const float m2 = st.mx * TC_LOG2E;
-    float s = 0.f;
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;   // four chains of 8 dependent adds instead of one of 32
 #pragma unroll
-    for (int j = 0; j < 32; ++j) s += fast_ex2(fmaf(x[j], TC_LOG2E, -m2));
-    st.sum += s;
+    for (int j = 0; j < 32; j += 4) {
+      s0 += fast_ex2(fmaf(x[j], TC_LOG2E, -m2));
+      s1 += fast_ex2(fmaf(x[j + 1], TC_LOG2E, -m2));
+      s2 += fast_ex2(fmaf(x[j + 2], TC_LOG2E, -m2));
+      s3 += fast_ex2(fmaf(x[j + 3], TC_LOG2E, -m2));
+    }
+    st.sum += (s0 + s1) + (s2 + s3);
     const int t_rel = target - col0;  // rare: the chunk holding this row's target
     if (t_rel >= 0 && t_rel < ncols) {
 #pragma unroll
