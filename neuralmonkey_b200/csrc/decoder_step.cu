@@ -36,7 +36,8 @@ namespace cg = cooperative_groups;
 
 namespace nm {
 
-constexpr int DS_R = 8;          // rows per cluster
+constexpr int DS_R = 8;          // rows per cluster (the default; DS_R_MAX with NMB200_DECSTEP_ROWS=16)
+constexpr int DS_R_MAX = 16;     // 16 rows per cluster: every weight byte a cluster pulls from L2 feeds twice the rows
 constexpr int DS_THREADS = 512;
 constexpr int DS_WARPS = DS_THREADS / 32;
 constexpr int DS_UNROLL = 8;     // weight rows in flight per thread
@@ -44,11 +45,13 @@ constexpr int DS_SLOTS = 4;      // TMA ring depth
 constexpr int DS_RED_FLOATS = 128 * 32;   // K-split scratch of ds_panel: up to 128 partial sums of 32 floats
 constexpr int DS_WSLOTS = 4;     // weight-tile ring depth (weights staged by 2-D TMA)
 constexpr int DS_WKT = 32;       // weight rows (k) per staged tile
-constexpr int DS_WTMA_DEFAULT = 0;   // until verified on the GPU: NMB200_DECSTEP_WTMA=1 opts in
+constexpr int DS_WTMA_DEFAULT = 0;   // measured slower than the 16-byte loads: NMB200_DECSTEP_WTMA=1 opts in
+constexpr int DS_ROWS_DEFAULT = 8;   // until measured on the GPU: NMB200_DECSTEP_ROWS=16 opts in
 
 struct DecStep {
   int rows, E, H, A, C, Tx, O, group, act, maxout;
   int cl;            // cluster size
+  int R;             // rows (hypotheses) per cluster: 8 or 16
   int tck, tcv;      // time steps per staged keys / values tile (TMA path)
   int slot_floats;   // floats per ring slot (TMA path)
   const int64_t* symbols;
@@ -78,20 +81,20 @@ __host__ __device__ inline int ds_align4(int x) { return (x + 3) & ~3; }
 
 __host__ __device__ inline DsLayout ds_layout(const DecStep& p, bool tma) {
   DsLayout L;
-  const int rpc = DS_R / p.cl;
+  const int rpc = p.R / p.cl;
   int maxn = 2 * p.H;
   if (p.A > maxn) maxn = p.A;
   const int no = (p.maxout ? 2 : 1) * p.O;
   if (no > maxn) maxn = no;
   L.res_ld = ds_align4((maxn + p.cl - 1) / p.cl + 16);
   int o = 0;
-  L.xT = o;   o += ds_align4(p.E * DS_R);
-  L.hT = o;   o += ds_align4(p.H * DS_R);
-  L.rhT = o;  o += ds_align4(p.H * DS_R);
-  L.hnT = o;  o += ds_align4(p.H * DS_R);
-  L.ctxT = o; o += ds_align4(p.C * DS_R);
-  L.ug = o;   o += ds_align4(DS_R * ((p.H + p.cl - 1) / p.cl + 8));
-  L.res = o;  o += DS_R * L.res_ld;
+  L.xT = o;   o += ds_align4(p.E * p.R);
+  L.hT = o;   o += ds_align4(p.H * p.R);
+  L.rhT = o;  o += ds_align4(p.H * p.R);
+  L.hnT = o;  o += ds_align4(p.H * p.R);
+  L.ctxT = o; o += ds_align4(p.C * p.R);
+  L.ug = o;   o += ds_align4(p.R * ((p.H + p.cl - 1) / p.cl + 8));
+  L.res = o;  o += p.R * L.res_ld;
   L.red = o;  o += DS_RED_FLOATS;
   L.qs = o;   o += ds_align4(rpc * p.A);
   L.es = o;   o += ds_align4(rpc * p.Tx);
@@ -161,12 +164,13 @@ __device__ __forceinline__ float4 lds128(uint32_t addr) {
   return v;
 }
 
-template <int G>
+template <int G, int R>
 __device__ __noinline__ void ds_panel(const DsSeg* segs, int nseg, int K, const float* __restrict__ W,
                                       int ldw, int colA, int nA, int colB, int nB,
                                       float* __restrict__ res, int res_ld, float* __restrict__ red) {
   const int ng = nA + nB;
-  constexpr int RG = DS_R * G;
+  constexpr int RG = R * G;
+  constexpr int UN = R > 8 ? DS_UNROLL / 2 : DS_UNROLL;   // weight rows in flight per thread
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   // groups per warp: the choice that keeps most warps busy (38 groups: gw = 8 -> 5 quads x 3 warps; gw = 4
   // would leave 6 of 16 warps idle and every busy lane with twice the k range)
@@ -194,9 +198,9 @@ __device__ __noinline__ void ds_panel(const DsSeg* segs, int nseg, int K, const 
     const int kper = (K + kslices - 1) / kslices;
     const int k0 = min(K, (ws * DS_KSL + ksl) * kper);
     const int k1 = min(K, k0 + kper);
-    float acc[DS_R][G];
+    float acc[R][G];
 #pragma unroll
-    for (int r = 0; r < DS_R; ++r)
+    for (int r = 0; r < R; ++r)
 #pragma unroll
       for (int c = 0; c < G; ++c) acc[r][c] = 0.f;
     if (active) {
@@ -207,14 +211,14 @@ __device__ __noinline__ void ds_panel(const DsSeg* segs, int nseg, int K, const 
         const int lo = max(k0, start), hi = min(k1, start + len);
         if (lo < hi) {
           const float* wp = W + (int64_t)lo * ldw + col;
-          uint32_t ip = smem_u32(segs[s].inT) + (uint32_t)(lo - start) * DS_R * 4u;
+          uint32_t ip = smem_u32(segs[s].inT) + (uint32_t)(lo - start) * R * 4u;
           // batches of DS_UNROLL weight rows: all loads of a batch are in flight together; the last,
           // partial batch is predicated instead of falling back to one dependent load per row
 #pragma unroll 1
-          for (int k = lo; k < hi; k += DS_UNROLL) {
-            float w[DS_UNROLL][G];
+          for (int k = lo; k < hi; k += UN) {
+            float w[UN][G];
 #pragma unroll
-            for (int u = 0; u < DS_UNROLL; ++u) {
+            for (int u = 0; u < UN; ++u) {
               if (k + u < hi) {
                 if constexpr (G == 4) {
                   const float4 t = ldg_weight4(wp + (int64_t)u * ldw, wpolicy);
@@ -228,19 +232,22 @@ __device__ __noinline__ void ds_panel(const DsSeg* segs, int nseg, int K, const 
               }
             }
 #pragma unroll
-            for (int u = 0; u < DS_UNROLL; ++u) {
+            for (int u = 0; u < UN; ++u) {
               if (k + u < hi) {
-                const float4 i0 = lds128(ip + u * DS_R * 4);
-                const float4 i1 = lds128(ip + u * DS_R * 4 + 16);
-                const float in[DS_R] = {i0.x, i0.y, i0.z, i0.w, i1.x, i1.y, i1.z, i1.w};
+                float in[R];
 #pragma unroll
-                for (int r = 0; r < DS_R; ++r)
+                for (int q = 0; q < R / 4; ++q) {
+                  const float4 t4 = lds128(ip + u * R * 4 + 16 * q);
+                  in[4 * q] = t4.x; in[4 * q + 1] = t4.y; in[4 * q + 2] = t4.z; in[4 * q + 3] = t4.w;
+                }
+#pragma unroll
+                for (int r = 0; r < R; ++r)
 #pragma unroll
                   for (int c = 0; c < G; ++c) acc[r][c] = fmaf(in[r], w[u][c], acc[r][c]);
               }
             }
-            wp += (int64_t)DS_UNROLL * ldw;
-            ip += DS_UNROLL * DS_R * 4;
+            wp += (int64_t)UN * ldw;
+            ip += UN * R * 4;
           }
         }
         start += len;
@@ -251,7 +258,7 @@ __device__ __noinline__ void ds_panel(const DsSeg* segs, int nseg, int K, const 
     for (int off = 2; off < 32; off <<= 1) {
       if (off >= DS_GW) {        // warp-uniform
 #pragma unroll
-        for (int r = 0; r < DS_R; ++r)
+        for (int r = 0; r < R; ++r)
 #pragma unroll
           for (int c = 0; c < G; ++c) acc[r][c] += __shfl_xor_sync(0xffffffffu, acc[r][c], off);
       }
@@ -259,7 +266,7 @@ __device__ __noinline__ void ds_panel(const DsSeg* segs, int nseg, int K, const 
     if (wsplit == 1) {
       if (active && ksl == 0) {
 #pragma unroll
-        for (int r = 0; r < DS_R; ++r)
+        for (int r = 0; r < R; ++r)
 #pragma unroll
           for (int c = 0; c < G; ++c) res[r * res_ld + gg * G + c] = acc[r][c];
       }
@@ -269,7 +276,7 @@ __device__ __noinline__ void ds_panel(const DsSeg* segs, int nseg, int K, const 
       if (ws < wsplit && ksl == 0) {
         const int slot = ws * nq * DS_GW + quad * DS_GW + gl;
 #pragma unroll
-        for (int r = 0; r < DS_R; ++r)
+        for (int r = 0; r < R; ++r)
 #pragma unroll
           for (int c = 0; c < G; ++c) red[(r * G + c) * S + slot] = acc[r][c];
       }
@@ -446,18 +453,19 @@ __device__ __forceinline__ void ds_slice(int total, int cl, int rank, int& first
 // (a thread of the context pass owns one (row, column group) pair).  Computed by thread 0 into shared memory.
 struct DsRuns {
   int n;
-  int e[DS_R], first[DS_R], cnt[DS_R];
+  int e[DS_R_MAX], first[DS_R_MAX], cnt[DS_R_MAX];
 };
 
-template <int G, bool WT>
+template <int G, bool WT, int R>
 __global__ void __launch_bounds__(DS_THREADS, 1) attn_decoder_step_kernel(const __grid_constant__ DecStep p) {
   static_assert(!WT || G == 4, "staged weights need the 16-byte path");
+  static_assert(R == 8 || (R == DS_R_MAX && G == 4 && !WT), "16 rows per cluster: vector path, weights from L2");
   constexpr bool TMA = (G == 4);
   cg::cluster_group cluster = cg::this_cluster();
   const int CL = p.cl;
   const int rank = (int)cluster.block_rank();
-  const int row0 = (int)(blockIdx.x / CL) * DS_R;
-  const int rpc = DS_R / CL;                   // rows this CTA attends for
+  const int row0 = (int)(blockIdx.x / CL) * R;
+  const int rpc = R / CL;                   // rows this CTA attends for
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const DsLayout L = ds_layout(p, TMA);
 
@@ -486,7 +494,7 @@ __global__ void __launch_bounds__(DS_THREADS, 1) attn_decoder_step_kernel(const 
   const int nk = TMA ? (p.Tx + p.tck - 1) / p.tck : 1;    // tiles per run: keys, then values
   const int nv = TMA ? (p.Tx + p.tcv - 1) / p.tcv : 1;
   const int ncg = (p.C + G - 1) / G;                      // context column groups (host: <= DS_THREADS)
-  const int jt = min(DS_R, DS_THREADS / ncg);             // rows per run
+  const int jt = min(R, DS_THREADS / ncg);             // rows per run
 
   // tile i of this CTA's schedule (run-major: the key tiles of a run, then its value tiles)
   auto issue_tile = [&](int i) {   // one thread
@@ -561,7 +569,7 @@ __global__ void __launch_bounds__(DS_THREADS, 1) attn_decoder_step_kernel(const 
   // lane -> (row = lane & 7, k offset = lane >> 3): the stores walk shared memory linearly (no bank
   // conflicts); the global side reads 16 contiguous bytes of each of the 8 rows per warp instruction
   {
-    const int r = lane & (DS_R - 1);
+    const int r = lane & (R - 1);
     const int grow = row0 + r;
     const bool ok = grow < p.rows;
     const float* xsrc = nullptr;
@@ -572,13 +580,13 @@ __global__ void __launch_bounds__(DS_THREADS, 1) attn_decoder_step_kernel(const 
       hsrc = p.h_prev + (int64_t)src * p.H;
     }
 #pragma unroll 1
-    for (int k = tid >> 3; k < p.E; k += DS_THREADS / DS_R) {
+    for (int k = tid / R; k < p.E; k += DS_THREADS / R) {
       const float val = ok ? xsrc[k] : 0.f;
       if (ok && p.x_out && rank == 0) p.x_out[(int64_t)grow * p.E + k] = val;
-      xT[k * DS_R + r] = val;
+      xT[k * R + r] = val;
     }
 #pragma unroll 1
-    for (int k = tid >> 3; k < p.H; k += DS_THREADS / DS_R) hT[k * DS_R + r] = ok ? hsrc[k] : 0.f;
+    for (int k = tid / R; k < p.H; k += DS_THREADS / R) hT[k * R + r] = ok ? hsrc[k] : 0.f;
   }
 #pragma unroll 1
   for (int a = tid; a < p.A; a += DS_THREADS) vs[a] = p.v[a];
@@ -588,8 +596,8 @@ __global__ void __launch_bounds__(DS_THREADS, 1) attn_decoder_step_kernel(const 
   cluster.sync();   // every CTA of the cluster has started: its shared memory may be written remotely
   if (prof) p.prof[1] = clock64();
 
-  const int r_w = warp & (DS_R - 1), half_w = warp / DS_R;   // element-wise passes: warp -> (row, half)
-  constexpr int NHALF = DS_WARPS / DS_R;
+  const int r_w = warp & (R - 1), half_w = warp / R;   // element-wise passes: warp -> (row, half)
+  constexpr int NHALF = DS_WARPS / R;
 
   // ---- phase 1: gates of this CTA's hidden units -------------------------------------------------
   int uf, un;   // first unit group / number of unit groups
@@ -599,16 +607,16 @@ __global__ void __launch_bounds__(DS_THREADS, 1) attn_decoder_step_kernel(const 
   {
     const DsSeg segs[2] = {{xT, p.E}, {hT, p.H}};
     if constexpr (WT) ds_panel_w(p, wsched, 0, segs, 2, un, un, res, res_ld, red, wring, wbar);
-    else ds_panel<G>(segs, 2, p.E + p.H, p.Wg, 2 * p.H, u0, un, p.H + u0, un, res, res_ld, red);
+    else ds_panel<G, R>(segs, 2, p.E + p.H, p.Wg, 2 * p.H, u0, un, p.H + u0, un, res, res_ld, red);
 #pragma unroll 1
     for (int ul = lane + 32 * half_w; ul < nu; ul += 32 * NHALF) {
       const int r = r_w, u = u0 + ul;
       const float rr = sigmoidf_(res[r * res_ld + ul] + p.bg[u]);
       const float uu = sigmoidf_(res[r * res_ld + un * G + ul] + p.bg[p.H + u]);
       ugs[r * nu + ul] = uu;
-      const float rh = rr * hT[u * DS_R + r];
+      const float rh = rr * hT[u * R + r];
 #pragma unroll 1
-      for (int c = 0; c < CL; ++c) cluster.map_shared_rank(rhT, c)[u * DS_R + r] = rh;
+      for (int c = 0; c < CL; ++c) cluster.map_shared_rank(rhT, c)[u * R + r] = rh;
     }
   }
   cluster.sync();
@@ -618,15 +626,15 @@ __global__ void __launch_bounds__(DS_THREADS, 1) attn_decoder_step_kernel(const 
   {
     const DsSeg segs[2] = {{xT, p.E}, {rhT, p.H}};
     if constexpr (WT) ds_panel_w(p, wsched, 1, segs, 2, un, 0, res, res_ld, red, wring, wbar);
-    else ds_panel<G>(segs, 2, p.E + p.H, p.Wc, p.H, u0, un, 0, 0, res, res_ld, red);
+    else ds_panel<G, R>(segs, 2, p.E + p.H, p.Wc, p.H, u0, un, 0, 0, res, res_ld, red);
 #pragma unroll 1
     for (int ul = lane + 32 * half_w; ul < nu; ul += 32 * NHALF) {
       const int r = r_w, u = u0 + ul;
       const float c = tanhf(res[r * res_ld + ul] + p.bc[u]);
       const float uu = ugs[r * nu + ul];
-      const float hn = uu * hT[u * DS_R + r] + (1.f - uu) * c;
+      const float hn = uu * hT[u * R + r] + (1.f - uu) * c;
 #pragma unroll 1
-      for (int cc = 0; cc < CL; ++cc) cluster.map_shared_rank(hnT, cc)[u * DS_R + r] = hn;
+      for (int cc = 0; cc < CL; ++cc) cluster.map_shared_rank(hnT, cc)[u * R + r] = hn;
       if (row0 + r < p.rows) p.h_out[(int64_t)(row0 + r) * p.H + u] = hn;
     }
   }
@@ -641,7 +649,7 @@ __global__ void __launch_bounds__(DS_THREADS, 1) attn_decoder_step_kernel(const 
     const int na = min(p.A, a0 + an * G) - a0;
     const DsSeg segs[1] = {{hnT, p.H}};
     if constexpr (WT) ds_panel_w(p, wsched, 2, segs, 1, an, 0, res, res_ld, red, wring, wbar);
-    else ds_panel<G>(segs, 1, p.H, p.Wq, p.A, a0, an, 0, 0, res, res_ld, red);
+    else ds_panel<G, R>(segs, 1, p.H, p.Wq, p.A, a0, an, 0, 0, res, res_ld, red);
     float* qdst = cluster.map_shared_rank(qs, r_w / rpc) + (r_w % rpc) * p.A;
 #pragma unroll 1
     for (int al = lane + 32 * half_w; al < na; al += 32 * NHALF)
@@ -777,7 +785,7 @@ __global__ void __launch_bounds__(DS_THREADS, 1) attn_decoder_step_kernel(const 
           const int col = cgi * G + c;
           if (col < p.C) {
 #pragma unroll 1
-            for (int cc = 0; cc < CL; ++cc) cluster.map_shared_rank(ctxT, cc)[col * DS_R + rl] = cacc[c];
+            for (int cc = 0; cc < CL; ++cc) cluster.map_shared_rank(ctxT, cc)[col * R + rl] = cacc[c];
             if (p.ctx_out) p.ctx_out[(int64_t)(my0 + j0 + cj) * p.C + col] = cacc[c];
           }
         }
@@ -790,7 +798,7 @@ __global__ void __launch_bounds__(DS_THREADS, 1) attn_decoder_step_kernel(const 
 #pragma unroll 1
       for (int col = tid; col < p.C; col += DS_THREADS)
 #pragma unroll 1
-        for (int cc = 0; cc < CL; ++cc) cluster.map_shared_rank(ctxT, cc)[col * DS_R + rl] = 0.f;
+        for (int cc = 0; cc < CL; ++cc) cluster.map_shared_rank(ctxT, cc)[col * R + rl] = 0.f;
     }
   }
   if (prof) p.prof[5] = clock64();
@@ -806,7 +814,7 @@ __global__ void __launch_bounds__(DS_THREADS, 1) attn_decoder_step_kernel(const 
     const DsSeg segs[3] = {{hnT, p.H}, {xT, p.E}, {ctxT, p.C}};
     const int ldo = (p.maxout ? 2 : 1) * p.O;
     if constexpr (WT) ds_panel_w(p, wsched, 3, segs, 3, on, p.maxout ? on : 0, res, res_ld, red, wring, wbar);
-    else ds_panel<G>(segs, 3, p.H + p.E + p.C, p.Wo, ldo, o0, on, p.O + o0, p.maxout ? on : 0, res, res_ld, red);
+    else ds_panel<G, R>(segs, 3, p.H + p.E + p.C, p.Wo, ldo, o0, on, p.O + o0, p.maxout ? on : 0, res, res_ld, red);
     if (row0 + r_w < p.rows) {
 #pragma unroll 1
       for (int ol = lane + 32 * half_w; ol < no; ol += 32 * NHALF) {
@@ -831,6 +839,7 @@ using namespace nm;
 
 static long long* g_decstep_prof = nullptr;
 static int g_decstep_staging = -1;   // nm_attn_decoder_step_set_staging
+static int g_decstep_rows = -1;      // nm_attn_decoder_step_set_rows
 
 // 2-D tensor map of a row-major fp32 weight matrix [rows, cols]: box = {box_cols, DS_WKT rows}, no swizzle,
 // out-of-range elements read as zeros.  Encoded once per (matrix, box) and kept: the weights of a model do not move.
@@ -894,6 +903,12 @@ int nm_attn_decoder_step_set_staging(int mode) {
   return NM_OK;
 }
 
+int nm_attn_decoder_step_set_rows(int rows) {
+  NM_REQUIRE(rows == -1 || rows == 8 || rows == 16, NM_E_INVALID, "nm_attn_decoder_step_set_rows: -1, 8 or 16");
+  g_decstep_rows = rows;
+  return NM_OK;
+}
+
 int nm_attn_decoder_step_fwd(const int64_t* symbols, const float* emb_table, const float* x_in,
                              const float* h_prev, const int32_t* parent, const float* Wg, const float* bg,
                              const float* Wc, const float* bc, const float* Wq, const float* bq,
@@ -928,8 +943,16 @@ int nm_attn_decoder_step_fwd(const int64_t* symbols, const float* emb_table, con
   NM_REQUIRE(ceil_div(C, g) <= DS_THREADS, NM_E_UNSUPPORTED,
              "nm_attn_decoder_step_fwd: context size %lld too large for one CTA", (long long)C);
 
+  // rows per cluster: 16 halves the number of clusters that re-read the weights (NMB200_DECSTEP_ROWS=8|16)
+  static const int rows_env = [] {
+    const char* e = getenv("NMB200_DECSTEP_ROWS");
+    const int v = (e && *e) ? atoi(e) : DS_ROWS_DEFAULT;
+    return v == 16 ? 16 : 8;
+  }();
+  const int rows_mode = g_decstep_rows > 0 ? g_decstep_rows : rows_env;
+  p.R = (vec && rows_mode == 16 && rows > DS_R) ? DS_R_MAX : DS_R;
   // cluster size: as many CTAs as fill the chip, at most 8, at least one attended row per CTA
-  const int64_t clusters = ceil_div(rows, DS_R);
+  const int64_t clusters = ceil_div(rows, p.R);
   int cl = 8;
   while (cl > 1 && clusters * cl > (int64_t)sm_count()) cl >>= 1;
   const char* env = getenv("NMB200_DECSTEP_CLUSTER");
@@ -944,7 +967,7 @@ int nm_attn_decoder_step_fwd(const int64_t* symbols, const float* emb_table, con
     const char* e = getenv("NMB200_DECSTEP_WTMA");
     return (e && *e) ? atoi(e) : DS_WTMA_DEFAULT;
   }();
-  bool wt = vec && (g_decstep_staging >= 0 ? g_decstep_staging : wtma_env) != 0;
+  bool wt = vec && p.R == DS_R && (g_decstep_staging >= 0 ? g_decstep_staging : wtma_env) != 0;
   if (wt) {
     const int64_t totals[4] = {H / 4, H / 4, A / 4, O / 4};
     const int nbox[4] = {2, 1, 1, maxout ? 2 : 1};
@@ -1000,10 +1023,12 @@ int nm_attn_decoder_step_fwd(const int64_t* symbols, const float* emb_table, con
   NM_REQUIRE(smem_bytes <= (size_t)DS_MAX_DYN_SMEM, NM_E_UNSUPPORTED,
              "nm_attn_decoder_step_fwd: needs %zu bytes of shared memory", smem_bytes);
 
-  auto kern = p.wtma ? attn_decoder_step_kernel<4, true>
-                     : (vec ? attn_decoder_step_kernel<4, false> : attn_decoder_step_kernel<1, false>);
-  static bool attr_done[3] = {false, false, false};
-  const int variant = p.wtma ? 2 : (vec ? 1 : 0);
+  auto kern = p.R == DS_R_MAX ? attn_decoder_step_kernel<4, false, DS_R_MAX>
+                              : (p.wtma ? attn_decoder_step_kernel<4, true, DS_R>
+                                        : (vec ? attn_decoder_step_kernel<4, false, DS_R>
+                                               : attn_decoder_step_kernel<1, false, DS_R>));
+  static bool attr_done[4] = {false, false, false, false};
+  const int variant = p.R == DS_R_MAX ? 3 : (p.wtma ? 2 : (vec ? 1 : 0));
   if (!attr_done[variant]) {
     NM_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, DS_MAX_DYN_SMEM));
     attr_done[variant] = true;
