@@ -61,7 +61,7 @@ if os.path.exists(path):
 
 # ---- launch list of the Transformer workload (newest call directory that has one) ---------------------------
 import glob
-cands = sorted(glob.glob("gpurun_out/call*/transformer_launches.csv"), key=os.path.getmtime)
+cands = sorted(glob.glob("gpurun_out/*/transformer_launches.csv"), key=os.path.getmtime)
 if cands:
     lines = [l for l in open(cands[-1]) if not l.startswith("==")]
     rows = []
