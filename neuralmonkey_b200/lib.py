@@ -109,6 +109,12 @@ def profile_start() -> None:
     _profile = {}
 
 
+def profiling() -> bool:
+    """True between profile_start() and profile_stop(): per-call times are only meaningful when the calls do not
+    overlap, so the trainers keep everything on one stream meanwhile."""
+    return _profile is not None
+
+
 def profile_stop() -> Dict[str, Dict[str, float]]:
     """Stop recording; returns {entry point: {"calls": n, "ms": total device time}}."""
     global _profile

@@ -86,8 +86,8 @@ _wg = {"stream": None, "keep": [], "open": False}
 
 
 def weight_grad_stream(enable: bool) -> None:
-    if enable and os.environ.get("NMB200_WGRAD_STREAM", _WGRAD_STREAM_DEFAULT) != "1":
-        enable = False
+    if enable and (os.environ.get("NMB200_WGRAD_STREAM", _WGRAD_STREAM_DEFAULT) != "1" or lib.profiling()):
+        enable = False      # (the per-call profiler times calls one by one: no overlap while it runs)
     if enable and _wg["stream"] is None:
         _wg["stream"] = torch.cuda.Stream()
     _wg["open"] = bool(enable)
