@@ -22,3 +22,14 @@ NMB200_DECSTEP_ROWS=16 timeout -k 10 600 python -m pytest tests/test_gpu_decode.
 echo "decode tests (16 rows default) exit $?" | tee -a "$out/summary.txt"
 tail -n 4 "$out/decode_tests_rows16.log" | cut -c1-220
 du -sh gpurun_out
+# the bench line once more: its roofline object now comes from per-call times taken on one stream
+timeout -k 10 1200 python bench.py > "$out/bench.json" 2> "$out/bench.log"
+echo "bench exit $?" | tee -a "$out/summary.txt"
+python - <<'PY'
+import json
+try:
+    d = [json.loads(l) for l in open("gpurun_out/call12/bench.json") if l.startswith("{")][-1]
+    print("en-de", d["ms_per_step"], "ms", round(d["value"]), "e2e", round(d["e2e"]["value"]), "frac", d["roofline"]["frac"], "f16", d["roofline"]["f16_instances"]["frac"])
+except Exception as e:
+    print("bench unreadable", e)
+PY
