@@ -46,7 +46,7 @@ constexpr int DS_RED_FLOATS = 128 * 32;   // K-split scratch of ds_panel: up to 
 constexpr int DS_WSLOTS = 4;     // weight-tile ring depth (weights staged by 2-D TMA)
 constexpr int DS_WKT = 32;       // weight rows (k) per staged tile
 constexpr int DS_WTMA_DEFAULT = 0;   // measured slower than the 16-byte loads: NMB200_DECSTEP_WTMA=1 opts in
-constexpr int DS_ROWS_DEFAULT = 8;   // until measured on the GPU: NMB200_DECSTEP_ROWS=16 opts in
+constexpr int DS_ROWS_DEFAULT = 8;   // 16 measured slower (16 clusters of 8 CTAs do not fit the chip at once: DESIGN.md)
 
 struct DecStep {
   int rows, E, H, A, C, Tx, O, group, act, maxout;
@@ -950,16 +950,31 @@ int nm_attn_decoder_step_fwd(const int64_t* symbols, const float* emb_table, con
     return v == 16 ? 16 : 8;
   }();
   const int rows_mode = g_decstep_rows > 0 ? g_decstep_rows : rows_env;
-  p.R = (vec && rows_mode == 16 && rows > DS_R) ? DS_R_MAX : DS_R;
   // cluster size: as many CTAs as fill the chip, at most 8, at least one attended row per CTA
-  const int64_t clusters = ceil_div(rows, p.R);
-  int cl = 8;
-  while (cl > 1 && clusters * cl > (int64_t)sm_count()) cl >>= 1;
-  const char* env = getenv("NMB200_DECSTEP_CLUSTER");
-  if (env && *env) {
-    const int want = atoi(env);
-    if (want == 1 || want == 2 || want == 4 || want == 8) cl = want;
+  auto cluster_size = [&](int R) {
+    const int64_t n = ceil_div(rows, R);
+    int c = 8;
+    while (c > 1 && n * c > (int64_t)sm_count()) c >>= 1;
+    const char* env = getenv("NMB200_DECSTEP_CLUSTER");
+    if (env && *env) {
+      const int want = atoi(env);
+      if (want == 1 || want == 2 || want == 4 || want == 8) c = want;
+    }
+    return c;
+  };
+  p.R = (vec && rows_mode == 16 && rows > DS_R) ? DS_R_MAX : DS_R;
+  int cl = cluster_size(p.R);
+  if (p.R == DS_R_MAX) {   // twice the row vectors in shared memory: back to 8 rows when no key / value tile fits
+    DecStep q = p;
+    q.cl = cl;
+    q.slot_floats = 0;
+    const int64_t avail16 = (int64_t)(227 * 1024 - 1024) / 4 - ds_layout(q, true).total;
+    if (avail16 / DS_SLOTS - (avail16 / DS_SLOTS) % 32 < (A > C ? A : C)) {
+      p.R = DS_R;
+      cl = cluster_size(p.R);
+    }
   }
+  const int64_t clusters = ceil_div(rows, p.R);
   p.cl = cl;
 
   // weights through shared memory (2-D TMA tiles) when every column range fits one box; NMB200_DECSTEP_WTMA=0/1
