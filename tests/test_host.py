@@ -335,3 +335,48 @@ def test_data_parallel_training_never_hands_a_rank_an_empty_shard(monkeypatch):
         assert all(len(x) > 0 for x in Manager.executed)
     # rank 0's shards are the leading sentences of the merged batches
     assert Manager.executed is not None
+
+
+def test_shutdown_releases_what_was_registered_first_and_is_idempotent():
+    """distributed.shutdown(): cleanups (a trainer's CUDA graphs that captured collectives) run before the
+    process group would be destroyed, newest first, once; without a process group the rest is a no-op."""
+    from neuralmonkey_b200 import distributed
+    order = []
+    first, second = (lambda: order.append("first")), (lambda: order.append("second"))
+    distributed.register_cleanup(first)
+    distributed.register_cleanup(second)
+    distributed.register_cleanup(first)              # registered once
+    distributed.shutdown()
+    distributed.shutdown()
+    assert order == ["second", "first"]
+
+
+def test_weight_gradient_window_stays_shut_without_a_gpu_and_while_profiling(monkeypatch):
+    """ops.weight_grad_stream(): the second stream is a GPU affair (the trainer opens the window only for CUDA
+    arenas) and yields to the per-call profiler, whose times assume calls that do not overlap."""
+    from neuralmonkey_b200 import lib, ops
+    ran = []
+    ops.weight_grad_stream(False)
+    ops._off_the_chain(lambda: ran.append(1))        # window shut: runs in place, keeps nothing alive
+    assert ran == [1] and not ops._wg["keep"]
+    ops.join_weight_grads()                           # nothing to wait for
+    monkeypatch.setenv("NMB200_WGRAD_STREAM", "0")
+    ops.weight_grad_stream(True)
+    assert ops._wg["open"] is False
+    monkeypatch.setenv("NMB200_WGRAD_STREAM", "1")
+    monkeypatch.setattr(lib, "_profile", {})          # as between profile_start() and profile_stop()
+    ops.weight_grad_stream(True)
+    assert ops._wg["open"] is False
+
+
+def test_dropout_helper_on_the_cpu_with_a_residual():
+    """nn.utils.dropout off the GPU (the stand-in path of the host tests): identity when inactive, mask product
+    plus the residual otherwise."""
+    import torch
+    from neuralmonkey_b200.nn import utils
+    x, res = torch.ones(4, 6), torch.full((4, 6), 2.0)
+    assert utils.dropout(x, 1.0, True) is x and utils.dropout(x, 0.5, False) is x
+    assert torch.equal(utils.dropout(x, 1.0, True, residual=res), x + res)
+    torch.manual_seed(0)
+    y = utils.dropout(x, 0.5, True, residual=res)
+    assert set(y.unique().tolist()) <= {2.0, 4.0}     # 0 or 1 / keep_prob, plus the residual
