@@ -92,8 +92,9 @@ def workload_config(workload, n_gpus, batch, dropout=True):
             "vocab": ENDE["vocab"], "emb": 300, "rnn": 300, "optimizer": "Adam 1e-4, clip 1.0 per tensor, l2 1e-8",
             "lengths": "fixed (no padding)", "parallelism": "dp{}".format(n_gpus),
             "step_submission": "CrossEntropyTrainer(use_cuda_graph=True): the step is captured once per batch "
-                               "shape and replayed (N>1: backward graph, bucketed NCCL all-reduce overlapped "
-                               "with the backward pass, clip+Adam graph)",
+                               "shape and replayed; weight gradients are issued on a second stream inside the "
+                               "captured backward pass (N>1: the bucketed NCCL all-reduce starts inside the "
+                               "backward pass and is captured in the same graph)",
             "gemm": "tcgen05: kind::f16 for the vocabulary projection and its gradients (fp16 operands, fp32 "
                     "accumulate), kind::tf32 elsewhere; GRU recurrences on tcgen05 with weights resident in "
                     "tensor memory",
