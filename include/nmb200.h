@@ -118,7 +118,8 @@ int nm_layernorm_fwd(const float* x, const float* gamma, const float* beta,
                      float* y, float* mean, float* rstd, int64_t M, int64_t D,
                      float eps, void* stream);
 /* dgamma/dbeta are accumulated into (two call sites share LayerNorm/{gamma,beta}
- * in RecurrentEncoder: encoders/recurrent.py:215-216). */
+ * in RecurrentEncoder: encoders/recurrent.py:215-216).  dx == NULL: parameter gradients only;
+ * dgamma == dbeta == NULL: input gradient only (two launches that a caller may put on different streams). */
 int nm_layernorm_bwd(const float* x, const float* gamma, const float* mean,
                      const float* rstd, const float* dy, float* dx, float* dgamma,
                      float* dbeta, int64_t M, int64_t D, void* stream);

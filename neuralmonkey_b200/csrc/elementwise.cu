@@ -422,15 +422,19 @@ int nm_layernorm_fwd(const float* x, const float* gamma, const float* beta, floa
 int nm_layernorm_bwd(const float* x, const float* gamma, const float* mean, const float* rstd,
                      const float* dy, float* dx, float* dgamma, float* dbeta, int64_t M, int64_t D,
                      void* stream) {
-  NM_REQUIRE(x && gamma && mean && rstd && dy && dx && dgamma && dbeta, NM_E_INVALID,
-             "nm_layernorm_bwd: null pointer");
+  NM_REQUIRE(x && gamma && mean && rstd && dy, NM_E_INVALID, "nm_layernorm_bwd: null pointer");
+  NM_REQUIRE((dgamma == nullptr) == (dbeta == nullptr) && (dx || dgamma), NM_E_INVALID,
+             "nm_layernorm_bwd: dgamma and dbeta come together, and dx or the pair must be asked for");
   NM_REQUIRE(M >= 0 && D > 0, NM_E_INVALID, "nm_layernorm_bwd: bad sizes");
   NM_REQUIRE(D <= LN_MAX_D, NM_E_UNSUPPORTED, "nm_layernorm_bwd: D too large");
   if (M == 0) return NM_OK;
   cudaStream_t s = (cudaStream_t)stream;
-  NM_LN_DISPATCH(D, (layernorm_bwd_dx_kernel<PL><<<grid_for(M, 4, 16), 128, 0, s>>>(
-                        x, gamma, mean, rstd, dy, dx, M, (int)D)));
-  NM_LAUNCH_CHECK("nm_layernorm_bwd(dx)");
+  if (dx) {
+    NM_LN_DISPATCH(D, (layernorm_bwd_dx_kernel<PL><<<grid_for(M, 4, 16), 128, 0, s>>>(
+                          x, gamma, mean, rstd, dy, dx, M, (int)D)));
+    NM_LAUNCH_CHECK("nm_layernorm_bwd(dx)");
+  }
+  if (!dgamma) return NM_OK;
   const int64_t strips = ceil_div(D, 32);
   int64_t chunks = ceil_div((int64_t)sm_count() * 4, strips);
   int64_t rows_per_block = ceil_div(M, chunks < 1 ? 1 : chunks);

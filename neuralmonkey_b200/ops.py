@@ -411,6 +411,13 @@ class _LayerNorm(torch.autograd.Function):
         dy2 = dy.reshape(m, d).contiguous()
         dx = torch.empty_like(x2)
         sg, sb = ctx.sinks
+        if sg is not None and sb is not None:
+            # the input gradient continues the chain; the parameter gradients only add into the gradient buffer
+            call("nm_layernorm_bwd", ptr(x2), ptr(gamma), ptr(mean), ptr(rstd), ptr(dy2), ptr(dx), None, None, m, d,
+                 lib.stream())
+            _off_the_chain(lambda: call("nm_layernorm_bwd", ptr(x2), ptr(gamma), ptr(mean), ptr(rstd), ptr(dy2), None,
+                                        ptr(sg), ptr(sb), m, d, lib.stream()), x2, dy2, mean, rstd)
+            return dx.view(ctx.in_shape), None, None, None
         dg = sg if sg is not None else torch.zeros(d, device=dy.device, dtype=torch.float32)
         db = sb if sb is not None else torch.zeros(d, device=dy.device, dtype=torch.float32)
         call("nm_layernorm_bwd", ptr(x2), ptr(gamma), ptr(mean), ptr(rstd), ptr(dy2), ptr(dx), ptr(dg),
