@@ -27,13 +27,6 @@ for f in ("bench.json", "bench_ref.json"):
     except Exception as e:
         print(f, "unreadable", e)
 PY
-# decoder step with 16 hypotheses per cluster (opt-in): phases and the decoding workload
-NMB200_DECSTEP_ROWS=16 timeout -k 10 300 python tools/decstep_phases.py > "$out/phases_rows16.txt" 2> "$out/phases_rows16.log"
-echo "phases (16 rows per cluster) exit $?" | tee -a "$out/summary.txt"
-cat "$out/phases_rows16.txt"
-NMB200_DECSTEP_ROWS=16 timeout -k 10 600 python bench_workloads.py rnn_decode --no-cpu > "$out/rnn_decode_rows16.json" 2> "$out/rnn_decode_rows16.log"
-echo "rnn_decode (16 rows per cluster) exit $?" | tee -a "$out/summary.txt"
-python tools/print_rnn_decode.py "$out/rnn_decode_rows16.json"
 timeout -k 10 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 --csv \
     --log-file "$out/transformer_launches.csv" python bench_workloads.py transformer --no-cpu > "$out/transformer_list.log" 2>&1
 echo "transformer list exit $?" | tee -a "$out/summary.txt"
