@@ -23,6 +23,7 @@ SURVEY.md 8(c)) on the workload's shape, all host threads, a bounded number of s
 The models are built from INI text through the package's configuration builder (bench_models.py).
 """
 import argparse
+import contextlib
 import json
 import os
 import re
@@ -363,7 +364,9 @@ def run_b200(args):
 
     for i in range(max(args.warmup, 3)):
         step_device_inputs(i)
-    with ClockSampler(dev.index or 0) as clocks:
+    # rank 0 alone samples the clocks (its line is the one printed): eight ranks polling nvidia-smi at once
+    # contend for the driver and stall each other's launches (seen as 6 ms of host time per step at N=8)
+    with (ClockSampler(dev.index or 0) if rank == 0 else contextlib.nullcontext()) as clocks:
         ms_step, _ = timed(step_device_inputs, args.steps, read_loss=False)
     host_enqueue_ms = host_ms[0]
 
