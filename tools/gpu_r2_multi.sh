@@ -2,6 +2,7 @@
 # Round 2, multi-GPU call (gpurun --gpus N): DP equivalence test, en-de and transformer bench at N ranks
 set -u
 N=${1:-2}
+WLS=${2:-"ende transformer"}
 out=gpurun_out/multi$N
 mkdir -p "$out"
 export PYTHONUNBUFFERED=1
@@ -11,7 +12,7 @@ if [ "$N" = "2" ]; then
   timeout 900 python -m pytest tests/test_gpu_dp.py -m gpu -q -s > "$out/dp_tests.log" 2>&1
   echo "dp tests exit $?" | tee -a "$out/summary.txt"
 fi
-for wl in ende transformer; do
+for wl in $WLS; do
   timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29555 \
       bench.py --gpus $N --steps 10 --warmup 3 --workload $wl > "$out/bench_${wl}_n$N.json" 2> "$out/bench_${wl}_n$N.log"
   echo "bench $wl N=$N exit $?" | tee -a "$out/summary.txt"
