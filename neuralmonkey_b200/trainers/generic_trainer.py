@@ -162,6 +162,16 @@ class GenericTrainer(GraphExecutor, Feedable):
             t.register_hook(hook)
         works.append(("armed", fired, early))
 
+    @staticmethod
+    def _update_in_ranges() -> bool:
+        """NMB200_RANGE_UPDATE=1: optimizer range by range behind the exchange (see `_finish_exchange`).  Off by
+        default: on two GPUs it takes the en-de step from 6.63 to 6.43 ms, but on four and eight GPUs the
+        graph-replayed loop then spends 4-6 ms of HOST time per step inside the graph launch (device-resident
+        loop slower than the end-to-end one) - measured with the round's last GPU minutes and not understood
+        yet; the default is the path whose eight-GPU run was clean."""
+        import os
+        return os.environ.get("NMB200_RANGE_UPDATE", "0") == "1"
+
     def _finish_exchange(self, works: list, update=None) -> bool:
         """All-reduce what the hook did not cover (the encoders' ranges and the statistic slots - or, when
         it never fired, everything) and make the compute stream wait for the exchange.
@@ -236,7 +246,7 @@ class GenericTrainer(GraphExecutor, Feedable):
             # optimizer kernel -> N ranks reproduce the single-GPU token mean exactly
             loss_sum, count = exact
             w = self.objectives[0].weight
-            if works is not None:
+            if works is not None and self._update_in_ranges():
                 # the token count is known before the backward pass: exchanged on its own, right away, so that
                 # the optimizer can start on the ranges that come back first
                 if getattr(self, "_count_global", None) is None:
