@@ -189,8 +189,56 @@ class ClockSampler:
         self.samples = []
         self._stop = threading.Event()
         self._thread = threading.Thread(target=self._run, daemon=True)
+        self._nvml = self._open_nvml(index)
+
+    @staticmethod
+    def _open_nvml(index):
+        """An NVML handle of this process' GPU, opened ONCE before the timed region.  Polling through it costs
+        microseconds; spawning `nvidia-smi` every 100 ms instead re-initialises NVML each time, which takes the
+        driver's locks for tens of milliseconds and stalls this (and every other) process' launches - seen as 3-6 ms
+        of host time per step in the device-resident loop.  None (-> the nvidia-smi fallback) if NVML is not usable."""
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            handle = None
+            try:
+                uuid = str(torch.cuda.get_device_properties(index).uuid)
+                handle = pynvml.nvmlDeviceGetHandleByUUID(uuid if uuid.startswith("GPU-") else "GPU-" + uuid)
+            except Exception:  # pylint: disable=broad-except
+                visible = [v for v in os.environ.get("CUDA_VISIBLE_DEVICES", "").split(",") if v.strip()]
+                phys = int(visible[index]) if visible and all(v.strip().isdigit() for v in visible) else index
+                handle = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            pynvml.nvmlDeviceGetClockInfo(handle, pynvml.NVML_CLOCK_SM)      # must answer, else fall back
+            return pynvml, handle
+        except Exception:  # pylint: disable=broad-except
+            return None
+
+    def _poll_nvml(self):
+        pynvml, handle = self._nvml
+        sm = pynvml.nvmlDeviceGetClockInfo(handle, pynvml.NVML_CLOCK_SM)
+        sm_max = pynvml.nvmlDeviceGetMaxClockInfo(handle, pynvml.NVML_CLOCK_SM)
+        try:
+            power = pynvml.nvmlDeviceGetPowerUsage(handle) / 1000.0
+        except Exception:  # pylint: disable=broad-except
+            power = 0.0
+        try:
+            mask = pynvml.nvmlDeviceGetCurrentClocksEventReasons(handle)
+        except Exception:  # pylint: disable=broad-except
+            mask = pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(handle)
+
+        def flag(bit):
+            return "Active" if (mask & bit) else "Not Active"
+        # hw_slowdown 0x8, hw_thermal_slowdown 0x40, sw_thermal_slowdown 0x20, sw_power_cap 0x4 (nvml.h)
+        return [str(sm), str(sm_max), "{:.1f}".format(power), flag(0x8), flag(0x40), flag(0x20), flag(0x4)]
 
     def _run(self):
+        while self._nvml is not None and not self._stop.is_set():
+            try:
+                self.samples.append(self._poll_nvml())
+            except Exception:  # pylint: disable=broad-except
+                self._nvml = None          # NVML stopped answering: fall through to nvidia-smi below
+                break
+            self._stop.wait(0.02)
         while not self._stop.is_set():
             try:
                 out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.FIELDS,
