@@ -100,6 +100,11 @@ def training_loop(cfg: Namespace) -> None:
                             score = val_eval[cfg.main_metric]
                             if distributed.rank() == 0:
                                 cfg.tf_manager.validation_hook(score, epoch_n, batch_n)
+                                if score == cfg.tf_manager.best_score:
+                                    # a new best: the parts with a `save_checkpoint` file store their
+                                    # variables (learning_utils.py:146-159)
+                                    cfg.tf_manager.initialize_model_parts(cfg.runners + cfg.trainers,
+                                                                          save=True)
                             if hasattr(cfg.tf_manager, "sync_validation_state"):
                                 cfg.tf_manager.sync_validation_state()
                             log("best {} on validation: {:.4g} (in epoch {}, after batch number {})"

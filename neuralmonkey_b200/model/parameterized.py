@@ -56,3 +56,39 @@ class Parameterized:
         if not self._declared:
             self._declared = True
             self.declare_variables()
+
+    # -- per-part checkpoints (parameterized.py:109-125) ---------------------------------------
+    def _scope_names(self) -> List[str]:
+        """Names of the variables the part's Saver covers: `tf.get_collection(GLOBAL_VARIABLES, scope=name)`
+        (parameterized.py:100-107) keeps every variable - trainable or not - whose name MATCHES the scope as a
+        regular expression at its start, so `enc` also covers `enc_input/...` (a SentenceEncoder's checkpoint
+        holds its input sequence's embeddings too)."""
+        import re
+        return [n for n in runtime.arena().order if re.match(self._scope, n)]
+
+    def _scope_variables(self) -> Dict[str, torch.Tensor]:
+        state = runtime.arena().state_dict()
+        return {n: state[n] for n in self._scope_names()}
+
+    def save(self, session: Any = None) -> None:
+        """Save the part's variables to its `save_checkpoint` file (no-op without one)."""
+        if self._save_checkpoint:
+            from neuralmonkey_b200.logging import log
+            torch.save({"variables": self._scope_variables()}, self._save_checkpoint)
+            log("Variables of '{}' saved to '{}'".format(self.name, self._save_checkpoint))
+
+    def load(self, session: Any = None) -> None:
+        """Load the part's variables from its `load_checkpoint` file (no-op without one).  The file is
+        one written by `save` or a whole-model checkpoint of `TensorFlowManager.save`; variables of other
+        scopes in it are ignored, a variable of this part missing from it is an error (Saver.restore)."""
+        if self._load_checkpoint:
+            from neuralmonkey_b200.logging import log
+            ckpt = torch.load(self._load_checkpoint, map_location="cpu")
+            stored = ckpt["variables"] if "variables" in ckpt else ckpt
+            wanted = self._scope_names()
+            missing = [n for n in wanted if n not in stored]
+            if missing:
+                raise KeyError("checkpoint '{}' holds no value for variable(s) {} of '{}'".format(
+                    self._load_checkpoint, missing, self.name))
+            runtime.arena().load_dict({n: stored[n] for n in wanted})
+            log("Variables of '{}' loaded from '{}'".format(self.name, self._load_checkpoint))

@@ -195,16 +195,17 @@ class TensorFlowManager:
         """Variables were initialised when the arena was finalised; nothing to run."""
 
     def initialize_model_parts(self, runners, save: bool = False) -> None:
-        """Per-ModelPart `load_checkpoint` / `save_checkpoint` files (tf_manager.py:279-289)."""
+        """Initialize model parts variables from their checkpoints (tf_manager.py:279-289); with `save`,
+        write the parts' `save_checkpoint` files instead (what learning_utils.py:150-159 does on a new
+        best validation score)."""
+        if any(not hasattr(r, "parameterizeds") for r in runners):
+            raise TypeError("Args to initialize_model_parts must be trainers or runners")
         parameterizeds = set.union(*[rnr.parameterizeds for rnr in runners]) if runners else set()
-        for coder in parameterizeds:
-            path = getattr(coder, "_load_checkpoint", None)
-            if path:
-                log("Loading {} from {}".format(coder.name, path))
-                ckpt = torch.load(path, map_location="cpu")
-                prefix = coder.scope_name + "/"
-                runtime.arena().load_dict({k: v for k, v in ckpt["variables"].items()
-                                           if k.startswith(prefix)})
+        for coder in sorted(parameterizeds, key=lambda c: getattr(c, "name", "")):
+            if save:
+                coder.save()
+            else:
+                coder.load()
 
 
 def get_default_tf_manager() -> TensorFlowManager:

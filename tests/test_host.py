@@ -380,3 +380,73 @@ def test_dropout_helper_on_the_cpu_with_a_residual():
     torch.manual_seed(0)
     y = utils.dropout(x, 0.5, True, residual=res)
     assert set(y.unique().tolist()) <= {2.0, 4.0}     # 0 or 1 / keep_prob, plus the residual
+
+
+def test_model_part_save_and_load(tmp_path, monkeypatch):
+    """The reference's tests/test_model_part.py::test_save_and_load restated without sessions: a part with
+    `save_checkpoint` / `load_checkpoint` files stores the variables of ITS scope and restores them into a
+    freshly initialised model; other parts' variables are neither written nor touched
+    (model/parameterized.py:98-125, tf_manager.py:279-289, learning_utils.py:146-159)."""
+    from neuralmonkey_b200 import runtime
+    from neuralmonkey_b200.encoders import SentenceEncoder
+    from neuralmonkey_b200.tf_manager import TensorFlowManager
+    from neuralmonkey_b200.vocabulary import Vocabulary
+
+    # relative file names: SentenceEncoder derives its input sequence's files as "input_" + name
+    # (encoders/recurrent.py:279-280), which only works for those
+    monkeypatch.chdir(tmp_path)
+    path = "enc.ckpt"
+
+    def make(seed):
+        runtime.reset()
+        vocabulary = Vocabulary(["a", "b"])
+        enc = SentenceEncoder(name="enc", vocabulary=vocabulary, data_id="data_id", embedding_size=10,
+                              rnn_size=20, max_input_len=30, save_checkpoint=path, load_checkpoint=path)
+        other = SentenceEncoder(name="other", vocabulary=vocabulary, data_id="data_id", embedding_size=10,
+                                rnn_size=20, max_input_len=30)
+        for part in (enc, other):
+            for dep in part.get_dependencies()[1]:
+                dep.ensure_declared()
+        runtime.arena().finalize(torch.device("cpu"), seed=seed)
+        return enc, other
+
+    class _Runner:          # what initialize_model_parts looks at
+        def __init__(self, *parts):
+            self.parameterizeds = set()
+            for p in parts:
+                self.parameterizeds |= p.get_dependencies()[1]
+
+    enc, other = make(seed=1)
+    first = runtime.arena().state_dict()
+    TensorFlowManager(num_sessions=1, num_threads=1).initialize_model_parts([_Runner(enc, other)], save=True)
+    stored = torch.load(path)["variables"]
+    # tf.get_collection(..., scope="enc") is a regex match at the start of the name: `enc_input/...` is covered
+    mine = [n for n in first if n.startswith("enc/") or n.startswith("enc_input/")]
+    assert any(n.startswith("enc/") for n in mine) and any(n.startswith("enc_input/") for n in mine)
+    assert sorted(stored) == sorted(mine)                   # nothing of `other/`
+    assert sorted(torch.load("input_enc.ckpt")["variables"]) == sorted(n for n in first if n.startswith("enc_input/"))
+
+    enc, other = make(seed=2)
+    second = runtime.arena().state_dict()
+    assert any(not torch.equal(first[n], second[n]) for n in mine)
+    TensorFlowManager(num_sessions=1, num_threads=1).initialize_model_parts([_Runner(enc, other)])
+    now = runtime.arena().state_dict()
+    assert all(torch.equal(now[n], first[n]) for n in mine)
+    assert all(torch.equal(now[n], second[n]) for n in now if n.startswith("other"))
+
+    # a checkpoint that lacks one of the part's variables is an error, as with Saver.restore
+    del stored[mine[0]]
+    torch.save({"variables": stored}, path)
+    try:
+        enc.load()
+    except KeyError as exc:
+        assert mine[0] in str(exc)
+    else:
+        raise AssertionError("a missing variable must be reported")
+    try:
+        TensorFlowManager(num_sessions=1, num_threads=1).initialize_model_parts([object()])
+    except TypeError:
+        pass
+    else:
+        raise AssertionError("executors without `parameterizeds` must be refused")
+    runtime.reset()

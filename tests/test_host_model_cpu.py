@@ -295,6 +295,10 @@ def test_experiments_end_to_end_on_the_cpu(cpu_model, monkeypatch, tmp_path, whi
     cli._write_data(data)
     ini = tmp_path / "exp.ini"
     template = cli.INI if which == "bahdanau" else cli.TRANSFORMER_INI
+    if which == "bahdanau":     # a per-part checkpoint, written whenever validation finds a new best score
+        assert 'name="bahdanau_decoder"\n' in template
+        template = template.replace('name="bahdanau_decoder"\n',
+                                    'name="bahdanau_decoder"\nsave_checkpoint="{out}/decoder.part"\n')
     ini.write_text(template.format(out=out, data=data, epochs=2))
     _cli(monkeypatch, "neuralmonkey_b200.train", ["neuralmonkey-train", str(ini)])
     log_text = open(os.path.join(out, "experiment.log")).read()
@@ -303,6 +307,12 @@ def test_experiments_end_to_end_on_the_cpu(cpu_model, monkeypatch, tmp_path, whi
         assert os.path.exists(os.path.join(out, name)), name
     if which == "bahdanau":
         assert os.path.exists(os.path.join(out, "variables.data"))
+        import torch
+        part = torch.load(os.path.join(out, "decoder.part"))["variables"]
+        best = torch.load(os.path.join(out, open(os.path.join(out, "variables.data.best")).read().strip()))
+        assert part and all(n.startswith("bahdanau_decoder") for n in part)
+        assert all(torch.equal(v, best["variables"][n]) for n, v in part.items())
+        assert "Variables of 'bahdanau_decoder' saved to" in log_text
         losses = training_log_values(log_text, "target/train_xent")
         assert len(losses) >= 2 and losses[-1] < losses[0], losses
         assert len(open(os.path.join(out, "val.out")).read().splitlines()) == 30
