@@ -196,6 +196,10 @@ class ParameterArena:
         self.stats = self.grad_buffer[tsz:tsz + self.STAT_SLOTS]
         self.adam_m = torch.zeros(tsz, device=device, dtype=torch.float32)
         self.adam_v = torch.zeros(tsz, device=device, dtype=torch.float32)
+        # optimizer slots: slot 0 is (adam_m, adam_v); further optimizer OBJECTS of the experiment get their own
+        # pair on first use (`optimizer_slot`), as every tf.train.Optimizer keeps its own moment variables
+        self.optimizer_slots = []           # [(optimizer, m, v)], in order of first use
+        self.restored_optimizer_state = {}  # slot index -> {"m": dict, "v": dict, "steps": int} from a checkpoint
         train_names = [n for n in names if self.variables[n].trainable]
         # segment i spans [seg_off[i], seg_off[i+1]) including its alignment padding (zeros)
         offs = [self.variables[n].offset for n in train_names] + [self.trainable_size]
@@ -259,6 +263,30 @@ class ParameterArena:
 
     def state_dict(self) -> Dict[str, torch.Tensor]:
         return {n: self._views[n].detach().cpu().clone() for n in self.order}
+
+    def optimizer_slot(self, optimizer) -> Tuple[torch.Tensor, torch.Tensor]:
+        """(m, v) flat moment buffers of `optimizer`.  TensorFlow keeps Adam's moments (slot variables) and its
+        beta-power accumulators per optimizer OBJECT: two trainers with an optimizer each (tests/bahdanau.ini)
+        do not share them, one optimizer handed to two trainers does.  The first optimizer that updates the
+        model gets `adam_m` / `adam_v`; every further one a fresh zero pair (order of first use, the same on
+        every rank and in a continued run).  State restored from a checkpoint before the slot existed is
+        applied when it is claimed."""
+        for owner, m, v in self.optimizer_slots:
+            if owner is optimizer:
+                return m, v
+        index = len(self.optimizer_slots)
+        if index == 0:
+            m, v = self.adam_m, self.adam_v
+        else:
+            m, v = torch.zeros_like(self.adam_m), torch.zeros_like(self.adam_v)
+        self.optimizer_slots.append((optimizer, m, v))
+        pending = self.restored_optimizer_state.pop(index, None)
+        if pending is not None:
+            if index > 0:
+                self.load_moments(m, pending["m"])
+                self.load_moments(v, pending["v"])
+        optimizer.steps = int(pending["steps"]) if pending is not None else 0
+        return m, v
 
     def moment_dict(self, flat: torch.Tensor) -> Dict[str, torch.Tensor]:
         """A flat per-parameter buffer (Adam m / v) split by trainable variable name."""

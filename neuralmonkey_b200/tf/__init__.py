@@ -22,6 +22,10 @@ class Optimizer:
         self.beta2 = beta2
         self.epsilon = epsilon
         self.name = name
+        # updates THIS optimizer has applied: tf.train.AdamOptimizer's beta1_power / beta2_power accumulators
+        # are its own non-slot variables, multiplied once per apply_gradients call of this object - the bias
+        # correction follows them, not the global step the trainers of an experiment share
+        self.steps = 0
 
     def lr_at(self, global_step: int) -> float:
         lr = self.learning_rate

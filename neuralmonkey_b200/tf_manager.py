@@ -148,9 +148,17 @@ class TensorFlowManager:
         arena = runtime.arena()
         for index, path in enumerate(variable_files):
             self.activate_session(index)
-            torch.save({"variables": arena.state_dict(), "adam_m": arena.moment_dict(arena.adam_m),
-                        "adam_v": arena.moment_dict(arena.adam_v),
-                        "global_step": runtime.global_step()}, path)   # the Saver stores it too
+            state = {"variables": arena.state_dict(), "adam_m": arena.moment_dict(arena.adam_m),
+                     "adam_v": arena.moment_dict(arena.adam_v),
+                     "global_step": runtime.global_step()}    # the Saver stores it too
+            # per-optimizer state (the Saver stores every optimizer's slot variables and beta powers): the update
+            # counts, and the moments of the optimizers beyond the first one
+            slots = getattr(arena, "optimizer_slots", [])
+            state["optimizer_steps"] = [int(opt.steps) for opt, _m, _v in slots]
+            for i, (_opt, m, v) in enumerate(slots[1:], start=1):
+                state["adam_m_{}".format(i)] = arena.moment_dict(m)
+                state["adam_v_{}".format(i)] = arena.moment_dict(v)
+            torch.save(state, path)
 
     def restore(self, variable_files: Union[str, List[str]]) -> None:
         if isinstance(variable_files, str):
@@ -168,8 +176,24 @@ class TensorFlowManager:
             elif isinstance(ckpt.get("adam_m"), dict):   # optimizer moments, keyed by variable name
                 arena.load_moments(arena.adam_m, ckpt["adam_m"])
                 arena.load_moments(arena.adam_v, ckpt["adam_v"])
-                # warm moments need the step they belong to: bias correction and lr schedules resume
-                runtime.set_global_step(int(ckpt.get("global_step", 0)))
+                # warm moments need the steps they belong to: lr schedules (global step) and every optimizer's
+                # bias correction (its own update count; checkpoints without it: one optimizer, = global step)
+                gstep = int(ckpt.get("global_step", 0))
+                runtime.set_global_step(gstep)
+                steps = list(ckpt.get("optimizer_steps") or [gstep])
+                slots = arena.optimizer_slots
+                arena.restored_optimizer_state = {}
+                for i, count in enumerate(steps):
+                    m_i = ckpt.get("adam_m_{}".format(i)) if i else ckpt["adam_m"]
+                    v_i = ckpt.get("adam_v_{}".format(i)) if i else ckpt["adam_v"]
+                    if i < len(slots):                  # the optimizer is already at work: apply now
+                        opt, m, v = slots[i]
+                        if i and isinstance(m_i, dict):
+                            arena.load_moments(m, m_i)
+                            arena.load_moments(v, v_i)
+                        opt.steps = int(count)
+                    else:                               # applied when the optimizer claims its slot
+                        arena.restored_optimizer_state[i] = {"m": m_i or {}, "v": v_i or {}, "steps": int(count)}
 
     def sync_validation_state(self) -> None:
         """Data parallel: rank 0 alone runs validation_hook (it owns the checkpoint files); the other ranks

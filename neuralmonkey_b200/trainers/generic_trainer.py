@@ -296,7 +296,6 @@ class GenericTrainer(GraphExecutor, Feedable):
             return None
         if entry == "failed":
             return None
-        opt = self.optimizer
         if entry == "seen":
             captured = [k for k, v in self._graphs.items() if isinstance(v, tuple)]
             if len(captured) >= self.MAX_GRAPHS:          # bounded: a captured step owns its activations
@@ -356,10 +355,7 @@ class GenericTrainer(GraphExecutor, Feedable):
             for k, t in d.items():
                 if st[k] is not t:
                     st[k].copy_(t)
-        self.global_step += 1
-        t = self.global_step
-        lr = opt.lr_at(t - 1)
-        self._lr_dev.fill_(lr * math.sqrt(1.0 - opt.beta2 ** t) / (1.0 - opt.beta1 ** t))
+        self._lr_dev.fill_(self._advance_step())
         graph.replay()
         if graph2 is not None:
             distributed.all_reduce_sum(arena.allreduce_view)
@@ -428,11 +424,16 @@ class GenericTrainer(GraphExecutor, Feedable):
         return min(self._waited_ms(w) for w in history)
 
     def _advance_step(self) -> float:
-        """Increment the global step; returns Adam's bias-corrected step size for it."""
+        """Increment the global step and the optimizer's own update count; returns Adam's bias-corrected step
+        size.  The learning-rate schedule reads the GLOBAL step (shared by the trainers of an experiment,
+        before its increment); the bias correction follows the number of updates THIS optimizer applied
+        (TF's per-optimizer beta-power accumulators) - the two differ as soon as several trainers alternate."""
         opt = self.optimizer
+        runtime.arena().optimizer_slot(opt)          # claims the slot (and a restored step count) on first use
         self.global_step += 1
-        t = self.global_step
-        lr = opt.lr_at(t - 1)  # schedules read the global step before its increment
+        opt.steps += 1
+        t = opt.steps
+        lr = opt.lr_at(self.global_step - 1)
         return lr * math.sqrt(1.0 - opt.beta2 ** t) / (1.0 - opt.beta1 ** t)
 
     def apply_gradients(self, grad_scale: float = 1.0,
@@ -470,6 +471,7 @@ class GenericTrainer(GraphExecutor, Feedable):
             self._l1l2_buf = torch.zeros(2, device=arena.params.device, dtype=torch.float32)
         n = arena.trainable_size
         seg_flags = arena.seg_reg
+        adam_m, adam_v = arena.optimizer_slot(opt)
         if getattr(opt, "lazy", False):
             # LazyAdam: embedding tables are updated only where a gradient arrived (flag bit 1)
             if not hasattr(self, "_lazy_flags"):
@@ -483,8 +485,8 @@ class GenericTrainer(GraphExecutor, Feedable):
         common = (float(opt.beta1), float(opt.beta2), float(opt.epsilon),
                   float(self.clip_norm) if self.clip_norm else 0.0, float(self.l1_weight), float(self.l2_weight))
         if ranges is None:
-            call("nm_clip_adam_step", ptr(arena.params), ptr(arena.grads), ptr(arena.adam_m),
-                 ptr(arena.adam_v), ptr(arena.seg_off), ptr(seg_flags), ptr(arena.seg_norms), n,
+            call("nm_clip_adam_step", ptr(arena.params), ptr(arena.grads), ptr(adam_m),
+                 ptr(adam_v), ptr(arena.seg_off), ptr(seg_flags), ptr(arena.seg_norms), n,
                  len(arena.train_names), float(grad_scale), ptr(denominator), float(lr_t), *common,
                  ptr(self._l1l2_buf), ptr(lr_t_dev), lib.stream())
             return
@@ -494,8 +496,8 @@ class GenericTrainer(GraphExecutor, Feedable):
         for (first, count, rel), (lo, hi) in zip(self._segments_of(ranges), ranges):
             if count <= 0:
                 continue
-            call("nm_clip_adam_step", ptr(arena.params[lo:]), ptr(arena.grads[lo:]), ptr(arena.adam_m[lo:]),
-                 ptr(arena.adam_v[lo:]), ptr(rel), ptr(seg_flags[first:]), ptr(arena.seg_norms[first:]), hi - lo,
+            call("nm_clip_adam_step", ptr(arena.params[lo:]), ptr(arena.grads[lo:]), ptr(adam_m[lo:]),
+                 ptr(adam_v[lo:]), ptr(rel), ptr(seg_flags[first:]), ptr(arena.seg_norms[first:]), hi - lo,
                  count, float(grad_scale), ptr(denominator), float(lr_t), *common,
                  ptr(self._l1l2_part), ptr(lr_t_dev), lib.stream())
             if early and lo == early[0][0]:

@@ -145,6 +145,7 @@ def adam_kernel(trainer, grad_scale, denominator, lr_t, lr_t_dev, ranges=None):
     scale = float(grad_scale) / (float(denominator) if denominator is not None else 1.0)
     if not hasattr(trainer, "_l1l2_buf"):
         trainer._l1l2_buf = torch.zeros(2)
+    adam_m, adam_v = arena.optimizer_slot(opt)
     l1 = l2 = 0.0
     with torch.no_grad():
         for name in trainer.var_list:                 # with var_scopes: only the variables in scope
@@ -159,8 +160,8 @@ def adam_kernel(trainer, grad_scale, denominator, lr_t, lr_t_dev, ranges=None):
             if trainer.clip_norm:
                 grad = O.clip_by_norm(grad, float(trainer.clip_norm))
             info = arena.variables[name]
-            m = arena.adam_m[info.offset:info.offset + var.numel()].view(var.shape)
-            v = arena.adam_v[info.offset:info.offset + var.numel()].view(var.shape)
+            m = adam_m[info.offset:info.offset + var.numel()].view(var.shape)
+            v = adam_v[info.offset:info.offset + var.numel()].view(var.shape)
             m.mul_(opt.beta1).add_(grad, alpha=1 - opt.beta1)
             v.mul_(opt.beta2).addcmul_(grad, grad, value=1 - opt.beta2)
             var.sub_((float(lr_t_dev) if lr_t_dev is not None else lr_t) * m / (v.sqrt() + opt.epsilon))

@@ -1285,3 +1285,76 @@ def test_recurrent_encoder_over_a_temporal_filler(cpu_model):
     assert max_abs(enc.output, want["output"]) < 1e-5
     assert torch.equal(enc.temporal_mask.cpu(), seq.temporal_mask.cpu())
     runtime.reset()
+
+
+def test_every_optimizer_keeps_its_own_adam_state(cpu_model, monkeypatch, tmp_path):
+    """Several trainers on one model (tests/bahdanau.ini: trainer1, trainer2, greedy_trainer): every
+    tf.train.AdamOptimizer object owns its moment slots and beta-power accumulators, while ONE global step
+    counts the updates of all of them (generic_trainer.py:56-57,183-195).  Two alternating trainers here against
+    two oracle Adam states; then the whole state through a checkpoint into a fresh model."""
+    from neuralmonkey_b200 import runtime, tf
+    from neuralmonkey_b200.tf_manager import TensorFlowManager
+    from neuralmonkey_b200.trainers import CrossEntropyTrainer
+    from neuralmonkey_b200.trainers.generic_trainer import GenericTrainer
+    monkeypatch.setattr(GenericTrainer, "_adam_kernel", cpu_ops.adam_kernel)
+    lrs = (1e-2, 3e-3)
+    src, tgt = random_batch(6, 8, 7, TOY["vs"], TOY["vt"], seed=3)
+
+    def make():
+        model = build_bahdanau(**TOY, lr=lrs[0])
+        second = CrossEntropyTrainer(decoders=[model["dec"]], optimizer=tf.AdamOptimizer(learning_rate=lrs[1]))
+        return model, [model["trainer"], second]
+
+    def step(model, trainer):
+        feed(model, src, tgt, train=True)
+        return float(trainer.train_step()["losses"][0])
+
+    model, trainers = make()
+    params = oracle_params_for(model)
+    model["arena"].load_dict(params)
+    p32 = {n: v.clone() for n, v in params.items()}
+    shared_p = {n: v.clone() for n, v in params.items()}     # what ONE state for both trainers would give
+    states, shared = [O.AdamState(p32), O.AdamState(p32)], O.AdamState(shared_p)
+    spec = oracle_spec(TOY["maxout"], TOY["max_len"], TOY["supress_unk"])
+    order = [0, 0, 1, 0, 1]
+    for which in order:
+        loss = step(model, trainers[which])
+        ref = O.train_step(p32, spec, "sentence_encoder", src, tgt.t(), states[which], lr=lrs[which])
+        O.train_step(shared_p, spec, "sentence_encoder", src, tgt.t(), shared, lr=lrs[which])
+        assert abs(loss - float(ref["loss"])) < 1e-4
+    arena = model["arena"]
+    got = arena.state_dict()
+    # Adam moves every element by about lr per step whatever the gradient's size, so rounding noise on the
+    # near-zero gradients shows up at a few per cent of one step (the same with a single trainer); sharing the
+    # state between the optimizers would show up at the size of a step
+    assert max(max_abs(got[n], p32[n]) for n in p32) < 1e-3
+    assert max(max_abs(got[n], shared_p[n]) for n in p32) > 3e-3
+    assert runtime.global_step() == len(order)
+    assert [t.optimizer.steps for t in trainers] == [3, 2] == [s.t for s in states]
+    slots = arena.optimizer_slots
+    assert len(slots) == 2 and slots[0][1] is arena.adam_m and slots[1][1] is not arena.adam_m
+    for (opt, m, _v), st in zip(slots, states):
+        flat = arena.moment_dict(m)
+        assert max(max_abs(flat[n], st.m[n]) for n in flat) < 1e-5
+
+    # checkpoint -> fresh model: moments of both optimizers, their update counts and the global step resume
+    path = str(tmp_path / "variables.data")
+    manager = TensorFlowManager(num_sessions=1, num_threads=1)
+    manager.save(path)
+    next_losses = [step(model, trainers[1]), step(model, trainers[0])]
+    want = model["arena"].state_dict()
+
+    model2, trainers2 = make()
+    manager2 = TensorFlowManager(num_sessions=1, num_threads=1)
+    manager2.restore(path)
+    assert runtime.global_step() == len(order)
+    # the continued run uses its trainers in the same order of first use as the run that wrote the file
+    # (slot 0 = first optimizer that ever stepped): here trainer 0 first, as above
+    trainers2[0].optimizer.steps, trainers2[1].optimizer.steps = 0, 0
+    model2["arena"].optimizer_slot(trainers2[0].optimizer)
+    model2["arena"].optimizer_slot(trainers2[1].optimizer)
+    assert [t.optimizer.steps for t in trainers2] == [3, 2]
+    again = [step(model2, trainers2[1]), step(model2, trainers2[0])]
+    assert max(abs(a - b) for a, b in zip(again, next_losses)) < 1e-6
+    got = model2["arena"].state_dict()
+    assert max(max_abs(got[n], want[n]) for n in want) < 1e-6
