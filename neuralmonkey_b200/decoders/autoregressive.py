@@ -349,24 +349,74 @@ class AutoregressiveDecoder(ModelPart):
         return LoopState(histories=next_histories, constants=loop_state.constants,
                          feedables=next_feedables)
 
+    def get_body(self, train_mode: bool, sample: bool = False, temperature: float = 1.):
+        """The loop body as a callable over a LoopState (autoregressive.py:442-517).  Run time without
+        sampling at temperature 1 is `body` (fused logits + argmax).  `sample=True` draws the next symbols from
+        softmax(logits / temperature) - tf.multinomial over the logits, what the RL trainer's sampling pass asks
+        for (trainers/rl_trainer.py:124) - and a temperature other than 1 divides the logits that enter the
+        histories, as the reference does before choosing the symbols.  The teacher-forced pass is not stepped
+        in this package (`train_logits` & co. come from whole-sequence kernels), so `train_mode=True` is
+        refused here."""
+        if train_mode:
+            raise NotImplementedError(
+                "the teacher-forced pass is not stepped: use train_logits / train_output_states / train_xents")
+        if not sample and float(temperature) == 1.0:
+            return self.body
+        temperature = float(temperature)
+
+        def body(loop_state: LoopState) -> LoopState:
+            feedables = loop_state.feedables
+            histories = loop_state.histories
+            output_state, dec_other, hist_other = self.next_state(loop_state)
+            logits, _lse, argmax = self.state_to_logits(output_state)
+            if temperature != 1.0:
+                logits = logits / temperature       # argmax is unchanged by a positive scale
+            if sample:
+                probs = torch.softmax(logits, dim=-1)
+                next_symbols = torch.multinomial(probs, num_samples=1).squeeze(1)
+            else:
+                next_symbols = argmax
+            next_symbols = next_symbols * (~feedables.finished).to(torch.int64)
+            finished = feedables.finished | (next_symbols == END_TOKEN_INDEX)
+            next_feedables = DecoderFeedables(
+                step=feedables.step + 1, finished=finished,
+                embedded_input=self.embed_input_symbols(next_symbols), other=dec_other)
+            histories.logits.append(logits)
+            histories.output_states.append(output_state)
+            histories.output_symbols.append(next_symbols)
+            histories.output_mask.append(~finished)
+            return LoopState(histories=histories._replace(other=hist_other), constants=loop_state.constants,
+                             feedables=next_feedables)
+
+        return body
+
+    def decoding_loop(self, train_mode: bool, sample: bool = False, temperature: float = 1) -> LoopState:
+        """Run the decoding loop with the body of `get_body` until every hypothesis has finished or
+        `max_output_len` steps were taken (autoregressive.py:425-437,532-562); the histories are lists of
+        per-step tensors (`torch.stack` them time-major)."""
+        if temperature <= 0:
+            raise ValueError("The softmax temperature must be positive")
+        body = self.get_body(train_mode, sample, temperature)
+        with torch.no_grad():
+            loop_state = self.get_initial_loop_state()
+            step = 0
+            while step < self.max_output_len:
+                loop_state = body(loop_state)
+                step += 1
+                if bool(loop_state.feedables.finished.all()):
+                    break
+            self.finalize_loop(loop_state, train_mode)
+        return loop_state
+
     def finalize_loop(self, final_loop_state: LoopState, train_mode: bool) -> None:
         """Post-loop hook (attention histories etc.)."""
 
     @tensor
     def runtime_loop_result(self) -> LoopState:
         """decoding_loop(train_mode=False) (autoregressive.py:532-562)."""
-        with torch.no_grad():
-            loop_state = self.get_initial_loop_state()
-            step = 0
-            # loop_continue_criterion: not all finished and step < max_output_len (:425-437);
-            # the all-finished test is one device->host flag per step
-            while step < self.max_output_len:
-                loop_state = self.body(loop_state)
-                step += 1
-                if bool(loop_state.feedables.finished.all()):
-                    break
-            self.finalize_loop(loop_state, False)
-        return loop_state
+        # loop_continue_criterion: not all finished and step < max_output_len (:425-437);
+        # the all-finished test is one device->host flag per step
+        return self.decoding_loop(train_mode=False)
 
     @tensor
     def _runtime(self) -> Dict[str, Any]:

@@ -1358,3 +1358,58 @@ def test_every_optimizer_keeps_its_own_adam_state(cpu_model, monkeypatch, tmp_pa
     assert max(abs(a - b) for a, b in zip(again, next_losses)) < 1e-6
     got = model2["arena"].state_dict()
     assert max(max_abs(got[n], want[n]) for n in want) < 1e-6
+
+
+@pytest.mark.parametrize("kind", ["rnn", "transformer"])
+def test_decoding_loop_with_sampling_and_temperature(cpu_model, kind):
+    """`decoding_loop(train_mode=False, sample=..., temperature=...)` / `get_body` (autoregressive.py:442-562,
+    the RL trainer's sampling pass): a temperature divides the logits that enter the histories and leaves the
+    greedy symbols alone; sampled symbols follow softmax(logits / temperature) - at a very low temperature they
+    ARE the greedy symbols, at temperature 1 their first-step frequencies match the first-step distribution -
+    finished hypotheses emit <pad> and stay finished."""
+    if kind == "rnn":
+        model = build_bahdanau(**TOY)
+        model["arena"].load_dict(oracle_params_for(model))
+        src, tgt = random_batch(6, 8, 7, TOY["vs"], TOY["vt"], seed=3)
+        feed(model, src, tgt, train=False)
+    else:
+        from tests.test_gpu_transformer import feed_transformer
+        model, _params, src, tgt, _cfg = _transformer(seed=2, bsz=3)
+        feed_transformer(model, src, tgt, train=False)
+    dec = model["dec"]
+    greedy = dec.decoding_loop(train_mode=False)
+    g_logits = torch.stack(greedy.histories.logits, 0)
+    g_symbols = torch.stack(greedy.histories.output_symbols, 0)
+    assert bool((g_symbols == dec.runtime_symbols).all())
+
+    warm = dec.decoding_loop(train_mode=False, temperature=2.0)
+    assert bool((torch.stack(warm.histories.output_symbols, 0) == g_symbols).all())
+    assert max_abs(torch.stack(warm.histories.logits, 0), g_logits / 2.0) < 1e-6
+
+    torch.manual_seed(0)
+    cold = dec.decoding_loop(train_mode=False, sample=True, temperature=1e-4)
+    c_symbols = torch.stack(cold.histories.output_symbols, 0)
+    assert c_symbols.shape == g_symbols.shape and bool((c_symbols == g_symbols).all())
+
+    torch.manual_seed(1)
+    first = []
+    for _ in range(300):
+        drawn = dec.decoding_loop(train_mode=False, sample=True)
+        sym = torch.stack(drawn.histories.output_symbols, 0)
+        mask = torch.stack(drawn.histories.output_mask, 0)
+        first.append(sym[0])
+        # once </s> (2) was emitted the hypothesis is finished: <pad> (0) afterwards, mask off from that step on
+        ended = torch.cumsum((sym == 2).to(torch.int64), 0) > 0
+        assert bool((sym[1:][ended[:-1]] == 0).all()) and bool((mask == ~ended).all())
+    first = torch.stack(first, 0)                                   # [draws, batch]
+    probs = torch.softmax(g_logits[0], dim=-1)                      # the first step does not depend on the draw
+    vocab = probs.shape[-1]
+    for b in range(first.shape[1]):
+        freq = torch.bincount(first[:, b], minlength=vocab).to(torch.float32) / first.shape[0]
+        assert float((freq - probs[b]).abs().sum()) < 0.6           # total variation of 300 draws over V=70: ~0.4
+        assert float(freq[3]) == 0.0 or not getattr(dec, "supress_unk", False)   # <unk> carries -1e9
+
+    with pytest.raises(NotImplementedError):
+        dec.get_body(train_mode=True)
+    with pytest.raises(ValueError):
+        dec.decoding_loop(train_mode=False, temperature=0.0)
