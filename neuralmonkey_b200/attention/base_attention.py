@@ -58,6 +58,11 @@ class BaseAttention(ModelPart):
                   decoder_input: torch.Tensor, loop_state: Any) -> Tuple[torch.Tensor, Any]:
         raise NotImplementedError("Abstract method")
 
+    def record_weights(self, key: str, weights: torch.Tensor) -> None:
+        """Keep the weights of a whole pass, as `attention_sequence` returned them (batch-major,
+        [batch, NQ, time]), under `key` - time-major, like the histories of a stepped loop."""
+        self.histories[key] = weights.detach().transpose(0, 1)
+
     def initial_loop_state(self) -> Any:
         raise NotImplementedError("Abstract method")
 

@@ -175,6 +175,8 @@ class Decoder(AutoregressiveDecoder):
         self.output_projection.declare(self, self.rnn_size + self.embedding_size + ctx_size)
         for att in self.attentions:
             att.ensure_declared()
+            if hasattr(att, "set_step_owner"):       # head projections live in this decoder's step scope
+                att.set_step_owner(self)
 
     # -- initial state ---------------------------------------------------------------------
     @tensor
@@ -226,8 +228,8 @@ class Decoder(AutoregressiveDecoder):
         outputs, cells, weights = [], [], [[] for _ in self.attentions]
 
         def attend(att, query):
-            ctx, w = att.attention_sequence(query.unsqueeze(1))
-            return ctx[:, 0], w[:, 0]
+            ctx, w = att.attention_sequence(query.unsqueeze(1))    # one query per sentence: NQ = 1
+            return ctx[:, 0], w
 
         for t in range(fed.shape[1]):
             out, prev, _ctx, attended = self._variant_step(emb[:, t], prev, attend)
@@ -235,9 +237,10 @@ class Decoder(AutoregressiveDecoder):
             cells.append(prev[1] if isinstance(prev, tuple) else prev)
             for hist, (_c, w) in zip(weights, attended):
                 hist.append(w)
-        for att, hist in zip(self.attentions, weights):
-            att.histories["{}_train".format(self.name)] = torch.stack(hist, 0).detach()
-        return torch.stack(outputs, 1), torch.stack(cells, 1), [torch.stack(h, 1) for h in weights]
+        weights = [torch.cat(hist, dim=-2) for hist in weights]     # the query axis is the one before time
+        for att, w in zip(self.attentions, weights):
+            att.record_weights("{}_train".format(self.name), w)
+        return torch.stack(outputs, 1), torch.stack(cells, 1), weights
 
     # -- training: all steps at once ------------------------------------------------------
     @tensor
@@ -258,7 +261,7 @@ class Decoder(AutoregressiveDecoder):
             weights.append(w)
         out = self.output_projection(self, dropped, emb, contexts, self.train_mode)  # [B,T,O]
         for att, w in zip(self.attentions, weights):
-            att.histories["{}_train".format(self.name)] = w.detach().transpose(0, 1)
+            att.record_weights("{}_train".format(self.name), w)
         return out, dropped, weights
 
     @property

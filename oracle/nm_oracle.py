@@ -338,7 +338,18 @@ def _decoder_cell(p: Params, spec: RNNDecoderSpec, scope: str, x: torch.Tensor, 
                     p[scope + "candidate/kernel"], p[scope + "candidate/bias"])
 
 
-def decoder_step(p: Params, spec: RNNDecoderSpec, embedded_input, prev_output, hidden, states, mask):
+def multihead_attention_step(p: Params, scope: str, query: torch.Tensor, keys: torch.Tensor,
+                             values: torch.Tensor, keys_mask: Optional[torch.Tensor], heads: int):
+    """MultiHeadAttention.attention / ScaledDotProdAttention (scaled_dot_product.py:296-350): the attention
+    OBJECT an RNN decoder queries once per step - `attention()` over a one-step query sequence; the head
+    projections (heads > 1) are created while the decoder's step scope is open, i.e. `scope` is
+    `<decoder>/attention_decoder`.  Returns (context [B, dim], weights [B, heads, time])."""
+    context, weights = multihead_attention(p, scope, query.unsqueeze(1), keys, values, keys_mask, heads)
+    return context[:, 0], weights[:, :, 0]
+
+
+def decoder_step(p: Params, spec: RNNDecoderSpec, embedded_input, prev_output, hidden, states, mask,
+                 attend: Optional[Sequence[Callable]] = None):
     """Decoder.next_state, GRU / NematusGRU branch, attention_on_input=False (decoder.py:279-358; the
     reference cannot build attention_on_input=True - `feedables.prev_contexts`, :273, does not exist);
     dropout off so prev_rnn_output == cell_output.  With `conditional_gru` the context is run through
@@ -352,12 +363,23 @@ def decoder_step(p: Params, spec: RNNDecoderSpec, embedded_input, prev_output, h
         # return value.  No conditional cell in this branch.
         prev_c, prev_h = prev_output if isinstance(prev_output, tuple) else (prev_output, prev_output)
         new_c, cell_output = lstm_cell(p, step + "lstm_cell/", embedded_input, prev_c, prev_h)
-        context, weights = bahdanau_step(p, spec.att_prefix, cell_output, hidden, states, mask)
+        if attend is not None:
+            attended = [f(cell_output) for f in attend]
+            context, weights = torch.cat([c for c, _w in attended], 1), [w for _c, w in attended]
+        else:
+            context, weights = bahdanau_step(p, spec.att_prefix, cell_output, hidden, states, mask)
         output = output_projection(p, spec, cell_output, embedded_input, context)
         return output, (new_c, cell_output), context, weights
     first = step + ("nematus_gru_cell/" if spec.rnn_cell == "NematusGRU" else "OrthoGRUCell/")
     cell_output = _decoder_cell(p, spec, first, embedded_input, prev_output)
-    context, weights = bahdanau_step(p, spec.att_prefix, cell_output, hidden, states, mask)
+    if attend is not None:
+        # any list of attention objects (decoder.py:290-300): each is queried with the cell output, the
+        # contexts are concatenated in the order of `attentions` wherever they are consumed
+        attended = [f(cell_output) for f in attend]
+        context = torch.cat([c for c, _w in attended], 1)
+        weights = [w for _c, w in attended]
+    else:
+        context, weights = bahdanau_step(p, spec.att_prefix, cell_output, hidden, states, mask)
     if spec.conditional_gru:
         cell_output = _decoder_cell(p, spec, step + "cond_gru_2_cell/", context, cell_output)
     output = output_projection(p, spec, cell_output, embedded_input, context)
@@ -413,19 +435,20 @@ def sequence_xents(logits: torch.Tensor, targets: torch.Tensor, mask: torch.Tens
 
 
 def decoder_train(p: Params, spec: RNNDecoderSpec, enc: Dict[str, torch.Tensor],
-                  train_inputs: torch.Tensor, label_smoothing: Optional[float] = None) -> Dict[str, torch.Tensor]:
+                  train_inputs: torch.Tensor, label_smoothing: Optional[float] = None,
+                  attend: Optional[Sequence[Callable]] = None) -> Dict[str, torch.Tensor]:
     """decoding_loop(train_mode=True) + train_xents/train_loss (autoregressive.py:292-316,532-562).
 
     train_inputs: [T, B] int64 = padded references with </s> appended (feed_dict :579-582),
     already transposed to time-major as `train_inputs` is (:199-202)."""
     emb = p[spec.prefix + "/word_embeddings"]
     _steps, bsz = train_inputs.shape
-    states, mask = enc["temporal_states"], enc["temporal_mask"]
-    hidden = bahdanau_precompute(p, spec.att_prefix, states)
+    states, mask = enc.get("temporal_states"), enc.get("temporal_mask")
+    hidden = bahdanau_precompute(p, spec.att_prefix, states) if attend is None else None
     rnn = {"prev": decoder_initial_state(p, spec, enc.get("output"), enc, bsz)}
 
     def next_output(embedded, _finished):
-        output, rnn["prev"], _ctx, w = decoder_step(p, spec, embedded, rnn["prev"], hidden, states, mask)
+        output, rnn["prev"], _ctx, w = decoder_step(p, spec, embedded, rnn["prev"], hidden, states, mask, attend)
         return output, (w, rnn["prev"][1] if isinstance(rnn["prev"], tuple) else rnn["prev"])
 
     hist = autoregressive_loop(next_output, lambda o: state_to_logits(p, spec, o), lambda ids: emb[ids], bsz,
@@ -439,22 +462,24 @@ def decoder_train(p: Params, spec: RNNDecoderSpec, enc: Dict[str, torch.Tensor],
     loss = xents.sum() / train_mask.sum()
     return {"train_logits": logits_t, "train_xents": xents.t(), "train_loss": loss,
             "train_mask": train_mask, "train_output_states": torch.stack(out_states, 0),
-            "attention_weights": torch.stack(att_weights, 0),
+            "attention_weights": (torch.stack(att_weights, 0) if attend is None else
+                                  [torch.stack([w[i] for w in att_weights], 0) for i in range(len(attend))]),
             "rnn_outputs": torch.stack(rnn_outputs, 0)}
 
 
 def decoder_greedy(p: Params, spec: RNNDecoderSpec, enc: Dict[str, torch.Tensor],
-                   train_inputs: Optional[torch.Tensor] = None) -> Dict[str, torch.Tensor]:
+                   train_inputs: Optional[torch.Tensor] = None,
+                   attend: Optional[Sequence[Callable]] = None) -> Dict[str, torch.Tensor]:
     """decoding_loop(train_mode=False): argmax feedback (autoregressive.py:446-519) and, when
     references are given, runtime_xents / runtime_loss (:351-371)."""
     emb = p[spec.prefix + "/word_embeddings"]
-    states, mask = enc["temporal_states"], enc["temporal_mask"]
-    bsz = states.shape[0]
-    hidden = bahdanau_precompute(p, spec.att_prefix, states)
+    states, mask = enc.get("temporal_states"), enc.get("temporal_mask")
+    bsz = states.shape[0] if states is not None else enc["output"].shape[0]
+    hidden = bahdanau_precompute(p, spec.att_prefix, states) if attend is None else None
     rnn = {"prev": decoder_initial_state(p, spec, enc.get("output"), enc, bsz)}
 
     def next_output(embedded, _finished):
-        output, rnn["prev"], _ctx, _w = decoder_step(p, spec, embedded, rnn["prev"], hidden, states, mask)
+        output, rnn["prev"], _ctx, _w = decoder_step(p, spec, embedded, rnn["prev"], hidden, states, mask, attend)
         return output, None
 
     hist = autoregressive_loop(next_output, lambda o: state_to_logits(p, spec, o), lambda ids: emb[ids], bsz,

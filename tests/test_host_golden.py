@@ -265,3 +265,33 @@ def test_learning_utils_helpers_match_reference(runner_golden, monkeypatch):
     LU._print_examples({"source": [["s1"]], "target": [["t1"]], "extra": [1]}, {"target": [["o1"]], "rep": [7]},
                        val_preview_input_series=["source", "target"], val_preview_output_series=["target"])
     assert printed == want["lu_examples_selected"]
+
+
+def test_editops_match_the_reference_module():
+    """processors/editops.py against the reference's module run on the same inputs
+    (tests/golden/make_editops_golden.py): the operation scripts - incl. the choice among equally cheap ones -
+    and their application, also of scripts shorter / longer than the source."""
+    import json
+    import os
+    from neuralmonkey_b200.processors import editops
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "editops_golden.json")
+    with open(path, encoding="utf-8") as handle:
+        golden = json.load(handle)
+    assert len(golden["convert"]) > 130
+    for case in golden["convert"]:
+        assert editops.convert_to_edits(case["source"], case["target"]) == case["edits"], case
+        assert editops.reconstruct(case["source"], case["edits"]) == case["target"]
+    for case in golden["reconstruct"]:
+        assert editops.reconstruct(case["source"], case["edits"]) == case["result"], case
+    pre = editops.Preprocess("mt", "pe")
+    rows = list(pre({"mt": lambda: iter([["a", "b"], ["c"]]), "pe": lambda: iter([["a", "c"], ["c"]])}))
+    assert rows == [["<keep>", "c", "<delete>"], ["<keep>"]]        # delete preferred as the LAST operation of a tie
+    post = editops.Postprocess("mt", "edits")
+    assert post({"mt": [["a", "b"]]}, {"edits": [["<keep>", "<delete>", "c"]]}) == [["a", "c"]]
+    for bad in (({}, {"edits": []}), ({"mt": []}, {})):
+        try:
+            post(*bad)
+        except ValueError:
+            pass
+        else:
+            raise AssertionError("missing series must be reported")

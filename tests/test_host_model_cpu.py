@@ -1413,3 +1413,156 @@ def test_decoding_loop_with_sampling_and_temperature(cpu_model, kind):
         dec.get_body(train_mode=True)
     with pytest.raises(ValueError):
         dec.decoding_loop(train_mode=False, temperature=0.0)
+
+
+def _post_edit_model(heads=3, keep=1.0):
+    """tests/post-edit.ini's topology: two recurrent encoders, a MultiHeadAttention whose keys come from one and
+    whose values from the other, a ScaledDotProdAttention over the first, one GRU decoder over both."""
+    from neuralmonkey_b200 import runtime, tf
+    from neuralmonkey_b200.attention import ScaledDotProdAttention
+    from neuralmonkey_b200.attention.scaled_dot_product import MultiHeadAttention
+    from neuralmonkey_b200.decoders import Decoder
+    from neuralmonkey_b200.encoders import SentenceEncoder
+    from neuralmonkey_b200.trainers import CrossEntropyTrainer
+    from neuralmonkey_b200.vocabulary import Vocabulary
+    runtime.reset()
+    vs, vt = 40, 50
+    src_vocab = Vocabulary(["s{}".format(i) for i in range(vs - 4)])
+    tgt_vocab = Vocabulary(["t{}".format(i) for i in range(vt - 4)])
+    src = SentenceEncoder(name="src_encoder", vocabulary=src_vocab, data_id="source", embedding_size=7,
+                          rnn_size=6, max_input_len=9)
+    trans = SentenceEncoder(name="trans_encoder", vocabulary=tgt_vocab, data_id="translated", embedding_size=5,
+                            rnn_size=6, max_input_len=9)
+    mha = MultiHeadAttention(name="attention_trans_encoder", n_heads=heads, keys_encoder=src,
+                             values_encoder=trans, dropout_keep_prob=keep)
+    sdp = ScaledDotProdAttention(name="attention_source_encoder", keys_encoder=src)
+    dec = Decoder(encoders=[trans, src], attentions=[mha, sdp], vocabulary=tgt_vocab, data_id="edits",
+                  name="decoder", max_output_len=8, rnn_size=12, embedding_size=12)
+    trainer = CrossEntropyTrainer(decoders=[dec], optimizer=tf.AdamOptimizer(learning_rate=1e-3))
+    for part in trainer.parameterizeds:
+        part.ensure_declared()
+    runtime.arena().finalize(runtime.device())
+    return {"src": src, "trans": trans, "mha": mha, "sdp": sdp, "dec": dec, "trainer": trainer,
+            "arena": runtime.arena(), "vs": vs, "vt": vt}
+
+
+def _post_edit_feed(model, src_ids, trans_ids, tgt_ids, train):
+    bsz = src_ids.shape[0]
+    model["src"].input_sequence.feed_ids([src_ids], train=train)
+    model["trans"].input_sequence.feed_ids([trans_ids], train=train)
+    for part in (model["src"], model["trans"], model["mha"], model["sdp"]):
+        part.reset_batch()
+        part.train_mode = train
+        part.batch_size = bsz
+    model["dec"].feed_ids(tgt_ids, bsz, train=train)
+
+
+def _post_edit_oracle(p, heads, src_ids, trans_ids, beam=1):
+    so = O.sentence_encoder(p, "src_encoder", src_ids)
+    to = O.sentence_encoder(p, "trans_encoder", trans_ids)
+    rep = (lambda x: x.repeat_interleave(beam, 0)) if beam > 1 else (lambda x: x)
+    keys, kmask, values = rep(so["temporal_states"]), rep(so["temporal_mask"]), rep(to["temporal_states"])
+    attend = [lambda q: O.multihead_attention_step(p, "decoder/attention_decoder", q, keys, values, kmask, heads),
+              lambda q: O.multihead_attention_step(p, "decoder/attention_decoder", q, keys, keys, kmask, 1)]
+    enc = {"output": torch.cat([to["output"], so["output"]], 1)}
+    return enc, attend
+
+
+@pytest.mark.parametrize("heads", [3, 1])
+def test_rnn_decoder_with_scaled_dot_attention_objects(cpu_model, heads):
+    """`attention.ScaledDotProdAttention` / `attention.scaled_dot_product.MultiHeadAttention` as the attentions of
+    an RNN decoder (scaled_dot_product.py:246-402; tests/factored.ini, tests/post-edit.ini): variables (the head
+    projections belong to the decoder's step scope), the hoisted training pass with every gradient, the greedy
+    loop with its per-head histories, and beam search over the tiled keys - against the oracle."""
+    from neuralmonkey_b200.decoders import BeamSearchDecoder
+    model = _post_edit_model(heads)
+    arena, dec = model["arena"], model["dec"]
+    proj = sorted(n for n in arena.order if "_proj/" in n)
+    want_proj = ["decoder/attention_decoder/{}_proj/kernel".format(k) for k in ("keys", "output", "query", "vals")]
+    assert proj == (want_proj if heads > 1 else [])
+    assert not any(n.startswith("attention_") for n in arena.order)      # the attention objects own nothing
+    assert model["mha"].context_vector_size == 12 and model["sdp"].context_vector_size == 12
+    params = oracle_params_for(model)
+    arena.load_dict(params)
+    src, tgt = random_batch(5, 8, 7, model["vs"], model["vt"], seed=4)
+    trans, _ = random_batch(5, 8, 7, model["vt"], model["vt"], seed=5)      # keys and values: one time axis
+
+    _post_edit_feed(model, src, trans, tgt, train=True)
+    p = {n: v.clone().requires_grad_(True) for n, v in params.items()}
+    spec = O.RNNDecoderSpec("decoder", None, 8, "tanh", False)
+    enc, attend = _post_edit_oracle(p, heads, src, trans)
+    odec = O.decoder_train(p, spec, enc, tgt.t(), attend=attend)
+    assert max_abs(dec.train_output_states, odec["train_output_states"]) < 1e-5
+    assert abs(float(dec.train_loss) - float(odec["train_loss"])) < 1e-5
+    for i in range(heads):      # [time, batch, keys] per head, like a stepped loop's history
+        assert max_abs(model["mha"].histories["decoder_train_head{}".format(i)],
+                       odec["attention_weights"][0][:, :, i]) < 1e-5
+    assert max_abs(model["sdp"].histories["decoder_train_head0"], odec["attention_weights"][1][:, :, 0]) < 1e-5
+    dec.train_loss.backward()
+    odec["train_loss"].backward()
+    for name, grad in _grads(model).items():
+        want = p[name].grad if p[name].grad is not None else torch.zeros_like(p[name])
+        got = grad if grad is not None else torch.zeros_like(p[name])
+        assert float((got - want.reshape(got.shape)).norm()) <= 1e-4 * float(want.norm()) + 1e-7, name
+
+    _post_edit_feed(model, src, trans, tgt, train=False)
+    enc, attend = _post_edit_oracle(params, heads, src, trans)
+    og = O.decoder_greedy(params, spec, enc, tgt.t(), attend=attend)
+    assert dec.decode_engine is None            # the fused step kernel covers the Bahdanau attention only
+    assert max_abs(dec.runtime_logits, og["runtime_logits"]) < 1e-4
+    assert bool((dec.runtime_symbols == og["output_symbols"]).all())
+    steps = dec.runtime_symbols.shape[0]
+    for i in range(heads):
+        assert tuple(model["mha"].histories["decoder_run_head{}".format(i)].shape) == (steps, 5, src.shape[1])
+
+    beam, bsz = 3, 4
+    bs = BeamSearchDecoder(name="bs", parent_decoder=dec, beam_size=beam, max_steps=7, length_normalization=1.0)
+    bs.use_cuda_graph = False
+    _post_edit_feed(model, src[:bsz], trans[:bsz], None, train=False)
+    bs.reset_batch()
+    bs.batch_size = bsz
+    out = bs.outputs
+    enc, attend = _post_edit_oracle(params, heads, src[:bsz], trans[:bsz], beam=beam)
+    emb = params["decoder/word_embeddings"]
+    prev0 = O.decoder_initial_state(params, spec, enc["output"]).repeat_interleave(beam, 0)
+
+    def run(embedded, prev):
+        output, cell, _c, _w = O.decoder_step(params, spec, embedded, prev, None, None, None, attend)
+        return cell, torch.log_softmax(O.state_to_logits(params, spec, output), -1)
+
+    prev1, first = run(emb[torch.full((bsz * beam,), O.START, dtype=torch.int64)], prev0)
+    want = O.beam_search(lambda prev, words, _f: run(emb[words], prev), prev1, first, beam, 7, 1.0,
+                         lambda st, idx: st[idx])
+    got = out.last_search_step_output
+    assert bool((got.token_ids[1:] == want["token_ids"]).all())
+    assert max_abs(got.scores, want["scores"]) < 1e-4
+
+
+def test_scaled_dot_attention_objects_validate_their_sizes(cpu_model):
+    """The checks `attention()` makes on the first query (scaled_dot_product.py:148-169) are made when the
+    decoder announces its query size."""
+    from neuralmonkey_b200 import runtime
+    from neuralmonkey_b200.attention import ScaledDotProdAttention
+    from neuralmonkey_b200.attention.scaled_dot_product import MultiHeadAttention
+    from neuralmonkey_b200.decoders import Decoder
+    from neuralmonkey_b200.encoders import SentenceEncoder
+    from neuralmonkey_b200.vocabulary import Vocabulary
+    runtime.reset()
+    vocab = Vocabulary(["a", "b"])
+    enc = SentenceEncoder(name="enc", vocabulary=vocab, data_id="source", embedding_size=4, rnn_size=6,
+                          max_input_len=5)
+    with pytest.raises(ValueError, match="greater than zero"):
+        MultiHeadAttention(name="a0", n_heads=0, keys_encoder=enc)
+    with pytest.raises(ValueError, match="keep prob"):
+        ScaledDotProdAttention(name="a1", keys_encoder=enc, dropout_keep_prob=0.0)
+
+    def decoder(att, size):
+        return Decoder(encoders=[enc], attentions=[att], vocabulary=vocab, data_id="target", name="dec" + att.name,
+                       max_output_len=5, rnn_size=size, embedding_size=size)
+    with pytest.raises(ValueError, match="do not match in the last dimension"):
+        decoder(ScaledDotProdAttention(name="a2", keys_encoder=enc), 10)
+    with pytest.raises(ValueError, match="divisible by the number of heads"):
+        decoder(MultiHeadAttention(name="a3", n_heads=5, keys_encoder=enc), 12)
+    att = ScaledDotProdAttention(name="a4", keys_encoder=enc)
+    feedables, params = decoder(att, 12).get_dependencies()
+    assert att in params and enc in params and att in feedables

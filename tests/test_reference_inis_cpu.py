@@ -1,5 +1,5 @@
-"""The reference's OWN experiment INIs for the hot path (tests/{bahdanau,transformer,beamsearch,small}.ini
-of /root/reference, the ones `tests/tests_run.sh` trains), unchanged, through this package's
+"""The reference's OWN experiment INIs for the hot path (tests/{bahdanau,transformer,beamsearch,small,
+factored,post-edit}.ini of /root/reference, the ones `tests/tests_run.sh` trains), unchanged, through this package's
 `neuralmonkey-train` entry point - on the CPU over the stand-in operations of tests/cpu_ops.py.
 What is exercised is everything but the kernels: the INI grammar with variables and environment
 substitution, `class=` resolution against this package, constructor signatures and validation, datasets
@@ -26,6 +26,11 @@ CASES = {
     "transformer": [],
     "beamsearch": [],
     "small": ['main.evaluation=[("target", $bleu), ("target", evaluators.ChrF3)]'],
+    # FactoredEncoder + attention.ScaledDotProdAttention as the RNN decoder's attention object
+    "factored": [],
+    # two encoders (GRU and LSTM), MultiHeadAttention (3 heads, keys and values from different encoders) +
+    # ScaledDotProdAttention on one decoder, the edit-operation pre/postprocessors; pyter's TER dropped
+    "post-edit": ['main.evaluation=[("target", <bleu>)]'],
 }
 
 
