@@ -6,7 +6,8 @@ from typing import List
 from neuralmonkey_b200.evaluators.bleu import BLEU, BLEU1, BLEU2, BLEU4, BLEUEvaluator
 from neuralmonkey_b200.evaluators.metrics import (AverageEvaluator, ChrFEvaluator, EditDistanceEvaluator,
                                                   MeanSquaredErrorEvaluator,
-                                                  PairwiseMeanSquaredErrorEvaluator, TEREvaluator,
+                                                  PairwiseMeanSquaredErrorEvaluator, PerplexityEvaluator,
+                                                  TEREvaluator,
                                                   WEREvaluator)
 
 

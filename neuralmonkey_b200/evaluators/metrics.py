@@ -143,6 +143,21 @@ class AverageEvaluator(_Metric):
         return hypothesis
 
 
+class PerplexityEvaluator(_Metric):
+    """2 ** (sum of a runner's per-position cross-entropies / number of non-zero ones): masked positions carry a
+    cross-entropy of exactly 0 and do not count (evaluators/perplexity.py; tests/language-model.ini feeds it the
+    XentRunner's series).  NaN for a batch without any counted position.  The reference leaves `compare_scores`
+    at the base class's "higher is better"; the INI sets `minimize_metric=True` instead."""
+
+    def score_batch(self, hypotheses, references) -> float:
+        _check(hypotheses, references)
+        total = sum(float(x) for row in hypotheses for x in row)
+        counted = sum(1 for row in hypotheses for x in row if x != 0.0)
+        if counted == 0:
+            return float("nan")
+        return float(2 ** (total / counted))
+
+
 class MeanSquaredErrorEvaluator(_Metric):
     """Mean of the element-wise squared errors of the whole batch (evaluators/mse.py:7-22)."""
     higher_is_better = False

@@ -450,3 +450,42 @@ def test_model_part_save_and_load(tmp_path, monkeypatch):
     else:
         raise AssertionError("executors without `parameterizeds` must be refused")
     runtime.reset()
+
+
+def test_word2vec_files_and_the_perplexity_evaluator(tmp_path):
+    """util/word2vec.py (vocabulary + embedding initialiser from a word2vec text file: special tokens first,
+    zeros unless the file has them) and evaluators.PerplexityEvaluator (2 ** mean of the non-zero
+    cross-entropies), as tests/language-model.ini uses them; compared with the reference's module when the
+    reference tree is there."""
+    import numpy as np
+    from neuralmonkey_b200.evaluators import PerplexityEvaluator
+    from neuralmonkey_b200.util import word2vec
+    path = tmp_path / "toy.w2v"
+    path.write_text("3 2\nhello 0.5 -1\n</s> 0.25 0.75\nworld 2 3\n")
+    w2v = word2vec.Word2Vec(str(path))
+    assert w2v.vocabulary.index_to_word == ["<pad>", "<s>", "</s>", "<unk>", "hello", "world"]
+    assert w2v.embeddings.tolist() == [[0, 0], [0, 0], [0.25, 0.75], [0, 0], [0.5, -1], [2, 3]]
+    assert word2vec.word2vec_vocabulary(w2v) is w2v.vocabulary
+    init = word2vec.get_word2vec_initializer(w2v)
+    assert init([6, 2], None).tolist() == w2v.embeddings.tolist()
+    with pytest.raises(ValueError, match="do not match"):
+        init([6, 3], None)
+    arena = ParameterArena()
+    arena.declare("decoder/word_embeddings", [6, 2], init)
+    arena.finalize(torch.device("cpu"))
+    assert arena.get("decoder/word_embeddings").tolist() == w2v.embeddings.tolist()
+
+    ppl = PerplexityEvaluator("perplexity")
+    assert ppl([[1.0, 3.0, 0.0], [2.0, 0.0, 0.0]], [[], []]) == 2 ** 2.0
+    assert ppl([[0.0]], [[]]) != ppl([[0.0]], [[]])          # NaN: nothing counted
+    sample = "/root/reference/tests/data/sample.w2v"
+    module = "/root/reference/neuralmonkey/util/word2vec.py"
+    if os.path.exists(sample) and os.path.exists(module):
+        code = open(module).read().replace("from typeguard import check_argument_types", "") \
+            .replace("from neuralmonkey.vocabulary import", "from neuralmonkey_b200.vocabulary import") \
+            .replace("check_argument_types()", "").replace("np.float)", "np.float64)")
+        ref = {}
+        exec(compile(code, module, "exec"), ref)            # the reference's own loader, its imports redirected
+        theirs, ours = ref["Word2Vec"](sample), word2vec.Word2Vec(sample)
+        assert np.array_equal(theirs.embeddings, ours.embeddings)
+        assert theirs.vocabulary.index_to_word == ours.vocabulary.index_to_word

@@ -31,6 +31,8 @@ CASES = {
     # two encoders (GRU and LSTM), MultiHeadAttention (3 heads, keys and values from different encoders) +
     # ScaledDotProdAttention on one decoder, the edit-operation pre/postprocessors; pyter's TER dropped
     "post-edit": ['main.evaluation=[("target", <bleu>)]'],
+    # an RNN decoder without encoders, word2vec-initialised embeddings, XentRunner + PerplexityEvaluator
+    "language-model": [],
 }
 
 
@@ -63,6 +65,8 @@ def test_reference_ini_trains_unchanged(monkeypatch, tmp_path, name):
         assert os.path.exists(os.path.join(out, "encoded.npy"))
     if name == "beamsearch":
         assert "beam_search_score" in log_text
+    if name == "language-model":
+        assert "xents/perplexity" in log_text
 
 
 _FEATURES_INI = """
