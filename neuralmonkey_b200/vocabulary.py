@@ -12,6 +12,7 @@ import numpy as np
 import torch
 
 from neuralmonkey_b200.logging import log, notice, warn
+from neuralmonkey_b200.typecheck import check_argument_types
 
 PAD_TOKEN = "<pad>"
 START_TOKEN = "<s>"
@@ -64,6 +65,24 @@ def from_wordlist(path: str, encoding: str = "utf-8", contains_header: bool = Tr
             words.append(word)
             line_number += 1
     log("Vocabulary from wordlist loaded, containing {} words".format(len(words)))
+    return Vocabulary(words)
+
+
+def from_t2t_vocabulary(path: str, encoding: str = "utf-8") -> "Vocabulary":
+    """A vocabulary file written by tensor2tensor (vocabulary.py:102-134): one entry per line, usually
+    wrapped in a pair of single or double quotes (stripped); T2T's own `<pad>` and `<EOS>` entries are dropped,
+    the special tokens of this toolkit take the first four indices as always."""
+    check_argument_types()
+    words = []  # type: List[str]
+    with open(path, encoding=encoding) as wordlist:
+        for line in wordlist:
+            entry = line.strip()
+            if entry and entry[0] == entry[-1] and entry[0] in "'\"":
+                entry = entry[1:-1]
+            if entry in ("<pad>", "<EOS>"):
+                continue
+            words.append(entry)
+    log("Vocabulary form wordlist loaded, containing {} words".format(len(words)))
     return Vocabulary(words)
 
 

@@ -25,6 +25,9 @@ CORPUS = ["a", "b c", "d e f", "g h i j", "k l m n o", "p", "q r", "s t u v w x 
 TEXT_LINES = ["Hello, world!  It's 42.", "  leading and trailing  ", "naive café: 3.14 -- ok", "x", "a+b=c (d)",
               "Ünïcödé ... \u4e2d\u6587 test"]
 TSV_LINES = ["id1\tthe first text\tlabel a", "id2\t second  text \tlabel b", "id3\tthird"]
+T2T_VOCAB_LINES = ["'<pad>'", "'<EOS>'", "'hello_'", '"quoted"', "plain", "'", "''", "'a\"", "  'spaced'  ", "<pad>",
+                   "x'y", "'it''s'"]
+XENT_ROWS = [[1.0, 3.0, 0.0], [2.0, 0.0, 0.0], [0.25, 0.5, 4.0]]
 CSV_LINES = ['one two, "quoted, with comma", x y', 'three, plain field, z', 'four five,,']
 
 
@@ -97,6 +100,11 @@ def main():
         padded = V.pad_batch([list(s) for s in SENTENCES], max_len, start, end)
         key = "pad_{}_{}_{}".format(max_len, int(start), int(end))
         out[key] = [list(s) for s in padded]
+    with tempfile.TemporaryDirectory() as tmp:
+        path = os.path.join(tmp, "vocab.t2t")
+        with open(path, "w") as f:
+            f.write("\n".join(T2T_VOCAB_LINES) + "\n")
+        out["t2t_vocabulary"] = list(V.from_t2t_vocabulary(path).index_to_word)
     out["sentence_mask_rule"] = "id != 0"
     vectors = np.array([[4, 5, 6, 2, 0], [7, 8, 2, 0, 0], [3, 3, 3, 3, 3]]).T      # time-major
     out["vectors_to_sentences"] = vocab.vectors_to_sentences(vectors)
@@ -165,6 +173,9 @@ def main():
         "pairwise_mse": float(PairwiseMSE([[1.0, 2.0, 3.0], [0.5]], [[1.5, 2.0, 1.0], [0.0]])),
         "pairwise_mse_name": PairwiseMSE.name,
         "average": float(AverageEvaluator("avg")([1.0, 2.5, 4.0], [0.0, 0.0, 0.0]))}
+    from neuralmonkey.evaluators.perplexity import PerplexityEvaluator
+    out["more_evaluators"]["perplexity"] = float(PerplexityEvaluator("perplexity")(XENT_ROWS, [[], [], []]))
+    out["more_evaluators"]["perplexity_name"] = PerplexityEvaluator("perplexity").name
     # ---- helpers -----------------------------------------------------------------------------------
     from neuralmonkey.processors import helpers as H
     out["char_based"] = [H.preprocess_char_based(s) for s in SENTENCES]
@@ -205,7 +216,8 @@ def main():
         AutoWriter(os.path.join(tmp, "g"), np.arange(6).reshape(2, 3))
         out["writer_auto_npy"] = np.load(os.path.join(tmp, "g.npy")).tolist()
     out["inputs"] = {"text_lines": TEXT_LINES, "tsv_lines": TSV_LINES, "csv_lines": CSV_LINES,
-                     "sentences": SENTENCES, "words": WORDS, "hyps": HYPS, "refs": REFS, "corpus": CORPUS}
+                     "sentences": SENTENCES, "words": WORDS, "hyps": HYPS, "refs": REFS, "corpus": CORPUS,
+                     "t2t_vocab_lines": T2T_VOCAB_LINES, "xent_rows": XENT_ROWS}
     json.dump(out, open(os.path.join(HERE, "host_golden.json"), "w"), indent=1, sort_keys=True)
     print({k: (v if not isinstance(v, list) else "...") for k, v in out.items()})
 

@@ -35,6 +35,14 @@ def test_vocabulary_and_padding_match_reference(golden, tmp_path):
     assert vocab.vectors_to_sentences(vectors) == golden["vectors_to_sentences"]
 
 
+def test_t2t_vocabulary_matches_reference(golden, tmp_path):
+    """`vocabulary.from_t2t_vocabulary` (vocabulary.py:102-134) on quoted, unquoted and degenerate lines."""
+    from neuralmonkey_b200.vocabulary import from_t2t_vocabulary
+    path = tmp_path / "vocab.t2t"
+    path.write_text("\n".join(golden["inputs"]["t2t_vocab_lines"]) + "\n")
+    assert from_t2t_vocabulary(str(path)).index_to_word == golden["t2t_vocabulary"]
+
+
 def test_strings_to_indices_follow_the_reference_vocabulary_order(golden, tmp_path):
     from neuralmonkey_b200.vocabulary import pad_batch
     vocab = _vocab(tmp_path, golden["inputs"]["words"])
@@ -217,6 +225,10 @@ def test_further_evaluators_match_reference(golden):
     assert E.MSE.name == want["mse_name"] and E.PairwiseMSE.name == want["pairwise_mse_name"]
     assert E.PairwiseMSE([[1.0, 2.0, 3.0], [0.5]], [[1.5, 2.0, 1.0], [0.0]]) == pytest.approx(want["pairwise_mse"])
     assert E.AverageEvaluator("avg")([1.0, 2.5, 4.0], [0.0, 0.0, 0.0]) == pytest.approx(want["average"])
+    rows = golden["inputs"]["xent_rows"]
+    ppl = E.PerplexityEvaluator("perplexity")
+    assert ppl(rows, [[] for _ in rows]) == pytest.approx(want["perplexity"], rel=1e-12)
+    assert ppl.name == want["perplexity_name"]
     # word error rate: Levenshtein over words, summed, over the summed reference lengths
     assert E.WER([["a", "b"], []], [["a", "c", "d"], ["x"]]) == pytest.approx((2 + 1) / 4)
     with pytest.raises(ImportError, match="pyter"):
