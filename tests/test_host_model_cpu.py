@@ -1566,3 +1566,61 @@ def test_scaled_dot_attention_objects_validate_their_sizes(cpu_model):
     att = ScaledDotProdAttention(name="a4", keys_encoder=enc)
     feedables, params = decoder(att, 12).get_dependencies()
     assert att in params and enc in params and att in feedables
+
+
+def test_gradient_blocking_views_freeze_the_encoder(cpu_model):
+    """model.gradient_blocking.{StatefulView,TemporalStatefulView} (tests/bpe.ini, second run of tests_run.sh):
+    a decoder and an attention over VIEWS of the encoder compute what they compute over the encoder itself,
+    their own gradients are unchanged, and nothing reaches the encoder's variables; the wrapped encoder is still
+    found as a dependency (variables declared, batches fed)."""
+    from neuralmonkey_b200 import runtime
+    from neuralmonkey_b200.attention import Attention
+    from neuralmonkey_b200.decoders import Decoder
+    from neuralmonkey_b200.decoders.output_projection import maxout_output
+    from neuralmonkey_b200.encoders import SentenceEncoder
+    from neuralmonkey_b200.model.gradient_blocking import SpatialStatefulView, StatefulView, TemporalStatefulView
+    from neuralmonkey_b200.trainers import CrossEntropyTrainer
+    from neuralmonkey_b200.vocabulary import Vocabulary
+
+    plain = build_bahdanau(**TOY)
+    params = oracle_params_for(plain)
+    plain["arena"].load_dict(params)
+    src, tgt = random_batch(6, 8, 7, TOY["vs"], TOY["vt"], seed=0)
+    feed(plain, src, tgt, train=True)
+    want_loss = float(plain["dec"].train_loss)
+    plain["dec"].train_loss.backward()
+    want = {n: (g.clone() if g is not None else None) for n, g in _grads(plain).items()}
+
+    runtime.reset()
+    src_vocab = Vocabulary(["s{}".format(i) for i in range(TOY["vs"] - 4)])
+    tgt_vocab = Vocabulary(["t{}".format(i) for i in range(TOY["vt"] - 4)])
+    enc = SentenceEncoder(name="sentence_encoder", vocabulary=src_vocab, data_id="source",
+                          embedding_size=TOY["es"], rnn_size=TOY["he"], max_input_len=TOY["max_len"])
+    att = Attention(name="attention", encoder=TemporalStatefulView(enc))
+    dec = Decoder(encoders=[StatefulView(enc)], vocabulary=tgt_vocab, data_id="target", name="decoder",
+                  max_output_len=TOY["max_len"], rnn_size=TOY["hd"], embedding_size=TOY["et"], attentions=[att],
+                  output_projection=maxout_output(TOY["out"]), supress_unk=True)
+    trainer = CrossEntropyTrainer(decoders=[dec])
+    feedables, parameterizeds = trainer.get_dependencies()
+    assert enc in parameterizeds and enc in feedables and enc.input_sequence in feedables
+    for part in parameterizeds:
+        part.ensure_declared()
+    runtime.arena().finalize(runtime.device())
+    frozen = {"enc": enc, "att": att, "dec": dec, "trainer": trainer, "arena": runtime.arena()}
+    assert sorted(frozen["arena"].order) == sorted(params)
+    frozen["arena"].load_dict(params)
+    feed(frozen, src, tgt, train=True)
+    assert abs(float(dec.train_loss) - want_loss) < 1e-6
+    dec.train_loss.backward()
+    for name, grad in _grads(frozen).items():
+        upstream = name.startswith("sentence_encoder")
+        if upstream:
+            assert grad is None or float(grad.abs().max()) == 0.0, name
+        elif want[name] is not None:
+            assert max_abs(grad, want[name]) < 1e-6, name
+    assert any(n.startswith("sentence_encoder") and want[n] is not None and float(want[n].abs().max()) > 0
+               for n in want)
+    view = TemporalStatefulView(enc)
+    assert view.dimension == enc.dimension and view.temporal_mask is enc.temporal_mask
+    assert not view.temporal_states.requires_grad and enc.temporal_states.requires_grad
+    assert SpatialStatefulView.__mro__[1].__name__ == "SpatialStateful"
