@@ -867,6 +867,82 @@ def main():
     trainer2 = object.__new__(GenericTrainer)
     trainer2.__dict__.update(dict(var_scopes=["enc", "dec/state"], var_collection="trainable_variables"))
     out["trn_scoped_var_list"] = np.array([v.name for v in trainer2.var_list])
+
+    # ---- the reference's RNN Decoder with scaled-dot attention OBJECTS (attention/scaled_dot_product.py:246-402;
+    #      tests/post-edit.ini): a MultiHeadAttention whose keys and values come from different encoders plus a
+    #      ScaledDotProdAttention, both queried by one GRU decoder.  Records which dense layers the run created
+    #      (the head projections land in the DECODER's step scope) and the per-head histories.  Appended after
+    #      every other case so that their random draws stay what they were. ---------------------------------------
+    from neuralmonkey.attention.scaled_dot_product import MultiHeadAttention, ScaledDotProdAttention
+
+    def rnn_multihead_case(tag, heads):
+        nb, tx, hsz, vsz, max_len = 3, 5, 12, 12, 5
+        esz = hsz                                         # default tanh projection: output dimension = rnn_size
+        dname = "md_" + tag
+        first = len(shim.VARIABLES)
+        var = shim.VARIABLES
+        var[dname + "/initial_state/encoders_projection/kernel"] = f32(2 * hsz, hsz, scale=0.4)
+        var[dname + "/initial_state/encoders_projection/bias"] = f32(hsz, scale=0.3)
+        cell = dname + "/attention_decoder/OrthoGRUCell/"
+        var[cell + "gates/kernel"], var[cell + "gates/bias"] = f32(esz + hsz, 2 * hsz, scale=0.5), 1.0 + f32(2 * hsz, scale=0.2)
+        var[cell + "candidate/kernel"], var[cell + "candidate/bias"] = f32(esz + hsz, hsz, scale=0.5), f32(hsz, scale=0.2)
+        proj = dname + "/attention_decoder/dense/"
+        var[proj + "kernel"], var[proj + "bias"] = f32(hsz + esz + 2 * hsz, hsz, scale=0.4), f32(hsz, scale=0.3)
+        if heads > 1:
+            for name in ("query_proj", "keys_proj", "vals_proj", "output_proj"):
+                var["{}/attention_decoder/{}/kernel".format(dname, name)] = f32(hsz, hsz, scale=0.4)
+        for name in list(var)[first:]:
+            out["mv::" + name] = var[name]
+        keys, values = f32(nb, tx, hsz), f32(nb, tx, hsz)
+        enc_outs = [f32(nb, hsz), f32(nb, hsz)]
+        amask = np.array([[1, 1, 1, 1, 0], [1, 1, 1, 1, 1], [1, 1, 0, 0, 0]], np.float32)
+        dec_w, dec_b, table = f32(hsz, vsz, scale=0.8), f32(vsz, scale=0.3), f32(vsz, esz)
+        gold = np.array([[5, 6, 7, 2, 0], [7, 8, 9, 4, 2], [4, 2, 0, 0, 0]], np.int64).T
+        pre = "md_{}_".format(tag)
+        out.update({pre + "keys": keys, pre + "values": values, pre + "mask": amask, pre + "w": dec_w, pre + "b": dec_b,
+                    pre + "table": table, pre + "gold": gold, pre + "enc_out0": enc_outs[0], pre + "enc_out1": enc_outs[1]})
+        mha = object.__new__(MultiHeadAttention)
+        mha.__dict__.update(dict(
+            _variable_scope=shim.VarScope("ma_" + tag), _reuse=None, _name="ma_" + tag, n_heads=heads,
+            dropout_keep_prob=1.0, train_mode=None, batch_size=nb, _histories={},
+            _attention_keys_cached_placeholder=shim.t(keys), _attention_values_cached_placeholder=shim.t(values),
+            _attention_mask_cached_placeholder=shim.t(amask)))
+        sdp_att = object.__new__(ScaledDotProdAttention)
+        sdp_att.__dict__.update(dict(
+            _variable_scope=shim.VarScope("sa_" + tag), _reuse=None, _name="sa_" + tag, n_heads=1,
+            dropout_keep_prob=1.0, train_mode=None, batch_size=nb, _histories={},
+            _attention_keys_cached_placeholder=shim.t(keys), _attention_values_cached_placeholder=shim.t(keys),
+            _attention_mask_cached_placeholder=shim.t(amask)))
+        rd = object.__new__(Decoder)
+        rd.__dict__.update(dict(
+            vocabulary=list(range(vsz)), supress_unk=False, max_output_len=max_len, batch_size=nb, label_smoothing=None,
+            dropout_keep_prob=1.0, train_mode=None, _embedding_size=esz, embeddings_source=None,
+            _variable_scope=shim.VarScope(dname), _reuse=None, _name=dname,
+            _decoding_w_cached_placeholder=shim.t(dec_w), _decoding_b_cached_placeholder=shim.t(dec_b),
+            _embedding_matrix_cached_placeholder=shim.t(table),
+            _go_symbols_cached_placeholder=shim.t(np.full((nb,), 1, np.int64)),
+            _train_inputs_cached_placeholder=shim.t(gold),
+            encoders=[types.SimpleNamespace(output=shim.t(e)) for e in enc_outs],
+            _output_projection_spec=None, _conditional_gru=False, _attention_on_input=False, _rnn_cell_str="GRU",
+            _rnn_size=hsz, _encoder_projection=None, attentions=[mha, sdp_att],
+            step_scope=shim.VarScope(dname + "/attention_decoder"), encoder_states=lambda: [], encoder_masks=lambda: [],
+            input_projection=lambda *args: LoopState(*args).feedables.embedded_input))
+        shim.USED[:] = []
+        out[pre + "context_sizes"] = np.array([mha.context_vector_size, sdp_att.context_vector_size])
+        out[pre + "train_logits"] = np.asarray(rd.train_logits)
+        out[pre + "train_loss"] = np.asarray(rd.train_loss)
+        out[pre + "train_rnn_outputs"] = np.asarray(rd.train_loop_result.histories.other.rnn_outputs)
+        out[pre + "run_logits"] = np.asarray(rd.runtime_logits)
+        out[pre + "run_symbols"] = np.asarray(rd.runtime_loop_result.histories.output_symbols)
+        for mode in ("train", "run"):
+            for i in range(heads):
+                out["{}{}_mha_head{}".format(pre, mode, i)] = np.asarray(mha.histories["{}_{}_head{}".format(dname, mode, i)])
+            out["{}{}_sdp_head0".format(pre, mode)] = np.asarray(sdp_att.histories["{}_{}_head0".format(dname, mode)])
+        out[pre + "history_keys"] = np.array(sorted(mha.histories) + sorted(sdp_att.histories))
+        out[pre + "dense_names"] = np.array(sorted(set(shim.USED)))
+
+    rnn_multihead_case("h3", 3)
+    rnn_multihead_case("h1", 1)
     np.savez_compressed(os.path.join(HERE, "tf_shim_golden.npz"), **out)
     print(sorted(out))
 

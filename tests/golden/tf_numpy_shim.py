@@ -516,7 +516,7 @@ def install():
     tf.losses = _Namespace("tensorflow.losses")
     tf.losses.softmax_cross_entropy = _softmax_cross_entropy
     tf.control_dependencies = _name_scope_cm
-    tf.squeeze = lambda x, axis=None: t(np.squeeze(np.asarray(x), axis=axis))
+    tf.squeeze = lambda x, axis=None: t(np.squeeze(np.asarray(x), axis=tuple(axis) if isinstance(axis, list) else axis))
     tf.orthogonal_initializer = lambda *a, **k: None
     tf.random_normal_initializer = lambda *a, **k: None
     sys.modules["tensorflow"] = tf

@@ -1624,3 +1624,61 @@ def test_gradient_blocking_views_freeze_the_encoder(cpu_model):
     assert view.dimension == enc.dimension and view.temporal_mask is enc.temporal_mask
     assert not view.temporal_states.requires_grad and enc.temporal_states.requires_grad
     assert SpatialStatefulView.__mro__[1].__name__ == "SpatialStateful"
+
+
+@pytest.mark.parametrize("tag,heads", [("h3", 3), ("h1", 1)])
+def test_scaled_dot_attention_objects_against_the_reference_run(cpu_model, tag, heads):
+    """The PRODUCT's Decoder with MultiHeadAttention + ScaledDotProdAttention against the REFERENCE's classes run
+    over the TF stand-in (tests/golden/make_tf_shim_golden.py, `rnn_multihead_case`): the reference's variables
+    under the reference's names (the name sets must be equal: head projections in the decoder's step scope),
+    training logits / loss, the greedy loop, per-head attention histories under the reference's keys."""
+    from neuralmonkey_b200 import runtime
+    from neuralmonkey_b200.attention import ScaledDotProdAttention
+    from neuralmonkey_b200.attention.scaled_dot_product import MultiHeadAttention
+    from neuralmonkey_b200.decoders import Decoder
+    from neuralmonkey_b200.vocabulary import Vocabulary
+    golden = _golden()
+    dname, pre = "md_" + tag, "md_{}_".format(tag)
+    g = lambda n: torch.from_numpy(golden[pre + n])
+    runtime.reset()
+    keys_enc = _stub_encoder(g("keys"), g("mask"), g("enc_out1"))
+    vals_enc = _stub_encoder(g("values"), g("mask"), g("enc_out0"))
+    table = g("table")
+    vocab = Vocabulary(["t{}".format(i) for i in range(table.shape[0] - 4)])
+    mha = MultiHeadAttention(name="ma_" + tag, n_heads=heads, keys_encoder=keys_enc, values_encoder=vals_enc)
+    sdp = ScaledDotProdAttention(name="sa_" + tag, keys_encoder=keys_enc)
+    gold = g("gold").t().contiguous()
+    dec = Decoder(encoders=[vals_enc, keys_enc], vocabulary=vocab, data_id="target", name=dname,
+                  max_output_len=gold.shape[1], rnn_size=12, embedding_size=12, attentions=[mha, sdp])
+    for part in (mha, sdp, dec):
+        part.ensure_declared()
+    arena = runtime.arena()
+    arena.finalize(runtime.device())
+    reference_vars = {k[4:]: torch.from_numpy(golden[k]) for k in golden.files if k.startswith("mv::" + dname + "/")}
+    reference_vars[dname + "/word_embeddings"] = table
+    reference_vars[dname + "/state_to_word_W"], reference_vars[dname + "/state_to_word_b"] = g("w"), g("b")
+    assert set(arena.order) == set(reference_vars), set(arena.order) ^ set(reference_vars)
+    arena.load_dict({n: v.reshape(arena.variables[n].shape) for n, v in reference_vars.items()})
+    assert [mha.context_vector_size, sdp.context_vector_size] == golden[pre + "context_sizes"].tolist()
+    bsz = gold.shape[0]
+
+    def feed_all(train):
+        for att in (mha, sdp):
+            att.reset_batch()
+            att.train_mode, att.batch_size = train, bsz
+        dec.feed_ids(gold, bsz, train=train)
+
+    feed_all(True)
+    assert max_abs(dec.train_logits, g("train_logits")) < 2e-5
+    assert abs(float(dec.train_loss) - float(golden[pre + "train_loss"])) < 2e-5
+    for i in range(heads):
+        assert max_abs(mha.histories["{}_train_head{}".format(dname, i)], g("train_mha_head{}".format(i))) < 1e-5
+    assert max_abs(sdp.histories[dname + "_train_head0"], g("train_sdp_head0")) < 1e-5
+    feed_all(False)
+    assert dec.runtime_logits.shape == g("run_logits").shape
+    assert max_abs(dec.runtime_logits, g("run_logits")) < 2e-5
+    assert bool((dec.runtime_symbols == g("run_symbols")).all())
+    for i in range(heads):
+        assert max_abs(mha.histories["{}_run_head{}".format(dname, i)], g("run_mha_head{}".format(i))) < 1e-5
+    assert max_abs(sdp.histories[dname + "_run_head0"], g("run_sdp_head0")) < 1e-5
+    assert sorted(list(mha.histories) + list(sdp.histories)) == sorted(golden[pre + "history_keys"].tolist())

@@ -580,3 +580,39 @@ def test_transformer_training_logits_ignore_supress_unk():
     keep = np.arange(G["tloop_unk_run_logits"].shape[-1]) != O.UNK
     assert np.abs(run["logits"].numpy()[..., keep] - G["tloop_unk_run_logits"][..., keep]).max() < 5e-5
     assert float(G["tloop_unk_run_logits"][..., O.UNK].max()) < -1e8 and float(run["logits"][..., O.UNK].max()) < -1e8
+
+
+@pytest.mark.parametrize("tag,heads", [("h3", 3), ("h1", 1)])
+def test_rnn_decoder_with_scaled_dot_attention_objects(tag, heads):
+    """The reference's Decoder run whole with a MultiHeadAttention (keys and values from different tensors) and a
+    ScaledDotProdAttention as its attentions (attention/scaled_dot_product.py:246-402, tests/post-edit.ini):
+    the oracle's decoder over a LIST of attention objects reproduces its training pass, greedy loop and per-head
+    histories; the head projections the run created live in the DECODER's step scope."""
+    dname, pre = "md_" + tag, "md_{}_".format(tag)
+    p = {k[4:]: _t(k) for k in G.files if k.startswith("mv::" + dname + "/")}
+    p[dname + "/word_embeddings"] = _t(pre + "table")
+    p[dname + "/state_to_word_W"], p[dname + "/state_to_word_b"] = _t(pre + "w"), _t(pre + "b")
+    want_dense = ["{}/attention_decoder/dense/kernel".format(dname), "{}/initial_state/encoders_projection/kernel".format(dname)]
+    if heads > 1:
+        want_dense += ["{}/attention_decoder/{}_proj/kernel".format(dname, n) for n in ("keys", "output", "query", "vals")]
+    assert sorted(G[pre + "dense_names"].tolist()) == sorted(want_dense)
+    assert G[pre + "context_sizes"].tolist() == [12, 12]
+    keys, values, mask = _t(pre + "keys"), _t(pre + "values"), _t(pre + "mask")
+    scope = dname + "/attention_decoder"
+    attend = [lambda q: O.multihead_attention_step(p, scope, q, keys, values, mask, heads),
+              lambda q: O.multihead_attention_step(p, scope, q, keys, keys, mask, 1)]
+    spec = O.RNNDecoderSpec(dname, None, max_output_len=5, output_projection="tanh")
+    enc = {"output": torch.cat([_t(pre + "enc_out0"), _t(pre + "enc_out1")], 1)}
+    gold = torch.from_numpy(G[pre + "gold"])
+    train = O.decoder_train(p, spec, enc, gold, attend=attend)
+    assert np.abs(train["train_logits"].numpy() - G[pre + "train_logits"]).max() < 1e-5
+    assert np.abs(train["rnn_outputs"].numpy() - G[pre + "train_rnn_outputs"]).max() < 1e-5
+    assert abs(float(train["train_loss"]) - float(G[pre + "train_loss"])) < 1e-5
+    for i in range(heads):
+        assert np.abs(train["attention_weights"][0][:, :, i].numpy() - G["{}train_mha_head{}".format(pre, i)]).max() < 1e-6
+    assert np.abs(train["attention_weights"][1][:, :, 0].numpy() - G[pre + "train_sdp_head0"]).max() < 1e-6
+    run = O.decoder_greedy(p, spec, enc, attend=attend)
+    assert np.array_equal(run["output_symbols"].numpy(), G[pre + "run_symbols"])
+    assert np.abs(run["runtime_logits"].numpy() - G[pre + "run_logits"]).max() < 1e-5
+    keys_want = sorted("{}_{}_head{}".format(dname, m, i) for m in ("train", "run") for i in range(heads))
+    assert G[pre + "history_keys"].tolist() == keys_want + sorted("{}_{}_head0".format(dname, m) for m in ("train", "run"))
