@@ -36,6 +36,8 @@ class TensorFlowManager:
         self._session_params = None   # type: Optional[List[torch.Tensor]]
         self._session_caches = []     # type: List[dict]
         self.num_threads = num_threads  # host threads only matter for the CPU reference
+        if save_n_best < 1:
+            raise Exception("save_n_best parameter must be greater than zero")
         self.saver_max_to_keep = save_n_best
         self.minimize_metric = minimize_metric
         self.best_score_index = 0

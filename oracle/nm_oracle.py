@@ -4,12 +4,22 @@ TEST INFRASTRUCTURE ONLY.  Nothing under neuralmonkey_b200/ may import this
 module; only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
 --impl reference legs do, and only as the checker or the timed CPU baseline.
 
-PARITY UNPINNED.  The reference (ufal/neuralmonkey @ 8b14652) evaluates this path
-with TensorFlow 1.12, which cannot be installed here (Python 3.12, no network),
-and its own tests hold no numeric golden vectors for the path.
-This file therefore restates the reference graph from its source, following the
-files cited at each function, plus the published TF-1.12 semantics of the ops
-they call:
+PARITY: pinned to the reference's own code; the TensorFlow-library primitives are restated.
+The reference (ufal/neuralmonkey @ 8b14652) evaluates this path with TensorFlow
+(`tensorflow>=1.12.0,<1.13`, requirements.txt:13), a third-party dependency that is
+absent from /root/reference and cannot be installed here (Python 3.12, no network);
+its own tests hold no numeric golden vectors for the path.  So:
+
+  * everything the REFERENCE implements - the attention functions and objects, whole
+    encoder / decoder stacks, the decoding loops, beam search, the loss tensors, the
+    trainer's host logic, the host pipeline - is pinned by running the reference's own
+    Python, imported from /root/reference, over a numpy stand-in for the TF ops it
+    calls (tests/golden/tf_numpy_shim.py); the generated vectors and the generating
+    scripts are committed (tests/golden/make_*_golden.py) and this file is tested
+    against them (tests/test_oracle_vs_reference_code.py, tests/test_host_golden.py);
+  * what TensorFlow itself implements is restated below from its published algorithm,
+    with parity anchored on the reference's call sites (scopes, variable names, what is
+    fed to which cell), which the stand-in runs pin:
 
   * tf.contrib.rnn.GRUCell (TF 1.12 rnn_cell_impl.py):
         gate_inputs = matmul(concat([x, h], 1), gates/kernel) + gates/bias
