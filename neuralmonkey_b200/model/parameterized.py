@@ -67,8 +67,8 @@ class Parameterized:
         return [n for n in runtime.arena().order if re.match(self._scope, n)]
 
     def _scope_variables(self) -> Dict[str, torch.Tensor]:
-        state = runtime.arena().state_dict()
-        return {n: state[n] for n in self._scope_names()}
+        arena = runtime.arena()
+        return {n: arena.get(n).detach().cpu().clone() for n in self._scope_names()}
 
     def save(self, session: Any = None) -> None:
         """Save the part's variables to its `save_checkpoint` file (no-op without one)."""
