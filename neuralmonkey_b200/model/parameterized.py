@@ -20,6 +20,10 @@ class Parameterized:
                  load_checkpoint: str = None, initializers: InitializerSpecs = None) -> None:
         self._name = name
         self._reuse = reuse
+        if reuse is not None and initializers is not None:
+            # the variables already exist in the other part's scope (parameterized.py:50-56)
+            raise ValueError("Cannot use initializers in model part '{}' that reuses variables from '{}'."
+                             .format(name, reuse.name))
         self._save_checkpoint = save_checkpoint
         self._load_checkpoint = load_checkpoint
         self._initializers = dict(initializers) if initializers else {}  # type: Dict[str, Any]

@@ -489,3 +489,30 @@ def test_word2vec_files_and_the_perplexity_evaluator(tmp_path):
         theirs, ours = ref["Word2Vec"](sample), word2vec.Word2Vec(sample)
         assert np.array_equal(theirs.embeddings, ours.embeddings)
         assert theirs.vocabulary.index_to_word == ours.vocabulary.index_to_word
+
+
+def test_model_part_reuse_shares_variables():
+    """The reference's tests/test_model_part.py::test_reuse restated without sessions: a part built with
+    `reuse=<other part>` lives in the other part's variable scope - same variables, one copy in the arena - while
+    an independent part of the same shape gets its own, differently initialised ones (parameterized.py:44-60)."""
+    from neuralmonkey_b200 import runtime
+    from neuralmonkey_b200.model.sequence import EmbeddedSequence
+    from neuralmonkey_b200.vocabulary import Vocabulary
+    runtime.reset()
+    vocabulary = Vocabulary(["a", "b"])
+    seq1 = EmbeddedSequence(name="seq1", vocabulary=vocabulary, data_id="id", embedding_size=10)
+    seq2 = EmbeddedSequence(name="seq2", vocabulary=vocabulary, embedding_size=10, data_id="id")
+    seq3 = EmbeddedSequence(name="seq3", vocabulary=vocabulary, data_id="id", embedding_size=10, reuse=seq1)
+    for part in (seq1, seq2, seq3):
+        part.ensure_declared()
+    arena = runtime.arena()
+    arena.finalize(torch.device("cpu"))
+    assert sorted(arena.order) == ["seq1/embedding_matrix_0", "seq2/embedding_matrix_0"]
+    first, second, third = seq1.embedding_matrix, seq2.embedding_matrix, seq3.embedding_matrix
+    assert not torch.equal(first, second)
+    assert torch.equal(first, third) and first.data_ptr() == third.data_ptr()
+    # a reusing part may not bring its own initialisers (parameterized.py:52-56)
+    with pytest.raises(ValueError, match="Cannot use initializers in model part"):
+        EmbeddedSequence(name="seq4", vocabulary=vocabulary, data_id="id", embedding_size=10, reuse=seq1,
+                         initializers=[("embedding_matrix_0", zeros_initializer())])
+    runtime.reset()
