@@ -30,6 +30,9 @@ _BUILTIN_MASK = dropout_mask
 def dropout(variable: torch.Tensor, keep_prob: float, train_mode: bool,
             residual: Optional[torch.Tensor] = None) -> torch.Tensor:
     """dropout(variable) [+ residual]: the residual connection of the Transformer sublayers rides in the same pass."""
+    if keep_prob != 1.0 and not 0.0 < keep_prob <= 1.0:
+        # tf.nn.dropout's check; the reference builds the op whatever the mode, so this is raised in eval mode too
+        raise ValueError("keep_prob must be a scalar tensor or a float in the range (0, 1], got {:g}".format(keep_prob))
     if keep_prob >= 1.0 or not train_mode:
         return variable if residual is None else variable + residual
     if variable.is_cuda and dropout_mask is _BUILTIN_MASK:

@@ -516,3 +516,22 @@ def test_model_part_reuse_shares_variables():
         EmbeddedSequence(name="seq4", vocabulary=vocabulary, data_id="id", embedding_size=10, reuse=seq1,
                          initializers=[("embedding_matrix_0", zeros_initializer())])
     runtime.reset()
+
+
+def test_dropout_helper_as_the_reference_unit_test():
+    """neuralmonkey/tests/test_nn_utils.py restated: invalid keep probabilities raise (tf.nn.dropout's check, in
+    either mode), the dropped share follows 1 - keep_prob with the survivors scaled by 1 / keep_prob, and nothing
+    happens outside training."""
+    from neuralmonkey_b200.nn.utils import dropout
+    var = torch.ones(10000)
+    for kprob in (-1, 2, 0):
+        for mode in (True, False):
+            with pytest.raises(ValueError):
+                dropout(var, kprob, mode)
+    torch.manual_seed(0)
+    for kprob in (0.1, 0.7):
+        dropped = dropout(var, kprob, True)
+        assert abs(int((dropped == 0.0).sum()) - 10000 * (1 - kprob)) < 500
+        assert float(dropped.max()) == pytest.approx(1.0 / kprob)
+    assert float(dropout(var, 0.1, False).sum()) == 10000
+    assert dropout(var, 1.0, True) is var
