@@ -18,7 +18,7 @@ def load_runtime_config(config_path: str) -> Configuration:
     """The second, small INI: `test_datasets` and optionally `variables`."""
     cfg = Configuration()
     cfg.add_argument("test_datasets")
-    cfg.add_argument("variables", required=False, default=None)
+    cfg.add_argument("variables", required=False, default=None, cond=lambda x: x is None or isinstance(x, list))
     cfg.load_file(config_path)
     cfg.build_model()
     return cfg
@@ -28,7 +28,12 @@ def _cli() -> argparse.ArgumentParser:
     cli = argparse.ArgumentParser(description="Runs a model on the given datasets.")
     cli.add_argument("config", metavar="INI-FILE", help="the configuration file of the experiment")
     cli.add_argument("datasets", metavar="INI-TEST-DATASETS", help="the configuration of the test datasets")
-    cli.add_argument("--json", type=str, help="write the evaluation results to this file")
+    cli.add_argument("-s", "--set", type=str, metavar="SETTING", action="append", dest="config_changes", default=[],
+                     help="override an option in the configuration; the syntax is [section.]option=value")
+    cli.add_argument("-v", "--var", type=str, metavar="VAR", default=[], action="append", dest="config_vars",
+                     help="set a variable in the configuration; the syntax is var=value (shorthand for "
+                          "-s vars.var=value)")
+    cli.add_argument("--json", type=str, help="write the evaluation results to this file in JSON format")
     cli.add_argument("-g", "--grid", dest="grid", action="store_true",
                      help="look at the SGE variables for slicing the data")
     return cli
@@ -48,9 +53,10 @@ def _grid_slice(dataset: Dataset) -> Dataset:
 
 def main() -> None:
     args = _cli().parse_args()
-    exp = Experiment(config_path=args.config)
+    runtime_cfg = load_runtime_config(args.datasets)       # first, as the reference does: a bad dataset INI fails early
+    changes = list(args.config_changes) + ["vars.{}".format(v) for v in args.config_vars]
+    exp = Experiment(config_path=args.config, config_changes=changes)
     exp.build_model()
-    runtime_cfg = load_runtime_config(args.datasets)
     exp.load_variables(runtime_cfg.model.variables)
     datasets = runtime_cfg.model.test_datasets
     if args.grid and len(datasets) > 1:
