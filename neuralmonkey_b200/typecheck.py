@@ -80,3 +80,11 @@ def check_argument_types() -> bool:
             raise TypeError('type of argument "{}" must be {}; got {} instead'.format(
                 name, getattr(expected, "__name__", str(expected)), type(value).__name__))
     return True
+
+
+def check_type(name: str, value: Any, expected: Any) -> bool:
+    """One value against one annotation (typeguard's `check_type`), same message as for an argument."""
+    if not _matches(value, expected):
+        raise TypeError('type of argument "{}" must be {}; got {} instead'.format(
+            name, getattr(expected, "__name__", str(expected)), type(value).__name__))
+    return True

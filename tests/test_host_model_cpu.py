@@ -1623,7 +1623,10 @@ def test_gradient_blocking_views_freeze_the_encoder(cpu_model):
     view = TemporalStatefulView(enc)
     assert view.dimension == enc.dimension and view.temporal_mask is enc.temporal_mask
     assert not view.temporal_states.requires_grad and enc.temporal_states.requires_grad
-    assert SpatialStatefulView.__mro__[1].__name__ == "SpatialStateful"
+    from neuralmonkey_b200.model.stateful import SpatialStateful
+    assert issubclass(SpatialStatefulView, SpatialStateful)
+    with pytest.raises(TypeError, match="blocked_object"):
+        StatefulView("not a stateful object")
 
 
 @pytest.mark.parametrize("tag,heads", [("h3", 3), ("h1", 1)])
