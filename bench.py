@@ -59,8 +59,11 @@ def parse_args():
                     help="issue every kernel of a step from Python instead of replaying the captured step")
     ap.add_argument("--no-extras", action="store_true",
                     help="skip the secondary workloads (RNN decoding / transformer / beam-8 / captioning) at N=1")
-    ap.add_argument("--extras", default="rnn_decode,transformer,beam,captioning")
+    ap.add_argument("--extras", default="rnn_decode,transformer,beam,captioning,ende_realistic")
     ap.add_argument("--no-dropout", action="store_true", help="transformer workload: keep_prob 1.0")
+    ap.add_argument("--lengths", default="fixed", choices=["fixed", "realistic"],
+                    help="en-de workload at N=1: 'realistic' draws sentence lengths from a clipped N(0.6 T, 0.2 T) "
+                         "(SURVEY.md 8(d)); the tokens counted are the non-pad target tokens actually in the batches")
     ap.add_argument("--breakdown", action="store_true", help="print the per-entry-point time table")
     return ap.parse_args()
 
@@ -103,11 +106,24 @@ def workload_config(workload, n_gpus, batch, dropout=True):
                                 "exceeds the 126 MB L2"}
 
 
-def synthetic_batch(batch, seed, tx=ENDE["tx"], ty=ENDE["ty"], vocab=ENDE["vocab"]):
+def synthetic_batch(batch, seed, tx=ENDE["tx"], ty=ENDE["ty"], vocab=ENDE["vocab"], realistic=False):
     g = torch.Generator().manual_seed(seed)
     src = torch.randint(4, vocab, (batch, tx), generator=g)
     tgt = torch.randint(4, vocab, (batch, ty), generator=g)
     tgt[:, ty - 1] = 2  # </s>
+    if realistic:
+        # SURVEY.md 8(d), "realistic" variant: lengths ~ N(0.6 T, 0.2 T) clipped to [1, T]; the target length counts
+        # its </s>; one full-length sentence per batch keeps the padded shape (pad_batch pads to the longest
+        # sentence) - and with it the captured step - the same for every batch
+        def lengths(limit):
+            drawn = (torch.randn(batch, generator=g) * 0.2 * limit + 0.6 * limit).round().to(torch.int64)
+            drawn = drawn.clamp(1, limit)
+            drawn[0] = limit
+            return drawn
+        src_len, tgt_len = lengths(tx), lengths(ty)
+        src[torch.arange(tx)[None, :] >= src_len[:, None]] = 0
+        tgt.scatter_(1, (tgt_len - 1)[:, None], 2)
+        tgt[torch.arange(ty)[None, :] >= tgt_len[:, None]] = 0
     return src, tgt
 
 
@@ -372,9 +388,12 @@ def run_b200(args):
     trainer = model.trainer
     dev = model.arena.params.device
     tokens_per_step_rank = batch * ty
+    realistic = args.lengths == "realistic"
+    if realistic and (world > 1 or workload != "ende"):
+        raise SystemExit("--lengths realistic is an N=1 variant of the en-de workload")
 
     # a few distinct synthetic batches, resident on the device (value) and pinned on host (e2e)
-    host_batches = [synthetic_batch(batch, SEED + rank + 1000 * i, tx, ty) for i in range(4)]
+    host_batches = [synthetic_batch(batch, SEED + rank + 1000 * i, tx, ty, realistic=realistic) for i in range(4)]
     pinned = [(s.pin_memory(), t.pin_memory()) for s, t in host_batches]
     # decoder ids stay on the host: feed_ids derives the teacher-forcing inputs there (a few microseconds of
     # integer work) and uploads both id tensors through pinned staging
@@ -446,6 +465,27 @@ def run_b200(args):
         return
     value = world * tokens_per_step_rank / (ms_step * 1e-3)
     e2e_value = world * tokens_per_step_rank / (ms_e2e * 1e-3)
+    if realistic:
+        # the tokens that were in the timed batches: non-pad target positions (sum of train_mask, </s> included)
+        tgt_tokens = [int((t != 0).sum()) for _s, t in host_batches]
+        src_tokens = [int((s_ != 0).sum()) for s_, _t in host_batches]
+        timed = [i % len(host_batches) for i in range(args.steps)]
+        mean_tgt = sum(tgt_tokens[i] for i in timed) / len(timed)
+        mean_src = sum(src_tokens[i] for i in timed) / len(timed)
+        value, e2e_value = mean_tgt / (ms_step * 1e-3), mean_tgt / (ms_e2e * 1e-3)
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps,
+                "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
+                "lengths": "realistic: N(0.6 T, 0.2 T) clipped to [1, T], one full-length sentence per batch",
+                "target_tokens_per_step": mean_tgt, "source_tokens_per_step": mean_src,
+                "padded_positions_per_step": batch * ty,
+                "source_plus_target_tokens_per_sec": (mean_src + mean_tgt) / (ms_step * 1e-3),
+                "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e,
+                        "h2d_bytes_per_step": 2 * batch * (tx + ty) * 8, "d2h_bytes_per_step": 4, "last_loss": loss},
+                "clocks": clocks.summary(), "config": workload_config(workload, world, batch)}
+        line["config"]["lengths"] = line["lengths"]
+        emit(line)
+        bench_models.cleanup()
+        return
 
     peaks = measured_peaks()
     table = sorted(((n, d["ms"] / prof_steps, d["calls"] // prof_steps) for n, d in prof.items()),

@@ -10,6 +10,8 @@ configuration builder) and to the same contract: every workload carries its own 
   beam        : tests/beamsearch.ini at the perf shape - beam 8 x 128 forced steps over that Transformer;
                 emitted tokens/s at batch 64 and latency at batch 1
   captioning  : tests/captioning.ini - frozen VGG-16 conv stack on 224x224 images + Bahdanau decoder; images/s
+  ende_realistic : the headline en-de workload with sentence lengths ~ N(0.6 T, 0.2 T), in a
+                process of its own
 
 Usage: python bench_workloads.py [rnn_decode|transformer|beam|captioning] ...   (one JSON line each)
 """
@@ -473,8 +475,32 @@ def _is_conv_gemm(name: str) -> bool:
     return bool(mm) and int(mm.group(3)) in (27, 28, 576, 1152, 2304, 4608)
 
 
+def run_ende_realistic(cpu=True, steps=10, warmup=3):
+    """SURVEY.md 8(d), "realistic" variant of the headline workload: sentence lengths ~ N(0.6 T, 0.2 T) clipped to
+    [1, T] instead of all = T; tokens/s counts the non-pad target tokens that were in the batches (and
+    source + target tokens/s next to it).  Run as `bench.py --lengths realistic` in a process of its own, after
+    this process released its model: whatever happens there cannot touch the headline measurement."""
+    import os
+    import subprocess
+    del cpu                 # the CPU arm is the fixed-length one of the main line
+    root = os.path.dirname(os.path.abspath(__file__))
+    cmd = [sys.executable, os.path.join(root, "bench.py"), "--gpus", "1", "--steps", str(steps), "--warmup",
+           str(warmup), "--lengths", "realistic", "--no-extras", "--no-cpu-baseline"]
+    env = {k: v for k, v in os.environ.items()
+           if k not in ("RANK", "LOCAL_RANK", "WORLD_SIZE", "MASTER_ADDR", "MASTER_PORT")}
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=root, env=env)
+    lines = [l for l in res.stdout.splitlines() if l.startswith("{")]
+    if res.returncode != 0 or not lines:
+        raise RuntimeError("bench.py --lengths realistic exited with {}: {}".format(
+            res.returncode, res.stderr.strip().splitlines()[-1:] or "no output"))
+    line = json.loads(lines[-1])
+    keep = ("metric", "value", "unit", "ms_per_step", "steps", "warmup", "lengths", "target_tokens_per_step",
+            "source_tokens_per_step", "padded_positions_per_step", "source_plus_target_tokens_per_sec", "e2e", "clocks")
+    return {k: line[k] for k in keep if k in line}
+
+
 RUNNERS = {"rnn_decode": run_rnn_decode, "transformer": run_transformer, "beam": run_beam,
-           "captioning": run_captioning}
+           "captioning": run_captioning, "ende_realistic": run_ende_realistic}
 
 if __name__ == "__main__":
     for name in ([a for a in sys.argv[1:] if not a.startswith("--")] or list(RUNNERS)):

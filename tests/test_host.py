@@ -535,3 +535,22 @@ def test_dropout_helper_as_the_reference_unit_test():
         assert float(dropped.max()) == pytest.approx(1.0 / kprob)
     assert float(dropout(var, 0.1, False).sum()) == 10000
     assert dropout(var, 1.0, True) is var
+
+
+def test_bench_realistic_length_batches_are_well_formed():
+    """`bench.py --lengths realistic`: lengths ~ N(0.6 T, 0.2 T) clipped to [1, T], rows are
+    tokens, (target: </s>,) padding; one full-length sentence keeps the padded shape fixed; the fixed-length batches
+    of the headline are what they were (same generator draws)."""
+    import bench
+    src, tgt = bench.synthetic_batch(256, 5, realistic=True)
+    fixed_src, fixed_tgt = bench.synthetic_batch(256, 5)
+    assert src.shape == fixed_src.shape == (256, 50) and tgt.shape == (256, 50)
+    assert bool((fixed_src >= 4).all()) and bool((fixed_tgt[:, :-1] >= 4).all()) and bool((fixed_tgt[:, -1] == 2).all())
+    src_len, tgt_len = (src != 0).sum(1), (tgt != 0).sum(1)
+    assert int(src_len[0]) == 50 and int(tgt_len[0]) == 50 and int(src_len.min()) >= 1 and int(tgt_len.min()) >= 1
+    assert 25 < float(src_len.float().mean()) < 35 and 25 < float(tgt_len.float().mean()) < 35
+    for b in range(256):
+        n, m = int(src_len[b]), int(tgt_len[b])
+        assert bool((src[b, :n] >= 4).all()) and bool((src[b, n:] == 0).all())
+        assert bool((tgt[b, :m - 1] >= 4).all()) and int(tgt[b, m - 1]) == 2 and bool((tgt[b, m:] == 0).all())
+        assert bool((src[b, :n] == fixed_src[b, :n]).all())       # the same ids, cut
