@@ -488,7 +488,7 @@ def run_ende_realistic(cpu=True, steps=10, warmup=3):
            str(warmup), "--lengths", "realistic", "--no-extras", "--no-cpu-baseline"]
     env = {k: v for k, v in os.environ.items()
            if k not in ("RANK", "LOCAL_RANK", "WORLD_SIZE", "MASTER_ADDR", "MASTER_PORT")}
-    res = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=root, env=env)
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=420, cwd=root, env=env)
     lines = [l for l in res.stdout.splitlines() if l.startswith("{")]
     if res.returncode != 0 or not lines:
         raise RuntimeError("bench.py --lengths realistic exited with {}: {}".format(
@@ -515,7 +515,7 @@ def run_late_gpu_checks(cpu=True):
     env = {k: v for k, v in os.environ.items()
            if k not in ("RANK", "LOCAL_RANK", "WORLD_SIZE", "MASTER_ADDR", "MASTER_PORT")}
     env["NMB200_RUN_UNRUN_GPU_TESTS"] = "1"
-    res = subprocess.run(cmd, capture_output=True, text=True, timeout=900, cwd=root, env=env)
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=420, cwd=root, env=env)
     tail = [l for l in res.stdout.strip().splitlines() if l.strip()]
     summary = tail[-1] if tail else ""
     counts = {word: int(num) for num, word in re.findall(r"(\d+) (passed|failed|error|errors|skipped)", summary)}
