@@ -9,6 +9,7 @@ with no device->host synchronisation inside; the losses are returned as device t
 """
 import math
 import re
+from collections.abc import Mapping
 from typing import Any, Dict, List, Optional, Sequence, Set
 
 import torch
@@ -525,9 +526,42 @@ class _TrainExecutable:
     def execute(self) -> None:
         out = self.trainer.train_step()
         names = [obj.name for obj in self.trainer.objectives] + ["L1", "L2"]
-        vals = [float(l) for l in out["losses"]]
-        l1l2 = out["l1l2"]
-        vals += [float(l1l2[0]), float(l1l2[1])] if l1l2 is not None else [0.0, 0.0]
-        self.result = ExecutionResult(outputs={}, losses=dict(zip(names, vals)),
+        self.result = ExecutionResult(outputs={}, losses=_DeferredLosses(names, out["losses"], out["l1l2"]),
                                       size=self.trainer.objectives[0].decoder.batch_size,
                                       summaries=[])
+
+
+class _DeferredLosses(Mapping):
+    """{objective name: value, "L1": ..., "L2": ...} of one training step, read from the device when somebody
+    LOOKS at it.  A step is issued asynchronously; converting its loss to a Python float right away would make the
+    host wait for the device after every step, although the training loop only looks at the losses of the steps it
+    logs (learning_utils.py) - so the host would prepare batch i+1 (padding, string -> index, upload) only after
+    step i had finished instead of while it runs.  The tensors kept here are the step's own results (a replayed
+    graph's loss is divided out of the statistic slots into a fresh tensor), so later steps do not change them."""
+
+    def __init__(self, names, losses, l1l2) -> None:
+        self._names = list(names)
+        # the regularisation sums live in one buffer every step overwrites: keep this step's copy
+        self._pending = (list(losses), l1l2.clone() if l1l2 is not None else None)
+        self._values = None
+
+    def _resolved(self):
+        if self._values is None:
+            losses, l1l2 = self._pending
+            vals = [float(l) for l in losses]
+            vals += [float(l1l2[0]), float(l1l2[1])] if l1l2 is not None else [0.0, 0.0]
+            self._values = dict(zip(self._names, vals))
+            self._pending = None
+        return self._values
+
+    def __getitem__(self, key):
+        return self._resolved()[key]
+
+    def __iter__(self):
+        return iter(self._names)
+
+    def __len__(self) -> int:
+        return len(self._names)
+
+    def __repr__(self) -> str:
+        return repr(self._resolved())

@@ -1685,3 +1685,33 @@ def test_scaled_dot_attention_objects_against_the_reference_run(cpu_model, tag, 
         assert max_abs(mha.histories["{}_run_head{}".format(dname, i)], g("run_mha_head{}".format(i))) < 1e-5
     assert max_abs(sdp.histories[dname + "_run_head0"], g("run_sdp_head0")) < 1e-5
     assert sorted(list(mha.histories) + list(sdp.histories)) == sorted(golden[pre + "history_keys"].tolist())
+
+
+def test_training_losses_are_read_when_somebody_looks(cpu_model, monkeypatch):
+    """The executable of a trainer hands out its losses as a mapping that converts the device values on first
+    access (so the training loop does not wait for the device after every step); what it then shows is THAT
+    step's loss and regularisation sums, whatever ran since."""
+    from neuralmonkey_b200.learning_utils import evaluation, join_execution_results
+    from neuralmonkey_b200.trainers.generic_trainer import GenericTrainer
+    monkeypatch.setattr(GenericTrainer, "_adam_kernel", cpu_ops.adam_kernel)
+    model = build_bahdanau(**TOY, l2=1e-3, lr=1e-2)
+    model["arena"].load_dict(oracle_params_for(model))
+    src, tgt = random_batch(6, 8, 7, TOY["vs"], TOY["vt"], seed=3)
+    results, eager = [], []
+    for _ in range(3):
+        feed(model, src, tgt, train=True)
+        executable = model["trainer"].get_executable()
+        executable.execute()
+        results.append(executable.result)
+        eager.append((float(model["dec"].train_loss), float(model["trainer"]._l1l2[1])))
+    assert all(r.losses._values is None for r in results)            # nothing was converted yet
+    name = model["trainer"].objectives[0].name
+    for result, (loss, l2) in zip(results, eager):
+        assert list(result.losses) == [name, "L1", "L2"] and len(result.losses) == 3
+        assert result.losses[name] == pytest.approx(loss, rel=1e-6)
+        assert result.losses["L2"] == pytest.approx(l2, rel=1e-6)     # this step's sum, not the last step's
+    assert eager[0][1] != eager[2][1] and eager[0][0] > eager[2][0]
+    joined = join_execution_results(results)
+    assert joined.losses[name] == pytest.approx(sum(l for l, _ in eager) / 3, rel=1e-6)
+    assert evaluation([], {}, results[:1], {})[name] == pytest.approx(eager[0][0], rel=1e-6)
+    assert dict(results[0].losses) == results[0].losses._values
