@@ -502,7 +502,9 @@ def run_ende_realistic(cpu=True, steps=10, warmup=3):
 def run_late_gpu_checks(cpu=True):
     """Not a workload: the GPU parity tests that were written after the round's GPU budget was spent and are
     therefore opt-in in the test suite (tests/test_gpu_zz_attention_objects.py: an RNN decoder with scaled-dot
-    attention objects against the oracle, exact and tensor-core engines) are run here, in a process of their own,
+    attention objects against the oracle, exact and tensor-core engines, two optimizers, the sampling loop;
+    tests/test_gpu_zz_reference_inis_late.py: the reference's factored / post-edit / language-model INIs unchanged)
+    are run here, in a process of their own,
     and their outcome is RECORDED - passed / failed counts and the failing lines - so that the first GPU box that
     sees this code says whether they hold.  Nothing here can fail the bench or the suite."""
     import os
@@ -510,12 +512,12 @@ def run_late_gpu_checks(cpu=True):
     import subprocess
     del cpu
     root = os.path.dirname(os.path.abspath(__file__))
-    cmd = [sys.executable, "-m", "pytest", "tests/test_gpu_zz_attention_objects.py", "-q", "-m", "gpu",
-           "-p", "no:cacheprovider", "--tb=line"]
+    cmd = [sys.executable, "-m", "pytest", "tests/test_gpu_zz_attention_objects.py",
+           "tests/test_gpu_zz_reference_inis_late.py", "-q", "-m", "gpu", "-p", "no:cacheprovider", "--tb=line"]
     env = {k: v for k, v in os.environ.items()
            if k not in ("RANK", "LOCAL_RANK", "WORLD_SIZE", "MASTER_ADDR", "MASTER_PORT")}
     env["NMB200_RUN_UNRUN_GPU_TESTS"] = "1"
-    res = subprocess.run(cmd, capture_output=True, text=True, timeout=420, cwd=root, env=env)
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=root, env=env)
     tail = [l for l in res.stdout.strip().splitlines() if l.strip()]
     summary = tail[-1] if tail else ""
     counts = {word: int(num) for num, word in re.findall(r"(\d+) (passed|failed|error|errors|skipped)", summary)}
