@@ -140,8 +140,9 @@ def test_bench_reference_arm_prints_the_contract_line():
     import subprocess
     import sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    res = subprocess.run([sys.executable, "bench.py", "--impl", "reference", "--steps", "1", "--warmup", "0"],
-                         capture_output=True, text=True, timeout=600, cwd=root)
+    # 16 sentences per step instead of the whole 256-sentence batch: the line's shape is what is checked here
+    res = subprocess.run([sys.executable, "bench.py", "--impl", "reference", "--steps", "1", "--warmup", "0",
+                          "--batch", "16"], capture_output=True, text=True, timeout=600, cwd=root)
     assert res.returncode == 0, res.stderr[-2000:]
     lines = [l for l in res.stdout.splitlines() if l.strip()]
     assert len(lines) == 1, res.stdout
@@ -150,6 +151,8 @@ def test_bench_reference_arm_prints_the_contract_line():
                 "scaling", "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
         assert key in line, key
     assert line["impl"] == "reference" and line["value"] > 0 and "workload" in line["config"]
+    assert line["config"]["per_gpu_batch"] == 16 and line["cpu_sample_sentences_per_step"] == 16
+    assert line["cpu_baseline"]["value_with_4_threads"] > 0
     assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["value"] == line["value"]
     assert line["e2e"]["value"] == line["value"] and line["e2e"]["h2d_bytes_per_step"] == 0
     assert line["e2e"]["d2h_bytes_per_step"] == 0
