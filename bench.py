@@ -159,12 +159,14 @@ def cpu_ende_train(n_sent, steps, warmup, seed=SEED):
     per_step = sum(times) / len(times)
     # the INIs all say num_threads=4 (tests/bahdanau.ini:23, examples/translation.ini:46) - one
     # more step at that setting, reported next to the headline CPU figure
-    if threads != 4 and cores >= 4:
+    if threads == 4:
+        FOUR_THREADS["tokens_per_sec"] = n_sent * ENDE["ty"] / per_step
+    elif cores >= 4 and per_step * threads / 4 < 60.0:      # bounded: skipped where it would take minutes
         torch.set_num_threads(4)
         FOUR_THREADS["tokens_per_sec"] = n_sent * ENDE["ty"] / one()
         torch.set_num_threads(threads)
     else:
-        FOUR_THREADS["tokens_per_sec"] = n_sent * ENDE["ty"] / per_step
+        FOUR_THREADS["tokens_per_sec"] = None
     return n_sent * ENDE["ty"] / per_step, per_step, threads
 
 
