@@ -13,7 +13,7 @@ Variants (see nn/variants.py; GPU-verified by tests/test_gpu_
 or `rnn_cell="NematusGRU"` the context feeds the recurrence, so training steps through time with the
 same `_variant_step` the runtime uses (teacher-forced inputs), one set of T = 1 launches per step.
 """
-from typing import Any, List, NamedTuple, Optional, Tuple
+from typing import Any, List, NamedTuple, Tuple
 
 import torch
 

@@ -13,7 +13,7 @@ buffer) and swaps in that session's cache of per-batch tensors, so the model par
 parameters.  Only runners support several sessions, as in the reference.
 """
 import os
-from typing import Any, List, Optional, Set, Union
+from typing import List, Optional, Set, Union
 
 import numpy as np
 import torch

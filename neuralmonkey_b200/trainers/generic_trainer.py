@@ -10,7 +10,7 @@ with no device->host synchronisation inside; the losses are returned as device t
 import math
 import re
 from collections.abc import Mapping
-from typing import Any, Dict, List, Optional, Sequence, Set
+from typing import Any, Dict, List, Optional, Sequence
 
 import torch
 
