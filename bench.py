@@ -59,7 +59,7 @@ def parse_args():
                     help="issue every kernel of a step from Python instead of replaying the captured step")
     ap.add_argument("--no-extras", action="store_true",
                     help="skip the secondary workloads (RNN decoding / transformer / beam-8 / captioning) at N=1")
-    ap.add_argument("--extras", default="rnn_decode,transformer,beam,captioning,ende_realistic,late_gpu_checks")
+    ap.add_argument("--extras", default="rnn_decode,transformer,beam,captioning,ende_realistic,ini_loop,late_gpu_checks")
     ap.add_argument("--no-dropout", action="store_true", help="transformer workload: keep_prob 1.0")
     ap.add_argument("--lengths", default="fixed", choices=["fixed", "realistic"],
                     help="en-de workload at N=1: 'realistic' draws sentence lengths from a clipped N(0.6 T, 0.2 T) "

@@ -12,6 +12,8 @@ configuration builder) and to the same contract: every workload carries its own 
   captioning  : tests/captioning.ini - frozen VGG-16 conv stack on 224x224 images + Bahdanau decoder; images/s
   ende_realistic : the headline en-de workload with sentence lengths ~ N(0.6 T, 0.2 T), in a
                 process of its own
+  ini_loop    : `neuralmonkey-train` itself on text files at the en-de bench shape (tools/ini_loop_bench.py), in
+                processes of its own
 
 Usage: python bench_workloads.py [rnn_decode|transformer|beam|captioning] ...   (one JSON line each)
 """
@@ -499,6 +501,31 @@ def run_ende_realistic(cpu=True, steps=10, warmup=3):
     return {k: line[k] for k in keep if k in line}
 
 
+def run_ini_loop(cpu=True):
+    """`neuralmonkey-train` itself on text files (tools/ini_loop_bench.py): the en-de model at the bench shape fed
+    from a synthetic corpus on disk through the package's own training loop - dataset iteration, padding,
+    string -> index, pinned upload, captured step.  Two runs in processes of their own: with the losses read when
+    somebody looks at them (the default since the CPU-only part of round 2: never, in this run) and with every
+    step's loss read right away (the behaviour before).  Never run on a GPU before the round-end bench."""
+    import os
+    import subprocess
+    del cpu
+    root = os.path.dirname(os.path.abspath(__file__))
+    out = {}
+    for label, eager in (("deferred_loss_read", "0"), ("loss_read_every_step", "1")):
+        env = {k: v for k, v in os.environ.items()
+               if k not in ("RANK", "LOCAL_RANK", "WORLD_SIZE", "MASTER_ADDR", "MASTER_PORT")}
+        env["NMB200_INI_LOOP_EAGER_LOSS"] = eager
+        res = subprocess.run([sys.executable, os.path.join(root, "tools", "ini_loop_bench.py")],
+                             capture_output=True, text=True, timeout=420, cwd=root, env=env)
+        lines = [l for l in res.stdout.splitlines() if l.startswith("{")]
+        if res.returncode != 0 or not lines:
+            out[label] = {"error": "exit {}: {}".format(res.returncode, res.stderr.strip().splitlines()[-1:])}
+        else:
+            out[label] = json.loads(lines[-1])
+    return out
+
+
 def run_late_gpu_checks(cpu=True):
     """Not a workload: the GPU parity tests that were written after the round's GPU budget was spent and are
     therefore opt-in in the test suite (tests/test_gpu_zz_attention_objects.py: an RNN decoder with scaled-dot
@@ -530,7 +557,7 @@ def run_late_gpu_checks(cpu=True):
 
 
 RUNNERS = {"rnn_decode": run_rnn_decode, "transformer": run_transformer, "beam": run_beam,
-           "captioning": run_captioning, "ende_realistic": run_ende_realistic,
+           "captioning": run_captioning, "ende_realistic": run_ende_realistic, "ini_loop": run_ini_loop,
            "late_gpu_checks": run_late_gpu_checks}
 
 if __name__ == "__main__":

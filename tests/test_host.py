@@ -557,3 +557,20 @@ def test_bench_realistic_length_batches_are_well_formed():
         assert bool((src[b, :n] >= 4).all()) and bool((src[b, n:] == 0).all())
         assert bool((tgt[b, :m - 1] >= 4).all()) and int(tgt[b, m - 1]) == 2 and bool((tgt[b, m:] == 0).all())
         assert bool((src[b, :n] == fixed_src[b, :n]).all())       # the same ids, cut
+
+
+def test_ini_loop_bench_tool_over_the_stand_in_operations():
+    """tools/ini_loop_bench.py (`neuralmonkey-train` on a synthetic corpus on disk, timed from inside the loop):
+    its host logic over the CPU stand-ins at toy dims - one JSON line on stdout, the step / token bookkeeping."""
+    import json
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    res = subprocess.run([sys.executable, os.path.join(root, "tools", "ini_loop_bench.py"), "--standins", "--rnn", "16",
+                          "--vocab", "300", "--sentences", "160", "--batch", "16", "--skip", "3"],
+                         capture_output=True, text=True, timeout=600, cwd=root)
+    assert res.returncode == 0, res.stderr[-2000:]
+    lines = [l for l in res.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1, res.stdout
+    line = json.loads(lines[0])
+    assert line["steps"] == 7 and line["value"] > 0 and line["unit"] == "tokens/s"
+    assert line["value"] == pytest.approx(7 * 16 * 50 / (line["ms_per_step"] * 7 * 1e-3), rel=1e-6)
+    assert "Training finished" in res.stderr
