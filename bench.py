@@ -536,12 +536,15 @@ def run_b200(args):
         del model
         torch.cuda.empty_cache()
         for name in [n for n in args.extras.split(",") if n]:
+            t_extra = time.perf_counter()
             try:
                 extras[name] = bench_workloads.RUNNERS[name](cpu=not args.no_cpu_baseline)
             except Exception as exc:  # pylint: disable=broad-except
                 import traceback
                 traceback.print_exc()
                 extras[name] = {"error": "{}: {}".format(type(exc).__name__, exc)}
+            if isinstance(extras[name], dict):
+                extras[name]["wall_s"] = round(time.perf_counter() - t_extra, 1)
             torch.cuda.empty_cache()
 
     h2d = 2 * batch * (tx + ty) * 8  # int64 ids: encoder ids, decoder targets + fed symbols
